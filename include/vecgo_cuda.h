@@ -1,0 +1,221 @@
+/*
+ * vecgo_cuda.h — C ABI of libvecgo_cuda.so: the B200 (sm_100a) replacement for
+ * vecgo's vector-scan hot path.
+ *
+ * This is the boundary a cgo shim binds (INTEGRATION.md shows the Go side).
+ * Plain pointers and sizes only; no C++/torch types.  Every entry point
+ * returns VG_OK (0) or a negative vg_status; vg_last_error() returns the
+ * thread-local message of the last failure on the calling thread.  Nothing
+ * here ever falls back to the CPU: without a CUDA device every compute call
+ * fails with VG_ERR_CUDA.
+ *
+ * Pointer naming: `h_` = host memory owned by the caller for the duration of
+ * the call only (cgo rule: never retained); `d_` = device memory (e.g. a
+ * torch tensor's data_ptr, or memory from vg_dev_alloc).  Handles are opaque.
+ *
+ * Reference interfaces replaced (paths relative to hupe1980/vecgo):
+ *   internal/simd/kernels.go:39-123        kernel table  -> vg_simd_*
+ *   distance/distance.go:13-53             Dot/SquaredL2/NormalizeL2InPlace
+ *   internal/quantization/quantizer.go:12-24 Quantizer   -> vg_sq8_*, vg_int4_*, vg_bq_*, vg_rabitq_*, vg_pq_*
+ *   internal/kmeans/kmeans.go:16,142,217   k-means       -> vg_kmeans_*
+ *   internal/segment/segment.go:77-95      Segment.Search/Rerank -> vg_index_search / vg_index_rerank
+ *   internal/segment/flat/segment.go:105   flat.Open     -> vg_flat_open
+ *   internal/searcher/candidate_queue.go   top-k order   -> result order of every search, vg_topk_merge
+ */
+#ifndef VECGO_CUDA_H
+#define VECGO_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+typedef int32_t vg_status;
+enum {
+    VG_OK = 0,
+    VG_ERR_INVALID = -1,   /* bad argument / dimension mismatch (Go: errors.New("dimension mismatch")) */
+    VG_ERR_CUDA = -2,      /* CUDA runtime failure, no device, out of memory */
+    VG_ERR_STATE = -3,     /* quantizer not trained / handle closed */
+    VG_ERR_FORMAT = -4,    /* flat segment file: bad magic/version/short file/checksum */
+    VG_ERR_UNSUPPORTED = -5
+};
+
+/* distance.Metric — distance/distance.go:68-73 */
+enum { VG_METRIC_L2 = 0, VG_METRIC_COSINE = 1, VG_METRIC_DOT = 2, VG_METRIC_HAMMING = 3 };
+
+/* Scan codecs.  Values 0..6 follow quantization.Type (internal/quantization/types.go:6-14). */
+enum {
+    VG_CODEC_F32 = 0,    /* QuantizationNone: exact float32 rows */
+    VG_CODEC_PQ = 1,     /* ProductQuantizer ADC (int8 codebooks, K=256) */
+    VG_CODEC_OPQ = 2,    /* rotation + PQ */
+    VG_CODEC_SQ8 = 3,    /* ScalarQuantizer, L2 via Sq8uL2BatchPerDimension */
+    VG_CODEC_BQ = 4,     /* BinaryQuantizer, Hamming score */
+    VG_CODEC_RABITQ = 5, /* RaBitQuantizer estimator */
+    VG_CODEC_INT4 = 6    /* Int4Quantizer */
+};
+
+typedef uint64_t vg_index_t; /* device-resident scan index (one segment / one shard) */
+
+/* ---------------------------------------------------------------- runtime */
+const char *vg_last_error(void);
+const char *vg_version(void);
+vg_status vg_device_count(int32_t *count);
+/* Binds the calling thread (and the library's streams) to `device`. */
+vg_status vg_init(int32_t device);
+vg_status vg_synchronize(void);
+vg_status vg_dev_alloc(void **d_ptr, size_t bytes);
+vg_status vg_dev_free(void *d_ptr);
+vg_status vg_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes);
+vg_status vg_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes);
+/* Number of kernels this library has launched since load (for gpu_launches). */
+uint64_t vg_launch_count(void);
+/* Run subsequent kernels on this CUDA stream (cudaStream_t as integer; 0 = library default). */
+vg_status vg_set_stream(uint64_t cuda_stream);
+
+/* ------------------------------------------------ simd kernel-table mirrors
+ * Batch forms of internal/simd/kernels.go:39-123 — host in, host out, full
+ * distance vectors/matrices (no top-k).  Arithmetic = the AVX-512 kernels
+ * (internal/simd/src/*_avx512.c), bit for bit.
+ * out is row-major [nq x n]. */
+vg_status vg_simd_dot(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, float *h_out);          /* simd.Dot per pair */
+vg_status vg_simd_squared_l2(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, float *h_out);   /* simd.SquaredL2 per pair */
+vg_status vg_simd_dot_batch(const float *h_queries, int64_t nq, const float *h_targets, int64_t n, int64_t dim, float *h_out);        /* simd.DotBatch */
+vg_status vg_simd_squared_l2_batch(const float *h_queries, int64_t nq, const float *h_targets, int64_t n, int64_t dim, float *h_out); /* simd.SquaredL2Batch */
+vg_status vg_simd_sq8u_l2_batch(const float *h_queries, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t dim,
+                                const float *h_mins, const float *h_inv_scales, float *h_out);                   /* simd.Sq8uL2BatchPerDimension */
+vg_status vg_simd_int4_l2_batch(const float *h_queries, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t dim,
+                                const float *h_min, const float *h_diff, float *h_out);                          /* simd.Int4L2DistanceBatch */
+vg_status vg_simd_pq_adc_lookup(const float *h_tables, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t m, float *h_out); /* simd.PqAdcLookup; table [nq][m*256] */
+vg_status vg_simd_hamming(const uint8_t *h_queries, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t nbytes, int32_t *h_out); /* simd.Hamming */
+vg_status vg_simd_scale(float *h_a, int64_t n, float scalar);                                                    /* simd.ScaleInPlace */
+/* distance.NormalizeL2InPlace on each of n rows; h_ok[i]=0 for zero-norm rows (left untouched). */
+vg_status vg_normalize_l2(float *h_vecs, int64_t n, int64_t dim, uint8_t *h_ok);
+
+/* ------------------------------------------------------------- quantizers
+ * Batch Train/Encode/Decode of internal/quantization; parameter arrays are
+ * caller-owned host buffers, byte-compatible with the Go structs' fields. */
+/* ScalarQuantizer.Train (quantizer.go:130-180): mins,maxs,scales,inv_scales [dim] */
+vg_status vg_sq8_train(const float *h_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs, float *h_scales, float *h_inv_scales);
+/* ScalarQuantizer.SetBounds (quantizer.go:51-75) */
+vg_status vg_sq8_set_bounds(const float *h_mins, const float *h_maxs, int64_t dim, float *h_scales, float *h_inv_scales);
+vg_status vg_sq8_encode(const float *h_vecs, int64_t n, int64_t dim, const float *h_mins, const float *h_maxs, const float *h_scales, uint8_t *h_codes);
+vg_status vg_sq8_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_mins, const float *h_inv_scales, float *h_vecs);
+/* Int4Quantizer (int4.go:29-132): min,diff [dim]; codes [n][(dim+1)/2] */
+vg_status vg_int4_train(const float *h_vecs, int64_t n, int64_t dim, float *h_min, float *h_diff);
+vg_status vg_int4_encode(const float *h_vecs, int64_t n, int64_t dim, const float *h_min, const float *h_diff, uint8_t *h_codes);
+vg_status vg_int4_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_min, const float *h_diff, float *h_vecs);
+/* BinaryQuantizer (binary.go:59-154): threshold = float32(mean in float64); codes [n][ceil(dim/64)*8] */
+vg_status vg_bq_train(const float *h_vecs, int64_t n, int64_t dim, float *h_threshold);
+vg_status vg_bq_encode(const float *h_vecs, int64_t n, int64_t dim, float threshold, uint8_t *h_codes);
+/* RaBitQuantizer.Encode (rabitq.go:51-78): codes [n][ceil(dim/64)*8 + 4] (sign bits ‖ f32 norm LE) */
+vg_status vg_rabitq_encode(const float *h_vecs, int64_t n, int64_t dim, uint8_t *h_codes);
+/* ProductQuantizer with given int8 codebooks [m][k][dim/m], scales[m], offsets[m] (pq.go:147-229,452-491) */
+vg_status vg_pq_encode(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_codebooks, const float *h_scales, const float *h_offsets, uint8_t *h_codes);
+vg_status vg_pq_decode(const uint8_t *h_codes, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_codebooks, const float *h_scales, const float *h_offsets, float *h_vecs);
+vg_status vg_pq_build_distance_table(const float *h_queries, int64_t nq, int64_t dim, int64_t m, int64_t k, const int8_t *h_codebooks, const float *h_scales, const float *h_offsets, float *h_tables /* [nq][m*k] */);
+/* ProductQuantizer.Train (pq.go:68-143,275-433): k-means++ (seeded) + `iters` Lloyd
+ * iterations per subspace, then int8 codebook quantisation. */
+vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
+                      int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32 /* optional [m][k][dim/m] */);
+
+/* ----------------------------------------------------------------- k-means
+ * internal/kmeans/kmeans.go. */
+vg_status vg_kmeans_train(const float *h_vecs, int64_t n, int64_t dim, int64_t k, int32_t metric, int64_t max_iter,
+                          const int64_t *h_init_rows /* [k] = Go's rand.Perm(n)[:k] */, uint64_t seed,
+                          float *h_centroids, int32_t *h_assign /* optional [n] */, int64_t *iters_run);
+vg_status vg_kmeans_assign(const float *h_vecs, int64_t n, int64_t dim, const float *h_centroids, int64_t k, int32_t metric, int32_t *h_assign); /* AssignPartition per row */
+vg_status vg_kmeans_find_closest(const float *h_queries, int64_t nq, int64_t dim, const float *h_centroids, int64_t k, int64_t nprobe, int32_t metric, int32_t *h_out /* [nq][min(nprobe,k)] */);
+
+/* ------------------------------------------------------- device scan index
+ * One immutable, device-resident code matrix (a flat segment, or one row
+ * shard of it).  Search semantics = flat.(*Segment).Search
+ * (internal/segment/flat/segment.go:447-752): the k best rows under the
+ * CandidateHeap order (score asc for L2 / desc otherwise, then row asc),
+ * returned best-first.  Row ids returned are row_base + local row. */
+typedef struct {
+    int32_t codec;        /* VG_CODEC_* */
+    int32_t metric;       /* VG_METRIC_* (ordering: L2 ascending, others descending) */
+    int64_t dim;
+    int64_t rows;
+    uint32_t segment_id;
+    uint32_t reserved;
+    uint64_t row_base;    /* global id of local row 0 (row sharding) */
+    /* codec parameters (host pointers, copied) */
+    const float *sq8_mins, *sq8_inv_scales;          /* [dim] */
+    const float *int4_min, *int4_diff;               /* [dim] */
+    int64_t pq_m, pq_k;
+    const int8_t *pq_codebooks;                      /* [m][k][dim/m] */
+    const float *pq_scales, *pq_offsets;             /* [m] */
+    const float *opq_rotation;                       /* optional [blocks][bs][bs] row-major */
+    int64_t opq_block;
+    float bq_threshold;                              /* BinaryQuantizer.threshold (queries are sign-coded with it) */
+    uint32_t reserved2;
+    /* IVF partitions (flat format): rows are partition-ordered */
+    int64_t num_partitions;
+    const float *centroids;                          /* [P][dim] */
+    const uint32_t *partition_offsets;               /* [P+1] */
+} vg_index_desc;
+
+vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out);
+/* Upload rows [row0,row0+n) of codes and/or float vectors from host memory
+ * (e.g. the mmap'd segment) through the pinned staging ring.  Either may be
+ * NULL.  Code row sizes: F32 none; SQ8 dim; INT4 (dim+1)/2; PQ m; BQ
+ * ceil(dim/64)*8; RaBitQ ceil(dim/64)*8+4. */
+vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h_codes, const float *h_vectors);
+/* Fill rows from device memory instead (d_codes / d_vectors already resident). */
+vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const void *d_codes, const float *d_vectors);
+vg_status vg_index_close(vg_index_t idx);
+vg_status vg_index_info(vg_index_t idx, int64_t *rows, int64_t *dim, int64_t *code_bytes_per_row, int64_t *device_bytes);
+
+/* Batched Segment.Search.  h_row_mask: optional bitmap (bit r set = row r
+ * allowed; segment.Filter.AsBitmap), ceil(rows/8) bytes.  nprobes as
+ * model.SearchOptions.NProbes (only used when num_partitions > 1).
+ * Outputs are [nq][k]; rows beyond out_counts[q] are 0xFFFFFFFF / NaN. */
+vg_status vg_index_search(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes,
+                          const uint8_t *h_row_mask, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+/* Same with device-resident queries and outputs (no host copies; stream-ordered). */
+vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                              const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
+/* Batched Segment.Rerank (flat/segment.go:754-781): exact SquaredL2/Dot of each
+ * query against its r candidate rows (local row ids); rows >= RowCount give NaN. */
+vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores);
+vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, float *d_scores);
+/* Approximate scan to top-r, exact rerank, final top-k (engine refine path,
+ * internal/engine/search.go:188-192,913-973), all on device. */
+vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t nq, int64_t r, int64_t k,
+                                 uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+
+/* flat.Open (internal/segment/flat/segment.go:105-342) on the raw file bytes:
+ * header decode, optional CRC32C verify, section views, staging to HBM. */
+vg_status vg_flat_open(const uint8_t *h_file, size_t len, int32_t verify_checksum, vg_index_t *out);
+/* Header fields of an opened flat segment (format.go:28-51). */
+typedef struct {
+    uint64_t segment_id;
+    uint32_t row_count, dim, metric, num_partitions, quantization_type, checksum;
+} vg_flat_header;
+vg_status vg_flat_decode_header(const uint8_t *h_file, size_t len, vg_flat_header *out);
+/* model.ID column of the segment for the given local rows (FetchIDs). */
+vg_status vg_index_fetch_ids(vg_index_t idx, const uint32_t *h_rows, int64_t n, uint64_t *h_ids);
+
+/* ---------------------------------------------------------- top-k merging
+ * Merge `lists` best-first candidate lists per query (per-shard results after
+ * the NCCL allgather, or per-segment heaps: engine/search.go:903-908) into the
+ * k best under the CandidateHeap order.  Layout [lists][nq][k_in]; entries
+ * with row 0xFFFFFFFF are empty. */
+vg_status vg_topk_merge_dev(const uint32_t *d_rows, const float *d_scores, int64_t lists, int64_t nq, int64_t k_in,
+                            int32_t descending, int64_t k_out, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
+vg_status vg_topk_merge(const uint32_t *h_rows, const float *h_scores, int64_t lists, int64_t nq, int64_t k_in,
+                        int32_t descending, int64_t k_out, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* VECGO_CUDA_H */

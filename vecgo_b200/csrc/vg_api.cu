@@ -1,0 +1,1253 @@
+// vg_api.cu — the C ABI (include/vecgo_cuda.h): runtime, pinned staging,
+// device-resident scan indexes, flat-segment opening, simd/quantizer mirrors.
+// Host-side logic mirrors the Go callers it replaces; all arithmetic that
+// decides a result runs in the CUDA kernels of vg_scan.cu / vg_quant.cu /
+// vg_kmeans.cu.  There is no CPU compute path in this file.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "vg_kmeans.cuh"
+#include "vg_quant.cuh"
+#include "vg_scan.cuh"
+
+namespace vg {
+
+// ------------------------------------------------------------------ runtime
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+static cudaStream_t g_stream = nullptr;       // library stream (created by vg_init)
+static cudaStream_t g_user_stream = nullptr;  // vg_set_stream override
+static bool g_user_stream_set = false;
+static int g_device = -1;
+static int g_sms = 0;
+static std::mutex g_mu;
+
+void set_error(const std::string &msg) { t_error = msg; }
+vg_status fail(vg_status code, const std::string &msg) {
+    t_error = msg;
+    return code;
+}
+vg_status cuda_fail(cudaError_t e, const char *what) {
+    t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what;
+    cudaGetLastError();
+    return VG_ERR_CUDA;
+}
+cudaStream_t stream() { return g_user_stream_set ? g_user_stream : g_stream; }
+int sm_count() { return g_sms > 0 ? g_sms : 148; }
+
+vg_status ensure_init() {
+    if (g_device >= 0) {
+        VG_CUDA(cudaSetDevice(g_device));
+        return VG_OK;
+    }
+    return vg_init(0);
+}
+
+vg_status DevBuf::alloc(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return cuda_fail(e, "cudaMalloc");
+    }
+    bytes = n;
+    return VG_OK;
+}
+void DevBuf::release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+}
+
+// Pinned staging ring: two 32 MiB page-locked buffers.  The CPU fills one
+// while the copy engine drains the other (mmap'd segment pages are pageable,
+// so this is where they become DMA-able).
+static const size_t kStageBytes = 32u << 20;
+static void *g_stage[2] = {nullptr, nullptr};
+static cudaEvent_t g_stage_ev[2];
+static std::mutex g_stage_mu;
+
+static vg_status ensure_stage() {
+    if (g_stage[0]) return VG_OK;
+    for (int i = 0; i < 2; i++) {
+        VG_CUDA(cudaHostAlloc(&g_stage[i], kStageBytes, cudaHostAllocDefault));
+        VG_CUDA(cudaEventCreateWithFlags(&g_stage_ev[i], cudaEventDisableTiming));
+    }
+    return VG_OK;
+}
+vg_status staged_h2d(void *d_dst, const void *h_src, size_t bytes) {
+    if (bytes == 0) return VG_OK;
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    VG_TRY(ensure_stage());
+    cudaStream_t st = stream();
+    size_t off = 0;
+    int i = 0;
+    while (off < bytes) {
+        const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+        VG_CUDA(cudaEventSynchronize(g_stage_ev[i]));
+        memcpy(g_stage[i], (const char *)h_src + off, n);
+        VG_CUDA(cudaMemcpyAsync((char *)d_dst + off, g_stage[i], n, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaEventRecord(g_stage_ev[i], st));
+        off += n;
+        i ^= 1;
+    }
+    VG_CUDA(cudaEventSynchronize(g_stage_ev[0]));
+    VG_CUDA(cudaEventSynchronize(g_stage_ev[1]));
+    return VG_OK;
+}
+vg_status staged_d2h(void *h_dst, const void *d_src, size_t bytes) {
+    if (bytes == 0) return VG_OK;
+    std::lock_guard<std::mutex> lk(g_stage_mu);
+    VG_TRY(ensure_stage());
+    cudaStream_t st = stream();
+    size_t off = 0;
+    while (off < bytes) {
+        const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
+        VG_CUDA(cudaMemcpyAsync(g_stage[0], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        memcpy((char *)h_dst + off, g_stage[0], n);
+        off += n;
+    }
+    return VG_OK;
+}
+
+// Upload helper: host array → fresh device buffer.
+template <class T>
+static vg_status to_device(DevBuf &buf, const T *h, size_t count) {
+    VG_TRY(buf.alloc(count * sizeof(T)));
+    return staged_h2d(buf.p, h, count * sizeof(T));
+}
+
+// ------------------------------------------------------------------ index
+struct Index {
+    vg_index_desc d{};
+    int variant = 0;
+    int64_t code_row_bytes = 0;      // host/file layout
+    int64_t dev_row_bytes = 0;       // device layout
+    DevBuf codes, vectors, p0, p1, norms, ids;
+    DevBuf pq_cb, pq_scales, pq_offsets, centroids, part_off, rotation;
+    std::vector<uint32_t> h_part_off;
+    int words32 = 0;
+    bool has_vectors = false, has_codes = false, has_ids = false;
+    size_t device_bytes() const {
+        return codes.bytes + vectors.bytes + p0.bytes + p1.bytes + norms.bytes + ids.bytes + pq_cb.bytes + centroids.bytes;
+    }
+};
+static std::unordered_map<uint64_t, Index *> g_indexes;
+static uint64_t g_next_handle = 1;
+
+static Index *lookup(vg_index_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_indexes.find(h);
+    return it == g_indexes.end() ? nullptr : it->second;
+}
+
+static int64_t host_code_bytes(const vg_index_desc &d) {
+    switch (d.codec) {
+        case VG_CODEC_SQ8: return d.dim;
+        case VG_CODEC_INT4: return (d.dim + 1) / 2;
+        case VG_CODEC_PQ:
+        case VG_CODEC_OPQ: return d.pq_m;
+        case VG_CODEC_BQ: return ((d.dim + 63) / 64) * 8;
+        case VG_CODEC_RABITQ: return ((d.dim + 63) / 64) * 8 + 4;
+        default: return 0;
+    }
+}
+
+static CodecParams params_of(const Index &ix) {
+    CodecParams cp;
+    cp.codec = ix.d.codec;
+    cp.variant = ix.variant;
+    cp.dim = ix.d.dim;
+    cp.row_bytes = ix.dev_row_bytes;
+    cp.codes = ix.codes.as<uint8_t>();
+    cp.vectors = ix.vectors.as<float>();
+    cp.p0 = ix.p0.as<float>();
+    cp.p1 = ix.p1.as<float>();
+    cp.pq_m = (int)ix.d.pq_m;
+    cp.pq_k = (int)ix.d.pq_k;
+    cp.pq_dsub = ix.d.pq_m > 0 ? (int)(ix.d.dim / ix.d.pq_m) : 0;
+    cp.pq_codebooks = ix.pq_cb.as<int8_t>();
+    cp.pq_scales = ix.pq_scales.as<float>();
+    cp.pq_offsets = ix.pq_offsets.as<float>();
+    cp.norms = ix.norms.as<float>();
+    cp.words32 = ix.words32;
+    return cp;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+// =================================================================== C ABI
+extern "C" {
+
+const char *vg_last_error(void) { return t_error.c_str(); }
+const char *vg_version(void) { return "vecgo_b200 0.1 (sm_100a)"; }
+uint64_t vg_launch_count(void) { return g_launches.load(); }
+
+vg_status vg_device_count(int32_t *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return cuda_fail(e, "cudaGetDeviceCount");
+    }
+    *count = n;
+    return VG_OK;
+}
+
+vg_status vg_init(int32_t device) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        if (e != cudaSuccess) cudaGetLastError();
+        return fail(VG_ERR_CUDA, "no CUDA device: libvecgo_cuda has no CPU path");
+    }
+    if (device < 0 || device >= n) return fail(VG_ERR_INVALID, "device ordinal out of range");
+    VG_CUDA(cudaSetDevice(device));
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_device != device) {
+        cudaDeviceProp prop;
+        VG_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) return fail(VG_ERR_CUDA, "libvecgo_cuda is built for sm_100a (Blackwell) only");
+        g_sms = prop.multiProcessorCount;
+        if (g_stream) {
+            cudaStreamDestroy(g_stream);
+            g_stream = nullptr;
+        }
+        VG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+        g_device = device;
+    }
+    return VG_OK;
+}
+vg_status vg_synchronize(void) {
+    VG_TRY(ensure_init());
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return VG_OK;
+}
+vg_status vg_set_stream(uint64_t cuda_stream) {
+    VG_TRY(ensure_init());
+    g_user_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    g_user_stream_set = cuda_stream != 0;
+    return VG_OK;
+}
+vg_status vg_dev_alloc(void **d_ptr, size_t bytes) {
+    VG_TRY(ensure_init());
+    VG_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return VG_OK;
+}
+vg_status vg_dev_free(void *d_ptr) {
+    if (d_ptr) VG_CUDA(cudaFree(d_ptr));
+    return VG_OK;
+}
+vg_status vg_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes) {
+    VG_TRY(ensure_init());
+    return staged_h2d(d_dst, h_src, bytes);
+}
+vg_status vg_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes) {
+    VG_TRY(ensure_init());
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_dst, d_src, bytes);
+}
+
+// ----------------------------------------------------------- index lifecycle
+vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
+    VG_TRY(ensure_init());
+    if (!desc || !out) return fail(VG_ERR_INVALID, "null argument");
+    const vg_index_desc &d = *desc;
+    if (d.dim <= 0 || d.rows < 0) return fail(VG_ERR_INVALID, "dim must be positive and rows non-negative");
+    if (d.rows > 0xFFFFFFFEll) return fail(VG_ERR_INVALID, "rows exceed uint32 RowID space");
+    std::unique_ptr<Index> ix(new Index());
+    ix->d = d;
+    ix->code_row_bytes = host_code_bytes(d);
+    ix->dev_row_bytes = ix->code_row_bytes;
+    const int64_t rows = d.rows > 0 ? d.rows : 1;
+    switch (d.codec) {
+        case VG_CODEC_F32:
+            break;
+        case VG_CODEC_SQ8:
+            if (!d.sq8_mins || !d.sq8_inv_scales) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
+            VG_TRY(to_device(ix->p0, d.sq8_mins, (size_t)d.dim));
+            VG_TRY(to_device(ix->p1, d.sq8_inv_scales, (size_t)d.dim));
+            if (d.metric != VG_METRIC_L2) ix->variant = VG_VAR_GO_SCALAR;  // flat.Search: sq.DotProduct per row
+            else if (d.dim % 64 == 0) ix->variant = VG_VAR_PERM;
+            break;
+        case VG_CODEC_INT4:
+            if (!d.int4_min || !d.int4_diff) return fail(VG_ERR_STATE, "Int4Quantizer not trained");
+            VG_TRY(to_device(ix->p0, d.int4_min, (size_t)d.dim));
+            VG_TRY(to_device(ix->p1, d.int4_diff, (size_t)d.dim));
+            if (d.dim % 256 == 0) ix->variant = VG_VAR_PERM;
+            break;
+        case VG_CODEC_PQ:
+        case VG_CODEC_OPQ: {
+            if (!d.pq_codebooks || !d.pq_scales || !d.pq_offsets) return fail(VG_ERR_STATE, "ProductQuantizer not trained");
+            if (d.pq_m <= 0 || d.dim % d.pq_m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
+            if (d.pq_k <= 0 || d.pq_k > 256) return fail(VG_ERR_INVALID, "numCentroids must be in 1..256");
+            VG_TRY(to_device(ix->pq_cb, d.pq_codebooks, (size_t)(d.pq_m * d.pq_k * (d.dim / d.pq_m))));
+            VG_TRY(to_device(ix->pq_scales, d.pq_scales, (size_t)d.pq_m));
+            VG_TRY(to_device(ix->pq_offsets, d.pq_offsets, (size_t)d.pq_m));
+            if (d.codec == VG_CODEC_OPQ) {
+                if (!d.opq_rotation || d.opq_block <= 0 || d.dim % d.opq_block != 0)
+                    return fail(VG_ERR_INVALID, "OPQ needs block rotations with dim % block == 0");
+                VG_TRY(to_device(ix->rotation, d.opq_rotation, (size_t)(d.dim * d.opq_block)));
+            }
+            break;
+        }
+        case VG_CODEC_BQ:
+        case VG_CODEC_RABITQ: {
+            const int64_t nbytes = ((d.dim + 63) / 64) * 8;
+            ix->dev_row_bytes = (nbytes + 15) / 16 * 16;
+            ix->words32 = (int)(ix->dev_row_bytes / 4);
+            if (d.codec == VG_CODEC_RABITQ) VG_TRY(ix->norms.alloc((size_t)rows * 4));
+            break;
+        }
+        default:
+            return fail(VG_ERR_INVALID, "unknown codec");
+    }
+    if (ix->code_row_bytes > 0) VG_TRY(ix->codes.alloc((size_t)rows * ix->dev_row_bytes));
+    if (d.num_partitions > 1) {
+        if (!d.centroids || !d.partition_offsets) return fail(VG_ERR_INVALID, "partitioned index needs centroids and offsets");
+        VG_TRY(to_device(ix->centroids, d.centroids, (size_t)(d.num_partitions * d.dim)));
+        VG_TRY(to_device(ix->part_off, d.partition_offsets, (size_t)(d.num_partitions + 1)));
+        ix->h_part_off.assign(d.partition_offsets, d.partition_offsets + d.num_partitions + 1);
+    }
+    // the descriptor's host pointers are not retained
+    ix->d.sq8_mins = ix->d.sq8_inv_scales = ix->d.int4_min = ix->d.int4_diff = nullptr;
+    ix->d.pq_codebooks = nullptr;
+    ix->d.pq_scales = ix->d.pq_offsets = ix->d.opq_rotation = ix->d.centroids = nullptr;
+    ix->d.partition_offsets = nullptr;
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint64_t h = g_next_handle++;
+    g_indexes[h] = ix.release();
+    *out = h;
+    return VG_OK;
+}
+
+vg_status vg_index_close(vg_index_t idx) {
+    Index *ix = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_indexes.find(idx);
+        if (it == g_indexes.end()) return fail(VG_ERR_STATE, "unknown or closed index handle");
+        ix = it->second;
+        g_indexes.erase(it);
+    }
+    cudaStreamSynchronize(stream());
+    delete ix;
+    return VG_OK;
+}
+
+vg_status vg_index_info(vg_index_t idx, int64_t *rows, int64_t *dim, int64_t *code_bytes_per_row, int64_t *device_bytes) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (rows) *rows = ix->d.rows;
+    if (dim) *dim = ix->d.dim;
+    if (code_bytes_per_row) *code_bytes_per_row = ix->code_row_bytes;
+    if (device_bytes) *device_bytes = (int64_t)ix->device_bytes();
+    return VG_OK;
+}
+
+// Place rows [row0,row0+n) of codes (device source, host layout) into the index's device layout.
+static vg_status place_codes(Index *ix, int64_t row0, int64_t n, const uint8_t *d_src) {
+    cudaStream_t st = stream();
+    uint8_t *dst = ix->codes.as<uint8_t>() + row0 * ix->dev_row_bytes;
+    switch (ix->d.codec) {
+        case VG_CODEC_SQ8:
+            if (ix->variant & VG_VAR_PERM) return dev_permute_sq8(d_src, dst, n, ix->d.dim, ix->d.dim % 256 == 0 ? 16 : 4, st);
+            break;
+        case VG_CODEC_INT4:
+            if (ix->variant & VG_VAR_PERM) return dev_permute_int4(d_src, dst, n, ix->code_row_bytes, st);
+            break;
+        case VG_CODEC_BQ:
+            return dev_split_sign(d_src, n, ix->code_row_bytes, ix->code_row_bytes, ix->dev_row_bytes, dst, nullptr, st);
+        case VG_CODEC_RABITQ:
+            return dev_split_sign(d_src, n, ix->code_row_bytes - 4, ix->code_row_bytes, ix->dev_row_bytes, dst,
+                                  ix->norms.as<float>() + row0, st);
+        default:
+            break;
+    }
+    VG_CUDA(cudaMemcpyAsync(dst, d_src, (size_t)n * ix->code_row_bytes, cudaMemcpyDeviceToDevice, st));
+    return VG_OK;
+}
+
+static vg_status ensure_vectors(Index *ix) {
+    if (!ix->vectors.p) VG_TRY(ix->vectors.alloc((size_t)(ix->d.rows > 0 ? ix->d.rows : 1) * ix->d.dim * 4));
+    return VG_OK;
+}
+
+vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const void *d_codes, const float *d_vectors) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (row0 < 0 || n < 0 || row0 + n > ix->d.rows) return fail(VG_ERR_INVALID, "row range outside the index");
+    if (n == 0) return VG_OK;
+    if (d_codes) {
+        if (ix->code_row_bytes == 0) return fail(VG_ERR_INVALID, "this index has no code section");
+        VG_TRY(place_codes(ix, row0, n, (const uint8_t *)d_codes));
+        ix->has_codes = true;
+    }
+    if (d_vectors) {
+        VG_TRY(ensure_vectors(ix));
+        VG_CUDA(cudaMemcpyAsync(ix->vectors.as<float>() + row0 * ix->d.dim, d_vectors, (size_t)n * ix->d.dim * 4,
+                                cudaMemcpyDeviceToDevice, stream()));
+        ix->has_vectors = true;
+    }
+    return VG_OK;
+}
+
+vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h_codes, const float *h_vectors) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (row0 < 0 || n < 0 || row0 + n > ix->d.rows) return fail(VG_ERR_INVALID, "row range outside the index");
+    if (n == 0) return VG_OK;
+    if (h_codes) {
+        if (ix->code_row_bytes == 0) return fail(VG_ERR_INVALID, "this index has no code section");
+        // chunks of <= 64 MiB go host → pinned → device scratch → (re-tiled) final place
+        const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / ix->code_row_bytes);
+        DevBuf tmp;
+        VG_TRY(tmp.alloc((size_t)std::min(chunk_rows, n) * ix->code_row_bytes));
+        for (int64_t r = 0; r < n; r += chunk_rows) {
+            const int64_t c = std::min(chunk_rows, n - r);
+            VG_TRY(staged_h2d(tmp.p, (const uint8_t *)h_codes + r * ix->code_row_bytes, (size_t)c * ix->code_row_bytes));
+            VG_TRY(place_codes(ix, row0 + r, c, tmp.as<uint8_t>()));
+            VG_CUDA(cudaStreamSynchronize(stream()));
+        }
+        ix->has_codes = true;
+    }
+    if (h_vectors) {
+        VG_TRY(ensure_vectors(ix));
+        VG_TRY(staged_h2d(ix->vectors.as<float>() + row0 * ix->d.dim, h_vectors, (size_t)n * ix->d.dim * 4));
+        ix->has_vectors = true;
+    }
+    return VG_OK;
+}
+
+// --------------------------------------------------------------- search
+// OPQ query rotation (opq.go:196-214): out[b*bs + i] = simd.Dot(R_b[i], v_b).
+__global__ void __launch_bounds__(256) opq_rotate_kernel(const float *v, int64_t n, int64_t dim, int bs, const float *rot,
+                                                         float *out) {
+    const int64_t hwid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const int64_t total = n * dim;
+    const bool live = hwid < total;
+    const int64_t o = live ? hwid : total - 1;
+    const int64_t r = o / dim, d = o - r * dim;
+    const int64_t b = d / bs, i = d - b * bs;
+    const float *row = rot + (b * bs + i) * bs;
+    const float *x = v + r * dim + b * bs;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int epochs = bs >> 6;
+    for (int e = 0; e < epochs; e++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) a[j] = __fmaf_rn(row[e * 64 + j * 16 + lane], x[e * 64 + j * 16 + lane], a[j]);
+    float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+    if (lane == 0 && live) {
+        for (int t = epochs * 64; t < bs; t++) tot = __fmaf_rn(row[t], x[t], tot);
+        out[o] = tot;
+    }
+}
+
+static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                                 const uint8_t *d_mask, uint32_t *d_rows, float *d_scores, int32_t *d_counts) {
+    if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
+    if (nq == 0) return VG_OK;
+    const vg_index_desc &d = ix->d;
+    if (d.codec == VG_CODEC_F32 ? !ix->has_vectors : !ix->has_codes) {
+        if (d.rows > 0) return fail(VG_ERR_STATE, "index rows were never uploaded");
+    }
+    cudaStream_t st = stream();
+    CodecParams cp = params_of(*ix);
+    ScanArgs a;
+    a.queries = d_queries;
+    a.nq = nq;
+    a.rows = d.rows;
+    a.k = (int)k;
+    a.descending = d.metric != VG_METRIC_L2;
+    a.is_dot = d.metric != VG_METRIC_L2;
+    a.row_base = (uint32_t)d.row_base;
+    a.mask = d_mask;
+    a.out_rows = d_rows;
+    a.out_scores = d_scores;
+    a.out_counts = d_counts;
+    DevBuf qwords, qnorms, probe, rotated;
+    if (d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_BQ || d.codec == VG_CODEC_RABITQ) {
+        a.descending = 0;  // these scores are distances whatever the segment metric
+        a.is_dot = 0;
+    }
+    if (d.codec == VG_CODEC_BQ || d.codec == VG_CODEC_RABITQ) {
+        VG_TRY(qwords.alloc((size_t)nq * ix->words32 * 4));
+        VG_CUDA(cudaMemsetAsync(qwords.p, 0, qwords.bytes, st));
+        if (d.codec == VG_CODEC_RABITQ) VG_TRY(qnorms.alloc((size_t)nq * 4));
+        // prep writes ceil(dim/64)*2 words per query into rows of words32 (zero padded)
+        const int w_live = (int)(((d.dim + 63) / 64) * 2);
+        if (w_live == ix->words32) {
+            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, d.codec == VG_CODEC_BQ ? d.bq_threshold : 0.0f, qwords.as<uint32_t>(),
+                                     qnorms.as<float>(), st));
+        } else {
+            DevBuf tight;
+            VG_TRY(tight.alloc((size_t)nq * w_live * 4));
+            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, d.codec == VG_CODEC_BQ ? d.bq_threshold : 0.0f, tight.as<uint32_t>(),
+                                     qnorms.as<float>(), st));
+            VG_CUDA(cudaMemcpy2DAsync(qwords.p, (size_t)ix->words32 * 4, tight.p, (size_t)w_live * 4, (size_t)w_live * 4, (size_t)nq,
+                                      cudaMemcpyDeviceToDevice, st));
+            VG_CUDA(cudaStreamSynchronize(st));
+        }
+        cp.q_words = qwords.as<uint32_t>();
+        cp.q_norms = qnorms.as<float>();
+    }
+    if (d.codec == VG_CODEC_OPQ) {
+        VG_TRY(rotated.alloc((size_t)nq * d.dim * 4));
+        const int64_t threads = nq * d.dim * 16;
+        opq_rotate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_queries, nq, d.dim, (int)d.opq_block,
+                                                                            ix->rotation.as<float>(), rotated.as<float>());
+        VG_LAUNCHED();
+        a.queries = rotated.as<float>();
+    }
+    if (d.num_partitions > 1) {
+        // kmeans.FindClosestCentroids per query (flat/segment.go:726-745)
+        int64_t np = nprobes <= 0 ? 1 : nprobes;
+        if (np > d.num_partitions) np = d.num_partitions;
+        VG_TRY(probe.alloc((size_t)nq * np * 4));
+        VG_TRY(dev_find_closest(a.queries, nq, d.dim, ix->centroids.as<float>(), d.num_partitions, np, d.metric,
+                                probe.as<int32_t>(), st));
+        a.probe = probe.as<int32_t>();
+        a.nprobe = (int)np;
+        a.part_off = ix->part_off.as<uint32_t>();
+        a.num_parts = (int)d.num_partitions;
+    }
+    VG_TRY(scan_topk(cp, a, st));
+    VG_CUDA(cudaStreamSynchronize(st));  // temporaries above are freed on return
+    return VG_OK;
+}
+
+vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                              const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    return search_dev_impl(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts);
+}
+
+vg_status vg_index_search(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes,
+                          const uint8_t *h_row_mask, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
+    if (nq == 0) return VG_OK;
+    DevBuf q, mask, rows, scores, counts;
+    VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
+    if (h_row_mask) VG_TRY(to_device(mask, h_row_mask, (size_t)((ix->d.rows + 7) / 8)));
+    VG_TRY(rows.alloc((size_t)nq * k * 4));
+    VG_TRY(scores.alloc((size_t)nq * k * 4));
+    VG_TRY(counts.alloc((size_t)nq * 4));
+    VG_TRY(search_dev_impl(ix, q.as<float>(), nq, k, nprobes, h_row_mask ? mask.as<uint8_t>() : nullptr, rows.as<uint32_t>(),
+                           scores.as<float>(), counts.as<int32_t>()));
+    VG_TRY(staged_d2h(h_out_rows, rows.p, (size_t)nq * k * 4));
+    VG_TRY(staged_d2h(h_out_scores, scores.p, (size_t)nq * k * 4));
+    VG_TRY(staged_d2h(h_out_counts, counts.p, (size_t)nq * 4));
+    return VG_OK;
+}
+
+vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r,
+                              float *d_scores) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
+    return rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2,
+                         d_scores, stream());
+}
+
+vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (nq <= 0 || r <= 0) return VG_OK;
+    DevBuf q, rows, scores;
+    VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
+    VG_TRY(to_device(rows, h_rows, (size_t)nq * r));
+    VG_TRY(scores.alloc((size_t)nq * r * 4));
+    VG_TRY(vg_index_rerank_dev(idx, q.as<float>(), nq, rows.as<uint32_t>(), r, scores.as<float>()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_scores, scores.p, (size_t)nq * r * 4);
+}
+
+// exact scores → keys → per-query top-k (one list per query of length r)
+__global__ void __launch_bounds__(256) rerank_keys_kernel(const uint32_t *rows, const float *scores, int64_t n, uint32_t row_base,
+                                                          int descending, unsigned long long *keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = rows[i];
+    keys[i] = (g == 0xFFFFFFFFu) ? VG_KEY_EMPTY : make_key(scores[i], g, descending != 0);
+    (void)row_base;
+}
+__global__ void __launch_bounds__(256) local_rows_kernel(const uint32_t *rows, int64_t n, uint32_t row_base, uint32_t *local) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    local[i] = (rows[i] == 0xFFFFFFFFu) ? 0xFFFFFFFFu : rows[i] - row_base;
+}
+
+vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t nq, int64_t r, int64_t k, uint32_t *h_out_rows,
+                                 float *h_out_scores, int32_t *h_out_counts) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (nq <= 0) return VG_OK;
+    if (r < k) r = k;
+    if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
+    cudaStream_t st = stream();
+    DevBuf q, rows, local, scores, counts, exact, keys, orows, oscores, ocounts;
+    VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
+    VG_TRY(rows.alloc((size_t)nq * r * 4));
+    VG_TRY(local.alloc((size_t)nq * r * 4));
+    VG_TRY(scores.alloc((size_t)nq * r * 4));
+    VG_TRY(counts.alloc((size_t)nq * 4));
+    VG_TRY(exact.alloc((size_t)nq * r * 4));
+    VG_TRY(keys.alloc((size_t)nq * r * 8));
+    VG_TRY(orows.alloc((size_t)nq * k * 4));
+    VG_TRY(oscores.alloc((size_t)nq * k * 4));
+    VG_TRY(ocounts.alloc((size_t)nq * 4));
+    VG_TRY(search_dev_impl(ix, q.as<float>(), nq, r, 0, nullptr, rows.as<uint32_t>(), scores.as<float>(), counts.as<int32_t>()));
+    const int64_t n = nq * r;
+    local_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows.as<uint32_t>(), n, (uint32_t)ix->d.row_base,
+                                                                   local.as<uint32_t>());
+    VG_LAUNCHED();
+    const int desc = ix->d.metric != VG_METRIC_L2;
+    VG_TRY(rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, q.as<float>(), nq, local.as<uint32_t>(), r, desc,
+                         exact.as<float>(), st));
+    rerank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows.as<uint32_t>(), exact.as<float>(), n,
+                                                                    (uint32_t)ix->d.row_base, desc, keys.as<unsigned long long>());
+    VG_LAUNCHED();
+    VG_TRY(launch_merge_keys(keys.as<unsigned long long>(), 1, nq, r, 0, r, desc != 0, k, orows.as<uint32_t>(), oscores.as<float>(),
+                             ocounts.as<int32_t>(), st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    VG_TRY(staged_d2h(h_out_rows, orows.p, (size_t)nq * k * 4));
+    VG_TRY(staged_d2h(h_out_scores, oscores.p, (size_t)nq * k * 4));
+    VG_TRY(staged_d2h(h_out_counts, ocounts.p, (size_t)nq * 4));
+    return VG_OK;
+}
+
+// --------------------------------------------------------------- top-k merge
+vg_status vg_topk_merge_dev(const uint32_t *d_rows, const float *d_scores, int64_t lists, int64_t nq, int64_t k_in,
+                            int32_t descending, int64_t k_out, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts) {
+    VG_TRY(ensure_init());
+    if (lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(VG_ERR_INVALID, "bad merge shape");
+    return launch_merge_pairs(d_rows, d_scores, lists, nq, k_in, descending != 0, k_out, d_out_rows, d_out_scores, d_out_counts,
+                              stream());
+}
+vg_status vg_topk_merge(const uint32_t *h_rows, const float *h_scores, int64_t lists, int64_t nq, int64_t k_in,
+                        int32_t descending, int64_t k_out, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
+    VG_TRY(ensure_init());
+    if (lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(VG_ERR_INVALID, "bad merge shape");
+    if (nq == 0) return VG_OK;
+    DevBuf r, s, orow, osc, ocnt;
+    VG_TRY(to_device(r, h_rows, (size_t)(lists * nq * k_in)));
+    VG_TRY(to_device(s, h_scores, (size_t)(lists * nq * k_in)));
+    VG_TRY(orow.alloc((size_t)nq * k_out * 4));
+    VG_TRY(osc.alloc((size_t)nq * k_out * 4));
+    VG_TRY(ocnt.alloc((size_t)nq * 4));
+    VG_TRY(launch_merge_pairs(r.as<uint32_t>(), s.as<float>(), lists, nq, k_in, descending != 0, k_out, orow.as<uint32_t>(),
+                              osc.as<float>(), ocnt.as<int32_t>(), stream()));
+    VG_TRY(staged_d2h(h_out_rows, orow.p, (size_t)nq * k_out * 4));
+    VG_TRY(staged_d2h(h_out_scores, osc.p, (size_t)nq * k_out * 4));
+    return staged_d2h(h_out_counts, ocnt.p, (size_t)nq * 4);
+}
+
+// ------------------------------------------------------------ simd mirrors
+static vg_status dense_host(CodecParams cp, const float *h_q, int64_t nq, int64_t qfloats, int64_t n, int is_dot, float *h_out) {
+    DevBuf q, out;
+    if (h_q) VG_TRY(to_device(q, h_q, (size_t)nq * qfloats));
+    VG_TRY(out.alloc((size_t)nq * n * 4));
+    VG_TRY(scan_dense(cp, q.as<float>(), nq, n, is_dot, out.as<float>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_out, out.p, (size_t)nq * n * 4);
+}
+
+static vg_status f32_dense(const float *h_q, int64_t nq, const float *h_t, int64_t n, int64_t dim, int is_dot, int variant,
+                           float *h_out) {
+    VG_TRY(ensure_init());
+    if (dim < 0 || nq < 0 || n < 0) return fail(VG_ERR_INVALID, "negative size");
+    if (nq == 0 || n == 0) return VG_OK;
+    if (dim == 0) {
+        memset(h_out, 0, (size_t)nq * n * 4);
+        return VG_OK;
+    }
+    DevBuf t;
+    VG_TRY(to_device(t, h_t, (size_t)n * dim));
+    CodecParams cp;
+    cp.codec = VG_CODEC_F32;
+    cp.variant = variant;
+    cp.dim = dim;
+    cp.vectors = t.as<float>();
+    return dense_host(cp, h_q, nq, dim, n, is_dot, h_out);
+}
+vg_status vg_simd_dot_batch(const float *h_q, int64_t nq, const float *h_t, int64_t n, int64_t dim, float *h_out) {
+    return f32_dense(h_q, nq, h_t, n, dim, 1, VG_VAR_BATCH, h_out);
+}
+vg_status vg_simd_squared_l2_batch(const float *h_q, int64_t nq, const float *h_t, int64_t n, int64_t dim, float *h_out) {
+    return f32_dense(h_q, nq, h_t, n, dim, 0, VG_VAR_BATCH, h_out);
+}
+
+// per-pair Dot / SquaredL2: rerank kernel with rows[i] = i, one "query" per pair
+__global__ void iota_kernel(uint32_t *p, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = (uint32_t)i;
+}
+static vg_status pair_host(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, int is_dot, float *h_out) {
+    VG_TRY(ensure_init());
+    if (n_pairs <= 0) return VG_OK;
+    if (dim <= 0) {
+        memset(h_out, 0, (size_t)n_pairs * 4);
+        return VG_OK;
+    }
+    DevBuf a, b, rows, out;
+    VG_TRY(to_device(a, h_a, (size_t)n_pairs * dim));
+    VG_TRY(to_device(b, h_b, (size_t)n_pairs * dim));
+    VG_TRY(rows.alloc((size_t)n_pairs * 4));
+    VG_TRY(out.alloc((size_t)n_pairs * 4));
+    iota_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream()>>>(rows.as<uint32_t>(), n_pairs);
+    VG_LAUNCHED();
+    VG_TRY(rerank_gather(b.as<float>(), n_pairs, dim, a.as<float>(), n_pairs, rows.as<uint32_t>(), 1, is_dot, out.as<float>(),
+                         stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_out, out.p, (size_t)n_pairs * 4);
+}
+vg_status vg_simd_dot(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, float *h_out) {
+    return pair_host(h_a, h_b, n_pairs, dim, 1, h_out);
+}
+vg_status vg_simd_squared_l2(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, float *h_out) {
+    return pair_host(h_a, h_b, n_pairs, dim, 0, h_out);
+}
+
+vg_status vg_simd_sq8u_l2_batch(const float *h_q, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_mins,
+                                const float *h_inv, float *h_out) {
+    VG_TRY(ensure_init());
+    if (nq <= 0 || n <= 0) return VG_OK;
+    if (dim <= 0) {
+        memset(h_out, 0, (size_t)nq * n * 4);
+        return VG_OK;
+    }
+    DevBuf c, mn, iv;
+    VG_TRY(to_device(c, h_codes, (size_t)n * dim));
+    VG_TRY(to_device(mn, h_mins, (size_t)dim));
+    VG_TRY(to_device(iv, h_inv, (size_t)dim));
+    CodecParams cp;
+    cp.codec = VG_CODEC_SQ8;
+    cp.dim = dim;
+    cp.row_bytes = dim;
+    cp.codes = c.as<uint8_t>();
+    cp.p0 = mn.as<float>();
+    cp.p1 = iv.as<float>();
+    return dense_host(cp, h_q, nq, dim, n, 0, h_out);
+}
+vg_status vg_simd_int4_l2_batch(const float *h_q, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_min,
+                                const float *h_diff, float *h_out) {
+    VG_TRY(ensure_init());
+    if (nq <= 0 || n <= 0) return VG_OK;
+    if (dim <= 0) {
+        memset(h_out, 0, (size_t)nq * n * 4);
+        return VG_OK;
+    }
+    const int64_t cs = (dim + 1) / 2;
+    DevBuf c, mn, df;
+    VG_TRY(to_device(c, h_codes, (size_t)n * cs));
+    VG_TRY(to_device(mn, h_min, (size_t)dim));
+    VG_TRY(to_device(df, h_diff, (size_t)dim));
+    CodecParams cp;
+    cp.codec = VG_CODEC_INT4;
+    cp.dim = dim;
+    cp.row_bytes = cs;
+    cp.codes = c.as<uint8_t>();
+    cp.p0 = mn.as<float>();
+    cp.p1 = df.as<float>();
+    return dense_host(cp, h_q, nq, dim, n, 0, h_out);
+}
+vg_status vg_simd_pq_adc_lookup(const float *h_tables, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t m, float *h_out) {
+    VG_TRY(ensure_init());
+    if (nq <= 0 || n <= 0) return VG_OK;
+    if (m <= 0) {
+        memset(h_out, 0, (size_t)nq * n * 4);
+        return VG_OK;
+    }
+    DevBuf c, t;
+    VG_TRY(to_device(c, h_codes, (size_t)n * m));
+    VG_TRY(to_device(t, h_tables, (size_t)nq * m * 256));
+    CodecParams cp;
+    cp.codec = VG_CODEC_PQ;
+    cp.dim = m;
+    cp.row_bytes = m;
+    cp.codes = c.as<uint8_t>();
+    cp.pq_m = (int)m;
+    cp.pq_k = 256;
+    cp.pq_tables = t.as<float>();
+    return dense_host(cp, nullptr, nq, 0, n, 0, h_out);
+}
+vg_status vg_simd_hamming(const uint8_t *h_q, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t nbytes, int32_t *h_out) {
+    VG_TRY(ensure_init());
+    if (nq <= 0 || n <= 0) return VG_OK;
+    if (nbytes <= 0) {
+        memset(h_out, 0, (size_t)nq * n * 4);
+        return VG_OK;
+    }
+    DevBuf q, c, out;
+    VG_TRY(to_device(q, h_q, (size_t)nq * nbytes));
+    VG_TRY(to_device(c, h_codes, (size_t)n * nbytes));
+    VG_TRY(out.alloc((size_t)nq * n * 4));
+    VG_TRY(hamming_dense(q.as<uint8_t>(), nq, c.as<uint8_t>(), n, nbytes, out.as<int32_t>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_out, out.p, (size_t)nq * n * 4);
+}
+vg_status vg_simd_scale(float *h_a, int64_t n, float scalar) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    DevBuf a;
+    VG_TRY(to_device(a, h_a, (size_t)n));
+    VG_TRY(dev_scale(a.as<float>(), n, scalar, stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_a, a.p, (size_t)n * 4);
+}
+vg_status vg_normalize_l2(float *h_vecs, int64_t n, int64_t dim, uint8_t *h_ok) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    if (dim <= 0) {
+        if (h_ok) memset(h_ok, 0, (size_t)n);
+        return VG_OK;
+    }
+    DevBuf v, ok;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(ok.alloc((size_t)n));
+    VG_TRY(dev_normalize(v.as<float>(), n, dim, ok.as<uint8_t>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    VG_TRY(staged_d2h(h_vecs, v.p, (size_t)n * dim * 4));
+    if (h_ok) VG_TRY(staged_d2h(h_ok, ok.p, (size_t)n));
+    return VG_OK;
+}
+
+// ------------------------------------------------------------ quantizers
+vg_status vg_sq8_set_bounds(const float *h_mins, const float *h_maxs, int64_t dim, float *h_scales, float *h_inv) {
+    // quantizer.go:51-75 — parameter algebra only (single rounded float32 ops)
+    if (dim <= 0) return fail(VG_ERR_INVALID, "dimension mismatch");
+    for (int64_t i = 0; i < dim; i++) {
+        volatile float diff = h_maxs[i] - h_mins[i];
+        if (diff < 1e-9f) {
+            h_scales[i] = 0;
+            h_inv[i] = 0;
+        } else {
+            volatile float s = 255.0f / diff, v = diff / 255.0f;
+            h_scales[i] = s;
+            h_inv[i] = v;
+        }
+    }
+    return VG_OK;
+}
+vg_status vg_sq8_train(const float *h_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs, float *h_scales, float *h_inv) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    if (dim <= 0) return fail(VG_ERR_INVALID, "vector dimension mismatch");
+    DevBuf v, mm;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(mm.alloc((size_t)dim * 8));
+    VG_TRY(dev_minmax(v.as<float>(), n, dim, mm.as<float>(), mm.as<float>() + dim, stream()));
+    VG_TRY(staged_d2h(h_mins, mm.p, (size_t)dim * 4));
+    VG_TRY(staged_d2h(h_maxs, mm.as<float>() + dim, (size_t)dim * 4));
+    for (int64_t i = 0; i < dim; i++) {  // quantizer.go:166-176
+        if (h_mins[i] == h_maxs[i]) {
+            volatile float t = h_mins[i] + 1e-6f;
+            h_maxs[i] = t;
+        }
+        volatile float range = h_maxs[i] - h_mins[i];
+        volatile float s = 255.0f / range, iv = range / 255.0f;
+        h_scales[i] = s;
+        h_inv[i] = iv;
+    }
+    return VG_OK;
+}
+vg_status vg_sq8_encode(const float *h_vecs, int64_t n, int64_t dim, const float *h_mins, const float *h_maxs, const float *h_scales,
+                        uint8_t *h_codes) {
+    VG_TRY(ensure_init());
+    if (!h_mins || !h_maxs || !h_scales) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
+    if (n <= 0) return VG_OK;
+    DevBuf v, mn, mx, sc, out;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(to_device(mn, h_mins, (size_t)dim));
+    VG_TRY(to_device(mx, h_maxs, (size_t)dim));
+    VG_TRY(to_device(sc, h_scales, (size_t)dim));
+    VG_TRY(out.alloc((size_t)n * dim));
+    VG_TRY(dev_sq8_encode(v.as<float>(), n, dim, mn.as<float>(), mx.as<float>(), sc.as<float>(), out.as<uint8_t>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_codes, out.p, (size_t)n * dim);
+}
+vg_status vg_sq8_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_mins, const float *h_inv, float *h_vecs) {
+    VG_TRY(ensure_init());
+    if (!h_mins || !h_inv) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
+    if (n <= 0) return VG_OK;
+    DevBuf c, mn, iv, out;
+    VG_TRY(to_device(c, h_codes, (size_t)n * dim));
+    VG_TRY(to_device(mn, h_mins, (size_t)dim));
+    VG_TRY(to_device(iv, h_inv, (size_t)dim));
+    VG_TRY(out.alloc((size_t)n * dim * 4));
+    VG_TRY(dev_sq8_decode(c.as<uint8_t>(), n, dim, mn.as<float>(), iv.as<float>(), out.as<float>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_vecs, out.p, (size_t)n * dim * 4);
+}
+vg_status vg_int4_train(const float *h_vecs, int64_t n, int64_t dim, float *h_min, float *h_diff) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    DevBuf v, mm;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(mm.alloc((size_t)dim * 8));
+    VG_TRY(dev_minmax(v.as<float>(), n, dim, mm.as<float>(), mm.as<float>() + dim, stream()));
+    std::vector<float> mx((size_t)dim);
+    VG_TRY(staged_d2h(h_min, mm.p, (size_t)dim * 4));
+    VG_TRY(staged_d2h(mx.data(), mm.as<float>() + dim, (size_t)dim * 4));
+    for (int64_t i = 0; i < dim; i++) {  // int4.go:53-59
+        volatile float df = mx[(size_t)i] - h_min[i];
+        h_diff[i] = (df == 0) ? 1.0f : (float)df;
+    }
+    return VG_OK;
+}
+vg_status vg_int4_encode(const float *h_vecs, int64_t n, int64_t dim, const float *h_min, const float *h_diff, uint8_t *h_codes) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    const int64_t cs = (dim + 1) / 2;
+    DevBuf v, mn, df, out;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(to_device(mn, h_min, (size_t)dim));
+    VG_TRY(to_device(df, h_diff, (size_t)dim));
+    VG_TRY(out.alloc((size_t)n * cs));
+    VG_TRY(dev_int4_encode(v.as<float>(), n, dim, mn.as<float>(), df.as<float>(), out.as<uint8_t>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_codes, out.p, (size_t)n * cs);
+}
+vg_status vg_int4_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_min, const float *h_diff, float *h_vecs) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    const int64_t cs = (dim + 1) / 2;
+    DevBuf c, mn, df, out;
+    VG_TRY(to_device(c, h_codes, (size_t)n * cs));
+    VG_TRY(to_device(mn, h_min, (size_t)dim));
+    VG_TRY(to_device(df, h_diff, (size_t)dim));
+    VG_TRY(out.alloc((size_t)n * dim * 4));
+    VG_TRY(dev_int4_decode(c.as<uint8_t>(), n, dim, mn.as<float>(), df.as<float>(), out.as<float>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_vecs, out.p, (size_t)n * dim * 4);
+}
+vg_status vg_bq_train(const float *h_vecs, int64_t n, int64_t dim, float *h_threshold) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    DevBuf v;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    double sum = 0;
+    VG_TRY(dev_mean_f64(v.as<float>(), n * dim, &sum, stream()));
+    *h_threshold = (float)(sum / (double)(n * dim));
+    return VG_OK;
+}
+static vg_status sign_encode_host(const float *h_vecs, int64_t n, int64_t dim, float thr, bool with_norm, uint8_t *h_codes) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    const int64_t stride = ((dim + 63) / 64) * 8 + (with_norm ? 4 : 0);
+    DevBuf v, out;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(out.alloc((size_t)n * stride));
+    VG_TRY(dev_sign_encode(v.as<float>(), n, dim, thr, with_norm, out.as<uint8_t>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_codes, out.p, (size_t)n * stride);
+}
+vg_status vg_bq_encode(const float *h_vecs, int64_t n, int64_t dim, float threshold, uint8_t *h_codes) {
+    return sign_encode_host(h_vecs, n, dim, threshold, false, h_codes);
+}
+vg_status vg_rabitq_encode(const float *h_vecs, int64_t n, int64_t dim, uint8_t *h_codes) {
+    return sign_encode_host(h_vecs, n, dim, 0.0f, true, h_codes);
+}
+
+struct PqDev {
+    DevBuf cb, sc, of;
+};
+static vg_status pq_params(PqDev &p, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc, const float *h_of) {
+    if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
+    if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");
+    if (!h_cb || !h_sc || !h_of) return fail(VG_ERR_STATE, "ProductQuantizer not trained");
+    VG_TRY(to_device(p.cb, h_cb, (size_t)(m * k * (dim / m))));
+    VG_TRY(to_device(p.sc, h_sc, (size_t)m));
+    return to_device(p.of, h_of, (size_t)m);
+}
+vg_status vg_pq_encode(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc,
+                       const float *h_of, uint8_t *h_codes) {
+    VG_TRY(ensure_init());
+    PqDev p;
+    VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
+    if (n <= 0) return VG_OK;
+    DevBuf v, out;
+    VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
+    VG_TRY(out.alloc((size_t)n * m));
+    VG_TRY(dev_pq_encode(v.as<float>(), n, dim, (int)m, (int)k, p.cb.as<int8_t>(), p.sc.as<float>(), p.of.as<float>(),
+                         out.as<uint8_t>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_codes, out.p, (size_t)n * m);
+}
+vg_status vg_pq_decode(const uint8_t *h_codes, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc,
+                       const float *h_of, float *h_vecs) {
+    VG_TRY(ensure_init());
+    PqDev p;
+    VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
+    if (n <= 0) return VG_OK;
+    DevBuf c, out;
+    VG_TRY(to_device(c, h_codes, (size_t)n * m));
+    VG_TRY(out.alloc((size_t)n * dim * 4));
+    VG_TRY(dev_pq_decode(c.as<uint8_t>(), n, dim, (int)m, (int)k, p.cb.as<int8_t>(), p.sc.as<float>(), p.of.as<float>(),
+                         out.as<float>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_vecs, out.p, (size_t)n * dim * 4);
+}
+vg_status vg_pq_build_distance_table(const float *h_q, int64_t nq, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb,
+                                     const float *h_sc, const float *h_of, float *h_tables) {
+    VG_TRY(ensure_init());
+    PqDev p;
+    VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
+    if (nq <= 0) return VG_OK;
+    DevBuf q, out;
+    VG_TRY(to_device(q, h_q, (size_t)nq * dim));
+    VG_TRY(out.alloc((size_t)nq * m * k * 4));
+    VG_TRY(dev_pq_tables(q.as<float>(), nq, dim, (int)m, (int)k, p.cb.as<int8_t>(), p.sc.as<float>(), p.of.as<float>(),
+                         out.as<float>(), stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_tables, out.p, (size_t)nq * m * k * 4);
+}
+
+// ------------------------------------------------------------ flat segment file
+// format.go:110-165 / segment.go:105-342
+static uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
+static uint64_t rd64(const uint8_t *p) { return (uint64_t)rd32(p) | ((uint64_t)rd32(p + 4) << 32); }
+static const size_t kFlatHeaderSize = 152;
+
+vg_status vg_flat_decode_header(const uint8_t *f, size_t len, vg_flat_header *out) {
+    if (!f || len < kFlatHeaderSize) return fail(VG_ERR_FORMAT, "buffer too small for header");
+    if (rd32(f) != 0x56454331u) return fail(VG_ERR_FORMAT, "invalid magic number");
+    if (rd32(f + 4) != 1) return fail(VG_ERR_FORMAT, "unsupported version");
+    out->segment_id = rd64(f + 8);
+    out->row_count = rd32(f + 16);
+    out->dim = rd32(f + 20);
+    out->metric = f[24];
+    out->num_partitions = rd32(f + 28);
+    out->quantization_type = f[32];
+    out->checksum = rd32(f + 104);
+    return VG_OK;
+}
+
+// CRC32C of the body, computed on the device copy of the file (one pass, 4 KiB
+// strides combined on the host would need GF(2) matrices; the body is hashed
+// by a single sequential slicing-by-1 kernel thread per 1 MiB chunk and the
+// chunk CRCs are combined with the standard zero-extension operator).
+__global__ void crc32c_chunks_kernel(const uint8_t *data, size_t n, size_t chunk, uint32_t *out) {
+    const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t b = c * chunk;
+    if (b >= n) return;
+    size_t e = b + chunk;
+    if (e > n) e = n;
+    uint32_t crc = 0;  // raw register value, no pre/post inversion
+    for (size_t i = b; i < e; i++) {
+        crc ^= data[i];
+        for (int k = 0; k < 8; k++) crc = (crc >> 1) ^ (0x82F63B78u & (0u - (crc & 1u)));
+    }
+    out[c] = crc;
+}
+static uint32_t gf2_times(const uint32_t *mat, uint32_t vec) {
+    uint32_t s = 0;
+    while (vec) {
+        if (vec & 1) s ^= *mat;
+        vec >>= 1;
+        mat++;
+    }
+    return s;
+}
+static void gf2_square(uint32_t *sq, const uint32_t *mat) {
+    for (int n = 0; n < 32; n++) sq[n] = gf2_times(mat, mat[n]);
+}
+// advance raw crc register over `len` zero bytes
+static uint32_t crc_shift(uint32_t crc, size_t len) {
+    uint32_t even[32], odd[32];
+    odd[0] = 0x82F63B78u;
+    uint32_t row = 1;
+    for (int n = 1; n < 32; n++) {
+        odd[n] = row;
+        row <<= 1;
+    }
+    gf2_square(even, odd);
+    gf2_square(odd, even);
+    do {
+        gf2_square(even, odd);
+        if (len & 1) crc = gf2_times(even, crc);
+        len >>= 1;
+        if (!len) break;
+        gf2_square(odd, even);
+        if (len & 1) crc = gf2_times(odd, crc);
+        len >>= 1;
+    } while (len);
+    return crc;
+}
+static vg_status device_crc32c(const uint8_t *d_data, size_t n, uint32_t *crc_out) {
+    const size_t chunk = 4096;
+    const size_t chunks = (n + chunk - 1) / chunk;
+    if (n == 0) {
+        *crc_out = 0;
+        return VG_OK;
+    }
+    DevBuf out;
+    VG_TRY(out.alloc(chunks * 4));
+    crc32c_chunks_kernel<<<(unsigned)((chunks + 127) / 128), 128, 0, stream()>>>(d_data, n, chunk, out.as<uint32_t>());
+    VG_LAUNCHED();
+    std::vector<uint32_t> h(chunks);
+    VG_CUDA(cudaMemcpyAsync(h.data(), out.p, chunks * 4, cudaMemcpyDeviceToHost, stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    // crc(A‖B) with init I: raw(A‖B) = shift(raw_I(A), |B|) ^ raw_0(B); fold left to right.
+    uint32_t reg = 0xFFFFFFFFu;
+    for (size_t c = 0; c < chunks; c++) {
+        const size_t len = (c + 1 == chunks) ? n - c * chunk : chunk;
+        reg = crc_shift(reg, len) ^ h[c];
+    }
+    *crc_out = reg ^ 0xFFFFFFFFu;
+    return VG_OK;
+}
+
+vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg_index_t *out) {
+    VG_TRY(ensure_init());
+    vg_flat_header h;
+    VG_TRY(vg_flat_decode_header(f, len, &h));
+    const uint64_t off_centroid = rd64(f + 40), off_part = rd64(f + 48), off_quant = rd64(f + 56), off_codes = rd64(f + 64),
+                   off_vec = rd64(f + 72), off_pk = rd64(f + 80), off_meta = rd64(f + 88);
+    const uint64_t rows = h.row_count, dim = h.dim;
+    if (dim == 0) return fail(VG_ERR_FORMAT, "zero dimension");
+    vg_index_desc d;
+    memset(&d, 0, sizeof d);
+    d.dim = (int64_t)dim;
+    d.rows = (int64_t)rows;
+    d.metric = (int32_t)h.metric;
+    d.segment_id = (uint32_t)h.segment_id;
+    std::vector<float> mins, maxs, scales, inv, cent;
+    std::vector<uint32_t> poff;
+    std::vector<float> pq_sc, pq_of;
+    const uint8_t *codes = nullptr;
+    if (h.num_partitions > 0) {
+        const uint64_t cb = (uint64_t)h.num_partitions * dim * 4;
+        if (len < off_centroid + cb) return fail(VG_ERR_FORMAT, "file too short for centroids");
+        if (len < off_part + ((uint64_t)h.num_partitions + 1) * 4) return fail(VG_ERR_FORMAT, "file too short for partition offsets");
+        cent.resize((size_t)h.num_partitions * dim);
+        memcpy(cent.data(), f + off_centroid, cb);
+        poff.resize((size_t)h.num_partitions + 1);
+        memcpy(poff.data(), f + off_part, poff.size() * 4);
+        d.num_partitions = h.num_partitions;
+        d.centroids = cent.data();
+        d.partition_offsets = poff.data();
+    }
+    if (h.quantization_type == 1) {  // QuantizationSQ8 → SetBounds(mins, maxs)
+        if (len < off_quant + dim * 8) return fail(VG_ERR_FORMAT, "file too short for quantization metadata");
+        mins.resize(dim);
+        maxs.resize(dim);
+        scales.resize(dim);
+        inv.resize(dim);
+        memcpy(mins.data(), f + off_quant, dim * 4);
+        memcpy(maxs.data(), f + off_quant + dim * 4, dim * 4);
+        VG_TRY(vg_sq8_set_bounds(mins.data(), maxs.data(), (int64_t)dim, scales.data(), inv.data()));
+        if (len < off_codes + rows * dim) return fail(VG_ERR_FORMAT, "file too short for codes");
+        d.codec = VG_CODEC_SQ8;
+        d.sq8_mins = mins.data();
+        d.sq8_inv_scales = inv.data();
+        codes = f + off_codes;
+    } else if (h.quantization_type == 2) {  // QuantizationPQ
+        if (len < off_quant + 8) return fail(VG_ERR_FORMAT, "file too short for PQ metadata");
+        const uint64_t m = rd32(f + off_quant), k = rd32(f + off_quant + 4);
+        if (m == 0 || dim % m != 0) return fail(VG_ERR_FORMAT, "dimension must be divisible by numSubvectors");
+        const uint64_t dsub = dim / m, cbsize = m * k * dsub, meta = 8 + m * 8 + cbsize;
+        if (len < off_quant + meta) return fail(VG_ERR_FORMAT, "file too short for PQ metadata");
+        pq_sc.resize(m);
+        pq_of.resize(m);
+        memcpy(pq_sc.data(), f + off_quant + 8, m * 4);
+        memcpy(pq_of.data(), f + off_quant + 8 + m * 4, m * 4);
+        if (len < off_codes + rows * m) return fail(VG_ERR_FORMAT, "file too short for codes");
+        d.codec = VG_CODEC_PQ;
+        d.pq_m = (int64_t)m;
+        d.pq_k = (int64_t)k;
+        d.pq_codebooks = reinterpret_cast<const int8_t *>(f + off_quant + 8 + m * 8);
+        d.pq_scales = pq_sc.data();
+        d.pq_offsets = pq_of.data();
+        codes = f + off_codes;
+    } else if (h.quantization_type == 0) {
+        d.codec = VG_CODEC_F32;
+    } else {
+        return fail(VG_ERR_FORMAT, "unknown quantization type");
+    }
+    if (len < off_vec + rows * dim * 4) return fail(VG_ERR_FORMAT, "file too short for vectors");
+    if (off_meta < off_pk || len < off_pk + (off_meta - off_pk)) return fail(VG_ERR_FORMAT, "file too short for IDs");
+    if (rows > 0 && off_meta - off_pk < rows * 8) return fail(VG_ERR_FORMAT, "id section too small");
+    if (verify_checksum && h.checksum != 0 && len > kFlatHeaderSize) {
+        DevBuf body;
+        VG_TRY(to_device(body, f + kFlatHeaderSize, len - kFlatHeaderSize));
+        uint32_t crc = 0;
+        VG_TRY(device_crc32c(body.as<uint8_t>(), len - kFlatHeaderSize, &crc));
+        if (crc != h.checksum) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "checksum mismatch: expected %x, got %x", h.checksum, crc);
+            return fail(VG_ERR_FORMAT, msg);
+        }
+    }
+    vg_index_t idx = 0;
+    VG_TRY(vg_index_create(&d, &idx));
+    vg_status s = VG_OK;
+    if (rows > 0) {
+        // sections are only 4-byte aligned in the file (HeaderSize = 152); staging re-aligns them
+        std::vector<float> tmp;
+        const float *vec = reinterpret_cast<const float *>(f + off_vec);
+        if ((reinterpret_cast<uintptr_t>(vec) & 3) != 0) {
+            tmp.resize(rows * dim);
+            memcpy(tmp.data(), f + off_vec, rows * dim * 4);
+            vec = tmp.data();
+        }
+        s = vg_index_upload(idx, 0, (int64_t)rows, codes, vec);
+        if (s == VG_OK) {
+            Index *ix = lookup(idx);
+            s = ix->ids.alloc(rows * 8);
+            if (s == VG_OK) s = staged_h2d(ix->ids.p, f + off_pk, rows * 8);
+            if (s == VG_OK) ix->has_ids = true;
+        }
+    }
+    if (s != VG_OK) {
+        std::string keep = t_error;
+        vg_index_close(idx);
+        t_error = keep;
+        return s;
+    }
+    *out = idx;
+    return VG_OK;
+}
+
+__global__ void gather_u64_kernel(const uint64_t *src, const uint32_t *rows, int64_t n, int64_t nrows, uint64_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = ((int64_t)rows[i] < nrows) ? src[rows[i]] : 0ull;
+}
+vg_status vg_index_fetch_ids(vg_index_t idx, const uint32_t *h_rows, int64_t n, uint64_t *h_ids) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (!ix->has_ids) return fail(VG_ERR_STATE, "index has no id column");
+    if (n <= 0) return VG_OK;
+    DevBuf r, o;
+    VG_TRY(to_device(r, h_rows, (size_t)n));
+    VG_TRY(o.alloc((size_t)n * 8));
+    gather_u64_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream()>>>(ix->ids.as<uint64_t>(), r.as<uint32_t>(), n, ix->d.rows,
+                                                                         o.as<uint64_t>());
+    VG_LAUNCHED();
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_ids, o.p, (size_t)n * 8);
+}
+
+}  // extern "C"

@@ -1,0 +1,602 @@
+// vg_kmeans.cu — Lloyd k-means (internal/kmeans/kmeans.go) and the
+// ProductQuantizer's private per-subspace k-means + k-means++ init + int8
+// codebook quantisation (internal/quantization/pq.go:68-143,275-433).
+//
+// Exactness plan.  Assignment is an argmin with "strict <, first wins", i.e.
+// the smallest (distance, centroid id) — distances are evaluated in the
+// reference's summation order.  The centroid update is a SEQUENTIAL float32
+// sum in sample order per (cluster, dim); we keep that order by building the
+// per-cluster member lists with a stable partition and letting one thread walk
+// each (cluster, dim) chain — thousands of chains run in parallel, each chain
+// is order-exact.  k-means++ draws from an explicit seed (the reference uses
+// Go's unseeded global RNG and is not reproducible even against itself); its
+// float32 running sums are sequential chains too and are kept sequential.
+#include "vg_kmeans.cuh"
+
+#include <vector>
+
+#include "vg_scan.cuh"
+
+namespace vg {
+
+// ---------------------------------------------------------------- RNG
+__host__ __device__ inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+__host__ __device__ inline uint64_t rng_u64(uint64_t seed, uint64_t a, uint64_t b) {
+    return splitmix64(splitmix64(seed ^ (a * 0xD6E8FEB86659FD93ull)) ^ b);
+}
+__host__ __device__ inline int64_t rng_intn(uint64_t seed, uint64_t a, uint64_t b, int64_t n) {
+    return (int64_t)(rng_u64(seed, a, b) % (uint64_t)n);
+}
+__host__ __device__ inline float rng_f32(uint64_t seed, uint64_t a, uint64_t b) {
+    return (float)(rng_u64(seed, a, b) >> 40) * (1.0f / 16777216.0f);
+}
+
+// ---------------------------------------------------------------- helpers
+// simd.SquaredL2 (floats_avx512.c:69-129) evaluated by ONE thread, same order.
+__device__ float sql2_pair_thread(const float *a, const float *b, int n) {
+    float tot = 0.0f;
+    const int epochs = n >> 6;
+    if (epochs > 0) {
+        float acc[64];
+        for (int i = 0; i < 64; i++) acc[i] = 0.0f;
+        for (int e = 0; e < epochs; e++)
+            for (int i = 0; i < 64; i++) {
+                const float d = __fsub_rn(a[e * 64 + i], b[e * 64 + i]);
+                acc[i] = __fmaf_rn(d, d, acc[i]);
+            }
+        float c[16];
+        for (int l = 0; l < 16; l++) c[l] = __fadd_rn(__fadd_rn(acc[l], acc[16 + l]), __fadd_rn(acc[32 + l], acc[48 + l]));
+        for (int l = 0; l < 8; l++) c[l] = __fadd_rn(c[l], c[l + 8]);
+        for (int l = 0; l < 4; l++) c[l] = __fadd_rn(c[l], c[l + 4]);
+        tot = __fadd_rn(__fadd_rn(c[0], c[2]), __fadd_rn(c[1], c[3]));
+    }
+    for (int i = epochs * 64; i < n; i++) {
+        const float d = __fsub_rn(a[i], b[i]);
+        tot = __fmaf_rn(d, d, tot);
+    }
+    return tot;
+}
+
+// ---------------------------------------------------------------- assignment
+// Generic: top-1 scan over the centroid table (any dim, pair or batch order).
+static vg_status assign_generic(const float *d_vecs, int64_t n, int64_t stride, int64_t dim, const float *d_cent, int64_t k,
+                                int variant, int is_dot, uint32_t *d_assign, float *d_score, int32_t *d_cnt, cudaStream_t st) {
+    CodecParams cp;
+    cp.codec = VG_CODEC_F32;
+    cp.variant = variant;
+    cp.dim = dim;
+    cp.vectors = d_cent;
+    ScanArgs a;
+    a.queries = d_vecs;
+    a.q_stride = stride;
+    a.nq = n;
+    a.rows = k;
+    a.k = 1;
+    a.descending = is_dot;
+    a.is_dot = is_dot;
+    a.out_rows = d_assign;
+    a.out_scores = d_score;
+    a.out_counts = d_cnt;
+    return scan_topk(cp, a, st);
+}
+
+// PQ subspaces with ds < 64: simd.SquaredL2 runs entirely in its FMA scalar tail
+// (sum = fma(d, d, sum), floats_avx512.s:316-323).  One thread per (sample, subspace);
+// the subspace's K x DS centroid table sits in shared memory (broadcast reads).
+template <int DS>
+__global__ void __launch_bounds__(256) pq_assign_small_kernel(const float *vecs, int64_t n, int64_t dim, int K,
+                                                              const float *cent /*[G][K][DS]*/, uint32_t *assign /*[G][n]*/) {
+    extern __shared__ __align__(16) float sc[];
+    const int g = blockIdx.y;
+    for (int i = threadIdx.x; i < K * DS; i += blockDim.x) sc[i] = cent[(int64_t)g * K * DS + i];
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    float x[DS];
+#pragma unroll
+    for (int i = 0; i < DS; i++) x[i] = vecs[r * dim + (int64_t)g * DS + i];
+    float best = 3.402823466e+38f;
+    int idx = 0;
+    for (int c = 0; c < K; c++) {
+        float tot = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DS; i++) {
+            const float d = __fsub_rn(x[i], sc[c * DS + i]);
+            tot = __fmaf_rn(d, d, tot);
+        }
+        if (tot < best) {
+            best = tot;
+            idx = c;
+        }
+    }
+    assign[(int64_t)g * n + r] = (uint32_t)idx;
+}
+
+// changed[g] |= (new != old); old = new  (assignments start at zero, pq.go:349)
+__global__ void __launch_bounds__(256) diff_assign_kernel(const uint32_t *newa, int32_t *olda, int64_t n, int G, const int *active,
+                                                          int *changed) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (i >= n || !active[g]) return;
+    const int32_t v = (int32_t)newa[(int64_t)g * n + i];
+    if (olda[(int64_t)g * n + i] != v) {
+        olda[(int64_t)g * n + i] = v;
+        changed[g] = 1;
+    }
+}
+// after the assignment pass: a group whose pass changed nothing stops (break before update)
+__global__ void settle_kernel(int *active, int *changed, int *iters, int G) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    if (active[g]) {
+        if (!changed[g]) active[g] = 0;
+        else iters[g] += 1;
+    }
+    changed[g] = 0;
+}
+
+// ---------------------------------------------------------------- stable partition
+static const int kSB = 1024;  // samples per partition block
+__global__ void __launch_bounds__(256) part_count_kernel(const int32_t *assign, int64_t n, int K, int64_t B, const int *active,
+                                                         int *counts /*[G][K][B]*/) {
+    extern __shared__ int hist[];
+    const int g = blockIdx.y;
+    if (!active[g]) return;
+    const int64_t b = blockIdx.x;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) hist[c] = 0;
+    __syncthreads();
+    const int64_t i0 = b * kSB;
+    for (int i = threadIdx.x; i < kSB; i += blockDim.x)
+        if (i0 + i < n) atomicAdd(&hist[assign[(int64_t)g * n + i0 + i]], 1);
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += blockDim.x) counts[((int64_t)g * K + c) * B + b] = hist[c];
+}
+__global__ void __launch_bounds__(256) part_scan_kernel(int *counts, int K, int64_t B, int G, const int *active, int *totals) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)G * K) return;
+    if (!active[t / K]) return;
+    int run = 0;
+    int *p = counts + t * B;
+    for (int64_t b = 0; b < B; b++) {
+        const int v = p[b];
+        p[b] = run;
+        run += v;
+    }
+    totals[t] = run;
+}
+__global__ void part_base_kernel(const int *totals, int K, int G, const int *active, int64_t n, int64_t *base) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G || !active[g]) return;
+    int64_t run = (int64_t)g * n;
+    for (int c = 0; c < K; c++) {
+        base[(int64_t)g * K + c] = run;
+        run += totals[(int64_t)g * K + c];
+    }
+}
+__global__ void __launch_bounds__(256) part_scatter_kernel(const int32_t *assign, int64_t n, int K, int64_t B, const int *active,
+                                                           const int *counts, const int64_t *base, uint32_t *members) {
+    __shared__ int a[kSB];
+    const int g = blockIdx.y;
+    if (!active[g]) return;
+    const int64_t b = blockIdx.x;
+    const int64_t i0 = b * kSB;
+    int cnt = (int)((n - i0 < kSB) ? (n - i0) : kSB);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) a[i] = assign[(int64_t)g * n + i0 + i];
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        int64_t pos = base[(int64_t)g * K + c] + counts[((int64_t)g * K + c) * B + b];
+        for (int i = 0; i < cnt; i++)
+            if (a[i] == c) members[pos++] = (uint32_t)(i0 + i);
+    }
+}
+// One thread per (group, cluster, dim): sequential float32 sum over the members in
+// sample order, then  sum/count (pq.go:388-413)  or  sum*(1/count) (kmeans.go:110-134).
+__global__ void __launch_bounds__(256) centroid_update_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int G,
+                                                              const int *active, const int *totals, const int64_t *base,
+                                                              const uint32_t *members, int reciprocal, uint64_t seed,
+                                                              uint64_t tag_xor, int tag_is_group, const int *iters,
+                                                              float *cent /*[G][K][ds]*/) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)G * K * ds) return;
+    const int j = (int)(t % ds);
+    const int64_t gc = t / ds;
+    const int g = (int)(gc / K), c = (int)(gc % K);
+    if (!active[g]) return;
+    const int cntc = totals[gc];
+    const float *col = vecs + (int64_t)g * ds + j;
+    if (cntc > 0) {
+        const uint32_t *mem = members + base[gc];
+        float sum = 0.0f;
+        int i = 0;
+        for (; i + 4 <= cntc; i += 4) {
+            const float v0 = col[(int64_t)mem[i] * stride], v1 = col[(int64_t)mem[i + 1] * stride];
+            const float v2 = col[(int64_t)mem[i + 2] * stride], v3 = col[(int64_t)mem[i + 3] * stride];
+            sum = __fadd_rn(sum, v0);
+            sum = __fadd_rn(sum, v1);
+            sum = __fadd_rn(sum, v2);
+            sum = __fadd_rn(sum, v3);
+        }
+        for (; i < cntc; i++) sum = __fadd_rn(sum, col[(int64_t)mem[i] * stride]);
+        if (reciprocal) cent[t] = __fmul_rn(sum, __fdiv_rn(1.0f, (float)cntc));
+        else cent[t] = __fdiv_rn(sum, (float)cntc);
+    } else {
+        // empty cluster: re-seed from a random sample (explicit RNG; iteration = completed updates)
+        const uint64_t tag = (tag_is_group ? (uint64_t)g : 0ull) ^ tag_xor;
+        const int64_t idx = rng_intn(seed, tag, (uint64_t)((int64_t)(iters[g] - 1) * K + c), n);
+        cent[t] = col[idx * stride];
+    }
+}
+
+struct Lloyd {
+    int G, K, ds;
+    int64_t n, stride, B;
+    DevBuf assign_new, assign_old, counts, totals, base, members, active, changed, iters, score, cnt;
+    vg_status init(int G_, int K_, int ds_, int64_t n_, int64_t stride_, cudaStream_t st) {
+        G = G_;
+        K = K_;
+        ds = ds_;
+        n = n_;
+        stride = stride_;
+        B = (n + kSB - 1) / kSB;
+        VG_TRY(assign_new.alloc((size_t)G * n * 4));
+        VG_TRY(assign_old.alloc((size_t)G * n * 4));
+        VG_TRY(counts.alloc((size_t)G * K * B * 4));
+        VG_TRY(totals.alloc((size_t)G * K * 4));
+        VG_TRY(base.alloc((size_t)G * K * 8));
+        VG_TRY(members.alloc((size_t)G * n * 4));
+        VG_TRY(active.alloc((size_t)G * 4));
+        VG_TRY(changed.alloc((size_t)G * 4));
+        VG_TRY(iters.alloc((size_t)G * 4));
+        VG_CUDA(cudaMemsetAsync(assign_old.p, 0, assign_old.bytes, st));
+        VG_CUDA(cudaMemsetAsync(changed.p, 0, changed.bytes, st));
+        VG_CUDA(cudaMemsetAsync(iters.p, 0, iters.bytes, st));
+        std::vector<int> ones((size_t)G, 1);
+        VG_CUDA(cudaMemcpyAsync(active.p, ones.data(), (size_t)G * 4, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        return VG_OK;
+    }
+    // assign_new must hold this pass's assignments.  Returns (via host) whether any group is still active.
+    vg_status step(const float *d_vecs, float *d_cent, int reciprocal, uint64_t seed, uint64_t tag_xor, int tag_is_group,
+                   bool *any_active, cudaStream_t st) {
+        dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
+        diff_assign_kernel<<<gd, 256, 0, st>>>(assign_new.as<uint32_t>(), assign_old.as<int32_t>(), n, G, active.as<int>(),
+                                               changed.as<int>());
+        VG_LAUNCHED();
+        settle_kernel<<<(G + 63) / 64, 64, 0, st>>>(active.as<int>(), changed.as<int>(), iters.as<int>(), G);
+        VG_LAUNCHED();
+        std::vector<int> h((size_t)G);
+        VG_CUDA(cudaMemcpyAsync(h.data(), active.p, (size_t)G * 4, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        bool any = false;
+        for (int v : h) any = any || v;
+        *any_active = any;
+        if (!any) return VG_OK;
+        dim3 gb((unsigned)B, (unsigned)G);
+        part_count_kernel<<<gb, 256, (size_t)K * 4, st>>>(assign_old.as<int32_t>(), n, K, B, active.as<int>(), counts.as<int>());
+        VG_LAUNCHED();
+        part_scan_kernel<<<(unsigned)(((int64_t)G * K + 255) / 256), 256, 0, st>>>(counts.as<int>(), K, B, G, active.as<int>(),
+                                                                                  totals.as<int>());
+        VG_LAUNCHED();
+        part_base_kernel<<<(G + 63) / 64, 64, 0, st>>>(totals.as<int>(), K, G, active.as<int>(), n, base.as<int64_t>());
+        VG_LAUNCHED();
+        part_scatter_kernel<<<gb, 256, 0, st>>>(assign_old.as<int32_t>(), n, K, B, active.as<int>(), counts.as<int>(),
+                                                base.as<int64_t>(), members.as<uint32_t>());
+        VG_LAUNCHED();
+        const int64_t chains = (int64_t)G * K * ds;
+        centroid_update_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(
+            d_vecs, n, stride, ds, K, G, active.as<int>(), totals.as<int>(), base.as<int64_t>(), members.as<uint32_t>(), reciprocal,
+            seed, tag_xor, tag_is_group, iters.as<int>(), d_cent);
+        VG_LAUNCHED();
+        return VG_OK;
+    }
+};
+
+// ---------------------------------------------------------------- public device API
+vg_status dev_find_closest(const float *d_queries, int64_t nq, int64_t dim, const float *d_centroids, int64_t k, int64_t np,
+                           int metric, int32_t *d_out, cudaStream_t st) {
+    if (np > k) np = k;
+    CodecParams cp;
+    cp.codec = VG_CODEC_F32;
+    cp.variant = VG_VAR_BATCH;
+    cp.dim = dim;
+    cp.vectors = d_centroids;
+    DevBuf sc, cnt;
+    VG_TRY(sc.alloc((size_t)nq * np * 4));
+    VG_TRY(cnt.alloc((size_t)nq * 4));
+    ScanArgs a;
+    a.queries = d_queries;
+    a.nq = nq;
+    a.rows = k;
+    a.k = (int)np;
+    a.descending = metric != VG_METRIC_L2;
+    a.is_dot = metric != VG_METRIC_L2;
+    a.out_rows = reinterpret_cast<uint32_t *>(d_out);
+    a.out_scores = sc.as<float>();
+    a.out_counts = cnt.as<int32_t>();
+    VG_TRY(scan_topk(cp, a, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    return VG_OK;
+}
+
+// ---------------------------------------------------------------- k-means++ (pq.go:281-345)
+__global__ void __launch_bounds__(256) gather_centroid_kernel(const float *vecs, int64_t stride, int ds, int K, int G, int c,
+                                                              const int64_t *chosen, float *cent) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= G * ds) return;
+    const int g = t / ds, j = t % ds;
+    cent[((int64_t)g * K + c) * ds + j] = vecs[chosen[g] * stride + (int64_t)g * ds + j];
+}
+__global__ void __launch_bounds__(256) pp_dist_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int c,
+                                                      const float *cent, const int *zero, float *mind /*[G][n]*/) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (i >= n) return;
+    if (c > 0 && zero[g]) return;  // `sum == 0` branch: no distance update (pq.go:306-310)
+    const float d = sql2_pair_thread(vecs + i * stride + (int64_t)g * ds, cent + ((int64_t)g * K + c) * ds, ds);
+    float *m = mind + (int64_t)g * n + i;
+    if (c == 0 || d < *m) *m = d;
+}
+// One warp per group.  Lane 0 owns the two sequential float32 chains (sum, then the
+// cumulative search); the warp streams mind[] through shared memory for it.
+__global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t n, int c, uint64_t seed, int *zero,
+                                                     int64_t *chosen) {
+    __shared__ float buf[1024];
+    const int g = blockIdx.x, lane = threadIdx.x;
+    const float *m = mind + (int64_t)g * n;
+    float sum = 0.0f;
+    for (int64_t b = 0; b < n; b += 1024) {
+        for (int j = lane; j < 1024; j += 32) buf[j] = (b + j < n) ? m[b + j] : 0.0f;
+        __syncwarp();
+        if (lane == 0) {
+            const int cnt = (int)((n - b < 1024) ? (n - b) : 1024);
+            for (int j = 0; j < cnt; j++) sum = __fadd_rn(sum, buf[j]);
+        }
+        __syncwarp();
+    }
+    sum = __shfl_sync(0xffffffffu, sum, 0);
+    if (sum == 0.0f) {
+        if (lane == 0) {
+            zero[g] = 1;
+            chosen[g] = rng_intn(seed, (uint64_t)g, (uint64_t)c, n);
+        }
+        return;
+    }
+    const float target = __fmul_rn(rng_f32(seed, (uint64_t)g, (uint64_t)c), sum);
+    float cum = 0.0f;
+    int64_t pick = 0;
+    int found = 0;
+    for (int64_t b = 0; b < n && !found; b += 1024) {
+        for (int j = lane; j < 1024; j += 32) buf[j] = (b + j < n) ? m[b + j] : 0.0f;
+        __syncwarp();
+        if (lane == 0) {
+            const int cnt = (int)((n - b < 1024) ? (n - b) : 1024);
+            for (int j = 0; j < cnt; j++) {
+                cum = __fadd_rn(cum, buf[j]);
+                if (cum >= target) {
+                    pick = b + j;
+                    found = 1;
+                    break;
+                }
+            }
+        }
+        found = __shfl_sync(0xffffffffu, found, 0);
+    }
+    if (lane == 0) {
+        zero[g] = 0;
+        chosen[g] = pick;
+    }
+}
+__global__ void pp_first_kernel(int64_t n, uint64_t seed, int G, int64_t *chosen, int *zero) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= G) return;
+    chosen[g] = rng_intn(seed, (uint64_t)g, 0, n);
+    zero[g] = 0;
+}
+__global__ void __launch_bounds__(256) pp_small_init_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int G,
+                                                            float *cent) {
+    // len(vectors) < k: centroid i = vectors[i % n] (pq.go:285-290)
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (int64_t)G * K * ds) return;
+    const int j = (int)(t % ds);
+    const int64_t gc = t / ds;
+    const int g = (int)(gc / K), c = (int)(gc % K);
+    cent[t] = vecs[(int64_t)(c % n) * stride + (int64_t)g * ds + j];
+}
+
+// Train (pq.go:98-136): float32 centroids of one subspace → int8 + scale/offset. One CTA per subspace.
+__global__ void __launch_bounds__(256) pq_quantize_kernel(const float *cent, int count, int8_t *out, float *scales, float *offsets) {
+    __shared__ float smin[256], smax[256];
+    const int g = blockIdx.x;
+    const float *c = cent + (int64_t)g * count;
+    float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const float v = c[i];
+        if (v < mn) mn = v;
+        if (v > mx) mx = v;
+    }
+    smin[threadIdx.x] = mn;
+    smax[threadIdx.x] = mx;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            if (smin[threadIdx.x + o] < smin[threadIdx.x]) smin[threadIdx.x] = smin[threadIdx.x + o];
+            if (smax[threadIdx.x + o] > smax[threadIdx.x]) smax[threadIdx.x] = smax[threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    mn = smin[0];
+    mx = smax[0];
+    if (mx == mn) mx = __fadd_rn(mn, 1e-6f);
+    const float scale = __fdiv_rn(__fsub_rn(mx, mn), 255.0f);
+    const float offset = __fadd_rn(mn, __fmul_rn(128.0f, scale));
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        const float r = __fdiv_rn(__fsub_rn(c[i], mn), scale);
+        int val = (int)round((double)r);
+        if (val < 0) val = 0;
+        if (val > 255) val = 255;
+        out[(int64_t)g * count + i] = (int8_t)(val - 128);
+    }
+    if (threadIdx.x == 0) {
+        scales[g] = scale;
+        offsets[g] = offset;
+    }
+}
+
+template <int DS>
+static vg_status launch_small_assign(const float *d_vecs, int64_t n, int64_t dim, int G, int K, const float *d_cent,
+                                     uint32_t *d_assign, cudaStream_t st) {
+    dim3 grid((unsigned)((n + 255) / 256), (unsigned)G);
+    pq_assign_small_kernel<DS><<<grid, 256, (size_t)K * DS * 4, st>>>(d_vecs, n, dim, K, d_cent, d_assign);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+static vg_status pq_assign_all(const float *d_vecs, int64_t n, int64_t dim, int G, int K, int ds, const float *d_cent,
+                               uint32_t *d_assign, DevBuf &score, DevBuf &cnt, cudaStream_t st) {
+    switch (ds) {
+        case 2: return launch_small_assign<2>(d_vecs, n, dim, G, K, d_cent, d_assign, st);
+        case 4: return launch_small_assign<4>(d_vecs, n, dim, G, K, d_cent, d_assign, st);
+        case 8: return launch_small_assign<8>(d_vecs, n, dim, G, K, d_cent, d_assign, st);
+        case 16: return launch_small_assign<16>(d_vecs, n, dim, G, K, d_cent, d_assign, st);
+        case 32: return launch_small_assign<32>(d_vecs, n, dim, G, K, d_cent, d_assign, st);
+        default: break;
+    }
+    if (!score.p) VG_TRY(score.alloc((size_t)n * 4));
+    if (!cnt.p) VG_TRY(cnt.alloc((size_t)n * 4));
+    for (int g = 0; g < G; g++)
+        VG_TRY(assign_generic(d_vecs + (int64_t)g * ds, n, dim, ds, d_cent + (int64_t)g * K * ds, K, VG_VAR_PAIR, 0,
+                              d_assign + (int64_t)g * n, score.as<float>(), cnt.as<int32_t>(), st));
+    return VG_OK;
+}
+
+}  // namespace vg
+
+using namespace vg;
+
+extern "C" {
+
+vg_status vg_kmeans_find_closest(const float *h_queries, int64_t nq, int64_t dim, const float *h_centroids, int64_t k,
+                                 int64_t nprobe, int32_t metric, int32_t *h_out) {
+    VG_TRY(ensure_init());
+    if (nq <= 0) return VG_OK;
+    if (k <= 0 || dim <= 0 || nprobe <= 0) return fail(VG_ERR_INVALID, "bad shape");
+    if (nprobe > k) nprobe = k;
+    DevBuf q, c, out;
+    VG_TRY(q.alloc((size_t)nq * dim * 4));
+    VG_TRY(staged_h2d(q.p, h_queries, (size_t)nq * dim * 4));
+    VG_TRY(c.alloc((size_t)k * dim * 4));
+    VG_TRY(staged_h2d(c.p, h_centroids, (size_t)k * dim * 4));
+    VG_TRY(out.alloc((size_t)nq * nprobe * 4));
+    VG_TRY(dev_find_closest(q.as<float>(), nq, dim, c.as<float>(), k, nprobe, metric, out.as<int32_t>(), stream()));
+    return staged_d2h(h_out, out.p, (size_t)nq * nprobe * 4);
+}
+
+vg_status vg_kmeans_assign(const float *h_vecs, int64_t n, int64_t dim, const float *h_centroids, int64_t k, int32_t metric,
+                           int32_t *h_assign) {
+    return vg_kmeans_find_closest(h_vecs, n, dim, h_centroids, k, 1, metric, h_assign);
+}
+
+vg_status vg_kmeans_train(const float *h_vecs, int64_t n, int64_t dim, int64_t k, int32_t metric, int64_t max_iter,
+                          const int64_t *h_init_rows, uint64_t seed, float *h_centroids, int32_t *h_assign, int64_t *iters_run) {
+    VG_TRY(ensure_init());
+    if (dim <= 0 || k <= 0) return fail(VG_ERR_INVALID, "bad shape");
+    if (n < k) return fail(VG_ERR_INVALID, "not enough vectors to cluster (n < k)");  // Go returns (nil, nil)
+    if (metric != VG_METRIC_L2 && metric != VG_METRIC_COSINE && metric != VG_METRIC_DOT)
+        return fail(VG_ERR_UNSUPPORTED, "unsupported metric for float32");
+    cudaStream_t st = stream();
+    DevBuf v, cent, score, cnt;
+    VG_TRY(v.alloc((size_t)n * dim * 4));
+    VG_TRY(staged_h2d(v.p, h_vecs, (size_t)n * dim * 4));
+    VG_TRY(cent.alloc((size_t)k * dim * 4));
+    for (int64_t i = 0; i < k; i++) {
+        if (h_init_rows[i] < 0 || h_init_rows[i] >= n) return fail(VG_ERR_INVALID, "init row out of range");
+        VG_CUDA(cudaMemcpyAsync(cent.as<float>() + i * dim, v.as<float>() + h_init_rows[i] * dim, (size_t)dim * 4,
+                                cudaMemcpyDeviceToDevice, st));
+    }
+    VG_TRY(score.alloc((size_t)n * 4));
+    VG_TRY(cnt.alloc((size_t)n * 4));
+    Lloyd L;
+    VG_TRY(L.init(1, (int)k, (int)dim, n, dim, st));
+    const int is_dot = metric != VG_METRIC_L2;
+    int64_t it = 0;
+    for (; it < max_iter; it++) {
+        VG_TRY(assign_generic(v.as<float>(), n, dim, dim, cent.as<float>(), k, VG_VAR_BATCH, is_dot, L.assign_new.as<uint32_t>(),
+                              score.as<float>(), cnt.as<int32_t>(), st));
+        bool any = false;
+        VG_TRY(L.step(v.as<float>(), cent.as<float>(), 1, seed, 0xE0E0E0E0ull, 0, &any, st));
+        if (!any) break;
+    }
+    VG_CUDA(cudaStreamSynchronize(st));
+    if (iters_run) *iters_run = it;
+    VG_TRY(staged_d2h(h_centroids, cent.p, (size_t)k * dim * 4));
+    if (h_assign) VG_TRY(staged_d2h(h_assign, L.assign_old.p, (size_t)n * 4));
+    return VG_OK;
+}
+
+vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
+                      int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
+    if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");
+    cudaStream_t st = stream();
+    const int G = (int)m, K = (int)k, ds = (int)(dim / m);
+    DevBuf v, cent, mind, zero, chosen, score, cnt, cb, sc, of;
+    VG_TRY(v.alloc((size_t)n * dim * 4));
+    VG_TRY(staged_h2d(v.p, h_vecs, (size_t)n * dim * 4));
+    VG_TRY(cent.alloc((size_t)G * K * ds * 4));
+    // ---- initializeCentroids
+    if (n < k) {
+        const int64_t t = (int64_t)G * K * ds;
+        pp_small_init_kernel<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(v.as<float>(), n, dim, ds, K, G, cent.as<float>());
+        VG_LAUNCHED();
+    } else {
+        VG_TRY(mind.alloc((size_t)G * n * 4));
+        VG_TRY(zero.alloc((size_t)G * 4));
+        VG_TRY(chosen.alloc((size_t)G * 8));
+        pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
+        VG_LAUNCHED();
+        dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
+        for (int c = 0; c < K; c++) {
+            if (c > 0) {
+                pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>());
+                VG_LAUNCHED();
+            }
+            gather_centroid_kernel<<<(G * ds + 255) / 256, 256, 0, st>>>(v.as<float>(), dim, ds, K, G, c, chosen.as<int64_t>(),
+                                                                       cent.as<float>());
+            VG_LAUNCHED();
+            if (c + 1 < K) {
+                pp_dist_kernel<<<gd, 256, 0, st>>>(v.as<float>(), n, dim, ds, K, c, cent.as<float>(), zero.as<int>(), mind.as<float>());
+                VG_LAUNCHED();
+            }
+        }
+    }
+    // ---- runKMeansIterations
+    Lloyd L;
+    VG_TRY(L.init(G, K, ds, n, dim, st));
+    for (int64_t it = 0; it < iters; it++) {
+        VG_TRY(pq_assign_all(v.as<float>(), n, dim, G, K, ds, cent.as<float>(), L.assign_new.as<uint32_t>(), score, cnt, st));
+        bool any = false;
+        VG_TRY(L.step(v.as<float>(), cent.as<float>(), 0, seed, 0xE0E0E0E0ull, 1, &any, st));
+        if (!any) break;
+    }
+    // ---- int8 codebooks
+    VG_TRY(cb.alloc((size_t)G * K * ds));
+    VG_TRY(sc.alloc((size_t)G * 4));
+    VG_TRY(of.alloc((size_t)G * 4));
+    pq_quantize_kernel<<<G, 256, 0, st>>>(cent.as<float>(), K * ds, cb.as<int8_t>(), sc.as<float>(), of.as<float>());
+    VG_LAUNCHED();
+    VG_CUDA(cudaStreamSynchronize(st));
+    VG_TRY(staged_d2h(h_codebooks, cb.p, (size_t)G * K * ds));
+    VG_TRY(staged_d2h(h_scales, sc.p, (size_t)G * 4));
+    VG_TRY(staged_d2h(h_offsets, of.p, (size_t)G * 4));
+    if (h_centroids_f32) VG_TRY(staged_d2h(h_centroids_f32, cent.p, (size_t)G * K * ds * 4));
+    return VG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,9 @@
+// vg_kmeans.cuh — device entry points of vg_kmeans.cu.
+#pragma once
+#include "vg_common.cuh"
+
+namespace vg {
+// kmeans.FindClosestCentroids: out[q][0..np) = partition ids by (distance asc | dot desc, id asc).
+vg_status dev_find_closest(const float *d_queries, int64_t nq, int64_t dim, const float *d_centroids, int64_t k, int64_t np,
+                           int metric, int32_t *d_out, cudaStream_t st);
+}  // namespace vg

@@ -1,0 +1,1103 @@
+// vg_scan.cu — the scan kernels: exact Flat L2/dot, SQ8, INT4, PQ-ADC, BQ and
+// RaBitQ distance evaluation fused with the shared-memory bounded top-k.
+//
+// Thread model.  The reference's AVX-512 kernels keep 16 float lanes per
+// accumulator and finish with _mm512_reduce_add_ps.  Here a HALF-WARP is one
+// zmm register: lane l of the half-warp owns AVX lane l, walks the dimensions
+// d = 16*t + l in the same order, and the 16 partial sums are combined with
+// reduce16() in the same tree order, so every float32 distance is
+// bit-identical to the reference's.  Each half-warp
+// register-tiles R rows x QH queries, so a code byte / vector element fetched
+// once is reused for all queries of the CTA's query tile.
+//
+// Grid.  blockIdx.x = query tile (QT queries whose top-k state lives in this
+// CTA's shared memory for the whole sweep), blockIdx.y = row split (only when
+// there are too few query tiles to fill 148 SMs; partials are merged by
+// merge_keys_kernel).  All CTAs sweep rows in the same direction, so code
+// tiles are served from the 126 MB L2 after the first CTA touched them.
+#include "vg_scan.cuh"
+
+namespace vg {
+
+// ============================================================ sinks
+struct SinkTopK {
+    TopK tk;
+    const uint8_t *mask;
+    const int32_t *probe;
+    const uint32_t *part_off;
+    int nprobe, trigger, q0;
+    uint32_t row_base;
+    bool descending;
+    __device__ __forceinline__ void operator()(int slot, int64_t row, float score) const {
+        if (mask && !((mask[row >> 3] >> (row & 7)) & 1)) return;
+        if (probe) {
+            const int32_t *pp = probe + (int64_t)(q0 + slot) * nprobe;
+            bool ok = false;
+            for (int j = 0; j < nprobe; j++) {
+                const int p = pp[j];
+                if (p >= 0 && row >= part_off[p] && row < part_off[p + 1]) ok = true;
+            }
+            if (!ok) return;
+        }
+        topk_offer(tk, slot, make_key(score, row_base + (uint32_t)row, descending), trigger);
+    }
+};
+struct SinkDense {
+    float *out;
+    int64_t n;
+    int q0;
+    __device__ __forceinline__ void operator()(int slot, int64_t row, float score) const {
+        out[(int64_t)(q0 + slot) * n + row] = score;
+    }
+};
+
+// ============================================================ codec: F32
+// simd.SquaredL2 / simd.Dot (floats_avx512.c:12-129) and the Batch variants
+// (batch_avx512.c:19-143).
+template <bool BATCH>
+struct CodecF32 {
+    static constexpr int QT = 4, R = 2, THREADS = 256, RB = 16 * R, MINB = 2;
+    static size_t qsmem(const CodecParams &P) { return (size_t)QT * P.dim * 4; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        float *qs = reinterpret_cast<float *>(sm);
+        const int64_t dim = P.dim;
+        for (int64_t i = tid; i < (int64_t)QT * dim; i += THREADS) {
+            int q = (int)(i / dim);
+            int64_t d = i - (int64_t)q * dim;
+            qs[i] = (q < nqv) ? queries[(int64_t)(q0 + q) * qs_ + d] : 0.0f;
+        }
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool is_dot, const unsigned char *sm, int64_t base, int64_t row_end,
+                                int nqv, int tid, const Sink &sink) {
+        const float *qs = reinterpret_cast<const float *>(sm);
+        const int hw = tid >> 4, lane = tid & 15;
+        const int64_t dim = P.dim;
+        const int64_t r0 = base + (int64_t)hw * R;
+        const float *x[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t rr = r0 + r;
+            if (rr > row_end - 1) rr = row_end - 1;
+            x[r] = P.vectors + rr * dim;
+        }
+        float acc[R][QT][4];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[r][q][j] = 0.0f;
+        const int64_t epochs = dim >> 6;
+        for (int64_t e = 0; e < epochs; e++) {
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int64_t d = e * 64 + j * 16 + lane;
+                float xv[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) xv[r] = __ldg(x[r] + d);
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    const float qv = qs[(int64_t)q * dim + d];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        if (is_dot) {
+                            acc[r][q][j] = __fmaf_rn(qv, xv[r], acc[r][q][j]);
+                        } else {
+                            const float df = __fsub_rn(qv, xv[r]);
+                            acc[r][q][j] = __fmaf_rn(df, df, acc[r][q][j]);
+                        }
+                    }
+                }
+            }
+        }
+        int64_t done = epochs * 64;
+        float c[R][QT];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++)
+                c[r][q] = __fadd_rn(__fadd_rn(acc[r][q][0], acc[r][q][1]), __fadd_rn(acc[r][q][2], acc[r][q][3]));
+        if (BATCH) {
+            for (; done + 16 <= dim; done += 16) {
+                const int64_t d = done + lane;
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float xv = __ldg(x[r] + d);
+#pragma unroll
+                    for (int q = 0; q < QT; q++) {
+                        const float qv = qs[(int64_t)q * dim + d];
+                        if (is_dot) {
+                            c[r][q] = __fmaf_rn(qv, xv, c[r][q]);
+                        } else {
+                            const float df = __fsub_rn(qv, xv);
+                            c[r][q] = __fmaf_rn(df, df, c[r][q]);
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) c[r][q] = reduce16(c[r][q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r0 + r >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    if (q >= nqv) continue;
+                    float tot = c[r][q];
+                    for (int64_t d = done; d < dim; d++) {  // scalar tail, FMA-contracted in the shipped asm
+                        const float qv = qs[(int64_t)q * dim + d], xv = __ldg(x[r] + d);
+                        if (is_dot) {
+                            tot = __fmaf_rn(qv, xv, tot);
+                        } else {
+                            const float df = __fsub_rn(qv, xv);
+                            tot = __fmaf_rn(df, df, tot);
+                        }
+                    }
+                    sink(q, r0 + r, tot);
+                }
+            }
+        }
+    }
+};
+
+// ============================================================ codec: SQ8
+// simd.Sq8uL2BatchPerDimension (sq8_avx512.c:59-104): one 16-lane accumulator,
+// rec = fma(float(c), invScale, min); diff = q - rec; acc = fma(diff, diff, acc).
+// Natural (row-major) device layout; any dim.
+struct CodecSQ8 {
+    static constexpr int QT = 8, R = 4, THREADS = 256, RB = 16 * R, MINB = 2;
+    static size_t qsmem(const CodecParams &P) { return (size_t)(QT + 2) * P.dim * 4; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        float *qs = reinterpret_cast<float *>(sm);
+        const int64_t dim = P.dim;
+        for (int64_t i = tid; i < (int64_t)QT * dim; i += THREADS) {
+            int q = (int)(i / dim);
+            int64_t d = i - (int64_t)q * dim;
+            qs[i] = (q < nqv) ? queries[(int64_t)(q0 + q) * qs_ + d] : 0.0f;
+        }
+        float *mn = qs + (int64_t)QT * dim, *iv = mn + dim;
+        for (int64_t d = tid; d < dim; d += THREADS) {
+            mn[d] = P.p0[d];
+            iv[d] = P.p1[d];
+        }
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const float *qs = reinterpret_cast<const float *>(sm);
+        const int64_t dim = P.dim;
+        const float *mn = qs + (int64_t)QT * dim, *iv = mn + dim;
+        const int hw = tid >> 4, lane = tid & 15;
+        const int64_t r0 = base + (int64_t)hw * R;
+        const uint8_t *code[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t rr = r0 + r;
+            if (rr > row_end - 1) rr = row_end - 1;
+            code[r] = P.codes + rr * P.row_bytes;
+        }
+        float acc[R][QT];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) acc[r][q] = 0.0f;
+        int64_t j = 0;
+        for (; j + 16 <= dim; j += 16) {
+            const int64_t d = j + lane;
+            const float m = mn[d], s = iv[d];
+            float rec[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) rec[r] = __fmaf_rn(u8_to_f32(__ldg(code[r] + d)), s, m);
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                const float qv = qs[(int64_t)q * dim + d];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float df = __fsub_rn(qv, rec[r]);
+                    acc[r][q] = __fmaf_rn(df, df, acc[r][q]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) acc[r][q] = reduce16(acc[r][q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r0 + r >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    if (q >= nqv) continue;
+                    float tot = acc[r][q];
+                    for (int64_t d = j; d < dim; d++) {
+                        const float rec = __fmaf_rn(u8_to_f32(__ldg(code[r] + d)), iv[d], mn[d]);
+                        const float df = __fsub_rn(qs[(int64_t)q * dim + d], rec);
+                        tot = __fmaf_rn(df, df, tot);
+                    }
+                    sink(q, r0 + r, tot);
+                }
+            }
+        }
+    }
+};
+
+// SQ8 fast path: dim % (16*VB) == 0 and codes stored lane-transposed on device
+// (upload kernel permute_sq8): inside every block of 16*VB dims the byte of
+// (step s, lane l) sits at l*VB + s, so lane l fetches VB consecutive steps
+// with one VB-byte load and the half-warp's 16 loads cover 16*VB contiguous
+// bytes.  Queries / mins / invScales are staged lane-major [16][SP] (SP = steps
+// padded to 4*odd, which makes the float4 reads of 8 lanes hit 32 distinct
+// banks); both half-warps of a warp read identical query words (broadcast).
+template <int VB>
+struct CodecSQ8Perm {
+    static constexpr int QT = 8, R = 4, THREADS = 256, RB = 16 * R, MINB = 2;
+    __host__ __device__ static int steps_padded(int64_t dim) {
+        int s = (int)(dim / 16);
+        int sp = (s + 3) & ~3;
+        if (((sp >> 2) & 1) == 0) sp += 4;
+        return sp;
+    }
+    static size_t qsmem(const CodecParams &P) { return (size_t)(QT + 2) * 16 * steps_padded(P.dim) * 4; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        float *qs = reinterpret_cast<float *>(sm);
+        const int64_t dim = P.dim;
+        const int SP = steps_padded(dim);
+        for (int64_t i = tid; i < (int64_t)QT * dim; i += THREADS) {
+            int q = (int)(i / dim);
+            int d = (int)(i - (int64_t)q * dim);
+            qs[((int64_t)q * 16 + (d & 15)) * SP + (d >> 4)] = (q < nqv) ? queries[(int64_t)(q0 + q) * qs_ + d] : 0.0f;
+        }
+        float *mn = qs + (int64_t)QT * 16 * SP, *iv = mn + 16 * SP;
+        for (int d = tid; d < dim; d += THREADS) {
+            mn[(d & 15) * SP + (d >> 4)] = P.p0[d];
+            iv[(d & 15) * SP + (d >> 4)] = P.p1[d];
+        }
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const int64_t dim = P.dim;
+        const int SP = steps_padded(dim);
+        const float *qs = reinterpret_cast<const float *>(sm);
+        const float *mn = qs + (int64_t)QT * 16 * SP, *iv = mn + 16 * SP;
+        const int hw = tid >> 4, lane = tid & 15;
+        const int64_t r0 = base + (int64_t)hw * R;
+        const uint8_t *code[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t rr = r0 + r;
+            if (rr > row_end - 1) rr = row_end - 1;
+            code[r] = P.codes + rr * P.row_bytes + lane * VB;
+        }
+        float acc[R][QT];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) acc[r][q] = 0.0f;
+        const float *mnl = mn + lane * SP, *ivl = iv + lane * SP;
+        const float *ql = qs + lane * SP;
+        const int nblk = (int)(dim / (16 * VB));
+        for (int b = 0; b < nblk; b++) {
+            uint32_t w[R][VB / 4];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if constexpr (VB == 16) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(code[r] + (int64_t)b * 16 * VB));
+                    w[r][0] = v.x;
+                    w[r][1] = v.y;
+                    w[r][2] = v.z;
+                    w[r][3] = v.w;
+                } else {
+                    w[r][0] = __ldg(reinterpret_cast<const uint32_t *>(code[r] + (int64_t)b * 16 * VB));
+                }
+            }
+#pragma unroll
+            for (int s4 = 0; s4 < VB / 4; s4++) {
+                const int t0 = b * VB + s4 * 4;
+                const float4 m4 = *reinterpret_cast<const float4 *>(mnl + t0);
+                const float4 i4 = *reinterpret_cast<const float4 *>(ivl + t0);
+                const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float ii[4] = {i4.x, i4.y, i4.z, i4.w};
+                float rec[R][4];
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        // byte -> float via 0x4B000000|b = 8388608+b (exact), minus 8388608 (exact)
+                        const float f = __fsub_rn(__uint_as_float(__byte_perm(w[r][s4], 0x4B000000u, 0x7650 + i)), 8388608.0f);
+                        rec[r][i] = __fmaf_rn(f, ii[i], mm[i]);
+                    }
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    const float4 q4 = *reinterpret_cast<const float4 *>(ql + (int64_t)q * 16 * SP + t0);
+                    const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float df = __fsub_rn(qq[i], rec[r][i]);
+                            acc[r][q] = __fmaf_rn(df, df, acc[r][q]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) acc[r][q] = reduce16(acc[r][q]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r0 + r >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < QT; q++)
+                    if (q < nqv) sink(q, r0 + r, acc[r][q]);
+            }
+        }
+    }
+};
+
+// SQ8 through the scalar Go loops (quantizer.go:78-91,109-119): sequential,
+// unfused.  flat.Search uses these for SQ8 segments whose metric is not L2.
+// One thread per row (the sum is one dependent chain).
+struct CodecSQ8Go {
+    static constexpr int QT = 4, R = 1, THREADS = 256, RB = THREADS, MINB = 2;
+    static size_t qsmem(const CodecParams &P) { return CodecSQ8::qsmem(P); }  // shares CodecSQ8's 8-slot layout
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        CodecSQ8::stage(P, queries, qs_, q0, nqv, sm, tid);
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool is_dot, const unsigned char *sm, int64_t base, int64_t row_end,
+                                int nqv, int tid, const Sink &sink) {
+        const float *qs = reinterpret_cast<const float *>(sm);
+        const int64_t dim = P.dim;
+        const float *mn = qs + (int64_t)8 * dim, *iv = mn + dim;  // CodecSQ8::stage layout (QT = 8 slots)
+        const int64_t row = base + tid;
+        if (row >= row_end) return;
+        const uint8_t *code = P.codes + row * P.row_bytes;
+        float acc[QT];
+#pragma unroll
+        for (int q = 0; q < QT; q++) acc[q] = 0.0f;
+        for (int64_t d = 0; d < dim; d++) {
+            const float val = __fadd_rn(mn[d], __fmul_rn(u8_to_f32(__ldg(code + d)), iv[d]));
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                const float qv = qs[(int64_t)q * dim + d];
+                if (is_dot) {
+                    acc[q] = __fadd_rn(acc[q], __fmul_rn(qv, val));
+                } else {
+                    const float df = __fsub_rn(qv, val);
+                    acc[q] = __fadd_rn(acc[q], __fmul_rn(df, df));
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < QT; q++)
+            if (q < nqv) sink(q, row, acc[q]);
+    }
+};
+
+// ============================================================ codec: INT4
+// simd.Int4L2DistanceBatch (int4_avx512.c:193-299).  High nibble = even dim.
+__device__ __forceinline__ float int4_nibble(const uint8_t *code, int64_t d) {
+    const uint32_t b = __ldg(code + (d >> 1));
+    return u8_to_f32((d & 1) ? (b & 0x0Fu) : (b >> 4));
+}
+struct CodecINT4 {
+    static constexpr int QT = 8, R = 2, THREADS = 256, RB = 16 * R, MINB = 2;
+    static size_t qsmem(const CodecParams &P) { return (size_t)(QT + 2) * P.dim * 4; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        CodecSQ8::stage(P, queries, qs_, q0, nqv, sm, tid);  // same layout: queries | p0 (min) | p1 (diff)
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const float k15 = __uint_as_float(0x3d888889u);
+        const float *qs = reinterpret_cast<const float *>(sm);
+        const int64_t dim = P.dim;
+        const float *mn = qs + (int64_t)QT * dim, *df_ = mn + dim;
+        const int hw = tid >> 4, lane = tid & 15;
+        const int64_t r0 = base + (int64_t)hw * R;
+        const uint8_t *code[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t rr = r0 + r;
+            if (rr > row_end - 1) rr = row_end - 1;
+            code[r] = P.codes + rr * P.row_bytes;
+        }
+        float s1[R][QT], s2[R][QT];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) s1[r][q] = s2[r][q] = 0.0f;
+        int64_t i = 0;
+        for (; i + 64 <= dim; i += 64) {
+#pragma unroll
+            for (int blk = 0; blk < 4; blk++) {
+                const int64_t d = i + blk * 16 + lane;
+                const float m = mn[d], dd = df_[d];
+                float deq[R];
+#pragma unroll
+                for (int r = 0; r < R; r++) deq[r] = __fmaf_rn(__fmul_rn(int4_nibble(code[r], d), k15), dd, m);
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    const float qv = qs[(int64_t)q * dim + d];
+#pragma unroll
+                    for (int r = 0; r < R; r++) {
+                        const float e = __fsub_rn(qv, deq[r]);
+                        if (blk < 2) s1[r][q] = __fmaf_rn(e, e, s1[r][q]);
+                        else s2[r][q] = __fmaf_rn(e, e, s2[r][q]);
+                    }
+                }
+            }
+        }
+        for (; i + 32 <= dim; i += 32) {
+#pragma unroll
+            for (int blk = 0; blk < 2; blk++) {
+                const int64_t d = i + blk * 16 + lane;
+                const float m = mn[d], dd = df_[d];
+#pragma unroll
+                for (int r = 0; r < R; r++) {
+                    const float deq = __fmaf_rn(__fmul_rn(int4_nibble(code[r], d), k15), dd, m);
+#pragma unroll
+                    for (int q = 0; q < QT; q++) {
+                        const float e = __fsub_rn(qs[(int64_t)q * dim + d], deq);
+                        s1[r][q] = __fmaf_rn(e, e, s1[r][q]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) s1[r][q] = reduce16(__fadd_rn(s1[r][q], s2[r][q]));
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r0 + r >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    if (q >= nqv) continue;
+                    float tot = s1[r][q];
+                    for (int64_t d = i; d < dim; d++) {
+                        const float deq = __fmaf_rn(__fmul_rn(int4_nibble(code[r], d), k15), df_[d], mn[d]);
+                        const float e = __fsub_rn(qs[(int64_t)q * dim + d], deq);
+                        tot = __fmaf_rn(e, e, tot);
+                    }
+                    sink(q, r0 + r, tot);
+                }
+            }
+        }
+    }
+};
+
+// INT4 fast path: dim % 256 == 0, codes lane-transposed on device
+// (permute_int4): inside each 128-byte block (256 dims = 4 epochs of 64) the
+// byte holding dims (64e + 16b + 2p, +1) of lane pair p sits at 16p + 4e + b,
+// so lanes 2p and 2p+1 read the same 16 bytes (one broadcast request) and get
+// their nibbles for 4 epochs x 4 blocks.
+struct CodecINT4Perm {
+    static constexpr int QT = 8, R = 2, THREADS = 256, RB = 16 * R, MINB = 2;
+    static size_t qsmem(const CodecParams &P) { return (size_t)(QT + 2) * 16 * CodecSQ8Perm<16>::steps_padded(P.dim) * 4; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        CodecSQ8Perm<16>::stage(P, queries, qs_, q0, nqv, sm, tid);
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const float k15 = __uint_as_float(0x3d888889u);
+        const int64_t dim = P.dim;
+        const int SP = CodecSQ8Perm<16>::steps_padded(dim);
+        const float *qs = reinterpret_cast<const float *>(sm);
+        const float *mn = qs + (int64_t)QT * 16 * SP, *dfp = mn + 16 * SP;
+        const int hw = tid >> 4, lane = tid & 15;
+        const int64_t r0 = base + (int64_t)hw * R;
+        const uint8_t *code[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t rr = r0 + r;
+            if (rr > row_end - 1) rr = row_end - 1;
+            code[r] = P.codes + rr * P.row_bytes + (lane >> 1) * 16;
+        }
+        const int shift = (lane & 1) ? 0 : 4;  // even lane (even dim) = high nibble
+        float s1[R][QT], s2[R][QT];
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) s1[r][q] = s2[r][q] = 0.0f;
+        const float *mnl = mn + lane * SP, *dfl = dfp + lane * SP, *ql = qs + lane * SP;
+        const int nblk = (int)(dim / 256);
+        for (int b = 0; b < nblk; b++) {
+            uint32_t w[R][4];
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(code[r] + (int64_t)b * 128));
+                w[r][0] = v.x;
+                w[r][1] = v.y;
+                w[r][2] = v.z;
+                w[r][3] = v.w;
+            }
+#pragma unroll
+            for (int e = 0; e < 4; e++) {  // epoch e of this block: steps t0..t0+3 are blk 0..3
+                const int t0 = b * 16 + e * 4;
+                const float4 m4 = *reinterpret_cast<const float4 *>(mnl + t0);
+                const float4 d4 = *reinterpret_cast<const float4 *>(dfl + t0);
+                const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                float deq[R][4];
+#pragma unroll
+                for (int r = 0; r < R; r++)
+#pragma unroll
+                    for (int blk = 0; blk < 4; blk++) {
+                        const uint32_t nib = (w[r][e] >> (8 * blk + shift)) & 0xFu;
+                        const float f = __fsub_rn(__uint_as_float(0x4B000000u | nib), 8388608.0f);
+                        deq[r][blk] = __fmaf_rn(__fmul_rn(f, k15), dd[blk], mm[blk]);
+                    }
+#pragma unroll
+                for (int q = 0; q < QT; q++) {
+                    const float4 q4 = *reinterpret_cast<const float4 *>(ql + (int64_t)q * 16 * SP + t0);
+                    const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+                    for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+                        for (int r = 0; r < R; r++) {
+                            const float ee = __fsub_rn(qq[blk], deq[r][blk]);
+                            if (blk < 2) s1[r][q] = __fmaf_rn(ee, ee, s1[r][q]);
+                            else s2[r][q] = __fmaf_rn(ee, ee, s2[r][q]);
+                        }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++)
+#pragma unroll
+            for (int q = 0; q < QT; q++) s1[r][q] = reduce16(__fadd_rn(s1[r][q], s2[r][q]));
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r0 + r >= row_end) continue;
+#pragma unroll
+                for (int q = 0; q < QT; q++)
+                    if (q < nqv) sink(q, r0 + r, s1[r][q]);
+            }
+        }
+    }
+};
+
+// ============================================================ codec: PQ ADC
+// simd.PqAdcLookup (floats_avx512.c:135-167): lane l sums table[(16t+l)*256 +
+// code[16t+l]] over t in order, reduce, sequential tail.  The per-query table
+// is simd.BuildDistanceTableInt8 (kernels.go:354-374, the live generic path:
+// sequential, unfused) built INSIDE the kernel from the int8 codebooks — or
+// copied from caller-provided tables for the simd mirror.
+//
+// One CTA owns TWO queries; half-warp 0 of every warp serves query A, half-warp
+// 1 query B.  Table layout: word (t*256 + c)*32 + 16*half + lane, so the 32
+// lanes of any lookup instruction hit 32 distinct banks whatever the codes are.
+struct CodecPQ {
+    static constexpr int QT = 2, R = 4, THREADS = 256, RB = (THREADS / 32) * R, MINB = 1;
+    static size_t qsmem(const CodecParams &P) {
+        const int t16 = P.pq_m / 16, tail = P.pq_m % 16;
+        return ((size_t)t16 * 256 * 32 + (size_t)QT * tail * 256) * 4;
+    }
+    __device__ static float entry(const CodecParams &P, const float *query, int m, int c) {
+        const int ds = P.pq_dsub;
+        const int8_t *cb = P.pq_codebooks + ((int64_t)m * P.pq_k + c) * ds;
+        const float scale = P.pq_scales[m], offset = P.pq_offsets[m];
+        const float *qv = query + (int64_t)m * ds;
+        float sum = 0.0f;
+        for (int i = 0; i < ds; i++) {
+            const float v = __fadd_rn(__fmul_rn((float)cb[i], scale), offset);
+            const float d = __fsub_rn(qv[i], v);
+            sum = __fadd_rn(sum, __fmul_rn(d, d));
+        }
+        return sum;
+    }
+    // `queries`: float vectors [nq][dim] (tables built here) or, when P.pq_tables is set, ignored.
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        float *lut = reinterpret_cast<float *>(sm);
+        const int M = P.pq_m, t16 = M / 16, tail = M % 16;
+        float *tl = lut + (int64_t)t16 * 256 * 32;
+        for (int idx = tid; idx < M * 256; idx += THREADS) {
+            const int m = idx >> 8, c = idx & 255;
+#pragma unroll
+            for (int h = 0; h < QT; h++) {
+                float v = 0.0f;
+                if (h < nqv) {
+                    if (P.pq_tables) v = P.pq_tables[(int64_t)(q0 + h) * M * 256 + idx];
+                    else v = entry(P, queries + (int64_t)(q0 + h) * qs_, m, c);
+                }
+                if (m < t16 * 16) lut[((int64_t)(m >> 4) * 256 + c) * 32 + 16 * h + (m & 15)] = v;
+                else tl[((int64_t)h * tail + (m - t16 * 16)) * 256 + c] = v;
+            }
+        }
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const float *lut = reinterpret_cast<const float *>(sm);
+        const int M = P.pq_m, t16 = M / 16, tail = M % 16;
+        const float *tl = lut + (int64_t)t16 * 256 * 32;
+        const int warp = tid >> 5, half = (tid >> 4) & 1, lane = tid & 15;
+        const int64_t r0 = base + (int64_t)warp * R;
+        const uint8_t *code[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+            int64_t rr = r0 + r;
+            if (rr > row_end - 1) rr = row_end - 1;
+            code[r] = P.codes + rr * P.row_bytes;
+        }
+        float s[R];
+#pragma unroll
+        for (int r = 0; r < R; r++) s[r] = 0.0f;
+        const float *lane_lut = lut + 16 * half + lane;
+        for (int t = 0; t < t16; t++) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                const uint32_t c = __ldg(code[r] + t * 16 + lane);
+                s[r] = __fadd_rn(s[r], lane_lut[((int64_t)t * 256 + c) * 32]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; r++) s[r] = reduce16(s[r]);
+        if (lane == 0 && half < nqv) {
+#pragma unroll
+            for (int r = 0; r < R; r++) {
+                if (r0 + r >= row_end) continue;
+                float tot = s[r];
+                for (int m = 0; m < tail; m++)
+                    tot = __fadd_rn(tot, tl[((int64_t)half * tail + m) * 256 + __ldg(code[r] + t16 * 16 + m)]);
+                sink(half, r0 + r, tot);
+            }
+        }
+    }
+};
+
+// ============================================================ codec: sign bits
+// BQ: score = float32(Hamming) (distance.Hamming).  RaBitQ: estimator of
+// rabitq.go:119-176, unfused Go arithmetic.  Integer popcounts are exact in any
+// order, so one thread owns one row and loops over the CTA's QT queries.
+// Query side = prepared sign words P.q_words [nq][words32] (+ P.q_norms for
+// RaBitQ), see prep_sign_queries(); the float `queries` pointer is unused.
+template <bool RABITQ>
+struct CodecSign {
+    static constexpr int QT = 8, R = 1, THREADS = 256, RB = THREADS, MINB = 2;
+    static size_t qsmem(const CodecParams &P) { return (size_t)QT * (P.words32 + 4) * 4; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        (void)queries;
+        (void)qs_;
+        uint32_t *qw = reinterpret_cast<uint32_t *>(sm);
+        const int W = P.words32;
+        for (int i = tid; i < QT * W; i += THREADS) {
+            const int q = i / W, j = i - q * W;
+            qw[i] = (q < nqv) ? P.q_words[(int64_t)(q0 + q) * W + j] : 0u;
+        }
+        float *qn = reinterpret_cast<float *>(qw + QT * W);
+        if (tid < QT) qn[tid] = (RABITQ && tid < nqv) ? P.q_norms[q0 + tid] : 0.0f;
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const uint32_t *qw = reinterpret_cast<const uint32_t *>(sm);
+        const int W = P.words32;
+        const float *qn = reinterpret_cast<const float *>(qw + QT * W);
+        const int64_t row = base + tid;
+        if (row >= row_end) return;
+        const uint32_t *code = reinterpret_cast<const uint32_t *>(P.codes + row * P.row_bytes);
+        int h[QT];
+#pragma unroll
+        for (int q = 0; q < QT; q++) h[q] = 0;
+        int j = 0;
+        for (; j + 4 <= W; j += 4) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(code + j));
+#pragma unroll
+            for (int q = 0; q < QT; q++) {
+                const uint4 u = *reinterpret_cast<const uint4 *>(qw + q * W + j);
+                h[q] += __popc(v.x ^ u.x) + __popc(v.y ^ u.y) + __popc(v.z ^ u.z) + __popc(v.w ^ u.w);
+            }
+        }
+        for (; j < W; j++) {
+            const uint32_t v = __ldg(code + j);
+#pragma unroll
+            for (int q = 0; q < QT; q++) h[q] += __popc(v ^ qw[q * W + j]);
+        }
+        float yn = 0.0f;
+        if (RABITQ) yn = __ldg(P.norms + row);
+        const float fdim = (float)P.dim;
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+            if (q >= nqv) continue;
+            float score;
+            if (RABITQ) {
+                const float hm = (float)h[q];
+                const float t1 = __fsub_rn(qn[q], yn);
+                const float t1sq = __fmul_rn(t1, t1);
+                float a = __fmul_rn(4.0f, qn[q]);
+                a = __fmul_rn(a, yn);
+                a = __fdiv_rn(a, fdim);
+                score = __fadd_rn(t1sq, __fmul_rn(a, hm));
+            } else {
+                score = (float)h[q];
+            }
+            sink(q, row, score);
+        }
+    }
+};
+
+// ============================================================ kernels
+template <class Codec>
+__global__ void __launch_bounds__(Codec::THREADS, Codec::MINB) scan_topk_kernel(CodecParams P, ScanArgs A, size_t qbytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * Codec::QT;
+    const int nqv = (A.nq - q0 < Codec::QT) ? (int)(A.nq - q0) : Codec::QT;
+    const int split = blockIdx.y;
+    SinkTopK sink;
+    sink.tk = topk_carve(smem + qbytes, Codec::QT, A.C, A.k);
+    sink.mask = A.mask;
+    sink.probe = A.probe;
+    sink.part_off = A.part_off;
+    sink.nprobe = A.nprobe;
+    sink.trigger = A.trigger;
+    sink.q0 = q0;
+    sink.row_base = A.row_base;
+    sink.descending = A.descending != 0;
+    Codec::stage(P, A.queries, A.q_stride ? A.q_stride : P.dim, q0, nqv, smem, tid);
+    topk_init(sink.tk, Codec::QT, tid, Codec::THREADS);
+    __syncthreads();
+    const int64_t row_begin = (int64_t)split * A.rows_per_split;
+    int64_t row_end = row_begin + A.rows_per_split;
+    if (row_end > A.rows) row_end = A.rows;
+    for (int64_t base = row_begin; base < row_end; base += Codec::RB) {
+        Codec::tile(P, A.is_dot != 0, smem, base, row_end, nqv, tid, sink);
+        __syncthreads();
+        topk_block_maintain(sink.tk, Codec::QT, tid, Codec::THREADS);
+    }
+    __syncthreads();
+    const int warp = tid >> 5, lane = tid & 31;
+    for (int s = warp; s < nqv; s += Codec::THREADS / 32) {
+        const int64_t q = q0 + s;
+        if (A.splits == 1)
+            topk_emit_warp(sink.tk, s, lane, A.descending != 0, A.out_rows + q * A.k, A.out_scores + q * A.k, A.out_counts + q,
+                           A.k);
+        else
+            topk_emit_keys_warp(sink.tk, s, lane, A.partial + (q * A.splits + split) * A.k, A.k);
+    }
+}
+
+template <class Codec>
+__global__ void __launch_bounds__(Codec::THREADS, Codec::MINB)
+scan_dense_kernel(CodecParams P, const float *queries, int64_t nq, int64_t n, int is_dot, float *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int q0 = blockIdx.x * Codec::QT;
+    const int nqv = (nq - q0 < Codec::QT) ? (int)(nq - q0) : Codec::QT;
+    SinkDense sink{out, n, q0};
+    Codec::stage(P, queries, P.dim, q0, nqv, smem, tid);
+    __syncthreads();
+    for (int64_t base = (int64_t)blockIdx.y * Codec::RB; base < n; base += (int64_t)gridDim.y * Codec::RB)
+        Codec::tile(P, is_dot != 0, smem, base, n, nqv, tid, sink);
+}
+
+// One warp per query merges `lists` sorted key lists.
+__global__ void __launch_bounds__(256) merge_keys_kernel(const unsigned long long *keys, int64_t lists, int64_t nq, int64_t k_in,
+                                                         int64_t list_stride, int64_t query_stride, int descending, int k_out,
+                                                         int C, uint32_t *out_rows, float *out_scores, int32_t *out_counts) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    TopK tk = topk_carve(smem, nw, C, k_out);
+    topk_init(tk, nw, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int64_t q = (int64_t)blockIdx.x * nw + warp;
+    if (q >= nq) return;
+    const int trigger = C - 32;
+    for (int64_t l = 0; l < lists; l++) {
+        const unsigned long long *src = keys + l * list_stride + q * query_stride;
+        for (int64_t i0 = 0; i0 < k_in; i0 += 32) {
+            const int64_t i = i0 + lane;
+            if (i < k_in) {
+                const unsigned long long key = src[i];
+                if (key != VG_KEY_EMPTY && key < tk.tau[warp]) {
+                    int pos = atomicAdd(&tk.cnt[warp], 1);
+                    if (pos < C) tk.keys[(size_t)warp * C + pos] = key;
+                }
+            }
+            __syncwarp();
+            if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
+            __syncwarp();
+        }
+    }
+    topk_emit_warp(tk, warp, lane, descending != 0, out_rows + q * k_out, out_scores + q * k_out, out_counts + q, k_out);
+}
+
+__global__ void pairs_to_keys_kernel(const uint32_t *rows, const float *scores, int64_t n, int descending,
+                                     unsigned long long *keys) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    keys[i] = (rows[i] == 0xFFFFFFFFu) ? VG_KEY_EMPTY : make_key(scores[i], rows[i], descending != 0);
+}
+
+vg_status launch_merge_keys(const unsigned long long *d_keys, int64_t lists, int64_t nq, int64_t k_in, int64_t list_stride,
+                            int64_t query_stride, bool descending, int64_t k_out, uint32_t *d_rows, float *d_scores,
+                            int32_t *d_counts, cudaStream_t st) {
+    if (nq <= 0) return VG_OK;
+    const int C = topk_capacity((int)k_out, 32);
+    int nw = 8;
+    while (nw > 1 && topk_smem_bytes(nw, C) > 200 * 1024) nw >>= 1;
+    const size_t sm = topk_smem_bytes(nw, C);
+    if (sm > 220 * 1024) return fail(VG_ERR_UNSUPPORTED, "k too large for the shared-memory top-k");
+    VG_CUDA(cudaFuncSetAttribute(merge_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int64_t blocks = (nq + nw - 1) / nw;
+    merge_keys_kernel<<<(unsigned)blocks, nw * 32, sm, st>>>(d_keys, lists, nq, k_in, list_stride, query_stride, descending ? 1 : 0,
+                                                             (int)k_out, C, d_rows, d_scores, d_counts);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+vg_status launch_merge_pairs(const uint32_t *d_rows_in, const float *d_scores_in, int64_t lists, int64_t nq, int64_t k_in,
+                             bool descending, int64_t k_out, uint32_t *d_rows, float *d_scores, int32_t *d_counts,
+                             cudaStream_t st) {
+    const int64_t n = lists * nq * k_in;
+    if (n <= 0 || nq <= 0) return VG_OK;
+    DevBuf keys;
+    VG_TRY(keys.alloc((size_t)n * 8));
+    pairs_to_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_rows_in, d_scores_in, n, descending ? 1 : 0,
+                                                                      keys.as<unsigned long long>());
+    VG_LAUNCHED();
+    VG_TRY(launch_merge_keys(keys.as<unsigned long long>(), lists, nq, k_in, nq * k_in, k_in, descending, k_out, d_rows, d_scores,
+                             d_counts, st));
+    VG_CUDA(cudaStreamSynchronize(st));  // keys is freed on return
+    return VG_OK;
+}
+
+// ------------------------------------------------------------ dispatch
+template <class Codec>
+static vg_status run_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st) {
+    const size_t qb = (Codec::qsmem(cp) + 15) & ~(size_t)15;
+    a.C = topk_capacity(a.k, Codec::RB);
+    a.trigger = a.C - Codec::RB;
+    const size_t sm = qb + topk_smem_bytes(Codec::QT, a.C);
+    if (sm > 227 * 1024) return fail(VG_ERR_UNSUPPORTED, "query tile + top-k state exceed 227 KB of shared memory (dim or k too large)");
+    const int64_t qtiles = (a.nq + Codec::QT - 1) / Codec::QT;
+    // Row splits only when the query tiles alone cannot fill the machine.
+    const int64_t target = (int64_t)sm_count() * Codec::MINB;
+    int64_t splits = 1;
+    if (qtiles < target) {
+        splits = (target + qtiles - 1) / qtiles;
+        const int64_t min_rows = (int64_t)Codec::RB * 8;
+        const int64_t max_splits = (a.rows + min_rows - 1) / min_rows;
+        if (splits > max_splits) splits = max_splits;
+        if (splits > 1024) splits = 1024;
+        if (splits < 1) splits = 1;
+    }
+    int64_t rps = (a.rows + splits - 1) / splits;
+    rps = (rps + Codec::RB - 1) / Codec::RB * Codec::RB;
+    splits = (a.rows + rps - 1) / rps;
+    if (splits < 1) splits = 1;
+    a.splits = (int)splits;
+    a.rows_per_split = rps;
+    DevBuf partial;
+    if (splits > 1) {
+        VG_TRY(partial.alloc((size_t)a.nq * splits * a.k * 8));
+        a.partial = partial.as<unsigned long long>();
+    }
+    VG_CUDA(cudaFuncSetAttribute(scan_topk_kernel<Codec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid((unsigned)qtiles, (unsigned)splits);
+    scan_topk_kernel<Codec><<<grid, Codec::THREADS, sm, st>>>(cp, a, qb);
+    VG_LAUNCHED();
+    if (splits > 1) {
+        VG_TRY(launch_merge_keys(a.partial, splits, a.nq, a.k, a.k, splits * a.k, a.descending != 0, a.k, a.out_rows, a.out_scores,
+                                 a.out_counts, st));
+        VG_CUDA(cudaStreamSynchronize(st));  // partial is freed on return
+    }
+    return VG_OK;
+}
+
+template <class Codec>
+static vg_status run_dense(const CodecParams &cp, const float *q, int64_t nq, int64_t n, int is_dot, float *out,
+                           cudaStream_t st) {
+    const size_t sm = (Codec::qsmem(cp) + 15) & ~(size_t)15;
+    if (sm > 227 * 1024) return fail(VG_ERR_UNSUPPORTED, "query tile exceeds 227 KB of shared memory");
+    if (nq <= 0 || n <= 0) return VG_OK;
+    VG_CUDA(cudaFuncSetAttribute(scan_dense_kernel<Codec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    const int64_t qtiles = (nq + Codec::QT - 1) / Codec::QT;
+    int64_t gy = (n + Codec::RB - 1) / Codec::RB;
+    const int64_t want = (4LL * sm_count() + qtiles - 1) / qtiles;
+    if (gy > want) gy = want;
+    if (gy > 65535) gy = 65535;
+    dim3 grid((unsigned)qtiles, (unsigned)gy);
+    scan_dense_kernel<Codec><<<grid, Codec::THREADS, sm, st>>>(cp, q, nq, n, is_dot, out);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+#define VG_DISPATCH(FN, ...)                                                                                     \
+    switch (cp.codec) {                                                                                          \
+        case VG_CODEC_F32:                                                                                       \
+            return (cp.variant & VG_VAR_BATCH) ? FN<CodecF32<true>>(__VA_ARGS__) : FN<CodecF32<false>>(__VA_ARGS__); \
+        case VG_CODEC_SQ8:                                                                                       \
+            if (cp.variant & VG_VAR_GO_SCALAR) return FN<CodecSQ8Go>(__VA_ARGS__);                               \
+            if (cp.variant & VG_VAR_PERM)                                                                        \
+                return (cp.dim % 256 == 0) ? FN<CodecSQ8Perm<16>>(__VA_ARGS__) : FN<CodecSQ8Perm<4>>(__VA_ARGS__); \
+            return FN<CodecSQ8>(__VA_ARGS__);                                                                    \
+        case VG_CODEC_INT4:                                                                                      \
+            return (cp.variant & VG_VAR_PERM) ? FN<CodecINT4Perm>(__VA_ARGS__) : FN<CodecINT4>(__VA_ARGS__);     \
+        case VG_CODEC_PQ:                                                                                        \
+        case VG_CODEC_OPQ:                                                                                       \
+            return FN<CodecPQ>(__VA_ARGS__);                                                                     \
+        default:                                                                                                 \
+            break;                                                                                               \
+    }
+
+vg_status scan_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st) {
+    if (a.nq <= 0) return VG_OK;
+    if (a.k <= 0) return fail(VG_ERR_INVALID, "k must be positive");
+    if (a.rows <= 0) {
+        // empty index: counts = 0, rows = 0xFFFFFFFF
+        VG_CUDA(cudaMemsetAsync(a.out_counts, 0, (size_t)a.nq * 4, st));
+        VG_CUDA(cudaMemsetAsync(a.out_rows, 0xFF, (size_t)a.nq * a.k * 4, st));
+        VG_CUDA(cudaMemsetAsync(a.out_scores, 0xFF, (size_t)a.nq * a.k * 4, st));
+        return VG_OK;
+    }
+    if ((cp.codec == VG_CODEC_PQ || cp.codec == VG_CODEC_OPQ) && cp.pq_k != 256)
+        return fail(VG_ERR_UNSUPPORTED, "PQ ADC requires K=256 (simd.PqAdcLookup hard-wires the table stride, kernels.go:249)");
+    VG_DISPATCH(run_topk, cp, a, st)
+    if (cp.codec == VG_CODEC_BQ) return run_topk<CodecSign<false>>(cp, a, st);
+    if (cp.codec == VG_CODEC_RABITQ) return run_topk<CodecSign<true>>(cp, a, st);
+    return fail(VG_ERR_UNSUPPORTED, "unknown codec");
+}
+
+vg_status scan_dense(const CodecParams &cp, const float *d_queries, int64_t nq, int64_t n, int is_dot, float *d_out,
+                     cudaStream_t st) {
+    if ((cp.codec == VG_CODEC_PQ || cp.codec == VG_CODEC_OPQ) && cp.pq_k != 256)
+        return fail(VG_ERR_UNSUPPORTED, "PQ ADC requires K=256");
+    VG_DISPATCH(run_dense, cp, d_queries, nq, n, is_dot, d_out, st)
+    if (cp.codec == VG_CODEC_BQ) return run_dense<CodecSign<false>>(cp, d_queries, nq, n, is_dot, d_out, st);
+    if (cp.codec == VG_CODEC_RABITQ) return run_dense<CodecSign<true>>(cp, d_queries, nq, n, is_dot, d_out, st);
+    return fail(VG_ERR_UNSUPPORTED, "unknown codec");
+}
+
+// ------------------------------------------------------------ rerank (gather)
+// flat.Rerank (segment.go:754-781): half-warp per (query, candidate) pair.
+__global__ void __launch_bounds__(256) rerank_kernel(const float *vectors, int64_t nrows, int64_t dim, const float *queries,
+                                                     int64_t nq, const uint32_t *rows, int64_t r, int is_dot, float *out) {
+    const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const int64_t total = nq * r;
+    const bool live = pair < total;
+    const int64_t p = live ? pair : total - 1;
+    const int64_t q = p / r;
+    const uint32_t row = rows[p];
+    const bool valid = (int64_t)row < nrows;
+    const float *x = vectors + (valid ? (int64_t)row : 0) * dim;
+    const float *qv = queries + q * dim;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t epochs = dim >> 6;
+    for (int64_t e = 0; e < epochs; e++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t d = e * 64 + j * 16 + lane;
+            if (is_dot) {
+                a[j] = __fmaf_rn(qv[d], __ldg(x + d), a[j]);
+            } else {
+                const float df = __fsub_rn(qv[d], __ldg(x + d));
+                a[j] = __fmaf_rn(df, df, a[j]);
+            }
+        }
+    float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+    if (lane == 0 && live) {
+        for (int64_t d = epochs * 64; d < dim; d++) {
+            if (is_dot) {
+                tot = __fmaf_rn(qv[d], __ldg(x + d), tot);
+            } else {
+                const float df = __fsub_rn(qv[d], __ldg(x + d));
+                tot = __fmaf_rn(df, df, tot);
+            }
+        }
+        out[p] = valid ? tot : __uint_as_float(0x7fc00000u);
+    }
+}
+
+vg_status rerank_gather(const float *d_vectors, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq,
+                        const uint32_t *d_rows, int64_t r, int is_dot, float *d_out, cudaStream_t st) {
+    const int64_t total = nq * r;
+    if (total <= 0) return VG_OK;
+    if (!d_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
+    const int64_t threads = total * 16;
+    rerank_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_vectors, nrows, dim, d_queries, nq, d_rows, r, is_dot, d_out);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+// ------------------------------------------------------------ hamming matrix
+__global__ void __launch_bounds__(256) hamming_kernel(const uint8_t *q, int64_t nq, const uint8_t *codes, int64_t n,
+                                                      int64_t nbytes, int32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nq * n) return;
+    const int64_t qi = i / n, r = i - qi * n;
+    const uint8_t *a = q + qi * nbytes, *b = codes + r * nbytes;
+    int h = 0;
+    for (int64_t j = 0; j < nbytes; j++) h += __popc((uint32_t)(a[j] ^ b[j]));
+    out[i] = h;
+}
+vg_status hamming_dense(const uint8_t *d_q, int64_t nq, const uint8_t *d_codes, int64_t n, int64_t nbytes, int32_t *d_out,
+                        cudaStream_t st) {
+    const int64_t total = nq * n;
+    if (total <= 0) return VG_OK;
+    hamming_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_q, nq, d_codes, n, nbytes, d_out);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+// ------------------------------------------------------------ sign-query prep
+// Query sign words (q[i] >= threshold → bit i, LSB first: rabitq.go:143-151,
+// binary.go:138-152) and ||q|| = Sqrt(simd.Dot(q,q)) in AVX-512 order.
+__global__ void __launch_bounds__(256) prep_sign_kernel(const float *queries, int64_t nq, int64_t dim, float threshold,
+                                                        int words32, uint32_t *words, float *norms) {
+    const int64_t hwid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const bool live = hwid < nq;
+    const int64_t q = live ? hwid : nq - 1;
+    const float *v = queries + q * dim;
+    if (live)
+        for (int w = lane; w < words32; w += 16) {
+            uint32_t bits = 0;
+            for (int b = 0; b < 32; b++) {
+                const int64_t d = (int64_t)w * 32 + b;
+                if (d < dim && v[d] >= threshold) bits |= 1u << b;
+            }
+            words[q * words32 + w] = bits;
+        }
+    if (norms) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        const int64_t epochs = dim >> 6;
+        for (int64_t e = 0; e < epochs; e++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float x = v[e * 64 + j * 16 + lane];
+                a[j] = __fmaf_rn(x, x, a[j]);
+            }
+        float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+        if (lane == 0 && live) {
+            for (int64_t d = epochs * 64; d < dim; d++) tot = __fmaf_rn(v[d], v[d], tot);
+            norms[q] = (float)sqrt((double)tot);  // simd.Sqrt: float32(math.Sqrt(float64(x)))
+        }
+    }
+}
+vg_status prep_sign_queries(const float *d_queries, int64_t nq, int64_t dim, float threshold, uint32_t *d_words,
+                            float *d_norms, cudaStream_t st) {
+    if (nq <= 0) return VG_OK;
+    const int words32 = (int)(((dim + 63) / 64) * 2);
+    const int64_t threads = nq * 16;
+    prep_sign_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_queries, nq, dim, threshold, words32, d_words, d_norms);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+}  // namespace vg

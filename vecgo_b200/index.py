@@ -1,0 +1,154 @@
+"""DeviceIndex: one immutable, device-resident code matrix (vg_index_* in
+include/vecgo_cuda.h) — a flat segment or one row shard of it."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+F = np.float32
+EMPTY_ROW = 0xFFFFFFFF
+
+
+class DeviceIndex:
+    def __init__(self, *, codec: int, metric: int, dim: int, rows: int, segment_id: int = 0, row_base: int = 0,
+                 sq8=None, int4=None, pq=None, opq=None, bq_threshold: float = 0.0, centroids=None,
+                 partition_offsets=None, _handle=None):
+        self.codec, self.metric, self.dim, self.rows = codec, metric, dim, rows
+        self.segment_id, self.row_base = segment_id, row_base
+        self.handle = None
+        if _handle is not None:
+            self.handle = _handle
+            return
+        keep = []
+        d = L.IndexDesc()
+        d.codec, d.metric, d.dim, d.rows = codec, int(metric), dim, rows
+        d.segment_id, d.row_base = segment_id, row_base
+        d.bq_threshold = float(bq_threshold)
+
+        def fp(a):
+            a = L.as_f32(a)
+            keep.append(a)
+            return L.ptr(a, L.f32p)
+
+        if sq8 is not None:  # (mins, invScales)
+            d.sq8_mins, d.sq8_inv_scales = fp(sq8[0]), fp(sq8[1])
+        if int4 is not None:  # (min, diff)
+            d.int4_min, d.int4_diff = fp(int4[0]), fp(int4[1])
+        if pq is not None:  # (codebooks int8, scales, offsets, m, k)
+            cb = np.ascontiguousarray(pq[0], np.int8).reshape(-1)
+            keep.append(cb)
+            d.pq_codebooks, d.pq_scales, d.pq_offsets = L.ptr(cb, L.i8p), fp(pq[1]), fp(pq[2])
+            d.pq_m, d.pq_k = pq[3], pq[4]
+        if opq is not None:  # (rotations [blocks][bs][bs], block size)
+            d.opq_rotation, d.opq_block = fp(opq[0]), opq[1]
+        if centroids is not None:
+            cen = L.as_f32(centroids).reshape(-1, dim)
+            po = np.ascontiguousarray(partition_offsets, np.uint32)
+            keep += [cen, po]
+            d.num_partitions, d.centroids, d.partition_offsets = cen.shape[0], L.ptr(cen, L.f32p), L.ptr(po, L.u32p)
+        h = C.c_uint64()
+        L.call("vg_index_create", C.byref(d), C.byref(h))
+        self.handle = h.value
+
+    # ------------------------------------------------------------------ data
+    def upload(self, codes=None, vectors=None, row0: int = 0):
+        n = None
+        cp = vp = None
+        if codes is not None:
+            codes = L.as_u8(codes)
+            n = codes.shape[0]
+            cp = codes.ctypes.data
+        if vectors is not None:
+            vectors = L.as_f32(vectors)
+            n = vectors.shape[0]
+            vp = L.ptr(vectors, L.f32p)
+        if n:
+            L.call("vg_index_upload", self.handle, row0, n, cp, vp)
+
+    def upload_dev(self, n: int, d_codes: int = 0, d_vectors: int = 0, row0: int = 0):
+        """Fill rows from device pointers (e.g. torch tensors' data_ptr())."""
+        L.call("vg_index_upload_dev", self.handle, row0, n, d_codes or None, d_vectors or None)
+
+    def info(self):
+        r, d, cb, db = (C.c_int64() for _ in range(4))
+        L.call("vg_index_info", self.handle, C.byref(r), C.byref(d), C.byref(cb), C.byref(db))
+        return dict(rows=r.value, dim=d.value, code_bytes_per_row=cb.value, device_bytes=db.value)
+
+    # ---------------------------------------------------------------- search
+    def search(self, queries, k: int, nprobes: int = 0, row_mask=None):
+        """Batched Segment.Search → (rows [nq,k] u32, scores [nq,k] f32, counts [nq] i32), best-first."""
+        q = L.as_f32(queries).reshape(-1, self.dim)
+        nq = q.shape[0]
+        rows = np.full((nq, k), EMPTY_ROW, np.uint32)
+        scores = np.full((nq, k), np.nan, F)
+        counts = np.zeros(nq, np.int32)
+        m = None
+        if row_mask is not None:
+            m = L.as_u8(row_mask)
+            if m.size < (self.rows + 7) // 8:
+                raise ValueError("row mask shorter than ceil(rows/8) bytes")
+        L.call("vg_index_search", self.handle, L.ptr(q, L.f32p), nq, k, nprobes, L.ptr(m, L.u8p), L.ptr(rows, L.u32p),
+               L.ptr(scores, L.f32p), L.ptr(counts, L.i32p))
+        return rows, scores, counts
+
+    def search_dev(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int, nprobes: int = 0,
+                   d_mask: int = 0):
+        L.call("vg_index_search_dev", self.handle, d_queries, nq, k, nprobes, d_mask or None, d_rows, d_scores, d_counts)
+
+    def rerank(self, queries, rows):
+        """Batched Segment.Rerank: exact scores for rows[q, j] (local row ids)."""
+        q = L.as_f32(queries).reshape(-1, self.dim)
+        r = np.ascontiguousarray(rows, np.uint32).reshape(q.shape[0], -1)
+        out = np.zeros(r.shape, F)
+        L.call("vg_index_rerank", self.handle, L.ptr(q, L.f32p), q.shape[0], L.ptr(r, L.u32p), r.shape[1], L.ptr(out, L.f32p))
+        return out
+
+    def search_rerank(self, queries, r: int, k: int):
+        q = L.as_f32(queries).reshape(-1, self.dim)
+        nq = q.shape[0]
+        rows = np.full((nq, k), EMPTY_ROW, np.uint32)
+        scores = np.full((nq, k), np.nan, F)
+        counts = np.zeros(nq, np.int32)
+        L.call("vg_index_search_rerank", self.handle, L.ptr(q, L.f32p), nq, r, k, L.ptr(rows, L.u32p), L.ptr(scores, L.f32p),
+               L.ptr(counts, L.i32p))
+        return rows, scores, counts
+
+    def fetch_ids(self, rows):
+        r = np.ascontiguousarray(rows, np.uint32).reshape(-1)
+        out = np.zeros(r.size, np.uint64)
+        L.call("vg_index_fetch_ids", self.handle, L.ptr(r, L.u32p), r.size, L.ptr(out, L.u64p))
+        return out
+
+    def close(self):
+        if self.handle is not None:
+            L.call("vg_index_close", self.handle)
+            self.handle = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            if self.handle is not None:
+                L.lib.vg_index_close(self.handle)
+        except Exception:
+            pass
+
+
+def topk_merge(rows, scores, descending: bool, k_out: int):
+    """Merge [lists][nq][k] best-first lists (engine/search.go:903-908 semantics)."""
+    r = np.ascontiguousarray(rows, np.uint32)
+    s = L.as_f32(scores)
+    lists, nq, k_in = r.shape
+    orow = np.full((nq, k_out), EMPTY_ROW, np.uint32)
+    osc = np.full((nq, k_out), np.nan, F)
+    ocnt = np.zeros(nq, np.int32)
+    L.call("vg_topk_merge", L.ptr(r, L.u32p), L.ptr(s, L.f32p), lists, nq, k_in, int(descending), k_out, L.ptr(orow, L.u32p),
+           L.ptr(osc, L.f32p), L.ptr(ocnt, L.i32p))
+    return orow, osc, ocnt
