@@ -52,7 +52,7 @@ def test_simd_kat(vg):  # internal/simd/floats_test.go:11-33,55-74
     assert vg.simd.Hamming(list(range(17)), [0xFF, 1, 0xFD, 3, 0xFB, 5, 0xF9, 7, 0xF7, 9, 0xF5, 0xB, 0xF3, 0xD, 0xF1, 0xF, 0xEF]) == 72
     table = np.array([[i * 1000 + j for j in range(256)] for i in range(16)], F).ravel()
     codes = np.array([17 * i for i in range(16)], np.uint8)
-    assert vg.simd.PqAdcLookup(table, codes, 16) == sum(table[i * 256 + codes[i]] for i in range(16))
+    assert vg.simd.PqAdcLookup(table, codes, 16) == sum(table[i * 256 + int(codes[i])] for i in range(16))
 
 
 def test_batch_kernels_bit_exact(vg):

@@ -1,6 +1,9 @@
 """Quick device-resident timing probe (not the bench): python tools/probe.py [codec ...]"""
+import os
 import sys
 import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 import numpy as np
 import torch
