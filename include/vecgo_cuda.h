@@ -123,6 +123,14 @@ vg_status vg_pq_build_distance_table(const float *h_queries, int64_t nq, int64_t
 vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
                       int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32 /* optional [m][k][dim/m] */);
 
+/* Device-resident variants (d_vecs / d_codes in HBM; parameters still host arrays): used to
+ * encode shards that never exist on the host (flat.Writer.Flush-style bulk encode). */
+vg_status vg_minmax_dev(const float *d_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs);
+vg_status vg_sq8_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const float *h_mins, const float *h_maxs, const float *h_scales, uint8_t *d_codes);
+vg_status vg_int4_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const float *h_min, const float *h_diff, uint8_t *d_codes);
+vg_status vg_rabitq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, uint8_t *d_codes);
+vg_status vg_pq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_codebooks, const float *h_scales, const float *h_offsets, uint8_t *d_codes);
+
 /* ----------------------------------------------------------------- k-means
  * internal/kmeans/kmeans.go. */
 vg_status vg_kmeans_train(const float *h_vecs, int64_t n, int64_t dim, int64_t k, int32_t metric, int64_t max_iter,

@@ -89,6 +89,11 @@ _SIGS = {
     "vg_pq_decode": [u8p, i64, i64, i64, i64, i8p, f32p, f32p, f32p],
     "vg_pq_build_distance_table": [f32p, i64, i64, i64, i64, i8p, f32p, f32p, f32p],
     "vg_pq_train": [f32p, i64, i64, i64, i64, i64, u64, i8p, f32p, f32p, f32p],
+    "vg_minmax_dev": [vp, i64, i64, f32p, f32p],
+    "vg_sq8_encode_dev": [vp, i64, i64, f32p, f32p, f32p, vp],
+    "vg_int4_encode_dev": [vp, i64, i64, f32p, f32p, vp],
+    "vg_rabitq_encode_dev": [vp, i64, i64, vp],
+    "vg_pq_encode_dev": [vp, i64, i64, i64, i64, i8p, f32p, f32p, vp],
     "vg_kmeans_train": [f32p, i64, i64, i64, i32, i64, i64p, u64, f32p, i32p, i64p],
     "vg_kmeans_assign": [f32p, i64, i64, f32p, i64, i32, i32p],
     "vg_kmeans_find_closest": [f32p, i64, i64, f32p, i64, i64, i32, i32p],

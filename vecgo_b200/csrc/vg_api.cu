@@ -1023,6 +1023,57 @@ vg_status vg_pq_build_distance_table(const float *h_q, int64_t nq, int64_t dim, 
     return staged_d2h(h_tables, out.p, (size_t)nq * m * k * 4);
 }
 
+// device-resident variants
+vg_status vg_minmax_dev(const float *d_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs) {
+    VG_TRY(ensure_init());
+    if (n <= 0 || dim <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    DevBuf mm;
+    VG_TRY(mm.alloc((size_t)dim * 8));
+    VG_TRY(dev_minmax(d_vecs, n, dim, mm.as<float>(), mm.as<float>() + dim, stream()));
+    VG_TRY(staged_d2h(h_mins, mm.p, (size_t)dim * 4));
+    return staged_d2h(h_maxs, mm.as<float>() + dim, (size_t)dim * 4);
+}
+vg_status vg_sq8_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const float *h_mins, const float *h_maxs,
+                            const float *h_scales, uint8_t *d_codes) {
+    VG_TRY(ensure_init());
+    if (!h_mins || !h_maxs || !h_scales) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
+    if (n <= 0) return VG_OK;
+    DevBuf mn, mx, sc;
+    VG_TRY(to_device(mn, h_mins, (size_t)dim));
+    VG_TRY(to_device(mx, h_maxs, (size_t)dim));
+    VG_TRY(to_device(sc, h_scales, (size_t)dim));
+    VG_TRY(dev_sq8_encode(d_vecs, n, dim, mn.as<float>(), mx.as<float>(), sc.as<float>(), d_codes, stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return VG_OK;
+}
+vg_status vg_int4_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const float *h_min, const float *h_diff, uint8_t *d_codes) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    DevBuf mn, df;
+    VG_TRY(to_device(mn, h_min, (size_t)dim));
+    VG_TRY(to_device(df, h_diff, (size_t)dim));
+    VG_TRY(dev_int4_encode(d_vecs, n, dim, mn.as<float>(), df.as<float>(), d_codes, stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return VG_OK;
+}
+vg_status vg_rabitq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, uint8_t *d_codes) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return VG_OK;
+    VG_TRY(dev_sign_encode(d_vecs, n, dim, 0.0f, true, d_codes, stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return VG_OK;
+}
+vg_status vg_pq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc,
+                           const float *h_of, uint8_t *d_codes) {
+    VG_TRY(ensure_init());
+    PqDev p;
+    VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
+    if (n <= 0) return VG_OK;
+    VG_TRY(dev_pq_encode(d_vecs, n, dim, (int)m, (int)k, p.cb.as<int8_t>(), p.sc.as<float>(), p.of.as<float>(), d_codes, stream()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return VG_OK;
+}
+
 // ------------------------------------------------------------ flat segment file
 // format.go:110-165 / segment.go:105-342
 static uint32_t rd32(const uint8_t *p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
