@@ -31,11 +31,13 @@ def exchange_topk(rows, scores, group=None):
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     if world == 1:
         return rows.unsqueeze(0), scores.unsqueeze(0)
-    all_rows = torch.empty((world,) + tuple(rows.shape), dtype=rows.dtype, device=rows.device)
-    all_scores = torch.empty((world,) + tuple(scores.shape), dtype=scores.dtype, device=scores.device)
+    nq, k = rows.shape
+    # concatenated-along-dim-0 output is the layout every backend (NCCL, gloo) accepts
+    all_rows = torch.empty((world * nq, k), dtype=rows.dtype, device=rows.device)
+    all_scores = torch.empty((world * nq, k), dtype=scores.dtype, device=scores.device)
     dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=group)
     dist.all_gather_into_tensor(all_scores, scores.contiguous(), group=group)
-    return all_rows, all_scores
+    return all_rows.view(world, nq, k), all_scores.view(world, nq, k)
 
 
 class ShardedIndex:
