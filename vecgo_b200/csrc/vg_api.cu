@@ -293,6 +293,11 @@ vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
             VG_TRY(to_device(ix->pq_cb, d.pq_codebooks, (size_t)(d.pq_m * d.pq_k * (d.dim / d.pq_m))));
             VG_TRY(to_device(ix->pq_scales, d.pq_scales, (size_t)d.pq_m));
             VG_TRY(to_device(ix->pq_offsets, d.pq_offsets, (size_t)d.pq_m));
+            // thread-per-row ADC scan with a two-query float2 table (M*256*8 B of shared memory): K=256 only
+            if (d.pq_k == 256 && (size_t)d.pq_m * 2048 <= 200 * 1024) {
+                ix->variant = VG_VAR_PERM;
+                ix->dev_row_bytes = (d.pq_m + 15) / 16 * 16;
+            }
             if (d.codec == VG_CODEC_OPQ) {
                 if (!d.opq_rotation || d.opq_block <= 0 || d.dim % d.opq_block != 0)
                     return fail(VG_ERR_INVALID, "OPQ needs block rotations with dim % block == 0");
@@ -311,7 +316,12 @@ vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
         default:
             return fail(VG_ERR_INVALID, "unknown codec");
     }
-    if (ix->code_row_bytes > 0) VG_TRY(ix->codes.alloc((size_t)rows * ix->dev_row_bytes));
+    if (ix->code_row_bytes > 0) {
+        const bool pq_tiled = (d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ) && (ix->variant & VG_VAR_PERM);
+        const int64_t alloc_rows = pq_tiled ? (rows + 31) / 32 * 32 : rows;  // PQ tiles hold 32 rows
+        VG_TRY(ix->codes.alloc((size_t)alloc_rows * ix->dev_row_bytes));
+        if (pq_tiled) VG_CUDA(cudaMemsetAsync(ix->codes.p, 0, ix->codes.bytes, stream()));
+    }
     if (d.num_partitions > 1) {
         if (!d.centroids || !d.partition_offsets) return fail(VG_ERR_INVALID, "partitioned index needs centroids and offsets");
         VG_TRY(to_device(ix->centroids, d.centroids, (size_t)(d.num_partitions * d.dim)));
@@ -364,6 +374,11 @@ static vg_status place_codes(Index *ix, int64_t row0, int64_t n, const uint8_t *
             break;
         case VG_CODEC_INT4:
             if (ix->variant & VG_VAR_PERM) return dev_permute_int4(d_src, dst, n, ix->code_row_bytes, st);
+            break;
+        case VG_CODEC_PQ:
+        case VG_CODEC_OPQ:
+            if (ix->variant & VG_VAR_PERM)
+                return dev_permute_pq(d_src, ix->codes.as<uint8_t>(), row0, n, (int)ix->d.pq_m, (int)ix->dev_row_bytes, st);
             break;
         case VG_CODEC_BQ:
             return dev_split_sign(d_src, n, ix->code_row_bytes, ix->code_row_bytes, ix->dev_row_bytes, dst, nullptr, st);

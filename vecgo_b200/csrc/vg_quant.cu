@@ -408,6 +408,25 @@ vg_status dev_permute_int4(const uint8_t *d_src, uint8_t *d_dst, int64_t n, int6
     VG_LAUNCHED();
     return VG_OK;
 }
+// PQ fast path: rows are grouped in tiles of 32; inside a tile the 16 codes of
+// chunk t (subspaces 16t..16t+15) of row r sit at t*512 + r*16, so one warp's
+// 16-byte loads of a chunk cover 512 contiguous bytes (thread-per-row scan).
+// mpad = M rounded up to 16; missing subspaces are zero bytes (never looked up).
+__global__ void __launch_bounds__(256) permute_pq_kernel(const uint8_t *src, uint8_t *dst, int64_t row0, int64_t n, int m, int mpad) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * mpad) return;
+    const int64_t r = i / mpad;
+    const int o = (int)(i - r * mpad);
+    const int64_t g = row0 + r;
+    dst[(g >> 5) * (32 * (int64_t)mpad) + (int64_t)(o >> 4) * 512 + (g & 31) * 16 + (o & 15)] = (o < m) ? src[r * m + o] : (uint8_t)0;
+}
+vg_status dev_permute_pq(const uint8_t *d_src, uint8_t *d_dst_base, int64_t row0, int64_t n, int m, int mpad, cudaStream_t st) {
+    const int64_t total = n * mpad;
+    if (total <= 0) return VG_OK;
+    permute_pq_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_src, d_dst_base, row0, n, m, mpad);
+    VG_LAUNCHED();
+    return VG_OK;
+}
 // Sign-bit rows (BQ: bits; RaBitQ: bits ‖ f32 norm, 196 B for 1536-d) → a
 // 16-byte aligned, zero padded bit plane (+ a separate norm column).
 __global__ void __launch_bounds__(256) split_sign_kernel(const uint8_t *src, int64_t n, int64_t nbytes, int64_t src_stride,

@@ -25,6 +25,7 @@ vg_status dev_scale(float *d_a, int64_t n, float s, cudaStream_t st);
 vg_status dev_normalize(float *d_v, int64_t n, int64_t dim, uint8_t *d_ok, cudaStream_t st);
 vg_status dev_permute_sq8(const uint8_t *d_src, uint8_t *d_dst, int64_t n, int64_t dim, int vb, cudaStream_t st);
 vg_status dev_permute_int4(const uint8_t *d_src, uint8_t *d_dst, int64_t n, int64_t cs, cudaStream_t st);
+vg_status dev_permute_pq(const uint8_t *d_src, uint8_t *d_dst_base, int64_t row0, int64_t n, int m, int mpad, cudaStream_t st);
 vg_status dev_split_sign(const uint8_t *d_src, int64_t n, int64_t nbytes, int64_t src_stride, int64_t dst_stride, uint8_t *d_bits,
                          float *d_norms, cudaStream_t st);
 }  // namespace vg

@@ -247,13 +247,122 @@ struct CodecSQ8 {
     }
 };
 
+// ---- packed float32x2 helpers (sm_100a FADD2 / FFMA2).  Each half is an
+// IEEE round-to-nearest op, so results are bit-identical to the scalar
+// intrinsics; one instruction issue carries two lanes of work.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
+// Transposed _mm512_reduce_add_ps for NA accumulators per lane of a half-warp
+// (NA = 32): the same pairs are added at every level of the reference tree
+// (i+8, i+4, i+2, i+1; floats_avx512.s:46-53) — float addition is commutative,
+// so only WHERE each partial sum lives changes.  At the level with lane
+// distance D the lanes with (lane & D) == 0 keep the lower half of the
+// accumulators still alive and their partners keep the upper half, so after
+// four levels lane l holds the finished totals of accumulators 2l and 2l+1.
+// 30 shuffles + 30 adds instead of 128 + 128, and the 32 results end up spread
+// over the 16 lanes, which lets every lane run its own top-k offers.
+__device__ __forceinline__ void reduce16_transposed32(float (&v)[32], int lane, float &out0, float &out1) {
+    float a16[16], a8[8], a4[4];
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float send = up ? v[i] : v[16 + i];
+            const float keep = up ? v[16 + i] : v[i];
+            a16[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8, 16));
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float send = up ? a16[i] : a16[8 + i];
+            const float keep = up ? a16[8 + i] : a16[i];
+            a8[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4, 16));
+        }
+    }
+    {
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = up ? a8[i] : a8[4 + i];
+            const float keep = up ? a8[4 + i] : a8[i];
+            a4[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 2, 16));
+        }
+    }
+    {
+        const bool up = (lane & 1) != 0;
+        const float s0 = up ? a4[0] : a4[2], k0 = up ? a4[2] : a4[0];
+        const float s1 = up ? a4[1] : a4[3], k1 = up ? a4[3] : a4[1];
+        out0 = __fadd_rn(k0, __shfl_xor_sync(0xffffffffu, s0, 1, 16));
+        out1 = __fadd_rn(k1, __shfl_xor_sync(0xffffffffu, s1, 1, 16));
+    }
+}
+
+// Same for 16 accumulators per lane: lane l ends with the total of accumulator l.
+__device__ __forceinline__ float reduce16_transposed16(float (&v)[16], int lane) {
+    float a8[8], a4[4], a2[2];
+    {
+        const bool up = (lane & 8) != 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float send = up ? v[i] : v[8 + i];
+            const float keep = up ? v[8 + i] : v[i];
+            a8[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 8, 16));
+        }
+    }
+    {
+        const bool up = (lane & 4) != 0;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float send = up ? a8[i] : a8[4 + i];
+            const float keep = up ? a8[4 + i] : a8[i];
+            a4[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 4, 16));
+        }
+    }
+    {
+        const bool up = (lane & 2) != 0;
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+            const float send = up ? a4[i] : a4[2 + i];
+            const float keep = up ? a4[2 + i] : a4[i];
+            a2[i] = __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 2, 16));
+        }
+    }
+    const bool up = (lane & 1) != 0;
+    const float send = up ? a2[0] : a2[1], keep = up ? a2[1] : a2[0];
+    return __fadd_rn(keep, __shfl_xor_sync(0xffffffffu, send, 1, 16));
+}
+
 // SQ8 fast path: dim % (16*VB) == 0 and codes stored lane-transposed on device
 // (upload kernel permute_sq8): inside every block of 16*VB dims the byte of
 // (step s, lane l) sits at l*VB + s, so lane l fetches VB consecutive steps
 // with one VB-byte load and the half-warp's 16 loads cover 16*VB contiguous
-// bytes.  Queries / mins / invScales are staged lane-major [16][SP] (SP = steps
-// padded to 4*odd, which makes the float4 reads of 8 lanes hit 32 distinct
-// banks); both half-warps of a warp read identical query words (broadcast).
+// bytes.
+//
+// Arithmetic (sq8_avx512.c:59-104) per (query, row, dim):
+//     rec = fma(c, inv, min); e = q - rec; acc = fma(e, e, acc)
+// evaluated here as nrec = fma(c, -inv, -min) (= -rec exactly), e = q + nrec,
+// with the e / acc updates of two QUERIES packed into one FADD2 / FFMA2.
+// Shared-memory layout: -mins / -invScales lane-major [16][SP]; queries
+// [16 lanes][steps][8 queries] with a 16-byte pad per lane so the two
+// LDS.128 that fetch the 8 query values of one step are conflict-free.
 template <int VB>
 struct CodecSQ8Perm {
     static constexpr int QT = 8, R = 4, THREADS = 256, RB = 16 * R, MINB = 2;
@@ -263,29 +372,30 @@ struct CodecSQ8Perm {
         if (((sp >> 2) & 1) == 0) sp += 4;
         return sp;
     }
-    static size_t qsmem(const CodecParams &P) { return (size_t)(QT + 2) * 16 * steps_padded(P.dim) * 4; }
+    __host__ __device__ static int lane_stride(int64_t dim) { return (int)(dim / 16) * QT + 4; }  // floats
+    static size_t qsmem(const CodecParams &P) { return ((size_t)16 * lane_stride(P.dim) + (size_t)2 * 16 * steps_padded(P.dim)) * 4; }
     __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
         float *qs = reinterpret_cast<float *>(sm);
         const int64_t dim = P.dim;
-        const int SP = steps_padded(dim);
+        const int SP = steps_padded(dim), LS = lane_stride(dim);
         for (int64_t i = tid; i < (int64_t)QT * dim; i += THREADS) {
             int q = (int)(i / dim);
             int d = (int)(i - (int64_t)q * dim);
-            qs[((int64_t)q * 16 + (d & 15)) * SP + (d >> 4)] = (q < nqv) ? queries[(int64_t)(q0 + q) * qs_ + d] : 0.0f;
+            qs[(int64_t)(d & 15) * LS + (d >> 4) * QT + q] = (q < nqv) ? queries[(int64_t)(q0 + q) * qs_ + d] : 0.0f;
         }
-        float *mn = qs + (int64_t)QT * 16 * SP, *iv = mn + 16 * SP;
+        float *mn = qs + (int64_t)16 * LS, *iv = mn + 16 * SP;
         for (int d = tid; d < dim; d += THREADS) {
-            mn[(d & 15) * SP + (d >> 4)] = P.p0[d];
-            iv[(d & 15) * SP + (d >> 4)] = P.p1[d];
+            mn[(d & 15) * SP + (d >> 4)] = -P.p0[d];
+            iv[(d & 15) * SP + (d >> 4)] = -P.p1[d];
         }
     }
     template <class Sink>
     __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
                                 int tid, const Sink &sink) {
         const int64_t dim = P.dim;
-        const int SP = steps_padded(dim);
+        const int SP = steps_padded(dim), LS = lane_stride(dim);
         const float *qs = reinterpret_cast<const float *>(sm);
-        const float *mn = qs + (int64_t)QT * 16 * SP, *iv = mn + 16 * SP;
+        const float *mn = qs + (int64_t)16 * LS, *iv = mn + 16 * SP;
         const int hw = tid >> 4, lane = tid & 15;
         const int64_t r0 = base + (int64_t)hw * R;
         const uint8_t *code[R];
@@ -295,13 +405,13 @@ struct CodecSQ8Perm {
             if (rr > row_end - 1) rr = row_end - 1;
             code[r] = P.codes + rr * P.row_bytes + lane * VB;
         }
-        float acc[R][QT];
+        f32x2 acc[R][QT / 2];
 #pragma unroll
         for (int r = 0; r < R; r++)
 #pragma unroll
-            for (int q = 0; q < QT; q++) acc[r][q] = 0.0f;
+            for (int q = 0; q < QT / 2; q++) acc[r][q] = 0ull;
         const float *mnl = mn + lane * SP, *ivl = iv + lane * SP;
-        const float *ql = qs + lane * SP;
+        const float *ql = qs + (int64_t)lane * LS;
         const int nblk = (int)(dim / (16 * VB));
         for (int b = 0; b < nblk; b++) {
             uint32_t w[R][VB / 4];
@@ -324,41 +434,39 @@ struct CodecSQ8Perm {
                 const float4 i4 = *reinterpret_cast<const float4 *>(ivl + t0);
                 const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
                 const float ii[4] = {i4.x, i4.y, i4.z, i4.w};
-                float rec[R][4];
 #pragma unroll
-                for (int r = 0; r < R; r++)
+                for (int i = 0; i < 4; i++) {
+                    const ulonglong2 qa = *reinterpret_cast<const ulonglong2 *>(ql + (t0 + i) * QT);      // queries 0..3
+                    const ulonglong2 qb = *reinterpret_cast<const ulonglong2 *>(ql + (t0 + i) * QT + 4);  // queries 4..7
+                    const f32x2 qq[4] = {qa.x, qa.y, qb.x, qb.y};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
+                    for (int r = 0; r < R; r++) {
                         // byte -> float via 0x4B000000|b = 8388608+b (exact), minus 8388608 (exact)
                         const float f = __fsub_rn(__uint_as_float(__byte_perm(w[r][s4], 0x4B000000u, 0x7650 + i)), 8388608.0f);
-                        rec[r][i] = __fmaf_rn(f, ii[i], mm[i]);
-                    }
+                        const float nrec = __fmaf_rn(f, ii[i], mm[i]);
+                        const f32x2 n2 = pk2(nrec, nrec);
 #pragma unroll
-                for (int q = 0; q < QT; q++) {
-                    const float4 q4 = *reinterpret_cast<const float4 *>(ql + (int64_t)q * 16 * SP + t0);
-                    const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const float df = __fsub_rn(qq[i], rec[r][i]);
-                            acc[r][q] = __fmaf_rn(df, df, acc[r][q]);
+                        for (int q = 0; q < QT / 2; q++) {
+                            const f32x2 e = add2(qq[q], n2);
+                            acc[r][q] = fma2(e, e, acc[r][q]);
                         }
+                    }
                 }
             }
         }
+        float v[32];
 #pragma unroll
         for (int r = 0; r < R; r++)
 #pragma unroll
-            for (int q = 0; q < QT; q++) acc[r][q] = reduce16(acc[r][q]);
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (r0 + r >= row_end) continue;
-#pragma unroll
-                for (int q = 0; q < QT; q++)
-                    if (q < nqv) sink(q, r0 + r, acc[r][q]);
-            }
+            for (int q = 0; q < QT / 2; q++) unpk2(acc[r][q], v[r * QT + 2 * q], v[r * QT + 2 * q + 1]);
+        float o0, o1;
+        reduce16_transposed32(v, lane, o0, o1);
+        // lane l holds accumulators 2l, 2l+1 = (row l/4, queries 2(l%4), 2(l%4)+1)
+        const int64_t row = r0 + (lane >> 2);
+        const int qq0 = 2 * (lane & 3);
+        if (row < row_end) {
+            if (qq0 < nqv) sink(qq0, row, o0);
+            if (qq0 + 1 < nqv) sink(qq0 + 1, row, o1);
         }
     }
 };
@@ -501,21 +609,23 @@ struct CodecINT4 {
 // (permute_int4): inside each 128-byte block (256 dims = 4 epochs of 64) the
 // byte holding dims (64e + 16b + 2p, +1) of lane pair p sits at 16p + 4e + b,
 // so lanes 2p and 2p+1 read the same 16 bytes (one broadcast request) and get
-// their nibbles for 4 epochs x 4 blocks.
+// their nibbles for 4 epochs x 4 blocks.  Shared-memory layout and the packed
+// two-queries-per-instruction arithmetic are CodecSQ8Perm's: ndeq =
+// fma(g, -diff, -min) = -deq exactly, e = q + ndeq, S = fma(e, e, S).
 struct CodecINT4Perm {
     static constexpr int QT = 8, R = 2, THREADS = 256, RB = 16 * R, MINB = 2;
-    static size_t qsmem(const CodecParams &P) { return (size_t)(QT + 2) * 16 * CodecSQ8Perm<16>::steps_padded(P.dim) * 4; }
+    static size_t qsmem(const CodecParams &P) { return CodecSQ8Perm<16>::qsmem(P); }
     __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
-        CodecSQ8Perm<16>::stage(P, queries, qs_, q0, nqv, sm, tid);
+        CodecSQ8Perm<16>::stage(P, queries, qs_, q0, nqv, sm, tid);  // queries | -min | -diff
     }
     template <class Sink>
     __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
                                 int tid, const Sink &sink) {
         const float k15 = __uint_as_float(0x3d888889u);
         const int64_t dim = P.dim;
-        const int SP = CodecSQ8Perm<16>::steps_padded(dim);
+        const int SP = CodecSQ8Perm<16>::steps_padded(dim), LS = CodecSQ8Perm<16>::lane_stride(dim);
         const float *qs = reinterpret_cast<const float *>(sm);
-        const float *mn = qs + (int64_t)QT * 16 * SP, *dfp = mn + 16 * SP;
+        const float *mn = qs + (int64_t)16 * LS, *dfp = mn + 16 * SP;
         const int hw = tid >> 4, lane = tid & 15;
         const int64_t r0 = base + (int64_t)hw * R;
         const uint8_t *code[R];
@@ -526,12 +636,13 @@ struct CodecINT4Perm {
             code[r] = P.codes + rr * P.row_bytes + (lane >> 1) * 16;
         }
         const int shift = (lane & 1) ? 0 : 4;  // even lane (even dim) = high nibble
-        float s1[R][QT], s2[R][QT];
+        f32x2 s1[R][QT / 2], s2[R][QT / 2];
 #pragma unroll
         for (int r = 0; r < R; r++)
 #pragma unroll
-            for (int q = 0; q < QT; q++) s1[r][q] = s2[r][q] = 0.0f;
-        const float *mnl = mn + lane * SP, *dfl = dfp + lane * SP, *ql = qs + lane * SP;
+            for (int q = 0; q < QT / 2; q++) s1[r][q] = s2[r][q] = 0ull;
+        const float *mnl = mn + lane * SP, *dfl = dfp + lane * SP;
+        const float *ql = qs + (int64_t)lane * LS;
         const int nblk = (int)(dim / 256);
         for (int b = 0; b < nblk; b++) {
             uint32_t w[R][4];
@@ -550,43 +661,40 @@ struct CodecINT4Perm {
                 const float4 d4 = *reinterpret_cast<const float4 *>(dfl + t0);
                 const float mm[4] = {m4.x, m4.y, m4.z, m4.w};
                 const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
-                float deq[R][4];
 #pragma unroll
-                for (int r = 0; r < R; r++)
+                for (int blk = 0; blk < 4; blk++) {
+                    const ulonglong2 qa = *reinterpret_cast<const ulonglong2 *>(ql + (t0 + blk) * QT);
+                    const ulonglong2 qb = *reinterpret_cast<const ulonglong2 *>(ql + (t0 + blk) * QT + 4);
+                    const f32x2 qq[4] = {qa.x, qa.y, qb.x, qb.y};
 #pragma unroll
-                    for (int blk = 0; blk < 4; blk++) {
+                    for (int r = 0; r < R; r++) {
                         const uint32_t nib = (w[r][e] >> (8 * blk + shift)) & 0xFu;
                         const float f = __fsub_rn(__uint_as_float(0x4B000000u | nib), 8388608.0f);
-                        deq[r][blk] = __fmaf_rn(__fmul_rn(f, k15), dd[blk], mm[blk]);
-                    }
+                        const float ndeq = __fmaf_rn(__fmul_rn(f, k15), dd[blk], mm[blk]);
+                        const f32x2 n2 = pk2(ndeq, ndeq);
 #pragma unroll
-                for (int q = 0; q < QT; q++) {
-                    const float4 q4 = *reinterpret_cast<const float4 *>(ql + (int64_t)q * 16 * SP + t0);
-                    const float qq[4] = {q4.x, q4.y, q4.z, q4.w};
-#pragma unroll
-                    for (int blk = 0; blk < 4; blk++)
-#pragma unroll
-                        for (int r = 0; r < R; r++) {
-                            const float ee = __fsub_rn(qq[blk], deq[r][blk]);
-                            if (blk < 2) s1[r][q] = __fmaf_rn(ee, ee, s1[r][q]);
-                            else s2[r][q] = __fmaf_rn(ee, ee, s2[r][q]);
+                        for (int q = 0; q < QT / 2; q++) {
+                            const f32x2 ee = add2(qq[q], n2);
+                            if (blk < 2) s1[r][q] = fma2(ee, ee, s1[r][q]);
+                            else s2[r][q] = fma2(ee, ee, s2[r][q]);
                         }
+                    }
                 }
             }
         }
+        float v[16];
 #pragma unroll
         for (int r = 0; r < R; r++)
 #pragma unroll
-            for (int q = 0; q < QT; q++) s1[r][q] = reduce16(__fadd_rn(s1[r][q], s2[r][q]));
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < R; r++) {
-                if (r0 + r >= row_end) continue;
-#pragma unroll
-                for (int q = 0; q < QT; q++)
-                    if (q < nqv) sink(q, r0 + r, s1[r][q]);
+            for (int q = 0; q < QT / 2; q++) {
+                const f32x2 t = add2(s1[r][q], s2[r][q]);
+                unpk2(t, v[r * QT + 2 * q], v[r * QT + 2 * q + 1]);
             }
-        }
+        const float tot = reduce16_transposed16(v, lane);
+        // lane l holds accumulator l = (row l/8, query l%8)
+        const int64_t row = r0 + (lane >> 3);
+        const int q = lane & 7;
+        if (row < row_end && q < nqv) sink(q, row, tot);
     }
 };
 
@@ -675,6 +783,82 @@ struct CodecPQ {
                     tot = __fadd_rn(tot, tl[((int64_t)half * tail + m) * 256 + __ldg(code[r] + t16 * 16 + m)]);
                 sink(half, r0 + r, tot);
             }
+        }
+    }
+};
+
+// PQ ADC fast path (K = 256, codes tiled by permute_pq): ONE THREAD PER ROW, two
+// queries per CTA whose tables are interleaved as float2 (T_q0[m][c], T_q1[m][c]),
+// so a single 8-byte shared-memory lookup + one FADD2 advances both queries.
+// The thread keeps the reference's 16 lane accumulators itself (lane l sums
+// table[(16t+l)*256 + code[16t+l]] for t = 0,1,...), then applies the
+// _mm512_reduce_add_ps tree and the sequential tail (floats_avx512.c:135-167) —
+// the same additions in the same order as the half-warp version above.
+// Bound: random 8-byte LDS = 7.6 lookups/clk/SM measured (profiles/r01_ubench.log).
+struct CodecPQ2 {
+    static constexpr int QT = 2, R = 1, THREADS = 256, RB = THREADS, MINB = 1;
+    static size_t qsmem(const CodecParams &P) { return (size_t)P.pq_m * 256 * 8; }
+    __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
+        float2 *lut = reinterpret_cast<float2 *>(sm);
+        const int M = P.pq_m;
+        for (int idx = tid; idx < M * 256; idx += THREADS) {
+            const int m = idx >> 8, c = idx & 255;
+            float v[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int h = 0; h < 2; h++)
+                if (h < nqv) {
+                    if (P.pq_tables) v[h] = P.pq_tables[(int64_t)(q0 + h) * M * 256 + idx];
+                    else v[h] = CodecPQ::entry(P, queries + (int64_t)(q0 + h) * qs_, m, c);
+                }
+            lut[idx] = make_float2(v[0], v[1]);
+        }
+    }
+    template <class Sink>
+    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
+                                int tid, const Sink &sink) {
+        const int M = P.pq_m, t16 = M >> 4, tail = M & 15;
+        const int64_t row = base + tid;
+        const int64_t rr = row < row_end ? row : row_end - 1;
+        const uint8_t *cbase = P.codes + (rr >> 5) * (32 * P.row_bytes) + (rr & 31) * 16;
+        const unsigned char *lut = sm;
+        f32x2 acc[16];
+#pragma unroll
+        for (int j = 0; j < 16; j++) acc[j] = 0ull;
+        for (int t = 0; t < t16; t++) {
+            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(cbase + (int64_t)t * 512));
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const unsigned char *lt = lut + (size_t)t * 16 * 2048;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const uint32_t off = (j & 3) == 0 ? (w[j >> 2] << 3) & 0x7F8u : (w[j >> 2] >> (8 * (j & 3) - 3)) & 0x7F8u;
+                acc[j] = add2(acc[j], *reinterpret_cast<const f32x2 *>(lt + j * 2048 + off));
+            }
+        }
+        // _mm512_reduce_add_ps: i+8, i+4, i+2, i+1
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = add2(acc[j], acc[j + 8]);
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[j] = add2(acc[j], acc[j + 4]);
+        acc[0] = add2(acc[0], acc[2]);
+        acc[1] = add2(acc[1], acc[3]);
+        f32x2 tot = add2(acc[0], acc[1]);
+        if (tail) {
+            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(cbase + (int64_t)t16 * 512));
+            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
+            const unsigned char *lt = lut + (size_t)t16 * 16 * 2048;
+#pragma unroll
+            for (int j = 0; j < 15; j++) {
+                if (j < tail) {
+                    const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                    tot = add2(tot, *reinterpret_cast<const f32x2 *>(lt + j * 2048 + c * 8));
+                }
+            }
+        }
+        if (row < row_end) {
+            float s0, s1;
+            unpk2(tot, s0, s1);
+            sink(0, row, s0);
+            if (nqv > 1) sink(1, row, s1);
         }
     }
 };
@@ -950,7 +1134,7 @@ static vg_status run_dense(const CodecParams &cp, const float *q, int64_t nq, in
             return (cp.variant & VG_VAR_PERM) ? FN<CodecINT4Perm>(__VA_ARGS__) : FN<CodecINT4>(__VA_ARGS__);     \
         case VG_CODEC_PQ:                                                                                        \
         case VG_CODEC_OPQ:                                                                                       \
-            return FN<CodecPQ>(__VA_ARGS__);                                                                     \
+            return (cp.variant & VG_VAR_PERM) ? FN<CodecPQ2>(__VA_ARGS__) : FN<CodecPQ>(__VA_ARGS__);            \
         default:                                                                                                 \
             break;                                                                                               \
     }
