@@ -107,6 +107,9 @@ _SIGS = {
     "vg_index_rerank": [u64, f32p, i64, u32p, i64, f32p],
     "vg_index_rerank_dev": [u64, vp, i64, vp, i64, vp],
     "vg_index_search_rerank": [u64, f32p, i64, i64, i64, u32p, f32p, i32p],
+    "vg_flat_tc_enable": [i32],
+    "vg_flat_tc_stats": [u64p, u64p],
+    "vg_flat_tc_candidates": [u64, f32p, i64, i64, u32p, f32p, i32p],
     "vg_flat_open": [u8p, sz, i32, u64p],
     "vg_flat_decode_header": [u8p, sz, C.POINTER(FlatHeader)],
     "vg_index_fetch_ids": [u64, u32p, i64, u64p],

@@ -14,6 +14,7 @@
 #include "vg_kmeans.cuh"
 #include "vg_quant.cuh"
 #include "vg_scan.cuh"
+#include "vg_flat_tc.cuh"
 
 namespace vg {
 
@@ -135,6 +136,9 @@ struct Index {
     std::vector<uint32_t> h_part_off;
     int words32 = 0;
     bool has_vectors = false, has_codes = false, has_ids = false;
+    // tensor-core Flat filter state (vg_flat_tc.cu): squared row norms + their maximum, rebuilt after uploads
+    DevBuf xn, xmax;
+    bool xn_dirty = true;
     size_t device_bytes() const {
         return codes.bytes + vectors.bytes + p0.bytes + p1.bytes + norms.bytes + ids.bytes + pq_cb.bytes + centroids.bytes;
     }
@@ -294,7 +298,7 @@ vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
             VG_TRY(to_device(ix->pq_scales, d.pq_scales, (size_t)d.pq_m));
             VG_TRY(to_device(ix->pq_offsets, d.pq_offsets, (size_t)d.pq_m));
             // thread-per-row ADC scan with a two-query float2 table (M*256*8 B of shared memory): K=256 only
-            if (d.pq_k == 256 && (size_t)d.pq_m * 2048 <= 200 * 1024) {
+            if (d.pq_k == 256 && d.pq_m <= 96) {  // 192 KB of tables + 32 KB of top-k state
                 ix->variant = VG_VAR_PERM;
                 ix->dev_row_bytes = (d.pq_m + 15) / 16 * 16;
             }
@@ -413,6 +417,7 @@ vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const voi
         VG_CUDA(cudaMemcpyAsync(ix->vectors.as<float>() + row0 * ix->d.dim, d_vectors, (size_t)n * ix->d.dim * 4,
                                 cudaMemcpyDeviceToDevice, stream()));
         ix->has_vectors = true;
+        ix->xn_dirty = true;
     }
     return VG_OK;
 }
@@ -441,6 +446,7 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
         VG_TRY(ensure_vectors(ix));
         VG_TRY(staged_h2d(ix->vectors.as<float>() + row0 * ix->d.dim, h_vectors, (size_t)n * ix->d.dim * 4));
         ix->has_vectors = true;
+        ix->xn_dirty = true;
     }
     return VG_OK;
 }
@@ -470,6 +476,120 @@ __global__ void __launch_bounds__(256) opq_rotate_kernel(const float *v, int64_t
     }
 }
 
+// Flat float32 search through the tcgen05 filter (vg_flat_tc.cu): candidates by TF32 GEMM, exact re-check in simd
+// pair order, certificate; queries whose certificate fails are re-run on the exact CUDA-core scan below.
+static std::atomic<int> g_tc_enabled{-1};
+static std::atomic<uint64_t> g_tc_queries{0}, g_tc_fallbacks{0};
+static bool tc_enabled() {
+    int v = g_tc_enabled.load();
+    if (v < 0) {
+        const char *e = getenv("VECGO_FLAT_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_tc_enabled.store(v);
+    }
+    return v != 0;
+}
+__global__ void gather_rows_kernel(const float *src, const int32_t *idx, int64_t n, int64_t dim, float *dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    const int64_t r = i / dim, c = i - r * dim;
+    dst[i] = src[(int64_t)idx[r] * dim + c];
+}
+__global__ void scatter_results_kernel(const uint32_t *rows, const float *scores, const int32_t *counts, const int32_t *idx, int64_t n,
+                                       int64_t k, uint32_t *out_rows, float *out_scores, int32_t *out_counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * k) return;
+    const int64_t r = i / k, c = i - r * k;
+    out_rows[(int64_t)idx[r] * k + c] = rows[i];
+    out_scores[(int64_t)idx[r] * k + c] = scores[i];
+    if (c == 0) out_counts[idx[r]] = counts[r];
+}
+static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
+    if (!ix->xn_dirty && ix->xn.p) return VG_OK;
+    const int64_t rows = ix->d.rows;
+    if (!ix->xn.p) VG_TRY(ix->xn.alloc((size_t)rows * 4));
+    if (!ix->xmax.p) VG_TRY(ix->xmax.alloc(16));
+    VG_CUDA(cudaMemsetAsync(ix->xmax.p, 0, 16, st));
+    VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
+    ix->xn_dirty = false;
+    return VG_OK;
+}
+static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, int64_t k, const uint8_t *d_mask, uint32_t *d_rows,
+                                float *d_scores, int32_t *d_counts, bool *handled) {
+    *handled = false;
+    const vg_index_desc &d = ix->d;
+    if (!tc_enabled() || d.codec != VG_CODEC_F32 || d.num_partitions > 1 || !ix->has_vectors) return VG_OK;
+    if (!tc::supported(d.dim, d.rows, nq, k)) return VG_OK;
+    if ((reinterpret_cast<uintptr_t>(d_queries) & 15) != 0) return VG_OK;  // TMA needs 16-byte aligned bases
+    cudaStream_t st = stream();
+    VG_TRY(ensure_row_norms(ix, st));
+    const int is_dot = d.metric != VG_METRIC_L2;
+    tc::FilterArgs f;
+    f.d_queries = d_queries;
+    f.d_vectors = ix->vectors.as<float>();
+    f.d_xn = ix->xn.as<float>();
+    f.d_mask = d_mask;
+    f.nq = nq;
+    f.rows = d.rows;
+    f.dim = d.dim;
+    f.kc = tc::candidates_for(k);
+    f.is_dot = is_dot;
+    f.row_base = (uint32_t)d.row_base;
+    DevBuf crow, cs, ccnt, qn, failb;
+    VG_TRY(crow.alloc((size_t)nq * f.kc * 4));
+    VG_TRY(cs.alloc((size_t)nq * f.kc * 4));
+    VG_TRY(ccnt.alloc((size_t)nq * 4));
+    VG_TRY(qn.alloc((size_t)nq * 4));
+    VG_TRY(failb.alloc((size_t)nq * 4));
+    f.d_cand_rows = crow.as<uint32_t>();
+    f.d_cand_s = cs.as<float>();
+    f.d_cand_cnt = ccnt.as<int32_t>();
+    VG_TRY(tc::sqnorms(d_queries, nq, d.dim, qn.as<float>(), nullptr, st));
+    VG_TRY(tc::filter(f, st));
+    VG_TRY(tc::finalize(f, (int)k, qn.as<float>(), ix->xmax.as<unsigned int>(), d_rows, d_scores, d_counts, failb.as<int32_t>(), st));
+    std::vector<int32_t> h_fail((size_t)nq);
+    VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> bad;
+    for (int64_t q = 0; q < nq; q++)
+        if (h_fail[(size_t)q]) bad.push_back((int32_t)q);
+    g_tc_queries.fetch_add((uint64_t)nq);
+    g_tc_fallbacks.fetch_add((uint64_t)bad.size());
+    if (!bad.empty()) {
+        // exact CUDA-core scan for the queries the certificate could not clear
+        const int64_t nb = (int64_t)bad.size();
+        DevBuf bidx, bq, brow, bsc, bcnt;
+        VG_TRY(bidx.alloc((size_t)nb * 4));
+        VG_TRY(bq.alloc((size_t)nb * d.dim * 4));
+        VG_TRY(brow.alloc((size_t)nb * k * 4));
+        VG_TRY(bsc.alloc((size_t)nb * k * 4));
+        VG_TRY(bcnt.alloc((size_t)nb * 4));
+        VG_CUDA(cudaMemcpyAsync(bidx.p, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        gather_rows_kernel<<<(unsigned)((nb * d.dim + 255) / 256), 256, 0, st>>>(d_queries, bidx.as<int32_t>(), nb, d.dim, bq.as<float>());
+        VG_LAUNCHED();
+        CodecParams cp = params_of(*ix);
+        ScanArgs a;
+        a.queries = bq.as<float>();
+        a.nq = nb;
+        a.rows = d.rows;
+        a.k = (int)k;
+        a.descending = is_dot;
+        a.is_dot = is_dot;
+        a.row_base = (uint32_t)d.row_base;
+        a.mask = d_mask;
+        a.out_rows = brow.as<uint32_t>();
+        a.out_scores = bsc.as<float>();
+        a.out_counts = bcnt.as<int32_t>();
+        VG_TRY(scan_topk(cp, a, st));
+        scatter_results_kernel<<<(unsigned)((nb * k + 255) / 256), 256, 0, st>>>(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(),
+                                                                                bidx.as<int32_t>(), nb, k, d_rows, d_scores, d_counts);
+        VG_LAUNCHED();
+        VG_CUDA(cudaStreamSynchronize(st));
+    }
+    *handled = true;
+    return VG_OK;
+}
+
 static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
                                  const uint8_t *d_mask, uint32_t *d_rows, float *d_scores, int32_t *d_counts) {
     if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
@@ -477,6 +597,11 @@ static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, 
     const vg_index_desc &d = ix->d;
     if (d.codec == VG_CODEC_F32 ? !ix->has_vectors : !ix->has_codes) {
         if (d.rows > 0) return fail(VG_ERR_STATE, "index rows were never uploaded");
+    }
+    {
+        bool handled = false;
+        VG_TRY(flat_tc_search(ix, d_queries, nq, k, d_mask, d_rows, d_scores, d_counts, &handled));
+        if (handled) return VG_OK;
     }
     cudaStream_t st = stream();
     CodecParams cp = params_of(*ix);
@@ -549,6 +674,50 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
     return search_dev_impl(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts);
+}
+
+vg_status vg_flat_tc_enable(int32_t on) {
+    g_tc_enabled.store(on ? 1 : 0);
+    return VG_OK;
+}
+vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
+    if (queries) *queries = g_tc_queries.load();
+    if (fallbacks) *fallbacks = g_tc_fallbacks.load();
+    return VG_OK;
+}
+vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_rows, float *h_s,
+                                int32_t *h_counts) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (ix->d.codec != VG_CODEC_F32 || !ix->has_vectors) return fail(VG_ERR_STATE, "not a float32 index");
+    if (kc != 32 && (kc < 33 || kc > 96)) return fail(VG_ERR_INVALID, "kc must be 32 or in 33..96");
+    if (!tc::supported(ix->d.dim, ix->d.rows, nq, 1)) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
+    cudaStream_t st = stream();
+    VG_TRY(ensure_row_norms(ix, st));
+    DevBuf q, crow, cs, ccnt;
+    VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
+    VG_TRY(crow.alloc((size_t)nq * kc * 4));
+    VG_TRY(cs.alloc((size_t)nq * kc * 4));
+    VG_TRY(ccnt.alloc((size_t)nq * 4));
+    tc::FilterArgs f;
+    f.d_queries = q.as<float>();
+    f.d_vectors = ix->vectors.as<float>();
+    f.d_xn = ix->xn.as<float>();
+    f.nq = nq;
+    f.rows = ix->d.rows;
+    f.dim = ix->d.dim;
+    f.kc = (int)kc;
+    f.is_dot = ix->d.metric != VG_METRIC_L2;
+    f.row_base = (uint32_t)ix->d.row_base;
+    f.d_cand_rows = crow.as<uint32_t>();
+    f.d_cand_s = cs.as<float>();
+    f.d_cand_cnt = ccnt.as<int32_t>();
+    VG_TRY(tc::filter(f, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    VG_TRY(staged_d2h(h_rows, crow.p, (size_t)nq * kc * 4));
+    VG_TRY(staged_d2h(h_s, cs.p, (size_t)nq * kc * 4));
+    return staged_d2h(h_counts, ccnt.p, (size_t)nq * 4);
 }
 
 vg_status vg_index_search(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes,

@@ -15,6 +15,8 @@
 // there are too few query tiles to fill 148 SMs; partials are merged by
 // merge_keys_kernel).  All CTAs sweep rows in the same direction, so code
 // tiles are served from the 126 MB L2 after the first CTA touched them.
+#include <type_traits>
+
 #include "vg_scan.cuh"
 
 namespace vg {
@@ -796,7 +798,14 @@ struct CodecPQ {
 // the same additions in the same order as the half-warp version above.
 // Bound: random 8-byte LDS = 7.6 lookups/clk/SM measured (profiles/r01_ubench.log).
 struct CodecPQ2 {
-    static constexpr int QT = 2, R = 1, THREADS = 256, RB = THREADS, MINB = 1;
+    static constexpr int QT = 2, R = 1, THREADS = 512, RB = THREADS, MINB = 1;
+    static constexpr bool PIPELINED = true;
+    static constexpr int MAXCH = 6;  // code chunks of 16 subspaces held in registers: M <= 96
+    // The codes of the NEXT tile are requested before the current tile's lookups start, so the L2/HBM latency
+    // overlaps ~100 shared-memory lookups instead of being exposed after every block-wide barrier.
+    struct State {
+        uint4 w4[MAXCH];
+    };
     static size_t qsmem(const CodecParams &P) { return (size_t)P.pq_m * 256 * 8; }
     __device__ static void stage(const CodecParams &P, const float *queries, int64_t qs_, int q0, int nqv, unsigned char *sm, int tid) {
         float2 *lut = reinterpret_cast<float2 *>(sm);
@@ -813,25 +822,40 @@ struct CodecPQ2 {
             lut[idx] = make_float2(v[0], v[1]);
         }
     }
+    __device__ static void prefetch(const CodecParams &P, State &st, int64_t base, int64_t row_end, int tid) {
+        const int chunks = (P.pq_m + 15) >> 4;
+        int64_t rr = base + tid;
+        if (rr > row_end - 1) rr = row_end - 1;
+        if (rr < 0) rr = 0;
+        const uint8_t *cbase = P.codes + (rr >> 5) * (32 * P.row_bytes) + (rr & 31) * 16;
+#pragma unroll
+        for (int t = 0; t < MAXCH; t++)
+            if (t < chunks) st.w4[t] = __ldg(reinterpret_cast<const uint4 *>(cbase + (int64_t)t * 512));
+    }
+    // `next_base`: first row of the tile this thread block will process after this one (prefetched here).
     template <class Sink>
-    __device__ static void tile(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t row_end, int nqv,
-                                int tid, const Sink &sink) {
+    __device__ static void tile_p(const CodecParams &P, bool, const unsigned char *sm, int64_t base, int64_t next_base,
+                                  int64_t row_end, int nqv, int tid, const Sink &sink, State &st) {
         const int M = P.pq_m, t16 = M >> 4, tail = M & 15;
         const int64_t row = base + tid;
-        const int64_t rr = row < row_end ? row : row_end - 1;
-        const uint8_t *cbase = P.codes + (rr >> 5) * (32 * P.row_bytes) + (rr & 31) * 16;
         const unsigned char *lut = sm;
+        uint4 w4[MAXCH];
+#pragma unroll
+        for (int t = 0; t < MAXCH; t++) w4[t] = st.w4[t];
+        if (next_base < row_end) prefetch(P, st, next_base, row_end, tid);
         f32x2 acc[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) acc[j] = 0ull;
-        for (int t = 0; t < t16; t++) {
-            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(cbase + (int64_t)t * 512));
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-            const unsigned char *lt = lut + (size_t)t * 16 * 2048;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const uint32_t off = (j & 3) == 0 ? (w[j >> 2] << 3) & 0x7F8u : (w[j >> 2] >> (8 * (j & 3) - 3)) & 0x7F8u;
-                acc[j] = add2(acc[j], *reinterpret_cast<const f32x2 *>(lt + j * 2048 + off));
+        for (int t = 0; t < MAXCH; t++) {
+            if (t < t16) {
+                const uint32_t w[4] = {w4[t].x, w4[t].y, w4[t].z, w4[t].w};
+                const unsigned char *lt = lut + (size_t)t * 16 * 2048;
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                    const uint32_t off = (j & 3) == 0 ? (w[j >> 2] << 3) & 0x7F8u : (w[j >> 2] >> (8 * (j & 3) - 3)) & 0x7F8u;
+                    acc[j] = add2(acc[j], *reinterpret_cast<const f32x2 *>(lt + j * 2048 + off));
+                }
             }
         }
         // _mm512_reduce_add_ps: i+8, i+4, i+2, i+1
@@ -843,14 +867,18 @@ struct CodecPQ2 {
         acc[1] = add2(acc[1], acc[3]);
         f32x2 tot = add2(acc[0], acc[1]);
         if (tail) {
-            const uint4 w4 = __ldg(reinterpret_cast<const uint4 *>(cbase + (int64_t)t16 * 512));
-            const uint32_t w[4] = {w4.x, w4.y, w4.z, w4.w};
-            const unsigned char *lt = lut + (size_t)t16 * 16 * 2048;
 #pragma unroll
-            for (int j = 0; j < 15; j++) {
-                if (j < tail) {
-                    const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
-                    tot = add2(tot, *reinterpret_cast<const f32x2 *>(lt + j * 2048 + c * 8));
+            for (int t = 0; t < MAXCH; t++) {
+                if (t == t16) {
+                    const uint32_t w[4] = {w4[t].x, w4[t].y, w4[t].z, w4[t].w};
+                    const unsigned char *lt = lut + (size_t)t * 16 * 2048;
+#pragma unroll
+                    for (int j = 0; j < 15; j++) {
+                        if (j < tail) {
+                            const uint32_t c = (w[j >> 2] >> (8 * (j & 3))) & 0xFFu;
+                            tot = add2(tot, *reinterpret_cast<const f32x2 *>(lt + j * 2048 + c * 8));
+                        }
+                    }
                 }
             }
         }
@@ -935,6 +963,11 @@ struct CodecSign {
 };
 
 // ============================================================ kernels
+template <class T, class = void>
+struct is_pipelined : std::false_type {};
+template <class T>
+struct is_pipelined<T, std::enable_if_t<T::PIPELINED>> : std::true_type {};
+
 template <class Codec>
 __global__ void __launch_bounds__(Codec::THREADS, Codec::MINB) scan_topk_kernel(CodecParams P, ScanArgs A, size_t qbytes) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -958,10 +991,20 @@ __global__ void __launch_bounds__(Codec::THREADS, Codec::MINB) scan_topk_kernel(
     const int64_t row_begin = (int64_t)split * A.rows_per_split;
     int64_t row_end = row_begin + A.rows_per_split;
     if (row_end > A.rows) row_end = A.rows;
-    for (int64_t base = row_begin; base < row_end; base += Codec::RB) {
-        Codec::tile(P, A.is_dot != 0, smem, base, row_end, nqv, tid, sink);
-        __syncthreads();
-        topk_block_maintain(sink.tk, Codec::QT, tid, Codec::THREADS);
+    if constexpr (is_pipelined<Codec>::value) {
+        typename Codec::State stt;
+        Codec::prefetch(P, stt, row_begin, row_end, tid);
+        for (int64_t base = row_begin; base < row_end; base += Codec::RB) {
+            Codec::tile_p(P, A.is_dot != 0, smem, base, base + Codec::RB, row_end, nqv, tid, sink, stt);
+            __syncthreads();
+            topk_block_maintain(sink.tk, Codec::QT, tid, Codec::THREADS);
+        }
+    } else {
+        for (int64_t base = row_begin; base < row_end; base += Codec::RB) {
+            Codec::tile(P, A.is_dot != 0, smem, base, row_end, nqv, tid, sink);
+            __syncthreads();
+            topk_block_maintain(sink.tk, Codec::QT, tid, Codec::THREADS);
+        }
     }
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -985,8 +1028,16 @@ scan_dense_kernel(CodecParams P, const float *queries, int64_t nq, int64_t n, in
     SinkDense sink{out, n, q0};
     Codec::stage(P, queries, P.dim, q0, nqv, smem, tid);
     __syncthreads();
-    for (int64_t base = (int64_t)blockIdx.y * Codec::RB; base < n; base += (int64_t)gridDim.y * Codec::RB)
-        Codec::tile(P, is_dot != 0, smem, base, n, nqv, tid, sink);
+    if constexpr (is_pipelined<Codec>::value) {
+        typename Codec::State stt;
+        const int64_t step = (int64_t)gridDim.y * Codec::RB;
+        Codec::prefetch(P, stt, (int64_t)blockIdx.y * Codec::RB, n, tid);
+        for (int64_t base = (int64_t)blockIdx.y * Codec::RB; base < n; base += step)
+            Codec::tile_p(P, is_dot != 0, smem, base, base + step, n, nqv, tid, sink, stt);
+    } else {
+        for (int64_t base = (int64_t)blockIdx.y * Codec::RB; base < n; base += (int64_t)gridDim.y * Codec::RB)
+            Codec::tile(P, is_dot != 0, smem, base, n, nqv, tid, sink);
+    }
 }
 
 // One warp per query merges `lists` sorted key lists.
