@@ -1,0 +1,150 @@
+"""GPU parity tests of the tcgen05 Flat path (vecgo_b200/csrc/vg_flat_tc.cu) through the C ABI.
+
+The tensor-core GEMM only FILTERS; what vg_index_search returns must be bit-identical to
+flat.(*Segment).Search on the SIMD path: row ids with ties by row id, float32 scores in
+simd.SquaredL2 / simd.Dot summation order (checked against the CPU oracle), whatever the
+filter did — including the cases where its certificate fails and the exact scan takes over.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+def bits(x):
+    return np.ascontiguousarray(x, F).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def vg():
+    import vecgo_b200
+
+    return vecgo_b200
+
+
+def tc_stats(vg):
+    q, f = C.c_uint64(), C.c_uint64()
+    vg._lib.call("vg_flat_tc_stats", C.byref(q), C.byref(f))
+    return q.value, f.value
+
+
+def oracle_topk(q, k, **kw):
+    seg = o.FlatOracle(**kw)
+    out, cnt = seg.search_batch(q, k, threads=8, mask=kw.get("mask"))
+    return [out[i, : cnt[i]] for i in range(len(q))]
+
+
+def check(rows, scores, counts, want):
+    for i, w in enumerate(want):
+        c = int(counts[i])
+        assert c == len(w), (i, c, len(w))
+        assert np.array_equal(rows[i, :c], w["row"]), i
+        assert np.array_equal(bits(scores[i, :c]), bits(w["score"])), i
+        assert np.all(rows[i, c:] == 0xFFFFFFFF)
+
+
+@pytest.mark.parametrize("metric", [0, 2])
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (4096, 128, 256, 10),     # resident query tile, exact multiples
+    (5000, 100, 33, 10),      # dim % 32 != 0 (TMA zero fill), ragged query / row tiles
+    (20000, 36, 300, 1),      # k = 1, two query tiles
+    (3000, 768, 17, 32),      # streamed query tile (dim > 128), k = 32 -> 64 candidates
+    (70000, 64, 1000, 5),     # many row splits
+])
+def test_tc_search_matches_oracle(vg, metric, n, dim, nq, k):
+    rng = np.random.default_rng(n * 7 + dim)
+    x = (rng.random((n, dim)) - (0.5 if metric else 0.0)).astype(F)
+    q = (rng.random((nq, dim)) - (0.5 if metric else 0.0)).astype(F)
+    if metric == 2:
+        x, _ = vg.distance.NormalizeL2Batch(x)
+    x[n // 2] = x[n // 3]          # duplicate rows -> equal scores -> tie broken by row id
+    q[0] = x[n // 3]               # a query equal to a stored row (score 0 / max dot)
+    vg._lib.call("vg_flat_tc_enable", 1)
+    before = tc_stats(vg)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=metric, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        rows, scores, counts = ix.search(q, k)
+    after = tc_stats(vg)
+    assert after[0] - before[0] == nq, "the search did not go through the tensor-core filter"
+    check(rows, scores, counts, oracle_topk(q, k, dim=dim, metric=metric, vectors=x))
+
+
+def test_tc_filter_error_within_certificate_bound(vg):
+    """vg_flat_tc_candidates: approximate s = ||x||^2 - 2 q.x of the returned rows vs float64, against the bound E."""
+    n, dim, nq, kc = 50_000, 128, 64, 32
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=0, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        rows = np.zeros((nq, kc), np.uint32)
+        s = np.zeros((nq, kc), F)
+        cnt = np.zeros(nq, np.int32)
+        L = vg._lib
+        L.call("vg_flat_tc_candidates", ix.handle, L.ptr(q, L.f32p), nq, kc, L.ptr(rows, L.u32p), L.ptr(s, L.f32p), L.ptr(cnt, L.i32p))
+    assert np.all(cnt == kc)
+    x64, q64 = x.astype(np.float64), q.astype(np.float64)
+    s_true = np.sum(x64 * x64, 1)[None, :] - 2 * q64 @ x64.T
+    err = np.abs(np.take_along_axis(s_true, rows.astype(np.int64), 1) - s)
+    qn, xmax = np.sum(q64 * q64, 1), np.sum(x64 * x64, 1).max()
+    E = 1.125 / 256 * np.sqrt(qn * xmax) + (qn + xmax) / 16384
+    assert np.all(err.max(1) <= E), float((err.max(1) / E).max())
+    # the filter's candidate list is the top-kc by approximate score, so the true top-10 must be inside
+    top = np.argsort(s_true, axis=1, kind="stable")[:, :10]
+    for i in range(nq):
+        assert set(top[i]) <= set(rows[i].tolist())
+
+
+def test_tc_certificate_failure_falls_back_to_exact_scan(vg):
+    """Rows that are all (nearly) equidistant defeat any approximate filter: the certificate must fail and the exact
+    scan must produce the reference answer (ties by row id)."""
+    n, dim, nq, k = 6000, 64, 40, 10
+    rng = np.random.default_rng(9)
+    base = rng.random(dim).astype(F)
+    x = np.tile(base, (n, 1))
+    x[:, 0] += (np.arange(n) % 7).astype(F) * F(1e-6)   # thousands of exact ties and near-ties
+    q = rng.random((nq, dim)).astype(F)
+    vg._lib.call("vg_flat_tc_enable", 1)
+    before = tc_stats(vg)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=0, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        rows, scores, counts = ix.search(q, k)
+    after = tc_stats(vg)
+    assert after[1] - before[1] == nq, "every query should have needed the exact re-run"
+    check(rows, scores, counts, oracle_topk(q, k, dim=dim, metric=0, vectors=x))
+
+
+def test_tc_row_mask(vg):
+    n, dim, nq, k = 9000, 96, 50, 10
+    rng = np.random.default_rng(11)
+    x = rng.random((n, dim)).astype(F)
+    q = rng.random((nq, dim)).astype(F)
+    keep = rng.random(n) < 0.4
+    mask = np.packbits(keep, bitorder="little")
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=0, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        rows, scores, counts = ix.search(q, k, row_mask=mask)
+    seg = o.FlatOracle(dim=dim, metric=0, vectors=x)
+    out, cnt = seg.search_batch(q, k, mask=mask)
+    check(rows, scores, counts, [out[i, : cnt[i]] for i in range(nq)])
+    assert keep[rows[:, :k].reshape(-1)].all()
+
+
+def test_tc_equals_exact_scan_config1(vg):
+    """BASELINE configs[0] shape: the filter path and the exact CUDA-core scan return identical bits."""
+    n, dim, nq, k = 100_000, 128, 1000, 10
+    x = np.random.default_rng(42).random((n, dim), dtype=F)
+    q = np.random.default_rng(43).random((nq, dim), dtype=F)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=0, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        vg._lib.call("vg_flat_tc_enable", 1)
+        r1, s1, c1 = ix.search(q, k)
+        vg._lib.call("vg_flat_tc_enable", 0)
+        r0, s0, c0 = ix.search(q, k)
+        vg._lib.call("vg_flat_tc_enable", 1)
+    assert np.array_equal(r0, r1) and np.array_equal(bits(s0), bits(s1)) and np.array_equal(c0, c1)

@@ -30,7 +30,7 @@ def main():
     L.call("vg_init", 0)
     ix = vg.index.DeviceIndex(codec=L.CODEC_F32, metric=metric, dim=dim, rows=n)
     ix.upload(vectors=x)
-    kc = 32 if k <= 10 else k + 32
+    kc = 32 if k <= 16 else 2 * k
     rows = np.zeros((nq, kc), np.uint32)
     s = np.zeros((nq, kc), np.float32)
     cnt = np.zeros(nq, np.int32)

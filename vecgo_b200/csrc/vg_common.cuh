@@ -44,6 +44,7 @@ vg_status ensure_init();  // binds the thread to the library's device (vg_init(0
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
+    bool pooled = false;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;

@@ -27,17 +27,19 @@
 // c1 = 2^-8 * 1.125 (L2) or 2^-9 * 1.125 (dot), c2 = 2^-14 (norm rounding, accumulation
 // slack).  tests/test_gpu_flat_tc.py measures the realised error against E.
 //
-// Kernel (one CTA = 128 queries x a contiguous row range, 192 threads):
-//   warp 0     TMA producer: cp.async.bulk.tensor.2d of the 128 x 32-float query
-//              k-block (A) and the BN x 32-float row k-block (B), 128B swizzle,
-//              STAGES-deep mbarrier ring
-//   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128, N=BN, K=8,
-//              fp32 accumulators in TMEM, double-buffered (2 x BN columns)
-//   warps 2-5  epilogue: tcgen05.ld 32 columns at a time; thread = one query
-//              (TMEM lane), threshold in a register, candidate buffer private to
-//              the thread in shared memory (no atomics); warp-cooperative bitonic
-//              compaction when a buffer fills
+// Kernel (one CTA = 256 queries x a contiguous row range, 320 threads):
+//   warp 0     TMA producer (cp.async.bulk.tensor.2d, 128B swizzle).  dim <= 128: the 256 x dim
+//              query tile is loaded ONCE and stays resident (128 KB), only 128-row B tiles stream
+//              through a 4-stage mbarrier ring; larger dims stream A and B k-blocks together.
+//   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 x N=128 x K=8, two M halves
+//              per B tile, fp32 accumulators in TMEM (2 stages x 2 halves x 128 columns = 512)
+//   warps 2-9  epilogue: one thread = one query (= one TMEM lane).  tcgen05.ld 32 columns, 32
+//              independent FFMA + compares build a pass mask (no branch per column); the rare
+//              survivors go to the query's private candidate buffer in global memory (L2) — no
+//              atomics; a full buffer is compacted by its warp with a register bitonic sort.
 #include <cuda.h>
+
+#include <algorithm>
 
 #include "vg_flat_tc.cuh"
 #include "vg_topk.cuh"
@@ -45,9 +47,10 @@
 namespace vg {
 namespace tc {
 
-constexpr int BM = 128;   // queries per tile (UMMA M, = TMEM lanes)
-constexpr int BK = 32;    // floats per k-block: one 128-byte swizzle atom
-constexpr int NTHREADS = 192;
+constexpr int BM = 128;    // UMMA M (= TMEM lanes)
+constexpr int BMQ = 256;   // queries per CTA: two UMMA M halves that share every B tile
+constexpr int BK = 32;     // floats per k-block: one 128-byte swizzle atom
+constexpr int NTHREADS = 320;
 
 // ------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -120,67 +123,105 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
 }
 
 // ------------------------------------------------------------------ kernel
+constexpr int BN = 128;        // database rows per tile (UMMA N)
+constexpr int CBUF = 128;      // candidate keys per (query, row split) in global memory
+constexpr int STAGES = 4;
+constexpr int A_KB_BYTES = BMQ * BK * 4;   // 32 KB: one k-block of the 256-query tile (two UMMA M=128 halves)
+constexpr int B_KB_BYTES = BN * BK * 4;    // 16 KB
+constexpr int MAX_RES_KB = 4;              // query tile kept resident in shared memory when dim <= 128
+
 struct Args {
     const float *xn;        // [rows] ||x||^2 (L2) or nullptr (dot)
     const uint8_t *mask;    // optional row bitmap
     int64_t nq, rows, rows_per_split;
     int kb;                 // k-blocks = ceil(dim / 32)
     int kc;                 // candidates kept per query (k')
-    int is_dot;
     uint32_t row_base;
-    unsigned long long *partial;  // [nq][splits][kc] ascending keys, VG_KEY_EMPTY padded
+    unsigned long long *cand;  // [nq_pad][splits][CBUF] keys (unsorted)
+    int32_t *cand_cnt;         // [nq_pad][splits]
 };
 
-template <int BN, int STAGES, int C>
+template <bool RESIDENT>
 struct Smem {
-    static constexpr int A_BYTES = BM * BK * 4;        // 16 KB
-    static constexpr int B_BYTES = BN * BK * 4;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int KEY_STRIDE = C + 1;            // 8-byte words per query slot (+1: pushes of a warp spread over banks)
-    static constexpr size_t OFF_KEYS = (size_t)STAGES * STAGE_BYTES;
-    static constexpr size_t OFF_XN = OFF_KEYS + (size_t)BM * KEY_STRIDE * 8;
+    // RESIDENT: [A: kb x 32 KB][B ring: STAGES x 16 KB];  streaming: [ring: STAGES x (32 KB A + 16 KB B)]
+    static constexpr int STAGE_BYTES = RESIDENT ? B_KB_BYTES : A_KB_BYTES + B_KB_BYTES;
+    static constexpr size_t OFF_RING = RESIDENT ? (size_t)MAX_RES_KB * A_KB_BYTES : 0;
+    static constexpr size_t OFF_XN = OFF_RING + (size_t)STAGES * STAGE_BYTES;
     static constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
-    static constexpr size_t TOTAL = OFF_BAR + (size_t)(2 * STAGES + 4) * 8 + 16;
+    static constexpr size_t TOTAL = OFF_BAR + (size_t)(2 * STAGES + 5) * 8 + 16;
 };
 
-// Warp-cooperative: sort `n` keys of one slot ascending (bitonic over the power-of-two
-// prefix), keep the best kc.  Returns the new count; *tau_out = kc-th key or EMPTY.
-__device__ __forceinline__ int compact_slot(unsigned long long *a, int n, int kc, int cap, int lane, unsigned long long *tau_out) {
-    int len = 32;
-    while (len < n) len <<= 1;
-    if (len > cap) len = cap;
-    for (int i = n + lane; i < len; i += 32) a[i] = VG_KEY_EMPTY;
-    __syncwarp();
-    for (int size = 2; size <= len; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = lane; i < (len >> 1); i += 32) {
-                const int lo = 2 * i - (i & (stride - 1));
-                const int hi = lo + stride;
-                const bool up = ((lo & size) == 0);
-                const unsigned long long x = a[lo], y = a[hi];
-                if ((x > y) == up) {
-                    a[lo] = y;
-                    a[hi] = x;
+// ---- 128-key bitonic sort held in registers by one warp: element e = 4*lane + r.
+__device__ __forceinline__ void cswap(unsigned long long &a, unsigned long long &b, bool up) {
+    const bool sw = (a > b) == up;
+    const unsigned long long x = sw ? b : a, y = sw ? a : b;
+    a = x;
+    b = y;
+}
+__device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ void warp_sort128(unsigned long long (&k)[4], int lane) {
+#pragma unroll
+    for (int size = 2; size <= 128; size <<= 1) {
+#pragma unroll
+        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            if (stride >= 4) {
+                const int lm = stride >> 2;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int e = lane * 4 + r;
+                    const bool up = (e & size) == 0;
+                    const bool lower = (e & stride) == 0;
+                    const unsigned long long o = shfl_xor64(k[r], lm);
+                    const bool take_min = lower == up;
+                    k[r] = take_min ? (k[r] < o ? k[r] : o) : (k[r] > o ? k[r] : o);
                 }
+            } else if (stride == 2) {
+                const bool up = ((lane * 4) & size) == 0;
+                cswap(k[0], k[2], up);
+                cswap(k[1], k[3], up);
+            } else {
+                const bool up0 = ((lane * 4) & size) == 0, up2 = ((lane * 4 + 2) & size) == 0;
+                cswap(k[0], k[1], up0);
+                cswap(k[2], k[3], up2);
             }
-            __syncwarp();
         }
     }
-    const int m = n < kc ? n : kc;
-    *tau_out = (n >= kc) ? a[kc - 1] : VG_KEY_EMPTY;
-    return m;
+}
+// Warp-cooperative: keep the best kc of the n keys in `buf` (global, CBUF entries).  Returns the kc-th key (or EMPTY).
+__device__ __forceinline__ unsigned long long compact_global(unsigned long long *buf, int n, int kc, int lane) {
+    unsigned long long k[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = lane * 4 + r;
+        k[r] = e < n ? __ldcg(buf + e) : VG_KEY_EMPTY;
+    }
+    warp_sort128(k, lane);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int e = lane * 4 + r;
+        if (e < kc && e < n) __stcg(buf + e, k[r]);
+    }
+    // rank kc-1 lives in lane (kc-1)/4, register (kc-1)%4
+    const int tl = (kc - 1) >> 2, tr = (kc - 1) & 3;
+    const unsigned long long cand = tr == 0 ? k[0] : tr == 1 ? k[1] : tr == 2 ? k[2] : k[3];
+    const unsigned long long tau = shfl_xor64(cand, 0) ;
+    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)tau, tl), hi = __shfl_sync(0xffffffffu, (uint32_t)(tau >> 32), tl);
+    return n >= kc ? (((unsigned long long)hi << 32) | lo) : VG_KEY_EMPTY;
 }
 
-template <int BN, int STAGES, int C>
+template <bool RESIDENT, bool IS_DOT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, Args A) {
-    using S = Smem<BN, STAGES, C>;
+    using S = Smem<RESIDENT>;
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
     // SWIZZLE_128B tiles need 1024-byte aligned bases; the dynamic segment only guarantees 16
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int q0 = blockIdx.x * BM;
+    const int q0 = blockIdx.x * BMQ;
     const int split = blockIdx.y, splits = gridDim.y;
     const int64_t row_begin = (int64_t)split * A.rows_per_split;
     int64_t row_end = row_begin + A.rows_per_split;
@@ -188,12 +229,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + BN - 1) / BN) : 0;
 
     const uint32_t s_base = smem_u32(smem);
+    const uint32_t ring = s_base + (uint32_t)S::OFF_RING;
     const uint32_t bar0 = s_base + (uint32_t)S::OFF_BAR;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
-    constexpr uint32_t TMEM_COLS = 2 * BN;
+    const uint32_t afull_bar = bar0 + 8u * (2 * STAGES + 4);
+    constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages x 2 query halves x 128 columns
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -202,8 +245,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 128);
+            mbar_init(tempty_bar(s), 256);
         }
+        mbar_init(afull_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -218,7 +262,11 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
+        if (lane == 0 && ntiles > 0) {
+            if (RESIDENT) {
+                mbar_expect_tx(afull_bar, (uint32_t)A.kb * A_KB_BYTES);
+                for (int kb = 0; kb < A.kb; kb++) tma_load_2d(s_base + kb * A_KB_BYTES, &map_q, kb * BK, q0, afull_bar);
+            }
             uint32_t it = 0;
             for (int t = 0; t < ntiles; t++) {
                 const int n0 = (int)(row_begin + (int64_t)t * BN);
@@ -227,115 +275,138 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(empty_bar(st), ph ^ 1);
                     mbar_expect_tx(full_bar(st), S::STAGE_BYTES);
-                    const uint32_t sa = s_base + st * S::STAGE_BYTES;
-                    tma_load_2d(sa, &map_q, kb * BK, q0, full_bar(st));
-                    tma_load_2d(sa + S::A_BYTES, &map_x, kb * BK, n0, full_bar(st));
+                    const uint32_t sa = ring + st * S::STAGE_BYTES;
+                    if (!RESIDENT) {
+                        tma_load_2d(sa, &map_q, kb * BK, q0, full_bar(st));
+                        tma_load_2d(sa + A_KB_BYTES, &map_x, kb * BK, n0, full_bar(st));
+                    } else {
+                        tma_load_2d(sa, &map_x, kb * BK, n0, full_bar(st));
+                    }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (lane == 0 && ntiles > 0) {
             constexpr uint32_t idesc = make_idesc(BN);
+            if (RESIDENT) {
+                mbar_wait(afull_bar, 0);
+                tc_fence_after();
+            }
             uint32_t it = 0;
             for (int t = 0; t < ntiles; t++) {
                 const int as = t & 1;
                 const uint32_t aph = (t >> 1) & 1;
                 mbar_wait(tempty_bar(as), aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN);
                 for (int kb = 0; kb < A.kb; kb++, it++) {
                     const int st = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(full_bar(st), ph);
                     tc_fence_after();
-                    const uint32_t sa = s_base + st * S::STAGE_BYTES;
-                    const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + S::A_BYTES);
+                    const uint32_t sa = ring + st * S::STAGE_BYTES;
+                    const uint32_t a_addr = RESIDENT ? s_base + kb * A_KB_BYTES : sa;
+                    const uint32_t b_addr = RESIDENT ? sa : sa + A_KB_BYTES;
+                    const uint64_t bdesc = make_sdesc(b_addr);
 #pragma unroll
-                    for (int k = 0; k < BK / 8; k++)  // 8 tf32 = 32 bytes per UMMA: advance the start address inside the swizzle atom
-                        umma_tf32(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int h = 0; h < 2; h++) {  // the two 128-query halves share the B tile
+                        const uint64_t adesc = make_sdesc(a_addr + h * (BM * BK * 4));
+#pragma unroll
+                        for (int k = 0; k < BK / 8; k++)  // 8 tf32 = 32 bytes per UMMA: advance inside the swizzle atom
+                            umma_tf32(d_tmem + (uint32_t)(h * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                      (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit(empty_bar(st));
                 }
                 umma_commit(tfull_bar(as));
             }
         }
     } else {
-        // ===================== epilogue: warps 2..5 =====================
-        const int quad = warp & 3;            // TMEM lanes 32*quad .. 32*quad+31 are the ones this warp may read
-        const int slot = quad * 32 + lane;    // query within the tile = TMEM lane
+        // ===================== epilogue: warps 2..9, one thread per query =====================
+        const int quad = warp & 3;            // TMEM lanes 32*quad .. +31 are the ones this warp may read
+        const int half = (warp - 2) >> 2;     // which 128-query half (= accumulator column block)
+        const int slot = half * BM + quad * 32 + lane;
         const int et = (warp - 2) * 32 + lane;
-        unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem + S::OFF_KEYS) + (size_t)slot * S::KEY_STRIDE;
+        const int64_t q = (int64_t)q0 + slot;
         float *xs = reinterpret_cast<float *>(smem + S::OFF_XN);
-        const bool q_live = (int64_t)(q0 + slot) < A.nq;
-        float tau_f = q_live ? __int_as_float(0x7f800000) : -__int_as_float(0x7f800000);  // dead query rows accept nothing
-        int cnt = 0;
         const float INF = __int_as_float(0x7f800000);
+        const bool q_live = q < A.nq;
+        // candidate buffer of this (query, split): padded query index so dead slots have a private scratch row too
+        unsigned long long *buf = A.cand + ((size_t)((int64_t)q0 + slot) * splits + split) * CBUF;
+        float tau_f = q_live ? INF : -INF;   // dead query rows accept nothing
+        int cnt = 0;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
             const int64_t n0 = row_begin + (int64_t)t * BN;
             float *xt = xs + as * BN;
-            for (int i = et; i < BN; i += 128) {
-                const int64_t row = n0 + i;
-                xt[i] = (row < row_end) ? (A.is_dot ? 0.0f : __ldg(A.xn + row)) : INF;
+            if (et < BN) {
+                const int64_t row = n0 + et;
+                xt[et] = (row < row_end) ? (IS_DOT ? 0.0f : __ldg(A.xn + row)) : INF;
             }
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 tmem_ld_wait();
+                float s[32];
+                const float4 *x4 = reinterpret_cast<const float4 *>(xt + c * 32);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float dot = __uint_as_float(v[j]);
-                    const float xv = xt[c * 32 + j];
-                    const float s = A.is_dot ? __fsub_rn(xv, dot) : __fmaf_rn(-2.0f, dot, xv);  // dot: xv = 0 (live) or +inf (padding)
-                    if (s <= tau_f) {
-                        const int64_t row = n0 + c * 32 + j;
-                        bool ok = row < row_end;
-                        if (ok && A.mask) ok = (A.mask[row >> 3] >> (row & 7)) & 1;
-                        if (ok && cnt < C) {
-                            keys[cnt] = ((unsigned long long)f32_orderable(s) << 32) | (unsigned long long)(A.row_base + (uint32_t)row);
-                            cnt++;
+                for (int j4 = 0; j4 < 8; j4++) {
+                    const float4 xv = x4[j4];
+                    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float dot = __uint_as_float(v[j4 * 4 + i]);
+                        s[j4 * 4 + i] = IS_DOT ? __fsub_rn(xx[i], dot) : __fmaf_rn(-2.0f, dot, xx[i]);  // dot: xx = 0 | +inf (padding)
+                    }
+                }
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < 32; j++) m |= (s[j] <= tau_f) ? (1u << j) : 0u;
+                if (m) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) {
+                        if (m & (1u << j)) {
+                            const int64_t row = n0 + c * 32 + j;
+                            bool ok = row < row_end;
+                            if (ok && A.mask) ok = (A.mask[row >> 3] >> (row & 7)) & 1;
+                            if (ok && cnt < CBUF) {
+                                __stcg(buf + cnt, ((unsigned long long)f32_orderable(s[j]) << 32) | (unsigned long long)(A.row_base + (uint32_t)row));
+                                cnt++;
+                            }
                         }
                     }
                 }
-                // a buffer that could overflow during the next 32 columns is compacted now (warp-cooperative)
-                unsigned need = __ballot_sync(0xffffffffu, cnt > C - 32);
-                if (need) __syncwarp();  // candidate stores of the owning lanes become visible to the warp
-                while (need) {
-                    const int src = __ffs(need) - 1;
-                    need &= need - 1;
-                    const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-                    unsigned long long tau_key;
-                    unsigned long long *a = reinterpret_cast<unsigned long long *>(smem + S::OFF_KEYS) + (size_t)(quad * 32 + src) * S::KEY_STRIDE;
-                    const int m = compact_slot(a, n_src, A.kc, C, lane, &tau_key);
-                    if (lane == src) {
-                        cnt = m;
-                        tau_f = (tau_key == VG_KEY_EMPTY) ? INF : f32_from_orderable((uint32_t)(tau_key >> 32));
+                // a buffer that could overflow during the next 32 columns is compacted now (warp-cooperative, in registers)
+                unsigned need = __ballot_sync(0xffffffffu, cnt > CBUF - 32);
+                if (need) {
+                    __threadfence_block();
+                    __syncwarp();
+                    while (need) {
+                        const int src = __ffs(need) - 1;
+                        need &= need - 1;
+                        const int n_src = __shfl_sync(0xffffffffu, cnt, src);
+                        unsigned long long *b = A.cand + ((size_t)((int64_t)q0 + half * BM + quad * 32 + src) * splits + split) * CBUF;
+                        const unsigned long long tau_key = compact_global(b, n_src, A.kc, lane);
+                        if (lane == src) {
+                            cnt = n_src < A.kc ? n_src : A.kc;
+                            tau_f = (tau_key == VG_KEY_EMPTY) ? INF : f32_from_orderable((uint32_t)(tau_key >> 32));
+                        }
                     }
+                    __threadfence_block();
+                    __syncwarp();
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
         }
-        // final: every slot sorted, best kc emitted
-        __syncwarp();
-        for (int src = 0; src < 32; src++) {
-            const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-            unsigned long long tau_key;
-            unsigned long long *a = reinterpret_cast<unsigned long long *>(smem + S::OFF_KEYS) + (size_t)(quad * 32 + src) * S::KEY_STRIDE;
-            const int m = compact_slot(a, n_src, A.kc, C, lane, &tau_key);
-            const int64_t q = (int64_t)q0 + quad * 32 + src;
-            if (q < A.nq) {
-                unsigned long long *out = A.partial + ((size_t)q * splits + split) * A.kc;
-                for (int i = lane; i < A.kc; i += 32) out[i] = (i < m) ? a[i] : VG_KEY_EMPTY;
-            }
-            __syncwarp();
-        }
+        A.cand_cnt[(size_t)((int64_t)q0 + slot) * splits + split] = q_live ? cnt : 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -343,6 +414,37 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
+}
+
+// Per query: merge the (unsorted) candidate lists of all row splits into the best kc (one warp per query).
+__global__ void __launch_bounds__(256) tc_merge_kernel(const unsigned long long *cand, const int32_t *cand_cnt, int64_t nq, int splits,
+                                                       int kc, int C, uint32_t *out_rows, float *out_s, int32_t *out_cnt) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    TopK tk = topk_carve(smem, nw, C, kc);
+    topk_init(tk, nw, threadIdx.x, blockDim.x);
+    __syncthreads();
+    const int64_t q = (int64_t)blockIdx.x * nw + warp;
+    if (q >= nq) return;
+    const int trigger = C - 32;
+    for (int sp = 0; sp < splits; sp++) {
+        const int n = cand_cnt[q * splits + sp];
+        const unsigned long long *src = cand + ((size_t)q * splits + sp) * CBUF;
+        for (int i0 = 0; i0 < n; i0 += 32) {
+            const int i = i0 + lane;
+            if (i < n) {
+                const unsigned long long key = __ldcg(src + i);
+                if (key < tk.tau[warp]) {
+                    const int pos = atomicAdd(&tk.cnt[warp], 1);
+                    if (pos < C) tk.keys[(size_t)warp * C + pos] = key;
+                }
+            }
+            __syncwarp();
+            if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
+            __syncwarp();
+        }
+    }
+    topk_emit_warp(tk, warp, lane, false, out_rows + q * kc, out_s + q * kc, out_cnt + q, kc);
 }
 
 // ------------------------------------------------------------------ norms
@@ -415,12 +517,15 @@ __global__ void __launch_bounds__(128) flat_tc_finalize_kernel(const float *vect
     }
     __syncthreads();
     if (tid < 32) {
-        unsigned long long tau;
-        // sort all 128 slots (EMPTY beyond kc were written above only up to the 8-aligned bound; fill the rest)
+        // sort all 128 slots in registers (slots beyond the 8-aligned candidate bound are empty)
         const int filled = ((kc + 7) / 8) * 8;
-        for (int i = filled + tid; i < 128; i += 32) ek[i] = VG_KEY_EMPTY;
+        unsigned long long kk[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) kk[r] = (tid * 4 + r) < filled ? ek[tid * 4 + r] : VG_KEY_EMPTY;
+        warp_sort128(kk, tid);
+#pragma unroll
+        for (int r = 0; r < 4; r++) ek[tid * 4 + r] = kk[r];
         __syncwarp();
-        compact_slot(ek, 128, 128, 128, tid, &tau);
         const int m = n < k ? n : k;
         for (int i = tid; i < k; i += 32) {
             if (i < m) {
@@ -479,9 +584,9 @@ static vg_status make_map(CUtensorMap *map, const float *base, int64_t rows, int
 }
 
 bool supported(int64_t dim, int64_t rows, int64_t nq, int64_t k) {
-    return dim >= 16 && dim % 4 == 0 && rows >= 1024 && rows < (1ll << 31) && nq >= 16 && k >= 1 && k <= 64;
+    return dim >= 16 && dim % 4 == 0 && rows >= 1024 && rows < (1ll << 31) && nq >= 16 && k >= 1 && k <= 32;
 }
-int candidates_for(int64_t k) { return k <= 10 ? 32 : (int)(k + 32); }
+int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }
 
 vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsigned int *d_max_bits, cudaStream_t st) {
     if (n <= 0) return VG_OK;
@@ -491,30 +596,29 @@ vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsign
     return VG_OK;
 }
 
-template <int BN, int STAGES, int C>
+template <bool RESIDENT, bool IS_DOT>
 static vg_status launch(const CUtensorMap &mq, const CUtensorMap &mx, const Args &a, int64_t qtiles, int splits, cudaStream_t st) {
-    using S = Smem<BN, STAGES, C>;
+    using S = Smem<RESIDENT>;
     const size_t sm = S::TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-    VG_CUDA(cudaFuncSetAttribute(flat_tc_kernel<BN, STAGES, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VG_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RESIDENT, IS_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)qtiles, (unsigned)splits);
-    flat_tc_kernel<BN, STAGES, C><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
+    flat_tc_kernel<RESIDENT, IS_DOT><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
     VG_LAUNCHED();
     return VG_OK;
 }
 
 vg_status filter(const FilterArgs &f, cudaStream_t st) {
-    if (!supported(f.dim, f.rows, f.nq, f.kc > 32 ? f.kc - 32 : 1)) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
+    if (!supported(f.dim, f.rows, f.nq, 1) || f.kc < 1 || f.kc > 64) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
     CUtensorMap mq, mx;
-    const bool wide = f.kc <= 32;  // BN=256, C=64  |  BN=128, C=128
-    VG_TRY(make_map(&mq, f.d_queries, f.nq, f.dim, BM));
-    VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, wide ? 256 : 128));
-    const int bn = wide ? 256 : 128;
-    const int64_t qtiles = (f.nq + BM - 1) / BM;
+    VG_TRY(make_map(&mq, f.d_queries, f.nq, f.dim, BMQ));
+    VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, BN));
+    const int64_t qtiles = (f.nq + BMQ - 1) / BMQ;
     // one CTA per SM (shared memory): pick the row-split count whose CTA total fills whole waves best
     const int64_t sms = sm_count();
+    const int64_t max_splits = std::max<int64_t>(1, f.rows / (4 * BN));
     int64_t splits = 1;
     double best = 0.0;
-    for (int64_t s_ = 1; s_ <= sms; s_++) {
+    for (int64_t s_ = 1; s_ <= sms && s_ <= max_splits; s_++) {
         const int64_t ctas = qtiles * s_, waves = (ctas + sms - 1) / sms;
         const double eff = (double)ctas / (double)(waves * sms);
         if (eff > best + 0.02) {
@@ -523,10 +627,8 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
         }
         if (eff >= 0.97) break;
     }
-    const int64_t max_splits = (f.rows + 4 * bn - 1) / (4 * bn);
-    if (splits > max_splits) splits = max_splits;
     int64_t rps = (f.rows + splits - 1) / splits;
-    rps = (rps + bn - 1) / bn * bn;
+    rps = (rps + BN - 1) / BN * BN;
     splits = (f.rows + rps - 1) / rps;
     Args a;
     a.xn = f.d_xn;
@@ -536,17 +638,32 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
     a.rows_per_split = rps;
     a.kb = (int)((f.dim + BK - 1) / BK);
     a.kc = f.kc;
-    a.is_dot = f.is_dot;
     a.row_base = f.row_base;
-    DevBuf partial;
-    VG_TRY(partial.alloc((size_t)f.nq * splits * f.kc * 8));
-    a.partial = partial.as<unsigned long long>();
-    if (wide) VG_TRY((launch<256, 3, 64>(mq, mx, a, qtiles, (int)splits, st)));
-    else VG_TRY((launch<128, 2, 128>(mq, mx, a, qtiles, (int)splits, st)));
-    // merge the per-split lists: keys are already in s-space (ascending)
-    VG_TRY(launch_merge_keys(a.partial, splits, f.nq, f.kc, f.kc, splits * f.kc, false, f.kc, f.d_cand_rows, f.d_cand_s, f.d_cand_cnt, st));
-    VG_CUDA(cudaStreamSynchronize(st));  // partial is freed on return
-    return VG_OK;
+    DevBuf cand, ccnt;
+    const int64_t nq_pad = qtiles * BMQ;
+    VG_TRY(cand.alloc((size_t)nq_pad * splits * CBUF * 8));
+    VG_TRY(ccnt.alloc((size_t)nq_pad * splits * 4));
+    a.cand = cand.as<unsigned long long>();
+    a.cand_cnt = ccnt.as<int32_t>();
+    const bool resident = a.kb <= MAX_RES_KB;
+    if (resident) {
+        if (f.is_dot) VG_TRY((launch<true, true>(mq, mx, a, qtiles, (int)splits, st)));
+        else VG_TRY((launch<true, false>(mq, mx, a, qtiles, (int)splits, st)));
+    } else {
+        if (f.is_dot) VG_TRY((launch<false, true>(mq, mx, a, qtiles, (int)splits, st)));
+        else VG_TRY((launch<false, false>(mq, mx, a, qtiles, (int)splits, st)));
+    }
+    // merge the per-split lists (keys are in s-space, ascending = better)
+    {
+        const int C = topk_capacity(f.kc, 32);
+        const int nw = 8;
+        const size_t sm = topk_smem_bytes(nw, C);
+        VG_CUDA(cudaFuncSetAttribute(tc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        tc_merge_kernel<<<(unsigned)((f.nq + nw - 1) / nw), nw * 32, sm, st>>>(a.cand, a.cand_cnt, f.nq, (int)splits, f.kc, C, f.d_cand_rows,
+                                                                              f.d_cand_s, f.d_cand_cnt);
+        VG_LAUNCHED();
+    }
+    return VG_OK;  // cand / ccnt are returned to the stream-ordered pool (freed in stream order)
 }
 
 vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned int *d_xmax_bits, uint32_t *d_rows, float *d_scores,
