@@ -658,6 +658,193 @@ VGO_API void vgo_pq_quantize_centroids(const float *cent, int64_t count, int8_t 
 }
 
 /* ------------------------------------------------------------------------ */
+/* a15: OptimizedProductQuantizer — internal/quantization/opq.go, svd.go      */
+/* Go float32 arithmetic: every operation individually rounded, never fused.  */
+/* ------------------------------------------------------------------------ */
+/* NewOptimizedProductQuantizer block size :41-58 */
+VGO_API int64_t vgo_opq_block_size(int64_t dim, int64_t m) {
+    int64_t sub = dim / m, bs = dim;
+    if (dim > 64) {
+        int64_t best = 1000;
+        for (int64_t b = sub; b <= dim; b += sub) {
+            if (dim % b == 0) {
+                int64_t diff = b > 32 ? b - 32 : 32 - b;
+                if (diff < best) {
+                    best = diff;
+                    bs = b;
+                }
+            }
+        }
+    }
+    return bs;
+}
+/* rotateVector :196-214: dst[b*bs+i] = simd.Dot(R_b[i], src_b)  (rot = [blocks][bs][bs]) */
+VGO_API void vgo_opq_rotate(const float *src, int64_t dim, int64_t bs, const float *rot, float *dst) {
+    for (int64_t b = 0; b < dim / bs; b++)
+        for (int64_t i = 0; i < bs; i++) dst[b * bs + i] = vgo_dot_a512(rot + (b * bs + i) * bs, src + b * bs, bs);
+}
+/* Decode's inverse rotation :244-262: dst[i] = sum_j R[j][i]*src[j], sequential, unfused */
+VGO_API void vgo_opq_unrotate(const float *src, int64_t dim, int64_t bs, const float *rot, float *dst) {
+    for (int64_t b = 0; b < dim / bs; b++)
+        for (int64_t i = 0; i < bs; i++) {
+            float sum = 0;
+            for (int64_t j = 0; j < bs; j++) {
+                float p = rot[(b * bs + j) * bs + i] * src[b * bs + j];
+                sum = sum + p;
+            }
+            dst[b * bs + i] = sum;
+        }
+}
+/* Train step 3 accumulation :139-178: M_b[r][c] += x_b[r] * yhat_b[c], samples in order */
+VGO_API void vgo_opq_accumulate_m(const float *x, const float *yhat, int64_t n, int64_t dim, int64_t bs, float *M) {
+    int64_t blocks = dim / bs;
+    memset(M, 0, sizeof(float) * (size_t)(blocks * bs * bs));
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t b = 0; b < blocks; b++)
+            for (int64_t r = 0; r < bs; r++) {
+                float xr = x[i * dim + b * bs + r];
+                float *row = M + (b * bs + r) * bs;
+                for (int64_t c = 0; c < bs; c++) {
+                    float p = xr * yhat[i * dim + b * bs + c];
+                    row[c] = row[c] + p;
+                }
+            }
+}
+/* svd.go:13-127 one-sided Jacobi; a [n][n] becomes U, v [n][n], sigma [n] */
+static void opq_svd(float *u, float *v, float *sigma, int64_t n) {
+    const double tol = 1e-5;
+    memset(v, 0, sizeof(float) * (size_t)(n * n));
+    for (int64_t i = 0; i < n; i++) v[i * n + i] = 1.0f;
+    for (int iter = 0; iter < 100; iter++) {
+        int changed = 0;
+        for (int64_t i = 0; i < n - 1; i++)
+            for (int64_t j = i + 1; j < n; j++) {
+                float alpha = 0, beta = 0, gamma = 0;
+                for (int64_t k = 0; k < n; k++) {
+                    float a = u[k * n + i] * u[k * n + i];
+                    alpha = alpha + a;
+                    float b = u[k * n + j] * u[k * n + j];
+                    beta = beta + b;
+                    float g = u[k * n + i] * u[k * n + j];
+                    gamma = gamma + g;
+                }
+                if (alpha < 1e-12f || beta < 1e-12f) continue;
+                float ab = alpha * beta;
+                if (fabs((double)gamma) < tol * sqrt((double)ab)) continue;
+                changed = 1;
+                float ba = beta - alpha;
+                float g2 = 2 * gamma;
+                float zeta = ba / g2;
+                float zz = zeta * zeta;
+                float opz = 1 + zz;
+                float rt = (float)sqrt((double)opz);
+                float t;
+                if (zeta > 0) {
+                    float den = zeta + rt;
+                    t = 1 / den;
+                } else {
+                    float den = -zeta + rt;
+                    t = -1 / den;
+                }
+                float tt = t * t;
+                float opt = 1 + tt;
+                float c = 1 / (float)sqrt((double)opt);
+                float sn = c * t;
+                for (int64_t k = 0; k < n; k++) {
+                    float t1 = u[k * n + i], t2 = u[k * n + j];
+                    float a1 = c * t1, a2 = sn * t2, b1 = sn * t1, b2 = c * t2;
+                    u[k * n + i] = a1 - a2;
+                    u[k * n + j] = b1 + b2;
+                }
+                for (int64_t k = 0; k < n; k++) {
+                    float t1 = v[k * n + i], t2 = v[k * n + j];
+                    float a1 = c * t1, a2 = sn * t2, b1 = sn * t1, b2 = c * t2;
+                    v[k * n + i] = a1 - a2;
+                    v[k * n + j] = b1 + b2;
+                }
+            }
+        if (!changed) break;
+    }
+    for (int64_t j = 0; j < n; j++) {
+        float sum = 0;
+        for (int64_t i = 0; i < n; i++) {
+            float p = u[i * n + j] * u[i * n + j];
+            sum = sum + p;
+        }
+        sigma[j] = (float)sqrt((double)sum);
+        if (sigma[j] > 1e-10f) {
+            float inv = 1.0f / sigma[j]; /* Go: `inv := 1.0 / sigma[j]` — untyped constant / float32 is a float32 division */
+            for (int64_t i = 0; i < n; i++) u[i * n + j] = u[i * n + j] * inv;
+        }
+    }
+}
+/* svd.go:184-216 determinant (partial pivoting; |.| compared in float64) */
+static float opq_det(const float *m, int64_t n) {
+    float *t = (float *)malloc(sizeof(float) * (size_t)(n * n));
+    memcpy(t, m, sizeof(float) * (size_t)(n * n));
+    float det = 1.0f;
+    for (int64_t i = 0; i < n; i++) {
+        int64_t pivot = i;
+        for (int64_t j = i + 1; j < n; j++)
+            if (fabs((double)t[j * n + i]) > fabs((double)t[pivot * n + i])) pivot = j;
+        if (pivot != i) {
+            for (int64_t k = 0; k < n; k++) {
+                float tmp = t[i * n + k];
+                t[i * n + k] = t[pivot * n + k];
+                t[pivot * n + k] = tmp;
+            }
+            det = det * -1;
+        }
+        if (t[i * n + i] == 0) {
+            free(t);
+            return 0;
+        }
+        det = det * t[i * n + i];
+        for (int64_t j = i + 1; j < n; j++) {
+            float factor = t[j * n + i] / t[i * n + i];
+            for (int64_t k = i + 1; k < n; k++) {
+                float p = factor * t[i * n + k];
+                t[j * n + k] = t[j * n + k] - p;
+            }
+        }
+    }
+    free(t);
+    return det;
+}
+/* computeProcrustesRotation svd.go:129-182: R = U V^T, reflection fixed on the smallest singular value.
+ * M [n][n] is consumed (becomes U, as in the reference).  Optional outputs u/v/sigma for the SVD property tests. */
+VGO_API void vgo_opq_procrustes(float *M, int64_t n, float *R, float *sigma_out, float *v_out) {
+    float *v = (float *)malloc(sizeof(float) * (size_t)(n * n));
+    float *sigma = (float *)malloc(sizeof(float) * (size_t)n);
+    opq_svd(M, v, sigma, n);
+    if (sigma_out) memcpy(sigma_out, sigma, sizeof(float) * (size_t)n);
+    if (v_out) memcpy(v_out, v, sizeof(float) * (size_t)(n * n));
+    int64_t mi = 0;
+    float ms = sigma[0];
+    for (int64_t i = 1; i < n; i++)
+        if (sigma[i] < ms) {
+            ms = sigma[i];
+            mi = i;
+        }
+    for (int pass = 0; pass < 2; pass++) {
+        for (int64_t i = 0; i < n; i++)
+            for (int64_t j = 0; j < n; j++) {
+                float sum = 0;
+                for (int64_t k = 0; k < n; k++) {
+                    float p = M[i * n + k] * v[j * n + k];
+                    sum = sum + p;
+                }
+                R[i * n + j] = sum;
+            }
+        if (pass == 1) break;
+        if (!(opq_det(R, n) < 0)) break;
+        for (int64_t i = 0; i < n; i++) M[i * n + mi] = M[i * n + mi] * -1;
+    }
+    free(v);
+    free(sigma);
+}
+
+/* ------------------------------------------------------------------------ */
 /* Deterministic stand-in for Go's unseeded global math/rand (pq.go:294,     */
 /* 308,314,409; kmeans.go:25,131): the reference's training is not           */
 /* reproducible even against itself, so both this oracle and the CUDA path   */

@@ -540,6 +540,7 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     if (!tc_enabled() || d.codec != VG_CODEC_F32 || d.num_partitions > 1 || !ix->has_vectors) return VG_OK;
     if (!tc::supported(d.dim, d.rows, nq, k)) return VG_OK;
     if ((reinterpret_cast<uintptr_t>(d_queries) & 15) != 0) return VG_OK;  // TMA needs 16-byte aligned bases
+    if ((reinterpret_cast<uintptr_t>(d_mask) & 3) != 0) return VG_OK;      // the filter reads the row bitmap as 32-bit words
     cudaStream_t st = stream();
     VG_TRY(ensure_row_norms(ix, st));
     const int is_dot = d.metric != VG_METRIC_L2;
@@ -551,18 +552,18 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     f.nq = nq;
     f.rows = d.rows;
     f.dim = d.dim;
-    f.kc = tc::candidates_for(k);
+    f.kc = tc::candidates_for(k, d.dim);
     f.is_dot = is_dot;
     f.row_base = (uint32_t)d.row_base;
-    DevBuf crow, cs, ccnt, qn, failb;
-    VG_TRY(crow.alloc((size_t)nq * f.kc * 4));
-    VG_TRY(cs.alloc((size_t)nq * f.kc * 4));
+    DevBuf cand, ccnt, tau, qn, failb;
+    VG_TRY(cand.alloc((size_t)nq * tc::CAP * 8));
     VG_TRY(ccnt.alloc((size_t)nq * 4));
+    VG_TRY(tau.alloc((size_t)((nq + 255) / 256 * 256) * 4));
     VG_TRY(qn.alloc((size_t)nq * 4));
     VG_TRY(failb.alloc((size_t)nq * 4));
-    f.d_cand_rows = crow.as<uint32_t>();
-    f.d_cand_s = cs.as<float>();
+    f.d_cand = cand.as<unsigned long long>();
     f.d_cand_cnt = ccnt.as<int32_t>();
+    f.d_tau = tau.as<float>();
     VG_TRY(tc::sqnorms(d_queries, nq, d.dim, qn.as<float>(), nullptr, st));
     VG_TRY(tc::filter(f, st));
     VG_TRY(tc::finalize(f, (int)k, qn.as<float>(), ix->xmax.as<unsigned int>(), d_rows, d_scores, d_counts, failb.as<int32_t>(), st));
@@ -705,7 +706,7 @@ vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
     return VG_OK;
 }
 vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_rows, float *h_s,
-                                int32_t *h_counts) {
+                                int32_t *h_counts, float *h_tau) {
     VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
@@ -714,11 +715,11 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
     if (!tc::supported(ix->d.dim, ix->d.rows, nq, 1)) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
     cudaStream_t st = stream();
     VG_TRY(ensure_row_norms(ix, st));
-    DevBuf q, crow, cs, ccnt;
+    DevBuf q, cand, ccnt, tau;
     VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
-    VG_TRY(crow.alloc((size_t)nq * kc * 4));
-    VG_TRY(cs.alloc((size_t)nq * kc * 4));
+    VG_TRY(cand.alloc((size_t)nq * tc::CAP * 8));
     VG_TRY(ccnt.alloc((size_t)nq * 4));
+    VG_TRY(tau.alloc((size_t)((nq + 255) / 256 * 256) * 4));
     tc::FilterArgs f;
     f.d_queries = q.as<float>();
     f.d_vectors = ix->vectors.as<float>();
@@ -729,14 +730,27 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
     f.kc = (int)kc;
     f.is_dot = ix->d.metric != VG_METRIC_L2;
     f.row_base = (uint32_t)ix->d.row_base;
-    f.d_cand_rows = crow.as<uint32_t>();
-    f.d_cand_s = cs.as<float>();
+    f.d_cand = cand.as<unsigned long long>();
     f.d_cand_cnt = ccnt.as<int32_t>();
+    f.d_tau = tau.as<float>();
     VG_TRY(tc::filter(f, st));
     VG_CUDA(cudaStreamSynchronize(st));
-    VG_TRY(staged_d2h(h_rows, crow.p, (size_t)nq * kc * 4));
-    VG_TRY(staged_d2h(h_s, cs.p, (size_t)nq * kc * 4));
-    return staged_d2h(h_counts, ccnt.p, (size_t)nq * 4);
+    std::vector<unsigned long long> keys((size_t)nq * tc::CAP);
+    VG_TRY(staged_d2h(keys.data(), cand.p, keys.size() * 8));
+    VG_TRY(staged_d2h(h_counts, ccnt.p, (size_t)nq * 4));
+    VG_TRY(staged_d2h(h_tau, tau.p, (size_t)nq * 4));
+    for (int64_t i = 0; i < nq; i++)
+        for (int j = 0; j < tc::CAP; j++) {
+            const bool live = j < h_counts[i];
+            const unsigned long long key = keys[(size_t)i * tc::CAP + j];
+            const uint32_t o = (uint32_t)(key >> 32);
+            const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+            float sc;
+            memcpy(&sc, &u, 4);
+            h_rows[i * tc::CAP + j] = live ? (uint32_t)key : 0xFFFFFFFFu;
+            h_s[i * tc::CAP + j] = live ? sc : 0.0f;
+        }
+    return VG_OK;
 }
 
 vg_status vg_index_search(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes,

@@ -1,24 +1,32 @@
-// vg_flat_tc.cu — exact Flat L2 / dot search as a tcgen05 (TF32) GEMM *filter*
-// fed by TMA, with a register/shared-memory top-k' in the epilogue, followed by
-// an exact re-check in the reference's own summation order.
+// vg_flat_tc.cu — exact Flat L2 / dot search as a tcgen05 (TF32) GEMM *filter* fed by TMA,
+// followed by an exact re-check in the reference's own summation order.
 //
-// Why a filter.  flat.(*Segment).Search (internal/segment/flat/segment.go:690-697)
-// calls simd.SquaredL2 / simd.Dot per (query,row); BASELINE's north_star wants that
-// dense Q x N x d contraction on the 5th-gen tensor cores, AND top-k ids identical
-// to the SIMD path.  Tensor cores give q.x only to TF32 accuracy, so they are used
-// to shrink N rows to k' >= k candidates per query; the survivors are then scored
-// by the exact AVX-512-order kernel (same code path as Segment.Rerank) and a
-// certificate proves nothing outside the candidate set could have entered the
-// top-k.  Queries whose certificate fails are re-run on the exact CUDA-core scan.
+// Why a filter.  flat.(*Segment).Search (internal/segment/flat/segment.go:690-697) calls
+// simd.SquaredL2 / simd.Dot per (query,row); BASELINE's north_star wants that dense
+// Q x N x d contraction on the 5th-gen tensor cores AND top-k ids identical to the SIMD path.
+// Tensor cores give q.x only to TF32 accuracy, so they are used to shrink N rows to a few
+// dozen candidates per query; the survivors are scored by the exact AVX-512-order kernel
+// (same arithmetic as Segment.Rerank) and a certificate proves that nothing outside the
+// candidate set could have entered the top-k.  Queries whose certificate fails are re-run on
+// the exact CUDA-core scan.
 //
 //   s(q,x) = ||x||^2 - 2 q.x   (L2; the per-query constant ||q||^2 is dropped)
 //   s(q,x) = -q.x              (dot / cosine, descending in the reference)
 //
-// Certificate (per query).  Let T = the k'-th smallest approximate s, E >= |s_exact
-// - s_approx| for every row (bound below), e_k = exact k-th best.  Every row outside
-// the candidate set has s_approx >= T, hence s_exact >= T - E.  If s_exact(e_k) <
-// T - E no outside row can tie or beat the k-th candidate: the exact top-k of the
-// candidate set IS the exact top-k of the segment (ties by row id included).
+// Two GEMM passes, both with branch-free epilogues (no per-query heap inside the GEMM):
+//   pass 1  every thread (= one query) keeps the minimum of s over groups of G consecutive
+//           rows and writes one float per group.  The kc-th smallest group minimum tau(q) is
+//           an upper bound of the kc-th smallest s overall (kc groups each contain a row at
+//           or below it), and it is nearly tight when there are many more groups than kc.
+//   select  tau(q) per query (thread-private max-heap over the group minima).
+//   pass 2  the same GEMM again; rows with s <= tau(q) are appended to the query's candidate
+//           list (a global atomic per survivor — about kc of them per query in total).
+//
+// Certificate (per query).  The candidate list holds EVERY row with s_approx <= tau.  With
+// E >= |s_exact - s_approx| for every row (bound below) any other row has s_exact > tau - E.
+// If the exact k-th best candidate satisfies s_exact(e_k) < tau - E, no outside row can tie
+// or beat it: the exact top-k of the candidates IS the exact top-k of the segment (ties by
+// row id included).
 //
 // Error bound.  kind::tf32 keeps 10 explicit mantissa bits of each fp32 operand:
 // |fl_tf32(a) - a| <= 2^-10 |a|, so |q.x - (q.x)_tc| <= (2^-9 + 2^-20) sum|q_i x_i|
@@ -27,16 +35,14 @@
 // c1 = 2^-8 * 1.125 (L2) or 2^-9 * 1.125 (dot), c2 = 2^-14 (norm rounding, accumulation
 // slack).  tests/test_gpu_flat_tc.py measures the realised error against E.
 //
-// Kernel (one CTA = 256 queries x a contiguous row range, 320 threads):
+// GEMM kernel (one CTA = 256 queries x a contiguous row range, 320 threads):
 //   warp 0     TMA producer (cp.async.bulk.tensor.2d, 128B swizzle).  dim <= 128: the 256 x dim
 //              query tile is loaded ONCE and stays resident (128 KB), only 128-row B tiles stream
 //              through a 4-stage mbarrier ring; larger dims stream A and B k-blocks together.
 //   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 x N=128 x K=8, two M halves
 //              per B tile, fp32 accumulators in TMEM (2 stages x 2 halves x 128 columns = 512)
-//   warps 2-9  epilogue: one thread = one query (= one TMEM lane).  tcgen05.ld 32 columns, 32
-//              independent FFMA + compares build a pass mask (no branch per column); the rare
-//              survivors go to the query's private candidate buffer in global memory (L2) — no
-//              atomics; a full buffer is compacted by its warp with a register bitonic sort.
+//   warps 2-9  epilogue: one thread = one query (= one TMEM lane); tcgen05.ld 32 columns at a
+//              time, 32 independent FFMA, then FMNMX tree (pass 1) or compare-to-mask (pass 2).
 #include <cuda.h>
 
 #include <algorithm>
@@ -122,35 +128,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// ------------------------------------------------------------------ kernel
-constexpr int BN = 128;        // database rows per tile (UMMA N)
-constexpr int CBUF = 128;      // candidate keys per (query, row split) in global memory
-constexpr int STAGES = 4;
-constexpr int A_KB_BYTES = BMQ * BK * 4;   // 32 KB: one k-block of the 256-query tile (two UMMA M=128 halves)
-constexpr int B_KB_BYTES = BN * BK * 4;    // 16 KB
-constexpr int MAX_RES_KB = 4;              // query tile kept resident in shared memory when dim <= 128
-
-struct Args {
-    const float *xn;        // [rows] ||x||^2 (L2) or nullptr (dot)
-    const uint8_t *mask;    // optional row bitmap
-    int64_t nq, rows, rows_per_split;
-    int kb;                 // k-blocks = ceil(dim / 32)
-    int kc;                 // candidates kept per query (k')
-    uint32_t row_base;
-    unsigned long long *cand;  // [nq_pad][splits][CBUF] keys (unsorted)
-    int32_t *cand_cnt;         // [nq_pad][splits]
-};
-
-template <bool RESIDENT>
-struct Smem {
-    // RESIDENT: [A: kb x 32 KB][B ring: STAGES x 16 KB];  streaming: [ring: STAGES x (32 KB A + 16 KB B)]
-    static constexpr int STAGE_BYTES = RESIDENT ? B_KB_BYTES : A_KB_BYTES + B_KB_BYTES;
-    static constexpr size_t OFF_RING = RESIDENT ? (size_t)MAX_RES_KB * A_KB_BYTES : 0;
-    static constexpr size_t OFF_XN = OFF_RING + (size_t)STAGES * STAGE_BYTES;
-    static constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
-    static constexpr size_t TOTAL = OFF_BAR + (size_t)(2 * STAGES + 5) * 8 + 16;
-};
-
 // ---- 128-key bitonic sort held in registers by one warp: element e = 4*lane + r.
 __device__ __forceinline__ void cswap(unsigned long long &a, unsigned long long &b, bool up) {
     const bool sw = (a > b) == up;
@@ -190,29 +167,54 @@ __device__ __forceinline__ void warp_sort128(unsigned long long (&k)[4], int lan
         }
     }
 }
-// Warp-cooperative: keep the best kc of the n keys in `buf` (global, CBUF entries).  Returns the kc-th key (or EMPTY).
-__device__ __forceinline__ unsigned long long compact_global(unsigned long long *buf, int n, int kc, int lane) {
-    unsigned long long k[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int e = lane * 4 + r;
-        k[r] = e < n ? __ldcg(buf + e) : VG_KEY_EMPTY;
+
+// ------------------------------------------------------------------ kernel
+constexpr int BN = 128;        // database rows per tile (UMMA N)
+constexpr int STAGES = 4;
+constexpr int A_KB_BYTES = BMQ * BK * 4;   // 32 KB: one k-block of the 256-query tile (two UMMA M=128 halves)
+constexpr int B_KB_BYTES = BN * BK * 4;    // 16 KB
+constexpr int MAX_RES_KB = 4;              // query tile kept resident in shared memory when dim <= 128
+
+struct Args {
+    const float *xn;        // [rows] ||x||^2 (L2) or nullptr (dot)
+    const uint32_t *mask;   // optional row bitmap, read as 32-bit words (bit = 1 keeps the row)
+    int64_t nq, nq_pad, rows, rows_per_split;
+    int kb;                 // k-blocks = ceil(dim / 32)
+    int cpg;                // pass 1: 32-row chunks per minimum group (G / 32)
+    uint32_t row_base;
+    float *mins;            // pass 1 out: [nq_pad][groups]
+    int64_t groups;
+    const float *tau;       // pass 2 in:  [nq_pad]
+    unsigned long long *cand;  // pass 2 out: [nq][CAP] keys (unsorted)
+    int32_t *cand_cnt;         // pass 2 out: [nq] number of survivors (may exceed CAP = overflow)
+};
+
+template <bool RESIDENT>
+struct Smem {
+    // RESIDENT: [A: kb x 32 KB][B ring: STAGES x 16 KB];  streaming: [ring: STAGES x (32 KB A + 16 KB B)]
+    static constexpr int STAGE_BYTES = RESIDENT ? B_KB_BYTES : A_KB_BYTES + B_KB_BYTES;
+    static constexpr size_t OFF_RING = RESIDENT ? (size_t)MAX_RES_KB * A_KB_BYTES : 0;
+    static constexpr size_t OFF_XN = OFF_RING + (size_t)STAGES * STAGE_BYTES;
+    static constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
+    static constexpr size_t TOTAL = OFF_BAR + (size_t)(2 * STAGES + 5) * 8 + 16;
+};
+
+// value of s[j] for a warp-uniform j (jump table; keeps s[] in registers)
+__device__ __forceinline__ float pick32(const float (&s)[32], int j) {
+    float r = 0.0f;
+    switch (j) {
+#define VG_CASE(i) case i: r = s[i]; break;
+        VG_CASE(0) VG_CASE(1) VG_CASE(2) VG_CASE(3) VG_CASE(4) VG_CASE(5) VG_CASE(6) VG_CASE(7)
+        VG_CASE(8) VG_CASE(9) VG_CASE(10) VG_CASE(11) VG_CASE(12) VG_CASE(13) VG_CASE(14) VG_CASE(15)
+        VG_CASE(16) VG_CASE(17) VG_CASE(18) VG_CASE(19) VG_CASE(20) VG_CASE(21) VG_CASE(22) VG_CASE(23)
+        VG_CASE(24) VG_CASE(25) VG_CASE(26) VG_CASE(27) VG_CASE(28) VG_CASE(29) VG_CASE(30) VG_CASE(31)
+#undef VG_CASE
     }
-    warp_sort128(k, lane);
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-        const int e = lane * 4 + r;
-        if (e < kc && e < n) __stcg(buf + e, k[r]);
-    }
-    // rank kc-1 lives in lane (kc-1)/4, register (kc-1)%4
-    const int tl = (kc - 1) >> 2, tr = (kc - 1) & 3;
-    const unsigned long long cand = tr == 0 ? k[0] : tr == 1 ? k[1] : tr == 2 ? k[2] : k[3];
-    const unsigned long long tau = shfl_xor64(cand, 0) ;
-    const uint32_t lo = __shfl_sync(0xffffffffu, (uint32_t)tau, tl), hi = __shfl_sync(0xffffffffu, (uint32_t)(tau >> 32), tl);
-    return n >= kc ? (((unsigned long long)hi << 32) | lo) : VG_KEY_EMPTY;
+    return r;
 }
 
-template <bool RESIDENT, bool IS_DOT>
+// PASS 1: group minima.  PASS 2: collect rows with s <= tau(q).
+template <bool RESIDENT, bool IS_DOT, int PASS>
 __global__ void __launch_bounds__(NTHREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, Args A) {
     using S = Smem<RESIDENT>;
@@ -222,7 +224,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q0 = blockIdx.x * BMQ;
-    const int split = blockIdx.y, splits = gridDim.y;
+    const int split = blockIdx.y;
     const int64_t row_begin = (int64_t)split * A.rows_per_split;
     int64_t row_end = row_begin + A.rows_per_split;
     if (row_end > A.rows) row_end = A.rows;
@@ -332,10 +334,10 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         float *xs = reinterpret_cast<float *>(smem + S::OFF_XN);
         const float INF = __int_as_float(0x7f800000);
         const bool q_live = q < A.nq;
-        // candidate buffer of this (query, split): padded query index so dead slots have a private scratch row too
-        unsigned long long *buf = A.cand + ((size_t)((int64_t)q0 + slot) * splits + split) * CBUF;
-        float tau_f = q_live ? INF : -INF;   // dead query rows accept nothing
-        int cnt = 0;
+        float tau_f = -INF;                   // pass 2 threshold; dead query rows accept nothing
+        if (PASS == 2 && q_live) tau_f = A.tau[q];
+        float gmin = INF;                     // pass 1 running minimum of the current group
+        int cc = 0;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
@@ -353,6 +355,9 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                // rows n0 + 32c .. +31 start on a multiple of 32: one mask word covers the chunk
+                uint32_t mw = 0xFFFFFFFFu;
+                if (A.mask) mw = (n0 + c * 32 < A.rows) ? __ldg(A.mask + ((n0 + c * 32) >> 5)) : 0u;
                 tmem_ld_wait();
                 float s[32];
                 const float4 *x4 = reinterpret_cast<const float4 *>(xt + c * 32);
@@ -366,47 +371,52 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                         s[j4 * 4 + i] = IS_DOT ? __fsub_rn(xx[i], dot) : __fmaf_rn(-2.0f, dot, xx[i]);  // dot: xx = 0 | +inf (padding)
                     }
                 }
-                uint32_t m = 0;
+                if (mw != 0xFFFFFFFFu) {
 #pragma unroll
-                for (int j = 0; j < 32; j++) m |= (s[j] <= tau_f) ? (1u << j) : 0u;
-                if (m) {
+                    for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : INF;
+                }
+                if (PASS == 1) {
+                    float m8[8];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        if (m & (1u << j)) {
+                    for (int j = 0; j < 8; j++) m8[j] = fminf(fminf(s[j], s[j + 8]), fminf(s[j + 16], s[j + 24]));
+                    const float cm = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
+                    gmin = fminf(gmin, cm);
+                    if (++cc == A.cpg) {
+                        const int64_t gid = (n0 + c * 32) / (32 * (int64_t)A.cpg);
+                        A.mins[q * A.groups + gid] = gmin;
+                        gmin = INF;
+                        cc = 0;
+                    }
+                } else {
+                    uint32_t m4[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int j = 0; j < 32; j++) m4[j & 3] |= (s[j] <= tau_f) ? (1u << j) : 0u;
+                    const uint32_t m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
+                    uint32_t um = __reduce_or_sync(0xffffffffu, m);
+                    while (um) {  // rare: about kc survivors per query over the whole scan
+                        const int j = __ffs(um) - 1;
+                        um &= um - 1;
+                        const float sj = pick32(s, j);
+                        if ((m >> j) & 1u) {
                             const int64_t row = n0 + c * 32 + j;
-                            bool ok = row < row_end;
-                            if (ok && A.mask) ok = (A.mask[row >> 3] >> (row & 7)) & 1;
-                            if (ok && cnt < CBUF) {
-                                __stcg(buf + cnt, ((unsigned long long)f32_orderable(s[j]) << 32) | (unsigned long long)(A.row_base + (uint32_t)row));
-                                cnt++;
+                            if (row < row_end) {
+                                const int pos = atomicAdd(A.cand_cnt + q, 1);
+                                if (pos < CAP)
+                                    A.cand[(size_t)q * CAP + pos] =
+                                        ((unsigned long long)f32_orderable(sj) << 32) | (unsigned long long)(A.row_base + (uint32_t)row);
                             }
                         }
                     }
-                }
-                // a buffer that could overflow during the next 32 columns is compacted now (warp-cooperative, in registers)
-                unsigned need = __ballot_sync(0xffffffffu, cnt > CBUF - 32);
-                if (need) {
-                    __threadfence_block();
-                    __syncwarp();
-                    while (need) {
-                        const int src = __ffs(need) - 1;
-                        need &= need - 1;
-                        const int n_src = __shfl_sync(0xffffffffu, cnt, src);
-                        unsigned long long *b = A.cand + ((size_t)((int64_t)q0 + half * BM + quad * 32 + src) * splits + split) * CBUF;
-                        const unsigned long long tau_key = compact_global(b, n_src, A.kc, lane);
-                        if (lane == src) {
-                            cnt = n_src < A.kc ? n_src : A.kc;
-                            tau_f = (tau_key == VG_KEY_EMPTY) ? INF : f32_from_orderable((uint32_t)(tau_key >> 32));
-                        }
-                    }
-                    __threadfence_block();
-                    __syncwarp();
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
         }
-        A.cand_cnt[(size_t)((int64_t)q0 + slot) * splits + split] = q_live ? cnt : 0;
+        if (PASS == 1 && cc > 0 && ntiles > 0) {  // partial last group of this row range
+            const int64_t last_chunk_row = row_begin + (int64_t)ntiles * BN - 32;
+            const int64_t gid = last_chunk_row / (32 * (int64_t)A.cpg);
+            A.mins[q * A.groups + gid] = gmin;
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -416,35 +426,42 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
-// Per query: merge the (unsorted) candidate lists of all row splits into the best kc (one warp per query).
-__global__ void __launch_bounds__(256) tc_merge_kernel(const unsigned long long *cand, const int32_t *cand_cnt, int64_t nq, int splits,
-                                                       int kc, int C, uint32_t *out_rows, float *out_s, int32_t *out_cnt) {
+// tau(q) = kc-th smallest group minimum of query q: one warp per query streams mins[q][*] (coalesced) through the
+// shared-memory bounded top-k (threshold filter + bitonic compaction).  +inf when there are fewer than kc groups.
+__global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64_t groups, int64_t nq, int64_t nq_pad, int kc, int C,
+                                                        float *tau) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     TopK tk = topk_carve(smem, nw, C, kc);
     topk_init(tk, nw, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t q = (int64_t)blockIdx.x * nw + warp;
-    if (q >= nq) return;
-    const int trigger = C - 32;
-    for (int sp = 0; sp < splits; sp++) {
-        const int n = cand_cnt[q * splits + sp];
-        const unsigned long long *src = cand + ((size_t)q * splits + sp) * CBUF;
-        for (int i0 = 0; i0 < n; i0 += 32) {
-            const int i = i0 + lane;
-            if (i < n) {
-                const unsigned long long key = __ldcg(src + i);
-                if (key < tk.tau[warp]) {
-                    const int pos = atomicAdd(&tk.cnt[warp], 1);
-                    if (pos < C) tk.keys[(size_t)warp * C + pos] = key;
-                }
-            }
-            __syncwarp();
-            if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
-            __syncwarp();
-        }
+    if (q >= nq_pad) return;
+    const float INF = __int_as_float(0x7f800000);
+    if (q >= nq) {
+        if (lane == 0) tau[q] = -INF;
+        return;
     }
-    topk_emit_warp(tk, warp, lane, false, out_rows + q * kc, out_s + q * kc, out_cnt + q, kc);
+    const float *src = mins + q * groups;
+    const int trigger = C - 32;
+    for (int64_t g0 = 0; g0 < groups; g0 += 32) {
+        const int64_t g = g0 + lane;
+        if (g < groups) {
+            const unsigned long long key = ((unsigned long long)f32_orderable(src[g]) << 32) | (unsigned long long)(uint32_t)g;
+            if (key < tk.tau[warp]) {
+                const int pos = atomicAdd(&tk.cnt[warp], 1);
+                if (pos < C) tk.keys[(size_t)warp * C + pos] = key;
+            }
+        }
+        __syncwarp();
+        if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
+        __syncwarp();
+    }
+    topk_compact_warp(tk, warp, lane, true);
+    if (lane == 0) {
+        const int n = tk.cnt[warp];
+        tau[q] = (n >= kc) ? f32_from_orderable((uint32_t)(tk.keys[(size_t)warp * C + kc - 1] >> 32)) : INF;
+    }
 }
 
 // ------------------------------------------------------------------ norms
@@ -465,42 +482,43 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float *v, int64_t n, 
 }
 
 // ------------------------------------------------------------------ finalize
-// One CTA per query: exact scores of the k' candidates in simd.SquaredL2 / simd.Dot
-// order (floats_avx512.c:12-129: 4 x 16-lane FMA accumulators, (A1+A2)+(A3+A4), lane
-// tree, FMA scalar tail), then the heap order (score, row) picks the top k and the
-// certificate is evaluated in double precision.
+// One CTA per query: exact scores of the candidates in simd.SquaredL2 / simd.Dot order
+// (floats_avx512.c:12-129: 4 x 16-lane FMA accumulators, (A1+A2)+(A3+A4), lane tree, FMA
+// scalar tail), then the heap order (score, row) picks the top k and the certificate is
+// evaluated in double precision.
 __global__ void __launch_bounds__(128) flat_tc_finalize_kernel(const float *vectors, int64_t dim, const float *queries, int64_t nq,
-                                                               const uint32_t *cand_rows, const float *cand_s, const int32_t *cand_cnt,
-                                                               int kc, int k, int is_dot, uint32_t row_base, const float *qn,
+                                                               const unsigned long long *cand, const int32_t *cand_cnt, const float *tau,
+                                                               int k, int is_dot, uint32_t row_base, const float *qn,
                                                                const unsigned int *xmax_bits, uint32_t *out_rows, float *out_scores,
                                                                int32_t *out_counts, int32_t *fail_flags) {
-    __shared__ unsigned long long ek[128];
+    __shared__ unsigned long long ek[CAP];
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
-    const int n = cand_cnt[q];
+    const int n_all = cand_cnt[q];
+    const int n = n_all < CAP ? n_all : CAP;
     const float *qv = queries + q * dim;
-    for (int j0 = 0; j0 < 128; j0 += 8) {
+    for (int j0 = 0; j0 < CAP; j0 += 8) {
         const int j = j0 + hw;
-        if (j0 >= kc) break;
         const bool live = j < n;
-        const uint32_t row = live ? cand_rows[q * kc + j] : row_base;
+        const uint32_t row = live ? (uint32_t)__ldcg(cand + (size_t)q * CAP + j) : row_base;
         const float *x = vectors + (int64_t)(row - row_base) * dim;
-        float a[4] = {0.f, 0.f, 0.f, 0.f};
-        const int64_t epochs = dim >> 6;
-        for (int64_t e = 0; e < epochs; e++)
+        float tot = 0.0f;
+        if (j0 < n) {  // uniform per CTA
+            float a[4] = {0.f, 0.f, 0.f, 0.f};
+            const int64_t epochs = dim >> 6;
+            for (int64_t e = 0; e < epochs; e++)
 #pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int64_t d = e * 64 + jj * 16 + lane;
-                if (is_dot) {
-                    a[jj] = __fmaf_rn(qv[d], __ldg(x + d), a[jj]);
-                } else {
-                    const float df = __fsub_rn(qv[d], __ldg(x + d));
-                    a[jj] = __fmaf_rn(df, df, a[jj]);
+                for (int jj = 0; jj < 4; jj++) {
+                    const int64_t d = e * 64 + jj * 16 + lane;
+                    if (is_dot) {
+                        a[jj] = __fmaf_rn(qv[d], __ldg(x + d), a[jj]);
+                    } else {
+                        const float df = __fsub_rn(qv[d], __ldg(x + d));
+                        a[jj] = __fmaf_rn(df, df, a[jj]);
+                    }
                 }
-            }
-        float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
-        if (lane == 0 && j < 128) {
-            if (live) {
+            tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+            if (lane == 0 && live) {
                 for (int64_t d = epochs * 64; d < dim; d++) {
                     if (is_dot) {
                         tot = __fmaf_rn(qv[d], __ldg(x + d), tot);
@@ -509,19 +527,15 @@ __global__ void __launch_bounds__(128) flat_tc_finalize_kernel(const float *vect
                         tot = __fmaf_rn(df, df, tot);
                     }
                 }
-                ek[j] = make_key(tot, row, is_dot != 0);
-            } else {
-                ek[j] = VG_KEY_EMPTY;
             }
         }
+        if (lane == 0) ek[j] = live ? make_key(tot, row, is_dot != 0) : VG_KEY_EMPTY;
     }
     __syncthreads();
     if (tid < 32) {
-        // sort all 128 slots in registers (slots beyond the 8-aligned candidate bound are empty)
-        const int filled = ((kc + 7) / 8) * 8;
         unsigned long long kk[4];
 #pragma unroll
-        for (int r = 0; r < 4; r++) kk[r] = (tid * 4 + r) < filled ? ek[tid * 4 + r] : VG_KEY_EMPTY;
+        for (int r = 0; r < 4; r++) kk[r] = ek[tid * 4 + r];
         warp_sort128(kk, tid);
 #pragma unroll
         for (int r = 0; r < 4; r++) ek[tid * 4 + r] = kk[r];
@@ -539,15 +553,20 @@ __global__ void __launch_bounds__(128) flat_tc_finalize_kernel(const float *vect
         if (tid == 0) {
             out_counts[q] = m;
             int fail = 0;
-            if (n >= kc && m > 0) {  // candidate list was full: rows outside it exist (or may exist)
-                const double T = (double)cand_s[q * kc + kc - 1];
-                const double qq = (double)qn[q], xx = (double)__uint_as_float(*xmax_bits);
-                const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125, c2 = 1.0 / 16384.0;
-                const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx);
-                const double ex = (double)key_score(ek[m - 1], is_dot != 0);
-                const double s_exact = is_dot ? -ex : ex - qq;
-                if (!(s_exact < T - E)) fail = 1;
-                if (m < k) fail = 1;  // fewer than k candidates although the list was full: cannot happen (kc >= k)
+            const float t = tau[q];
+            if (n_all > CAP) {
+                fail = 1;  // survivors were dropped: the list is not the full set {s <= tau}
+            } else if (t < __int_as_float(0x7f800000)) {  // finite threshold: rows outside the list exist (or may exist)
+                if (m < k) {
+                    fail = 1;
+                } else {
+                    const double qq = (double)qn[q], xx = (double)__uint_as_float(*xmax_bits);
+                    const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125, c2 = 1.0 / 16384.0;
+                    const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx);
+                    const double ex = (double)key_score(ek[m - 1], is_dot != 0);
+                    const double s_exact = is_dot ? -ex : ex - qq;
+                    if (!(s_exact < (double)t - E)) fail = 1;
+                }
             }
             fail_flags[q] = fail;
         }
@@ -584,9 +603,12 @@ static vg_status make_map(CUtensorMap *map, const float *base, int64_t rows, int
 }
 
 bool supported(int64_t dim, int64_t rows, int64_t nq, int64_t k) {
-    return dim >= 16 && dim % 4 == 0 && rows >= 1024 && rows < (1ll << 31) && nq >= 16 && k >= 1 && k <= 32;
+    return dim >= 16 && dim % 4 == 0 && rows >= 8192 && rows < (1ll << 31) && nq >= 16 && k >= 1 && k <= 32;
 }
-int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }
+int candidates_for(int64_t k, int64_t dim) {
+    const int kc = k <= 16 ? 32 : (int)(2 * k);
+    return dim > 256 ? std::max(kc, 64) : kc;  // the error bound grows with ||q|| ||x||: keep more slack on long vectors
+}
 
 vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsigned int *d_max_bits, cudaStream_t st) {
     if (n <= 0) return VG_OK;
@@ -596,15 +618,21 @@ vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsign
     return VG_OK;
 }
 
-template <bool RESIDENT, bool IS_DOT>
+template <bool RESIDENT, bool IS_DOT, int PASS>
 static vg_status launch(const CUtensorMap &mq, const CUtensorMap &mx, const Args &a, int64_t qtiles, int splits, cudaStream_t st) {
     using S = Smem<RESIDENT>;
     const size_t sm = S::TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-    VG_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RESIDENT, IS_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VG_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RESIDENT, IS_DOT, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)qtiles, (unsigned)splits);
-    flat_tc_kernel<RESIDENT, IS_DOT><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
+    flat_tc_kernel<RESIDENT, IS_DOT, PASS><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
     VG_LAUNCHED();
     return VG_OK;
+}
+template <int PASS>
+static vg_status launch_pass(bool resident, bool is_dot, const CUtensorMap &mq, const CUtensorMap &mx, const Args &a, int64_t qtiles,
+                             int splits, cudaStream_t st) {
+    if (resident) return is_dot ? launch<true, true, PASS>(mq, mx, a, qtiles, splits, st) : launch<true, false, PASS>(mq, mx, a, qtiles, splits, st);
+    return is_dot ? launch<false, true, PASS>(mq, mx, a, qtiles, splits, st) : launch<false, false, PASS>(mq, mx, a, qtiles, splits, st);
 }
 
 vg_status filter(const FilterArgs &f, cudaStream_t st) {
@@ -613,9 +641,15 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
     VG_TRY(make_map(&mq, f.d_queries, f.nq, f.dim, BMQ));
     VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, BN));
     const int64_t qtiles = (f.nq + BMQ - 1) / BMQ;
+    const int64_t nq_pad = qtiles * BMQ;
+    // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
+    int64_t G = 32;
+    while (G < 8192 && f.rows / (G * 2) >= 128ll * f.kc) G *= 2;
+    const int64_t groups = (f.rows + G - 1) / G;
+    const int64_t unit = std::max<int64_t>(BN, G);  // row ranges are whole tiles and whole groups
     // one CTA per SM (shared memory): pick the row-split count whose CTA total fills whole waves best
     const int64_t sms = sm_count();
-    const int64_t max_splits = std::max<int64_t>(1, f.rows / (4 * BN));
+    const int64_t max_splits = std::max<int64_t>(1, f.rows / (4 * unit));
     int64_t splits = 1;
     double best = 0.0;
     for (int64_t s_ = 1; s_ <= sms && s_ <= max_splits; s_++) {
@@ -628,49 +662,42 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
         if (eff >= 0.97) break;
     }
     int64_t rps = (f.rows + splits - 1) / splits;
-    rps = (rps + BN - 1) / BN * BN;
+    rps = (rps + unit - 1) / unit * unit;
     splits = (f.rows + rps - 1) / rps;
     Args a;
     a.xn = f.d_xn;
-    a.mask = f.d_mask;
+    a.mask = reinterpret_cast<const uint32_t *>(f.d_mask);
     a.nq = f.nq;
+    a.nq_pad = nq_pad;
     a.rows = f.rows;
     a.rows_per_split = rps;
     a.kb = (int)((f.dim + BK - 1) / BK);
-    a.kc = f.kc;
+    a.cpg = (int)(G / 32);
+    a.groups = groups;
     a.row_base = f.row_base;
-    DevBuf cand, ccnt;
-    const int64_t nq_pad = qtiles * BMQ;
-    VG_TRY(cand.alloc((size_t)nq_pad * splits * CBUF * 8));
-    VG_TRY(ccnt.alloc((size_t)nq_pad * splits * 4));
-    a.cand = cand.as<unsigned long long>();
-    a.cand_cnt = ccnt.as<int32_t>();
+    DevBuf mins, tau;
+    VG_TRY(mins.alloc((size_t)groups * nq_pad * 4));
+    a.mins = mins.as<float>();
+    a.tau = f.d_tau;
+    a.cand = f.d_cand;
+    a.cand_cnt = f.d_cand_cnt;
     const bool resident = a.kb <= MAX_RES_KB;
-    if (resident) {
-        if (f.is_dot) VG_TRY((launch<true, true>(mq, mx, a, qtiles, (int)splits, st)));
-        else VG_TRY((launch<true, false>(mq, mx, a, qtiles, (int)splits, st)));
-    } else {
-        if (f.is_dot) VG_TRY((launch<false, true>(mq, mx, a, qtiles, (int)splits, st)));
-        else VG_TRY((launch<false, false>(mq, mx, a, qtiles, (int)splits, st)));
-    }
-    // merge the per-split lists (keys are in s-space, ascending = better)
+    VG_TRY(launch_pass<1>(resident, f.is_dot != 0, mq, mx, a, qtiles, (int)splits, st));
     {
-        const int C = topk_capacity(f.kc, 32);
-        const int nw = 8;
+        const int C = topk_capacity(f.kc, 32), nw = 8;
         const size_t sm = topk_smem_bytes(nw, C);
-        VG_CUDA(cudaFuncSetAttribute(tc_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-        tc_merge_kernel<<<(unsigned)((f.nq + nw - 1) / nw), nw * 32, sm, st>>>(a.cand, a.cand_cnt, f.nq, (int)splits, f.kc, C, f.d_cand_rows,
-                                                                              f.d_cand_s, f.d_cand_cnt);
+        tc_select_kernel<<<(unsigned)((nq_pad + nw - 1) / nw), nw * 32, sm, st>>>(a.mins, groups, f.nq, nq_pad, f.kc, C, f.d_tau);
         VG_LAUNCHED();
     }
-    return VG_OK;  // cand / ccnt are returned to the stream-ordered pool (freed in stream order)
+    VG_CUDA(cudaMemsetAsync(f.d_cand_cnt, 0, (size_t)f.nq * 4, st));
+    VG_TRY(launch_pass<2>(resident, f.is_dot != 0, mq, mx, a, qtiles, (int)splits, st));
+    return VG_OK;  // mins is returned to the stream-ordered pool (freed in stream order)
 }
 
 vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned int *d_xmax_bits, uint32_t *d_rows, float *d_scores,
                    int32_t *d_counts, int32_t *d_fail, cudaStream_t st) {
-    flat_tc_finalize_kernel<<<(unsigned)f.nq, 128, 0, st>>>(f.d_vectors, f.dim, f.d_queries, f.nq, f.d_cand_rows, f.d_cand_s, f.d_cand_cnt,
-                                                            f.kc, k, f.is_dot, f.row_base, d_qn, d_xmax_bits, d_rows, d_scores, d_counts,
-                                                            d_fail);
+    flat_tc_finalize_kernel<<<(unsigned)f.nq, 128, 0, st>>>(f.d_vectors, f.dim, f.d_queries, f.nq, f.d_cand, f.d_cand_cnt, f.d_tau, k,
+                                                            f.is_dot, f.row_base, d_qn, d_xmax_bits, d_rows, d_scores, d_counts, d_fail);
     VG_LAUNCHED();
     return VG_OK;
 }
