@@ -123,6 +123,19 @@ vg_status vg_pq_build_distance_table(const float *h_queries, int64_t nq, int64_t
 vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
                       int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32 /* optional [m][k][dim/m] */);
 
+/* OptimizedProductQuantizer (opq.go:28-282, svd.go:13-216).  Rotations are [dim/block][block][block] float32,
+ * block = vg_opq_block_size(dim, m) (NewOptimizedProductQuantizer's rule, opq.go:41-58).
+ * vg_opq_train: `opq_iters` rounds of rotate -> ProductQuantizer.Train (`pq_iters` Lloyd iterations, seed + round)
+ *   -> M_b = sum_i x_b^T Decode(Encode(Rx))_b in sample order -> Procrustes (one-sided Jacobi SVD, R = U V^T with the
+ *   reflection fix).  Outputs the final rotations and the codebooks of the LAST ProductQuantizer.Train, as the reference.
+ * vg_opq_rotate: rotateVector (inverse = 0, simd.Dot per output) or Decode's inverse rotation (inverse = 1).
+ * vg_opq_procrustes: computeProcrustesRotation for `blocks` n x n matrices (h_sigma optional: singular values). */
+vg_status vg_opq_block_size(int64_t dim, int64_t m, int64_t *block_size);
+vg_status vg_opq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t opq_iters, int64_t pq_iters,
+                       uint64_t seed, float *h_rotations, int8_t *h_codebooks, float *h_scales, float *h_offsets);
+vg_status vg_opq_rotate(const float *h_vecs, int64_t n, int64_t dim, int64_t block, const float *h_rotations, int32_t inverse, float *h_out);
+vg_status vg_opq_procrustes(const float *h_M, int64_t blocks, int64_t n, float *h_R, float *h_sigma);
+
 /* Device-resident variants (d_vecs / d_codes in HBM; parameters still host arrays): used to
  * encode shards that never exist on the host (flat.Writer.Flush-style bulk encode). */
 vg_status vg_minmax_dev(const float *d_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs);

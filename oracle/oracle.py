@@ -129,6 +129,11 @@ _sig(lib.vgo_pq_encode, None, f32p, i64, i64, i64, i8p, f32p, f32p, u8p)
 _sig(lib.vgo_pq_decode, None, u8p, i64, i64, i64, i8p, f32p, f32p, f32p)
 _sig(lib.vgo_pq_asymmetric, f32, f32p, u8p, i64, i64, i64, i8p, f32p, f32p)
 _sig(lib.vgo_pq_quantize_centroids, None, f32p, i64, i8p, f32p, f32p)
+_sig(lib.vgo_opq_block_size, i64, i64, i64)
+_sig(lib.vgo_opq_rotate, None, f32p, i64, i64, f32p, f32p)
+_sig(lib.vgo_opq_unrotate, None, f32p, i64, i64, f32p, f32p)
+_sig(lib.vgo_opq_accumulate_m, None, f32p, f32p, i64, i64, i64, f32p)
+_sig(lib.vgo_opq_procrustes, None, f32p, i64, f32p, f32p, f32p)
 _sig(lib.vgo_splitmix64, C.c_uint64, C.c_uint64)
 _sig(lib.vgo_rng_intn, i64, C.c_uint64, C.c_uint64, C.c_uint64, i64)
 _sig(lib.vgo_rng_f32, f32, C.c_uint64, C.c_uint64, C.c_uint64)

@@ -533,3 +533,81 @@ def test_pq_train_matches_oracle(vg):
     # pq_test.go:59-71: reconstruction MSE < 0.5 on N(0,1) data
     rec = pq.DecodeBatch(pq.EncodeBatch(v[:200]))
     assert float(np.mean((rec - v[:200]) ** 2)) < 0.5
+
+
+# ----------------------------------------------------------------- OPQ (opq.go, svd.go)
+def test_opq_procrustes_matches_oracle(vg):
+    """computeProcrustesRotation: bit-exact with the restatement; R orthogonal with det +1 (opq_test.go:56-99)."""
+    rng = np.random.default_rng(51)
+    for n in (8, 32, 48):
+        blocks = 3
+        M = rng.standard_normal((blocks, n, n)).astype(F)
+        M[1] = M[1] @ np.diag(np.linspace(1, -1, n)).astype(F)  # a block whose plain U V^T is a reflection
+        R = np.zeros_like(M)
+        sig = np.zeros((blocks, n), F)
+        L = vg._lib
+        L.call("vg_opq_procrustes", L.ptr(M, L.f32p), blocks, n, L.ptr(R, L.f32p), L.ptr(sig, L.f32p))
+        for b in range(blocks):
+            m = M[b].copy()
+            want = np.zeros((n, n), F)
+            ws = np.zeros(n, F)
+            o.lib.vgo_opq_procrustes(o.fp(m), n, o.fp(want), o.fp(ws), None)
+            assert np.array_equal(bits(R[b]), bits(want)), (n, b)
+            assert np.array_equal(bits(sig[b]), bits(ws)), (n, b)
+            assert np.allclose(R[b] @ R[b].T, np.eye(n), atol=1e-3)
+            assert np.linalg.det(R[b].astype(np.float64)) > 0.9
+
+
+@pytest.mark.parametrize("n,dim,m,rounds", [(600, 32, 8, 3), (500, 96, 12, 2)])
+def test_opq_train_matches_oracle(vg, n, dim, m, rounds):
+    """OptimizedProductQuantizer.Train against the restatement composed round by round (opq.go:89-193)."""
+    k, pq_iters, seed = 256, 4, 99
+    rng = np.random.default_rng(n + dim)
+    v = (rng.random((n, dim)) * 2 - 1).astype(F)           # UniformRangeVectors as opq_test.go
+    opq = vg.quantization.OptimizedProductQuantizer(dim, m, k, rounds)
+    opq.Train(v, pq_iters=pq_iters, seed=seed)
+    bs = int(o.lib.vgo_opq_block_size(dim, m))
+    assert opq.blockSize == bs == (32 if dim > 64 else dim)
+    ds, nb = dim // m, dim // bs
+    rot = np.tile(np.eye(bs, dtype=F), (nb, 1, 1))
+    cb = np.zeros(m * k * ds, np.int8)
+    sc, of = np.zeros(m, F), np.zeros(m, F)
+    for it in range(rounds):
+        xr = np.zeros_like(v)
+        for i in range(n):
+            o.lib.vgo_opq_rotate(o.fp(v[i]), dim, bs, o.fp(rot), o.fp(xr[i]))
+        for s in range(m):
+            cent = np.zeros((k, ds), F)
+            o.lib.vgo_pq_kmeanspp_init(o.fp(xr), n, dim, s * ds, ds, k, seed + it, s, o.fp(cent))
+            assign = np.zeros(n, np.int32)
+            o.lib.vgo_pq_lloyd(o.fp(xr), n, dim, s * ds, ds, k, pq_iters, seed + it, s, o.fp(cent), assign.ctypes.data_as(o.i32p))
+            s1, o1 = np.zeros(1, F), np.zeros(1, F)
+            o.lib.vgo_pq_quantize_centroids(o.fp(cent), k * ds, cb[s * k * ds:].ctypes.data_as(o.i8p), o.fp(s1), o.fp(o1))
+            sc[s], of[s] = s1[0], o1[0]
+        yh = np.zeros_like(v)
+        codes = np.zeros(m, np.uint8)
+        for i in range(n):
+            o.lib.vgo_pq_encode(o.fp(xr[i]), dim, m, k, cb.ctypes.data_as(o.i8p), o.fp(sc), o.fp(of), o.bp(codes))
+            o.lib.vgo_pq_decode(o.bp(codes), dim, m, k, cb.ctypes.data_as(o.i8p), o.fp(sc), o.fp(of), o.fp(yh[i]))
+        M = np.zeros((nb, bs, bs), F)
+        o.lib.vgo_opq_accumulate_m(o.fp(v), o.fp(yh), n, dim, bs, o.fp(M))
+        for b in range(nb):
+            o.lib.vgo_opq_procrustes(o.fp(M[b]), bs, o.fp(rot[b]), None, None)
+    assert np.array_equal(bits(opq.rotations), bits(rot))
+    assert np.array_equal(opq.pq.codebooks, cb)
+    assert np.array_equal(bits(opq.pq.scales), bits(sc)) and np.array_equal(bits(opq.pq.offsets), bits(of))
+    # opq_test.go:56-99 rotation orthogonality (0.1), :26-54 encode/decode shapes, :101-131 asymmetric distance
+    for b in range(nb):
+        assert np.allclose(opq.rotations[b] @ opq.rotations[b].T, np.eye(bs), atol=0.1)
+    codes = opq.EncodeBatch(v[:5])
+    assert codes.shape == (5, m)
+    rec = opq.DecodeBatch(codes)
+    want = np.zeros(dim, F)
+    tmp = np.zeros(dim, F)
+    for i in range(5):
+        o.lib.vgo_pq_decode(o.bp(codes[i]), dim, m, k, cb.ctypes.data_as(o.i8p), o.fp(sc), o.fp(of), o.fp(tmp))
+        o.lib.vgo_opq_unrotate(o.fp(tmp), dim, bs, o.fp(rot), o.fp(want))
+        assert np.array_equal(bits(rec[i]), bits(want))
+    d_self = opq.ComputeAsymmetricDistance(v[0], codes[0])
+    d_other = opq.ComputeAsymmetricDistance(v[0], codes[1])
+    assert 0 < d_self < d_other

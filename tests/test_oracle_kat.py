@@ -256,3 +256,54 @@ def test_kmeans_kat():  # internal/kmeans/kmeans_test.go:12-88 (two well separat
 def test_crc32c_kat():
     d = np.frombuffer(b"123456789", np.uint8)
     assert o.lib.vgo_crc32c(o.bp(d), 9) == 0xE3069283  # CRC-32C check value
+
+
+# ------------------------------------------------------------------ OPQ (opq.go, svd.go, opq_test.go)
+def test_opq_block_size_rule():
+    # NewOptimizedProductQuantizer opq.go:41-58: full dimension up to 64, else the multiple of the subvector size
+    # that divides dim and is closest to 32 (first wins on ties)
+    assert o.lib.vgo_opq_block_size(32, 8) == 32      # opq_test.go:11-24
+    assert o.lib.vgo_opq_block_size(64, 8) == 64
+    assert o.lib.vgo_opq_block_size(768, 96) == 32
+    assert o.lib.vgo_opq_block_size(128, 8) == 32
+    assert o.lib.vgo_opq_block_size(96, 2) == 48      # candidates 48, 96
+    assert o.lib.vgo_opq_block_size(100, 1) == 100
+
+
+def test_opq_svd_and_procrustes_properties():
+    """svd.go: M = U diag(sigma) V^T; computeProcrustesRotation: R orthogonal, det +1, maximises tr(R^T M)."""
+    rng = np.random.default_rng(3)
+    for n in (4, 16, 32):
+        M = rng.standard_normal((n, n)).astype(F)
+        u = M.copy()
+        R = np.zeros((n, n), F)
+        sig = np.zeros(n, F)
+        v = np.zeros((n, n), F)
+        o.lib.vgo_opq_procrustes(o.fp(u), n, o.fp(R), o.fp(sig), o.fp(v))
+        ref_sig = np.linalg.svd(M.astype(np.float64), compute_uv=False)
+        assert np.allclose(np.sort(sig)[::-1], ref_sig, rtol=1e-3, atol=1e-4)
+        assert np.allclose(R @ R.T, np.eye(n), atol=1e-4)
+        assert np.linalg.det(R.astype(np.float64)) > 0.99
+        # optimal rotation (Kabsch): trace(R^T M) equals sum(sigma) with the smallest one negated when det(U V^T) < 0
+        U64, s64, Vt64 = np.linalg.svd(M.astype(np.float64))
+        d = np.sign(np.linalg.det(U64 @ Vt64))
+        best = s64[:-1].sum() + d * s64[-1]
+        assert abs(np.trace(R.astype(np.float64).T @ M.astype(np.float64)) - best) < 1e-3 * best
+    # identity in, identity out (the first Train round rotates by I, opq.go:98-101)
+    eye = np.eye(8, dtype=F)
+    R = np.zeros((8, 8), F)
+    o.lib.vgo_opq_procrustes(o.fp(eye.copy()), 8, o.fp(R), None, None)
+    assert np.array_equal(R, eye)
+
+
+def test_opq_rotate_roundtrip():
+    rng = np.random.default_rng(4)
+    dim, bs = 96, 32
+    q, _ = np.linalg.qr(rng.standard_normal((bs, bs)))
+    rot = np.tile(q.astype(F), (dim // bs, 1, 1))
+    x = rng.standard_normal(dim).astype(F)
+    y, z = np.zeros(dim, F), np.zeros(dim, F)
+    o.lib.vgo_opq_rotate(o.fp(x), dim, bs, o.fp(rot), o.fp(y))
+    o.lib.vgo_opq_unrotate(o.fp(y), dim, bs, o.fp(rot), o.fp(z))
+    assert np.allclose(y.reshape(-1, bs), x.reshape(-1, bs) @ q.T.astype(F), atol=1e-5)
+    assert np.allclose(z, x, atol=1e-5)  # R^T R = I

@@ -471,30 +471,6 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
 }
 
 // --------------------------------------------------------------- search
-// OPQ query rotation (opq.go:196-214): out[b*bs + i] = simd.Dot(R_b[i], v_b).
-__global__ void __launch_bounds__(256) opq_rotate_kernel(const float *v, int64_t n, int64_t dim, int bs, const float *rot,
-                                                         float *out) {
-    const int64_t hwid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
-    const int lane = threadIdx.x & 15;
-    const int64_t total = n * dim;
-    const bool live = hwid < total;
-    const int64_t o = live ? hwid : total - 1;
-    const int64_t r = o / dim, d = o - r * dim;
-    const int64_t b = d / bs, i = d - b * bs;
-    const float *row = rot + (b * bs + i) * bs;
-    const float *x = v + r * dim + b * bs;
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
-    const int epochs = bs >> 6;
-    for (int e = 0; e < epochs; e++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) a[j] = __fmaf_rn(row[e * 64 + j * 16 + lane], x[e * 64 + j * 16 + lane], a[j]);
-    float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
-    if (lane == 0 && live) {
-        for (int t = epochs * 64; t < bs; t++) tot = __fmaf_rn(row[t], x[t], tot);
-        out[o] = tot;
-    }
-}
-
 // Flat float32 search through the tcgen05 filter (vg_flat_tc.cu): candidates by TF32 GEMM, exact re-check in simd
 // pair order, certificate; queries whose certificate fails are re-run on the exact CUDA-core scan below.
 static std::atomic<int> g_tc_enabled{-1};
@@ -665,10 +641,7 @@ static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, 
     }
     if (d.codec == VG_CODEC_OPQ) {
         VG_TRY(rotated.alloc((size_t)nq * d.dim * 4));
-        const int64_t threads = nq * d.dim * 16;
-        opq_rotate_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_queries, nq, d.dim, (int)d.opq_block,
-                                                                            ix->rotation.as<float>(), rotated.as<float>());
-        VG_LAUNCHED();
+        VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), rotated.as<float>(), st));  // opq.go:196-214
         a.queries = rotated.as<float>();
     }
     if (d.num_partitions > 1) {

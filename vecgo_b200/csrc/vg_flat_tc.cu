@@ -444,18 +444,28 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64
     }
     const float *src = mins + q * groups;
     const int trigger = C - 32;
-    for (int64_t g0 = 0; g0 < groups; g0 += 32) {
-        const int64_t g = g0 + lane;
-        if (g < groups) {
-            const unsigned long long key = ((unsigned long long)f32_orderable(src[g]) << 32) | (unsigned long long)(uint32_t)g;
-            if (key < tk.tau[warp]) {
-                const int pos = atomicAdd(&tk.cnt[warp], 1);
-                if (pos < C) tk.keys[(size_t)warp * C + pos] = key;
-            }
+    // 4 independent coalesced loads per lane per step (the loop is otherwise bound by L2 latency)
+    for (int64_t g0 = 0; g0 < groups; g0 += 128) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t g = g0 + u * 32 + lane;
+            v[u] = g < groups ? __ldcg(src + g) : INF;
         }
-        __syncwarp();
-        if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
-        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const int64_t g = g0 + u * 32 + lane;
+            if (g < groups) {
+                const unsigned long long key = ((unsigned long long)f32_orderable(v[u]) << 32) | (unsigned long long)(uint32_t)g;
+                if (key < tk.tau[warp]) {
+                    const int pos = atomicAdd(&tk.cnt[warp], 1);
+                    if (pos < C) tk.keys[(size_t)warp * C + pos] = key;
+                }
+            }
+            __syncwarp();
+            if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
+            __syncwarp();
+        }
     }
     topk_compact_warp(tk, warp, lane, true);
     if (lane == 0) {

@@ -478,6 +478,58 @@ static vg_status pq_assign_all(const float *d_vecs, int64_t n, int64_t dim, int 
 
 using namespace vg;
 
+namespace vg {
+// ProductQuantizer.Train on device-resident vectors (pq.go:68-143,275-433); outputs stay on the device.
+vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed, DevBuf &cent,
+                       DevBuf &cb, DevBuf &sc, DevBuf &of, cudaStream_t st) {
+    const int G = (int)m, K = (int)k, ds = (int)(dim / m);
+    DevBuf mind, zero, chosen, score, cnt;
+    VG_TRY(cent.alloc((size_t)G * K * ds * 4));
+    // ---- initializeCentroids
+    if (n < k) {
+        const int64_t t = (int64_t)G * K * ds;
+        pp_small_init_kernel<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(d_vecs, n, dim, ds, K, G, cent.as<float>());
+        VG_LAUNCHED();
+    } else {
+        VG_TRY(mind.alloc((size_t)G * n * 4));
+        VG_TRY(zero.alloc((size_t)G * 4));
+        VG_TRY(chosen.alloc((size_t)G * 8));
+        pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
+        VG_LAUNCHED();
+        dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
+        for (int c = 0; c < K; c++) {
+            if (c > 0) {
+                pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>());
+                VG_LAUNCHED();
+            }
+            gather_centroid_kernel<<<(G * ds + 255) / 256, 256, 0, st>>>(d_vecs, dim, ds, K, G, c, chosen.as<int64_t>(),
+                                                                       cent.as<float>());
+            VG_LAUNCHED();
+            if (c + 1 < K) {
+                pp_dist_kernel<<<gd, 256, 0, st>>>(d_vecs, n, dim, ds, K, c, cent.as<float>(), zero.as<int>(), mind.as<float>());
+                VG_LAUNCHED();
+            }
+        }
+    }
+    // ---- runKMeansIterations
+    Lloyd L;
+    VG_TRY(L.init(G, K, ds, n, dim, st));
+    for (int64_t it = 0; it < iters; it++) {
+        VG_TRY(pq_assign_all(d_vecs, n, dim, G, K, ds, cent.as<float>(), L.assign_new.as<uint32_t>(), score, cnt, st));
+        bool any = false;
+        VG_TRY(L.step(d_vecs, cent.as<float>(), 0, seed, 0xE0E0E0E0ull, 1, &any, st));
+        if (!any) break;
+    }
+    // ---- int8 codebooks
+    VG_TRY(cb.alloc((size_t)G * K * ds));
+    VG_TRY(sc.alloc((size_t)G * 4));
+    VG_TRY(of.alloc((size_t)G * 4));
+    pq_quantize_kernel<<<G, 256, 0, st>>>(cent.as<float>(), K * ds, cb.as<int8_t>(), sc.as<float>(), of.as<float>());
+    VG_LAUNCHED();
+    return VG_OK;
+}
+}  // namespace vg
+
 extern "C" {
 
 vg_status vg_kmeans_find_closest(const float *h_queries, int64_t nq, int64_t dim, const float *h_centroids, int64_t k,
@@ -546,51 +598,10 @@ vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, in
     if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");
     cudaStream_t st = stream();
     const int G = (int)m, K = (int)k, ds = (int)(dim / m);
-    DevBuf v, cent, mind, zero, chosen, score, cnt, cb, sc, of;
+    DevBuf v, cent, cb, sc, of;
     VG_TRY(v.alloc((size_t)n * dim * 4));
     VG_TRY(staged_h2d(v.p, h_vecs, (size_t)n * dim * 4));
-    VG_TRY(cent.alloc((size_t)G * K * ds * 4));
-    // ---- initializeCentroids
-    if (n < k) {
-        const int64_t t = (int64_t)G * K * ds;
-        pp_small_init_kernel<<<(unsigned)((t + 255) / 256), 256, 0, st>>>(v.as<float>(), n, dim, ds, K, G, cent.as<float>());
-        VG_LAUNCHED();
-    } else {
-        VG_TRY(mind.alloc((size_t)G * n * 4));
-        VG_TRY(zero.alloc((size_t)G * 4));
-        VG_TRY(chosen.alloc((size_t)G * 8));
-        pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
-        VG_LAUNCHED();
-        dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
-        for (int c = 0; c < K; c++) {
-            if (c > 0) {
-                pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>());
-                VG_LAUNCHED();
-            }
-            gather_centroid_kernel<<<(G * ds + 255) / 256, 256, 0, st>>>(v.as<float>(), dim, ds, K, G, c, chosen.as<int64_t>(),
-                                                                       cent.as<float>());
-            VG_LAUNCHED();
-            if (c + 1 < K) {
-                pp_dist_kernel<<<gd, 256, 0, st>>>(v.as<float>(), n, dim, ds, K, c, cent.as<float>(), zero.as<int>(), mind.as<float>());
-                VG_LAUNCHED();
-            }
-        }
-    }
-    // ---- runKMeansIterations
-    Lloyd L;
-    VG_TRY(L.init(G, K, ds, n, dim, st));
-    for (int64_t it = 0; it < iters; it++) {
-        VG_TRY(pq_assign_all(v.as<float>(), n, dim, G, K, ds, cent.as<float>(), L.assign_new.as<uint32_t>(), score, cnt, st));
-        bool any = false;
-        VG_TRY(L.step(v.as<float>(), cent.as<float>(), 0, seed, 0xE0E0E0E0ull, 1, &any, st));
-        if (!any) break;
-    }
-    // ---- int8 codebooks
-    VG_TRY(cb.alloc((size_t)G * K * ds));
-    VG_TRY(sc.alloc((size_t)G * 4));
-    VG_TRY(of.alloc((size_t)G * 4));
-    pq_quantize_kernel<<<G, 256, 0, st>>>(cent.as<float>(), K * ds, cb.as<int8_t>(), sc.as<float>(), of.as<float>());
-    VG_LAUNCHED();
+    VG_TRY(dev_pq_train(v.as<float>(), n, dim, m, k, iters, seed, cent, cb, sc, of, st));
     VG_CUDA(cudaStreamSynchronize(st));
     VG_TRY(staged_d2h(h_codebooks, cb.p, (size_t)G * K * ds));
     VG_TRY(staged_d2h(h_scales, sc.p, (size_t)G * 4));

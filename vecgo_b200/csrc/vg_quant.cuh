@@ -28,4 +28,7 @@ vg_status dev_permute_int4(const uint8_t *d_src, uint8_t *d_dst, int64_t n, int6
 vg_status dev_permute_pq(const uint8_t *d_src, uint8_t *d_dst_base, int64_t row0, int64_t n, int m, int mpad, cudaStream_t st);
 vg_status dev_split_sign(const uint8_t *d_src, int64_t n, int64_t nbytes, int64_t src_stride, int64_t dst_stride, uint8_t *d_bits,
                          float *d_norms, cudaStream_t st);
+// OptimizedProductQuantizer (vg_opq.cu): rotateVector for n vectors; Procrustes rotations of `blocks` bs x bs matrices.
+vg_status dev_opq_rotate(const float *d_v, int64_t n, int64_t dim, int bs, const float *d_rot, float *d_out, cudaStream_t st);
+vg_status dev_opq_procrustes(const float *d_M, int blocks, int bs, float *d_R, float *d_sigma, cudaStream_t st);
 }  // namespace vg

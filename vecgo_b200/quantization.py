@@ -5,6 +5,7 @@ what production code should call (one C-ABI crossing per batch).
 """
 from __future__ import annotations
 
+import ctypes as C
 import enum
 import struct
 
@@ -442,6 +443,18 @@ class ProductQuantizer:
             raise QuantizerError("codes length mismatch")
         return simd.PqAdcLookup(table, c, self.numSubvectors)
 
+    def ComputeAsymmetricDistance(self, query, codes) -> np.float32:
+        """pq.go:234-260: dist += SquaredL2Int8Dequantized(q_m, centroid_m) over subspaces in order.  Every term equals the
+        distance-table entry (same scalar arithmetic, kernels.go:354-374); the sequential float32 sum is done on the host."""
+        c = L.as_u8(codes)
+        if c.size != self.numSubvectors:
+            raise QuantizerError("codes length mismatch")
+        t = self.BuildDistanceTable(query).reshape(self.numSubvectors, self.numCentroids)
+        dist = F(0)
+        for m in range(self.numSubvectors):
+            dist = F(dist + t[m, int(c[m])])
+        return dist
+
     def BytesPerVector(self) -> int:
         return self.numSubvectors
 
@@ -459,3 +472,73 @@ class ProductQuantizer:
 
     def CompressionRatio(self) -> float:
         return self.dimension * 4 / self.numSubvectors
+
+
+class OptimizedProductQuantizer:
+    """quantization.OptimizedProductQuantizer (opq.go): block-diagonal rotation + ProductQuantizer."""
+
+    def __init__(self, dimension: int, numSubvectors: int, numCentroids: int, numIterations: int):
+        self.pq = ProductQuantizer(dimension, numSubvectors, numCentroids)
+        bs = C.c_int64()
+        L.call("vg_opq_block_size", dimension, numSubvectors, C.byref(bs))
+        self.blockSize = int(bs.value)
+        self.numIterations = numIterations
+        nb = dimension // self.blockSize
+        self.rotations = np.tile(np.eye(self.blockSize, dtype=F), (nb, 1, 1))
+        self.trained = False
+
+    def Train(self, vectors, pq_iters: int = 20, seed: int = 0):
+        """opq.go:89-193: numIterations rounds of rotate -> pq.Train -> Procrustes."""
+        v = L.as_f32(vectors)
+        if v.size == 0:
+            raise QuantizerError("no vectors provided for training")
+        if v.ndim != 2 or v.shape[1] != self.pq.dimension:
+            raise QuantizerError("vector dimension mismatch")
+        rot = np.ascontiguousarray(self.rotations, F)
+        p = self.pq
+        L.call("vg_opq_train", L.ptr(v, L.f32p), v.shape[0], p.dimension, p.numSubvectors, p.numCentroids, self.numIterations, pq_iters,
+               seed, L.ptr(rot, L.f32p), L.ptr(p.codebooks, L.i8p), L.ptr(p.scales, L.f32p), L.ptr(p.offsets, L.f32p))
+        self.rotations = rot
+        p.trained = self.numIterations > 0
+        self.trained = True
+
+    def _check(self):
+        if not self.trained:
+            raise QuantizerError("OptimizedProductQuantizer not trained")
+
+    def RotateBatch(self, vectors, inverse: bool = False) -> np.ndarray:
+        v = L.as_f32(vectors).reshape(-1, self.pq.dimension)
+        out = np.zeros_like(v)
+        rot = np.ascontiguousarray(self.rotations, F)
+        L.call("vg_opq_rotate", L.ptr(v, L.f32p), v.shape[0], self.pq.dimension, self.blockSize, L.ptr(rot, L.f32p), int(inverse),
+               L.ptr(out, L.f32p))
+        return out
+
+    def EncodeBatch(self, vectors) -> np.ndarray:
+        self._check()
+        return self.pq.EncodeBatch(self.RotateBatch(vectors))
+
+    def Encode(self, vec):
+        return self.EncodeBatch(np.asarray(vec, F)[None, :])[0]
+
+    def DecodeBatch(self, codes) -> np.ndarray:
+        self._check()
+        return self.RotateBatch(self.pq.DecodeBatch(codes), inverse=True)
+
+    def Decode(self, codes):
+        return self.DecodeBatch(np.asarray(codes, np.uint8)[None, :])[0]
+
+    def ComputeAsymmetricDistance(self, query, codes) -> np.float32:
+        """opq.go:265-282: rotate the query once, then the PQ asymmetric distance."""
+        self._check()
+        rq = self.RotateBatch(np.asarray(query, F)[None, :])[0]
+        return self.pq.ComputeAsymmetricDistance(rq, codes)
+
+    def BytesPerVector(self) -> int:
+        return self.pq.BytesPerVector()
+
+    def CompressionRatio(self) -> float:
+        return self.pq.CompressionRatio()
+
+    def IsTrained(self):
+        return self.trained
