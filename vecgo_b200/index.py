@@ -98,6 +98,10 @@ class DeviceIndex:
                    d_mask: int = 0):
         L.call("vg_index_search_dev", self.handle, d_queries, nq, k, nprobes, d_mask or None, d_rows, d_scores, d_counts)
 
+    def rerank_dev(self, d_queries: int, nq: int, d_rows: int, r: int, d_scores: int):
+        """Device-resident Segment.Rerank: d_rows [nq, r] LOCAL row ids (0xFFFFFFFF / out of range -> NaN score)."""
+        L.call("vg_index_rerank_dev", self.handle, d_queries, nq, d_rows, r, d_scores)
+
     def rerank(self, queries, rows):
         """Batched Segment.Rerank: exact scores for rows[q, j] (local row ids)."""
         q = L.as_f32(queries).reshape(-1, self.dim)

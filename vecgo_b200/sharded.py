@@ -40,13 +40,76 @@ def exchange_topk(rows, scores, group=None):
     return all_rows.view(world, nq, k), all_scores.view(world, nq, k)
 
 
+EMPTY_ROW = 0xFFFFFFFF
+
+
+def owned_local_rows(rows_global, row_base: int, nrows: int):
+    """Split a [nq, r] tensor of GLOBAL row ids (uint32 bit patterns in int32) into this shard's view:
+    returns (local ids with 0xFFFFFFFF where the row lives on another shard, owned mask)."""
+    import torch
+
+    g = rows_global.to(torch.int64) & 0xFFFFFFFF
+    local = g - int(row_base)
+    owned = (local >= 0) & (local < int(nrows)) & (g != EMPTY_ROW)
+    local = torch.where(owned, local, torch.full_like(local, EMPTY_ROW))
+    return _as_u32_bits(local), owned
+
+
+def _as_u32_bits(t):
+    """int64 values in [0, 2^32) -> int32 tensor holding the same uint32 bit patterns."""
+    import torch
+
+    return torch.where(t >= 2 ** 31, t - 2 ** 32, t).to(torch.int32)
+
+
 class ShardedIndex:
     """A DeviceIndex holding this rank's row shard + the cross-GPU merge."""
 
-    def __init__(self, index, descending: bool, group=None):
+    def __init__(self, index, descending: bool, group=None, approx_descending: bool = False, merge=None):
         self.index = index
-        self.descending = descending
+        self.descending = descending              # order of the segment metric (exact scores)
+        self.approx_descending = approx_descending  # order of the codec's approximate scores (distances: ascending)
         self.group = group
+        self._merge_fn = merge                    # test hook; default = vg_topk_merge_dev
+
+    def _merge(self, all_rows, all_scores, k_in: int, k_out: int, descending: bool):
+        import torch
+
+        from . import _lib as L
+
+        if self._merge_fn is not None:
+            return self._merge_fn(all_rows, all_scores, k_in, k_out, descending)
+        world, nq = all_rows.shape[0], all_rows.shape[1]
+        dev = all_rows.device
+        orow = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+        osc = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+        ocnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        L.call("vg_topk_merge_dev", all_rows.contiguous().data_ptr(), all_scores.contiguous().data_ptr(), world, nq, k_in,
+               int(descending), k_out, orow.data_ptr(), osc.data_ptr(), ocnt.data_ptr())
+        return orow, osc, ocnt
+
+    def search_rerank_dev(self, d_queries, nq: int, r: int, k: int):
+        """Quantized scan + exact rerank across shards with the reference's semantics (engine/search.go:188-192,
+        913-973): the GLOBAL approximate top-r is reranked, not each shard's own top-r, so the ids are identical
+        for every world size.  Two exchanges: (1) all-gather the per-shard approximate top-r and merge to the global
+        top-r on every rank; (2) every rank scores exactly the rows it owns (Segment.Rerank), all-gather the exact
+        (score, row) pairs and merge to the final top-k."""
+        import torch
+
+        dev = d_queries.device
+        rows = torch.empty((nq, r), dtype=torch.int32, device=dev)
+        scores = torch.empty((nq, r), dtype=torch.float32, device=dev)
+        counts = torch.empty((nq,), dtype=torch.int32, device=dev)
+        self.index.search_dev(d_queries.data_ptr(), nq, r, rows.data_ptr(), scores.data_ptr(), counts.data_ptr())
+        all_rows, all_scores = exchange_topk(rows, scores, self.group)
+        if all_rows.shape[0] > 1:
+            rows, scores, counts = self._merge(all_rows, all_scores, r, r, self.approx_descending)
+        local, owned = owned_local_rows(rows, self.index.row_base, self.index.rows)
+        exact = torch.empty((nq, r), dtype=torch.float32, device=dev)
+        self.index.rerank_dev(d_queries.data_ptr(), nq, local.contiguous().data_ptr(), r, exact.data_ptr())
+        mine = torch.where(owned, rows, torch.full_like(rows, -1))  # -1 = 0xFFFFFFFF: not scored here
+        all_rows, all_exact = exchange_topk(mine, exact, self.group)
+        return self._merge(all_rows, all_exact, r, k, self.descending)
 
     def search_dev(self, d_queries, nq: int, k: int):
         """d_queries: CUDA float32 tensor [nq, dim] (replicated on every rank).
