@@ -1,0 +1,195 @@
+"""Device-resident throughput of every BASELINE.json config shape on ONE GPU (per-GPU shard sizes for the sharded
+configs), against the measured roofline.  One JSON line per config.  Not the driver's bench (bench.py is); its output
+is committed under profiles/ as the per-config evidence SURVEY.md §8(d) asks for.
+
+    python tools/bench_configs.py [c1 c1big c2a c2b c3 c4 c5] [--small]
+"""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import vecgo_b200 as vg
+
+L = vg._lib
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SMALL = "--small" in sys.argv
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), float(j["bf16_tflops"]), "measured"
+    return 6650.0, 1590.0, "fallback"
+
+
+HBM, TF, SRC = peaks()
+
+
+def timed(fn, warm=2, reps=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return float(np.median(ts))
+
+
+def out_bufs(nq, k, dev):
+    return (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
+            torch.empty((nq,), dtype=torch.int32, device=dev))
+
+
+def emit(name, workload, ms, nq, pairs, bytes_per_pair=None, flops=None, extra=None):
+    line = {"config": name, "workload": workload, "ms": ms, "qps": nq / ms * 1e3 if nq else None, "gpairs_per_s": pairs / ms / 1e6}
+    if bytes_per_pair is not None:
+        ach = pairs * bytes_per_pair / ms / 1e6
+        line["roofline"] = {"bound": "hbm", "achieved_gbs": ach, "peak_gbs": HBM, "frac": ach / HBM, "peak_source": SRC}
+    if flops is not None:
+        ach = flops / ms / 1e9
+        line["roofline"] = {"bound": "tensor", "achieved_tflops": ach, "peak_tflops_bf16": TF, "frac": ach / TF, "peak_source": SRC,
+                            "note": "useful FLOPs 2*Q*N*d; the filter runs the GEMM twice in TF32 (nominal dense TF32 peak is half of bf16)"}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def flat(name, n, dim, nq, k):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(42)
+    x = torch.rand((n, dim), dtype=torch.float32, device=dev, generator=g)
+    q = torch.rand((nq, dim), dtype=torch.float32, device=dev, generator=torch.Generator(device=dev).manual_seed(43))
+    ix = vg.index.DeviceIndex(codec=L.CODEC_F32, metric=0, dim=dim, rows=n)
+    ix.upload_dev(n, d_vectors=x.data_ptr())
+    r, s, c = out_bufs(nq, k, dev)
+    L.call("vg_flat_tc_enable", 1)
+    qa, fb = C.c_uint64(), C.c_uint64()
+    L.call("vg_flat_tc_stats", C.byref(qa), C.byref(fb))
+    f0 = fb.value
+    ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()))
+    L.call("vg_flat_tc_stats", C.byref(qa), C.byref(fb))
+    r1, s1 = r.clone(), s.clone()
+    L.call("vg_flat_tc_enable", 0)
+    ms0 = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=1)
+    L.call("vg_flat_tc_enable", 1)
+    same = bool(torch.equal(r1, r) and torch.equal(s1.view(torch.int32), s.view(torch.int32)))
+    emit(name, f"Flat exact L2, {n} x {dim} f32 U[0,1), {nq} queries, k={k} (tcgen05 TF32 filter + exact re-check)", ms, nq, n * nq,
+         flops=2.0 * n * nq * dim,
+         extra={"exact_cuda_core_scan_ms": ms0, "identical_to_exact_scan": same, "certificate_fallback_queries": fb.value - f0})
+    ix.close()
+
+
+def sq(name, codec, n, dim, nq, k):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(42)
+    cb = dim if codec == "sq8" else dim // 2
+    ix = (vg.index.DeviceIndex(codec=L.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(np.full(dim, -4, np.float32), np.full(dim, 8 / 255, np.float32)))
+          if codec == "sq8" else
+          vg.index.DeviceIndex(codec=L.CODEC_INT4, metric=0, dim=dim, rows=n, int4=(np.full(dim, -4, np.float32), np.full(dim, 8, np.float32))))
+    chunk = 1 << 20
+    for r0 in range(0, n, chunk):
+        m = min(chunk, n - r0)
+        codes = torch.randint(0, 256, (m, cb), dtype=torch.uint8, device=dev, generator=g)
+        ix.upload_dev(m, d_codes=codes.data_ptr(), row0=r0)
+    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
+    r, s, c = out_bufs(nq, k, dev)
+    ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
+    emit(name, f"{codec.upper()} decode-and-scan, {n} x {dim}, {nq} queries, k={k} (uniform random codes)", ms, nq, n * nq, bytes_per_pair=cb)
+    ix.close()
+
+
+def pq(name, n, dim, m, nq, k):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(42)
+    rng = np.random.default_rng(0)
+    ix = vg.index.DeviceIndex(codec=L.CODEC_PQ, metric=0, dim=dim, rows=n,
+                              pq=(rng.integers(-128, 128, m * 256 * (dim // m), dtype=np.int8), np.full(m, 0.01, np.float32),
+                                  np.zeros(m, np.float32), m, 256))
+    chunk = 1 << 22
+    for r0 in range(0, n, chunk):
+        mm = min(chunk, n - r0)
+        codes = torch.randint(0, 256, (mm, m), dtype=torch.uint8, device=dev, generator=g)
+        ix.upload_dev(mm, d_codes=codes.data_ptr(), row0=r0)
+    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
+    r, s, c = out_bufs(nq, k, dev)
+    ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
+    emit(name, f"PQ M={m} x 256 ADC scan, {n} rows ({dim}-d), {nq} queries, k={k} (per-GPU shard of the 8-GPU config)", ms, nq, n * nq,
+         bytes_per_pair=m, extra={"binding_limit": "shared-memory table lookups (random 8-byte LDS, ~5.9 wavefronts per warp lookup)"})
+    ix.close()
+
+
+def rabitq(name, n, dim, nq, r_top, k):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(42)
+    ix = vg.index.DeviceIndex(codec=L.CODEC_RABITQ, metric=0, dim=dim, rows=n)
+    chunk = 1 << 18
+    code_bytes = dim // 8 + 4
+    codes = torch.empty((chunk, code_bytes), dtype=torch.uint8, device=dev)
+    t0 = time.time()
+    for r0 in range(0, n, chunk):
+        mm = min(chunk, n - r0)
+        x = torch.randn((mm, dim), dtype=torch.float32, device=dev, generator=g)
+        L.call("vg_rabitq_encode_dev", x.data_ptr(), mm, dim, codes.data_ptr())
+        ix.upload_dev(mm, d_codes=codes.data_ptr(), d_vectors=x.data_ptr(), row0=r0)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t0
+    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
+    sh = vg.sharded.ShardedIndex(ix, descending=False)
+    rr, ss, cc = out_bufs(nq, r_top, dev)
+    ms_scan = timed(lambda: ix.search_dev(q.data_ptr(), nq, r_top, rr.data_ptr(), ss.data_ptr(), cc.data_ptr()), warm=1, reps=2)
+    ms = timed(lambda: sh.search_rerank_dev(q, nq, r_top, k), warm=1, reps=2)
+    emit(name, f"RaBitQ 1-bit scan + float32 rerank of top-{r_top}, {n} x {dim}, {nq} queries, final k={k} (per-GPU shard)", ms, nq, n * nq,
+         bytes_per_pair=code_bytes, extra={"scan_only_ms": ms_scan, "rerank_and_merge_ms": ms - ms_scan, "generate_encode_upload_s": gen_s})
+    ix.close()
+
+
+def pqtrain(name, n, dim, m, iters):
+    rng = np.random.default_rng(42)
+    x = rng.standard_normal((n, dim), dtype=np.float32)
+    pq_ = vg.quantization.ProductQuantizer(dim, m, 256)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    pq_.Train(x, iters=iters, seed=1)
+    torch.cuda.synchronize()
+    s = time.time() - t0
+    print(json.dumps({"config": name, "workload": f"PQ codebook training (k-means++ init + {iters} Lloyd iterations), {n} x {dim}, {m} subspaces x 256 "
+                      "centroids, host vectors (includes the H2D copy of the training set)", "seconds": s, "samples_per_s": n * iters / s,
+                      "note": "order-exact path: sequential-FMA distances, strict-< first-wins argmin, sample-order float32 centroid sums"}), flush=True)
+
+
+def main():
+    which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["c1", "c1big", "c2a", "c2b", "c3", "c4", "c5"]
+    L.call("vg_init", 0)
+    L.call("vg_set_stream", torch.cuda.current_stream().cuda_stream)
+    for w in which:
+        if w == "c1":
+            flat("C1", 100_000, 128, 1000, 10)
+        elif w == "c1big":
+            flat("C1-scaled", 2_000_000 if SMALL else 10_000_000, 128, 1000 if SMALL else 4096, 10)
+            flat("C1-768d", 1_000_000, 768, 2048, 10)
+        elif w == "c2a":
+            sq("C2a", "sq8", 1_000_000 if SMALL else 10_000_000, 768, 2048 if SMALL else 10_000, 100)
+        elif w == "c2b":
+            sq("C2b", "int4", 1_000_000 if SMALL else 10_000_000, 768, 2048 if SMALL else 10_000, 100)
+        elif w == "c3":
+            pq("C3", 4_000_000 if SMALL else 25_000_000, 768, 96, 592 if SMALL else 2072, 100)
+        elif w == "c4":
+            rabitq("C4", 2_000_000 if SMALL else 12_500_000, 1536, 512 if SMALL else 1000, 1000, 100)
+        elif w == "c5":
+            pqtrain("C5", 100_000 if SMALL else 1_000_000, 768, 96, 25)
+
+
+if __name__ == "__main__":
+    main()

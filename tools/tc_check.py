@@ -33,16 +33,16 @@ def main():
     kc = 32 if k <= 16 else 2 * k
     if dim > 256:
         kc = max(kc, 64)
-    CAP = 128
-    rows = np.zeros((nq, CAP), np.uint32)
-    s = np.zeros((nq, CAP), np.float32)
+    gids = np.zeros((nq, kc), np.uint32)
     cnt = np.zeros(nq, np.int32)
     tau = np.zeros(nq, np.float32)
+    G = C.c_int64()
     t0 = time.time()
-    L.call("vg_flat_tc_candidates", ix.handle, L.ptr(q, L.f32p), nq, kc, L.ptr(rows, L.u32p), L.ptr(s, L.f32p), L.ptr(cnt, L.i32p),
-           L.ptr(tau, L.f32p))
-    print(f"candidates call: {time.time() - t0:.3f}s  survivors per query min/mean/max {cnt.min()}/{cnt.mean():.1f}/{cnt.max()} (kc={kc})", flush=True)
-    # exact s in float64
+    L.call("vg_flat_tc_candidates", ix.handle, L.ptr(q, L.f32p), nq, kc, L.ptr(gids, L.u32p), L.ptr(cnt, L.i32p), L.ptr(tau, L.f32p),
+           C.byref(G))
+    G = int(G.value)
+    print(f"filter call: {time.time() - t0:.3f}s  groups of {G} rows, {-(-n // G)} groups, kc={kc}, listed min/max {cnt.min()}/{cnt.max()}", flush=True)
+    # exact s in float64: group minima vs tau and the error bound
     x64, q64 = x.astype(np.float64), q.astype(np.float64)
     nchk = min(nq, 64)
     dots = q64[:nchk] @ x64.T
@@ -50,18 +50,19 @@ def main():
     qn, xn = np.sum(q64 * q64, 1), np.sum(x64 * x64, 1)
     c1 = (1 / 512 if metric != 0 else 1 / 256) * 1.125
     E = c1 * np.sqrt(qn[:nchk] * xn.max()) + (qn[:nchk] + xn.max()) / 16384
-    worst = 0.0
-    inside = 0.0
+    ng = -(-n // G)
+    pad = ng * G - n
     true_top = np.argsort(s_true, axis=1, kind="stable")[:, :k]
+    inside, worst = 0.0, 0.0
     for i in range(nchk):
-        c = min(int(cnt[i]), CAP)
-        err = np.abs(s_true[i, rows[i, :c].astype(np.int64)] - s[i, :c])
-        worst = max(worst, float(err.max() / E[i]))
-        inside += len(set(true_top[i]) & set(rows[i, :c].tolist())) / k
-        # the list must be exactly the rows with approximate s <= tau: check with the true s and the error bound
-        must = np.where(s_true[i] <= tau[i] - E[i])[0]
-        assert set(must.tolist()) <= set(rows[i, :c].tolist()), "a row far below tau is missing from the candidate list"
-    print(f"max err/E = {worst:.4f}; true top-{k} contained in candidates: {inside / nchk:.4f}")
+        gm = np.pad(s_true[i], (0, pad), constant_values=np.inf).reshape(ng, G).min(1)   # true group minima
+        sel = gids[i, : cnt[i]].astype(np.int64)
+        # every group whose true minimum is below tau - E must be selected; no selected group may be above tau + E
+        assert set(np.where(gm <= tau[i] - E[i])[0].tolist()) <= set(sel.tolist()), "a group far below tau was not selected"
+        assert np.all(gm[sel] <= tau[i] + E[i]), "a selected group is far above tau"
+        worst = max(worst, float(np.abs(np.sort(gm)[kc - 1] - tau[i]) / E[i]))
+        inside += len(set((true_top[i] // G).tolist()) - set(sel.tolist())) == 0
+    print(f"|tau - true kc-th group minimum| / E max = {worst:.4f}; true top-{k} rows inside the selected groups: {inside / nchk:.4f}")
     # end-to-end identity with the exact scan
     qa, fb = C.c_uint64(), C.c_uint64()
     L.call("vg_flat_tc_enable", 1)

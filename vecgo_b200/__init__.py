@@ -11,7 +11,7 @@ modules here mirror the Go packages it plugs into:
     sharded       row sharding across GPUs + NCCL all-gather merge
 """
 from . import _lib  # noqa: F401  (fails loudly when the CUDA library is missing)
-from . import distance, flat, index, kmeans, quantization, simd  # noqa: F401
+from . import distance, flat, index, kmeans, quantization, sharded, simd  # noqa: F401
 from ._lib import VecgoError, launch_count  # noqa: F401
 
 __all__ = ["simd", "distance", "quantization", "kmeans", "index", "flat", "VecgoError", "launch_count"]

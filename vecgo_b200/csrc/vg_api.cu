@@ -531,14 +531,14 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     f.kc = tc::candidates_for(k, d.dim);
     f.is_dot = is_dot;
     f.row_base = (uint32_t)d.row_base;
-    DevBuf cand, ccnt, tau, qn, failb;
-    VG_TRY(cand.alloc((size_t)nq * tc::CAP * 8));
-    VG_TRY(ccnt.alloc((size_t)nq * 4));
-    VG_TRY(tau.alloc((size_t)((nq + 255) / 256 * 256) * 4));
+    DevBuf gids, gcnt, tau, qn, failb;
+    VG_TRY(gids.alloc((size_t)nq * f.kc * 4));
+    VG_TRY(gcnt.alloc((size_t)nq * 4));
+    VG_TRY(tau.alloc((size_t)nq * 4));
     VG_TRY(qn.alloc((size_t)nq * 4));
     VG_TRY(failb.alloc((size_t)nq * 4));
-    f.d_cand = cand.as<unsigned long long>();
-    f.d_cand_cnt = ccnt.as<int32_t>();
+    f.d_gids = gids.as<uint32_t>();
+    f.d_gcnt = gcnt.as<int32_t>();
     f.d_tau = tau.as<float>();
     VG_TRY(tc::sqnorms(d_queries, nq, d.dim, qn.as<float>(), nullptr, st));
     VG_TRY(tc::filter(f, st));
@@ -678,8 +678,8 @@ vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
     if (fallbacks) *fallbacks = g_tc_fallbacks.load();
     return VG_OK;
 }
-vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_rows, float *h_s,
-                                int32_t *h_counts, float *h_tau) {
+vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_groups, int32_t *h_counts,
+                                float *h_tau, int64_t *group_rows) {
     VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
@@ -688,11 +688,11 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
     if (!tc::supported(ix->d.dim, ix->d.rows, nq, 1)) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
     cudaStream_t st = stream();
     VG_TRY(ensure_row_norms(ix, st));
-    DevBuf q, cand, ccnt, tau;
+    DevBuf q, gids, gcnt, tau;
     VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
-    VG_TRY(cand.alloc((size_t)nq * tc::CAP * 8));
-    VG_TRY(ccnt.alloc((size_t)nq * 4));
-    VG_TRY(tau.alloc((size_t)((nq + 255) / 256 * 256) * 4));
+    VG_TRY(gids.alloc((size_t)nq * kc * 4));
+    VG_TRY(gcnt.alloc((size_t)nq * 4));
+    VG_TRY(tau.alloc((size_t)nq * 4));
     tc::FilterArgs f;
     f.d_queries = q.as<float>();
     f.d_vectors = ix->vectors.as<float>();
@@ -703,26 +703,15 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
     f.kc = (int)kc;
     f.is_dot = ix->d.metric != VG_METRIC_L2;
     f.row_base = (uint32_t)ix->d.row_base;
-    f.d_cand = cand.as<unsigned long long>();
-    f.d_cand_cnt = ccnt.as<int32_t>();
+    f.d_gids = gids.as<uint32_t>();
+    f.d_gcnt = gcnt.as<int32_t>();
     f.d_tau = tau.as<float>();
     VG_TRY(tc::filter(f, st));
     VG_CUDA(cudaStreamSynchronize(st));
-    std::vector<unsigned long long> keys((size_t)nq * tc::CAP);
-    VG_TRY(staged_d2h(keys.data(), cand.p, keys.size() * 8));
-    VG_TRY(staged_d2h(h_counts, ccnt.p, (size_t)nq * 4));
+    VG_TRY(staged_d2h(h_groups, gids.p, (size_t)nq * kc * 4));
+    VG_TRY(staged_d2h(h_counts, gcnt.p, (size_t)nq * 4));
     VG_TRY(staged_d2h(h_tau, tau.p, (size_t)nq * 4));
-    for (int64_t i = 0; i < nq; i++)
-        for (int j = 0; j < tc::CAP; j++) {
-            const bool live = j < h_counts[i];
-            const unsigned long long key = keys[(size_t)i * tc::CAP + j];
-            const uint32_t o = (uint32_t)(key >> 32);
-            const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
-            float sc;
-            memcpy(&sc, &u, 4);
-            h_rows[i * tc::CAP + j] = live ? (uint32_t)key : 0xFFFFFFFFu;
-            h_s[i * tc::CAP + j] = live ? sc : 0.0f;
-        }
+    if (group_rows) *group_rows = tc::group_rows(ix->d.rows, (int)kc);
     return VG_OK;
 }
 

@@ -13,20 +13,20 @@
 //   s(q,x) = ||x||^2 - 2 q.x   (L2; the per-query constant ||q||^2 is dropped)
 //   s(q,x) = -q.x              (dot / cosine, descending in the reference)
 //
-// Two GEMM passes, both with branch-free epilogues (no per-query heap inside the GEMM):
-//   pass 1  every thread (= one query) keeps the minimum of s over groups of G consecutive
-//           rows and writes one float per group.  The kc-th smallest group minimum tau(q) is
-//           an upper bound of the kc-th smallest s overall (kc groups each contain a row at
-//           or below it), and it is nearly tight when there are many more groups than kc.
-//   select  tau(q) per query (thread-private max-heap over the group minima).
-//   pass 2  the same GEMM again; rows with s <= tau(q) are appended to the query's candidate
-//           list (a global atomic per survivor — about kc of them per query in total).
+// One GEMM pass with a branch-free epilogue (no per-query heap inside the GEMM), then a small exact scan:
+//   gemm    every thread (= one query) keeps the minimum of s over groups of G consecutive rows and
+//           writes one float per group (FFMA + FMNMX per accumulator element).
+//   select  tau(q) = the kc-th smallest group minimum and the kc groups that reach it.  kc groups
+//           with a row at or below tau exist, so at least kc rows have s <= tau; with many more
+//           groups than kc the bound is nearly tight.
+//   scan    the rows of those kc groups (kc x G rows per query, contiguous) are scored EXACTLY in
+//           simd.SquaredL2 / simd.Dot order and the heap order (score, row) keeps the best k.
 //
-// Certificate (per query).  The candidate list holds EVERY row with s_approx <= tau.  With
-// E >= |s_exact - s_approx| for every row (bound below) any other row has s_exact > tau - E.
-// If the exact k-th best candidate satisfies s_exact(e_k) < tau - E, no outside row can tie
-// or beat it: the exact top-k of the candidates IS the exact top-k of the segment (ties by
-// row id included).
+// Certificate (per query).  Every row OUTSIDE the scanned groups has s_approx > = tau (its group
+// minimum is not among the kc smallest).  With E >= |s_exact - s_approx| for every row (bound
+// below) such a row has s_exact >= tau - E.  If the exact k-th best scanned row satisfies
+// s_exact(e_k) < tau - E, no outside row can tie or beat it: the exact top-k of the scanned rows IS
+// the exact top-k of the segment (ties by row id included).
 //
 // Error bound.  kind::tf32 keeps 10 explicit mantissa bits of each fp32 operand:
 // |fl_tf32(a) - a| <= 2^-10 |a|, so |q.x - (q.x)_tc| <= (2^-9 + 2^-20) sum|q_i x_i|
@@ -42,7 +42,7 @@
 //   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 x N=128 x K=8, two M halves
 //              per B tile, fp32 accumulators in TMEM (2 stages x 2 halves x 128 columns = 512)
 //   warps 2-9  epilogue: one thread = one query (= one TMEM lane); tcgen05.ld 32 columns at a
-//              time, 32 independent FFMA, then FMNMX tree (pass 1) or compare-to-mask (pass 2).
+//              time, 32 independent FFMA, FMNMX tree, one store per group.
 #include <cuda.h>
 
 #include <algorithm>
@@ -128,46 +128,6 @@ __host__ __device__ constexpr uint32_t make_idesc(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
-// ---- 128-key bitonic sort held in registers by one warp: element e = 4*lane + r.
-__device__ __forceinline__ void cswap(unsigned long long &a, unsigned long long &b, bool up) {
-    const bool sw = (a > b) == up;
-    const unsigned long long x = sw ? b : a, y = sw ? a : b;
-    a = x;
-    b = y;
-}
-__device__ __forceinline__ unsigned long long shfl_xor64(unsigned long long v, int m) {
-    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m), hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
-    return ((unsigned long long)hi << 32) | lo;
-}
-__device__ __forceinline__ void warp_sort128(unsigned long long (&k)[4], int lane) {
-#pragma unroll
-    for (int size = 2; size <= 128; size <<= 1) {
-#pragma unroll
-        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
-            if (stride >= 4) {
-                const int lm = stride >> 2;
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int e = lane * 4 + r;
-                    const bool up = (e & size) == 0;
-                    const bool lower = (e & stride) == 0;
-                    const unsigned long long o = shfl_xor64(k[r], lm);
-                    const bool take_min = lower == up;
-                    k[r] = take_min ? (k[r] < o ? k[r] : o) : (k[r] > o ? k[r] : o);
-                }
-            } else if (stride == 2) {
-                const bool up = ((lane * 4) & size) == 0;
-                cswap(k[0], k[2], up);
-                cswap(k[1], k[3], up);
-            } else {
-                const bool up0 = ((lane * 4) & size) == 0, up2 = ((lane * 4 + 2) & size) == 0;
-                cswap(k[0], k[1], up0);
-                cswap(k[2], k[3], up2);
-            }
-        }
-    }
-}
-
 // ------------------------------------------------------------------ kernel
 constexpr int BN = 128;        // database rows per tile (UMMA N)
 constexpr int STAGES = 4;
@@ -180,13 +140,10 @@ struct Args {
     const uint32_t *mask;   // optional row bitmap, read as 32-bit words (bit = 1 keeps the row)
     int64_t nq, nq_pad, rows, rows_per_split;
     int kb;                 // k-blocks = ceil(dim / 32)
-    int cpg;                // pass 1: 32-row chunks per minimum group (G / 32)
+    int cpg;                // 32-row chunks per minimum group (G / 32)
     uint32_t row_base;
-    float *mins;            // pass 1 out: [nq_pad][groups]
+    float *mins;            // out: [nq_pad][groups]
     int64_t groups;
-    const float *tau;       // pass 2 in:  [nq_pad]
-    unsigned long long *cand;  // pass 2 out: [nq][CAP] keys (unsorted)
-    int32_t *cand_cnt;         // pass 2 out: [nq] number of survivors (may exceed CAP = overflow)
 };
 
 template <bool RESIDENT>
@@ -199,22 +156,8 @@ struct Smem {
     static constexpr size_t TOTAL = OFF_BAR + (size_t)(2 * STAGES + 5) * 8 + 16;
 };
 
-// value of s[j] for a warp-uniform j (jump table; keeps s[] in registers)
-__device__ __forceinline__ float pick32(const float (&s)[32], int j) {
-    float r = 0.0f;
-    switch (j) {
-#define VG_CASE(i) case i: r = s[i]; break;
-        VG_CASE(0) VG_CASE(1) VG_CASE(2) VG_CASE(3) VG_CASE(4) VG_CASE(5) VG_CASE(6) VG_CASE(7)
-        VG_CASE(8) VG_CASE(9) VG_CASE(10) VG_CASE(11) VG_CASE(12) VG_CASE(13) VG_CASE(14) VG_CASE(15)
-        VG_CASE(16) VG_CASE(17) VG_CASE(18) VG_CASE(19) VG_CASE(20) VG_CASE(21) VG_CASE(22) VG_CASE(23)
-        VG_CASE(24) VG_CASE(25) VG_CASE(26) VG_CASE(27) VG_CASE(28) VG_CASE(29) VG_CASE(30) VG_CASE(31)
-#undef VG_CASE
-    }
-    return r;
-}
-
-// PASS 1: group minima.  PASS 2: collect rows with s <= tau(q).
-template <bool RESIDENT, bool IS_DOT, int PASS>
+// GEMM + group minima.
+template <bool RESIDENT, bool IS_DOT>
 __global__ void __launch_bounds__(NTHREADS, 1)
 flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, Args A) {
     using S = Smem<RESIDENT>;
@@ -333,10 +276,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int64_t q = (int64_t)q0 + slot;
         float *xs = reinterpret_cast<float *>(smem + S::OFF_XN);
         const float INF = __int_as_float(0x7f800000);
-        const bool q_live = q < A.nq;
-        float tau_f = -INF;                   // pass 2 threshold; dead query rows accept nothing
-        if (PASS == 2 && q_live) tau_f = A.tau[q];
-        float gmin = INF;                     // pass 1 running minimum of the current group
+        float gmin = INF;                     // running minimum of the current group
         int cc = 0;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
@@ -375,7 +315,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : INF;
                 }
-                if (PASS == 1) {
+                {
                     float m8[8];
 #pragma unroll
                     for (int j = 0; j < 8; j++) m8[j] = fminf(fminf(s[j], s[j + 8]), fminf(s[j + 16], s[j + 24]));
@@ -383,39 +323,19 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
                     gmin = fminf(gmin, cm);
                     if (++cc == A.cpg) {
                         const int64_t gid = (n0 + c * 32) / (32 * (int64_t)A.cpg);
-                        A.mins[q * A.groups + gid] = gmin;
+                        if (gid < A.groups) A.mins[q * A.groups + gid] = gmin;  // chunks past the last row belong to no group
                         gmin = INF;
                         cc = 0;
-                    }
-                } else {
-                    uint32_t m4[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                    for (int j = 0; j < 32; j++) m4[j & 3] |= (s[j] <= tau_f) ? (1u << j) : 0u;
-                    const uint32_t m = (m4[0] | m4[1]) | (m4[2] | m4[3]);
-                    uint32_t um = __reduce_or_sync(0xffffffffu, m);
-                    while (um) {  // rare: about kc survivors per query over the whole scan
-                        const int j = __ffs(um) - 1;
-                        um &= um - 1;
-                        const float sj = pick32(s, j);
-                        if ((m >> j) & 1u) {
-                            const int64_t row = n0 + c * 32 + j;
-                            if (row < row_end) {
-                                const int pos = atomicAdd(A.cand_cnt + q, 1);
-                                if (pos < CAP)
-                                    A.cand[(size_t)q * CAP + pos] =
-                                        ((unsigned long long)f32_orderable(sj) << 32) | (unsigned long long)(A.row_base + (uint32_t)row);
-                            }
-                        }
                     }
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(as));
         }
-        if (PASS == 1 && cc > 0 && ntiles > 0) {  // partial last group of this row range
+        if (cc > 0 && ntiles > 0) {  // partial last group of this row range
             const int64_t last_chunk_row = row_begin + (int64_t)ntiles * BN - 32;
             const int64_t gid = last_chunk_row / (32 * (int64_t)A.cpg);
-            A.mins[q * A.groups + gid] = gmin;
+            if (gid < A.groups) A.mins[q * A.groups + gid] = gmin;
         }
     }
     tc_fence_before();
@@ -426,22 +346,19 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
-// tau(q) = kc-th smallest group minimum of query q: one warp per query streams mins[q][*] (coalesced) through the
-// shared-memory bounded top-k (threshold filter + bitonic compaction).  +inf when there are fewer than kc groups.
-__global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64_t groups, int64_t nq, int64_t nq_pad, int kc, int C,
-                                                        float *tau) {
+// tau(q) = kc-th smallest group minimum of query q and the ids of the kc groups that reach it: one warp per query
+// streams mins[q][*] (coalesced) through the shared-memory bounded top-k (threshold filter + bitonic compaction).
+// tau = +inf when there are fewer than kc groups (then every group is listed and the scan covers the whole segment).
+__global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64_t groups, int64_t nq, int kc, int C, float *tau,
+                                                        uint32_t *gids, int32_t *gcnt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     TopK tk = topk_carve(smem, nw, C, kc);
     topk_init(tk, nw, threadIdx.x, blockDim.x);
     __syncthreads();
     const int64_t q = (int64_t)blockIdx.x * nw + warp;
-    if (q >= nq_pad) return;
+    if (q >= nq) return;
     const float INF = __int_as_float(0x7f800000);
-    if (q >= nq) {
-        if (lane == 0) tau[q] = -INF;
-        return;
-    }
     const float *src = mins + q * groups;
     const int trigger = C - 32;
     // 4 independent coalesced loads per lane per step (the loop is otherwise bound by L2 latency)
@@ -468,9 +385,117 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64
         }
     }
     topk_compact_warp(tk, warp, lane, true);
+    const int n = tk.cnt[warp];
+    const unsigned long long *a = tk.keys + (size_t)warp * C;
+    for (int i = lane; i < kc; i += 32) gids[q * kc + i] = i < n ? (uint32_t)a[i] : 0xFFFFFFFFu;
     if (lane == 0) {
-        const int n = tk.cnt[warp];
-        tau[q] = (n >= kc) ? f32_from_orderable((uint32_t)(tk.keys[(size_t)warp * C + kc - 1] >> 32)) : INF;
+        gcnt[q] = n;
+        tau[q] = (n >= kc) ? f32_from_orderable((uint32_t)(a[kc - 1] >> 32)) : INF;
+    }
+}
+
+// Exact scan of the selected groups: one CTA per query, half-warp per row in simd.SquaredL2 / simd.Dot order
+// (floats_avx512.c:12-129: 4 x 16-lane FMA accumulators, (A1+A2)+(A3+A4), lane tree, FMA scalar tail), bounded
+// top-k under the heap order (score, row), then the certificate in double precision.
+__global__ void __launch_bounds__(256) tc_group_scan_kernel(const float *vectors, int64_t dim, int64_t rows, const float *queries,
+                                                            const uint32_t *gids, const int32_t *gcnt, int kc, int64_t G,
+                                                            const float *tau, const float *qn, const unsigned int *xmax_bits,
+                                                            const uint8_t *mask, int k, int C, int is_dot, uint32_t row_base,
+                                                            uint32_t *out_rows, float *out_scores, int32_t *out_counts,
+                                                            int32_t *fail_flags) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
+    float *qs = reinterpret_cast<float *>(smem);
+    const size_t qbytes = ((size_t)dim * 4 + 15) & ~(size_t)15;
+    TopK tk = topk_carve(smem + qbytes, 1, C, k);
+    for (int64_t d = tid; d < dim; d += 256) qs[d] = queries[q * dim + d];
+    topk_init(tk, 1, tid, 256);
+    __syncthreads();
+    const int ng = gcnt[q];
+    const int64_t total = (int64_t)ng * G;
+    const int64_t epochs = dim >> 6;
+    constexpr int RH = 8;                 // rows per half-warp per step: 8 independent load streams hide the L2 latency
+    const int trigger = C - 16 * RH;
+    for (int64_t base = 0; base < total; base += 16 * RH) {
+        int64_t rowi[RH];
+        const float *x[RH];
+#pragma unroll
+        for (int u = 0; u < RH; u++) {
+            const int64_t r = base + hw * RH + u;
+            int64_t row = -1;
+            if (r < total) {
+                const uint32_t g = gids[q * kc + r / G];
+                row = (int64_t)g * G + r % G;
+                if (row >= rows) row = -1;
+                else if (mask && !((mask[row >> 3] >> (row & 7)) & 1)) row = -1;
+            }
+            rowi[u] = row;
+            x[u] = vectors + (row >= 0 ? row : 0) * dim;  // dead rows are computed (full-mask shuffles below) but not offered
+        }
+        float a[RH][4];
+#pragma unroll
+        for (int u = 0; u < RH; u++)
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) a[u][jj] = 0.0f;
+        for (int64_t e = 0; e < epochs; e++)
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const int64_t d = e * 64 + jj * 16 + lane;
+                const float qv = qs[d];
+                float xv[RH];
+#pragma unroll
+                for (int u = 0; u < RH; u++) xv[u] = __ldg(x[u] + d);
+#pragma unroll
+                for (int u = 0; u < RH; u++) {
+                    if (is_dot) {
+                        a[u][jj] = __fmaf_rn(qv, xv[u], a[u][jj]);
+                    } else {
+                        const float df = __fsub_rn(qv, xv[u]);
+                        a[u][jj] = __fmaf_rn(df, df, a[u][jj]);
+                    }
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < RH; u++) {
+            float tot = reduce16(__fadd_rn(__fadd_rn(a[u][0], a[u][1]), __fadd_rn(a[u][2], a[u][3])));
+            if (lane == 0 && rowi[u] >= 0) {
+                for (int64_t d = epochs * 64; d < dim; d++) {
+                    if (is_dot) {
+                        tot = __fmaf_rn(qs[d], __ldg(x[u] + d), tot);
+                    } else {
+                        const float df = __fsub_rn(qs[d], __ldg(x[u] + d));
+                        tot = __fmaf_rn(df, df, tot);
+                    }
+                }
+                topk_offer(tk, 0, make_key(tot, row_base + (uint32_t)rowi[u], is_dot != 0), trigger);
+            }
+        }
+        __syncthreads();
+        topk_block_maintain(tk, 1, tid, 256);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        topk_emit_warp(tk, 0, tid, is_dot != 0, out_rows + q * k, out_scores + q * k, out_counts + q, k);
+        __syncwarp();
+        if (tid == 0) {
+            const int m = tk.cnt[0];
+            int fail = 0;
+            const float t = tau[q];
+            if (t < __int_as_float(0x7f800000)) {  // finite threshold: rows outside the scanned groups exist
+                if (m < k) {
+                    fail = 1;
+                } else {
+                    const double qq = (double)qn[q], xx = (double)__uint_as_float(*xmax_bits);
+                    const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125, c2 = 1.0 / 16384.0;
+                    const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx);
+                    const double ex = (double)out_scores[q * k + (k - 1)];
+                    const double s_exact = is_dot ? -ex : ex - qq;
+                    if (!(s_exact < (double)t - E)) fail = 1;
+                }
+            }
+            fail_flags[q] = fail;
+        }
     }
 }
 
@@ -488,98 +513,6 @@ __global__ void __launch_bounds__(256) sqnorm_kernel(const float *v, int64_t n, 
     if (lane == 0 && live) {
         out[hw] = a;
         if (max_bits) atomicMax(max_bits, __float_as_uint(a));  // a >= 0: uint order = float order
-    }
-}
-
-// ------------------------------------------------------------------ finalize
-// One CTA per query: exact scores of the candidates in simd.SquaredL2 / simd.Dot order
-// (floats_avx512.c:12-129: 4 x 16-lane FMA accumulators, (A1+A2)+(A3+A4), lane tree, FMA
-// scalar tail), then the heap order (score, row) picks the top k and the certificate is
-// evaluated in double precision.
-__global__ void __launch_bounds__(128) flat_tc_finalize_kernel(const float *vectors, int64_t dim, const float *queries, int64_t nq,
-                                                               const unsigned long long *cand, const int32_t *cand_cnt, const float *tau,
-                                                               int k, int is_dot, uint32_t row_base, const float *qn,
-                                                               const unsigned int *xmax_bits, uint32_t *out_rows, float *out_scores,
-                                                               int32_t *out_counts, int32_t *fail_flags) {
-    __shared__ unsigned long long ek[CAP];
-    const int64_t q = blockIdx.x;
-    const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
-    const int n_all = cand_cnt[q];
-    const int n = n_all < CAP ? n_all : CAP;
-    const float *qv = queries + q * dim;
-    for (int j0 = 0; j0 < CAP; j0 += 8) {
-        const int j = j0 + hw;
-        const bool live = j < n;
-        const uint32_t row = live ? (uint32_t)__ldcg(cand + (size_t)q * CAP + j) : row_base;
-        const float *x = vectors + (int64_t)(row - row_base) * dim;
-        float tot = 0.0f;
-        if (j0 < n) {  // uniform per CTA
-            float a[4] = {0.f, 0.f, 0.f, 0.f};
-            const int64_t epochs = dim >> 6;
-            for (int64_t e = 0; e < epochs; e++)
-#pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    const int64_t d = e * 64 + jj * 16 + lane;
-                    if (is_dot) {
-                        a[jj] = __fmaf_rn(qv[d], __ldg(x + d), a[jj]);
-                    } else {
-                        const float df = __fsub_rn(qv[d], __ldg(x + d));
-                        a[jj] = __fmaf_rn(df, df, a[jj]);
-                    }
-                }
-            tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
-            if (lane == 0 && live) {
-                for (int64_t d = epochs * 64; d < dim; d++) {
-                    if (is_dot) {
-                        tot = __fmaf_rn(qv[d], __ldg(x + d), tot);
-                    } else {
-                        const float df = __fsub_rn(qv[d], __ldg(x + d));
-                        tot = __fmaf_rn(df, df, tot);
-                    }
-                }
-            }
-        }
-        if (lane == 0) ek[j] = live ? make_key(tot, row, is_dot != 0) : VG_KEY_EMPTY;
-    }
-    __syncthreads();
-    if (tid < 32) {
-        unsigned long long kk[4];
-#pragma unroll
-        for (int r = 0; r < 4; r++) kk[r] = ek[tid * 4 + r];
-        warp_sort128(kk, tid);
-#pragma unroll
-        for (int r = 0; r < 4; r++) ek[tid * 4 + r] = kk[r];
-        __syncwarp();
-        const int m = n < k ? n : k;
-        for (int i = tid; i < k; i += 32) {
-            if (i < m) {
-                out_rows[q * k + i] = key_row(ek[i]);
-                out_scores[q * k + i] = key_score(ek[i], is_dot != 0);
-            } else {
-                out_rows[q * k + i] = 0xFFFFFFFFu;
-                out_scores[q * k + i] = __uint_as_float(0x7fc00000u);
-            }
-        }
-        if (tid == 0) {
-            out_counts[q] = m;
-            int fail = 0;
-            const float t = tau[q];
-            if (n_all > CAP) {
-                fail = 1;  // survivors were dropped: the list is not the full set {s <= tau}
-            } else if (t < __int_as_float(0x7f800000)) {  // finite threshold: rows outside the list exist (or may exist)
-                if (m < k) {
-                    fail = 1;
-                } else {
-                    const double qq = (double)qn[q], xx = (double)__uint_as_float(*xmax_bits);
-                    const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125, c2 = 1.0 / 16384.0;
-                    const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx);
-                    const double ex = (double)key_score(ek[m - 1], is_dot != 0);
-                    const double s_exact = is_dot ? -ex : ex - qq;
-                    if (!(s_exact < (double)t - E)) fail = 1;
-                }
-            }
-            fail_flags[q] = fail;
-        }
     }
 }
 
@@ -628,21 +561,23 @@ vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsign
     return VG_OK;
 }
 
-template <bool RESIDENT, bool IS_DOT, int PASS>
+template <bool RESIDENT, bool IS_DOT>
 static vg_status launch(const CUtensorMap &mq, const CUtensorMap &mx, const Args &a, int64_t qtiles, int splits, cudaStream_t st) {
     using S = Smem<RESIDENT>;
     const size_t sm = S::TOTAL + 1024;  // slack for the 1024-byte alignment of the dynamic segment
-    VG_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RESIDENT, IS_DOT, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VG_CUDA(cudaFuncSetAttribute(flat_tc_kernel<RESIDENT, IS_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)qtiles, (unsigned)splits);
-    flat_tc_kernel<RESIDENT, IS_DOT, PASS><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
+    flat_tc_kernel<RESIDENT, IS_DOT><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
     VG_LAUNCHED();
     return VG_OK;
 }
-template <int PASS>
-static vg_status launch_pass(bool resident, bool is_dot, const CUtensorMap &mq, const CUtensorMap &mx, const Args &a, int64_t qtiles,
-                             int splits, cudaStream_t st) {
-    if (resident) return is_dot ? launch<true, true, PASS>(mq, mx, a, qtiles, splits, st) : launch<true, false, PASS>(mq, mx, a, qtiles, splits, st);
-    return is_dot ? launch<false, true, PASS>(mq, mx, a, qtiles, splits, st) : launch<false, false, PASS>(mq, mx, a, qtiles, splits, st);
+
+int64_t group_rows(int64_t rows, int kc) {
+    // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
+    // while the exact scan of kc*G rows per query stays ~1% of the GEMM's work
+    int64_t G = 32;
+    while (G < 8192 && rows / (G * 2) >= 128ll * kc) G *= 2;
+    return G;
 }
 
 vg_status filter(const FilterArgs &f, cudaStream_t st) {
@@ -652,9 +587,7 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
     VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, BN));
     const int64_t qtiles = (f.nq + BMQ - 1) / BMQ;
     const int64_t nq_pad = qtiles * BMQ;
-    // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
-    int64_t G = 32;
-    while (G < 8192 && f.rows / (G * 2) >= 128ll * f.kc) G *= 2;
+    const int64_t G = group_rows(f.rows, f.kc);
     const int64_t groups = (f.rows + G - 1) / G;
     const int64_t unit = std::max<int64_t>(BN, G);  // row ranges are whole tiles and whole groups
     // one CTA per SM (shared memory): pick the row-split count whose CTA total fills whole waves best
@@ -683,31 +616,37 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
     a.rows_per_split = rps;
     a.kb = (int)((f.dim + BK - 1) / BK);
     a.cpg = (int)(G / 32);
-    a.groups = groups;
     a.row_base = f.row_base;
-    DevBuf mins, tau;
+    a.groups = groups;
+    DevBuf mins;
     VG_TRY(mins.alloc((size_t)groups * nq_pad * 4));
     a.mins = mins.as<float>();
-    a.tau = f.d_tau;
-    a.cand = f.d_cand;
-    a.cand_cnt = f.d_cand_cnt;
     const bool resident = a.kb <= MAX_RES_KB;
-    VG_TRY(launch_pass<1>(resident, f.is_dot != 0, mq, mx, a, qtiles, (int)splits, st));
+    if (resident) {
+        if (f.is_dot) VG_TRY((launch<true, true>(mq, mx, a, qtiles, (int)splits, st)));
+        else VG_TRY((launch<true, false>(mq, mx, a, qtiles, (int)splits, st)));
+    } else {
+        if (f.is_dot) VG_TRY((launch<false, true>(mq, mx, a, qtiles, (int)splits, st)));
+        else VG_TRY((launch<false, false>(mq, mx, a, qtiles, (int)splits, st)));
+    }
     {
         const int C = topk_capacity(f.kc, 32), nw = 8;
         const size_t sm = topk_smem_bytes(nw, C);
-        tc_select_kernel<<<(unsigned)((nq_pad + nw - 1) / nw), nw * 32, sm, st>>>(a.mins, groups, f.nq, nq_pad, f.kc, C, f.d_tau);
+        tc_select_kernel<<<(unsigned)((f.nq + nw - 1) / nw), nw * 32, sm, st>>>(a.mins, groups, f.nq, f.kc, C, f.d_tau, f.d_gids, f.d_gcnt);
         VG_LAUNCHED();
     }
-    VG_CUDA(cudaMemsetAsync(f.d_cand_cnt, 0, (size_t)f.nq * 4, st));
-    VG_TRY(launch_pass<2>(resident, f.is_dot != 0, mq, mx, a, qtiles, (int)splits, st));
     return VG_OK;  // mins is returned to the stream-ordered pool (freed in stream order)
 }
 
 vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned int *d_xmax_bits, uint32_t *d_rows, float *d_scores,
                    int32_t *d_counts, int32_t *d_fail, cudaStream_t st) {
-    flat_tc_finalize_kernel<<<(unsigned)f.nq, 128, 0, st>>>(f.d_vectors, f.dim, f.d_queries, f.nq, f.d_cand, f.d_cand_cnt, f.d_tau, k,
-                                                            f.is_dot, f.row_base, d_qn, d_xmax_bits, d_rows, d_scores, d_counts, d_fail);
+    const int C = topk_capacity(k, 128);  // 16 half-warps x 8 rows may be offered between two compaction checks
+    const size_t sm = (((size_t)f.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, C);
+    if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the group scan");
+    VG_CUDA(cudaFuncSetAttribute(tc_group_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    tc_group_scan_kernel<<<(unsigned)f.nq, 256, sm, st>>>(f.d_vectors, f.dim, f.rows, f.d_queries, f.d_gids, f.d_gcnt, f.kc,
+                                                         group_rows(f.rows, f.kc), f.d_tau, d_qn, d_xmax_bits, f.d_mask, k, C, f.is_dot,
+                                                         f.row_base, d_rows, d_scores, d_counts, d_fail);
     VG_LAUNCHED();
     return VG_OK;
 }
