@@ -213,14 +213,15 @@ vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t
 
 /* Tensor-core Flat filter (csrc/vg_flat_tc.cu).  vg_index_search / vg_index_search_dev on a float32 index run
  * flat.(*Segment).Search (internal/segment/flat/segment.go:447-752) as a tcgen05 TF32 GEMM whose epilogue keeps the
- * minimum approximate score of every group of G consecutive rows; the kc groups with the smallest minima are then
- * scanned EXACTLY in simd.SquaredL2 / simd.Dot order and an error-bound certificate proves that the result equals
+ * two smallest approximate scores of every group of G consecutive rows (and which row is the smallest); the arg-min
+ * rows of the kc groups with the smallest minima are then scored EXACTLY in simd.SquaredL2 / simd.Dot order and an error-bound certificate proves that the result equals
  * the exact scan's; queries without a proof are re-run on the exact scan.
  * vg_flat_tc_enable(0) forces the exact CUDA-core scan (also: environment VECGO_FLAT_TC=0).
  * vg_flat_tc_stats: queries that went through the filter, and how many of them needed the exact re-run.
  * vg_flat_tc_candidates (diagnostic): per query the threshold tau (kc-th smallest group minimum of the APPROXIMATE
- * s-space score, L2: ||x||^2 - 2 q.x, dot: -q.x), the ids of the kc selected groups (h_groups [nq][kc], best first,
- * group g = rows [g*G, (g+1)*G)) and G. */
+ * s-space score, L2: ||x||^2 - 2 q.x, dot: -q.x), and for each of the kc selected groups (h_groups [nq][kc], best
+ * first, group g = rows [g*G, (g+1)*G)) either the row that attains the group minimum or 0x80000000|g when the
+ * group's second smallest value is <= tau as well (then all its rows are scored exactly); *group_rows = G. */
 vg_status vg_flat_tc_enable(int32_t on);
 vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks);
 vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_groups, int32_t *h_counts,

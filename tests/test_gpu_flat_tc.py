@@ -94,13 +94,17 @@ def test_tc_filter_error_within_certificate_bound(vg):
     x64, q64 = x.astype(np.float64), q.astype(np.float64)
     s_true = np.sum(x64 * x64, 1)[None, :] - 2 * q64 @ x64.T
     qn, xmax = np.sum(q64 * q64, 1), np.sum(x64 * x64, 1).max()
-    E = 1.125 / 256 * np.sqrt(qn * xmax) + (qn + xmax) / 16384
+    E = 1.125 / 256 * np.sqrt(qn * xmax) + (qn + xmax) / 16384 + (xmax + 2 * np.sqrt(qn * xmax)) * G / 2 ** 23
     ng = -(-n // G)
     top = np.argsort(s_true, axis=1, kind="stable")[:, :10]
     for i in range(nq):
         gm = np.pad(s_true[i], (0, ng * G - n), constant_values=np.inf).reshape(ng, G).min(1)
-        sel = gids[i].astype(np.int64)
+        ent = gids[i].astype(np.int64)
+        crowded = (ent & 0x80000000) != 0                      # both the best and the second best of the group are <= tau
+        sel = np.where(crowded, ent & 0x7FFFFFFF, ent // G)    # otherwise the entry is the group's arg-min ROW
         assert len(set(sel.tolist())) == kc
+        named = ent[~crowded]
+        assert np.all(s_true[i, named] <= gm[named // G] + 2 * E[i])  # the named row is the group's minimum (to within E)
         # tau is the kc-th smallest APPROXIMATE group minimum: within E of the true one
         assert abs(np.sort(gm)[kc - 1] - tau[i]) <= E[i]
         # every group whose true minimum is clearly below tau is selected, none clearly above is

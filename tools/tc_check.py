@@ -56,7 +56,12 @@ def main():
     inside, worst = 0.0, 0.0
     for i in range(nchk):
         gm = np.pad(s_true[i], (0, pad), constant_values=np.inf).reshape(ng, G).min(1)   # true group minima
-        sel = gids[i, : cnt[i]].astype(np.int64)
+        ent = gids[i, : cnt[i]].astype(np.int64)
+        crowded = (ent & 0x80000000) != 0
+        sel = np.where(crowded, ent & 0x7FFFFFFF, ent // G)
+        rows_named = ent[~crowded]
+        # the row a group minimum names must be (within the error bound) the true minimum of its group
+        assert np.all(s_true[i, rows_named] <= gm[rows_named // G] + 2 * E[i]), "arg-min row is not the group minimum"
         # every group whose true minimum is below tau - E must be selected; no selected group may be above tau + E
         assert set(np.where(gm <= tau[i] - E[i])[0].tolist()) <= set(sel.tolist()), "a group far below tau was not selected"
         assert np.all(gm[sel] <= tau[i] + E[i]), "a selected group is far above tau"

@@ -13,27 +13,29 @@
 //   s(q,x) = ||x||^2 - 2 q.x   (L2; the per-query constant ||q||^2 is dropped)
 //   s(q,x) = -q.x              (dot / cosine, descending in the reference)
 //
-// One GEMM pass with a branch-free epilogue (no per-query heap inside the GEMM), then a small exact scan:
-//   gemm    every thread (= one query) keeps the minimum of s over groups of G consecutive rows and
-//           writes one float per group (FFMA + FMNMX per accumulator element).
-//   select  tau(q) = the kc-th smallest group minimum and the kc groups that reach it.  kc groups
-//           with a row at or below tau exist, so at least kc rows have s <= tau; with many more
-//           groups than kc the bound is nearly tight.
-//   scan    the rows of those kc groups (kc x G rows per query, contiguous) are scored EXACTLY in
-//           simd.SquaredL2 / simd.Dot order and the heap order (score, row) keeps the best k.
+// One GEMM pass with a branch-free epilogue (no per-query heap inside the GEMM), then a tiny exact stage:
+//   gemm    every thread (= one query) reduces s over groups of G consecutive rows to (m1, m2): the smallest
+//           value — with the row's index inside the group written into its low mantissa bits, so the
+//           minimum also names its row — and the second smallest.  FFMA + LOP3 + 3 FMNMX per element.
+//   select  tau(q) = the kc-th smallest m1 and the kc groups that reach it.  Those kc groups each hold
+//           a row with s <= tau, so at least kc rows lie at or below tau; with many more groups than kc
+//           the bound is nearly tight.  A selected group whose m2 is also <= tau is "crowded".
+//   scan    the arg-min row of every selected group (and ALL rows of a crowded group) is scored EXACTLY
+//           in simd.SquaredL2 / simd.Dot order; the heap order (score, row) keeps the best k.
 //
-// Certificate (per query).  Every row OUTSIDE the scanned groups has s_approx > = tau (its group
-// minimum is not among the kc smallest).  With E >= |s_exact - s_approx| for every row (bound
-// below) such a row has s_exact >= tau - E.  If the exact k-th best scanned row satisfies
-// s_exact(e_k) < tau - E, no outside row can tie or beat it: the exact top-k of the scanned rows IS
-// the exact top-k of the segment (ties by row id included).
+// Certificate (per query).  Every row that was not scored is either in an unselected group (s >= m1 >= tau)
+// or a non-minimal row of an uncrowded selected group (s >= m2 > tau).  With E >= |s_exact - s_approx|
+// for every row (bound below) such a row has s_exact > tau - E.  If the exact k-th best scored row
+// satisfies s_exact(e_k) < tau - E, no other row can tie or beat it: the result IS the exact top-k of
+// the segment (ties by row id included).
 //
 // Error bound.  kind::tf32 keeps 10 explicit mantissa bits of each fp32 operand:
 // |fl_tf32(a) - a| <= 2^-10 |a|, so |q.x - (q.x)_tc| <= (2^-9 + 2^-20) sum|q_i x_i|
 // <= 2^-9 (1 + 2^-11) ||q|| ||x||, plus fp32 accumulation (<= d 2^-23 ||q|| ||x||).
 // With the factor 2 of the L2 form:  E = c1 ||q|| max||x|| + c2 (||q||^2 + max||x||^2),
 // c1 = 2^-8 * 1.125 (L2) or 2^-9 * 1.125 (dot), c2 = 2^-14 (norm rounding, accumulation
-// slack).  tests/test_gpu_flat_tc.py measures the realised error against E.
+// slack), plus 2^-(23-b) max|s| for the b = log2(G) mantissa bits that carry the row index.
+// tests/test_gpu_flat_tc.py measures the realised error against E.
 //
 // GEMM kernel (one CTA = 256 queries x a contiguous row range, 320 threads):
 //   warp 0     TMA producer (cp.async.bulk.tensor.2d, 128B swizzle).  dim <= 128: the 256 x dim
@@ -42,7 +44,7 @@
 //   warp 1     MMA issuer: tcgen05.mma.cta_group::1.kind::tf32, M=128 x N=128 x K=8, two M halves
 //              per B tile, fp32 accumulators in TMEM (2 stages x 2 halves x 128 columns = 512)
 //   warps 2-9  epilogue: one thread = one query (= one TMEM lane); tcgen05.ld 32 columns at a
-//              time, 32 independent FFMA, FMNMX tree, one store per group.
+//              time, 32 independent FFMA, four (m1, m2) accumulators, one 8-byte store per group.
 #include <cuda.h>
 
 #include <algorithm>
@@ -142,8 +144,9 @@ struct Args {
     int kb;                 // k-blocks = ceil(dim / 32)
     int cpg;                // 32-row chunks per minimum group (G / 32)
     uint32_t row_base;
-    float *mins;            // out: [nq_pad][groups]
+    float2 *mins;           // out: [nq_pad][groups] (m1 with the row index in its low log2(G) bits, m2)
     int64_t groups;
+    uint32_t idx_mask;      // G - 1
 };
 
 template <bool RESIDENT>
@@ -276,7 +279,8 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         const int64_t q = (int64_t)q0 + slot;
         float *xs = reinterpret_cast<float *>(smem + S::OFF_XN);
         const float INF = __int_as_float(0x7f800000);
-        float gmin = INF;                     // running minimum of the current group
+        const float BIG = 3.0e38f;            // padding / masked rows: finite, so index bits can be written into it
+        float g1 = BIG, g2 = BIG;             // running (smallest, second smallest) of the current group
         int cc = 0;
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
@@ -285,7 +289,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
             float *xt = xs + as * BN;
             if (et < BN) {
                 const int64_t row = n0 + et;
-                xt[et] = (row < row_end) ? (IS_DOT ? 0.0f : __ldg(A.xn + row)) : INF;
+                xt[et] = (row < row_end) ? (IS_DOT ? 0.0f : __ldg(A.xn + row)) : BIG;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(tfull_bar(as), aph);
@@ -308,23 +312,34 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const float dot = __uint_as_float(v[j4 * 4 + i]);
-                        s[j4 * 4 + i] = IS_DOT ? __fsub_rn(xx[i], dot) : __fmaf_rn(-2.0f, dot, xx[i]);  // dot: xx = 0 | +inf (padding)
+                        s[j4 * 4 + i] = IS_DOT ? __fsub_rn(xx[i], dot) : __fmaf_rn(-2.0f, dot, xx[i]);  // dot: xx = 0 | BIG (padding)
                     }
                 }
                 if (mw != 0xFFFFFFFFu) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : INF;
+                    for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
                 }
                 {
-                    float m8[8];
+                    // index of the chunk's first row inside its group (rows are group-aligned per CTA range)
+                    const uint32_t cidx = (uint32_t)(n0 + c * 32) & A.idx_mask;
+                    float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
 #pragma unroll
-                    for (int j = 0; j < 8; j++) m8[j] = fminf(fminf(s[j], s[j + 8]), fminf(s[j + 16], s[j + 24]));
-                    const float cm = fminf(fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3])), fminf(fminf(m8[4], m8[5]), fminf(m8[6], m8[7])));
-                    gmin = fminf(gmin, cm);
+                    for (int j = 0; j < 32; j++) {
+                        const float v1 = __uint_as_float((__float_as_uint(s[j]) & ~A.idx_mask) | (cidx + j));
+                        a2[j & 3] = fminf(a2[j & 3], fmaxf(a1[j & 3], v1));
+                        a1[j & 3] = fminf(a1[j & 3], v1);
+                    }
+                    // merge (m1, m2) pairs: m2 = min(max(a1, b1), a2, b2)
+                    const float p1 = fminf(a1[0], a1[1]), p2 = fminf(fmaxf(a1[0], a1[1]), fminf(a2[0], a2[1]));
+                    const float r1 = fminf(a1[2], a1[3]), r2 = fminf(fmaxf(a1[2], a1[3]), fminf(a2[2], a2[3]));
+                    const float c1 = fminf(p1, r1), c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
+                    g2 = fminf(fmaxf(g1, c1), fminf(g2, c2));
+                    g1 = fminf(g1, c1);
                     if (++cc == A.cpg) {
                         const int64_t gid = (n0 + c * 32) / (32 * (int64_t)A.cpg);
-                        if (gid < A.groups) A.mins[q * A.groups + gid] = gmin;  // chunks past the last row belong to no group
-                        gmin = INF;
+                        if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);  // chunks past the last row: no group
+                        g1 = BIG;
+                        g2 = BIG;
                         cc = 0;
                     }
                 }
@@ -335,7 +350,7 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
         if (cc > 0 && ntiles > 0) {  // partial last group of this row range
             const int64_t last_chunk_row = row_begin + (int64_t)ntiles * BN - 32;
             const int64_t gid = last_chunk_row / (32 * (int64_t)A.cpg);
-            if (gid < A.groups) A.mins[q * A.groups + gid] = gmin;
+            if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);
         }
     }
     tc_fence_before();
@@ -346,11 +361,14 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
-// tau(q) = kc-th smallest group minimum of query q and the ids of the kc groups that reach it: one warp per query
-// streams mins[q][*] (coalesced) through the shared-memory bounded top-k (threshold filter + bitonic compaction).
-// tau = +inf when there are fewer than kc groups (then every group is listed and the scan covers the whole segment).
-__global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64_t groups, int64_t nq, int kc, int C, float *tau,
-                                                        uint32_t *gids, int32_t *gcnt) {
+// tau(q) = kc-th smallest group minimum (m1) of query q and the kc groups that reach it: one warp per query streams
+// mins[q][*] (coalesced) through the shared-memory bounded top-k (threshold filter + bitonic compaction).  Output per
+// selected group: the row its m1 names (gid * G + index bits) and a "crowded" flag (bit 31) when m2 <= tau as well.
+// tau = +inf when there are fewer than kc groups (then every group is listed as crowded: the scan covers everything).
+#define VG_TC_CROWDED 0x80000000u
+constexpr int TC_LIST_CAP = 4096;   // candidate rows per query in the exact stage
+__global__ void __launch_bounds__(256) tc_select_kernel(const float2 *mins, int64_t groups, int64_t nq, int kc, int C, uint32_t idx_mask,
+                                                        int g_shift, float *tau, uint32_t *cand, int32_t *gcnt) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
     TopK tk = topk_carve(smem, nw, C, kc);
@@ -359,7 +377,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64
     const int64_t q = (int64_t)blockIdx.x * nw + warp;
     if (q >= nq) return;
     const float INF = __int_as_float(0x7f800000);
-    const float *src = mins + q * groups;
+    const float2 *src = mins + q * groups;
     const int trigger = C - 32;
     // 4 independent coalesced loads per lane per step (the loop is otherwise bound by L2 latency)
     for (int64_t g0 = 0; g0 < groups; g0 += 128) {
@@ -367,7 +385,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const int64_t g = g0 + u * 32 + lane;
-            v[u] = g < groups ? __ldcg(src + g) : INF;
+            v[u] = g < groups ? __ldcg(&src[g].x) : INF;
         }
 #pragma unroll
         for (int u = 0; u < 4; u++) {
@@ -387,92 +405,111 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float *mins, int64
     topk_compact_warp(tk, warp, lane, true);
     const int n = tk.cnt[warp];
     const unsigned long long *a = tk.keys + (size_t)warp * C;
-    for (int i = lane; i < kc; i += 32) gids[q * kc + i] = i < n ? (uint32_t)a[i] : 0xFFFFFFFFu;
+    const float t = (n >= kc) ? f32_from_orderable((uint32_t)(a[kc - 1] >> 32)) : INF;
+    for (int i = lane; i < kc; i += 32) {
+        uint32_t out = 0xFFFFFFFFu;
+        if (i < n) {
+            const uint32_t g = (uint32_t)a[i];
+            const float m1 = f32_from_orderable((uint32_t)(a[i] >> 32));
+            const float m2 = __ldcg(&src[g].y);
+            const uint32_t row = (g << g_shift) | (__float_as_uint(m1) & idx_mask);
+            out = (m2 <= t) ? (VG_TC_CROWDED | g) : row;   // crowded: scan the whole group g
+        }
+        cand[q * kc + i] = out;
+    }
     if (lane == 0) {
         gcnt[q] = n;
-        tau[q] = (n >= kc) ? f32_from_orderable((uint32_t)(a[kc - 1] >> 32)) : INF;
+        tau[q] = t;
     }
 }
 
-// Exact scan of the selected groups: one CTA per query, half-warp per row in simd.SquaredL2 / simd.Dot order
-// (floats_avx512.c:12-129: 4 x 16-lane FMA accumulators, (A1+A2)+(A3+A4), lane tree, FMA scalar tail), bounded
-// top-k under the heap order (score, row), then the certificate in double precision.
-__global__ void __launch_bounds__(256) tc_group_scan_kernel(const float *vectors, int64_t dim, int64_t rows, const float *queries,
-                                                            const uint32_t *gids, const int32_t *gcnt, int kc, int64_t G,
-                                                            const float *tau, const float *qn, const unsigned int *xmax_bits,
-                                                            const uint8_t *mask, int k, int C, int is_dot, uint32_t row_base,
-                                                            uint32_t *out_rows, float *out_scores, int32_t *out_counts,
-                                                            int32_t *fail_flags) {
+// Exact stage: one CTA per query.  The candidate rows (arg-min row of every selected group, all rows of crowded
+// groups) are scored half-warp per row in simd.SquaredL2 / simd.Dot order (floats_avx512.c:12-129: 4 x 16-lane FMA
+// accumulators, (A1+A2)+(A3+A4), lane tree, FMA scalar tail), bounded top-k under the heap order (score, row), then
+// the certificate in double precision.
+__global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int64_t dim, int64_t rows, const float *queries,
+                                                       const uint32_t *cand, const int32_t *gcnt, int kc, int G, const float *tau,
+                                                       const float *qn, const unsigned int *xmax_bits, const uint8_t *mask, int k,
+                                                       int C, int is_dot, uint32_t row_base, uint32_t *out_rows, float *out_scores,
+                                                       int32_t *out_counts, int32_t *fail_flags) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t q = blockIdx.x;
     const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
     float *qs = reinterpret_cast<float *>(smem);
     const size_t qbytes = ((size_t)dim * 4 + 15) & ~(size_t)15;
     TopK tk = topk_carve(smem + qbytes, 1, C, k);
-    for (int64_t d = tid; d < dim; d += 256) qs[d] = queries[q * dim + d];
-    topk_init(tk, 1, tid, 256);
+    for (int64_t d = tid; d < dim; d += 128) qs[d] = queries[q * dim + d];
+    topk_init(tk, 1, tid, 128);
     __syncthreads();
     const int ng = gcnt[q];
-    const int64_t total = (int64_t)ng * G;
     const int64_t epochs = dim >> 6;
-    constexpr int RH = 8;                 // rows per half-warp per step: 8 independent load streams hide the L2 latency
-    const int trigger = C - 16 * RH;
-    for (int64_t base = 0; base < total; base += 16 * RH) {
-        int64_t rowi[RH];
-        const float *x[RH];
-#pragma unroll
-        for (int u = 0; u < RH; u++) {
-            const int64_t r = base + hw * RH + u;
-            int64_t row = -1;
-            if (r < total) {
-                const uint32_t g = gids[q * kc + r / G];
-                row = (int64_t)g * G + r % G;
-                if (row >= rows) row = -1;
-                else if (mask && !((mask[row >> 3] >> (row & 7)) & 1)) row = -1;
-            }
-            rowi[u] = row;
-            x[u] = vectors + (row >= 0 ? row : 0) * dim;  // dead rows are computed (full-mask shuffles below) but not offered
+    const int trigger = C - 16;
+    // expand the candidate entries (1 row, or G rows when crowded) into a flat row list in shared memory
+    int32_t *rowlist = reinterpret_cast<int32_t *>(smem + qbytes + topk_smem_bytes(1, C));
+    __shared__ int s_total;
+    if (tid == 0) {
+        int n = 0;
+        for (int gi = 0; gi < ng; gi++) {
+            const uint32_t c = cand[q * kc + gi];
+            n += (c & VG_TC_CROWDED) ? G : 1;
         }
-        float a[RH][4];
-#pragma unroll
-        for (int u = 0; u < RH; u++)
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) a[u][jj] = 0.0f;
-        for (int64_t e = 0; e < epochs; e++)
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const int64_t d = e * 64 + jj * 16 + lane;
-                const float qv = qs[d];
-                float xv[RH];
-#pragma unroll
-                for (int u = 0; u < RH; u++) xv[u] = __ldg(x[u] + d);
-#pragma unroll
-                for (int u = 0; u < RH; u++) {
-                    if (is_dot) {
-                        a[u][jj] = __fmaf_rn(qv, xv[u], a[u][jj]);
-                    } else {
-                        const float df = __fsub_rn(qv, xv[u]);
-                        a[u][jj] = __fmaf_rn(df, df, a[u][jj]);
-                    }
+        s_total = n;
+    }
+    __syncthreads();
+    const bool overflow = s_total > TC_LIST_CAP;   // pathological (most selected groups crowded): exact re-run
+    if (!overflow) {
+        if (tid < 32) {  // one warp writes the list: entries in order, crowded groups expanded by the lanes
+            int off = 0;
+            for (int gi = 0; gi < ng; gi++) {
+                const uint32_t c = cand[q * kc + gi];
+                if (c & VG_TC_CROWDED) {
+                    const int64_t first = (int64_t)(c & ~VG_TC_CROWDED) * G;
+                    for (int r = tid; r < G; r += 32) rowlist[off + r] = (first + r < rows) ? (int32_t)(first + r) : -1;
+                    off += G;
+                } else {
+                    if (tid == 0) rowlist[off] = ((int64_t)c < rows) ? (int32_t)c : -1;
+                    off += 1;
                 }
-            }
-#pragma unroll
-        for (int u = 0; u < RH; u++) {
-            float tot = reduce16(__fadd_rn(__fadd_rn(a[u][0], a[u][1]), __fadd_rn(a[u][2], a[u][3])));
-            if (lane == 0 && rowi[u] >= 0) {
-                for (int64_t d = epochs * 64; d < dim; d++) {
-                    if (is_dot) {
-                        tot = __fmaf_rn(qs[d], __ldg(x[u] + d), tot);
-                    } else {
-                        const float df = __fsub_rn(qs[d], __ldg(x[u] + d));
-                        tot = __fmaf_rn(df, df, tot);
-                    }
-                }
-                topk_offer(tk, 0, make_key(tot, row_base + (uint32_t)rowi[u], is_dot != 0), trigger);
             }
         }
         __syncthreads();
-        topk_block_maintain(tk, 1, tid, 256);
+        const int total = s_total;
+        for (int r0 = 0; r0 < total; r0 += 16) {  // 8 half-warps x 2 rows
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int r = r0 + hw * 2 + u;
+                int64_t row = (r < total) ? (int64_t)rowlist[r] : -1;
+                if (row >= 0 && mask && !((mask[row >> 3] >> (row & 7)) & 1)) row = -1;
+                const bool valid = row >= 0;  // dead rows are computed (full-mask shuffles in reduce16) but not offered
+                const float *x = vectors + (valid ? row : 0) * dim;
+                float a[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int64_t e = 0; e < epochs; e++)
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        const int64_t d = e * 64 + jj * 16 + lane;
+                        if (is_dot) {
+                            a[jj] = __fmaf_rn(qs[d], __ldg(x + d), a[jj]);
+                        } else {
+                            const float df = __fsub_rn(qs[d], __ldg(x + d));
+                            a[jj] = __fmaf_rn(df, df, a[jj]);
+                        }
+                    }
+                float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+                if (lane == 0 && valid) {
+                    for (int64_t d = epochs * 64; d < dim; d++) {
+                        if (is_dot) {
+                            tot = __fmaf_rn(qs[d], __ldg(x + d), tot);
+                        } else {
+                            const float df = __fsub_rn(qs[d], __ldg(x + d));
+                            tot = __fmaf_rn(df, df, tot);
+                        }
+                    }
+                    topk_offer(tk, 0, make_key(tot, row_base + (uint32_t)row, is_dot != 0), trigger);
+                }
+            }
+            __syncthreads();
+            topk_block_maintain(tk, 1, tid, 128);
+        }
     }
     __syncthreads();
     if (tid < 32) {
@@ -480,15 +517,16 @@ __global__ void __launch_bounds__(256) tc_group_scan_kernel(const float *vectors
         __syncwarp();
         if (tid == 0) {
             const int m = tk.cnt[0];
-            int fail = 0;
+            int fail = overflow ? 1 : 0;
             const float t = tau[q];
-            if (t < __int_as_float(0x7f800000)) {  // finite threshold: rows outside the scanned groups exist
+            if (!overflow && t < __int_as_float(0x7f800000)) {  // finite threshold: rows that were not scored exist
                 if (m < k) {
                     fail = 1;
                 } else {
                     const double qq = (double)qn[q], xx = (double)__uint_as_float(*xmax_bits);
                     const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125, c2 = 1.0 / 16384.0;
-                    const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx);
+                    const double smax = is_dot ? sqrt(qq * xx) : xx + 2.0 * sqrt(qq * xx);   // |s| of any row
+                    const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx) + smax * (double)G / 8388608.0;  // index bits: 2^-(23-log2 G)
                     const double ex = (double)out_scores[q * k + (k - 1)];
                     const double s_exact = is_dot ? -ex : ex - qq;
                     if (!(s_exact < (double)t - E)) fail = 1;
@@ -576,7 +614,7 @@ int64_t group_rows(int64_t rows, int kc) {
     // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
     // while the exact scan of kc*G rows per query stays ~1% of the GEMM's work
     int64_t G = 32;
-    while (G < 8192 && rows / (G * 2) >= 128ll * kc) G *= 2;
+    while (G < 1024 && rows / (G * 2) >= 128ll * kc) G *= 2;  // <= 10 mantissa bits carry the row index
     return G;
 }
 
@@ -619,8 +657,9 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
     a.row_base = f.row_base;
     a.groups = groups;
     DevBuf mins;
-    VG_TRY(mins.alloc((size_t)groups * nq_pad * 4));
-    a.mins = mins.as<float>();
+    VG_TRY(mins.alloc((size_t)groups * nq_pad * 8));
+    a.mins = mins.as<float2>();
+    a.idx_mask = (uint32_t)(G - 1);
     const bool resident = a.kb <= MAX_RES_KB;
     if (resident) {
         if (f.is_dot) VG_TRY((launch<true, true>(mq, mx, a, qtiles, (int)splits, st)));
@@ -632,7 +671,10 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
     {
         const int C = topk_capacity(f.kc, 32), nw = 8;
         const size_t sm = topk_smem_bytes(nw, C);
-        tc_select_kernel<<<(unsigned)((f.nq + nw - 1) / nw), nw * 32, sm, st>>>(a.mins, groups, f.nq, f.kc, C, f.d_tau, f.d_gids, f.d_gcnt);
+        int g_shift = 0;
+        while ((1ll << g_shift) < G) g_shift++;
+        tc_select_kernel<<<(unsigned)((f.nq + nw - 1) / nw), nw * 32, sm, st>>>(a.mins, groups, f.nq, f.kc, C, a.idx_mask, g_shift, f.d_tau,
+                                                                                f.d_gids, f.d_gcnt);
         VG_LAUNCHED();
     }
     return VG_OK;  // mins is returned to the stream-ordered pool (freed in stream order)
@@ -640,13 +682,13 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
 
 vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned int *d_xmax_bits, uint32_t *d_rows, float *d_scores,
                    int32_t *d_counts, int32_t *d_fail, cudaStream_t st) {
-    const int C = topk_capacity(k, 128);  // 16 half-warps x 8 rows may be offered between two compaction checks
-    const size_t sm = (((size_t)f.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, C);
-    if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the group scan");
-    VG_CUDA(cudaFuncSetAttribute(tc_group_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    tc_group_scan_kernel<<<(unsigned)f.nq, 256, sm, st>>>(f.d_vectors, f.dim, f.rows, f.d_queries, f.d_gids, f.d_gcnt, f.kc,
-                                                         group_rows(f.rows, f.kc), f.d_tau, d_qn, d_xmax_bits, f.d_mask, k, C, f.is_dot,
-                                                         f.row_base, d_rows, d_scores, d_counts, d_fail);
+    const int C = topk_capacity(k, 16);
+    const size_t sm = (((size_t)f.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, C) + (size_t)TC_LIST_CAP * 4;
+    if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
+    VG_CUDA(cudaFuncSetAttribute(tc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    tc_exact_kernel<<<(unsigned)f.nq, 128, sm, st>>>(f.d_vectors, f.dim, f.rows, f.d_queries, f.d_gids, f.d_gcnt, f.kc,
+                                                    (int)group_rows(f.rows, f.kc), f.d_tau, d_qn, d_xmax_bits, f.d_mask, k, C, f.is_dot,
+                                                    f.row_base, d_rows, d_scores, d_counts, d_fail);
     VG_LAUNCHED();
     return VG_OK;
 }

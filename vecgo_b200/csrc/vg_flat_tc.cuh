@@ -16,7 +16,7 @@ struct FilterArgs {
     uint32_t row_base = 0;
     // outputs of filter()
     float *d_tau = nullptr;            // [nq] kc-th smallest group minimum in s-space (s = ||x||^2 - 2q.x | -q.x)
-    uint32_t *d_gids = nullptr;        // [nq][kc] ids of the groups with the smallest minima (0xFFFFFFFF padded)
+    uint32_t *d_gids = nullptr;        // [nq][kc] per selected group: its arg-min row, or 0x80000000|group when crowded (0xFFFFFFFF padded)
     int32_t *d_gcnt = nullptr;         // [nq] number of listed groups (< kc only when the segment has fewer groups)
 };
 
@@ -27,7 +27,7 @@ vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsign
 int64_t group_rows(int64_t rows, int kc);  // rows per minimum group for a segment of `rows` rows
 // TF32 GEMM with group-minimum epilogue → tau and the kc best groups per query.
 vg_status filter(const FilterArgs &f, cudaStream_t st);
-// Exact scan of the selected groups in simd pair order, top-k by (score,row), certificate → d_fail[q] (1 = re-run exactly).
+// Exact scores of the candidate rows in simd pair order, top-k by (score,row), certificate → d_fail[q] (1 = re-run exactly).
 vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned int *d_xmax_bits, uint32_t *d_rows, float *d_scores,
                    int32_t *d_counts, int32_t *d_fail, cudaStream_t st);
 
