@@ -161,3 +161,38 @@ def test_tc_equals_exact_scan_config1(vg):
         r0, s0, c0 = ix.search(q, k)
         vg._lib.call("vg_flat_tc_enable", 1)
     assert np.array_equal(r0, r1) and np.array_equal(bits(s0), bits(s1)) and np.array_equal(c0, c1)
+
+
+# ----------------------------------------------------------------- k-means assignment through the tensor cores
+@pytest.mark.parametrize("metric", [0, 2])
+@pytest.mark.parametrize("n,dim,k", [(4096, 64, 256), (5000, 128, 300), (3000, 768, 130)])
+def test_kmeans_assignment_tc_matches_oracle(vg, metric, n, dim, k):
+    """kmeans.AssignPartition for a batch (kmeans.go:142-196: argmin L2 / argmax dot, strict, first wins) goes through
+    the tcgen05 filter when there are >= 1024 samples and >= 128 centroids; assignments must equal the scalar loop."""
+    rng = np.random.default_rng(n + k)
+    v = rng.standard_normal((n, dim)).astype(F)
+    cent = rng.standard_normal((k, dim)).astype(F)
+    cent[k // 2] = cent[k // 3]            # duplicate centroids: ties must resolve to the smaller id
+    v[0] = cent[k // 3]
+    vg._lib.call("vg_flat_tc_enable", 1)
+    before = tc_stats(vg)
+    got = vg.kmeans.AssignPartition(v, cent, dim, metric)
+    after = tc_stats(vg)
+    assert after[0] - before[0] == n, "the assignment did not go through the tensor-core filter"
+    want = np.array([o.lib.vgo_kmeans_assign(o.fp(v[i]), o.fp(cent), dim, k, metric) for i in range(n)], np.int32)
+    assert np.array_equal(got, want)
+    assert got[0] == k // 3
+
+
+def test_kmeans_train_tc_matches_exact_path(vg):
+    """TrainKMeans with the filter on and off must produce bit-identical centroids, assignments and iteration counts."""
+    rng = np.random.default_rng(77)
+    n, dim, k = 6000, 64, 160
+    v = (rng.standard_normal((n, dim)) + rng.integers(0, 6, (n, 1)) * 2).astype(F)
+    init = rng.permutation(n)[:k].astype(np.int64)
+    out = []
+    for on in (1, 0):
+        vg._lib.call("vg_flat_tc_enable", on)
+        out.append(vg.kmeans.TrainKMeans(v, dim, k, 0, 5, init_rows=init, seed=3, return_assign=True))
+    vg._lib.call("vg_flat_tc_enable", 1)
+    assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]

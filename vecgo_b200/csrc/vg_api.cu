@@ -473,39 +473,13 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
 // --------------------------------------------------------------- search
 // Flat float32 search through the tcgen05 filter (vg_flat_tc.cu): candidates by TF32 GEMM, exact re-check in simd
 // pair order, certificate; queries whose certificate fails are re-run on the exact CUDA-core scan below.
-static std::atomic<int> g_tc_enabled{-1};
-static std::atomic<uint64_t> g_tc_queries{0}, g_tc_fallbacks{0};
-static bool tc_enabled() {
-    int v = g_tc_enabled.load();
-    if (v < 0) {
-        const char *e = getenv("VECGO_FLAT_TC");
-        v = (e && e[0] == '0') ? 0 : 1;
-        g_tc_enabled.store(v);
-    }
-    return v != 0;
-}
-__global__ void gather_rows_kernel(const float *src, const int32_t *idx, int64_t n, int64_t dim, float *dst) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * dim) return;
-    const int64_t r = i / dim, c = i - r * dim;
-    dst[i] = src[(int64_t)idx[r] * dim + c];
-}
-__global__ void scatter_results_kernel(const uint32_t *rows, const float *scores, const int32_t *counts, const int32_t *idx, int64_t n,
-                                       int64_t k, uint32_t *out_rows, float *out_scores, int32_t *out_counts) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n * k) return;
-    const int64_t r = i / k, c = i - r * k;
-    out_rows[(int64_t)idx[r] * k + c] = rows[i];
-    out_scores[(int64_t)idx[r] * k + c] = scores[i];
-    if (c == 0) out_counts[idx[r]] = counts[r];
-}
 static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
     if (!ix->xn_dirty && ix->xn.p) return VG_OK;
     const int64_t rows = ix->d.rows;
     if (!ix->xn.p) VG_TRY(ix->xn.alloc((size_t)rows * 4));
     if (!ix->xmax.p) VG_TRY(ix->xmax.alloc(16));
     VG_CUDA(cudaMemsetAsync(ix->xmax.p, 0, 16, st));
-    VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
+    VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
     ix->xn_dirty = false;
     return VG_OK;
 }
@@ -513,74 +487,46 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
                                 float *d_scores, int32_t *d_counts, bool *handled) {
     *handled = false;
     const vg_index_desc &d = ix->d;
-    if (!tc_enabled() || d.codec != VG_CODEC_F32 || d.num_partitions > 1 || !ix->has_vectors) return VG_OK;
+    if (!tc::enabled() || d.codec != VG_CODEC_F32 || d.num_partitions > 1 || !ix->has_vectors) return VG_OK;
     if (!tc::supported(d.dim, d.rows, nq, k)) return VG_OK;
     if ((reinterpret_cast<uintptr_t>(d_queries) & 15) != 0) return VG_OK;  // TMA needs 16-byte aligned bases
     if ((reinterpret_cast<uintptr_t>(d_mask) & 3) != 0) return VG_OK;      // the filter reads the row bitmap as 32-bit words
     cudaStream_t st = stream();
     VG_TRY(ensure_row_norms(ix, st));
     const int is_dot = d.metric != VG_METRIC_L2;
-    tc::FilterArgs f;
-    f.d_queries = d_queries;
-    f.d_vectors = ix->vectors.as<float>();
-    f.d_xn = ix->xn.as<float>();
-    f.d_mask = d_mask;
-    f.nq = nq;
-    f.rows = d.rows;
-    f.dim = d.dim;
-    f.kc = tc::candidates_for(k, d.dim);
-    f.is_dot = is_dot;
-    f.row_base = (uint32_t)d.row_base;
-    DevBuf gids, gcnt, tau, qn, failb;
-    VG_TRY(gids.alloc((size_t)nq * f.kc * 4));
-    VG_TRY(gcnt.alloc((size_t)nq * 4));
-    VG_TRY(tau.alloc((size_t)nq * 4));
-    VG_TRY(qn.alloc((size_t)nq * 4));
-    VG_TRY(failb.alloc((size_t)nq * 4));
-    f.d_gids = gids.as<uint32_t>();
-    f.d_gcnt = gcnt.as<int32_t>();
-    f.d_tau = tau.as<float>();
-    VG_TRY(tc::sqnorms(d_queries, nq, d.dim, qn.as<float>(), nullptr, st));
-    VG_TRY(tc::filter(f, st));
-    VG_TRY(tc::finalize(f, (int)k, qn.as<float>(), ix->xmax.as<unsigned int>(), d_rows, d_scores, d_counts, failb.as<int32_t>(), st));
-    std::vector<int32_t> h_fail((size_t)nq);
-    VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
-    VG_CUDA(cudaStreamSynchronize(st));
+    tc::SearchIO io;
+    io.d_queries = d_queries;
+    io.nq = nq;
+    io.d_vectors = ix->vectors.as<float>();
+    io.rows = d.rows;
+    io.dim = d.dim;
+    io.d_xn = ix->xn.as<float>();
+    io.d_xmax_bits = ix->xmax.as<unsigned int>();
+    io.d_mask = d_mask;
+    io.k = (int)k;
+    io.is_dot = is_dot;
+    io.row_base = (uint32_t)d.row_base;
+    io.d_rows = d_rows;
+    io.d_scores = d_scores;
+    io.d_counts = d_counts;
     std::vector<int32_t> bad;
-    for (int64_t q = 0; q < nq; q++)
-        if (h_fail[(size_t)q]) bad.push_back((int32_t)q);
-    g_tc_queries.fetch_add((uint64_t)nq);
-    g_tc_fallbacks.fetch_add((uint64_t)bad.size());
+    VG_TRY(tc::search(io, tc::candidates_for(k, d.dim), bad, st));
     if (!bad.empty()) {
         // exact CUDA-core scan for the queries the certificate could not clear
-        const int64_t nb = (int64_t)bad.size();
-        DevBuf bidx, bq, brow, bsc, bcnt;
-        VG_TRY(bidx.alloc((size_t)nb * 4));
-        VG_TRY(bq.alloc((size_t)nb * d.dim * 4));
-        VG_TRY(brow.alloc((size_t)nb * k * 4));
-        VG_TRY(bsc.alloc((size_t)nb * k * 4));
-        VG_TRY(bcnt.alloc((size_t)nb * 4));
-        VG_CUDA(cudaMemcpyAsync(bidx.p, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
-        gather_rows_kernel<<<(unsigned)((nb * d.dim + 255) / 256), 256, 0, st>>>(d_queries, bidx.as<int32_t>(), nb, d.dim, bq.as<float>());
-        VG_LAUNCHED();
         CodecParams cp = params_of(*ix);
         ScanArgs a;
-        a.queries = bq.as<float>();
-        a.nq = nb;
+        a.queries = d_queries;
+        a.nq = nq;
         a.rows = d.rows;
         a.k = (int)k;
         a.descending = is_dot;
         a.is_dot = is_dot;
         a.row_base = (uint32_t)d.row_base;
         a.mask = d_mask;
-        a.out_rows = brow.as<uint32_t>();
-        a.out_scores = bsc.as<float>();
-        a.out_counts = bcnt.as<int32_t>();
-        VG_TRY(scan_topk(cp, a, st));
-        scatter_results_kernel<<<(unsigned)((nb * k + 255) / 256), 256, 0, st>>>(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(),
-                                                                                bidx.as<int32_t>(), nb, k, d_rows, d_scores, d_counts);
-        VG_LAUNCHED();
-        VG_CUDA(cudaStreamSynchronize(st));
+        a.out_rows = d_rows;
+        a.out_scores = d_scores;
+        a.out_counts = d_counts;
+        VG_TRY(scan_topk_subset(cp, a, bad, st));
     }
     *handled = true;
     return VG_OK;
@@ -670,12 +616,11 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
 }
 
 vg_status vg_flat_tc_enable(int32_t on) {
-    g_tc_enabled.store(on ? 1 : 0);
+    tc::set_enabled(on != 0);
     return VG_OK;
 }
 vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
-    if (queries) *queries = g_tc_queries.load();
-    if (fallbacks) *fallbacks = g_tc_fallbacks.load();
+    tc::stats(queries, fallbacks);
     return VG_OK;
 }
 vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_groups, int32_t *h_counts,

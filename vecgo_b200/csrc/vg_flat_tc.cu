@@ -48,6 +48,9 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
+#include <vector>
 
 #include "vg_flat_tc.cuh"
 #include "vg_topk.cuh"
@@ -427,7 +430,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2 *mins, int6
 // groups) are scored half-warp per row in simd.SquaredL2 / simd.Dot order (floats_avx512.c:12-129: 4 x 16-lane FMA
 // accumulators, (A1+A2)+(A3+A4), lane tree, FMA scalar tail), bounded top-k under the heap order (score, row), then
 // the certificate in double precision.
-__global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int64_t dim, int64_t rows, const float *queries,
+__global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int64_t dim, int64_t rows, const float *queries, int64_t q_stride,
                                                        const uint32_t *cand, const int32_t *gcnt, int kc, int G, const float *tau,
                                                        const float *qn, const unsigned int *xmax_bits, const uint8_t *mask, int k,
                                                        int C, int is_dot, uint32_t row_base, uint32_t *out_rows, float *out_scores,
@@ -438,7 +441,7 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int
     float *qs = reinterpret_cast<float *>(smem);
     const size_t qbytes = ((size_t)dim * 4 + 15) & ~(size_t)15;
     TopK tk = topk_carve(smem + qbytes, 1, C, k);
-    for (int64_t d = tid; d < dim; d += 128) qs[d] = queries[q * dim + d];
+    for (int64_t d = tid; d < dim; d += 128) qs[d] = queries[q * q_stride + d];
     topk_init(tk, 1, tid, 128);
     __syncthreads();
     const int ng = gcnt[q];
@@ -540,11 +543,12 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int
 // ------------------------------------------------------------------ norms
 // ||v||^2 per row, half-warp per row, 4x16-lane FMA accumulators (any accurate fp32
 // order would do: the value only feeds the filter and its error bound).
-__global__ void __launch_bounds__(256) sqnorm_kernel(const float *v, int64_t n, int64_t dim, float *out, unsigned int *max_bits) {
+__global__ void __launch_bounds__(256) sqnorm_kernel(const float *v, int64_t n, int64_t dim, int64_t stride, float *out,
+                                                     unsigned int *max_bits) {
     const int64_t hw = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
     const int lane = threadIdx.x & 15;
     const bool live = hw < n;
-    const float *x = v + (live ? hw : n - 1) * dim;
+    const float *x = v + (live ? hw : n - 1) * stride;
     float a = 0.0f;
     for (int64_t d = lane; d < dim; d += 16) a = __fmaf_rn(x[d], x[d], a);
     a = reduce16(a);
@@ -570,10 +574,10 @@ static vg_status get_encode() {
     return VG_OK;
 }
 
-static vg_status make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t dim, int box_rows) {
+static vg_status make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t dim, int64_t stride, int box_rows) {
     VG_TRY(get_encode());
     const cuuint64_t dims[2] = {(cuuint64_t)dim, (cuuint64_t)rows};
-    const cuuint64_t strides[1] = {(cuuint64_t)dim * 4};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride * 4};
     const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
@@ -590,11 +594,19 @@ int candidates_for(int64_t k, int64_t dim) {
     const int kc = k <= 16 ? 32 : (int)(2 * k);
     return dim > 256 ? std::max(kc, 64) : kc;  // the error bound grows with ||q|| ||x||: keep more slack on long vectors
 }
+// Nearest-centroid assignment (k = 1 against a small table): a few groups are enough.
+bool supported_assign(int64_t dim, int64_t rows, int64_t nq, int64_t q_stride) {
+    return dim >= 16 && dim % 4 == 0 && q_stride % 4 == 0 && rows >= 128 && rows < (1ll << 31) && nq >= 1024;
+}
+int candidates_for_assign(int64_t rows) {
+    const int64_t groups = (rows + 31) / 32;
+    return (int)std::max<int64_t>(2, std::min<int64_t>(8, groups / 2));
+}
 
-vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsigned int *d_max_bits, cudaStream_t st) {
+vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, int64_t stride, float *d_out, unsigned int *d_max_bits, cudaStream_t st) {
     if (n <= 0) return VG_OK;
     const int64_t threads = n * 16;
-    sqnorm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_v, n, dim, d_out, d_max_bits);
+    sqnorm_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_v, n, dim, stride, d_out, d_max_bits);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -619,10 +631,11 @@ int64_t group_rows(int64_t rows, int kc) {
 }
 
 vg_status filter(const FilterArgs &f, cudaStream_t st) {
-    if (!supported(f.dim, f.rows, f.nq, 1) || f.kc < 1 || f.kc > 64) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
+    if (f.dim < 16 || f.dim % 4 != 0 || f.rows < 128 || f.rows >= (1ll << 31) || f.kc < 1 || f.kc > 64 || (f.rows + 31) / 32 < f.kc)
+        return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
     CUtensorMap mq, mx;
-    VG_TRY(make_map(&mq, f.d_queries, f.nq, f.dim, BMQ));
-    VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, BN));
+    VG_TRY(make_map(&mq, f.d_queries, f.nq, f.dim, f.q_stride ? f.q_stride : f.dim, BMQ));
+    VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, f.dim, BN));
     const int64_t qtiles = (f.nq + BMQ - 1) / BMQ;
     const int64_t nq_pad = qtiles * BMQ;
     const int64_t G = group_rows(f.rows, f.kc);
@@ -686,10 +699,65 @@ vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned
     const size_t sm = (((size_t)f.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, C) + (size_t)TC_LIST_CAP * 4;
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
     VG_CUDA(cudaFuncSetAttribute(tc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
-    tc_exact_kernel<<<(unsigned)f.nq, 128, sm, st>>>(f.d_vectors, f.dim, f.rows, f.d_queries, f.d_gids, f.d_gcnt, f.kc,
+    tc_exact_kernel<<<(unsigned)f.nq, 128, sm, st>>>(f.d_vectors, f.dim, f.rows, f.d_queries, f.q_stride ? f.q_stride : f.dim, f.d_gids, f.d_gcnt, f.kc,
                                                     (int)group_rows(f.rows, f.kc), f.d_tau, d_qn, d_xmax_bits, f.d_mask, k, C, f.is_dot,
                                                     f.row_base, d_rows, d_scores, d_counts, d_fail);
     VG_LAUNCHED();
+    return VG_OK;
+}
+
+// ------------------------------------------------------------------ switch + statistics
+static std::atomic<int> g_enabled{-1};
+static std::atomic<uint64_t> g_queries{0}, g_fallbacks{0};
+bool enabled() {
+    int v = g_enabled.load();
+    if (v < 0) {
+        const char *e = getenv("VECGO_FLAT_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_enabled.store(v);
+    }
+    return v != 0;
+}
+void set_enabled(bool on) { g_enabled.store(on ? 1 : 0); }
+void stats(uint64_t *queries, uint64_t *fallbacks) {
+    if (queries) *queries = g_queries.load();
+    if (fallbacks) *fallbacks = g_fallbacks.load();
+}
+
+// Filter + exact stage + certificate for one batch; `failed` receives the queries that need the exact re-run.
+vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
+    failed.clear();
+    FilterArgs f;
+    f.d_queries = io.d_queries;
+    f.q_stride = io.q_stride;
+    f.d_vectors = io.d_vectors;
+    f.d_xn = io.d_xn;
+    f.d_mask = io.d_mask;
+    f.nq = io.nq;
+    f.rows = io.rows;
+    f.dim = io.dim;
+    f.kc = kc;
+    f.is_dot = io.is_dot;
+    f.row_base = io.row_base;
+    DevBuf gids, gcnt, tau, qn, failb;
+    VG_TRY(gids.alloc((size_t)io.nq * kc * 4));
+    VG_TRY(gcnt.alloc((size_t)io.nq * 4));
+    VG_TRY(tau.alloc((size_t)io.nq * 4));
+    VG_TRY(qn.alloc((size_t)io.nq * 4));
+    VG_TRY(failb.alloc((size_t)io.nq * 4));
+    f.d_gids = gids.as<uint32_t>();
+    f.d_gcnt = gcnt.as<int32_t>();
+    f.d_tau = tau.as<float>();
+    VG_TRY(sqnorms(io.d_queries, io.nq, io.dim, io.q_stride ? io.q_stride : io.dim, qn.as<float>(), nullptr, st));
+    VG_TRY(filter(f, st));
+    VG_TRY(finalize(f, io.k, qn.as<float>(), io.d_xmax_bits, io.d_rows, io.d_scores, io.d_counts, failb.as<int32_t>(), st));
+    std::vector<int32_t> h_fail((size_t)io.nq);
+    VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)io.nq * 4, cudaMemcpyDeviceToHost, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    for (int64_t q = 0; q < io.nq; q++)
+        if (h_fail[(size_t)q]) failed.push_back((int32_t)q);
+    g_queries.fetch_add((uint64_t)io.nq);
+    g_fallbacks.fetch_add((uint64_t)failed.size());
     return VG_OK;
 }
 

@@ -1,12 +1,15 @@
 // vg_flat_tc.cuh — tensor-core (tcgen05, TF32) candidate filter for Flat search (vg_flat_tc.cu).
 #pragma once
+#include <vector>
+
 #include "vg_common.cuh"
 
 namespace vg {
 namespace tc {
 
 struct FilterArgs {
-    const float *d_queries = nullptr;  // [nq][dim]
+    const float *d_queries = nullptr;  // [nq] rows of dim floats, q_stride floats apart
+    int64_t q_stride = 0;              // 0 = dim
     const float *d_vectors = nullptr;  // [rows][dim] row-major float32 (the segment's vector section)
     const float *d_xn = nullptr;       // [rows] squared norms (L2) — unused for dot
     const uint8_t *d_mask = nullptr;   // optional row bitmap (bit = 1 keeps the row), 4-byte aligned
@@ -22,14 +25,39 @@ struct FilterArgs {
 
 bool supported(int64_t dim, int64_t rows, int64_t nq, int64_t k);
 int candidates_for(int64_t k, int64_t dim);
+// nearest-centroid assignment (k-means): k = 1 against a small centroid table
+bool supported_assign(int64_t dim, int64_t rows, int64_t nq, int64_t q_stride);
+int candidates_for_assign(int64_t rows);
 // out[i] = ||v_i||^2; optional running maximum (as uint bits of a non-negative float).
-vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, float *d_out, unsigned int *d_max_bits, cudaStream_t st);
+vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, int64_t stride, float *d_out, unsigned int *d_max_bits, cudaStream_t st);
 int64_t group_rows(int64_t rows, int kc);  // rows per minimum group for a segment of `rows` rows
 // TF32 GEMM with group-minimum epilogue → tau and the kc best groups per query.
 vg_status filter(const FilterArgs &f, cudaStream_t st);
 // Exact scores of the candidate rows in simd pair order, top-k by (score,row), certificate → d_fail[q] (1 = re-run exactly).
 vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned int *d_xmax_bits, uint32_t *d_rows, float *d_scores,
                    int32_t *d_counts, int32_t *d_fail, cudaStream_t st);
+
+// One batch end to end (norms of the queries, filter, exact stage, certificate).
+struct SearchIO {
+    const float *d_queries = nullptr;
+    int64_t q_stride = 0, nq = 0;
+    const float *d_vectors = nullptr;
+    int64_t rows = 0, dim = 0;
+    const float *d_xn = nullptr;               // [rows] squared norms of the vectors
+    const unsigned int *d_xmax_bits = nullptr; // their maximum (float bits)
+    const uint8_t *d_mask = nullptr;
+    int k = 0, is_dot = 0;
+    uint32_t row_base = 0;
+    uint32_t *d_rows = nullptr;                // [nq][k]
+    float *d_scores = nullptr;                 // [nq][k]
+    int32_t *d_counts = nullptr;               // [nq]
+};
+vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st);
+
+// Process-wide switch (default on; environment VECGO_FLAT_TC=0 turns it off) and counters.
+bool enabled();
+void set_enabled(bool on);
+void stats(uint64_t *queries, uint64_t *fallbacks);
 
 }  // namespace tc
 }  // namespace vg

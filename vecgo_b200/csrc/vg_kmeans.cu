@@ -11,6 +11,7 @@
 // is order-exact.  k-means++ draws from an explicit seed (the reference uses
 // Go's unseeded global RNG and is not reproducible even against itself); its
 // float32 running sums are sequential chains too and are kept sequential.
+#include "vg_flat_tc.cuh"
 #include "vg_kmeans.cuh"
 
 #include <vector>
@@ -82,6 +83,34 @@ static vg_status assign_generic(const float *d_vecs, int64_t n, int64_t stride, 
     a.out_rows = d_assign;
     a.out_scores = d_score;
     a.out_counts = d_cnt;
+    // Nearest-centroid assignment is a dense [n x dim] . [dim x k] contraction: run it through the tcgen05 filter
+    // (vg_flat_tc.cu: TF32 GEMM -> arg-min rows of the best groups -> exact re-check in simd order -> certificate)
+    // whenever the Batch kernel's order coincides with the pair order the exact stage uses (dim % 64 < 16).
+    const bool same_order = !(variant & VG_VAR_BATCH) || (dim % 64) < 16;
+    if (tc::enabled() && same_order && tc::supported_assign(dim, k, n, stride) && (reinterpret_cast<uintptr_t>(d_vecs) & 15) == 0) {
+        DevBuf xn, xmax;
+        VG_TRY(xn.alloc((size_t)k * 4));
+        VG_TRY(xmax.alloc(16));
+        VG_CUDA(cudaMemsetAsync(xmax.p, 0, 16, st));
+        VG_TRY(tc::sqnorms(d_cent, k, dim, dim, xn.as<float>(), xmax.as<unsigned int>(), st));
+        tc::SearchIO io;
+        io.d_queries = d_vecs;
+        io.q_stride = stride;
+        io.nq = n;
+        io.d_vectors = d_cent;
+        io.rows = k;
+        io.dim = dim;
+        io.d_xn = xn.as<float>();
+        io.d_xmax_bits = xmax.as<unsigned int>();
+        io.k = 1;
+        io.is_dot = is_dot;
+        io.d_rows = d_assign;
+        io.d_scores = d_score;
+        io.d_counts = d_cnt;
+        std::vector<int32_t> bad;
+        VG_TRY(tc::search(io, tc::candidates_for_assign(k), bad, st));
+        return scan_topk_subset(cp, a, bad, st);  // samples whose certificate failed: exact scan
+    }
     return scan_topk(cp, a, st);
 }
 

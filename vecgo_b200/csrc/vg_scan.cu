@@ -1208,6 +1208,52 @@ vg_status scan_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st) {
     return fail(VG_ERR_UNSUPPORTED, "unknown codec");
 }
 
+__global__ void gather_rows_kernel(const float *src, int64_t stride, const int32_t *idx, int64_t n, int64_t dim, float *dst) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * dim) return;
+    const int64_t r = i / dim, c = i - r * dim;
+    dst[i] = src[(int64_t)idx[r] * stride + c];
+}
+__global__ void scatter_results_kernel(const uint32_t *rows, const float *scores, const int32_t *counts, const int32_t *idx, int64_t n,
+                                       int64_t k, uint32_t *out_rows, float *out_scores, int32_t *out_counts) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * k) return;
+    const int64_t r = i / k, c = i - r * k;
+    out_rows[(int64_t)idx[r] * k + c] = rows[i];
+    out_scores[(int64_t)idx[r] * k + c] = scores[i];
+    if (c == 0) out_counts[idx[r]] = counts[r];
+}
+vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<int32_t> &which, cudaStream_t st) {
+    const int64_t nb = (int64_t)which.size();
+    if (nb == 0) return VG_OK;
+    const int64_t dim = cp.dim, k = a.k;
+    DevBuf bidx, bq, brow, bsc, bcnt;
+    VG_TRY(bidx.alloc((size_t)nb * 4));
+    VG_TRY(bq.alloc((size_t)nb * dim * 4));
+    VG_TRY(brow.alloc((size_t)nb * k * 4));
+    VG_TRY(bsc.alloc((size_t)nb * k * 4));
+    VG_TRY(bcnt.alloc((size_t)nb * 4));
+    VG_CUDA(cudaMemcpyAsync(bidx.p, which.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+    gather_rows_kernel<<<(unsigned)((nb * dim + 255) / 256), 256, 0, st>>>(a.queries, a.q_stride ? a.q_stride : dim, bidx.as<int32_t>(), nb, dim,
+                                                                          bq.as<float>());
+    VG_LAUNCHED();
+    uint32_t *out_rows = a.out_rows;
+    float *out_scores = a.out_scores;
+    int32_t *out_counts = a.out_counts;
+    a.queries = bq.as<float>();
+    a.q_stride = 0;
+    a.nq = nb;
+    a.out_rows = brow.as<uint32_t>();
+    a.out_scores = bsc.as<float>();
+    a.out_counts = bcnt.as<int32_t>();
+    VG_TRY(scan_topk(cp, a, st));
+    scatter_results_kernel<<<(unsigned)((nb * k + 255) / 256), 256, 0, st>>>(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(),
+                                                                            bidx.as<int32_t>(), nb, k, out_rows, out_scores, out_counts);
+    VG_LAUNCHED();
+    VG_CUDA(cudaStreamSynchronize(st));  // `which` (host) and the temporaries are released on return
+    return VG_OK;
+}
+
 vg_status scan_dense(const CodecParams &cp, const float *d_queries, int64_t nq, int64_t n, int is_dot, float *d_out,
                      cudaStream_t st) {
     if ((cp.codec == VG_CODEC_PQ || cp.codec == VG_CODEC_OPQ) && cp.pq_k != 256)

@@ -1,5 +1,7 @@
 // vg_scan.cuh — host-visible descriptors of the scan kernels (vg_scan.cu).
 #pragma once
+#include <vector>
+
 #include "vg_common.cuh"
 #include "vg_topk.cuh"
 
@@ -62,6 +64,9 @@ struct ScanArgs {
 
 // Full top-k scan of one index (chooses tile kernel, row splits and merge).
 vg_status scan_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st);
+// Exact re-run of a subset of the batch (`which`: query indices into a.queries / a.out_*): gathers those queries,
+// scans them with scan_topk and scatters the results back into a.out_rows / a.out_scores / a.out_counts.
+vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<int32_t> &which, cudaStream_t st);
 // Dense distance matrix out[nq][n] (simd kernel-table mirrors, rerank, k-means); no top-k.
 vg_status scan_dense(const CodecParams &cp, const float *d_queries, int64_t nq, int64_t n, int is_dot, float *d_out,
                      cudaStream_t st);
