@@ -329,14 +329,20 @@ struct Lloyd {
 vg_status dev_find_closest(const float *d_queries, int64_t nq, int64_t dim, const float *d_centroids, int64_t k, int64_t np,
                            int metric, int32_t *d_out, cudaStream_t st) {
     if (np > k) np = k;
+    DevBuf sc, cnt;
+    VG_TRY(sc.alloc((size_t)nq * np * 4));
+    VG_TRY(cnt.alloc((size_t)nq * 4));
+    if (np == 1) {  // AssignPartition: nearest centroid (tensor-core filter for large batches)
+        VG_TRY(assign_generic(d_queries, nq, dim, dim, d_centroids, k, VG_VAR_BATCH, metric != VG_METRIC_L2,
+                              reinterpret_cast<uint32_t *>(d_out), sc.as<float>(), cnt.as<int32_t>(), st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        return VG_OK;
+    }
     CodecParams cp;
     cp.codec = VG_CODEC_F32;
     cp.variant = VG_VAR_BATCH;
     cp.dim = dim;
     cp.vectors = d_centroids;
-    DevBuf sc, cnt;
-    VG_TRY(sc.alloc((size_t)nq * np * 4));
-    VG_TRY(cnt.alloc((size_t)nq * 4));
     ScanArgs a;
     a.queries = d_queries;
     a.nq = nq;
