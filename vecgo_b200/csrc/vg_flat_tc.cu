@@ -53,6 +53,7 @@
 #include <vector>
 
 #include "vg_flat_tc.cuh"
+#include "vg_scan.cuh"
 #include "vg_topk.cuh"
 
 namespace vg {
@@ -724,8 +725,8 @@ void stats(uint64_t *queries, uint64_t *fallbacks) {
     if (fallbacks) *fallbacks = g_fallbacks.load();
 }
 
-// Filter + exact stage + certificate for one batch; `failed` receives the queries that need the exact re-run.
-vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
+// Filter + exact stage + certificate for one batch (norms of the queries included).
+static vg_status search_once(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
     failed.clear();
     FilterArgs f;
     f.d_queries = io.d_queries;
@@ -756,6 +757,42 @@ vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaS
     VG_CUDA(cudaStreamSynchronize(st));
     for (int64_t q = 0; q < io.nq; q++)
         if (h_fail[(size_t)q]) failed.push_back((int32_t)q);
+    return VG_OK;
+}
+
+// One batch end to end.  Queries whose certificate fails get a second chance with twice the number of groups (a
+// wider gap between the k-th best and tau) before they are reported in `failed` for the exact re-run.
+vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
+    VG_TRY(search_once(io, kc, failed, st));
+    const int64_t groups = (io.rows + group_rows(io.rows, kc) - 1) / group_rows(io.rows, kc);
+    const int kc2 = (int)std::min<int64_t>(64, std::min<int64_t>(2 * (int64_t)kc, groups / 2));
+    if (!failed.empty() && kc2 > kc) {
+        const int64_t nb = (int64_t)failed.size();
+        DevBuf bidx, bq, brow, bsc, bcnt;
+        VG_TRY(bidx.alloc((size_t)nb * 4));
+        VG_TRY(bq.alloc((size_t)nb * io.dim * 4));
+        VG_TRY(brow.alloc((size_t)nb * io.k * 4));
+        VG_TRY(bsc.alloc((size_t)nb * io.k * 4));
+        VG_TRY(bcnt.alloc((size_t)nb * 4));
+        VG_CUDA(cudaMemcpyAsync(bidx.p, failed.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+        VG_TRY(dev_gather_rows(io.d_queries, io.q_stride ? io.q_stride : io.dim, bidx.as<int32_t>(), nb, io.dim, bq.as<float>(), st));
+        SearchIO io2 = io;
+        io2.d_queries = bq.as<float>();
+        io2.q_stride = 0;
+        io2.nq = nb;
+        io2.d_rows = brow.as<uint32_t>();
+        io2.d_scores = bsc.as<float>();
+        io2.d_counts = bcnt.as<int32_t>();
+        std::vector<int32_t> failed2;
+        VG_TRY(search_once(io2, kc2, failed2, st));
+        // results of the retried queries (also of those that failed again: the caller overwrites them)
+        VG_TRY(dev_scatter_results(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(), bidx.as<int32_t>(), nb, io.k, io.d_rows,
+                                   io.d_scores, io.d_counts, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        std::vector<int32_t> still;
+        for (int32_t j : failed2) still.push_back(failed[(size_t)j]);
+        failed.swap(still);
+    }
     g_queries.fetch_add((uint64_t)io.nq);
     g_fallbacks.fetch_add((uint64_t)failed.size());
     return VG_OK;

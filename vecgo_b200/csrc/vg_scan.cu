@@ -1223,6 +1223,20 @@ __global__ void scatter_results_kernel(const uint32_t *rows, const float *scores
     out_scores[(int64_t)idx[r] * k + c] = scores[i];
     if (c == 0) out_counts[idx[r]] = counts[r];
 }
+vg_status dev_gather_rows(const float *d_src, int64_t stride, const int32_t *d_idx, int64_t n, int64_t dim, float *d_dst, cudaStream_t st) {
+    if (n <= 0) return VG_OK;
+    gather_rows_kernel<<<(unsigned)((n * dim + 255) / 256), 256, 0, st>>>(d_src, stride, d_idx, n, dim, d_dst);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+vg_status dev_scatter_results(const uint32_t *d_rows, const float *d_scores, const int32_t *d_counts, const int32_t *d_idx, int64_t n,
+                              int64_t k, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts, cudaStream_t st) {
+    if (n <= 0) return VG_OK;
+    scatter_results_kernel<<<(unsigned)((n * k + 255) / 256), 256, 0, st>>>(d_rows, d_scores, d_counts, d_idx, n, k, d_out_rows, d_out_scores,
+                                                                           d_out_counts);
+    VG_LAUNCHED();
+    return VG_OK;
+}
 vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<int32_t> &which, cudaStream_t st) {
     const int64_t nb = (int64_t)which.size();
     if (nb == 0) return VG_OK;

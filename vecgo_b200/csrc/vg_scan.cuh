@@ -67,6 +67,10 @@ vg_status scan_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st);
 // Exact re-run of a subset of the batch (`which`: query indices into a.queries / a.out_*): gathers those queries,
 // scans them with scan_topk and scatters the results back into a.out_rows / a.out_scores / a.out_counts.
 vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<int32_t> &which, cudaStream_t st);
+// dst[i] = src[idx[i]] (rows of `dim` floats, `stride` floats apart) and its inverse for (rows, scores, counts) results.
+vg_status dev_gather_rows(const float *d_src, int64_t stride, const int32_t *d_idx, int64_t n, int64_t dim, float *d_dst, cudaStream_t st);
+vg_status dev_scatter_results(const uint32_t *d_rows, const float *d_scores, const int32_t *d_counts, const int32_t *d_idx, int64_t n,
+                              int64_t k, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts, cudaStream_t st);
 // Dense distance matrix out[nq][n] (simd kernel-table mirrors, rerank, k-means); no top-k.
 vg_status scan_dense(const CodecParams &cp, const float *d_queries, int64_t nq, int64_t n, int is_dot, float *d_out,
                      cudaStream_t st);
