@@ -227,6 +227,16 @@ vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks);
 vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_groups, int32_t *h_counts,
                                 float *h_tau, int64_t *group_rows);
 
+/* Tensor-core filter of the quantized scans (csrc/vg_quant_tc.cu).  vg_index_search / vg_index_search_dev on an
+ * SQ8 / INT4 / PQ / OPQ index (L2, no IVF partitions, dim % 64 == 0, k <= 128, batches of >= 16 queries over >= 8192
+ * rows) run simd.Sq8uL2BatchPerDimension / simd.Int4L2DistanceBatch / simd.PqAdcLookup
+ * (internal/segment/flat/segment.go:543-552,603-611) as a tcgen05 fp16 GEMM over codes that are decoded inside the
+ * kernel; the candidates are re-scored in the reference's exact float32 order and a certificate proves the result
+ * equals the exact scan's (queries without a proof are re-run on the exact CUDA-core scan).  Environment
+ * VECGO_QUANT_TC=0 (or vg_flat_tc_enable(0)) forces the CUDA-core scan.  Counters: queries that went through the
+ * filter and how many of them needed the exact re-run. */
+vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks);
+
 /* flat.Open (internal/segment/flat/segment.go:105-342) on the raw file bytes:
  * header decode, optional CRC32C verify, section views, staging to HBM. */
 vg_status vg_flat_open(const uint8_t *h_file, size_t len, int32_t verify_checksum, vg_index_t *out);

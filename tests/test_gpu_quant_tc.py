@@ -1,0 +1,229 @@
+"""GPU parity tests of the decode-GEMM tensor-core path of the quantized scans (vecgo_b200/csrc/vg_quant_tc.cu).
+
+The fp16 GEMM over codes decoded inside the kernel only FILTERS; vg_index_search must return what
+flat.(*Segment).Search returns on the SIMD path: row ids with ties by row id and float32 scores in the order of
+simd.Sq8uL2BatchPerDimension / simd.Int4L2DistanceBatch / simd.PqAdcLookup — checked bit for bit against the CPU
+oracle and against this library's exact CUDA-core scan — whatever the filter did, including a failing certificate.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import oracle as o
+
+pytestmark = pytest.mark.gpu
+F = np.float32
+
+
+def bits(x):
+    return np.ascontiguousarray(x, F).view(np.uint32)
+
+
+@pytest.fixture(scope="module")
+def vg():
+    import vecgo_b200
+
+    return vecgo_b200
+
+
+def qtc_stats(vg):
+    q, f = C.c_uint64(), C.c_uint64()
+    vg._lib.call("vg_quant_tc_stats", C.byref(q), C.byref(f))
+    return q.value, f.value
+
+
+def check(rows, scores, counts, want):
+    for i, w in enumerate(want):
+        c = int(counts[i])
+        assert c == len(w), (i, c, len(w))
+        assert np.array_equal(rows[i, :c], w["row"]), i
+        assert np.array_equal(bits(scores[i, :c]), bits(w["score"])), i
+        assert np.all(rows[i, c:] == 0xFFFFFFFF)
+
+
+def oracle_flat(queries, k, mask=None, **kw):
+    seg = o.FlatOracle(**kw)
+    out, cnt = seg.search_batch(queries, k, threads=8, mask=mask)
+    return [out[i, : cnt[i]] for i in range(len(queries))]
+
+
+def exact_scan(vg, make_index, q, k, **kw):
+    """The same search on the exact CUDA-core scan (tensor-core filters off)."""
+    vg._lib.call("vg_flat_tc_enable", 0)
+    try:
+        with make_index() as ix:
+            return ix.search(q, k, **kw)
+    finally:
+        vg._lib.call("vg_flat_tc_enable", 1)
+
+
+def random_pq(rng, dim, m, k=256):
+    ds = dim // m
+    cb = rng.integers(-128, 128, m * k * ds, dtype=np.int8)
+    sc = (rng.random(m) * 0.02 + 0.005).astype(F)
+    of = (rng.standard_normal(m) * 0.1).astype(F)
+    return cb, sc, of
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (20000, 768, 40, 10),     # lane-transposed layout VB=16, streamed 12 k-blocks
+    (9000, 64, 300, 1),       # VB=4 layout, one k-block, two query tiles, ragged row tile
+    (70000, 256, 64, 32),     # many row splits
+    (150000, 128, 32, 100),   # k = 100 -> 200 candidate groups
+])
+def test_sq8_tc_matches_oracle(vg, n, dim, nq, k):
+    rng = np.random.default_rng(n + dim)
+    v = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    sq = vg.quantization.ScalarQuantizer(dim)
+    sq.Train(v)
+    codes = sq.EncodeBatch(v)
+    codes[n // 2] = codes[n // 3]   # duplicate rows -> equal scores -> tie by row id
+    q[0] = v[n // 3]                # a query that sits on a stored row
+
+    def make():
+        ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(sq.mins, sq.invScales))
+        ix.upload(codes=codes)
+        return ix
+
+    before = qtc_stats(vg)
+    with make() as ix:
+        rows, scores, counts = ix.search(q, k)
+    after = qtc_stats(vg)
+    assert after[0] - before[0] == nq, "the search did not go through the decode-GEMM filter"
+    want = oracle_flat(q, k, dim=dim, metric=0, quant=1, codes=codes, mins=sq.mins, inv=sq.invScales)
+    check(rows, scores, counts, want)
+    r2, s2, c2 = exact_scan(vg, make, q, k)
+    assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)
+    if k <= 32:
+        assert after[1] - before[1] <= nq // 4, "too many certificate failures on benign data"
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [(30000, 768, 33, 10), (9000, 256, 20, 5), (12000, 64, 17, 10), (100000, 192, 32, 50)])
+def test_int4_tc_matches_exact_scan(vg, n, dim, nq, k):
+    rng = np.random.default_rng(n + dim + 1)
+    v = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    iq = vg.quantization.Int4Quantizer(dim)
+    iq.Train(v)
+    codes = iq.EncodeBatch(v)
+    codes[n // 2] = codes[n // 3]
+
+    def make():
+        ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_INT4, metric=0, dim=dim, rows=n, int4=(iq.min, iq.diff))
+        ix.upload(codes=codes)
+        return ix
+
+    before = qtc_stats(vg)
+    with make() as ix:
+        rows, scores, counts = ix.search(q, k)
+    after = qtc_stats(vg)
+    assert after[0] - before[0] == nq
+    r2, s2, c2 = exact_scan(vg, make, q, k)
+    assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)
+    # and against the CPU oracle for a few queries (int4_avx512.c order)
+    for i in range(min(nq, 6)):
+        out = np.zeros(k, o.cand_dtype)
+        c = o.lib.vgo_int4_search(o.fp(q[i]), o.bp(codes), n, dim, o.fp(iq.min), o.fp(iq.diff), k,
+                                  o.fn_addr(o.lib.vgo_int4_l2_batch_a512), out.ctypes.data_as(C.POINTER(o.Cand)))
+        assert np.array_equal(rows[i, :c], out[:c]["row"]) and np.array_equal(bits(scores[i, :c]), bits(out[:c]["score"]))
+
+
+@pytest.mark.parametrize("n,dim,m,nq,k", [
+    (20000, 768, 96, 33, 10),    # C3 shape: tiled code layout, dsub = 8
+    (9000, 64, 8, 300, 1),       # one k-block
+    (40000, 128, 8, 20, 10),     # dsub = 16
+    (60000, 256, 32, 32, 100),   # k = 100
+    (10000, 128, 16, 16, 10),     # m = 16, dsub = 8
+])
+def test_pq_tc_matches_oracle(vg, n, dim, m, nq, k):
+    rng = np.random.default_rng(n + m)
+    cb, sc, of = random_pq(rng, dim, m)
+    codes = rng.integers(0, 256, (n, m), dtype=np.uint8)
+    codes[n // 2] = codes[n // 3]
+    q = (rng.standard_normal((nq, dim)) * 0.7).astype(F)
+
+    def make():
+        ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_PQ, metric=0, dim=dim, rows=n, pq=(cb, sc, of, m, 256))
+        ix.upload(codes=codes)
+        return ix
+
+    before = qtc_stats(vg)
+    with make() as ix:
+        rows, scores, counts = ix.search(q, k)
+    after = qtc_stats(vg)
+    assert after[0] - before[0] == nq
+    want = oracle_flat(q[:8], k, dim=dim, metric=0, quant=2, codes=codes, pq=(cb, sc, of, m, 256))
+    check(rows[:8], scores[:8], counts[:8], want)
+    r2, s2, c2 = exact_scan(vg, make, q, k)
+    assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)
+
+
+def test_tc_row_mask_row_base_and_chunked_upload(vg):
+    n, dim, nq, k = 50000, 128, 48, 10
+    rng = np.random.default_rng(77)
+    v = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    sq = vg.quantization.ScalarQuantizer(dim)
+    sq.Train(v)
+    codes = sq.EncodeBatch(v)
+    mask_bits = rng.random(n) < 0.3
+    mask = np.packbits(mask_bits, bitorder="little")
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_SQ8, metric=0, dim=dim, rows=n, row_base=1000, sq8=(sq.mins, sq.invScales)) as ix:
+        ix.upload(codes=codes[:20000])
+        ix.upload(codes=codes[20000:], row0=20000)  # second upload invalidates the prepared norms
+        before = qtc_stats(vg)
+        rows, scores, counts = ix.search(q, k, row_mask=mask)
+        assert qtc_stats(vg)[0] - before[0] == nq
+    want = oracle_flat(q, k, dim=dim, metric=0, quant=1, codes=codes, mins=sq.mins, inv=sq.invScales, mask=mask)
+    for i in range(nq):
+        assert np.array_equal(rows[i], want[i]["row"] + 1000)
+        assert np.array_equal(bits(scores[i]), bits(want[i]["score"]))
+        assert mask_bits[rows[i] - 1000].all()
+
+
+def test_tc_certificate_failure_falls_back_to_exact_scan(vg):
+    """Thousands of identical rows: the k-th best ties with rows outside any candidate set, no certificate can hold."""
+    n, dim, nq, k = 40000, 128, 32, 10
+    rng = np.random.default_rng(3)
+    v = rng.standard_normal((n, dim)).astype(F)
+    sq = vg.quantization.ScalarQuantizer(dim)
+    sq.Train(v)
+    codes = sq.EncodeBatch(v)
+    codes[5000:9000] = codes[5000]
+    q = (v[5000] + 0.01 * rng.standard_normal((nq, dim))).astype(F)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(sq.mins, sq.invScales)) as ix:
+        ix.upload(codes=codes)
+        before = qtc_stats(vg)
+        rows, scores, counts = ix.search(q, k)
+        after = qtc_stats(vg)
+    assert after[1] - before[1] > 0, "expected certificate failures"
+    want = oracle_flat(q, k, dim=dim, metric=0, quant=1, codes=codes, mins=sq.mins, inv=sq.invScales)
+    check(rows, scores, counts, want)
+    assert np.array_equal(rows[0], np.arange(5000, 5000 + k))  # ties by row id
+
+
+def test_tc_scaled_data_ranges(vg):
+    """Power-of-two scaling keeps fp16 in range: values around 1e-4 and around 3e4 give the same ids as the exact scan."""
+    n, dim, nq, k = 30000, 128, 16, 10
+    rng = np.random.default_rng(11)
+    for scale in (1e-4, 3e4):
+        v = (rng.standard_normal((n, dim)) * scale).astype(F)
+        q = (rng.standard_normal((nq, dim)) * scale).astype(F)
+        sq = vg.quantization.ScalarQuantizer(dim)
+        sq.Train(v)
+        codes = sq.EncodeBatch(v)
+
+        def make():
+            ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(sq.mins, sq.invScales))
+            ix.upload(codes=codes)
+            return ix
+
+        before = qtc_stats(vg)
+        with make() as ix:
+            rows, scores, counts = ix.search(q, k)
+        after = qtc_stats(vg)
+        assert after[0] - before[0] == nq and after[1] - before[1] == 0, scale
+        r2, s2, c2 = exact_scan(vg, make, q, k)
+        assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2))

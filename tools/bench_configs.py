@@ -47,6 +47,12 @@ def timed(fn, warm=2, reps=3):
     return float(np.median(ts))
 
 
+def qtc_stats():
+    a, b = C.c_uint64(), C.c_uint64()
+    L.call("vg_quant_tc_stats", C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
 def out_bufs(nq, k, dev):
     return (torch.empty((nq, k), dtype=torch.int32, device=dev), torch.empty((nq, k), dtype=torch.float32, device=dev),
             torch.empty((nq,), dtype=torch.int32, device=dev))
@@ -58,9 +64,11 @@ def emit(name, workload, ms, nq, pairs, bytes_per_pair=None, flops=None, extra=N
         ach = pairs * bytes_per_pair / ms / 1e6
         line["roofline"] = {"bound": "hbm", "achieved_gbs": ach, "peak_gbs": HBM, "frac": ach / HBM, "peak_source": SRC}
     if flops is not None:
+        if "roofline" in line:
+            line["hbm_equivalent"] = line.pop("roofline")  # per-query streaming bytes of the reference / time, vs the HBM peak
         ach = flops / ms / 1e9
         line["roofline"] = {"bound": "tensor", "achieved_tflops": ach, "peak_tflops_bf16": TF, "frac": ach / TF, "peak_source": SRC,
-                            "note": "useful FLOPs 2*Q*N*d; the filter runs the GEMM twice in TF32 (nominal dense TF32 peak is half of bf16)"}
+                            "note": "useful FLOPs 2*Q*N*d of the filter GEMM (Flat: TF32, nominal dense peak half of bf16; quantized scans: fp16)"}
     if extra:
         line.update(extra)
     print(json.dumps(line), flush=True)
@@ -105,8 +113,11 @@ def sq(name, codec, n, dim, nq, k):
         ix.upload_dev(m, d_codes=codes.data_ptr(), row0=r0)
     q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
     r, s, c = out_bufs(nq, k, dev)
+    st0 = qtc_stats()
     ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
-    emit(name, f"{codec.upper()} decode-and-scan, {n} x {dim}, {nq} queries, k={k} (uniform random codes)", ms, nq, n * nq, bytes_per_pair=cb)
+    st1 = qtc_stats()
+    emit(name, f"{codec.upper()} decode-and-scan, {n} x {dim}, {nq} queries, k={k} (uniform random codes)", ms, nq, n * nq, bytes_per_pair=cb,
+         flops=2.0 * n * nq * dim, extra={"tensor_core_filter": {"queries": st1[0] - st0[0], "exact_rerun_queries": st1[1] - st0[1]}})
     ix.close()
 
 
@@ -124,9 +135,12 @@ def pq(name, n, dim, m, nq, k):
         ix.upload_dev(mm, d_codes=codes.data_ptr(), row0=r0)
     q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
     r, s, c = out_bufs(nq, k, dev)
+    st0 = qtc_stats()
     ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
+    st1 = qtc_stats()
     emit(name, f"PQ M={m} x 256 ADC scan, {n} rows ({dim}-d), {nq} queries, k={k} (per-GPU shard of the 8-GPU config)", ms, nq, n * nq,
-         bytes_per_pair=m, extra={"binding_limit": "shared-memory table lookups (random 8-byte LDS, ~5.9 wavefronts per warp lookup)"})
+         bytes_per_pair=m, flops=2.0 * n * nq * dim,
+         extra={"tensor_core_filter": {"queries": st1[0] - st0[0], "exact_rerun_queries": st1[1] - st0[1]}})
     ix.close()
 
 

@@ -15,6 +15,7 @@
 #include "vg_quant.cuh"
 #include "vg_scan.cuh"
 #include "vg_flat_tc.cuh"
+#include "vg_quant_tc.cuh"
 
 namespace vg {
 
@@ -153,6 +154,9 @@ struct Index {
     // tensor-core Flat filter state (vg_flat_tc.cu): squared row norms + their maximum, rebuilt after uploads
     DevBuf xn, xmax;
     bool xn_dirty = true;
+    // decode-GEMM filter state of the quantized scans (vg_quant_tc.cu), rebuilt after code uploads
+    qtc::Prepared qtc;
+    bool qtc_dirty = true;
     size_t device_bytes() const {
         return codes.bytes + vectors.bytes + p0.bytes + p1.bytes + norms.bytes + ids.bytes + pq_cb.bytes + centroids.bytes;
     }
@@ -430,6 +434,7 @@ vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const voi
         if (ix->code_row_bytes == 0) return fail(VG_ERR_INVALID, "this index has no code section");
         VG_TRY(place_codes(ix, row0, n, (const uint8_t *)d_codes));
         ix->has_codes = true;
+        ix->qtc_dirty = true;
     }
     if (d_vectors) {
         VG_TRY(ensure_vectors(ix));
@@ -460,6 +465,7 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
             VG_CUDA(cudaStreamSynchronize(stream()));
         }
         ix->has_codes = true;
+        ix->qtc_dirty = true;
     }
     if (h_vectors) {
         VG_TRY(ensure_vectors(ix));
@@ -532,6 +538,44 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     return VG_OK;
 }
 
+// Quantized scans (SQ8 / INT4 / PQ / OPQ) through the tcgen05 decode-GEMM filter (vg_quant_tc.cu): candidates by fp16
+// GEMM over codes decoded inside the kernel, exact re-check in the reference's order, certificate; queries whose
+// certificate fails are re-run on the exact CUDA-core scan.  `d_queries` are already rotated for OPQ.
+static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArgs &a, bool *handled) {
+    *handled = false;
+    const vg_index_desc &d = ix->d;
+    if (!ix->has_codes || !qtc::supported(cp, d.metric, d.rows, a.nq, a.k, d.num_partitions)) return VG_OK;
+    if ((reinterpret_cast<uintptr_t>(a.mask) & 3) != 0) return VG_OK;  // the filter reads the row bitmap as 32-bit words
+    if (a.q_stride != 0 && a.q_stride != d.dim) return VG_OK;
+    cudaStream_t st = stream();
+    if (ix->qtc_dirty || !ix->qtc.ready) {
+        const bool pq = d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ;
+        const size_t np = pq ? (size_t)d.pq_m : (size_t)d.dim;
+        std::vector<float> h0(np), h1(np);
+        VG_CUDA(cudaMemcpyAsync(h0.data(), pq ? ix->pq_scales.p : ix->p0.p, np * 4, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaMemcpyAsync(h1.data(), pq ? ix->pq_offsets.p : ix->p1.p, np * 4, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        VG_TRY(qtc::prepare(cp, d.rows, h0.data(), h1.data(), ix->qtc, st));
+        ix->qtc_dirty = false;
+    }
+    qtc::SearchIO io;
+    io.d_queries = a.queries;
+    io.q_stride = a.q_stride;
+    io.nq = a.nq;
+    io.rows = d.rows;
+    io.d_mask = a.mask;
+    io.k = a.k;
+    io.row_base = a.row_base;
+    io.d_rows = a.out_rows;
+    io.d_scores = a.out_scores;
+    io.d_counts = a.out_counts;
+    std::vector<int32_t> bad;
+    VG_TRY(qtc::search(cp, ix->qtc, io, bad, st));
+    if (!bad.empty()) VG_TRY(scan_topk_subset(cp, a, bad, st));
+    *handled = true;
+    return VG_OK;
+}
+
 static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
                                  const uint8_t *d_mask, uint32_t *d_rows, float *d_scores, int32_t *d_counts) {
     if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
@@ -590,6 +634,14 @@ static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, 
         VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), rotated.as<float>(), st));  // opq.go:196-214
         a.queries = rotated.as<float>();
     }
+    if (d.codec == VG_CODEC_SQ8 || d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ) {
+        bool handled = false;
+        VG_TRY(quant_tc_search(ix, cp, a, &handled));
+        if (handled) {
+            VG_CUDA(cudaStreamSynchronize(st));  // `rotated` is freed on return
+            return VG_OK;
+        }
+    }
     if (d.num_partitions > 1) {
         // kmeans.FindClosestCentroids per query (flat/segment.go:726-745)
         int64_t np = nprobes <= 0 ? 1 : nprobes;
@@ -613,6 +665,11 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
     return search_dev_impl(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts);
+}
+
+vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
+    qtc::stats(queries, fallbacks);
+    return VG_OK;
 }
 
 vg_status vg_flat_tc_enable(int32_t on) {

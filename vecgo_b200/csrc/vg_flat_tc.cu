@@ -54,6 +54,7 @@
 
 #include "vg_flat_tc.cuh"
 #include "vg_scan.cuh"
+#include "vg_tc_ptx.cuh"
 #include "vg_topk.cuh"
 
 namespace vg {
@@ -64,70 +65,6 @@ constexpr int BMQ = 256;   // queries per CTA: two UMMA M halves that share ever
 constexpr int BK = 32;     // floats per k-block: one 128-byte swizzle atom
 constexpr int NTHREADS = 320;
 
-// ------------------------------------------------------------------ PTX
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar)
-        : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major operand tile in shared memory written by TMA with SWIZZLE_128B: row r
-// at r*128 bytes, 8-row groups 1024 bytes apart (SBO); LBO unused for swizzled
-// K-major; descriptor version 1 (sm_100); layout type 2 = SWIZZLE_128B.
-__device__ __forceinline__ uint64_t make_sdesc(uint32_t saddr) {
-    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 // kind::tf32 instruction descriptor: D=f32 (bits 4-5 = 1), A=B=TF32 (2 at bits 7-9 and
 // 10-12), both K-major (bits 15,16 = 0), N>>3 at bits 17-22, M>>4 at bits 24-28.
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
@@ -623,6 +560,35 @@ static vg_status launch(const CUtensorMap &mq, const CUtensorMap &mx, const Args
     return VG_OK;
 }
 
+vg_status select_groups(const float2 *d_mins, int64_t groups, int64_t nq, int kc, int64_t G, float *d_tau, uint32_t *d_cand,
+                        int32_t *d_gcnt, cudaStream_t st) {
+    const int C = topk_capacity(kc, 32);
+    int nw = 8;
+    while (nw > 1 && topk_smem_bytes(nw, C) > 96 * 1024) nw >>= 1;
+    const size_t sm = topk_smem_bytes(nw, C);
+    if (sm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    int g_shift = 0;
+    while ((1ll << g_shift) < G) g_shift++;
+    tc_select_kernel<<<(unsigned)((nq + nw - 1) / nw), nw * 32, sm, st>>>(d_mins, groups, nq, kc, C, (uint32_t)(G - 1), g_shift, d_tau, d_cand,
+                                                                         d_gcnt);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+vg_status tensor_map_2d(void *map, bool f16, const void *base, int64_t rows, int64_t cols, int64_t stride_elems, int box_cols, int box_rows) {
+    VG_TRY(get_encode());
+    const int es = f16 ? 2 : 4;
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride_elems * es};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(reinterpret_cast<CUtensorMap *>(map), f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                                const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VG_ERR_CUDA, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return VG_OK;
+}
+
 int64_t group_rows(int64_t rows, int kc) {
     // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
     // while the exact scan of kc*G rows per query stays ~1% of the GEMM's work
@@ -682,15 +648,7 @@ vg_status filter(const FilterArgs &f, cudaStream_t st) {
         if (f.is_dot) VG_TRY((launch<false, true>(mq, mx, a, qtiles, (int)splits, st)));
         else VG_TRY((launch<false, false>(mq, mx, a, qtiles, (int)splits, st)));
     }
-    {
-        const int C = topk_capacity(f.kc, 32), nw = 8;
-        const size_t sm = topk_smem_bytes(nw, C);
-        int g_shift = 0;
-        while ((1ll << g_shift) < G) g_shift++;
-        tc_select_kernel<<<(unsigned)((f.nq + nw - 1) / nw), nw * 32, sm, st>>>(a.mins, groups, f.nq, f.kc, C, a.idx_mask, g_shift, f.d_tau,
-                                                                                f.d_gids, f.d_gcnt);
-        VG_LAUNCHED();
-    }
+    VG_TRY(select_groups(a.mins, groups, f.nq, f.kc, G, f.d_tau, f.d_gids, f.d_gcnt, st));
     return VG_OK;  // mins is returned to the stream-ordered pool (freed in stream order)
 }
 

@@ -31,6 +31,11 @@ int candidates_for_assign(int64_t rows);
 // out[i] = ||v_i||^2; optional running maximum (as uint bits of a non-negative float).
 vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, int64_t stride, float *d_out, unsigned int *d_max_bits, cudaStream_t st);
 int64_t group_rows(int64_t rows, int kc);  // rows per minimum group for a segment of `rows` rows
+// tau and the kc best groups per query from the [nq][groups] (m1, m2) pairs a GEMM epilogue wrote (shared with vg_quant_tc.cu).
+vg_status select_groups(const float2 *d_mins, int64_t groups, int64_t nq, int kc, int64_t G, float *d_tau, uint32_t *d_cand,
+                        int32_t *d_gcnt, cudaStream_t st);
+// CUtensorMap (`map` points at one) over a row-major [rows][cols] matrix of float32 or float16, 128-byte swizzled boxes.
+vg_status tensor_map_2d(void *map, bool f16, const void *base, int64_t rows, int64_t cols, int64_t stride_elems, int box_cols, int box_rows);
 // TF32 GEMM with group-minimum epilogue → tau and the kc best groups per query.
 vg_status filter(const FilterArgs &f, cudaStream_t st);
 // Exact scores of the candidate rows in simd pair order, top-k by (score,row), certificate → d_fail[q] (1 = re-run exactly).

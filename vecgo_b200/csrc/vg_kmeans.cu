@@ -366,34 +366,77 @@ __global__ void __launch_bounds__(256) gather_centroid_kernel(const float *vecs,
     const int g = t / ds, j = t % ds;
     cent[((int64_t)g * K + c) * ds + j] = vecs[chosen[g] * stride + (int64_t)g * ds + j];
 }
-__global__ void __launch_bounds__(256) pp_dist_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int c,
+// minDistSq update (pq.go:321-330).  One CTA = PP_ROWS samples x all subspaces: consecutive threads read consecutive
+// subspaces of the same sample (whole rows, coalesced), the distances go through a shared-memory transpose and the
+// min-update of mind[g][i0 .. i0+PP_ROWS) is written as contiguous segments.
+constexpr int PP_ROWS = 64;
+__global__ void __launch_bounds__(256) pp_dist_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int G, int c,
                                                       const float *cent, const int *zero, float *mind /*[G][n]*/) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = blockIdx.y;
-    if (i >= n) return;
-    if (c > 0 && zero[g]) return;  // `sum == 0` branch: no distance update (pq.go:306-310)
-    const float d = sql2_pair_thread(vecs + i * stride + (int64_t)g * ds, cent + ((int64_t)g * K + c) * ds, ds);
-    float *m = mind + (int64_t)g * n + i;
-    if (c == 0 || d < *m) *m = d;
+    extern __shared__ float sd[];  // [G][PP_ROWS + 1]
+    const int64_t i0 = (int64_t)blockIdx.x * PP_ROWS;
+    const int pairs = PP_ROWS * G;
+    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+        const int r = p / G, g = p - r * G;
+        const int64_t i = i0 + r;
+        float d = 0.0f;
+        if (i < n) d = sql2_pair_thread(vecs + i * stride + (int64_t)g * ds, cent + ((int64_t)g * K + c) * ds, ds);
+        sd[g * (PP_ROWS + 1) + r] = d;
+    }
+    __syncthreads();
+    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+        const int g = p / PP_ROWS, r = p - g * PP_ROWS;
+        const int64_t i = i0 + r;
+        if (i >= n) continue;
+        if (c > 0 && zero[g]) continue;  // `sum == 0` branch: no distance update (pq.go:306-310)
+        const float d = sd[g * (PP_ROWS + 1) + r];
+        float *m = mind + (int64_t)g * n + i;
+        if (c == 0 || d < *m) *m = d;
+    }
 }
-// One warp per group.  Lane 0 owns the two sequential float32 chains (sum, then the
-// cumulative search); the warp streams mind[] through shared memory for it.
+// One warp per group.  The float32 running sum of pq.go:299-303,327-329 is a sequential chain; the cumulative search
+// of pq.go:314-320 walks the SAME chain, so one pass is enough: the running sum at the start of every PP_TILE-element
+// tile is kept as a checkpoint, the target's tile is the last one whose checkpoint is below the target (the chain is
+// non-decreasing: fl(s + d) >= s for d >= 0) and only that tile is walked again.  All 32 lanes evaluate the identical
+// chain from broadcast 16-byte shared-memory reads while cp.async streams the next tile in, so the cost per element is
+// the dependent-FADD latency.
+constexpr int PP_TILE = 2048;
+__device__ __forceinline__ void pp_load_tile(const float *m, int64_t n, int64_t t, float *dst, int lane) {
+    const int64_t b = t * PP_TILE;
+    for (int j = lane; j < PP_TILE; j += 32) {
+        if (b + j < n) {
+            const uint32_t sa = (uint32_t)__cvta_generic_to_shared(dst + j);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(m + b + j) : "memory");
+        } else {
+            dst[j] = 0.0f;  // fl(s + 0) = s: padding does not change the chain
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
 __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t n, int c, uint64_t seed, int *zero,
-                                                     int64_t *chosen) {
-    __shared__ float buf[1024];
+                                                     int64_t *chosen, float *ckpt /*[G][tiles]*/) {
+    __shared__ __align__(16) float buf[2][PP_TILE];
     const int g = blockIdx.x, lane = threadIdx.x;
     const float *m = mind + (int64_t)g * n;
+    const int64_t tiles = (n + PP_TILE - 1) / PP_TILE;
+    float *ck = ckpt + (int64_t)g * tiles;
     float sum = 0.0f;
-    for (int64_t b = 0; b < n; b += 1024) {
-        for (int j = lane; j < 1024; j += 32) buf[j] = (b + j < n) ? m[b + j] : 0.0f;
+    pp_load_tile(m, n, 0, buf[0], lane);
+    for (int64_t t = 0; t < tiles; t++) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
         __syncwarp();
-        if (lane == 0) {
-            const int cnt = (int)((n - b < 1024) ? (n - b) : 1024);
-            for (int j = 0; j < cnt; j++) sum = __fadd_rn(sum, buf[j]);
+        if (t + 1 < tiles) pp_load_tile(m, n, t + 1, buf[(t + 1) & 1], lane);
+        if (lane == 0) ck[t] = sum;
+        const float4 *b4 = reinterpret_cast<const float4 *>(buf[t & 1]);
+#pragma unroll 8
+        for (int j = 0; j < PP_TILE / 4; j++) {
+            const float4 v = b4[j];
+            sum = __fadd_rn(sum, v.x);
+            sum = __fadd_rn(sum, v.y);
+            sum = __fadd_rn(sum, v.z);
+            sum = __fadd_rn(sum, v.w);
         }
         __syncwarp();
     }
-    sum = __shfl_sync(0xffffffffu, sum, 0);
     if (sum == 0.0f) {
         if (lane == 0) {
             zero[g] = 1;
@@ -402,26 +445,28 @@ __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t 
         return;
     }
     const float target = __fmul_rn(rng_f32(seed, (uint64_t)g, (uint64_t)c), sum);
-    float cum = 0.0f;
-    int64_t pick = 0;
-    int found = 0;
-    for (int64_t b = 0; b < n && !found; b += 1024) {
-        for (int j = lane; j < 1024; j += 32) buf[j] = (b + j < n) ? m[b + j] : 0.0f;
-        __syncwarp();
-        if (lane == 0) {
-            const int cnt = (int)((n - b < 1024) ? (n - b) : 1024);
-            for (int j = 0; j < cnt; j++) {
-                cum = __fadd_rn(cum, buf[j]);
-                if (cum >= target) {
-                    pick = b + j;
-                    found = 1;
-                    break;
-                }
+    __syncwarp();
+    long long bt = 0;
+    for (int64_t t = lane; t < tiles; t += 32)
+        if (ck[t] < target) bt = t;  // t increases per lane: the last hit is the lane's largest
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long other = __shfl_xor_sync(0xffffffffu, bt, o);
+        bt = other > bt ? other : bt;
+    }
+    const int64_t b = (int64_t)bt * PP_TILE;
+    for (int j = lane; j < PP_TILE; j += 32) buf[0][j] = (b + j < n) ? m[b + j] : 0.0f;
+    __syncwarp();
+    if (lane == 0) {
+        const int cnt = (int)((n - b < PP_TILE) ? (n - b) : PP_TILE);
+        float cum = ck[bt];
+        int64_t pick = 0;
+        for (int j = 0; j < cnt; j++) {
+            cum = __fadd_rn(cum, buf[0][j]);
+            if (cum >= target) {
+                pick = b + j;
+                break;
             }
         }
-        found = __shfl_sync(0xffffffffu, found, 0);
-    }
-    if (lane == 0) {
         zero[g] = 0;
         chosen[g] = pick;
     }
@@ -518,7 +563,7 @@ namespace vg {
 vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed, DevBuf &cent,
                        DevBuf &cb, DevBuf &sc, DevBuf &of, cudaStream_t st) {
     const int G = (int)m, K = (int)k, ds = (int)(dim / m);
-    DevBuf mind, zero, chosen, score, cnt;
+    DevBuf mind, zero, chosen, score, cnt, ckpt;
     VG_TRY(cent.alloc((size_t)G * K * ds * 4));
     // ---- initializeCentroids
     if (n < k) {
@@ -529,19 +574,23 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         VG_TRY(mind.alloc((size_t)G * n * 4));
         VG_TRY(zero.alloc((size_t)G * 4));
         VG_TRY(chosen.alloc((size_t)G * 8));
+        VG_TRY(ckpt.alloc((size_t)G * ((n + PP_TILE - 1) / PP_TILE) * 4));
         pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
         VG_LAUNCHED();
-        dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
+        const size_t pp_sm = (size_t)G * (PP_ROWS + 1) * 4;
+        if (pp_sm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(pp_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_sm));
         for (int c = 0; c < K; c++) {
             if (c > 0) {
-                pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>());
+                pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
+                                                 ckpt.as<float>());
                 VG_LAUNCHED();
             }
             gather_centroid_kernel<<<(G * ds + 255) / 256, 256, 0, st>>>(d_vecs, dim, ds, K, G, c, chosen.as<int64_t>(),
                                                                        cent.as<float>());
             VG_LAUNCHED();
             if (c + 1 < K) {
-                pp_dist_kernel<<<gd, 256, 0, st>>>(d_vecs, n, dim, ds, K, c, cent.as<float>(), zero.as<int>(), mind.as<float>());
+                pp_dist_kernel<<<(unsigned)((n + PP_ROWS - 1) / PP_ROWS), 256, pp_sm, st>>>(d_vecs, n, dim, ds, K, G, c, cent.as<float>(),
+                                                                                            zero.as<int>(), mind.as<float>());
                 VG_LAUNCHED();
             }
         }

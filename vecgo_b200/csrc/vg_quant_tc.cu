@@ -1,0 +1,1034 @@
+// vg_quant_tc.cu — the quantized scans (SQ8, INT4 decode-and-scan, PQ/OPQ ADC) as a tcgen05 decode-GEMM *filter*
+// followed by an exact re-check in the reference's own arithmetic.
+//
+// Why.  flat.(*Segment).Search scores every (query,row) pair of a quantized segment with
+// simd.Sq8uL2BatchPerDimension / simd.Int4L2DistanceBatch / simd.PqAdcLookup
+// (internal/segment/flat/segment.go:543-552,603-611; sq8_avx512.c:59-104, int4_avx512.c:193-299,
+// floats_avx512.c:135-167).  All three are  ||q - decode(code)||^2  up to float32 rounding, i.e. a dense
+// Q x N x d contraction  ||x^||^2 - 2 q.x^  once the row is decoded.  A CUDA-core scan that replays the reference's
+// FMA order is bound by the FP32 pipe (SQ8/INT4) or by shared-memory table lookups (PQ) far below what a batch of
+// 10k queries allows.  Here the codes are decoded ONCE per 256-query tile, inside the kernel, into fp16 B tiles in
+// shared memory (never materialised in HBM: the database stays at 1 / 0.5 / 0.125 bytes per dimension), contracted on
+// the tensor cores, and the epilogue keeps per-group minima exactly like the Flat filter (vg_flat_tc.cu).  The few
+// hundred surviving rows per query are then scored in the reference's exact order (AVX-512 lane order, the same
+// fma/rounding sequence, PQ table built by the generic Go loop) and a certificate proves that no other row could
+// have entered the top-k; queries without a proof are re-run on the exact CUDA-core scan.  Result: ids and float32
+// scores bit-identical to the reference path.
+//
+// fp16 operands.  kind::f16 runs at twice the TF32 rate and rounds to nearest with 11 significant bits (TF32
+// truncates to 11).  Range is handled by exact power-of-two scaling: every query is scaled so that max|q_i| is in
+// [2^11, 2^12), the database so that max|x^_i| < 2^12; elements below 2^-14 of that lose absolute (not relative)
+// accuracy, which the bound below accounts for.
+//
+//   s(q,x)   = ||x^||^2 - 2 q.x^                      (the per-query constant ||q||^2 is dropped)
+//   |s_tc - s| <= E = c1 ||q|| max||x^|| + c2 (||q||^2 + max||x^||^2) + 2^-(23-log2 G) max|s|
+//   c1 = 2^-9 * 1.125   (two operands rounded to 2^-11 relative, factor 2 of the L2 form, slack for the cross term
+//                        and the subnormal tail), c2 = 2^-14 + d 2^-23 (norms, fp32 accumulation with truncation),
+//   the last term pays for the log2 G mantissa bits that carry the row index inside its group.
+// The reference's own float32 evaluation differs from the real ||q - x^||^2 by at most (d + 64) 2^-24 relative
+// (non-negative terms), which is added on the exact side of the comparison.
+//
+// Kernel (one CTA per SM = 256 queries x a contiguous row range, 576 threads):
+//   warp 0       TMA producer of the fp16 query k-blocks (256 x 64 halves, 128-byte swizzle)
+//   warp 1       tcgen05.mma.cta_group::1.kind::f16 issuer, M=128 x N=128 x K=16, two M halves per B tile,
+//                fp32 accumulators in TMEM (2 stages x 2 halves x 128 columns)
+//   warps 2-9    epilogue: one thread = one query; s = fma(f_q, acc, ||x^||^2), group (min, second min)
+//   warps 10-17  decode producers, two groups of 128 threads that alternate k-blocks; thread = row: codes -> f32
+//                decode (packed FFMA2) -> fp16 -> 16-byte stores at the swizzled position of the B tile, then
+//                fence.proxy.async + mbarrier arrive.  Loads for the group's next k-block are in flight meanwhile.
+// The code layout on the device is whatever the CUDA-core scan uses (lane-transposed SQ8/INT4, tiled PQ): the
+// contraction does not care about the order of the dimensions, so the QUERY tile is permuted into storage order
+// instead and the producer converts bytes in the order they are stored.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <vector>
+
+#include "vg_flat_tc.cuh"
+#include "vg_quant_tc.cuh"
+#include "vg_tc_ptx.cuh"
+#include "vg_topk.cuh"
+
+namespace vg {
+namespace qtc {
+
+using namespace vg::tc;
+
+constexpr int BM = 128;    // UMMA M
+constexpr int BMQ = 256;   // queries per CTA
+constexpr int BN = 128;    // rows per tile (UMMA N)
+constexpr int BK = 64;     // halves per k-block: one 128-byte swizzle atom
+constexpr int STAGES = 4;
+constexpr int A_KB_BYTES = BMQ * BK * 2;  // 32 KB
+constexpr int B_KB_BYTES = BN * BK * 2;   // 16 KB
+constexpr int STAGE_BYTES = A_KB_BYTES + B_KB_BYTES;
+constexpr int PROD_WARP0 = 10;            // first decode-producer warp
+constexpr int NTHREADS = (PROD_WARP0 + 8) * 32;
+constexpr size_t OFF_XN = (size_t)STAGES * STAGE_BYTES;
+constexpr size_t OFF_PAR = OFF_XN + (size_t)2 * BN * 4;
+constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2;
+constexpr int LIST_CAP = 4096;            // candidate rows per query in the exact stage
+
+// kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = F16 (0 at bits 7-9 / 10-12), both K-major,
+// N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint32_t h2_bits(f32x2 v) {
+    float lo, hi;
+    unpk2(v, lo, hi);
+    const __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct KArgs {
+    const float *xn;        // [rows] ||x^||^2
+    const uint32_t *mask;   // optional row bitmap as 32-bit words
+    const float *fq;        // [nq] -2 / (query scale x database scale)
+    int64_t nq, rows, rows_per_split;
+    int kb;                 // k-blocks = dimp / 64
+    int cpg;                // 32-row chunks per group
+    float2 *mins;           // [nq_pad][groups]
+    int64_t groups;
+    uint32_t idx_mask;
+    // decode
+    const uint8_t *codes;
+    int64_t row_bytes;
+    const float *pscale, *poffset;  // SQ8/INT4: [npar] storage order; PQ: [npar = m]
+    int npar;                       // multiple of 4
+    const int8_t *codebooks;
+    int dsub_shift;                 // PQ: log2(dsub)
+    int tiled;                      // PQ: codes stored in 32-row tiles (permute_pq)
+};
+
+// ------------------------------------------------------------------ decode producers
+// eight decoded values (one 16-byte chunk of the B row) from eight magic floats (8388608 + u): x = fma(u, s, o)
+__device__ __forceinline__ void emit_chunk(uint32_t dst, const float (&mf)[8], const float *ps, const float *po, float bias) {
+    const ulonglong2 s0 = *reinterpret_cast<const ulonglong2 *>(ps), s1 = *reinterpret_cast<const ulonglong2 *>(ps + 4);
+    const ulonglong2 o0 = *reinterpret_cast<const ulonglong2 *>(po), o1 = *reinterpret_cast<const ulonglong2 *>(po + 4);
+    const f32x2 nb = pk2(bias, bias);
+    const uint32_t h0 = h2_bits(fma2(add2(pk2(mf[0], mf[1]), nb), s0.x, o0.x));
+    const uint32_t h1 = h2_bits(fma2(add2(pk2(mf[2], mf[3]), nb), s0.y, o0.y));
+    const uint32_t h2 = h2_bits(fma2(add2(pk2(mf[4], mf[5]), nb), s1.x, o1.x));
+    const uint32_t h3 = h2_bits(fma2(add2(pk2(mf[6], mf[7]), nb), s1.y, o1.y));
+    sts128(dst, h0, h1, h2, h3);
+}
+
+template <int CODEC>
+struct Producer;
+
+// SQ8: 64 stored bytes per k-block.
+template <>
+struct Producer<Q_SQ8> {
+    uint4 w[4];
+    __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(A.codes + row * A.row_bytes + (int64_t)kb * 64);
+#pragma unroll
+        for (int j = 0; j < 4; j++) w[j] = __ldg(p + j);
+    }
+    __device__ __forceinline__ void convert(const KArgs &A, const float *par, int kb, uint32_t dst_row, int swz) const {
+        const float *ps = par + kb * 64, *po = par + A.npar + kb * 64;
+        const uint32_t ww[16] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w,
+                                 w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float mf[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) mf[i] = __uint_as_float(__byte_perm(ww[2 * c + (i >> 2)], 0x4B000000u, 0x7650 + (i & 3)));
+            emit_chunk(dst_row + (uint32_t)((c ^ swz) << 4), mf, ps + 8 * c, po + 8 * c, -8388608.0f);
+        }
+    }
+};
+
+// INT4: 32 stored bytes per k-block; storage position 2j = high nibble of byte j, 2j+1 = low nibble.
+template <>
+struct Producer<Q_INT4> {
+    uint4 w[2];
+    __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
+        const uint4 *p = reinterpret_cast<const uint4 *>(A.codes + row * A.row_bytes + (int64_t)kb * 32);
+        w[0] = __ldg(p);
+        w[1] = __ldg(p + 1);
+    }
+    __device__ __forceinline__ void convert(const KArgs &A, const float *par, int kb, uint32_t dst_row, int swz) const {
+        const float *ps = par + kb * 64, *po = par + A.npar + kb * 64;
+        const uint32_t ww[8] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            float mf[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                mf[2 * i] = __uint_as_float(((ww[c] >> (8 * i + 4)) & 0xFu) | 0x4B000000u);
+                mf[2 * i + 1] = __uint_as_float(((ww[c] >> (8 * i)) & 0xFu) | 0x4B000000u);
+            }
+            emit_chunk(dst_row + (uint32_t)((c ^ swz) << 4), mf, ps + 8 * c, po + 8 * c, -8388608.0f);
+        }
+    }
+};
+
+// PQ: per 16-byte chunk (8 dims) one 8-byte gather from the int8 codebook of its subspace.
+template <>
+struct Producer<Q_PQ> {
+    uint2 g[8];
+    __device__ __forceinline__ static uint2 load_codes(const KArgs &A, int64_t row, int kb) {
+        const int mb = ((kb * 64) >> A.dsub_shift) & ~7;  // 8 codes that cover this k-block's subspaces
+        const uint8_t *p = A.tiled ? A.codes + (row >> 5) * (32 * A.row_bytes) + (int64_t)(mb >> 4) * 512 + (row & 31) * 16 + (mb & 15)
+                                   : A.codes + row * A.row_bytes + mb;
+        return __ldg(reinterpret_cast<const uint2 *>(p));
+    }
+    __device__ __forceinline__ void gather(const KArgs &A, uint2 c8, int kb) {
+        const unsigned long long cw = ((unsigned long long)c8.y << 32) | c8.x;
+        const int mb = ((kb * 64) >> A.dsub_shift) & ~7;
+        const int dsub = 1 << A.dsub_shift;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int d0 = kb * 64 + 8 * c;
+            const int m = d0 >> A.dsub_shift, o = d0 & (dsub - 1);
+            const uint32_t code = (uint32_t)(cw >> (8 * (m - mb))) & 0xFFu;
+            g[c] = __ldg(reinterpret_cast<const uint2 *>(A.codebooks + (((int64_t)m * 256 + code) << A.dsub_shift) + o));
+        }
+    }
+    __device__ __forceinline__ void convert(const KArgs &A, const float *par, int kb, uint32_t dst_row, int swz) const {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int m = (kb * 64 + 8 * c) >> A.dsub_shift;
+            const float s = par[m], o = par[A.npar + m];
+            const uint32_t w0 = g[c].x ^ 0x80808080u, w1 = g[c].y ^ 0x80808080u;  // int8 + 128 as unsigned bytes
+            float mf[8];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                mf[i] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7650 + i));
+                mf[4 + i] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7650 + i));
+            }
+            const f32x2 nb = pk2(-8388736.0f, -8388736.0f), s2 = pk2(s, s), o2 = pk2(o, o);
+            const uint32_t h0 = h2_bits(fma2(add2(pk2(mf[0], mf[1]), nb), s2, o2));
+            const uint32_t h1 = h2_bits(fma2(add2(pk2(mf[2], mf[3]), nb), s2, o2));
+            const uint32_t h2 = h2_bits(fma2(add2(pk2(mf[4], mf[5]), nb), s2, o2));
+            const uint32_t h3 = h2_bits(fma2(add2(pk2(mf[6], mf[7]), nb), s2, o2));
+            sts128(dst_row + (uint32_t)((c ^ swz) << 4), h0, h1, h2, h3);
+        }
+    }
+};
+
+// ------------------------------------------------------------------ GEMM + group minima
+template <int CODEC>
+__global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant__ CUtensorMap map_q, KArgs A) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.x * BMQ;
+    const int split = blockIdx.y;
+    const int64_t row_begin = (int64_t)split * A.rows_per_split;
+    int64_t row_end = row_begin + A.rows_per_split;
+    if (row_end > A.rows) row_end = A.rows;
+    const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + BN - 1) / BN) : 0;
+
+    const uint32_t s_base = smem_u32(smem);
+    float *par = reinterpret_cast<float *>(smem + OFF_PAR);
+    const uint32_t bar0 = s_base + (uint32_t)OFF_PAR + (uint32_t)A.npar * 8u;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
+    constexpr uint32_t TMEM_COLS = 512;
+
+    for (int i = tid; i < A.npar; i += NTHREADS) {
+        par[i] = A.pscale[i];
+        par[A.npar + i] = A.poffset[i];
+    }
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(full_bar(s), 1 + 4);   // TMA (query k-block) + the four warps of one decode group
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 256);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int total_it = ntiles * A.kb;
+
+    if (warp == 0) {
+        // ===================== TMA producer: query k-blocks =====================
+        if (lane == 0) {
+            for (int it = 0; it < total_it; it++) {
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                const int kb = it % A.kb;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                mbar_expect_tx(full_bar(st), A_KB_BYTES);
+                tma_load_2d(s_base + st * STAGE_BYTES, &map_q, kb * BK, q0, full_bar(st));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16(BN);
+            int it = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int as = t & 1;
+                const uint32_t aph = (t >> 1) & 1;
+                mbar_wait(tempty_bar(as), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * 2 * BN);
+                for (int kb = 0; kb < A.kb; kb++, it++) {
+                    const int st = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(full_bar(st), ph);
+                    tc_fence_after();
+                    const uint32_t sa = s_base + st * STAGE_BYTES;
+                    const uint64_t bdesc = make_sdesc(sa + A_KB_BYTES);
+#pragma unroll
+                    for (int h = 0; h < 2; h++) {
+                        const uint64_t adesc = make_sdesc(sa + h * (BM * BK * 2));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; k++)  // 16 halves = 32 bytes per UMMA
+                            umma_f16(d_tmem + (uint32_t)(h * BN), adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc,
+                                     (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(st));
+                }
+                umma_commit(tfull_bar(as));
+            }
+        }
+    } else if (warp < PROD_WARP0) {
+        // ===================== epilogue: warps 2..9, one thread per query =====================
+        const int quad = warp & 3;
+        const int half = (warp - 2) >> 2;
+        const int slot = half * BM + quad * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;
+        const int64_t q = (int64_t)q0 + slot;
+        float *xs = reinterpret_cast<float *>(smem + OFF_XN);
+        const float BIG = 3.0e38f;
+        const float fq = q < A.nq ? __ldg(A.fq + q) : 0.0f;
+        float g1 = BIG, g2 = BIG;
+        int cc = 0;
+        for (int t = 0; t < ntiles; t++) {
+            const int as = t & 1;
+            const uint32_t aph = (t >> 1) & 1;
+            const int64_t n0 = row_begin + (int64_t)t * BN;
+            float *xt = xs + as * BN;
+            if (et < BN) {
+                const int64_t row = n0 + et;
+                xt[et] = (row < row_end) ? __ldg(A.xn + row) : BIG;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * 2 * BN + half * BN);
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                uint32_t mw = 0xFFFFFFFFu;
+                if (A.mask) mw = (n0 + c * 32 < A.rows) ? __ldg(A.mask + ((n0 + c * 32) >> 5)) : 0u;
+                tmem_ld_wait();
+                float s[32];
+                const float4 *x4 = reinterpret_cast<const float4 *>(xt + c * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) {
+                    const float4 xv = x4[j4];
+                    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) s[j4 * 4 + i] = __fmaf_rn(fq, __uint_as_float(v[j4 * 4 + i]), xx[i]);
+                }
+                if (mw != 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
+                }
+                const uint32_t cidx = (uint32_t)(n0 + c * 32) & A.idx_mask;
+                float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const float v1 = __uint_as_float((__float_as_uint(s[j]) & ~A.idx_mask) | (cidx + j));
+                    a2[j & 3] = fminf(a2[j & 3], fmaxf(a1[j & 3], v1));
+                    a1[j & 3] = fminf(a1[j & 3], v1);
+                }
+                const float p1 = fminf(a1[0], a1[1]), p2 = fminf(fmaxf(a1[0], a1[1]), fminf(a2[0], a2[1]));
+                const float r1 = fminf(a1[2], a1[3]), r2 = fminf(fmaxf(a1[2], a1[3]), fminf(a2[2], a2[3]));
+                const float c1 = fminf(p1, r1), c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
+                g2 = fminf(fmaxf(g1, c1), fminf(g2, c2));
+                g1 = fminf(g1, c1);
+                if (++cc == A.cpg) {
+                    const int64_t gid = (n0 + c * 32) / (32 * (int64_t)A.cpg);
+                    if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);
+                    g1 = BIG;
+                    g2 = BIG;
+                    cc = 0;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(as));
+        }
+        if (cc > 0 && ntiles > 0) {
+            const int64_t last_chunk_row = row_begin + (int64_t)ntiles * BN - 32;
+            const int64_t gid = last_chunk_row / (32 * (int64_t)A.cpg);
+            if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);
+        }
+    } else {
+        // ===================== decode producers: warps 10..17, two groups alternating k-blocks =====================
+        const int grp = (warp - PROD_WARP0) >> 2;
+        const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;  // row of the B tile this thread fills
+        const int swz = r & 7;
+        auto row_of = [&](int it) {
+            int64_t row = row_begin + (int64_t)(it / A.kb) * BN + r;
+            return row < A.rows ? row : A.rows - 1;  // padding rows of the last tile: any valid row (masked by xn = BIG)
+        };
+        Producer<CODEC> cur, nxt;
+        if constexpr (CODEC == Q_PQ) {
+            uint2 cnn = make_uint2(0u, 0u);
+            if (grp < total_it) nxt.gather(A, Producer<Q_PQ>::load_codes(A, row_of(grp), grp % A.kb), grp % A.kb);
+            if (grp + 2 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(grp + 2), (grp + 2) % A.kb);
+            for (int it = grp; it < total_it; it += 2) {
+                cur = nxt;
+                if (it + 2 < total_it) nxt.gather(A, cnn, (it + 2) % A.kb);
+                if (it + 4 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(it + 4), (it + 4) % A.kb);
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                cur.convert(A, par, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(st));
+            }
+        } else {
+            if (grp < total_it) nxt.fetch(A, row_of(grp), grp % A.kb);
+            for (int it = grp; it < total_it; it += 2) {
+                cur = nxt;
+                if (it + 2 < total_it) nxt.fetch(A, row_of(it + 2), (it + 2) % A.kb);
+                const int st = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                cur.convert(A, par, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(full_bar(st));
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ query preparation
+// One warp per query: power-of-two scale so that max|q_i| lands in [2^11, 2^12), fp16 conversion in STORAGE order
+// (perm[p] = dimension at storage position p, -1 = padding), f_q = -2 / (query scale x database scale).
+__global__ void __launch_bounds__(256) prep_queries_kernel(const float *queries, int64_t nq, int64_t q_stride, int dimp, const int32_t *perm,
+                                                           int sx_exp, __half *a16, float *fq) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float *qv = queries + q * q_stride;
+    float mx = 0.0f;
+    for (int p = lane; p < dimp; p += 32) {
+        const int d = perm[p];
+        if (d >= 0) mx = fmaxf(mx, fabsf(qv[d]));
+    }
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int e = 0;
+    if (mx > 0.0f && mx < __int_as_float(0x7f800000)) {
+        int ex;
+        frexpf(mx, &ex);  // mx = m * 2^ex, m in [0.5, 1)
+        e = 12 - ex;
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    const float sq = ldexpf(1.0f, e);
+    for (int p = lane; p < dimp; p += 32) {
+        const int d = perm[p];
+        a16[q * dimp + p] = __float2half_rn(d >= 0 ? __fmul_rn(qv[d], sq) : 0.0f);
+    }
+    if (lane == 0) fq[q] = -ldexpf(1.0f, 1 - e - sx_exp);
+}
+
+// ------------------------------------------------------------------ exact decode helpers (reference arithmetic)
+struct EArgs {
+    const uint8_t *codes;
+    int64_t row_bytes;
+    int layout;               // SQ8: 0 row-major | VB of the lane-transposed layout; INT4: 0 | 1 permuted; PQ: 0 | 1 tiled
+    const float *p0, *p1;     // SQ8 mins, invScales | INT4 min, diff (natural dimension order)
+    const int8_t *codebooks;  // PQ
+    const float *pq_scales, *pq_offsets;
+    int pq_m, pq_dsub;
+    int64_t dim, rows;
+    const float *queries;
+    int64_t q_stride;
+    const uint32_t *cand;
+    const int32_t *gcnt;
+    int kc, G;
+    const float *tau, *qn;
+    const unsigned int *xmax_bits;
+    const uint8_t *mask;
+    int k, C;
+    uint32_t row_base;
+    uint32_t *out_rows;
+    float *out_scores;
+    int32_t *out_counts, *fail_flags;
+};
+__device__ __forceinline__ int64_t sq8_off(int64_t d, int vb) {
+    if (vb == 0) return d;
+    const int blk = 16 * vb;
+    const int64_t b = d / blk;
+    const int o = (int)(d - b * blk);
+    return b * blk + (o & 15) * vb + (o >> 4);
+}
+__device__ __forceinline__ int64_t int4_off(int64_t d, int perm) {
+    const int64_t o = d >> 1;
+    if (!perm) return o;
+    const int w = (int)(o & 127);
+    return (o >> 7) * 128 + 16 * (w & 7) + 4 * (w >> 5) + ((w >> 3) & 3);
+}
+__device__ __forceinline__ int64_t pq_off(int64_t row, int m, int64_t row_bytes, int tiled) {
+    return tiled ? (row >> 5) * (32 * row_bytes) + (int64_t)(m >> 4) * 512 + (row & 31) * 16 + (m & 15) : row * row_bytes + m;
+}
+__device__ __forceinline__ float sq8_value(const EArgs &E, const uint8_t *code, int64_t d) {
+    return __fmaf_rn(u8_to_f32(__ldg(code + sq8_off(d, E.layout))), __ldg(E.p1 + d), __ldg(E.p0 + d));
+}
+__device__ __forceinline__ float int4_value(const EArgs &E, const uint8_t *code, int64_t d) {
+    const uint32_t b = __ldg(code + int4_off(d, E.layout));
+    const float nib = u8_to_f32((d & 1) ? (b & 0x0Fu) : (b >> 4));
+    return __fmaf_rn(__fmul_rn(nib, __uint_as_float(0x3d888889u)), __ldg(E.p1 + d), __ldg(E.p0 + d));
+}
+
+// Half-warp score of one row in the reference's order; valid in lane 0.
+template <int CODEC>
+__device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, const float *table, int64_t row, int lane) {
+    const int64_t dim = E.dim;
+    if constexpr (CODEC == Q_SQ8) {
+        // sq8_avx512.c:59-104: one 16-lane accumulator, rec = fma(c, inv, min); diff = q - rec; acc = fma(diff, diff, acc)
+        const uint8_t *code = E.codes + row * E.row_bytes;
+        float acc = 0.0f;
+        int64_t j = 0;
+        for (; j + 16 <= dim; j += 16) {
+            const int64_t d = j + lane;
+            const float df = __fsub_rn(qs[d], sq8_value(E, code, d));
+            acc = __fmaf_rn(df, df, acc);
+        }
+        float tot = reduce16(acc);
+        if (lane == 0)
+            for (int64_t d = j; d < dim; d++) {
+                const float df = __fsub_rn(qs[d], sq8_value(E, code, d));
+                tot = __fmaf_rn(df, df, tot);
+            }
+        return tot;
+    } else if constexpr (CODEC == Q_INT4) {
+        // int4_avx512.c:193-299: S1 takes the first two 16-dim blocks of every 64, S2 the last two; 32-blocks into S1
+        const uint8_t *code = E.codes + row * E.row_bytes;
+        float s1 = 0.0f, s2 = 0.0f;
+        int64_t i = 0;
+        for (; i + 64 <= dim; i += 64) {
+#pragma unroll
+            for (int blk = 0; blk < 4; blk++) {
+                const int64_t d = i + blk * 16 + lane;
+                const float e = __fsub_rn(qs[d], int4_value(E, code, d));
+                if (blk < 2) s1 = __fmaf_rn(e, e, s1);
+                else s2 = __fmaf_rn(e, e, s2);
+            }
+        }
+        for (; i + 32 <= dim; i += 32) {
+#pragma unroll
+            for (int blk = 0; blk < 2; blk++) {
+                const int64_t d = i + blk * 16 + lane;
+                const float e = __fsub_rn(qs[d], int4_value(E, code, d));
+                s1 = __fmaf_rn(e, e, s1);
+            }
+        }
+        float tot = reduce16(__fadd_rn(s1, s2));
+        if (lane == 0)
+            for (int64_t d = i; d < dim; d++) {
+                const float e = __fsub_rn(qs[d], int4_value(E, code, d));
+                tot = __fmaf_rn(e, e, tot);
+            }
+        return tot;
+    } else {
+        // floats_avx512.c:135-167: lane l sums table[(16t+l)*256 + code[16t+l]] over t, reduce, sequential tail
+        const int M = E.pq_m, t16 = M >> 4, tail = M & 15;
+        float s = 0.0f;
+        for (int t = 0; t < t16; t++) {
+            const int m = 16 * t + lane;
+            const uint32_t c = __ldg(E.codes + pq_off(row, m, E.row_bytes, E.layout));
+            s = __fadd_rn(s, table[m * 256 + c]);
+        }
+        float tot = reduce16(s);
+        if (lane == 0)
+            for (int m = t16 * 16; m < t16 * 16 + tail; m++)
+                tot = __fadd_rn(tot, table[m * 256 + __ldg(E.codes + pq_off(row, m, E.row_bytes, E.layout))]);
+        return tot;
+    }
+}
+
+// Exact stage: one CTA per query (see tc_exact_kernel in vg_flat_tc.cu; same candidate list format).
+template <int CODEC>
+__global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
+    float *qs = reinterpret_cast<float *>(smem);
+    const size_t qbytes = ((size_t)E.dim * 4 + 15) & ~(size_t)15;
+    TopK tk = topk_carve(smem + qbytes, 1, E.C, E.k);
+    int32_t *rowlist = reinterpret_cast<int32_t *>(smem + qbytes + topk_smem_bytes(1, E.C));
+    float *table = reinterpret_cast<float *>(rowlist + LIST_CAP);
+    for (int64_t d = tid; d < E.dim; d += 128) qs[d] = E.queries[q * E.q_stride + d];
+    topk_init(tk, 1, tid, 128);
+    __syncthreads();
+    if constexpr (CODEC == Q_PQ) {
+        // simd.BuildDistanceTableInt8, live generic path (kernels.go:354-374): sequential, unfused
+        const int ds = E.pq_dsub;
+        for (int idx = tid; idx < E.pq_m * 256; idx += 128) {
+            const int m = idx >> 8;
+            const int8_t *cb = E.codebooks + (int64_t)idx * ds;
+            const float scale = E.pq_scales[m], offset = E.pq_offsets[m];
+            const float *qv = qs + (int64_t)m * ds;
+            float sum = 0.0f;
+            for (int i = 0; i < ds; i++) {
+                const float v = __fadd_rn(__fmul_rn((float)cb[i], scale), offset);
+                const float d = __fsub_rn(qv[i], v);
+                sum = __fadd_rn(sum, __fmul_rn(d, d));
+            }
+            table[idx] = sum;
+        }
+    }
+    const int ng = E.gcnt[q];
+    const int trigger = E.C - 16;
+    __shared__ int s_total;
+    if (tid == 0) {
+        int n = 0;
+        for (int gi = 0; gi < ng; gi++) n += (E.cand[q * E.kc + gi] & 0x80000000u) ? E.G : 1;
+        s_total = n;
+    }
+    __syncthreads();
+    const bool overflow = s_total > LIST_CAP;
+    if (!overflow) {
+        if (tid < 32) {
+            int off = 0;
+            for (int gi = 0; gi < ng; gi++) {
+                const uint32_t c = E.cand[q * E.kc + gi];
+                if (c & 0x80000000u) {
+                    const int64_t first = (int64_t)(c & 0x7FFFFFFFu) * E.G;
+                    for (int r = tid; r < E.G; r += 32) rowlist[off + r] = (first + r < E.rows) ? (int32_t)(first + r) : -1;
+                    off += E.G;
+                } else {
+                    if (tid == 0) rowlist[off] = ((int64_t)c < E.rows) ? (int32_t)c : -1;
+                    off += 1;
+                }
+            }
+        }
+        __syncthreads();
+        const int total = s_total;
+        for (int r0 = 0; r0 < total; r0 += 16) {
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int r = r0 + hw * 2 + u;
+                int64_t row = (r < total) ? (int64_t)rowlist[r] : -1;
+                if (row >= 0 && E.mask && !((E.mask[row >> 3] >> (row & 7)) & 1)) row = -1;
+                const bool valid = row >= 0;
+                const float tot = exact_score<CODEC>(E, qs, table, valid ? row : 0, lane);
+                if (lane == 0 && valid) topk_offer(tk, 0, make_key(tot, E.row_base + (uint32_t)row, false), trigger);
+            }
+            __syncthreads();
+            topk_block_maintain(tk, 1, tid, 128);
+        }
+    }
+    __syncthreads();
+    if (tid < 32) {
+        topk_emit_warp(tk, 0, tid, false, E.out_rows + q * E.k, E.out_scores + q * E.k, E.out_counts + q, E.k);
+        __syncwarp();
+        if (tid == 0) {
+            const int m = tk.cnt[0];
+            int fail = overflow ? 1 : 0;
+            const float t = E.tau[q];
+            if (!overflow && t < __int_as_float(0x7f800000)) {
+                if (m < E.k) {
+                    fail = 1;
+                } else {
+                    const double qq = (double)E.qn[q], xx = (double)__uint_as_float(*E.xmax_bits);
+                    const double c1 = 1.125 / 512.0, c2 = 1.0 / 16384.0 + (double)E.dim / 8388608.0;
+                    const double smax = xx + 2.0 * sqrt(qq * xx);
+                    const double Eb = c1 * sqrt(qq * xx) + c2 * (qq + xx) + smax * (double)E.G / 8388608.0;
+                    const double eref = ((double)E.dim + 64.0) / 16777216.0;  // the reference's own float32 summation
+                    const double ex = (double)E.out_scores[q * E.k + (E.k - 1)];
+                    // an unscored row has true distance > tau - Eb + ||q||^2 and a reference score >= (1 - eref) of that
+                    if (!(ex < ((double)t - Eb + qq) * (1.0 - eref) - eref * qq)) fail = 1;
+                }
+            }
+            E.fail_flags[q] = fail;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ ||decode(row)||^2
+// One thread per row, eight interleaved float32 accumulators (the value only feeds the filter and its bound).
+template <int CODEC>
+__global__ void __launch_bounds__(128) code_norms_kernel(EArgs E, float *xn, unsigned int *max_bits) {
+    const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= E.rows) return;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if constexpr (CODEC == Q_PQ) {
+        const int ds = E.pq_dsub;
+        for (int m = 0; m < E.pq_m; m++) {
+            const uint32_t c = __ldg(E.codes + pq_off(row, m, E.row_bytes, E.layout));
+            const int8_t *cb = E.codebooks + ((int64_t)m * 256 + c) * ds;
+            const float scale = __ldg(E.pq_scales + m), offset = __ldg(E.pq_offsets + m);
+            for (int i = 0; i < ds; i++) {
+                const float v = __fadd_rn(__fmul_rn((float)cb[i], scale), offset);
+                acc[i & 7] = __fmaf_rn(v, v, acc[i & 7]);
+            }
+        }
+    } else {
+        const uint8_t *code = E.codes + row * E.row_bytes;
+        for (int64_t d = 0; d < E.dim; d++) {
+            const float v = CODEC == Q_SQ8 ? sq8_value(E, code, d) : int4_value(E, code, d);
+            acc[d & 7] = __fmaf_rn(v, v, acc[d & 7]);
+        }
+    }
+    const float a = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3])),
+                              __fadd_rn(__fadd_rn(acc[4], acc[5]), __fadd_rn(acc[6], acc[7])));
+    xn[row] = a;
+    atomicMax(max_bits, __float_as_uint(a));
+}
+
+// ------------------------------------------------------------------ host
+static int q_codec(const CodecParams &cp) {
+    switch (cp.codec) {
+        case VG_CODEC_SQ8: return Q_SQ8;
+        case VG_CODEC_INT4: return Q_INT4;
+        case VG_CODEC_PQ:
+        case VG_CODEC_OPQ: return Q_PQ;
+        default: return -1;
+    }
+}
+static int layout_of(const CodecParams &cp) {
+    const bool perm = (cp.variant & VG_VAR_PERM) != 0;
+    switch (cp.codec) {
+        case VG_CODEC_SQ8: return perm ? (cp.dim % 256 == 0 ? 16 : 4) : 0;
+        default: return perm ? 1 : 0;
+    }
+}
+
+static std::atomic<int> g_enabled{-1};
+static std::atomic<uint64_t> g_queries{0}, g_fallbacks{0};
+static bool enabled() {
+    int v = g_enabled.load();
+    if (v < 0) {
+        const char *e = getenv("VECGO_QUANT_TC");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_enabled.store(v);
+    }
+    return v != 0 && tc::enabled();
+}
+void stats(uint64_t *queries, uint64_t *fallbacks) {
+    if (queries) *queries = g_queries.load();
+    if (fallbacks) *fallbacks = g_fallbacks.load();
+}
+
+bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int64_t k, int64_t num_partitions) {
+    if (!enabled() || num_partitions > 1) return false;
+    if (rows < 8192 || rows >= (1ll << 31) || nq < 16 || k < 1 || k > 128) return false;
+    if (cp.dim % 64 != 0 || cp.dim < 64 || cp.dim > 2048) return false;
+    if ((reinterpret_cast<uintptr_t>(cp.codes) & 15) != 0) return false;
+    switch (cp.codec) {
+        case VG_CODEC_SQ8:
+            return metric == VG_METRIC_L2 && !(cp.variant & VG_VAR_GO_SCALAR);
+        case VG_CODEC_INT4:
+            return true;  // Int4 scores are L2 distances whatever the segment metric
+        case VG_CODEC_PQ:
+        case VG_CODEC_OPQ: {
+            if (metric != VG_METRIC_L2 || cp.pq_k != 256 || cp.pq_tables) return false;
+            const int ds = cp.pq_dsub;
+            if (ds != 8 && ds != 16 && ds != 32 && ds != 64) return false;
+            return (cp.variant & VG_VAR_PERM) || cp.pq_m % 8 == 0;
+        }
+        default:
+            return false;
+    }
+}
+
+static EArgs eargs_of(const CodecParams &cp, int64_t rows) {
+    EArgs e{};
+    e.codes = cp.codes;
+    e.row_bytes = cp.row_bytes;
+    e.layout = layout_of(cp);
+    e.p0 = cp.p0;
+    e.p1 = cp.p1;
+    e.codebooks = cp.pq_codebooks;
+    e.pq_scales = cp.pq_scales;
+    e.pq_offsets = cp.pq_offsets;
+    e.pq_m = cp.pq_m;
+    e.pq_dsub = cp.pq_dsub;
+    e.dim = cp.dim;
+    e.rows = rows;
+    return e;
+}
+
+vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const float *h_p1, Prepared &pp, cudaStream_t st) {
+    const int qc = q_codec(cp);
+    if (qc < 0) return fail(VG_ERR_UNSUPPORTED, "codec has no tensor-core filter");
+    const int dim = (int)cp.dim, dimp = (dim + 63) / 64 * 64;
+    const int layout = layout_of(cp);
+    // storage position -> dimension
+    std::vector<int32_t> perm((size_t)dimp, -1);
+    if (qc == Q_SQ8) {
+        for (int d = 0; d < dim; d++) {
+            int p = d;
+            if (layout) {
+                const int blk = 16 * layout, b = d / blk, o = d % blk;
+                p = b * blk + (o & 15) * layout + (o >> 4);
+            }
+            perm[(size_t)p] = d;
+        }
+    } else if (qc == Q_INT4) {
+        for (int d = 0; d < dim; d++) {
+            int o = d >> 1;
+            if (layout) {
+                const int w = o & 127;
+                o = (o >> 7) * 128 + 16 * (w & 7) + 4 * (w >> 5) + ((w >> 3) & 3);
+            }
+            perm[(size_t)(2 * o + (d & 1))] = d;  // high nibble (even dim) first
+        }
+    } else {
+        for (int d = 0; d < dim; d++) perm[(size_t)d] = d;
+    }
+    // database scale: max |decode| over the parameter box
+    double maxabs = 0.0;
+    const int np = qc == Q_PQ ? cp.pq_m : dim;
+    for (int i = 0; i < np; i++) {
+        double lo, hi;
+        if (qc == Q_SQ8) {
+            lo = h_p0[i];
+            hi = (double)h_p0[i] + 255.0 * (double)h_p1[i];
+        } else if (qc == Q_INT4) {
+            lo = h_p0[i];
+            hi = (double)h_p0[i] + (double)h_p1[i];
+        } else {
+            lo = (double)h_p1[i] - 128.0 * std::fabs((double)h_p0[i]);
+            hi = (double)h_p1[i] + 128.0 * std::fabs((double)h_p0[i]);
+        }
+        maxabs = std::max(maxabs, std::max(std::fabs(lo), std::fabs(hi)));
+    }
+    int sx_exp = 0;
+    if (maxabs > 0.0 && std::isfinite(maxabs)) {
+        int ex;
+        std::frexp(maxabs, &ex);  // maxabs = m 2^ex, m in [0.5, 1)
+        sx_exp = std::min(60, std::max(-60, 12 - ex));
+    }
+    const float sx = std::ldexp(1.0f, sx_exp);
+    const int npar = qc == Q_PQ ? (np + 3) / 4 * 4 : dimp;
+    std::vector<float> ps((size_t)npar, 0.0f), po((size_t)npar, 0.0f);
+    if (qc == Q_PQ) {
+        for (int m = 0; m < np; m++) {
+            ps[(size_t)m] = h_p0[m] * sx;
+            po[(size_t)m] = h_p1[m] * sx;
+        }
+    } else {
+        const float k15 = 1.0f / 15.0f;
+        for (int p = 0; p < dimp; p++) {
+            const int d = perm[(size_t)p];
+            if (d < 0) continue;
+            ps[(size_t)p] = (qc == Q_INT4 ? h_p1[d] * k15 : h_p1[d]) * sx;
+            po[(size_t)p] = h_p0[d] * sx;
+        }
+    }
+    VG_TRY(pp.perm.alloc((size_t)dimp * 4));
+    VG_TRY(pp.pscale.alloc((size_t)npar * 4));
+    VG_TRY(pp.poffset.alloc((size_t)npar * 4));
+    VG_TRY(pp.xn.alloc((size_t)std::max<int64_t>(rows, 1) * 4));
+    VG_TRY(pp.xmax.alloc(16));
+    VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
+    VG_CUDA(cudaMemcpyAsync(pp.pscale.p, ps.data(), (size_t)npar * 4, cudaMemcpyHostToDevice, st));
+    VG_CUDA(cudaMemcpyAsync(pp.poffset.p, po.data(), (size_t)npar * 4, cudaMemcpyHostToDevice, st));
+    VG_CUDA(cudaMemsetAsync(pp.xmax.p, 0, 16, st));
+    EArgs e = eargs_of(cp, rows);
+    const unsigned blocks = (unsigned)((rows + 127) / 128);
+    if (rows > 0) {
+        if (qc == Q_SQ8) code_norms_kernel<Q_SQ8><<<blocks, 128, 0, st>>>(e, pp.xn.as<float>(), pp.xmax.as<unsigned int>());
+        else if (qc == Q_INT4) code_norms_kernel<Q_INT4><<<blocks, 128, 0, st>>>(e, pp.xn.as<float>(), pp.xmax.as<unsigned int>());
+        else code_norms_kernel<Q_PQ><<<blocks, 128, 0, st>>>(e, pp.xn.as<float>(), pp.xmax.as<unsigned int>());
+        VG_LAUNCHED();
+    }
+    VG_CUDA(cudaStreamSynchronize(st));  // the host vectors above are read by the async copies
+    pp.dimp = dimp;
+    pp.sx_exp = sx_exp;
+    pp.ready = true;
+    return VG_OK;
+}
+
+static int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }
+
+template <int CODEC>
+static vg_status launch_gemm(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st) {
+    const size_t sm = OFF_PAR + (size_t)a.npar * 8 + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024;
+    if (sm > 227 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the decode-GEMM filter");
+    VG_CUDA(cudaFuncSetAttribute(qtc_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid((unsigned)qtiles, (unsigned)splits);
+    qtc_kernel<CODEC><<<grid, NTHREADS, sm, st>>>(mq, a);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+template <int CODEC>
+static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
+    const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)LIST_CAP * 4 +
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : 0);
+    if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
+    VG_CUDA(cudaFuncSetAttribute(qtc_exact_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    qtc_exact_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+// One chunk of queries through filter, select and exact stage.
+static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st) {
+    const int qc = q_codec(cp);
+    const int64_t nq = io.nq, rows = io.rows;
+    const int64_t q_stride = io.q_stride ? io.q_stride : cp.dim;
+    const int64_t qtiles = (nq + BMQ - 1) / BMQ, nq_pad = qtiles * BMQ;
+    const int64_t G = tc::group_rows(rows, kc);
+    const int64_t groups = (rows + G - 1) / G;
+    DevBuf a16, fq, qn, mins, gids, gcnt, tau;
+    VG_TRY(a16.alloc((size_t)nq * pp.dimp * 2));
+    VG_TRY(fq.alloc((size_t)nq * 4));
+    VG_TRY(qn.alloc((size_t)nq * 4));
+    VG_TRY(mins.alloc((size_t)groups * nq_pad * 8));
+    VG_TRY(gids.alloc((size_t)nq * kc * 4));
+    VG_TRY(gcnt.alloc((size_t)nq * 4));
+    VG_TRY(tau.alloc((size_t)nq * 4));
+    VG_TRY(tc::sqnorms(io.d_queries, nq, cp.dim, q_stride, qn.as<float>(), nullptr, st));
+    prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.sx_exp,
+                                                                          a16.as<__half>(), fq.as<float>());
+    VG_LAUNCHED();
+    CUtensorMap mq;
+    VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, BMQ));
+    // row splits: one CTA per SM, whole waves
+    const int64_t unit = std::max<int64_t>(BN, G);
+    const int64_t sms = sm_count();
+    const int64_t max_splits = std::max<int64_t>(1, rows / (4 * unit));
+    int64_t splits = 1;
+    double best = 0.0;
+    for (int64_t s_ = 1; s_ <= sms && s_ <= max_splits; s_++) {
+        const int64_t ctas = qtiles * s_, waves = (ctas + sms - 1) / sms;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff > best + 0.02) {
+            best = eff;
+            splits = s_;
+        }
+        if (eff >= 0.97) break;
+    }
+    int64_t rps = (rows + splits - 1) / splits;
+    rps = (rps + unit - 1) / unit * unit;
+    splits = (rows + rps - 1) / rps;
+    KArgs a{};
+    a.xn = pp.xn.as<float>();
+    a.mask = reinterpret_cast<const uint32_t *>(io.d_mask);
+    a.fq = fq.as<float>();
+    a.nq = nq;
+    a.rows = rows;
+    a.rows_per_split = rps;
+    a.kb = pp.dimp / BK;
+    a.cpg = (int)(G / 32);
+    a.mins = mins.as<float2>();
+    a.groups = groups;
+    a.idx_mask = (uint32_t)(G - 1);
+    a.codes = cp.codes;
+    a.row_bytes = cp.row_bytes;
+    a.pscale = pp.pscale.as<float>();
+    a.poffset = pp.poffset.as<float>();
+    a.npar = (int)(pp.pscale.bytes / 4);
+    a.codebooks = cp.pq_codebooks;
+    a.dsub_shift = 0;
+    while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
+    a.tiled = (qc == Q_PQ && (cp.variant & VG_VAR_PERM)) ? 1 : 0;
+    if (qc == Q_SQ8) VG_TRY(launch_gemm<Q_SQ8>(mq, a, qtiles, (int)splits, st));
+    else if (qc == Q_INT4) VG_TRY(launch_gemm<Q_INT4>(mq, a, qtiles, (int)splits, st));
+    else VG_TRY(launch_gemm<Q_PQ>(mq, a, qtiles, (int)splits, st));
+    VG_TRY(tc::select_groups(a.mins, groups, nq, kc, G, tau.as<float>(), gids.as<uint32_t>(), gcnt.as<int32_t>(), st));
+    EArgs e = eargs_of(cp, rows);
+    e.queries = io.d_queries;
+    e.q_stride = q_stride;
+    e.cand = gids.as<uint32_t>();
+    e.gcnt = gcnt.as<int32_t>();
+    e.kc = kc;
+    e.G = (int)G;
+    e.tau = tau.as<float>();
+    e.qn = qn.as<float>();
+    e.xmax_bits = pp.xmax.as<unsigned int>();
+    e.mask = io.d_mask;
+    e.k = io.k;
+    e.C = topk_capacity(io.k, 16);
+    e.row_base = io.row_base;
+    e.out_rows = io.d_rows;
+    e.out_scores = io.d_scores;
+    e.out_counts = io.d_counts;
+    e.fail_flags = d_fail;
+    if (qc == Q_SQ8) VG_TRY(launch_exact<Q_SQ8>(e, nq, st));
+    else if (qc == Q_INT4) VG_TRY(launch_exact<Q_INT4>(e, nq, st));
+    else VG_TRY(launch_exact<Q_PQ>(e, nq, st));
+    VG_CUDA(cudaStreamSynchronize(st));  // the temporaries above go back to the pool on return
+    return VG_OK;
+}
+
+vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st) {
+    failed.clear();
+    if (!pp.ready) return fail(VG_ERR_STATE, "decode-GEMM filter state was not prepared");
+    const int kc = candidates_for(io.k);
+    const int64_t G = tc::group_rows(io.rows, kc);
+    const int64_t groups = (io.rows + G - 1) / G;
+    // the [queries][groups] minima buffer is kept under 4 GiB: long batches go through in chunks of whole query tiles
+    int64_t chunk = std::max<int64_t>(BMQ, ((4ll << 30) / (groups * 8)) / BMQ * BMQ);
+    DevBuf failb;
+    VG_TRY(failb.alloc((size_t)io.nq * 4));
+    for (int64_t q0 = 0; q0 < io.nq; q0 += chunk) {
+        SearchIO part = io;
+        part.nq = std::min(chunk, io.nq - q0);
+        part.q_stride = io.q_stride ? io.q_stride : cp.dim;
+        part.d_queries = io.d_queries + q0 * part.q_stride;
+        part.d_rows = io.d_rows + q0 * io.k;
+        part.d_scores = io.d_scores + q0 * io.k;
+        part.d_counts = io.d_counts + q0;
+        VG_TRY(search_chunk(cp, pp, part, kc, failb.as<int32_t>() + q0, st));
+    }
+    std::vector<int32_t> h_fail((size_t)io.nq);
+    VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)io.nq * 4, cudaMemcpyDeviceToHost, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    for (int64_t q = 0; q < io.nq; q++)
+        if (h_fail[(size_t)q]) failed.push_back((int32_t)q);
+    g_queries.fetch_add((uint64_t)io.nq);
+    g_fallbacks.fetch_add((uint64_t)failed.size());
+    return VG_OK;
+}
+
+}  // namespace qtc
+}  // namespace vg

@@ -1,0 +1,50 @@
+// vg_quant_tc.cuh — decode-GEMM candidate filter for the quantized scans (SQ8, INT4, PQ/OPQ) on the tcgen05 tensor
+// cores (vg_quant_tc.cu): codes are decoded to fp16 inside the kernel, straight into the swizzled shared-memory
+// B tile, contracted against the fp16 query tile, and the survivors are re-scored exactly in the reference's order.
+#pragma once
+#include <vector>
+
+#include "vg_common.cuh"
+#include "vg_scan.cuh"
+
+namespace vg {
+namespace qtc {
+
+// Per-index state of the filter (built once per index, after its codes were uploaded).
+struct Prepared {
+    DevBuf perm;      // int32 [dimp]: dimension held at storage position p of a code row (-1 = padding)
+    DevBuf pscale;    // float: SQ8/INT4 [dimp] storage order, PQ [m] — decode scale  x 2^sx_exp
+    DevBuf poffset;   // float: same shape — decode offset x 2^sx_exp
+    DevBuf xn;        // float [rows]: ||decode(row)||^2
+    DevBuf xmax;      // uint  [4]: max of xn (float bits)
+    int dimp = 0;     // dim rounded up to a multiple of 64
+    int sx_exp = 0;   // database values are multiplied by 2^sx_exp before the fp16 conversion
+    bool ready = false;
+};
+
+// Shapes the filter handles; everything else stays on the CUDA-core scan.
+bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int64_t k, int64_t num_partitions);
+
+// Builds `pp` for the index described by `cp` (reads the codes: call after the upload).  h_* are host copies of the
+// codec parameters: SQ8 (mins, invScales), INT4 (min, diff), PQ (scales, offsets).
+vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const float *h_p1, Prepared &pp, cudaStream_t st);
+
+struct SearchIO {
+    const float *d_queries = nullptr;  // [nq][dim] float32 (OPQ: already rotated)
+    int64_t q_stride = 0, nq = 0;
+    int64_t rows = 0;
+    const uint8_t *d_mask = nullptr;
+    int k = 0;
+    uint32_t row_base = 0;
+    uint32_t *d_rows = nullptr;   // [nq][k]
+    float *d_scores = nullptr;    // [nq][k]
+    int32_t *d_counts = nullptr;  // [nq]
+};
+// Filter + exact stage + certificate for one batch.  `failed` lists the queries whose certificate did not hold: the
+// caller re-runs those on the exact scan (scan_topk_subset).
+vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st);
+
+void stats(uint64_t *queries, uint64_t *fallbacks);
+
+}  // namespace qtc
+}  // namespace vg
