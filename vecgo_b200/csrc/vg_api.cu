@@ -53,7 +53,7 @@ vg_status ensure_init() {
 // Scratch buffers (per-call temporaries: query copies, partial top-k lists, result staging) come from the device's
 // stream-ordered memory pool — after warm-up an allocation is a pointer bump instead of a 100+ us cudaMalloc/cudaFree
 // pair, which matters for small batches.  Large, long-lived buffers (code / vector sections) use cudaMalloc.
-static const size_t kPoolMaxBytes = 256u << 20;
+static const size_t kPoolMaxBytes = (size_t)4608 << 20;  // includes the <= 4 GiB group-minima buffers of the tensor-core filters
 vg_status DevBuf::alloc(size_t n) {
     release();
     if (n == 0) n = 16;
@@ -247,7 +247,7 @@ vg_status vg_init(int32_t device) {
         VG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = 2ull << 30;  // scratch stays cached in the pool up to 2 GiB
+            uint64_t keep = 6ull << 30;  // scratch stays cached in the pool up to 6 GiB
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         g_device = device;

@@ -15,16 +15,21 @@
 // have entered the top-k; queries without a proof are re-run on the exact CUDA-core scan.  Result: ids and float32
 // scores bit-identical to the reference path.
 //
-// fp16 operands.  kind::f16 runs at twice the TF32 rate and rounds to nearest with 11 significant bits (TF32
-// truncates to 11).  Range is handled by exact power-of-two scaling: every query is scaled so that max|q_i| is in
-// [2^11, 2^12), the database so that max|x^_i| < 2^12; elements below 2^-14 of that lose absolute (not relative)
-// accuracy, which the bound below accounts for.
+// Exact integer B operand.  All three codecs decode as  x^_d = mid_d + w_d * b_d  with a small signed integer b_d
+// (SQ8: code - 128, INT4: nibble - 8, PQ: the int8 codebook entry) and per-dimension constants (SQ8: w = invScale,
+// mid = min + 128 w; INT4: w = diff / 15, mid = min + 8 w; PQ: w = scale_m, mid = offset_m).  So
+//   q.x^ = q.mid + sum_d (q_d w_d) b_d :
+// the B tile holds the integers b_d as fp16 — EXACT, and one PRMT + one HSUB2 per two elements to produce — the
+// weights move to the query side (a_d = fp16(q_d w_d 2^e), e chosen per query so that max|a_d| is in [2^11, 2^12)),
+// and q.mid is a per-query constant c_q.  kind::f16 runs at twice the TF32 rate; only the A operand is rounded.
 //
-//   s(q,x)   = ||x^||^2 - 2 q.x^                      (the per-query constant ||q||^2 is dropped)
-//   |s_tc - s| <= E = c1 ||q|| max||x^|| + c2 (||q||^2 + max||x^||^2) + 2^-(23-log2 G) max|s|
-//   c1 = 2^-9 * 1.125   (two operands rounded to 2^-11 relative, factor 2 of the L2 form, slack for the cross term
-//                        and the subnormal tail), c2 = 2^-14 + d 2^-23 (norms, fp32 accumulation with truncation),
-//   the last term pays for the log2 G mantissa bits that carry the row index inside its group.
+//   s'(q,x)  = ||x^||^2 - 2 sum_d (q_d w_d) b_d          (what the GEMM epilogue ranks; s = s' + c_q, c_q = -2 q.mid)
+//   |s'_tc - s'| <= E = c1 ||q|| max||x^ - mid|| + c2 (||q||^2 + max(||x^||^2, ||x^ - mid||^2))
+//                       + (2^-22 + G 2^-23) max|s'| + 2^-21 ||q|| (||mid|| + max||x^ - mid||)
+//   c1 = 2^-10 * 1.125 (A rounded to 2^-11 relative, factor 2 of the L2 form, slack for the subnormal tail),
+//   c2 = 2^-14 + d 2^-23 (norms, fp32 accumulation with truncation), the third term pays for the log2 G mantissa
+//   bits that carry the row index and the epilogue's own rounding, the last for the few-ulp difference between
+//   mid + w b and the reference's float32 decode (fma(c, inv, min); fma(nib * (1/15), diff, min); c * scale + offset).
 // The reference's own float32 evaluation differs from the real ||q - x^||^2 by at most (d + 64) 2^-24 relative
 // (non-negative terms), which is added on the exact side of the comparison.
 //
@@ -33,9 +38,10 @@
 //   warp 1       tcgen05.mma.cta_group::1.kind::f16 issuer, M=128 x N=128 x K=16, two M halves per B tile,
 //                fp32 accumulators in TMEM (2 stages x 2 halves x 128 columns)
 //   warps 2-9    epilogue: one thread = one query; s = fma(f_q, acc, ||x^||^2), group (min, second min)
-//   warps 10-17  decode producers, two groups of 128 threads that alternate k-blocks; thread = row: codes -> f32
-//                decode (packed FFMA2) -> fp16 -> 16-byte stores at the swizzled position of the B tile, then
-//                fence.proxy.async + mbarrier arrive.  Loads for the group's next k-block are in flight meanwhile.
+//   warps 10-17  decode producers, two groups of 128 threads that alternate k-blocks; thread = row: code bytes ->
+//                fp16 integers (PRMT into 0x64xx = 1024 + byte, HSUB2) -> 16-byte stores at the swizzled position of
+//                the B tile, then fence.proxy.async + mbarrier arrive.  Loads for the group's next k-block are in
+//                flight meanwhile.
 // The code layout on the device is whatever the CUDA-core scan uses (lane-transposed SQ8/INT4, tiled PQ): the
 // contraction does not care about the order of the dimensions, so the QUERY tile is permuted into storage order
 // instead and the producer converts bytes in the order they are stored.
@@ -68,7 +74,8 @@ constexpr int STAGE_BYTES = A_KB_BYTES + B_KB_BYTES;
 constexpr int PROD_WARP0 = 10;            // first decode-producer warp
 constexpr int NTHREADS = (PROD_WARP0 + 8) * 32;
 constexpr size_t OFF_XN = (size_t)STAGES * STAGE_BYTES;
-constexpr size_t OFF_PAR = OFF_XN + (size_t)2 * BN * 4;
+constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
+constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024;  // + slack for the 1024-byte alignment
 constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2;
 constexpr int LIST_CAP = 4096;            // candidate rows per query in the exact stage
 
@@ -76,37 +83,25 @@ constexpr int LIST_CAP = 4096;            // candidate rows per query in the exa
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
-    f32x2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void unpk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-    f32x2 r;
-    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-    return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-    f32x2 r;
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-    return r;
-}
-__device__ __forceinline__ uint32_t h2_bits(f32x2 v) {
-    float lo, hi;
-    unpk2(v, lo, hi);
-    const __half2 h = __floats2half2_rn(lo, hi);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
+// two fp16 integers from two bytes: 0x6400 | u is the half 1024 + u (exact), minus `bias` (packed halves) is exact too
+__device__ __forceinline__ uint32_t hsub2_bits(uint32_t h2, uint32_t bias2) {
+    uint32_t r;
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(h2), "r"(bias2));
+    return r;
+}
+constexpr uint32_t H2_1152 = 0x64806480u;  // (1152, 1152): byte - 128
+constexpr uint32_t H2_1032 = 0x64086408u;  // (1032, 1032): nibble - 8
+// bytes 0,1 / 2,3 of w as (1024 + byte) halves
+__device__ __forceinline__ uint32_t bytes01_h2(uint32_t w) { return __byte_perm(w, 0x64646464u, 0x4140); }
+__device__ __forceinline__ uint32_t bytes23_h2(uint32_t w) { return __byte_perm(w, 0x64646464u, 0x4342); }
 
 struct KArgs {
     const float *xn;        // [rows] ||x^||^2
     const uint32_t *mask;   // optional row bitmap as 32-bit words
-    const float *fq;        // [nq] -2 / (query scale x database scale)
+    const float *fq;        // [nq] -2 / query scale
     int64_t nq, rows, rows_per_split;
     int kb;                 // k-blocks = dimp / 64
     int cpg;                // 32-row chunks per group
@@ -116,30 +111,16 @@ struct KArgs {
     // decode
     const uint8_t *codes;
     int64_t row_bytes;
-    const float *pscale, *poffset;  // SQ8/INT4: [npar] storage order; PQ: [npar = m]
-    int npar;                       // multiple of 4
     const int8_t *codebooks;
-    int dsub_shift;                 // PQ: log2(dsub)
-    int tiled;                      // PQ: codes stored in 32-row tiles (permute_pq)
+    int dsub_shift;         // PQ: log2(dsub)
+    int tiled;              // PQ: codes stored in 32-row tiles (permute_pq)
 };
 
 // ------------------------------------------------------------------ decode producers
-// eight decoded values (one 16-byte chunk of the B row) from eight magic floats (8388608 + u): x = fma(u, s, o)
-__device__ __forceinline__ void emit_chunk(uint32_t dst, const float (&mf)[8], const float *ps, const float *po, float bias) {
-    const ulonglong2 s0 = *reinterpret_cast<const ulonglong2 *>(ps), s1 = *reinterpret_cast<const ulonglong2 *>(ps + 4);
-    const ulonglong2 o0 = *reinterpret_cast<const ulonglong2 *>(po), o1 = *reinterpret_cast<const ulonglong2 *>(po + 4);
-    const f32x2 nb = pk2(bias, bias);
-    const uint32_t h0 = h2_bits(fma2(add2(pk2(mf[0], mf[1]), nb), s0.x, o0.x));
-    const uint32_t h1 = h2_bits(fma2(add2(pk2(mf[2], mf[3]), nb), s0.y, o0.y));
-    const uint32_t h2 = h2_bits(fma2(add2(pk2(mf[4], mf[5]), nb), s1.x, o1.x));
-    const uint32_t h3 = h2_bits(fma2(add2(pk2(mf[6], mf[7]), nb), s1.y, o1.y));
-    sts128(dst, h0, h1, h2, h3);
-}
-
 template <int CODEC>
 struct Producer;
 
-// SQ8: 64 stored bytes per k-block.
+// SQ8: 64 stored bytes per k-block -> code - 128.
 template <>
 struct Producer<Q_SQ8> {
     uint4 w[4];
@@ -148,21 +129,18 @@ struct Producer<Q_SQ8> {
 #pragma unroll
         for (int j = 0; j < 4; j++) w[j] = __ldg(p + j);
     }
-    __device__ __forceinline__ void convert(const KArgs &A, const float *par, int kb, uint32_t dst_row, int swz) const {
-        const float *ps = par + kb * 64, *po = par + A.npar + kb * 64;
+    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
         const uint32_t ww[16] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w,
                                  w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w};
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            float mf[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) mf[i] = __uint_as_float(__byte_perm(ww[2 * c + (i >> 2)], 0x4B000000u, 0x7650 + (i & 3)));
-            emit_chunk(dst_row + (uint32_t)((c ^ swz) << 4), mf, ps + 8 * c, po + 8 * c, -8388608.0f);
-        }
+        for (int c = 0; c < 8; c++)
+            sts128(dst_row + (uint32_t)((c ^ swz) << 4), hsub2_bits(bytes01_h2(ww[2 * c]), H2_1152), hsub2_bits(bytes23_h2(ww[2 * c]), H2_1152),
+                   hsub2_bits(bytes01_h2(ww[2 * c + 1]), H2_1152), hsub2_bits(bytes23_h2(ww[2 * c + 1]), H2_1152));
     }
 };
 
-// INT4: 32 stored bytes per k-block; storage position 2j = high nibble of byte j, 2j+1 = low nibble.
+// INT4: 32 stored bytes per k-block -> nibble - 8.  One 32-bit word = one 16-byte chunk; element order inside the
+// chunk (bytes b0..b3 of the word): b0.lo, b2.lo, b0.hi, b2.hi, b1.lo, b3.lo, b1.hi, b3.hi  (int4_chunk_slot below).
 template <>
 struct Producer<Q_INT4> {
     uint4 w[2];
@@ -171,23 +149,19 @@ struct Producer<Q_INT4> {
         w[0] = __ldg(p);
         w[1] = __ldg(p + 1);
     }
-    __device__ __forceinline__ void convert(const KArgs &A, const float *par, int kb, uint32_t dst_row, int swz) const {
-        const float *ps = par + kb * 64, *po = par + A.npar + kb * 64;
+    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
         const uint32_t ww[8] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w};
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            float mf[8];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                mf[2 * i] = __uint_as_float(((ww[c] >> (8 * i + 4)) & 0xFu) | 0x4B000000u);
-                mf[2 * i + 1] = __uint_as_float(((ww[c] >> (8 * i)) & 0xFu) | 0x4B000000u);
-            }
-            emit_chunk(dst_row + (uint32_t)((c ^ swz) << 4), mf, ps + 8 * c, po + 8 * c, -8388608.0f);
+            const uint32_t v = ww[c];
+            sts128(dst_row + (uint32_t)((c ^ swz) << 4), hsub2_bits((v & 0x000F000Fu) | 0x64006400u, H2_1032),
+                   hsub2_bits(((v >> 4) & 0x000F000Fu) | 0x64006400u, H2_1032), hsub2_bits(((v >> 8) & 0x000F000Fu) | 0x64006400u, H2_1032),
+                   hsub2_bits(((v >> 12) & 0x000F000Fu) | 0x64006400u, H2_1032));
         }
     }
 };
 
-// PQ: per 16-byte chunk (8 dims) one 8-byte gather from the int8 codebook of its subspace.
+// PQ: per 16-byte chunk (8 dims) one 8-byte gather from the int8 codebook of its subspace -> the int8 value.
 template <>
 struct Producer<Q_PQ> {
     uint2 g[8];
@@ -209,24 +183,12 @@ struct Producer<Q_PQ> {
             g[c] = __ldg(reinterpret_cast<const uint2 *>(A.codebooks + (((int64_t)m * 256 + code) << A.dsub_shift) + o));
         }
     }
-    __device__ __forceinline__ void convert(const KArgs &A, const float *par, int kb, uint32_t dst_row, int swz) const {
+    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-            const int m = (kb * 64 + 8 * c) >> A.dsub_shift;
-            const float s = par[m], o = par[A.npar + m];
             const uint32_t w0 = g[c].x ^ 0x80808080u, w1 = g[c].y ^ 0x80808080u;  // int8 + 128 as unsigned bytes
-            float mf[8];
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                mf[i] = __uint_as_float(__byte_perm(w0, 0x4B000000u, 0x7650 + i));
-                mf[4 + i] = __uint_as_float(__byte_perm(w1, 0x4B000000u, 0x7650 + i));
-            }
-            const f32x2 nb = pk2(-8388736.0f, -8388736.0f), s2 = pk2(s, s), o2 = pk2(o, o);
-            const uint32_t h0 = h2_bits(fma2(add2(pk2(mf[0], mf[1]), nb), s2, o2));
-            const uint32_t h1 = h2_bits(fma2(add2(pk2(mf[2], mf[3]), nb), s2, o2));
-            const uint32_t h2 = h2_bits(fma2(add2(pk2(mf[4], mf[5]), nb), s2, o2));
-            const uint32_t h3 = h2_bits(fma2(add2(pk2(mf[6], mf[7]), nb), s2, o2));
-            sts128(dst_row + (uint32_t)((c ^ swz) << 4), h0, h1, h2, h3);
+            sts128(dst_row + (uint32_t)((c ^ swz) << 4), hsub2_bits(bytes01_h2(w0), H2_1152), hsub2_bits(bytes23_h2(w0), H2_1152),
+                   hsub2_bits(bytes01_h2(w1), H2_1152), hsub2_bits(bytes23_h2(w1), H2_1152));
         }
     }
 };
@@ -246,18 +208,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
     const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + BN - 1) / BN) : 0;
 
     const uint32_t s_base = smem_u32(smem);
-    float *par = reinterpret_cast<float *>(smem + OFF_PAR);
-    const uint32_t bar0 = s_base + (uint32_t)OFF_PAR + (uint32_t)A.npar * 8u;
+    const uint32_t bar0 = s_base + (uint32_t)OFF_BAR;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
     auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
     auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + 2 + s); };
     constexpr uint32_t TMEM_COLS = 512;
 
-    for (int i = tid; i < A.npar; i += NTHREADS) {
-        par[i] = A.pscale[i];
-        par[A.npar + i] = A.poffset[i];
-    }
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(full_bar(s), 1 + 4);   // TMA (query k-block) + the four warps of one decode group
@@ -418,7 +375,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
-                cur.convert(A, par, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
+                cur.convert(A, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(st));
@@ -431,7 +388,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
-                cur.convert(A, par, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
+                cur.convert(A, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(st));
@@ -447,20 +404,28 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
 }
 
 // ------------------------------------------------------------------ query preparation
-// One warp per query: power-of-two scale so that max|q_i| lands in [2^11, 2^12), fp16 conversion in STORAGE order
-// (perm[p] = dimension at storage position p, -1 = padding), f_q = -2 / (query scale x database scale).
+// One warp per query.  a_p = fp16(q[perm[p]] * w[p] * 2^e) in STORAGE order (perm[p] = dimension at storage position p,
+// -1 = padding; w[p] = decode weight of that dimension), e such that max|a_p| lands in [2^11, 2^12);
+// f_q = -2 / 2^e;  c_q = -2 q.mid (float64 accumulation).
 __global__ void __launch_bounds__(256) prep_queries_kernel(const float *queries, int64_t nq, int64_t q_stride, int dimp, const int32_t *perm,
-                                                           int sx_exp, __half *a16, float *fq) {
+                                                           const float *wq, const float *midp, __half *a16, float *fq, float *cq) {
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     const float *qv = queries + q * q_stride;
     float mx = 0.0f;
+    double cm = 0.0;
     for (int p = lane; p < dimp; p += 32) {
         const int d = perm[p];
-        if (d >= 0) mx = fmaxf(mx, fabsf(qv[d]));
+        if (d >= 0) {
+            mx = fmaxf(mx, fabsf(__fmul_rn(qv[d], wq[p])));
+            cm += (double)qv[d] * (double)midp[p];
+        }
     }
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cm += __shfl_xor_sync(0xffffffffu, cm, o);
+    }
     int e = 0;
     if (mx > 0.0f && mx < __int_as_float(0x7f800000)) {
         int ex;
@@ -471,9 +436,12 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *queries,
     const float sq = ldexpf(1.0f, e);
     for (int p = lane; p < dimp; p += 32) {
         const int d = perm[p];
-        a16[q * dimp + p] = __float2half_rn(d >= 0 ? __fmul_rn(qv[d], sq) : 0.0f);
+        a16[q * dimp + p] = __float2half_rn(d >= 0 ? __fmul_rn(__fmul_rn(qv[d], wq[p]), sq) : 0.0f);
     }
-    if (lane == 0) fq[q] = -ldexpf(1.0f, 1 - e - sx_exp);
+    if (lane == 0) {
+        fq[q] = -ldexpf(1.0f, 1 - e);
+        cq[q] = (float)(-2.0 * cm);
+    }
 }
 
 // ------------------------------------------------------------------ exact decode helpers (reference arithmetic)
@@ -491,8 +459,9 @@ struct EArgs {
     const uint32_t *cand;
     const int32_t *gcnt;
     int kc, G;
-    const float *tau, *qn;
-    const unsigned int *xmax_bits;
+    const float *tau, *qn, *cq;
+    const unsigned int *xmax_bits;  // [0] max ||x^||^2, [1] max ||x^ - mid||^2 (float bits)
+    float mid_norm;                 // ||mid||
     const uint8_t *mask;
     int k, C;
     uint32_t row_base;
@@ -676,14 +645,18 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
                 if (m < E.k) {
                     fail = 1;
                 } else {
-                    const double qq = (double)E.qn[q], xx = (double)__uint_as_float(*E.xmax_bits);
-                    const double c1 = 1.125 / 512.0, c2 = 1.0 / 16384.0 + (double)E.dim / 8388608.0;
-                    const double smax = xx + 2.0 * sqrt(qq * xx);
-                    const double Eb = c1 * sqrt(qq * xx) + c2 * (qq + xx) + smax * (double)E.G / 8388608.0;
+                    const double qq = (double)E.qn[q], xx = (double)__uint_as_float(E.xmax_bits[0]), bb = (double)__uint_as_float(E.xmax_bits[1]);
+                    const double qn_ = sqrt(qq), bn = sqrt(bb);
+                    const double c1 = 1.125 / 1024.0, c2 = 1.0 / 16384.0 + (double)E.dim / 8388608.0;
+                    const double smax = xx + 2.0 * qn_ * bn;  // |s'| of any row
+                    const double Eb = c1 * qn_ * bn + c2 * (qq + fmax(xx, bb)) + smax * (1.0 / 4194304.0 + (double)E.G / 8388608.0) +
+                                      qn_ * ((double)E.mid_norm + bn) / 2097152.0;
                     const double eref = ((double)E.dim + 64.0) / 16777216.0;  // the reference's own float32 summation
                     const double ex = (double)E.out_scores[q * E.k + (E.k - 1)];
-                    // an unscored row has true distance > tau - Eb + ||q||^2 and a reference score >= (1 - eref) of that
-                    if (!(ex < ((double)t - Eb + qq) * (1.0 - eref) - eref * qq)) fail = 1;
+                    // an unscored row has s' >= tau, i.e. a true distance > tau + c_q - Eb + ||q||^2, and a reference
+                    // score >= (1 - eref) of that
+                    const double lower = (double)t + (double)E.cq[q] - Eb + qq;
+                    if (!(ex < lower * (1.0 - eref) - eref * qq)) fail = 1;
                 }
             }
             E.fail_flags[q] = fail;
@@ -691,13 +664,13 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     }
 }
 
-// ------------------------------------------------------------------ ||decode(row)||^2
-// One thread per row, eight interleaved float32 accumulators (the value only feeds the filter and its bound).
+// ------------------------------------------------------------------ ||decode(row)||^2 and ||decode(row) - mid||^2
+// One thread per row, eight interleaved float32 accumulators (the values only feed the filter and its bound).
 template <int CODEC>
 __global__ void __launch_bounds__(128) code_norms_kernel(EArgs E, float *xn, unsigned int *max_bits) {
     const int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= E.rows) return;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, bcc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if constexpr (CODEC == Q_PQ) {
         const int ds = E.pq_dsub;
         for (int m = 0; m < E.pq_m; m++) {
@@ -705,21 +678,36 @@ __global__ void __launch_bounds__(128) code_norms_kernel(EArgs E, float *xn, uns
             const int8_t *cb = E.codebooks + ((int64_t)m * 256 + c) * ds;
             const float scale = __ldg(E.pq_scales + m), offset = __ldg(E.pq_offsets + m);
             for (int i = 0; i < ds; i++) {
-                const float v = __fadd_rn(__fmul_rn((float)cb[i], scale), offset);
+                const float bw = __fmul_rn((float)cb[i], scale);
+                const float v = __fadd_rn(bw, offset);
                 acc[i & 7] = __fmaf_rn(v, v, acc[i & 7]);
+                bcc[i & 7] = __fmaf_rn(bw, bw, bcc[i & 7]);
             }
         }
     } else {
         const uint8_t *code = E.codes + row * E.row_bytes;
         for (int64_t d = 0; d < E.dim; d++) {
-            const float v = CODEC == Q_SQ8 ? sq8_value(E, code, d) : int4_value(E, code, d);
+            float v, bw;
+            if constexpr (CODEC == Q_SQ8) {
+                v = sq8_value(E, code, d);
+                bw = __fmul_rn(u8_to_f32(__ldg(code + sq8_off(d, E.layout))) - 128.0f, __ldg(E.p1 + d));
+            } else {
+                v = int4_value(E, code, d);
+                const uint32_t b = __ldg(code + int4_off(d, E.layout));
+                const float nib = u8_to_f32((d & 1) ? (b & 0x0Fu) : (b >> 4));
+                bw = __fmul_rn(nib - 8.0f, __fmul_rn(__ldg(E.p1 + d), __uint_as_float(0x3d888889u)));
+            }
             acc[d & 7] = __fmaf_rn(v, v, acc[d & 7]);
+            bcc[d & 7] = __fmaf_rn(bw, bw, bcc[d & 7]);
         }
     }
     const float a = __fadd_rn(__fadd_rn(__fadd_rn(acc[0], acc[1]), __fadd_rn(acc[2], acc[3])),
                               __fadd_rn(__fadd_rn(acc[4], acc[5]), __fadd_rn(acc[6], acc[7])));
+    const float b = __fadd_rn(__fadd_rn(__fadd_rn(bcc[0], bcc[1]), __fadd_rn(bcc[2], bcc[3])),
+                              __fadd_rn(__fadd_rn(bcc[4], bcc[5]), __fadd_rn(bcc[6], bcc[7])));
     xn[row] = a;
     atomicMax(max_bits, __float_as_uint(a));
+    atomicMax(max_bits + 1, __float_as_uint(b));
 }
 
 // ------------------------------------------------------------------ host
@@ -800,7 +788,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     if (qc < 0) return fail(VG_ERR_UNSUPPORTED, "codec has no tensor-core filter");
     const int dim = (int)cp.dim, dimp = (dim + 63) / 64 * 64;
     const int layout = layout_of(cp);
-    // storage position -> dimension
+    // storage position (= position along K of the B tile the producer writes) -> dimension
     std::vector<int32_t> perm((size_t)dimp, -1);
     if (qc == Q_SQ8) {
         for (int d = 0; d < dim; d++) {
@@ -812,65 +800,59 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
             perm[(size_t)p] = d;
         }
     } else if (qc == Q_INT4) {
-        for (int d = 0; d < dim; d++) {
-            int o = d >> 1;
+        // device byte B holds natural byte o (dims 2o high nibble, 2o+1 low nibble); the producer turns the word of
+        // bytes b0..b3 into the chunk  b0.lo b2.lo b0.hi b2.hi b1.lo b3.lo b1.hi b3.hi  (Producer<Q_INT4>::convert)
+        static const int slot_byte[8] = {0, 2, 0, 2, 1, 3, 1, 3}, slot_hi[8] = {0, 0, 1, 1, 0, 0, 1, 1};
+        std::vector<int> nat((size_t)(dim / 2));
+        for (int o = 0; o < dim / 2; o++) {
+            int B = o;
             if (layout) {
                 const int w = o & 127;
-                o = (o >> 7) * 128 + 16 * (w & 7) + 4 * (w >> 5) + ((w >> 3) & 3);
+                B = (o >> 7) * 128 + 16 * (w & 7) + 4 * (w >> 5) + ((w >> 3) & 3);
             }
-            perm[(size_t)(2 * o + (d & 1))] = d;  // high nibble (even dim) first
+            nat[(size_t)B] = o;
+        }
+        for (int p = 0; p < dim; p++) {
+            const int word = p >> 3, e = p & 7;
+            const int o = nat[(size_t)(4 * word + slot_byte[e])];
+            perm[(size_t)p] = 2 * o + (slot_hi[e] ? 0 : 1);  // high nibble = even dimension
         }
     } else {
         for (int d = 0; d < dim; d++) perm[(size_t)d] = d;
     }
-    // database scale: max |decode| over the parameter box
-    double maxabs = 0.0;
-    const int np = qc == Q_PQ ? cp.pq_m : dim;
-    for (int i = 0; i < np; i++) {
-        double lo, hi;
+    // x^_d = mid_d + w_d * b_d with the integer b_d the producer emits
+    std::vector<float> w((size_t)dim), mid((size_t)dim);
+    const float k15 = 1.0f / 15.0f;  // 0x3d888889, the constant of int4_avx512.c
+    for (int d = 0; d < dim; d++) {
         if (qc == Q_SQ8) {
-            lo = h_p0[i];
-            hi = (double)h_p0[i] + 255.0 * (double)h_p1[i];
+            w[(size_t)d] = h_p1[d];
+            mid[(size_t)d] = (float)((double)h_p0[d] + 128.0 * (double)h_p1[d]);
         } else if (qc == Q_INT4) {
-            lo = h_p0[i];
-            hi = (double)h_p0[i] + (double)h_p1[i];
+            w[(size_t)d] = h_p1[d] * k15;
+            mid[(size_t)d] = (float)((double)h_p0[d] + 8.0 * (double)w[(size_t)d]);
         } else {
-            lo = (double)h_p1[i] - 128.0 * std::fabs((double)h_p0[i]);
-            hi = (double)h_p1[i] + 128.0 * std::fabs((double)h_p0[i]);
+            const int m = d / cp.pq_dsub;
+            w[(size_t)d] = h_p0[m];
+            mid[(size_t)d] = h_p1[m];
         }
-        maxabs = std::max(maxabs, std::max(std::fabs(lo), std::fabs(hi)));
     }
-    int sx_exp = 0;
-    if (maxabs > 0.0 && std::isfinite(maxabs)) {
-        int ex;
-        std::frexp(maxabs, &ex);  // maxabs = m 2^ex, m in [0.5, 1)
-        sx_exp = std::min(60, std::max(-60, 12 - ex));
-    }
-    const float sx = std::ldexp(1.0f, sx_exp);
-    const int npar = qc == Q_PQ ? (np + 3) / 4 * 4 : dimp;
-    std::vector<float> ps((size_t)npar, 0.0f), po((size_t)npar, 0.0f);
-    if (qc == Q_PQ) {
-        for (int m = 0; m < np; m++) {
-            ps[(size_t)m] = h_p0[m] * sx;
-            po[(size_t)m] = h_p1[m] * sx;
-        }
-    } else {
-        const float k15 = 1.0f / 15.0f;
-        for (int p = 0; p < dimp; p++) {
-            const int d = perm[(size_t)p];
-            if (d < 0) continue;
-            ps[(size_t)p] = (qc == Q_INT4 ? h_p1[d] * k15 : h_p1[d]) * sx;
-            po[(size_t)p] = h_p0[d] * sx;
-        }
+    std::vector<float> wq((size_t)dimp, 0.0f), midp((size_t)dimp, 0.0f);
+    double mm = 0.0;
+    for (int p = 0; p < dimp; p++) {
+        const int d = perm[(size_t)p];
+        if (d < 0) continue;
+        wq[(size_t)p] = w[(size_t)d];
+        midp[(size_t)p] = mid[(size_t)d];
+        mm += (double)mid[(size_t)d] * (double)mid[(size_t)d];
     }
     VG_TRY(pp.perm.alloc((size_t)dimp * 4));
-    VG_TRY(pp.pscale.alloc((size_t)npar * 4));
-    VG_TRY(pp.poffset.alloc((size_t)npar * 4));
+    VG_TRY(pp.wq.alloc((size_t)dimp * 4));
+    VG_TRY(pp.midp.alloc((size_t)dimp * 4));
     VG_TRY(pp.xn.alloc((size_t)std::max<int64_t>(rows, 1) * 4));
     VG_TRY(pp.xmax.alloc(16));
     VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
-    VG_CUDA(cudaMemcpyAsync(pp.pscale.p, ps.data(), (size_t)npar * 4, cudaMemcpyHostToDevice, st));
-    VG_CUDA(cudaMemcpyAsync(pp.poffset.p, po.data(), (size_t)npar * 4, cudaMemcpyHostToDevice, st));
+    VG_CUDA(cudaMemcpyAsync(pp.wq.p, wq.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
+    VG_CUDA(cudaMemcpyAsync(pp.midp.p, midp.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
     VG_CUDA(cudaMemsetAsync(pp.xmax.p, 0, 16, st));
     EArgs e = eargs_of(cp, rows);
     const unsigned blocks = (unsigned)((rows + 127) / 128);
@@ -882,7 +864,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     }
     VG_CUDA(cudaStreamSynchronize(st));  // the host vectors above are read by the async copies
     pp.dimp = dimp;
-    pp.sx_exp = sx_exp;
+    pp.mid_norm = (float)std::sqrt(mm) * 1.0001f;
     pp.ready = true;
     return VG_OK;
 }
@@ -891,8 +873,7 @@ static int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }
 
 template <int CODEC>
 static vg_status launch_gemm(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st) {
-    const size_t sm = OFF_PAR + (size_t)a.npar * 8 + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024;
-    if (sm > 227 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the decode-GEMM filter");
+    const size_t sm = SMEM_BYTES;
     VG_CUDA(cudaFuncSetAttribute(qtc_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)qtiles, (unsigned)splits);
     qtc_kernel<CODEC><<<grid, NTHREADS, sm, st>>>(mq, a);
@@ -918,17 +899,18 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     const int64_t qtiles = (nq + BMQ - 1) / BMQ, nq_pad = qtiles * BMQ;
     const int64_t G = tc::group_rows(rows, kc);
     const int64_t groups = (rows + G - 1) / G;
-    DevBuf a16, fq, qn, mins, gids, gcnt, tau;
+    DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau;
     VG_TRY(a16.alloc((size_t)nq * pp.dimp * 2));
     VG_TRY(fq.alloc((size_t)nq * 4));
+    VG_TRY(cq.alloc((size_t)nq * 4));
     VG_TRY(qn.alloc((size_t)nq * 4));
     VG_TRY(mins.alloc((size_t)groups * nq_pad * 8));
     VG_TRY(gids.alloc((size_t)nq * kc * 4));
     VG_TRY(gcnt.alloc((size_t)nq * 4));
     VG_TRY(tau.alloc((size_t)nq * 4));
     VG_TRY(tc::sqnorms(io.d_queries, nq, cp.dim, q_stride, qn.as<float>(), nullptr, st));
-    prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.sx_exp,
-                                                                          a16.as<__half>(), fq.as<float>());
+    prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.wq.as<float>(),
+                                                                          pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
     VG_LAUNCHED();
     CUtensorMap mq;
     VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, BMQ));
@@ -964,9 +946,6 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.idx_mask = (uint32_t)(G - 1);
     a.codes = cp.codes;
     a.row_bytes = cp.row_bytes;
-    a.pscale = pp.pscale.as<float>();
-    a.poffset = pp.poffset.as<float>();
-    a.npar = (int)(pp.pscale.bytes / 4);
     a.codebooks = cp.pq_codebooks;
     a.dsub_shift = 0;
     while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
@@ -984,6 +963,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     e.G = (int)G;
     e.tau = tau.as<float>();
     e.qn = qn.as<float>();
+    e.cq = cq.as<float>();
+    e.mid_norm = pp.mid_norm;
     e.xmax_bits = pp.xmax.as<unsigned int>();
     e.mask = io.d_mask;
     e.k = io.k;

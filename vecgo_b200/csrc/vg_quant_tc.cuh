@@ -12,13 +12,13 @@ namespace qtc {
 
 // Per-index state of the filter (built once per index, after its codes were uploaded).
 struct Prepared {
-    DevBuf perm;      // int32 [dimp]: dimension held at storage position p of a code row (-1 = padding)
-    DevBuf pscale;    // float: SQ8/INT4 [dimp] storage order, PQ [m] — decode scale  x 2^sx_exp
-    DevBuf poffset;   // float: same shape — decode offset x 2^sx_exp
+    DevBuf perm;      // int32 [dimp]: dimension held at position p along K of the B tile (-1 = padding)
+    DevBuf wq;        // float [dimp]: decode weight w of that dimension (x^_d = mid_d + w_d b_d, b_d the integer the producer emits)
+    DevBuf midp;      // float [dimp]: mid of that dimension
     DevBuf xn;        // float [rows]: ||decode(row)||^2
-    DevBuf xmax;      // uint  [4]: max of xn (float bits)
+    DevBuf xmax;      // uint  [4]: max ||decode(row)||^2, max ||decode(row) - mid||^2 (float bits)
     int dimp = 0;     // dim rounded up to a multiple of 64
-    int sx_exp = 0;   // database values are multiplied by 2^sx_exp before the fp16 conversion
+    float mid_norm = 0.0f;  // ||mid||
     bool ready = false;
 };
 
