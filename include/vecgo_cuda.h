@@ -236,6 +236,9 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
  * VECGO_QUANT_TC=0 (or vg_flat_tc_enable(0)) forces the CUDA-core scan.  Counters: queries that went through the
  * filter and how many of them needed the exact re-run. */
 vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks);
+/* Measurement aid: enable = 1 brackets every GEMM launch of the filter with a CUDA-event pair on its own stream and
+ * resets the counters, 0 turns that off, < 0 only reads.  Returns the accumulated kernel time (ms) and launches. */
+vg_status vg_quant_tc_profile(int32_t enable, double *gemm_ms, uint64_t *gemm_launches);
 
 /* flat.Open (internal/segment/flat/segment.go:105-342) on the raw file bytes:
  * header decode, optional CRC32C verify, section views, staging to HBM. */

@@ -114,6 +114,7 @@ _SIGS = {
     "vg_flat_tc_enable": [i32],
     "vg_flat_tc_stats": [u64p, u64p],
     "vg_quant_tc_stats": [u64p, u64p],
+    "vg_quant_tc_profile": [i32, C.POINTER(C.c_double), u64p],
     "vg_flat_tc_candidates": [u64, f32p, i64, i64, u32p, i32p, f32p, i64p],
     "vg_flat_open": [u8p, sz, i32, u64p],
     "vg_flat_decode_header": [u8p, sz, C.POINTER(FlatHeader)],

@@ -72,6 +72,18 @@ vg_status DevBuf::alloc(size_t n) {
     bytes = n;
     return VG_OK;
 }
+vg_status DevBuf::alloc_persistent(size_t n) {
+    release();
+    if (n == 0) n = 16;
+    const cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+        p = nullptr;
+        return cuda_fail(e, "cudaMalloc");
+    }
+    pooled = false;
+    bytes = n;
+    return VG_OK;
+}
 void DevBuf::release() {
     if (p) {
         if (pooled) cudaFreeAsync(p, stream());
@@ -247,7 +259,8 @@ vg_status vg_init(int32_t device) {
         VG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = 6ull << 30;  // scratch stays cached in the pool up to 6 GiB
+            uint64_t keep = ~0ull;  // scratch stays cached in the pool (never trimmed at synchronisation points): its size is
+                                    // bounded by what one call needs (<= ~5 GiB for the largest group-minima buffer)
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
         g_device = device;
@@ -337,7 +350,7 @@ vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
             const int64_t nbytes = ((d.dim + 63) / 64) * 8;
             ix->dev_row_bytes = (nbytes + 15) / 16 * 16;
             ix->words32 = (int)(ix->dev_row_bytes / 4);
-            if (d.codec == VG_CODEC_RABITQ) VG_TRY(ix->norms.alloc((size_t)rows * 4));
+            if (d.codec == VG_CODEC_RABITQ) VG_TRY(ix->norms.alloc_persistent((size_t)rows * 4));
             break;
         }
         default:
@@ -346,7 +359,7 @@ vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
     if (ix->code_row_bytes > 0) {
         const bool pq_tiled = (d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ) && (ix->variant & VG_VAR_PERM);
         const int64_t alloc_rows = pq_tiled ? (rows + 31) / 32 * 32 : rows;  // PQ tiles hold 32 rows
-        VG_TRY(ix->codes.alloc((size_t)alloc_rows * ix->dev_row_bytes));
+        VG_TRY(ix->codes.alloc_persistent((size_t)alloc_rows * ix->dev_row_bytes));
         if (pq_tiled) VG_CUDA(cudaMemsetAsync(ix->codes.p, 0, ix->codes.bytes, stream()));
     }
     if (d.num_partitions > 1) {
@@ -420,7 +433,7 @@ static vg_status place_codes(Index *ix, int64_t row0, int64_t n, const uint8_t *
 }
 
 static vg_status ensure_vectors(Index *ix) {
-    if (!ix->vectors.p) VG_TRY(ix->vectors.alloc((size_t)(ix->d.rows > 0 ? ix->d.rows : 1) * ix->d.dim * 4));
+    if (!ix->vectors.p) VG_TRY(ix->vectors.alloc_persistent((size_t)(ix->d.rows > 0 ? ix->d.rows : 1) * ix->d.dim * 4));
     return VG_OK;
 }
 
@@ -482,7 +495,7 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
 static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
     if (!ix->xn_dirty && ix->xn.p) return VG_OK;
     const int64_t rows = ix->d.rows;
-    if (!ix->xn.p) VG_TRY(ix->xn.alloc((size_t)rows * 4));
+    if (!ix->xn.p) VG_TRY(ix->xn.alloc_persistent((size_t)rows * 4));
     if (!ix->xmax.p) VG_TRY(ix->xmax.alloc(16));
     VG_CUDA(cudaMemsetAsync(ix->xmax.p, 0, 16, st));
     VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
@@ -669,6 +682,11 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
 
 vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
     qtc::stats(queries, fallbacks);
+    return VG_OK;
+}
+
+vg_status vg_quant_tc_profile(int32_t enable, double *gemm_ms, uint64_t *gemm_launches) {
+    qtc::profile(enable, gemm_ms, gemm_launches);
     return VG_OK;
 }
 
@@ -1446,7 +1464,7 @@ vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg
         s = vg_index_upload(idx, 0, (int64_t)rows, codes, vec);
         if (s == VG_OK) {
             Index *ix = lookup(idx);
-            s = ix->ids.alloc(rows * 8);
+            s = ix->ids.alloc_persistent(rows * 8);
             if (s == VG_OK) s = staged_h2d(ix->ids.p, f + off_pk, rows * 8);
             if (s == VG_OK) ix->has_ids = true;
         }

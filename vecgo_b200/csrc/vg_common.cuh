@@ -49,7 +49,8 @@ struct DevBuf {
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
-    vg_status alloc(size_t n);
+    vg_status alloc(size_t n);              // per-call scratch: stream-ordered pool (cudaMallocAsync)
+    vg_status alloc_persistent(size_t n);   // long-lived index sections: cudaMalloc, never part of the scratch pool
     void release();
     template <class T> T *as() const { return reinterpret_cast<T *>(p); }
 };

@@ -108,6 +108,7 @@ struct KArgs {
     float2 *mins;           // [nq_pad][groups]
     int64_t groups;
     uint32_t idx_mask;
+    uint32_t keep_hi;       // ~31u (passed in so that (bits & keep_hi) | j compiles to one LOP3 with an immediate j)
     // decode
     const uint8_t *codes;
     int64_t row_bytes;
@@ -119,44 +120,63 @@ struct KArgs {
 // ------------------------------------------------------------------ decode producers
 template <int CODEC>
 struct Producer;
+template <int CODEC>
+struct ProducerBytes;
 
-// SQ8: 64 stored bytes per k-block -> code - 128.
-template <>
-struct Producer<Q_SQ8> {
-    uint4 w[4];
-    __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(A.codes + row * A.row_bytes + (int64_t)kb * 64);
+// SQ8 / INT4: BPR stored bytes of every row per k-block (64 / 32).  A warp fills a slab of 32 tile rows; its global
+// loads are arranged so that LPR = BPR/16 neighbouring lanes read the contiguous BPR bytes of one row and one 16-byte
+// load instruction covers 32/LPR rows (8 / 16 cache lines per instruction instead of 32): thread (lane) holds, for
+// j < LPR, the 16-byte piece (lane % LPR) of slab row  j * (32/LPR) + lane / LPR.
+template <int CODEC>
+struct ProducerBytes {
+    static constexpr int BPR = CODEC == Q_SQ8 ? 64 : 32;
+    static constexpr int LPR = BPR / 16;
+    static constexpr int RPI = 32 / LPR;  // rows per load instruction
+    uint4 w[LPR];
+    // Row pointers of the thread's LPR pieces for one tile (rows past the end are clamped; masked later by xn = BIG).
+    struct Rows {
+        const uint4 *p[LPR];
+        __device__ __forceinline__ void set(const KArgs &A, int64_t slab_row0, int lane) {
 #pragma unroll
-        for (int j = 0; j < 4; j++) w[j] = __ldg(p + j);
-    }
-    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
-        const uint32_t ww[16] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w,
-                                 w[2].x, w[2].y, w[2].z, w[2].w, w[3].x, w[3].y, w[3].z, w[3].w};
+            for (int j = 0; j < LPR; j++) {
+                int64_t row = slab_row0 + j * RPI + lane / LPR;
+                row = row < A.rows ? row : A.rows - 1;
+                p[j] = reinterpret_cast<const uint4 *>(A.codes + row * A.row_bytes) + (lane % LPR);
+            }
+        }
+    };
+    __device__ __forceinline__ void fetch(const Rows &R, int kb) {
 #pragma unroll
-        for (int c = 0; c < 8; c++)
-            sts128(dst_row + (uint32_t)((c ^ swz) << 4), hsub2_bits(bytes01_h2(ww[2 * c]), H2_1152), hsub2_bits(bytes23_h2(ww[2 * c]), H2_1152),
-                   hsub2_bits(bytes01_h2(ww[2 * c + 1]), H2_1152), hsub2_bits(bytes23_h2(ww[2 * c + 1]), H2_1152));
+        for (int j = 0; j < LPR; j++) w[j] = __ldg(R.p[j] + kb * (BPR / 16));
     }
-};
-
-// INT4: 32 stored bytes per k-block -> nibble - 8.  One 32-bit word = one 16-byte chunk; element order inside the
-// chunk (bytes b0..b3 of the word): b0.lo, b2.lo, b0.hi, b2.hi, b1.lo, b3.lo, b1.hi, b3.hi  (int4_chunk_slot below).
-template <>
-struct Producer<Q_INT4> {
-    uint4 w[2];
-    __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
-        const uint4 *p = reinterpret_cast<const uint4 *>(A.codes + row * A.row_bytes + (int64_t)kb * 32);
-        w[0] = __ldg(p);
-        w[1] = __ldg(p + 1);
-    }
-    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
-        const uint32_t ww[8] = {w[0].x, w[0].y, w[0].z, w[0].w, w[1].x, w[1].y, w[1].z, w[1].w};
+    // b_tile: shared address of the 128 x 128-byte B tile; slab: first tile row of this warp's slab
+    __device__ __forceinline__ void convert(uint32_t b_tile, int slab, int lane) const {
+        const int piece = lane % LPR;
 #pragma unroll
-        for (int c = 0; c < 8; c++) {
-            const uint32_t v = ww[c];
-            sts128(dst_row + (uint32_t)((c ^ swz) << 4), hsub2_bits((v & 0x000F000Fu) | 0x64006400u, H2_1032),
-                   hsub2_bits(((v >> 4) & 0x000F000Fu) | 0x64006400u, H2_1032), hsub2_bits(((v >> 8) & 0x000F000Fu) | 0x64006400u, H2_1032),
-                   hsub2_bits(((v >> 12) & 0x000F000Fu) | 0x64006400u, H2_1032));
+        for (int j = 0; j < LPR; j++) {
+            const int r = slab + j * RPI + lane / LPR;
+            const uint32_t dst = b_tile + (uint32_t)r * 128u;
+            const int swz = r & 7;
+            const uint32_t ww[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
+            if constexpr (CODEC == Q_SQ8) {
+                // 16 bytes = chunks 2*piece, 2*piece + 1; code - 128
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    sts128(dst + (uint32_t)(((2 * piece + h) ^ swz) << 4), hsub2_bits(bytes01_h2(ww[2 * h]), H2_1152),
+                           hsub2_bits(bytes23_h2(ww[2 * h]), H2_1152), hsub2_bits(bytes01_h2(ww[2 * h + 1]), H2_1152),
+                           hsub2_bits(bytes23_h2(ww[2 * h + 1]), H2_1152));
+            } else {
+                // 16 bytes = 4 words = chunks 4*piece .. 4*piece + 3; one word = one chunk, element order
+                // b0.lo b2.lo b0.hi b2.hi b1.lo b3.lo b1.hi b3.hi (bytes b0..b3 of the word); nibble - 8
+#pragma unroll
+                for (int h = 0; h < 4; h++) {
+                    const uint32_t v = ww[h];
+                    sts128(dst + (uint32_t)(((4 * piece + h) ^ swz) << 4), hsub2_bits((v & 0x000F000Fu) | 0x64006400u, H2_1032),
+                           hsub2_bits(((v >> 4) & 0x000F000Fu) | 0x64006400u, H2_1032),
+                           hsub2_bits(((v >> 8) & 0x000F000Fu) | 0x64006400u, H2_1032),
+                           hsub2_bits(((v >> 12) & 0x000F000Fu) | 0x64006400u, H2_1032));
+                }
+            }
         }
     }
 };
@@ -292,6 +312,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
         const float fq = q < A.nq ? __ldg(A.fq + q) : 0.0f;
         float g1 = BIG, g2 = BIG;
         int cc = 0;
+        const uint32_t keep_hi = A.keep_hi;  // 0xFFFFFFE0 as a run-time value: stays a register operand of the LOP3s below
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
@@ -325,17 +346,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
 #pragma unroll
                     for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
                 }
-                const uint32_t cidx = (uint32_t)(n0 + c * 32) & A.idx_mask;
+                // the row's position inside the 32-row chunk goes into the low 5 mantissa bits (one LOP3 with an immediate);
+                // the chunk's position inside the group is added to the chunk minimum afterwards (group sizes > 32)
                 float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const float v1 = __uint_as_float((__float_as_uint(s[j]) & ~A.idx_mask) | (cidx + j));
+                    uint32_t vb;  // (bits & ~31) | j as ONE LOP3 (register mask, immediate j)
+                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(vb) : "r"(__float_as_uint(s[j])), "r"(keep_hi), "r"((uint32_t)j));
+                    const float v1 = __uint_as_float(vb);
                     a2[j & 3] = fminf(a2[j & 3], fmaxf(a1[j & 3], v1));
                     a1[j & 3] = fminf(a1[j & 3], v1);
                 }
                 const float p1 = fminf(a1[0], a1[1]), p2 = fminf(fmaxf(a1[0], a1[1]), fminf(a2[0], a2[1]));
                 const float r1 = fminf(a1[2], a1[3]), r2 = fminf(fmaxf(a1[2], a1[3]), fminf(a2[2], a2[3]));
-                const float c1 = fminf(p1, r1), c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
+                const uint32_t cidx = (uint32_t)(n0 + c * 32) & A.idx_mask & ~31u;
+                const float c1 = __uint_as_float((__float_as_uint(fminf(p1, r1)) & ~A.idx_mask) | cidx | (__float_as_uint(fminf(p1, r1)) & 31u));
+                const float c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
                 g2 = fminf(fmaxf(g1, c1), fminf(g2, c2));
                 g1 = fminf(g1, c1);
                 if (++cc == A.cpg) {
@@ -357,38 +383,72 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
     } else {
         // ===================== decode producers: warps 10..17, two groups alternating k-blocks =====================
         const int grp = (warp - PROD_WARP0) >> 2;
-        const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;  // row of the B tile this thread fills
-        const int swz = r & 7;
-        auto row_of = [&](int it) {
-            int64_t row = row_begin + (int64_t)(it / A.kb) * BN + r;
-            return row < A.rows ? row : A.rows - 1;  // padding rows of the last tile: any valid row (masked by xn = BIG)
+        // (tile, k-block) cursor of iteration `it`, advanced by two iterations at a time without divisions
+        struct Cursor {
+            int t, kb;
+            __device__ __forceinline__ void init(int it, int KB) {
+                t = it / KB;
+                kb = it - t * KB;
+            }
+            __device__ __forceinline__ bool advance2(int KB) {  // returns true when the tile changed
+                kb += 2;
+                bool moved = false;
+                while (kb >= KB) {
+                    kb -= KB;
+                    t++;
+                    moved = true;
+                }
+                return moved;
+            }
         };
-        Producer<CODEC> cur, nxt;
         if constexpr (CODEC == Q_PQ) {
+            const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;  // row of the B tile this thread fills
+            const int swz = r & 7;
+            auto row_of = [&](int t) {
+                const int64_t row = row_begin + (int64_t)t * BN + r;
+                return row < A.rows ? row : A.rows - 1;  // padding rows of the last tile: any valid row (masked by xn = BIG)
+            };
+            Producer<Q_PQ> cur, nxt;
             uint2 cnn = make_uint2(0u, 0u);
-            if (grp < total_it) nxt.gather(A, Producer<Q_PQ>::load_codes(A, row_of(grp), grp % A.kb), grp % A.kb);
-            if (grp + 2 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(grp + 2), (grp + 2) % A.kb);
+            Cursor c0, c2, c4;  // iterations it, it + 2, it + 4
+            c0.init(grp, A.kb);
+            c2 = c0;
+            c2.advance2(A.kb);
+            c4 = c2;
+            c4.advance2(A.kb);
+            if (grp < total_it) nxt.gather(A, Producer<Q_PQ>::load_codes(A, row_of(c0.t), c0.kb), c0.kb);
+            if (grp + 2 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(c2.t), c2.kb);
             for (int it = grp; it < total_it; it += 2) {
                 cur = nxt;
-                if (it + 2 < total_it) nxt.gather(A, cnn, (it + 2) % A.kb);
-                if (it + 4 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(it + 4), (it + 4) % A.kb);
+                if (it + 2 < total_it) nxt.gather(A, cnn, c2.kb);
+                if (it + 4 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(c4.t), c4.kb);
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
-                cur.convert(A, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
+                cur.convert(A, c0.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(st));
+                c0 = c2;
+                c2 = c4;
+                c4.advance2(A.kb);
             }
         } else {
-            if (grp < total_it) nxt.fetch(A, row_of(grp), grp % A.kb);
+            const int slab = ((warp - PROD_WARP0) & 3) * 32;  // this warp fills tile rows slab .. slab + 31
+            ProducerBytes<CODEC> cur, nxt;
+            typename ProducerBytes<CODEC>::Rows rows;
+            Cursor c2;  // iteration it + 2 (the one being prefetched)
+            c2.init(grp, A.kb);
+            rows.set(A, row_begin + (int64_t)c2.t * BN + slab, lane);
+            if (grp < total_it) nxt.fetch(rows, c2.kb);
             for (int it = grp; it < total_it; it += 2) {
                 cur = nxt;
-                if (it + 2 < total_it) nxt.fetch(A, row_of(it + 2), (it + 2) % A.kb);
+                if (c2.advance2(A.kb)) rows.set(A, row_begin + (int64_t)c2.t * BN + slab, lane);
+                if (it + 2 < total_it) nxt.fetch(rows, c2.kb);
                 const int st = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
-                cur.convert(A, it % A.kb, s_base + st * STAGE_BYTES + A_KB_BYTES + r * 128, swz);
+                cur.convert(s_base + st * STAGE_BYTES + A_KB_BYTES, slab, lane);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(full_bar(st));
@@ -400,6 +460,329 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ CTA-pair variant (cta_group::2)
+// A cluster of two CTAs (one TPC) shares every MMA: tcgen05.mma.cta_group::2 with M = 256 (CTA r owns queries
+// q0 + 128 r .. + 127 and their accumulators: 128 TMEM lanes x 256 columns) and N = 256 (CTA r decodes rows
+// n0 + 128 r .. + 127 of the 256-row tile into ITS shared memory; the hardware exchanges the B halves).  Per SM the
+// operand traffic of one instruction is 4 KB of A + 4 KB of B for twice the FLOPs of the single-CTA M=128 x N=128
+// instruction, which is what lifts the shared-memory bound of the single-CTA kernel, and each CTA fetches only its
+// 128-query half of the query tile from L2.  Stage = 16 KB A + 16 KB B, six stages.
+//   full[s]   (leader CTA): leader's arrive.expect_tx (both CTAs' TMA bytes land here) + 4 producer warps of each CTA
+//   empty[s]  (both CTAs) : tcgen05.commit multicast
+//   tfull[a]  (both CTAs) : tcgen05.commit multicast;  tempty[a] (leader): 8 epilogue warps of each CTA
+// Row groups are at most 128 rows so that a group lives in one thread (thread = query x 128-column half).
+namespace pair {
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = BM * BK * 2;   // 16 KB: this CTA's 128 queries x 64 halves
+constexpr int B2_BYTES = BN * BK * 2;   // 16 KB: this CTA's 128 rows x 64 halves
+constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr int TILE_ROWS = 2 * BN;       // 256 rows per pair tile
+constexpr size_t OFF_XN2 = (size_t)STAGES2 * STAGE2_BYTES;
+constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)2 * TILE_ROWS * 4;
+constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 4) * 8 + 16 + 1024;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (default semantics, as CUTLASS's
+// ClusterBarrier::arrive(cta_id): an explicit .release.cluster costs a MEMBAR + ERRBAR per arrive — measured 19 % of all
+// stall samples; the data hand-off itself is ordered by fence.proxy.async / tcgen05.fence before the arrive)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(local_bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on the leader CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+// M = 256, N = 256, fp16 operands, fp32 accumulate, K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_f16_pair() { return (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
+}  // namespace pair
+
+template <int CODEC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_kernel(const __grid_constant__ CUtensorMap map_q, KArgs A) {
+    using namespace pair;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int q0 = (int)(blockIdx.x >> 1) * BMQ + (int)rank * BM;  // this CTA's 128 queries
+    const int split = blockIdx.y;
+    const int64_t row_begin = (int64_t)split * A.rows_per_split;
+    int64_t row_end = row_begin + A.rows_per_split;
+    if (row_end > A.rows) row_end = A.rows;
+    const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
+
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar0 = s_base + (uint32_t)OFF_BAR2;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES2 + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES2 + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES2 + 2 + s); };
+    constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages x 256 columns
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; s++) {
+            mbar_init(full_bar(s), 1 + 4 + 4);  // leader's expect_tx arrive + one decode group (4 warps) of each CTA
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 8 + 8);    // epilogue warps of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // both CTAs' barriers are initialised before anyone arrives remotely
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int total_it = ntiles * A.kb;
+
+    if (warp == 0) {
+        // ===================== TMA producer: this CTA's half of the query k-block =====================
+        if (lane == 0) {
+            for (int it = 0; it < total_it; it++) {
+                const int st = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1;
+                const int kb = it % A.kb;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
+                tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_pair();
+            int it = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int as = t & 1;
+                const uint32_t aph = (t >> 1) & 1;
+                mbar_wait_cluster(tempty_bar(as), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_ROWS);
+                for (int kb = 0; kb < A.kb; kb++, it++) {
+                    const int st = it % STAGES2;
+                    const uint32_t ph = (it / STAGES2) & 1;
+                    mbar_wait_cluster(full_bar(st), ph);
+                    tc_fence_after();
+                    const uint32_t sa = s_base + st * STAGE2_BYTES;
+                    const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A2_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; k++)
+                        umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(empty_bar(st));
+                }
+                umma_commit_pair(tfull_bar(as));
+            }
+        }
+    } else if (warp < PROD_WARP0) {
+        // ===================== epilogue: warps 2..9; thread = one query x one 128-column half of the tile =====================
+        const int quad = warp & 3;
+        const int colhalf = (warp - 2) >> 2;
+        const int et = (warp - 2) * 32 + lane;
+        const int64_t q = (int64_t)q0 + quad * 32 + lane;
+        float *xs = reinterpret_cast<float *>(smem + OFF_XN2);
+        const float BIG = 3.0e38f;
+        const float fq = q < A.nq ? __ldg(A.fq + q) : 0.0f;
+        const uint32_t keep_hi = A.keep_hi;
+        float g1 = BIG, g2 = BIG;
+        int cc = 0;
+        for (int t = 0; t < ntiles; t++) {
+            const int as = t & 1;
+            const uint32_t aph = (t >> 1) & 1;
+            const int64_t n0 = row_begin + (int64_t)t * TILE_ROWS;
+            float *xt = xs + as * TILE_ROWS;
+            {
+                const int64_t row = n0 + et;  // 256 epilogue threads stage the 256 row norms of the tile
+                xt[et] = (row < row_end) ? __ldg(A.xn + row) : BIG;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * BN);
+            const int64_t nh = n0 + colhalf * BN;  // first row of this thread's column half
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                uint32_t mw = 0xFFFFFFFFu;
+                if (A.mask) mw = (nh + c * 32 < A.rows) ? __ldg(A.mask + ((nh + c * 32) >> 5)) : 0u;
+                tmem_ld_wait();
+                float s[32];
+                const float4 *x4 = reinterpret_cast<const float4 *>(xt + colhalf * BN + c * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) {
+                    const float4 xv = x4[j4];
+                    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) s[j4 * 4 + i] = __fmaf_rn(fq, __uint_as_float(v[j4 * 4 + i]), xx[i]);
+                }
+                if (mw != 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
+                }
+                float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    uint32_t vb;
+                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(vb) : "r"(__float_as_uint(s[j])), "r"(keep_hi), "r"((uint32_t)j));
+                    const float v1 = __uint_as_float(vb);
+                    a2[j & 3] = fminf(a2[j & 3], fmaxf(a1[j & 3], v1));
+                    a1[j & 3] = fminf(a1[j & 3], v1);
+                }
+                const float p1 = fminf(a1[0], a1[1]), p2 = fminf(fmaxf(a1[0], a1[1]), fminf(a2[0], a2[1]));
+                const float r1 = fminf(a1[2], a1[3]), r2 = fminf(fmaxf(a1[2], a1[3]), fminf(a2[2], a2[3]));
+                const uint32_t cidx = (uint32_t)(nh + c * 32) & A.idx_mask & ~31u;
+                const float c1 = __uint_as_float((__float_as_uint(fminf(p1, r1)) & ~A.idx_mask) | cidx | (__float_as_uint(fminf(p1, r1)) & 31u));
+                const float c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
+                g2 = fminf(fmaxf(g1, c1), fminf(g2, c2));
+                g1 = fminf(g1, c1);
+                if (++cc == A.cpg) {  // groups are <= 128 rows and aligned: they never leave this thread's column half
+                    const int64_t gid = (nh + c * 32) / (32 * (int64_t)A.cpg);
+                    if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);
+                    g1 = BIG;
+                    g2 = BIG;
+                    cc = 0;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
+        }
+    } else {
+        // ===================== decode producers: this CTA's 128 rows of the 256-row tile =====================
+        const int grp = (warp - PROD_WARP0) >> 2;
+        struct Cursor {
+            int t, kb;
+            __device__ __forceinline__ void init(int it, int KB) {
+                t = it / KB;
+                kb = it - t * KB;
+            }
+            __device__ __forceinline__ bool advance2(int KB) {
+                kb += 2;
+                bool moved = false;
+                while (kb >= KB) {
+                    kb -= KB;
+                    t++;
+                    moved = true;
+                }
+                return moved;
+            }
+        };
+        const int64_t half_begin = row_begin + (int64_t)rank * BN;
+        if constexpr (CODEC == Q_PQ) {
+            const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
+            const int swz = r & 7;
+            auto row_of = [&](int t) {
+                const int64_t row = half_begin + (int64_t)t * TILE_ROWS + r;
+                return row < A.rows ? row : A.rows - 1;
+            };
+            Producer<Q_PQ> cur, nxt;
+            uint2 cnn = make_uint2(0u, 0u);
+            Cursor c0, c2, c4;
+            c0.init(grp, A.kb);
+            c2 = c0;
+            c2.advance2(A.kb);
+            c4 = c2;
+            c4.advance2(A.kb);
+            if (grp < total_it) nxt.gather(A, Producer<Q_PQ>::load_codes(A, row_of(c0.t), c0.kb), c0.kb);
+            if (grp + 2 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(c2.t), c2.kb);
+            for (int it = grp; it < total_it; it += 2) {
+                cur = nxt;
+                if (it + 2 < total_it) nxt.gather(A, cnn, c2.kb);
+                if (it + 4 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(c4.t), c4.kb);
+                const int st = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                cur.convert(A, c0.kb, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+                c0 = c2;
+                c2 = c4;
+                c4.advance2(A.kb);
+            }
+        } else {
+            const int slab = ((warp - PROD_WARP0) & 3) * 32;
+            ProducerBytes<CODEC> cur, nxt;
+            typename ProducerBytes<CODEC>::Rows rows;
+            Cursor c2;
+            c2.init(grp, A.kb);
+            rows.set(A, half_begin + (int64_t)c2.t * TILE_ROWS + slab, lane);
+            if (grp < total_it) nxt.fetch(rows, c2.kb);
+            for (int it = grp; it < total_it; it += 2) {
+                cur = nxt;
+                if (c2.advance2(A.kb)) rows.set(A, half_begin + (int64_t)c2.t * TILE_ROWS + slab, lane);
+                if (it + 2 < total_it) nxt.fetch(rows, c2.kb);
+                const int st = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                cur.convert(s_base + st * STAGE2_BYTES + A2_BYTES, slab, lane);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still touch its barriers / shared memory
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -743,6 +1126,24 @@ void stats(uint64_t *queries, uint64_t *fallbacks) {
     if (queries) *queries = g_queries.load();
     if (fallbacks) *fallbacks = g_fallbacks.load();
 }
+// Optional CUDA-event timing of the GEMM kernel on its own stream (bench.py's roofline line).
+static std::atomic<int> g_prof{0};
+static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+static double g_gemm_ms = 0.0;
+static uint64_t g_gemm_launches = 0;
+void profile(int enable, double *gemm_ms, uint64_t *gemm_launches) {
+    if (gemm_ms) *gemm_ms = g_gemm_ms;
+    if (gemm_launches) *gemm_launches = g_gemm_launches;
+    if (enable >= 0) {
+        if (enable && !g_ev[0]) {
+            cudaEventCreate(&g_ev[0]);
+            cudaEventCreate(&g_ev[1]);
+        }
+        g_gemm_ms = 0.0;
+        g_gemm_launches = 0;
+        g_prof.store(enable ? 1 : 0);
+    }
+}
 
 bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int64_t k, int64_t num_partitions) {
     if (!enabled() || num_partitions > 1) return false;
@@ -848,7 +1249,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     VG_TRY(pp.perm.alloc((size_t)dimp * 4));
     VG_TRY(pp.wq.alloc((size_t)dimp * 4));
     VG_TRY(pp.midp.alloc((size_t)dimp * 4));
-    VG_TRY(pp.xn.alloc((size_t)std::max<int64_t>(rows, 1) * 4));
+    VG_TRY(pp.xn.alloc_persistent((size_t)std::max<int64_t>(rows, 1) * 4));
     VG_TRY(pp.xmax.alloc(16));
     VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
     VG_CUDA(cudaMemcpyAsync(pp.wq.p, wq.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
@@ -881,6 +1282,29 @@ static vg_status launch_gemm(const CUtensorMap &mq, const KArgs &a, int64_t qtil
     return VG_OK;
 }
 template <int CODEC>
+static vg_status launch_gemm_pair(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st) {
+    const size_t sm = pair::SMEM2_BYTES;
+    VG_CUDA(cudaFuncSetAttribute(qtc2_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid((unsigned)(2 * qtiles), (unsigned)splits);  // clusters of two CTAs along x (__cluster_dims__)
+    qtc2_kernel<CODEC><<<grid, NTHREADS, sm, st>>>(mq, a);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+// CTA-pair kernel (cta_group::2) unless VECGO_QTC_PAIR=0
+static bool use_pair() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECGO_QTC_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+// Rows per minimum group: as the Flat filter, but at most 128 for the CTA-pair kernel (a group stays inside one thread).
+static int64_t qtc_group_rows(int64_t rows, int kc) {
+    const int64_t G = tc::group_rows(rows, kc);
+    return use_pair() ? std::min<int64_t>(G, 128) : G;
+}
+template <int CODEC>
 static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
     const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)LIST_CAP * 4 +
                       (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : 0);
@@ -897,7 +1321,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     const int64_t nq = io.nq, rows = io.rows;
     const int64_t q_stride = io.q_stride ? io.q_stride : cp.dim;
     const int64_t qtiles = (nq + BMQ - 1) / BMQ, nq_pad = qtiles * BMQ;
-    const int64_t G = tc::group_rows(rows, kc);
+    const bool pair_mode = use_pair();
+    const int64_t G = qtc_group_rows(rows, kc);
     const int64_t groups = (rows + G - 1) / G;
     DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau;
     VG_TRY(a16.alloc((size_t)nq * pp.dimp * 2));
@@ -913,10 +1338,10 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
                                                                           pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
     VG_LAUNCHED();
     CUtensorMap mq;
-    VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, BMQ));
-    // row splits: one CTA per SM, whole waves
-    const int64_t unit = std::max<int64_t>(BN, G);
-    const int64_t sms = sm_count();
+    VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, pair_mode ? BM : BMQ));
+    // row splits: one CTA (pair) per SM (pair), whole waves
+    const int64_t unit = pair_mode ? pair::TILE_ROWS : std::max<int64_t>(BN, G);
+    const int64_t sms = pair_mode ? sm_count() / 2 : sm_count();
     const int64_t max_splits = std::max<int64_t>(1, rows / (4 * unit));
     int64_t splits = 1;
     double best = 0.0;
@@ -944,15 +1369,25 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.mins = mins.as<float2>();
     a.groups = groups;
     a.idx_mask = (uint32_t)(G - 1);
+    a.keep_hi = ~31u;
     a.codes = cp.codes;
     a.row_bytes = cp.row_bytes;
     a.codebooks = cp.pq_codebooks;
     a.dsub_shift = 0;
     while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
     a.tiled = (qc == Q_PQ && (cp.variant & VG_VAR_PERM)) ? 1 : 0;
-    if (qc == Q_SQ8) VG_TRY(launch_gemm<Q_SQ8>(mq, a, qtiles, (int)splits, st));
-    else if (qc == Q_INT4) VG_TRY(launch_gemm<Q_INT4>(mq, a, qtiles, (int)splits, st));
-    else VG_TRY(launch_gemm<Q_PQ>(mq, a, qtiles, (int)splits, st));
+    const bool prof = g_prof.load() != 0 && g_ev[0];
+    if (prof) VG_CUDA(cudaEventRecord(g_ev[0], st));
+    if (pair_mode) {
+        if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
+        else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
+        else VG_TRY(launch_gemm_pair<Q_PQ>(mq, a, qtiles, (int)splits, st));
+    } else {
+        if (qc == Q_SQ8) VG_TRY(launch_gemm<Q_SQ8>(mq, a, qtiles, (int)splits, st));
+        else if (qc == Q_INT4) VG_TRY(launch_gemm<Q_INT4>(mq, a, qtiles, (int)splits, st));
+        else VG_TRY(launch_gemm<Q_PQ>(mq, a, qtiles, (int)splits, st));
+    }
+    if (prof) VG_CUDA(cudaEventRecord(g_ev[1], st));
     VG_TRY(tc::select_groups(a.mins, groups, nq, kc, G, tau.as<float>(), gids.as<uint32_t>(), gcnt.as<int32_t>(), st));
     EArgs e = eargs_of(cp, rows);
     e.queries = io.d_queries;
@@ -978,6 +1413,13 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     else if (qc == Q_INT4) VG_TRY(launch_exact<Q_INT4>(e, nq, st));
     else VG_TRY(launch_exact<Q_PQ>(e, nq, st));
     VG_CUDA(cudaStreamSynchronize(st));  // the temporaries above go back to the pool on return
+    if (prof) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess) {
+            g_gemm_ms += ms;
+            g_gemm_launches++;
+        }
+    }
     return VG_OK;
 }
 
@@ -985,7 +1427,7 @@ vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, 
     failed.clear();
     if (!pp.ready) return fail(VG_ERR_STATE, "decode-GEMM filter state was not prepared");
     const int kc = candidates_for(io.k);
-    const int64_t G = tc::group_rows(io.rows, kc);
+    const int64_t G = qtc_group_rows(io.rows, kc);
     const int64_t groups = (io.rows + G - 1) / G;
     // the [queries][groups] minima buffer is kept under 4 GiB: long batches go through in chunks of whole query tiles
     int64_t chunk = std::max<int64_t>(BMQ, ((4ll << 30) / (groups * 8)) / BMQ * BMQ);

@@ -45,6 +45,9 @@ struct SearchIO {
 vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st);
 
 void stats(uint64_t *queries, uint64_t *fallbacks);
+// Returns the accumulated CUDA-event time / launch count of the GEMM kernel since the last reset; enable = 1 / 0 turns
+// the event pair around every GEMM launch on / off and resets the counters, enable < 0 only reads.
+void profile(int enable, double *gemm_ms, uint64_t *gemm_launches);
 
 }  // namespace qtc
 }  // namespace vg
