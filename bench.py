@@ -452,15 +452,17 @@ def run_ours(a):
             flops = 2.0 * nq * nloc * dim * a.steps / gemm_launches
             ach = flops / (g_ms / 1e3) / 1e12
             roofline = {"bound": "tensor", "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": traffic,
-                        "kernel": f"qtc_kernel<{a.workload.upper()}> (tcgen05.mma kind::f16, fp32 accumulate in TMEM)",
+                        "kernel": (f"qtc_kernel<{a.workload.upper()}> (tcgen05.mma cta_group::1 kind::f16, M=128 x N=128)"
+                                   if os.environ.get("VECGO_QTC_PAIR", "1")[:1] == "0" else
+                                   f"qtc2_kernel<{a.workload.upper()}> (CTA pair, tcgen05.mma cta_group::2 kind::f16, M=256 x N=256, fp32 accumulate in TMEM)"),
                         "kernel_ms": g_ms, "kernel_launches_in_timed_region": gemm_launches, "share_of_step": g_ms * gemm_launches / a.steps / ms_per_step,
                         "algorithmic_flops_per_launch": flops, "peak_source": peak_src, "frac_of_burst_peak": ach / tf_burst,
                         "hbm_equivalent": {"achieved_gbs": hbm_equiv, "peak_gbs": hbm_peak, "frac": hbm_equiv / hbm_peak,
                                            "note": "queries x rows x code bytes per row / whole-search time: the per-query streaming bytes of "
                                                    "the reference (SURVEY 8d). Above 1 because one decoded code tile serves 256 queries."},
                         "note": "achieved = 2 x queries x rows x dim / GEMM kernel time (CUDA events on the library's stream around every "
-                                "launch). Codes are decoded to exact fp16 integers inside the kernel; the binding limit is the tensor pipe fed "
-                                "from shared memory (M=128 x N=128 tiles read 128 B/clk/SM at peak rate), not HBM."}
+                                "launch). Codes are decoded to exact fp16 integers inside the kernel; the binding limit is the tensor pipe, "
+                                "not HBM (DRAM traffic per launch in `traffic`)."}
             dtype = ("f16 tensor-core filter over exact integer codes with f32 accumulate, then f32 exact re-check in the reference's "
                      "AVX-512 order (results bit-identical to the f32 scan)")
         else:

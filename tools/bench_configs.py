@@ -198,7 +198,7 @@ def main():
         elif w == "c2b":
             sq("C2b", "int4", 1_000_000 if SMALL else 10_000_000, 768, 2048 if SMALL else 10_000, 100)
         elif w == "c3":
-            pq("C3", 4_000_000 if SMALL else 25_000_000, 768, 96, 592 if SMALL else 2072, 100)
+            pq("C3", 4_000_000 if SMALL else 25_000_000, 768, 96, 592 if SMALL else 10_000, 100)
         elif w == "c4":
             rabitq("C4", 2_000_000 if SMALL else 12_500_000, 1536, 512 if SMALL else 1000, 1000, 100)
         elif w == "c5":
