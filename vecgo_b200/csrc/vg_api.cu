@@ -4,6 +4,7 @@
 // decides a result runs in the CUDA kernels of vg_scan.cu / vg_quant.cu /
 // vg_kmeans.cu.  There is no CPU compute path in this file.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -166,6 +167,8 @@ struct Index {
     // tensor-core Flat filter state (vg_flat_tc.cu): squared row norms + their maximum, rebuilt after uploads
     DevBuf xn, xmax;
     bool xn_dirty = true;
+    DevBuf x16;           // fp16 shadow of the vectors (x * 2^x16_exp, rows padded to a multiple of 64 dims) for the CTA-pair filter
+    int x16_exp = 0;
     // decode-GEMM filter state of the quantized scans (vg_quant_tc.cu), rebuilt after code uploads
     qtc::Prepared qtc;
     bool qtc_dirty = true;
@@ -499,6 +502,22 @@ static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
     if (!ix->xmax.p) VG_TRY(ix->xmax.alloc(16));
     VG_CUDA(cudaMemsetAsync(ix->xmax.p, 0, 16, st));
     VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
+    if (rows >= 8192) {
+        // fp16 shadow for the CTA-pair filter: |x_i| <= sqrt(max ||x||^2) is scaled below 2^12
+        float xmax = 0.0f;
+        VG_CUDA(cudaMemcpyAsync(&xmax, ix->xmax.p, 4, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        int e = 0;
+        if (xmax > 0.0f && std::isfinite(xmax)) {
+            int ex;
+            std::frexp(std::sqrt((double)xmax), &ex);
+            e = std::min(60, std::max(-60, 12 - ex));
+        }
+        const int dimp = (int)((ix->d.dim + 63) / 64 * 64);
+        if (!ix->x16.p) VG_TRY(ix->x16.alloc_persistent((size_t)rows * dimp * 2));
+        VG_TRY(tc::make_shadow16(ix->vectors.as<float>(), rows, ix->d.dim, dimp, e, ix->x16.p, st));
+        ix->x16_exp = e;
+    }
     ix->xn_dirty = false;
     return VG_OK;
 }
@@ -521,6 +540,8 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     io.dim = d.dim;
     io.d_xn = ix->xn.as<float>();
     io.d_xmax_bits = ix->xmax.as<unsigned int>();
+    io.d_x16 = ix->x16.p;
+    io.x16_exp = ix->x16_exp;
     io.d_mask = d_mask;
     io.k = (int)k;
     io.is_dot = is_dot;

@@ -46,6 +46,7 @@
 //   warps 2-9  epilogue: one thread = one query (= one TMEM lane); tcgen05.ld 32 columns at a
 //              time, 32 independent FFMA, four (m1, m2) accumulators, one 8-byte store per group.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <algorithm>
 #include <atomic>
@@ -302,6 +303,241 @@ flat_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant_
     }
 }
 
+// ------------------------------------------------------------------ CTA-pair fp16 variant
+// Same filter on a cluster of two CTAs with tcgen05.mma.cta_group::2.kind::f16, M = 256 x N = 256 (see vg_quant_tc.cu
+// for the protocol): CTA r owns queries q0 + 128 r .. and TMA-loads rows n0 + 128 r .. of an fp16 SHADOW of the
+// vectors (x * 2^sx, built once per index; the float32 rows stay the source of the exact stage).  kind::f16 runs at
+// twice the TF32 rate, rounds to nearest (2^-11 relative per operand instead of TF32's 2^-10 truncation) and moves
+// half the operand bytes; queries are scaled per query so that max|q_i| lands in [2^11, 2^12).
+namespace pairf {
+using namespace vg::tc::pair;
+constexpr int BKH = 64;                  // halves per k-block (128 bytes)
+constexpr int STAGES2 = 6;
+constexpr int A2_BYTES = BM * BKH * 2;   // 16 KB
+constexpr int B2_BYTES = BN * BKH * 2;   // 16 KB
+constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
+constexpr int TILE_ROWS = 2 * BN;
+constexpr size_t OFF_XN2 = (size_t)STAGES2 * STAGE2_BYTES;
+constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)2 * TILE_ROWS * 4;
+constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 4) * 8 + 16 + 1024;
+}  // namespace pairf
+
+struct Args2 {
+    const float *xn;        // [rows] ||x||^2 (L2) or nullptr (dot)
+    const uint32_t *mask;
+    const float *fq;        // [nq] -2 (L2) or -1 (dot) / (query scale x database scale)
+    int64_t nq, rows, rows_per_split;
+    int kb;                 // k-blocks = dimp / 64
+    int cpg;                // 32-row chunks per group (<= 4)
+    float2 *mins;
+    int64_t groups;
+    uint32_t idx_mask, keep_hi;
+};
+
+template <bool IS_DOT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, Args2 A) {
+    using namespace pairf;
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ uint32_t tmem_base_slot;
+    unsigned char *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int q0 = (int)(blockIdx.x >> 1) * BMQ + (int)rank * BM;
+    const int split = blockIdx.y;
+    const int64_t row_begin = (int64_t)split * A.rows_per_split;
+    int64_t row_end = row_begin + A.rows_per_split;
+    if (row_end > A.rows) row_end = A.rows;
+    const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
+
+    const uint32_t s_base = smem_u32(smem);
+    const uint32_t bar0 = s_base + (uint32_t)OFF_BAR2;
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES2 + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES2 + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES2 + 2 + s); };
+    constexpr uint32_t TMEM_COLS = 512;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; s++) {
+            mbar_init(full_bar(s), 1);   // the leader's expect_tx arrive; all four TMA loads of the pair count their bytes here
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int s = 0; s < 2; s++) {
+            mbar_init(tfull_bar(s), 1);
+            mbar_init(tempty_bar(s), 8 + 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer: this CTA's query half and row half of every k-block =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int n0 = (int)(row_begin + (int64_t)t * TILE_ROWS) + (int)rank * BN;
+                for (int kb = 0; kb < A.kb; kb++, it++) {
+                    const int st = it % STAGES2;
+                    const uint32_t ph = (it / STAGES2) & 1;
+                    mbar_wait(empty_bar(st), ph ^ 1);
+                    if (leader) mbar_expect_tx(full_bar(st), 2 * STAGE2_BYTES);
+                    const uint32_t sa = s_base + st * STAGE2_BYTES;
+                    tma_load_2d_pair(sa, &map_q, kb * BKH, q0, full_bar(st));
+                    tma_load_2d_pair(sa + A2_BYTES, &map_x, kb * BKH, n0, full_bar(st));
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader && lane == 0) {
+            constexpr uint32_t idesc = make_idesc_f16_pair();
+            uint32_t it = 0;
+            for (int t = 0; t < ntiles; t++) {
+                const int as = t & 1;
+                const uint32_t aph = (t >> 1) & 1;
+                mbar_wait_cluster(tempty_bar(as), aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_ROWS);
+                for (int kb = 0; kb < A.kb; kb++, it++) {
+                    const int st = it % STAGES2;
+                    const uint32_t ph = (it / STAGES2) & 1;
+                    mbar_wait_cluster(full_bar(st), ph);
+                    tc_fence_after();
+                    const uint32_t sa = s_base + st * STAGE2_BYTES;
+                    const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A2_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BKH / 16; k++)
+                        umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit_pair(empty_bar(st));
+                }
+                umma_commit_pair(tfull_bar(as));
+            }
+        }
+    } else {
+        // ===================== epilogue: warps 2..9; thread = one query x one 128-column half of the tile =====================
+        const int quad = warp & 3;
+        const int colhalf = (warp - 2) >> 2;
+        const int et = (warp - 2) * 32 + lane;
+        const int64_t q = (int64_t)q0 + quad * 32 + lane;
+        float *xs = reinterpret_cast<float *>(smem + OFF_XN2);
+        const float BIG = 3.0e38f;
+        const float fq = q < A.nq ? __ldg(A.fq + q) : 0.0f;
+        const uint32_t keep_hi = A.keep_hi;
+        float g1 = BIG, g2 = BIG;
+        int cc = 0;
+        for (int t = 0; t < ntiles; t++) {
+            const int as = t & 1;
+            const uint32_t aph = (t >> 1) & 1;
+            const int64_t n0 = row_begin + (int64_t)t * TILE_ROWS;
+            float *xt = xs + as * TILE_ROWS;
+            {
+                const int64_t row = n0 + et;
+                xt[et] = (row < row_end) ? (IS_DOT ? 0.0f : __ldg(A.xn + row)) : BIG;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            mbar_wait(tfull_bar(as), aph);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * BN);
+            const int64_t nh = n0 + colhalf * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                uint32_t mw = 0xFFFFFFFFu;
+                if (A.mask) mw = (nh + c * 32 < A.rows) ? __ldg(A.mask + ((nh + c * 32) >> 5)) : 0u;
+                tmem_ld_wait();
+                float s[32];
+                const float4 *x4 = reinterpret_cast<const float4 *>(xt + colhalf * BN + c * 32);
+#pragma unroll
+                for (int j4 = 0; j4 < 8; j4++) {
+                    const float4 xv = x4[j4];
+                    const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) s[j4 * 4 + i] = __fmaf_rn(fq, __uint_as_float(v[j4 * 4 + i]), xx[i]);
+                }
+                if (mw != 0xFFFFFFFFu) {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
+                }
+                float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    uint32_t vb;  // (bits & ~31) | j as one LOP3
+                    asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(vb) : "r"(__float_as_uint(s[j])), "r"(keep_hi), "r"((uint32_t)j));
+                    const float v1 = __uint_as_float(vb);
+                    a2[j & 3] = fminf(a2[j & 3], fmaxf(a1[j & 3], v1));
+                    a1[j & 3] = fminf(a1[j & 3], v1);
+                }
+                const float p1 = fminf(a1[0], a1[1]), p2 = fminf(fmaxf(a1[0], a1[1]), fminf(a2[0], a2[1]));
+                const float r1 = fminf(a1[2], a1[3]), r2 = fminf(fmaxf(a1[2], a1[3]), fminf(a2[2], a2[3]));
+                const uint32_t cidx = (uint32_t)(nh + c * 32) & A.idx_mask & ~31u;
+                const float c1 = __uint_as_float((__float_as_uint(fminf(p1, r1)) & ~A.idx_mask) | cidx | (__float_as_uint(fminf(p1, r1)) & 31u));
+                const float c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
+                g2 = fminf(fmaxf(g1, c1), fminf(g2, c2));
+                g1 = fminf(g1, c1);
+                if (++cc == A.cpg) {
+                    const int64_t gid = (nh + c * 32) / (32 * (int64_t)A.cpg);
+                    if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);
+                    g1 = BIG;
+                    g2 = BIG;
+                    cc = 0;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    }
+}
+
+// fp16 shadow of the vectors: x16[r][p] = half(x[r][p] * 2^sx) for p < dim, 0 for the padding up to dimp.
+__global__ void __launch_bounds__(256) shadow16_kernel(const float *x, int64_t rows, int64_t dim, int dimp, int sx_exp, __half *x16) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * dimp) return;
+    const int64_t r = i / dimp;
+    const int p = (int)(i - r * dimp);
+    x16[i] = __float2half_rn(p < dim ? __fmul_rn(x[r * dim + p], ldexpf(1.0f, sx_exp)) : 0.0f);
+}
+// One warp per query: a16 = half(q * 2^e), e such that max|q_i| lands in [2^11, 2^12); f_q = -(2 | 1) / (2^e 2^sx).
+__global__ void __launch_bounds__(256) prep_queries16_kernel(const float *queries, int64_t nq, int64_t q_stride, int64_t dim, int dimp, int sx_exp,
+                                                             int is_dot, __half *a16, float *fq) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float *qv = queries + q * q_stride;
+    float mx = 0.0f;
+    for (int p = lane; p < dim; p += 32) mx = fmaxf(mx, fabsf(qv[p]));
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int e = 0;
+    if (mx > 0.0f && mx < __int_as_float(0x7f800000)) {
+        int ex;
+        frexpf(mx, &ex);
+        e = 12 - ex;
+        e = e > 100 ? 100 : (e < -100 ? -100 : e);
+    }
+    const float sq = ldexpf(1.0f, e);
+    for (int p = lane; p < dimp; p += 32) a16[q * dimp + p] = __float2half_rn(p < dim ? __fmul_rn(qv[p], sq) : 0.0f);
+    if (lane == 0) fq[q] = -ldexpf(1.0f, (is_dot ? 0 : 1) - e - sx_exp);
+}
+
 // tau(q) = kc-th smallest group minimum (m1) of query q and the kc groups that reach it: one warp per query streams
 // mins[q][*] (coalesced) through the shared-memory bounded top-k (threshold filter + bitonic compaction).  Output per
 // selected group: the row its m1 names (gid * G + index bits) and a "crowded" flag (bit 31) when m2 <= tau as well.
@@ -371,7 +607,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2 *mins, int6
 __global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int64_t dim, int64_t rows, const float *queries, int64_t q_stride,
                                                        const uint32_t *cand, const int32_t *gcnt, int kc, int G, const float *tau,
                                                        const float *qn, const unsigned int *xmax_bits, const uint8_t *mask, int k,
-                                                       int C, int is_dot, uint32_t row_base, uint32_t *out_rows, float *out_scores,
+                                                       int C, int is_dot, int fp16, uint32_t row_base, uint32_t *out_rows, float *out_scores,
                                                        int32_t *out_counts, int32_t *fail_flags) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int64_t q = blockIdx.x;
@@ -465,7 +701,9 @@ __global__ void __launch_bounds__(128) tc_exact_kernel(const float *vectors, int
                     fail = 1;
                 } else {
                     const double qq = (double)qn[q], xx = (double)__uint_as_float(*xmax_bits);
-                    const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125, c2 = 1.0 / 16384.0;
+                    // TF32 truncates each operand to 2^-10 relative; fp16 (pair kernel) rounds to 2^-11 and adds fp32 accumulation slack
+                    const double c1 = (is_dot ? 1.0 / 512.0 : 1.0 / 256.0) * 1.125 * (fp16 ? 0.5 : 1.0);
+                    const double c2 = 1.0 / 16384.0 + (fp16 ? (double)dim / 8388608.0 : 0.0);
                     const double smax = is_dot ? sqrt(qq * xx) : xx + 2.0 * sqrt(qq * xx);   // |s| of any row
                     const double E = c1 * sqrt(qq * xx) + c2 * (qq + xx) + smax * (double)G / 8388608.0;  // index bits: 2^-(23-log2 G)
                     const double ex = (double)out_scores[q * k + (k - 1)];
@@ -597,9 +835,97 @@ int64_t group_rows(int64_t rows, int kc) {
     return G;
 }
 
+static bool pair_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECGO_FLAT_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+bool uses_pair(const FilterArgs &f) {
+    return f.d_x16 != nullptr && pair_enabled() && f.rows >= 8192 && (f.q_stride == 0 || f.q_stride == f.dim) &&
+           (reinterpret_cast<uintptr_t>(f.d_x16) & 15) == 0;
+}
+int64_t filter_group_rows(const FilterArgs &f) {
+    const int64_t G = group_rows(f.rows, f.kc);
+    return uses_pair(f) ? std::min<int64_t>(G, 128) : G;  // pair kernel: a group stays inside one thread's 128-column half
+}
+vg_status make_shadow16(const float *d_x, int64_t rows, int64_t dim, int dimp, int sx_exp, void *d_x16, cudaStream_t st) {
+    const int64_t total = rows * dimp;
+    if (total <= 0) return VG_OK;
+    shadow16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_x, rows, dim, dimp, sx_exp, reinterpret_cast<__half *>(d_x16));
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+template <bool IS_DOT>
+static vg_status launch_pair(const CUtensorMap &mq, const CUtensorMap &mx, const Args2 &a, int64_t qtiles, int splits, cudaStream_t st) {
+    const size_t sm = pairf::SMEM2_BYTES;
+    VG_CUDA(cudaFuncSetAttribute(flat2_kernel<IS_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    dim3 grid((unsigned)(2 * qtiles), (unsigned)splits);
+    flat2_kernel<IS_DOT><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+// The filter on the CTA-pair fp16 kernel (f.d_x16 set).
+static vg_status filter_pair(const FilterArgs &f, cudaStream_t st) {
+    const int dimp = (int)((f.dim + 63) / 64 * 64);
+    const int64_t qtiles = (f.nq + BMQ - 1) / BMQ, nq_pad = qtiles * BMQ;
+    const int64_t G = filter_group_rows(f);
+    const int64_t groups = (f.rows + G - 1) / G;
+    DevBuf a16, fq, mins;
+    VG_TRY(a16.alloc((size_t)f.nq * dimp * 2));
+    VG_TRY(fq.alloc((size_t)f.nq * 4));
+    VG_TRY(mins.alloc((size_t)groups * nq_pad * 8));
+    prep_queries16_kernel<<<(unsigned)((f.nq * 32 + 255) / 256), 256, 0, st>>>(f.d_queries, f.nq, f.q_stride ? f.q_stride : f.dim, f.dim, dimp, f.x16_exp,
+                                                                              f.is_dot, a16.as<__half>(), fq.as<float>());
+    VG_LAUNCHED();
+    CUtensorMap mq, mx;
+    VG_TRY(tensor_map_2d(&mq, true, a16.p, f.nq, dimp, dimp, pairf::BKH, BM));
+    VG_TRY(tensor_map_2d(&mx, true, f.d_x16, f.rows, dimp, dimp, pairf::BKH, BN));
+    const int64_t unit = pairf::TILE_ROWS;
+    const int64_t sms = sm_count() / 2;
+    const int64_t max_splits = std::max<int64_t>(1, f.rows / (4 * unit));
+    int64_t splits = 1;
+    double best = 0.0;
+    for (int64_t s_ = 1; s_ <= sms && s_ <= max_splits; s_++) {
+        const int64_t ctas = qtiles * s_, waves = (ctas + sms - 1) / sms;
+        const double eff = (double)ctas / (double)(waves * sms);
+        if (eff > best + 0.02) {
+            best = eff;
+            splits = s_;
+        }
+        if (eff >= 0.97) break;
+    }
+    int64_t rps = (f.rows + splits - 1) / splits;
+    rps = (rps + unit - 1) / unit * unit;
+    splits = (f.rows + rps - 1) / rps;
+    Args2 a;
+    a.xn = f.d_xn;
+    a.mask = reinterpret_cast<const uint32_t *>(f.d_mask);
+    a.fq = fq.as<float>();
+    a.nq = f.nq;
+    a.rows = f.rows;
+    a.rows_per_split = rps;
+    a.kb = dimp / pairf::BKH;
+    a.cpg = (int)(G / 32);
+    a.mins = mins.as<float2>();
+    a.groups = groups;
+    a.idx_mask = (uint32_t)(G - 1);
+    a.keep_hi = ~31u;
+    if (f.is_dot) VG_TRY((launch_pair<true>(mq, mx, a, qtiles, (int)splits, st)));
+    else VG_TRY((launch_pair<false>(mq, mx, a, qtiles, (int)splits, st)));
+    VG_TRY(select_groups(a.mins, groups, f.nq, f.kc, G, f.d_tau, f.d_gids, f.d_gcnt, st));
+    VG_CUDA(cudaStreamSynchronize(st));  // a16 / fq / mins go back to the pool on return; the tensor maps live on this stack frame
+    return VG_OK;
+}
+
 vg_status filter(const FilterArgs &f, cudaStream_t st) {
     if (f.dim < 16 || f.dim % 4 != 0 || f.rows < 128 || f.rows >= (1ll << 31) || f.kc < 1 || f.kc > 64 || (f.rows + 31) / 32 < f.kc)
         return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
+    if (uses_pair(f)) return filter_pair(f, st);
     CUtensorMap mq, mx;
     VG_TRY(make_map(&mq, f.d_queries, f.nq, f.dim, f.q_stride ? f.q_stride : f.dim, BMQ));
     VG_TRY(make_map(&mx, f.d_vectors, f.rows, f.dim, f.dim, BN));
@@ -659,8 +985,8 @@ vg_status finalize(const FilterArgs &f, int k, const float *d_qn, const unsigned
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
     VG_CUDA(cudaFuncSetAttribute(tc_exact_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     tc_exact_kernel<<<(unsigned)f.nq, 128, sm, st>>>(f.d_vectors, f.dim, f.rows, f.d_queries, f.q_stride ? f.q_stride : f.dim, f.d_gids, f.d_gcnt, f.kc,
-                                                    (int)group_rows(f.rows, f.kc), f.d_tau, d_qn, d_xmax_bits, f.d_mask, k, C, f.is_dot,
-                                                    f.row_base, d_rows, d_scores, d_counts, d_fail);
+                                                    (int)filter_group_rows(f), f.d_tau, d_qn, d_xmax_bits, f.d_mask, k, C, f.is_dot,
+                                                    uses_pair(f) ? 1 : 0, f.row_base, d_rows, d_scores, d_counts, d_fail);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -691,6 +1017,8 @@ static vg_status search_once(const SearchIO &io, int kc, std::vector<int32_t> &f
     f.q_stride = io.q_stride;
     f.d_vectors = io.d_vectors;
     f.d_xn = io.d_xn;
+    f.d_x16 = io.d_x16;
+    f.x16_exp = io.x16_exp;
     f.d_mask = io.d_mask;
     f.nq = io.nq;
     f.rows = io.rows;

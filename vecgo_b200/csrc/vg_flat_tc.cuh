@@ -14,6 +14,10 @@ struct FilterArgs {
     const float *d_xn = nullptr;       // [rows] squared norms (L2) — unused for dot
     const uint8_t *d_mask = nullptr;   // optional row bitmap (bit = 1 keeps the row), 4-byte aligned
     int64_t nq = 0, rows = 0, dim = 0;
+    // optional fp16 shadow of the vectors, [rows][dimp] halves = x * 2^x16_exp (dimp = dim rounded up to 64): when set
+    // (and VECGO_FLAT_PAIR != 0) the filter runs the CTA-pair kind::f16 kernel instead of the single-CTA TF32 one
+    const void *d_x16 = nullptr;
+    int x16_exp = 0;
     int kc = 0;                        // number of row groups kept per query (>= k): at least kc rows have s <= tau
     int is_dot = 0;
     uint32_t row_base = 0;
@@ -31,6 +35,10 @@ int candidates_for_assign(int64_t rows);
 // out[i] = ||v_i||^2; optional running maximum (as uint bits of a non-negative float).
 vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, int64_t stride, float *d_out, unsigned int *d_max_bits, cudaStream_t st);
 int64_t group_rows(int64_t rows, int kc);  // rows per minimum group for a segment of `rows` rows
+bool uses_pair(const FilterArgs &f);       // the CTA-pair fp16 kernel will run this filter (groups are then <= 128 rows)
+int64_t filter_group_rows(const FilterArgs &f);
+// x16[r][p] = half(x[r][p] * 2^sx_exp), zero padded to dimp columns.
+vg_status make_shadow16(const float *d_x, int64_t rows, int64_t dim, int dimp, int sx_exp, void *d_x16, cudaStream_t st);
 // tau and the kc best groups per query from the [nq][groups] (m1, m2) pairs a GEMM epilogue wrote (shared with vg_quant_tc.cu).
 vg_status select_groups(const float2 *d_mins, int64_t groups, int64_t nq, int kc, int64_t G, float *d_tau, uint32_t *d_cand,
                         int32_t *d_gcnt, cudaStream_t st);
@@ -50,6 +58,8 @@ struct SearchIO {
     int64_t rows = 0, dim = 0;
     const float *d_xn = nullptr;               // [rows] squared norms of the vectors
     const unsigned int *d_xmax_bits = nullptr; // their maximum (float bits)
+    const void *d_x16 = nullptr;               // optional fp16 shadow (see FilterArgs)
+    int x16_exp = 0;
     const uint8_t *d_mask = nullptr;
     int k = 0, is_dot = 0;
     uint32_t row_base = 0;

@@ -475,6 +475,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) qtc_kernel(const __grid_constant_
 //   tfull[a]  (both CTAs) : tcgen05.commit multicast;  tempty[a] (leader): 8 epilogue warps of each CTA
 // Row groups are at most 128 rows so that a group lives in one thread (thread = query x 128-column half).
 namespace pair {
+using namespace vg::tc::pair;  // cluster / cta_group::2 PTX helpers (vg_tc_ptx.cuh)
 constexpr int STAGES2 = 6;
 constexpr int A2_BYTES = BM * BK * 2;   // 16 KB: this CTA's 128 queries x 64 halves
 constexpr int B2_BYTES = BN * BK * 2;   // 16 KB: this CTA's 128 rows x 64 halves
@@ -484,63 +485,6 @@ constexpr size_t OFF_XN2 = (size_t)STAGES2 * STAGE2_BYTES;
 constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)2 * TILE_ROWS * 4;
 constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 4) * 8 + 16 + 1024;
 
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (default semantics, as CUTLASS's
-// ClusterBarrier::arrive(cta_id): an explicit .release.cluster costs a MEMBAR + ERRBAR per arrive — measured 19 % of all
-// stall samples; the data hand-off itself is ordered by fence.proxy.async / tcgen05.fence before the arrive)
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
-    asm volatile(
-        "{\n\t"
-        ".reg .b32 ra;\n\t"
-        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
-        "}" ::"r"(local_bar), "r"(rank)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_LOOP_C:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_C;\n\t"
-        "bra WAIT_LOOP_C;\n\t"
-        "DONE_C:\n\t"
-        "}" ::"r"(bar), "r"(parity)
-        : "memory");
-}
-// TMA load into THIS CTA's shared memory whose bytes are counted on the leader CTA's barrier (peer bit cleared)
-__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
-        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
-        : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
-                 "h"((unsigned short)3)
-                 : "memory");
-}
-// M = 256, N = 256, fp16 operands, fp32 accumulate, K-major A and B
-__host__ __device__ constexpr uint32_t make_idesc_f16_pair() { return (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
 }  // namespace pair
 
 template <int CODEC>

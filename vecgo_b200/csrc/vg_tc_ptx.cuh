@@ -84,5 +84,67 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
 // generic-proxy shared-memory writes → visible to the async proxy (tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+
+// ------------------------------------------------------------------ CTA pair (cluster of two CTAs, cta_group::2)
+namespace pair {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster (default semantics, as CUTLASS's
+// ClusterBarrier::arrive(cta_id): an explicit .release.cluster costs a MEMBAR + ERRBAR per arrive — measured 19 % of all
+// stall samples; the data hand-off itself is ordered by fence.proxy.async / tcgen05.fence before the arrive)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t local_bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(local_bar), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP_C:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_C;\n\t"
+        "bra WAIT_LOOP_C;\n\t"
+        "DONE_C:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on the leader CTA's barrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
+        : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+// M = 256, N = 256, fp16 operands, fp32 accumulate, K-major A and B
+__host__ __device__ constexpr uint32_t make_idesc_f16_pair() { return (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
+}  // namespace pair
+
 }  // namespace tc
 }  // namespace vg
