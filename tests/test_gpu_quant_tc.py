@@ -227,3 +227,46 @@ def test_tc_scaled_data_ranges(vg):
         assert after[0] - before[0] == nq and after[1] - before[1] == 0, scale
         r2, s2, c2 = exact_scan(vg, make, q, k)
         assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2))
+
+
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (20000, 1536, 33, 10),      # C4 dimension: 24 k-blocks
+    (9000, 128, 300, 1),        # two k-blocks, two query tiles, ragged row tile
+    (200000, 256, 32, 1000),    # rerank depth of C4: 2000 candidate groups
+    (40000, 192, 20, 100),
+])
+def test_rabitq_tc_matches_oracle(vg, n, dim, nq, k):
+    """RaBitQ estimator scan (rabitq.go:119-176): sign bits as exact +-1 fp16 operands, estimator in the epilogue."""
+    rng = np.random.default_rng(n + dim + 5)
+    v = (rng.standard_normal((n, dim)) * (0.5 + rng.random((n, 1)))).astype(F)   # a spread of row norms
+    q = rng.standard_normal((nq, dim)).astype(F)
+    v[n // 2] = v[n // 3]
+    rq = vg.quantization.RaBitQuantizer(dim)
+    codes = rq.EncodeBatch(v)
+
+    def make():
+        ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_RABITQ, metric=0, dim=dim, rows=n)
+        ix.upload(codes=codes, vectors=v)
+        return ix
+
+    before = qtc_stats(vg)
+    with make() as ix:
+        rows, scores, counts = ix.search(q, k)
+        r2, s2, c2 = ix.search_rerank(q, k, min(10, k))
+    after = qtc_stats(vg)
+    assert after[0] - before[0] >= nq, "the scan did not go through the tensor-core filter"
+    for i in range(min(nq, 5)):
+        out = np.zeros(k, o.cand_dtype)
+        c = o.lib.vgo_rabitq_search(o.fp(q[i]), o.bp(codes), n, dim, k, None, out.ctypes.data_as(C.POINTER(o.Cand)), None)
+        assert c == counts[i]
+        assert np.array_equal(rows[i, :c], out[:c]["row"]), i
+        assert np.array_equal(bits(scores[i, :c]), bits(out[:c]["score"])), i
+    vg._lib.call("vg_flat_tc_enable", 0)
+    try:
+        with make() as ix:
+            e_rows, e_scores, e_counts = ix.search(q, k)
+            e2, es2, ec2 = ix.search_rerank(q, k, min(10, k))
+    finally:
+        vg._lib.call("vg_flat_tc_enable", 1)
+    assert np.array_equal(rows, e_rows) and np.array_equal(bits(scores), bits(e_scores)) and np.array_equal(counts, e_counts)
+    assert np.array_equal(r2, e2) and np.array_equal(bits(s2), bits(es2)) and np.array_equal(c2, ec2)

@@ -162,10 +162,14 @@ def rabitq(name, n, dim, nq, r_top, k):
     q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
     sh = vg.sharded.ShardedIndex(ix, descending=False)
     rr, ss, cc = out_bufs(nq, r_top, dev)
+    st0 = qtc_stats()
     ms_scan = timed(lambda: ix.search_dev(q.data_ptr(), nq, r_top, rr.data_ptr(), ss.data_ptr(), cc.data_ptr()), warm=1, reps=2)
     ms = timed(lambda: sh.search_rerank_dev(q, nq, r_top, k), warm=1, reps=2)
+    st1 = qtc_stats()
     emit(name, f"RaBitQ 1-bit scan + float32 rerank of top-{r_top}, {n} x {dim}, {nq} queries, final k={k} (per-GPU shard)", ms, nq, n * nq,
-         bytes_per_pair=code_bytes, extra={"scan_only_ms": ms_scan, "rerank_and_merge_ms": ms - ms_scan, "generate_encode_upload_s": gen_s})
+         bytes_per_pair=code_bytes, flops=2.0 * n * nq * dim,
+         extra={"scan_only_ms": ms_scan, "rerank_and_merge_ms": ms - ms_scan, "generate_encode_upload_s": gen_s,
+                "tensor_core_filter": {"queries": st1[0] - st0[0], "exact_rerun_queries": st1[1] - st0[1]}})
     ix.close()
 
 

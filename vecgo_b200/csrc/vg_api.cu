@@ -586,9 +586,11 @@ static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArg
         const bool pq = d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ;
         const size_t np = pq ? (size_t)d.pq_m : (size_t)d.dim;
         std::vector<float> h0(np), h1(np);
-        VG_CUDA(cudaMemcpyAsync(h0.data(), pq ? ix->pq_scales.p : ix->p0.p, np * 4, cudaMemcpyDeviceToHost, st));
-        VG_CUDA(cudaMemcpyAsync(h1.data(), pq ? ix->pq_offsets.p : ix->p1.p, np * 4, cudaMemcpyDeviceToHost, st));
-        VG_CUDA(cudaStreamSynchronize(st));
+        if (d.codec != VG_CODEC_RABITQ) {  // RaBitQ has no decode parameters
+            VG_CUDA(cudaMemcpyAsync(h0.data(), pq ? ix->pq_scales.p : ix->p0.p, np * 4, cudaMemcpyDeviceToHost, st));
+            VG_CUDA(cudaMemcpyAsync(h1.data(), pq ? ix->pq_offsets.p : ix->p1.p, np * 4, cudaMemcpyDeviceToHost, st));
+            VG_CUDA(cudaStreamSynchronize(st));
+        }
         VG_TRY(qtc::prepare(cp, d.rows, h0.data(), h1.data(), ix->qtc, st));
         ix->qtc_dirty = false;
     }
@@ -605,7 +607,12 @@ static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArg
     io.d_counts = a.out_counts;
     std::vector<int32_t> bad;
     VG_TRY(qtc::search(cp, ix->qtc, io, bad, st));
-    if (!bad.empty()) VG_TRY(scan_topk_subset(cp, a, bad, st));
+    if (!bad.empty()) {
+        // RaBitQ: the exact scan reads per-query sign words prepared for the WHOLE batch, so a failed certificate sends
+        // the whole batch through it (the caller falls through); the other codecs re-run only the failed queries
+        if (d.codec == VG_CODEC_RABITQ) return VG_OK;
+        VG_TRY(scan_topk_subset(cp, a, bad, st));
+    }
     *handled = true;
     return VG_OK;
 }
@@ -668,7 +675,8 @@ static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, 
         VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), rotated.as<float>(), st));  // opq.go:196-214
         a.queries = rotated.as<float>();
     }
-    if (d.codec == VG_CODEC_SQ8 || d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ) {
+    if (d.codec == VG_CODEC_SQ8 || d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ ||
+        d.codec == VG_CODEC_RABITQ) {
         bool handled = false;
         VG_TRY(quant_tc_search(ix, cp, a, &handled));
         if (handled) {

@@ -76,8 +76,8 @@ constexpr int NTHREADS = (PROD_WARP0 + 8) * 32;
 constexpr size_t OFF_XN = (size_t)STAGES * STAGE_BYTES;
 constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
 constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024;  // + slack for the 1024-byte alignment
-constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2;
-constexpr int LIST_CAP = 4096;            // candidate rows per query in the exact stage
+constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2, Q_RABITQ = 3;
+constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage
 
 // kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = F16 (0 at bits 7-9 / 10-12), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -209,6 +209,29 @@ struct Producer<Q_PQ> {
             const uint32_t w0 = g[c].x ^ 0x80808080u, w1 = g[c].y ^ 0x80808080u;  // int8 + 128 as unsigned bytes
             sts128(dst_row + (uint32_t)((c ^ swz) << 4), hsub2_bits(bytes01_h2(w0), H2_1152), hsub2_bits(bytes23_h2(w0), H2_1152),
                    hsub2_bits(bytes01_h2(w1), H2_1152), hsub2_bits(bytes23_h2(w1), H2_1152));
+        }
+    }
+};
+
+// RaBitQ sign bits: 8 stored bytes (64 dims) per k-block -> +1 / -1 as fp16, exact.  One 32-bit word = four 16-byte
+// chunks; half2 p (0..15) of a word holds bit p (low half) and bit p + 16 (high half): (~w << (15 - p)) puts the two
+// inverted bits on the sign positions, OR 0x3C003C00 makes them -1.0 / +1.0 (bit set = component >= 0 = +1).
+template <>
+struct Producer<Q_RABITQ> {
+    uint2 w;
+    __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
+        w = __ldg(reinterpret_cast<const uint2 *>(A.codes + row * A.row_bytes + (int64_t)kb * 8));
+    }
+    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
+        const uint32_t y[2] = {~w.x, ~w.y};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t v = y[c >> 2];
+            const int p0 = (c & 3) * 4;
+            uint32_t h[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) h[j] = ((v << (15 - (p0 + j))) & 0x80008000u) | 0x3C003C00u;
+            sts128(dst_row + (uint32_t)((c ^ swz) << 4), h[0], h[1], h[2], h[3]);
         }
     }
 };
@@ -591,7 +614,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             float *xt = xs + as * TILE_ROWS;
             {
                 const int64_t row = n0 + et;  // 256 epilogue threads stage the 256 row norms of the tile
-                xt[et] = (row < row_end) ? __ldg(A.xn + row) : BIG;
+                // RaBitQ: xn = the stored norm ||y||; a padding row gets 1e19 so that s' = yn * (yn + f_q acc) ~ 1e38 stays finite
+                xt[et] = (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(tfull_bar(as), aph);
@@ -612,7 +636,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                     const float4 xv = x4[j4];
                     const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                    for (int i = 0; i < 4; i++) s[j4 * 4 + i] = __fmaf_rn(fq, __uint_as_float(v[j4 * 4 + i]), xx[i]);
+                    for (int i = 0; i < 4; i++) {
+                        const float t = __fmaf_rn(fq, __uint_as_float(v[j4 * 4 + i]), xx[i]);
+                        s[j4 * 4 + i] = CODEC == Q_RABITQ ? __fmul_rn(t, xx[i]) : t;  // RaBitQ: yn^2 - (2 qn / D) yn acc
+                    }
                 }
                 if (mw != 0xFFFFFFFFu) {
 #pragma unroll
@@ -699,6 +726,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 c2 = c4;
                 c4.advance2(A.kb);
             }
+        } else if constexpr (CODEC == Q_RABITQ) {
+            const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
+            const int swz = r & 7;
+            auto row_of = [&](int t) {
+                const int64_t row = half_begin + (int64_t)t * TILE_ROWS + r;
+                return row < A.rows ? row : A.rows - 1;
+            };
+            Producer<Q_RABITQ> cur, nxt;
+            Cursor c0, c2;
+            c0.init(grp, A.kb);
+            c2 = c0;
+            if (grp < total_it) nxt.fetch(A, row_of(c2.t), c2.kb);
+            for (int it = grp; it < total_it; it += 2) {
+                cur = nxt;
+                c0 = c2;
+                c2.advance2(A.kb);
+                if (it + 2 < total_it) nxt.fetch(A, row_of(c2.t), c2.kb);
+                const int st = it % STAGES2;
+                const uint32_t ph = (it / STAGES2) & 1;
+                mbar_wait(empty_bar(st), ph ^ 1);
+                cur.convert(A, c0.kb, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+            }
         } else {
             const int slab = ((warp - PROD_WARP0) & 3) * 32;
             ProducerBytes<CODEC> cur, nxt;
@@ -771,6 +823,34 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *queries,
     }
 }
 
+// RaBitQ: the query side of the estimator (rabitq.go:119-176) is sign(q) and ||q||, both already prepared for the exact
+// scan (prep_sign_queries): a_p = +-1 in storage order, f_q = -2 ||q|| / D, c_q = ||q||^2, so that
+// dist = (qn - yn)^2 + (4 qn yn / D) h = c_q + yn^2 + f_q yn acc   with acc = sum s_q s_x = D - 2 h  (exact in fp16 x fp16 -> fp32).
+__global__ void __launch_bounds__(256) prep_queries_sign_kernel(const uint32_t *q_words, const float *q_norms, int64_t nq, int words32, int dim,
+                                                                int dimp, const int32_t *perm, __half *a16, float *fq, float *cq) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const uint32_t *qw = q_words + q * words32;
+    for (int p = lane; p < dimp; p += 32) {
+        const int d = perm[p];
+        float v = 0.0f;
+        if (d >= 0) v = ((qw[d >> 5] >> (d & 31)) & 1u) ? 1.0f : -1.0f;
+        a16[q * dimp + p] = __float2half_rn(v);
+    }
+    if (lane == 0) {
+        const float qn = q_norms[q];
+        fq[q] = __fdiv_rn(__fmul_rn(-2.0f, qn), (float)dim);
+        cq[q] = __fmul_rn(qn, qn);
+    }
+}
+__global__ void __launch_bounds__(256) norm_sq_max_kernel(const float *norms, int64_t rows, unsigned int *max_bits) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    const float y = norms[i];
+    atomicMax(max_bits, __float_as_uint(__fmul_rn(y, y)));
+}
+
 // ------------------------------------------------------------------ exact decode helpers (reference arithmetic)
 struct EArgs {
     const uint8_t *codes;
@@ -780,6 +860,10 @@ struct EArgs {
     const int8_t *codebooks;  // PQ
     const float *pq_scales, *pq_offsets;
     int pq_m, pq_dsub;
+    const float *norms;       // RaBitQ: stored row norms
+    const uint32_t *q_words;  // RaBitQ: prepared query sign words [nq][words32]
+    const float *q_norms;     // RaBitQ: prepared query norms
+    int words32;
     int64_t dim, rows;
     const float *queries;
     int64_t q_stride;
@@ -871,6 +955,22 @@ __device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, co
                 tot = __fmaf_rn(e, e, tot);
             }
         return tot;
+    } else if constexpr (CODEC == Q_RABITQ) {
+        // rabitq.go:119-176: exact popcount (popcount_avx512.c:25-46), then the unfused Go estimator
+        const uint32_t *code = reinterpret_cast<const uint32_t *>(E.codes + row * E.row_bytes);
+        const uint32_t *qw = reinterpret_cast<const uint32_t *>(table);  // the query's sign words staged in shared memory
+        int h = 0;
+        for (int w = lane; w < E.words32; w += 16) h += __popc(__ldg(code + w) ^ qw[w]);
+        h += __shfl_down_sync(0xffffffffu, h, 8, 16);
+        h += __shfl_down_sync(0xffffffffu, h, 4, 16);
+        h += __shfl_down_sync(0xffffffffu, h, 2, 16);
+        h += __shfl_down_sync(0xffffffffu, h, 1, 16);
+        const float qn = qs[0], yn = __ldg(E.norms + row);
+        const float t1 = __fsub_rn(qn, yn);
+        float a = __fmul_rn(4.0f, qn);
+        a = __fmul_rn(a, yn);
+        a = __fdiv_rn(a, (float)E.dim);
+        return __fadd_rn(__fmul_rn(t1, t1), __fmul_rn(a, (float)h));
     } else {
         // floats_avx512.c:135-167: lane l sums table[(16t+l)*256 + code[16t+l]] over t, reduce, sequential tail
         const int M = E.pq_m, t16 = M >> 4, tail = M & 15;
@@ -899,7 +999,13 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     TopK tk = topk_carve(smem + qbytes, 1, E.C, E.k);
     int32_t *rowlist = reinterpret_cast<int32_t *>(smem + qbytes + topk_smem_bytes(1, E.C));
     float *table = reinterpret_cast<float *>(rowlist + LIST_CAP);
-    for (int64_t d = tid; d < E.dim; d += 128) qs[d] = E.queries[q * E.q_stride + d];
+    if constexpr (CODEC == Q_RABITQ) {
+        if (tid == 0) qs[0] = E.q_norms[q];
+        uint32_t *qw = reinterpret_cast<uint32_t *>(table);
+        for (int w = tid; w < E.words32; w += 128) qw[w] = E.q_words[q * E.words32 + w];
+    } else {
+        for (int64_t d = tid; d < E.dim; d += 128) qs[d] = E.queries[q * E.q_stride + d];
+    }
     topk_init(tk, 1, tid, 128);
     __syncthreads();
     if constexpr (CODEC == Q_PQ) {
@@ -971,6 +1077,16 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
             if (!overflow && t < __int_as_float(0x7f800000)) {
                 if (m < E.k) {
                     fail = 1;
+                } else if (CODEC == Q_RABITQ) {
+                    // the GEMM is exact (acc = D - 2 Hamming); only the epilogue's float32 arithmetic, the index bits and
+                    // the reference estimator's own roundings separate s' + c_q from the reference score
+                    const double qq = (double)E.cq[q], xx = (double)__uint_as_float(E.xmax_bits[0]);
+                    const double qn_ = sqrt(qq), yn = sqrt(xx);
+                    const double smax = xx + 2.0 * qn_ * yn;
+                    const double Eb = smax * (1.0 / 2097152.0 + (double)E.G / 8388608.0);
+                    const double eref = (qn_ + yn) * (qn_ + yn) / 2097152.0;
+                    const double ex = (double)E.out_scores[q * E.k + (E.k - 1)];
+                    if (!(ex < (double)t - Eb + qq - eref)) fail = 1;
                 } else {
                     const double qq = (double)E.qn[q], xx = (double)__uint_as_float(E.xmax_bits[0]), bb = (double)__uint_as_float(E.xmax_bits[1]);
                     const double qn_ = sqrt(qq), bn = sqrt(bb);
@@ -1044,6 +1160,7 @@ static int q_codec(const CodecParams &cp) {
         case VG_CODEC_INT4: return Q_INT4;
         case VG_CODEC_PQ:
         case VG_CODEC_OPQ: return Q_PQ;
+        case VG_CODEC_RABITQ: return Q_RABITQ;
         default: return -1;
     }
 }
@@ -1089,9 +1206,19 @@ void profile(int enable, double *gemm_ms, uint64_t *gemm_launches) {
     }
 }
 
+// CTA-pair kernel (cta_group::2) unless VECGO_QTC_PAIR=0
+static bool use_pair() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECGO_QTC_PAIR");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int64_t k, int64_t num_partitions) {
     if (!enabled() || num_partitions > 1) return false;
-    if (rows < 8192 || rows >= (1ll << 31) || nq < 16 || k < 1 || k > 128) return false;
+    if (rows < 8192 || rows >= (1ll << 31) || nq < 16 || k < 1) return false;
+    if (k > (cp.codec == VG_CODEC_RABITQ ? 1024 : 128)) return false;
     if (cp.dim % 64 != 0 || cp.dim < 64 || cp.dim > 2048) return false;
     if ((reinterpret_cast<uintptr_t>(cp.codes) & 15) != 0) return false;
     switch (cp.codec) {
@@ -1099,6 +1226,9 @@ bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int6
             return metric == VG_METRIC_L2 && !(cp.variant & VG_VAR_GO_SCALAR);
         case VG_CODEC_INT4:
             return true;  // Int4 scores are L2 distances whatever the segment metric
+        case VG_CODEC_RABITQ:
+            // the estimator is a distance whatever the segment metric; CTA-pair kernel only; candidate groups must exist
+            return use_pair() && cp.norms != nullptr && cp.q_words != nullptr && cp.q_norms != nullptr && rows / 32 >= 2 * (k <= 16 ? 32 : 2 * k);
         case VG_CODEC_PQ:
         case VG_CODEC_OPQ: {
             if (metric != VG_METRIC_L2 || cp.pq_k != 256 || cp.pq_tables) return false;
@@ -1123,6 +1253,10 @@ static EArgs eargs_of(const CodecParams &cp, int64_t rows) {
     e.pq_offsets = cp.pq_offsets;
     e.pq_m = cp.pq_m;
     e.pq_dsub = cp.pq_dsub;
+    e.norms = cp.norms;
+    e.q_words = cp.q_words;
+    e.q_norms = cp.q_norms;
+    e.words32 = cp.words32;
     e.dim = cp.dim;
     e.rows = rows;
     return e;
@@ -1135,6 +1269,27 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     const int layout = layout_of(cp);
     // storage position (= position along K of the B tile the producer writes) -> dimension
     std::vector<int32_t> perm((size_t)dimp, -1);
+    if (qc == Q_RABITQ) {
+        // Producer<Q_RABITQ>::convert: position 64 kb + 32 word + 8 c + 2 j + hi holds bit 64 kb + 32 word + 4 c + j + 16 hi
+        for (int p = 0; p < dimp; p++) {
+            const int base = p & ~31, in = p & 31, c = in >> 3, j = (in >> 1) & 3, hi = in & 1;
+            const int d = base + 4 * c + j + 16 * hi;
+            perm[(size_t)p] = d < dim ? d : -1;
+        }
+        VG_TRY(pp.perm.alloc((size_t)dimp * 4));
+        VG_TRY(pp.xmax.alloc(16));
+        VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaMemsetAsync(pp.xmax.p, 0, 16, st));
+        if (rows > 0) {
+            norm_sq_max_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(cp.norms, rows, pp.xmax.as<unsigned int>());
+            VG_LAUNCHED();
+        }
+        VG_CUDA(cudaStreamSynchronize(st));
+        pp.dimp = dimp;
+        pp.mid_norm = 0.0f;
+        pp.ready = true;
+        return VG_OK;
+    }
     if (qc == Q_SQ8) {
         for (int d = 0; d < dim; d++) {
             int p = d;
@@ -1234,15 +1389,6 @@ static vg_status launch_gemm_pair(const CUtensorMap &mq, const KArgs &a, int64_t
     VG_LAUNCHED();
     return VG_OK;
 }
-// CTA-pair kernel (cta_group::2) unless VECGO_QTC_PAIR=0
-static bool use_pair() {
-    static int v = -1;
-    if (v < 0) {
-        const char *e = getenv("VECGO_QTC_PAIR");
-        v = (e && e[0] == '0') ? 0 : 1;
-    }
-    return v != 0;
-}
 // Rows per minimum group: as the Flat filter, but at most 128 for the CTA-pair kernel (a group stays inside one thread).
 static int64_t qtc_group_rows(int64_t rows, int kc) {
     const int64_t G = tc::group_rows(rows, kc);
@@ -1251,7 +1397,7 @@ static int64_t qtc_group_rows(int64_t rows, int kc) {
 template <int CODEC>
 static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
     const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)LIST_CAP * 4 +
-                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : 0);
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : CODEC == Q_RABITQ ? (size_t)e.words32 * 4 : 0);
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
     VG_CUDA(cudaFuncSetAttribute(qtc_exact_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     qtc_exact_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e);
@@ -1277,10 +1423,17 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     VG_TRY(gids.alloc((size_t)nq * kc * 4));
     VG_TRY(gcnt.alloc((size_t)nq * 4));
     VG_TRY(tau.alloc((size_t)nq * 4));
+    if (qc == Q_RABITQ) {
+        prep_queries_sign_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32, cp.q_norms + io.q_index0, nq,
+                                                                                   cp.words32, (int)cp.dim, pp.dimp, pp.perm.as<int32_t>(),
+                                                                                   a16.as<__half>(), fq.as<float>(), cq.as<float>());
+        VG_LAUNCHED();
+    } else {
     VG_TRY(tc::sqnorms(io.d_queries, nq, cp.dim, q_stride, qn.as<float>(), nullptr, st));
     prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.wq.as<float>(),
                                                                           pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
     VG_LAUNCHED();
+    }
     CUtensorMap mq;
     VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, pair_mode ? BM : BMQ));
     // row splits: one CTA (pair) per SM (pair), whole waves
@@ -1302,7 +1455,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     rps = (rps + unit - 1) / unit * unit;
     splits = (rows + rps - 1) / rps;
     KArgs a{};
-    a.xn = pp.xn.as<float>();
+    a.xn = qc == Q_RABITQ ? cp.norms : pp.xn.as<float>();
     a.mask = reinterpret_cast<const uint32_t *>(io.d_mask);
     a.fq = fq.as<float>();
     a.nq = nq;
@@ -1325,8 +1478,10 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     if (pair_mode) {
         if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
+        else if (qc == Q_RABITQ) VG_TRY(launch_gemm_pair<Q_RABITQ>(mq, a, qtiles, (int)splits, st));
         else VG_TRY(launch_gemm_pair<Q_PQ>(mq, a, qtiles, (int)splits, st));
     } else {
+        if (qc == Q_RABITQ) return fail(VG_ERR_UNSUPPORTED, "the RaBitQ filter needs the CTA-pair kernel");
         if (qc == Q_SQ8) VG_TRY(launch_gemm<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm<Q_INT4>(mq, a, qtiles, (int)splits, st));
         else VG_TRY(launch_gemm<Q_PQ>(mq, a, qtiles, (int)splits, st));
@@ -1353,7 +1508,11 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     e.out_scores = io.d_scores;
     e.out_counts = io.d_counts;
     e.fail_flags = d_fail;
-    if (qc == Q_SQ8) VG_TRY(launch_exact<Q_SQ8>(e, nq, st));
+    if (qc == Q_RABITQ) {
+        e.q_words = cp.q_words + io.q_index0 * cp.words32;
+        e.q_norms = cp.q_norms + io.q_index0;
+        VG_TRY(launch_exact<Q_RABITQ>(e, nq, st));
+    } else if (qc == Q_SQ8) VG_TRY(launch_exact<Q_SQ8>(e, nq, st));
     else if (qc == Q_INT4) VG_TRY(launch_exact<Q_INT4>(e, nq, st));
     else VG_TRY(launch_exact<Q_PQ>(e, nq, st));
     VG_CUDA(cudaStreamSynchronize(st));  // the temporaries above go back to the pool on return
@@ -1382,6 +1541,7 @@ vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, 
         part.nq = std::min(chunk, io.nq - q0);
         part.q_stride = io.q_stride ? io.q_stride : cp.dim;
         part.d_queries = io.d_queries + q0 * part.q_stride;
+        part.q_index0 = io.q_index0 + q0;
         part.d_rows = io.d_rows + q0 * io.k;
         part.d_scores = io.d_scores + q0 * io.k;
         part.d_counts = io.d_counts + q0;

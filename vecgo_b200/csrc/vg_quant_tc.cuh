@@ -32,6 +32,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
 struct SearchIO {
     const float *d_queries = nullptr;  // [nq][dim] float32 (OPQ: already rotated)
     int64_t q_stride = 0, nq = 0;
+    int64_t q_index0 = 0;              // index of the first query inside the prepared per-query arrays of `cp` (RaBitQ sign words / norms)
     int64_t rows = 0;
     const uint8_t *d_mask = nullptr;
     int k = 0;
