@@ -6,6 +6,9 @@ simd.Sq8uL2BatchPerDimension / simd.Int4L2DistanceBatch / simd.PqAdcLookup — c
 oracle and against this library's exact CUDA-core scan — whatever the filter did, including a failing certificate.
 """
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -270,3 +273,34 @@ def test_rabitq_tc_matches_oracle(vg, n, dim, nq, k):
         vg._lib.call("vg_flat_tc_enable", 1)
     assert np.array_equal(rows, e_rows) and np.array_equal(bits(scores), bits(e_scores)) and np.array_equal(counts, e_counts)
     assert np.array_equal(r2, e2) and np.array_equal(bits(s2), bits(es2)) and np.array_equal(c2, ec2)
+
+
+def test_single_cta_kernels_in_subprocess():
+    """The pair switches are read once per process: the single-CTA kernels (qtc_kernel, flat_tc_kernel) get their own process."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, VECGO_QTC_PAIR="0", VECGO_FLAT_PAIR="0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_legacy_check.py")], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "identical to the exact scan" in r.stdout
+
+
+def test_opq_index_through_the_filter(vg):
+    """OPQ = block rotation of the query (opq.go:196-214) + the PQ ADC scan: the rotated queries feed the decode-GEMM filter."""
+    n, dim, m, nq, k, bs = 30000, 128, 16, 24, 10, 32
+    rng = np.random.default_rng(123)
+    cb, sc, of = random_pq(rng, dim, m)
+    codes = rng.integers(0, 256, (n, m), dtype=np.uint8)
+    rot = np.stack([np.linalg.qr(rng.standard_normal((bs, bs)))[0] for _ in range(dim // bs)]).astype(F)
+    q = (rng.standard_normal((nq, dim)) * 0.7).astype(F)
+
+    def make():
+        ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_OPQ, metric=0, dim=dim, rows=n, pq=(cb, sc, of, m, 256), opq=(rot, bs))
+        ix.upload(codes=codes)
+        return ix
+
+    before = qtc_stats(vg)
+    with make() as ix:
+        rows, scores, counts = ix.search(q, k)
+    assert qtc_stats(vg)[0] - before[0] == nq
+    r2, s2, c2 = exact_scan(vg, make, q, k)
+    assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)

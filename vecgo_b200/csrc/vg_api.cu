@@ -502,7 +502,7 @@ static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
     if (!ix->xmax.p) VG_TRY(ix->xmax.alloc(16));
     VG_CUDA(cudaMemsetAsync(ix->xmax.p, 0, 16, st));
     VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
-    if (rows >= 8192) {
+    if (rows >= 8192 && tc::pair_enabled()) {
         // fp16 shadow for the CTA-pair filter: |x_i| <= sqrt(max ||x||^2) is scaled below 2^12
         float xmax = 0.0f;
         VG_CUDA(cudaMemcpyAsync(&xmax, ix->xmax.p, 4, cudaMemcpyDeviceToHost, st));

@@ -835,7 +835,7 @@ int64_t group_rows(int64_t rows, int kc) {
     return G;
 }
 
-static bool pair_enabled() {
+bool pair_enabled() {
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("VECGO_FLAT_PAIR");
@@ -918,8 +918,7 @@ static vg_status filter_pair(const FilterArgs &f, cudaStream_t st) {
     if (f.is_dot) VG_TRY((launch_pair<true>(mq, mx, a, qtiles, (int)splits, st)));
     else VG_TRY((launch_pair<false>(mq, mx, a, qtiles, (int)splits, st)));
     VG_TRY(select_groups(a.mins, groups, f.nq, f.kc, G, f.d_tau, f.d_gids, f.d_gcnt, st));
-    VG_CUDA(cudaStreamSynchronize(st));  // a16 / fq / mins go back to the pool on return; the tensor maps live on this stack frame
-    return VG_OK;
+    return VG_OK;  // a16 / fq / mins are returned to the stream-ordered pool (freed in stream order); tensor maps were copied at launch
 }
 
 vg_status filter(const FilterArgs &f, cudaStream_t st) {

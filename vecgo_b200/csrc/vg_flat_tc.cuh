@@ -35,6 +35,7 @@ int candidates_for_assign(int64_t rows);
 // out[i] = ||v_i||^2; optional running maximum (as uint bits of a non-negative float).
 vg_status sqnorms(const float *d_v, int64_t n, int64_t dim, int64_t stride, float *d_out, unsigned int *d_max_bits, cudaStream_t st);
 int64_t group_rows(int64_t rows, int kc);  // rows per minimum group for a segment of `rows` rows
+bool pair_enabled();                       // VECGO_FLAT_PAIR != 0
 bool uses_pair(const FilterArgs &f);       // the CTA-pair fp16 kernel will run this filter (groups are then <= 128 rows)
 int64_t filter_group_rows(const FilterArgs &f);
 // x16[r][p] = half(x[r][p] * 2^sx_exp), zero padded to dimp columns.

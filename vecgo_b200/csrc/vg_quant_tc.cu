@@ -1515,8 +1515,9 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     } else if (qc == Q_SQ8) VG_TRY(launch_exact<Q_SQ8>(e, nq, st));
     else if (qc == Q_INT4) VG_TRY(launch_exact<Q_INT4>(e, nq, st));
     else VG_TRY(launch_exact<Q_PQ>(e, nq, st));
-    VG_CUDA(cudaStreamSynchronize(st));  // the temporaries above go back to the pool on return
+    // the temporaries above go back to the stream-ordered pool (freed in stream order): no synchronisation needed for them
     if (prof) {
+        VG_CUDA(cudaStreamSynchronize(st));
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess) {
             g_gemm_ms += ms;
