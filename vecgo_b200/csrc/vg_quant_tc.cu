@@ -733,36 +733,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 const int64_t row = half_begin + (int64_t)t * TILE_ROWS + r;
                 return row < A.rows ? row : A.rows - 1;
             };
-            Producer<Q_RABITQ> cur, nxt;
-            Cursor c0, c2;
-            c0.init(grp, A.kb);
-            c2 = c0;
-            if (grp < total_it) nxt.fetch(A, row_of(c2.t), c2.kb);
-            for (int it = grp; it < total_it; it += 2) {
-                cur = nxt;
-                c0 = c2;
-                c2.advance2(A.kb);
-                if (it + 2 < total_it) nxt.fetch(A, row_of(c2.t), c2.kb);
+            // three buffers in rotation (see the byte producers below): loads of it + 2 and it + 4 in flight
+            Producer<Q_RABITQ> b0, b1, b2;
+            Cursor cf;
+            cf.init(grp, A.kb);
+            int it = grp;
+            auto fetch_next = [&](Producer<Q_RABITQ> &buf, int it_f) {
+                if (it_f < total_it) buf.fetch(A, row_of(cf.t), cf.kb);
+                cf.advance2(A.kb);
+            };
+            int kb_cur = cf.kb;  // k-block of iteration `it` (convert() does not need it, kept for symmetry)
+            auto step = [&](const Producer<Q_RABITQ> &cur, Producer<Q_RABITQ> &far) {
+                fetch_next(far, it + 4);
                 const int st = it % STAGES2;
                 const uint32_t ph = (it / STAGES2) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
-                cur.convert(A, c0.kb, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
+                cur.convert(A, kb_cur, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+                it += 2;
+            };
+            fetch_next(b0, it);
+            fetch_next(b1, it + 2);
+            while (it < total_it) {
+                step(b0, b2);
+                if (it >= total_it) break;
+                step(b1, b0);
+                if (it >= total_it) break;
+                step(b2, b1);
             }
         } else {
+            // Three register buffers in rotation: while iteration `it` is converted, the loads of it + 2 and it + 4 (one and
+            // two steps of this group ahead) are in flight — one step (two k-blocks of MMA time) is shorter than the
+            // L2 latency under load, which left the MMA waiting for B (ncu: the producers' top stall was the load result).
             const int slab = ((warp - PROD_WARP0) & 3) * 32;
-            ProducerBytes<CODEC> cur, nxt;
+            ProducerBytes<CODEC> b0, b1, b2;
             typename ProducerBytes<CODEC>::Rows rows;
-            Cursor c2;
-            c2.init(grp, A.kb);
-            rows.set(A, half_begin + (int64_t)c2.t * TILE_ROWS + slab, lane);
-            if (grp < total_it) nxt.fetch(rows, c2.kb);
-            for (int it = grp; it < total_it; it += 2) {
-                cur = nxt;
-                if (c2.advance2(A.kb)) rows.set(A, half_begin + (int64_t)c2.t * TILE_ROWS + slab, lane);
-                if (it + 2 < total_it) nxt.fetch(rows, c2.kb);
+            Cursor cf;  // cursor of the iteration whose loads are issued next
+            cf.init(grp, A.kb);
+            rows.set(A, half_begin + (int64_t)cf.t * TILE_ROWS + slab, lane);
+            int it = grp;
+            auto fetch_next = [&](ProducerBytes<CODEC> &buf, int it_f) {
+                if (it_f < total_it) buf.fetch(rows, cf.kb);
+                if (cf.advance2(A.kb)) rows.set(A, half_begin + (int64_t)cf.t * TILE_ROWS + slab, lane);
+            };
+            auto step = [&](const ProducerBytes<CODEC> &cur, ProducerBytes<CODEC> &far) {
+                fetch_next(far, it + 4);
                 const int st = it % STAGES2;
                 const uint32_t ph = (it / STAGES2) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
@@ -770,6 +787,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+                it += 2;
+            };
+            fetch_next(b0, it);
+            fetch_next(b1, it + 2);
+            while (it < total_it) {
+                step(b0, b2);
+                if (it >= total_it) break;
+                step(b1, b0);
+                if (it >= total_it) break;
+                step(b2, b1);
             }
         }
     }
