@@ -937,32 +937,85 @@ template <int CODEC>
 __device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, const float *table, int64_t row, int lane) {
     const int64_t dim = E.dim;
     if constexpr (CODEC == Q_SQ8) {
-        // sq8_avx512.c:59-104: one 16-lane accumulator, rec = fma(c, inv, min); diff = q - rec; acc = fma(diff, diff, acc)
+        // sq8_avx512.c:59-104: one 16-lane accumulator, rec = fma(c, inv, min); diff = q - rec; acc = fma(diff, diff, acc).
+        // `table` holds mins | invScales staged in shared memory.  In the lane-transposed layouts lane l's codes of VB
+        // consecutive steps are contiguous: one 16-byte (4-byte) load feeds 16 (4) steps.
         const uint8_t *code = E.codes + row * E.row_bytes;
+        const float *mn = table, *iv = table + dim;
         float acc = 0.0f;
         int64_t j = 0;
+        if (E.layout == 16) {
+            for (; j + 256 <= dim; j += 256) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(code + j + lane * 16));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int s_ = 0; s_ < 16; s_++) {
+                    const int64_t d = j + 16 * s_ + lane;
+                    const float c = u8_to_f32((w[s_ >> 2] >> (8 * (s_ & 3))) & 0xFFu);
+                    const float df = __fsub_rn(qs[d], __fmaf_rn(c, iv[d], mn[d]));
+                    acc = __fmaf_rn(df, df, acc);
+                }
+            }
+        } else if (E.layout == 4) {
+            for (; j + 64 <= dim; j += 64) {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(code + j + lane * 4));
+#pragma unroll
+                for (int s_ = 0; s_ < 4; s_++) {
+                    const int64_t d = j + 16 * s_ + lane;
+                    const float c = u8_to_f32((w >> (8 * s_)) & 0xFFu);
+                    const float df = __fsub_rn(qs[d], __fmaf_rn(c, iv[d], mn[d]));
+                    acc = __fmaf_rn(df, df, acc);
+                }
+            }
+        }
         for (; j + 16 <= dim; j += 16) {
             const int64_t d = j + lane;
-            const float df = __fsub_rn(qs[d], sq8_value(E, code, d));
+            const float df = __fsub_rn(qs[d], __fmaf_rn(u8_to_f32(__ldg(code + sq8_off(d, E.layout))), iv[d], mn[d]));
             acc = __fmaf_rn(df, df, acc);
         }
         float tot = reduce16(acc);
         if (lane == 0)
             for (int64_t d = j; d < dim; d++) {
-                const float df = __fsub_rn(qs[d], sq8_value(E, code, d));
+                const float df = __fsub_rn(qs[d], __fmaf_rn(u8_to_f32(__ldg(code + sq8_off(d, E.layout))), iv[d], mn[d]));
                 tot = __fmaf_rn(df, df, tot);
             }
         return tot;
     } else if constexpr (CODEC == Q_INT4) {
-        // int4_avx512.c:193-299: S1 takes the first two 16-dim blocks of every 64, S2 the last two; 32-blocks into S1
+        // int4_avx512.c:193-299: S1 takes the first two 16-dim blocks of every 64, S2 the last two; 32-blocks into S1.
+        // `table` holds min | diff staged in shared memory.  Permuted layout: lanes 2p, 2p+1 share the 16 bytes at 16 p of
+        // every 128-byte block, byte 4 e + b of them holds dims 64 e + 16 b + 2 p (+1).
         const uint8_t *code = E.codes + row * E.row_bytes;
+        const float *mn = table, *df_ = table + dim;
+        const float k15 = __uint_as_float(0x3d888889u);
+        auto val = [&](int64_t d, float nib) { return __fmaf_rn(__fmul_rn(nib, k15), df_[d], mn[d]); };
         float s1 = 0.0f, s2 = 0.0f;
         int64_t i = 0;
+        if (E.layout) {
+            const int sh = (lane & 1) ? 0 : 4;  // even lane (even dim) = high nibble
+            for (; i + 256 <= dim; i += 256) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4 *>(code + (i >> 1) + (lane >> 1) * 16));
+                const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+#pragma unroll
+                    for (int b = 0; b < 4; b++) {
+                        const int64_t d = i + 64 * e + 16 * b + lane;
+                        const float nib = u8_to_f32((w[e] >> (8 * b + sh)) & 0xFu);
+                        const float e_ = __fsub_rn(qs[d], val(d, nib));
+                        if (b < 2) s1 = __fmaf_rn(e_, e_, s1);
+                        else s2 = __fmaf_rn(e_, e_, s2);
+                    }
+            }
+        }
+        auto nibble = [&](int64_t d) {
+            const uint32_t b = __ldg(code + int4_off(d, E.layout));
+            return u8_to_f32((d & 1) ? (b & 0x0Fu) : (b >> 4));
+        };
         for (; i + 64 <= dim; i += 64) {
 #pragma unroll
             for (int blk = 0; blk < 4; blk++) {
                 const int64_t d = i + blk * 16 + lane;
-                const float e = __fsub_rn(qs[d], int4_value(E, code, d));
+                const float e = __fsub_rn(qs[d], val(d, nibble(d)));
                 if (blk < 2) s1 = __fmaf_rn(e, e, s1);
                 else s2 = __fmaf_rn(e, e, s2);
             }
@@ -971,14 +1024,14 @@ __device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, co
 #pragma unroll
             for (int blk = 0; blk < 2; blk++) {
                 const int64_t d = i + blk * 16 + lane;
-                const float e = __fsub_rn(qs[d], int4_value(E, code, d));
+                const float e = __fsub_rn(qs[d], val(d, nibble(d)));
                 s1 = __fmaf_rn(e, e, s1);
             }
         }
         float tot = reduce16(__fadd_rn(s1, s2));
         if (lane == 0)
             for (int64_t d = i; d < dim; d++) {
-                const float e = __fsub_rn(qs[d], int4_value(E, code, d));
+                const float e = __fsub_rn(qs[d], val(d, nibble(d)));
                 tot = __fmaf_rn(e, e, tot);
             }
         return tot;
@@ -1032,6 +1085,11 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
         for (int w = tid; w < E.words32; w += 128) qw[w] = E.q_words[q * E.words32 + w];
     } else {
         for (int64_t d = tid; d < E.dim; d += 128) qs[d] = E.queries[q * E.q_stride + d];
+        if constexpr (CODEC == Q_SQ8 || CODEC == Q_INT4)
+            for (int64_t d = tid; d < E.dim; d += 128) {  // decode parameters next to the query
+                table[d] = E.p0[d];
+                table[E.dim + d] = E.p1[d];
+            }
     }
     topk_init(tk, 1, tid, 128);
     __syncthreads();
@@ -1424,7 +1482,7 @@ static int64_t qtc_group_rows(int64_t rows, int kc) {
 template <int CODEC>
 static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
     const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)LIST_CAP * 4 +
-                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : CODEC == Q_RABITQ ? (size_t)e.words32 * 4 : 0);
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : CODEC == Q_RABITQ ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
     VG_CUDA(cudaFuncSetAttribute(qtc_exact_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     qtc_exact_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e);
