@@ -122,6 +122,10 @@ vg_status vg_pq_build_distance_table(const float *h_queries, int64_t nq, int64_t
  * iterations per subspace, then int8 codebook quantisation. */
 vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
                       int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32 /* optional [m][k][dim/m] */);
+/* ProductQuantizer.Train (internal/quantization/pq.go:68-143) on a training set that is already device-resident
+ * (row-major [n][dim] float32, 16-byte aligned); same outputs, no host copy of the vectors inside the call. */
+vg_status vg_pq_train_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
+                      int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32 /* optional [m][k][dim/m] */);
 
 /* OptimizedProductQuantizer (opq.go:28-282, svd.go:13-216).  Rotations are [dim/block][block][block] float32,
  * block = vg_opq_block_size(dim, m) (NewOptimizedProductQuantizer's rule, opq.go:41-58).

@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout -s KILL 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_flat_tc.py -x -q > gpurun_out/pytest_gpu_z.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu_z.log
+timeout -s KILL 300 python tools/bench_configs.py c5 2>&1 | cut -c1-330
+timeout -s KILL 300 python tools/bench_configs.py c5 2>&1 | cut -c200-330

@@ -146,6 +146,69 @@ __global__ void __launch_bounds__(256) pq_assign_small_kernel(const float *vecs,
     assign[(int64_t)g * n + r] = (uint32_t)idx;
 }
 
+// Same assignment with two CENTROIDS per packed instruction (sm_100a FADD2 / FFMA2, each half an IEEE round-to-nearest
+// op): the table is staged as (-c_{2j,i}, -c_{2j+1,i}) pairs, d = x + (-c) equals x - c exactly, and the two sums come
+// out bit-identical to the scalar chain.  K must be even.
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t km_pk2(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void km_unpk2(f32x2_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2_t km_add2(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t km_fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+template <int DS>
+__global__ void __launch_bounds__(256) pq_assign_small2_kernel(const float *vecs, int64_t n, int64_t dim, int K,
+                                                               const float *cent /*[G][K][DS]*/, uint32_t *assign /*[G][n]*/) {
+    extern __shared__ __align__(16) float sc[];  // [K/2][DS] pairs (-c_even, -c_odd)
+    const int g = blockIdx.y;
+    f32x2_t *sp = reinterpret_cast<f32x2_t *>(sc);
+    for (int i = threadIdx.x; i < (K / 2) * DS; i += blockDim.x) {
+        const int j = i / DS, d = i - j * DS;
+        const float *c0 = cent + ((int64_t)g * K + 2 * j) * DS;
+        sp[i] = km_pk2(-c0[d], -c0[DS + d]);
+    }
+    __syncthreads();
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    f32x2_t x2[DS];
+#pragma unroll
+    for (int i = 0; i < DS; i++) {
+        const float x = vecs[r * dim + (int64_t)g * DS + i];
+        x2[i] = km_pk2(x, x);
+    }
+    float best = 3.402823466e+38f;
+    int idx = 0;
+    for (int j = 0; j < K / 2; j++) {
+        f32x2_t tot = 0ull;
+#pragma unroll
+        for (int i = 0; i < DS; i++) {
+            const f32x2_t d = km_add2(x2[i], sp[j * DS + i]);
+            tot = km_fma2(d, d, tot);
+        }
+        float t0, t1;
+        km_unpk2(tot, t0, t1);
+        if (t0 < best) {
+            best = t0;
+            idx = 2 * j;
+        }
+        if (t1 < best) {
+            best = t1;
+            idx = 2 * j + 1;
+        }
+    }
+    assign[(int64_t)g * n + r] = (uint32_t)idx;
+}
+
 // changed[g] |= (new != old); old = new  (assignments start at zero, pq.go:349)
 __global__ void __launch_bounds__(256) diff_assign_kernel(const uint32_t *newa, int32_t *olda, int64_t n, int G, const int *active,
                                                           int *changed) {
@@ -370,6 +433,34 @@ __global__ void __launch_bounds__(256) gather_centroid_kernel(const float *vecs,
 // subspaces of the same sample (whole rows, coalesced), the distances go through a shared-memory transpose and the
 // min-update of mind[g][i0 .. i0+PP_ROWS) is written as contiguous segments.
 constexpr int PP_ROWS = 64;
+// simd.SquaredL2 for a subspace shorter than 64 dims = the kernel's FMA scalar tail (floats_avx512.s:316-323):
+// sum = fma(d, d, sum) in order.  DS known at compile time: 16-byte loads, fully unrolled chain.
+template <int DS>
+__device__ __forceinline__ float sql2_tail_fixed(const float *a, const float *b) {
+    float tot = 0.0f;
+    if constexpr (DS % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < DS; i += 4) {
+            const float4 x = *reinterpret_cast<const float4 *>(a + i), y = __ldg(reinterpret_cast<const float4 *>(b + i));
+            float d = __fsub_rn(x.x, y.x);
+            tot = __fmaf_rn(d, d, tot);
+            d = __fsub_rn(x.y, y.y);
+            tot = __fmaf_rn(d, d, tot);
+            d = __fsub_rn(x.z, y.z);
+            tot = __fmaf_rn(d, d, tot);
+            d = __fsub_rn(x.w, y.w);
+            tot = __fmaf_rn(d, d, tot);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < DS; i++) {
+            const float d = __fsub_rn(a[i], b[i]);
+            tot = __fmaf_rn(d, d, tot);
+        }
+    }
+    return tot;
+}
+template <int DS>  // DS = 0: any subspace length (sql2_pair_thread)
 __global__ void __launch_bounds__(256) pp_dist_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int G, int c,
                                                       const float *cent, const int *zero, float *mind /*[G][n]*/) {
     extern __shared__ float sd[];  // [G][PP_ROWS + 1]
@@ -379,7 +470,11 @@ __global__ void __launch_bounds__(256) pp_dist_kernel(const float *vecs, int64_t
         const int r = p / G, g = p - r * G;
         const int64_t i = i0 + r;
         float d = 0.0f;
-        if (i < n) d = sql2_pair_thread(vecs + i * stride + (int64_t)g * ds, cent + ((int64_t)g * K + c) * ds, ds);
+        if (i < n) {
+            const float *a = vecs + i * stride + (int64_t)g * ds, *b = cent + ((int64_t)g * K + c) * ds;
+            if constexpr (DS > 0) d = sql2_tail_fixed<DS>(a, b);
+            else d = sql2_pair_thread(a, b, ds);
+        }
         sd[g * (PP_ROWS + 1) + r] = d;
     }
     __syncthreads();
@@ -426,14 +521,27 @@ __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t 
         __syncwarp();
         if (t + 1 < tiles) pp_load_tile(m, n, t + 1, buf[(t + 1) & 1], lane);
         if (lane == 0) ck[t] = sum;
+        // the chain is one dependent FADD per element (4 cycles); the shared-memory reads of the NEXT 32 elements are issued
+        // before the current 32 are added, so their latency stays out of the chain
         const float4 *b4 = reinterpret_cast<const float4 *>(buf[t & 1]);
-#pragma unroll 8
-        for (int j = 0; j < PP_TILE / 4; j++) {
-            const float4 v = b4[j];
-            sum = __fadd_rn(sum, v.x);
-            sum = __fadd_rn(sum, v.y);
-            sum = __fadd_rn(sum, v.z);
-            sum = __fadd_rn(sum, v.w);
+        float4 cur[8], nxt[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) cur[u] = b4[u];
+#pragma unroll 1
+        for (int j = 8; j <= PP_TILE / 4; j += 8) {
+            if (j < PP_TILE / 4) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) nxt[u] = b4[j + u];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                sum = __fadd_rn(sum, cur[u].x);
+                sum = __fadd_rn(sum, cur[u].y);
+                sum = __fadd_rn(sum, cur[u].z);
+                sum = __fadd_rn(sum, cur[u].w);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) cur[u] = nxt[u];
         }
         __syncwarp();
     }
@@ -531,7 +639,8 @@ template <int DS>
 static vg_status launch_small_assign(const float *d_vecs, int64_t n, int64_t dim, int G, int K, const float *d_cent,
                                      uint32_t *d_assign, cudaStream_t st) {
     dim3 grid((unsigned)((n + 255) / 256), (unsigned)G);
-    pq_assign_small_kernel<DS><<<grid, 256, (size_t)K * DS * 4, st>>>(d_vecs, n, dim, K, d_cent, d_assign);
+    if (K % 2 == 0 && DS <= 16) pq_assign_small2_kernel<DS><<<grid, 256, (size_t)K * DS * 4, st>>>(d_vecs, n, dim, K, d_cent, d_assign);
+    else pq_assign_small_kernel<DS><<<grid, 256, (size_t)K * DS * 4, st>>>(d_vecs, n, dim, K, d_cent, d_assign);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -578,7 +687,10 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
         VG_LAUNCHED();
         const size_t pp_sm = (size_t)G * (PP_ROWS + 1) * 4;
-        if (pp_sm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(pp_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_sm));
+        // subspace lengths with a compile-time kernel (16-byte loads, unrolled chain); the row stride must keep them aligned
+        const int dsk = (dim % 4 == 0 && (ds == 4 || ds == 8 || ds == 16 || ds == 32)) ? ds : 0;
+        auto pp_dist = dsk == 4 ? pp_dist_kernel<4> : dsk == 8 ? pp_dist_kernel<8> : dsk == 16 ? pp_dist_kernel<16> : dsk == 32 ? pp_dist_kernel<32> : pp_dist_kernel<0>;
+        if (pp_sm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(pp_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_sm));
         for (int c = 0; c < K; c++) {
             if (c > 0) {
                 pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
@@ -589,7 +701,7 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
                                                                        cent.as<float>());
             VG_LAUNCHED();
             if (c + 1 < K) {
-                pp_dist_kernel<<<(unsigned)((n + PP_ROWS - 1) / PP_ROWS), 256, pp_sm, st>>>(d_vecs, n, dim, ds, K, G, c, cent.as<float>(),
+                pp_dist<<<(unsigned)((n + PP_ROWS - 1) / PP_ROWS), 256, pp_sm, st>>>(d_vecs, n, dim, ds, K, G, c, cent.as<float>(),
                                                                                             zero.as<int>(), mind.as<float>());
                 VG_LAUNCHED();
             }
@@ -686,6 +798,26 @@ vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, in
     VG_TRY(v.alloc((size_t)n * dim * 4));
     VG_TRY(staged_h2d(v.p, h_vecs, (size_t)n * dim * 4));
     VG_TRY(dev_pq_train(v.as<float>(), n, dim, m, k, iters, seed, cent, cb, sc, of, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    VG_TRY(staged_d2h(h_codebooks, cb.p, (size_t)G * K * ds));
+    VG_TRY(staged_d2h(h_scales, sc.p, (size_t)G * 4));
+    VG_TRY(staged_d2h(h_offsets, of.p, (size_t)G * 4));
+    if (h_centroids_f32) VG_TRY(staged_d2h(h_centroids_f32, cent.p, (size_t)G * K * ds * 4));
+    return VG_OK;
+}
+
+// Same with the training set already resident on the device (the writer staged the segment's vectors, or they were
+// generated there): no host copy of the vectors inside the call.
+vg_status vg_pq_train_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
+                          int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32) {
+    VG_TRY(ensure_init());
+    if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
+    if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");
+    cudaStream_t st = stream();
+    const int G = (int)m, K = (int)k, ds = (int)(dim / m);
+    DevBuf cent, cb, sc, of;
+    VG_TRY(dev_pq_train(d_vecs, n, dim, m, k, iters, seed, cent, cb, sc, of, st));
     VG_CUDA(cudaStreamSynchronize(st));
     VG_TRY(staged_d2h(h_codebooks, cb.p, (size_t)G * K * ds));
     VG_TRY(staged_d2h(h_scales, sc.p, (size_t)G * 4));
