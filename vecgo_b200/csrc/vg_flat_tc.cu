@@ -450,13 +450,19 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * BN);
             const int64_t nh = n0 + colhalf * BN;
+            // the TMEM load of chunk c + 1 is issued before chunk c is reduced (tcgen05.wait::ld at the top of the next
+            // iteration): with few k-blocks per tile (d = 128) the epilogue, not the MMA, sets the pace
+            uint32_t vn[32];
+            tmem_ld32(taddr, vn);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; c++) {
                 uint32_t v[32];
-                tmem_ld32(taddr + (uint32_t)(c * 32), v);
                 uint32_t mw = 0xFFFFFFFFu;
                 if (A.mask) mw = (nh + c * 32 < A.rows) ? __ldg(A.mask + ((nh + c * 32) >> 5)) : 0u;
                 tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; j++) v[j] = vn[j];
+                if (c + 1 < BN / 32) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vn);
                 float s[32];
                 const float4 *x4 = reinterpret_cast<const float4 *>(xt + colhalf * BN + c * 32);
 #pragma unroll
@@ -556,16 +562,16 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2 *mins, int6
     const float INF = __int_as_float(0x7f800000);
     const float2 *src = mins + q * groups;
     const int trigger = C - 32;
-    // 4 independent coalesced loads per lane per step (the loop is otherwise bound by L2 latency)
-    for (int64_t g0 = 0; g0 < groups; g0 += 128) {
-        float v[4];
+    // 8 independent coalesced loads per lane per step (the loop is otherwise bound by L2 latency)
+    for (int64_t g0 = 0; g0 < groups; g0 += 256) {
+        float v[8];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             const int64_t g = g0 + u * 32 + lane;
             v[u] = g < groups ? __ldcg(&src[g].x) : INF;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
+        for (int u = 0; u < 8; u++) {
             const int64_t g = g0 + u * 32 + lane;
             if (g < groups) {
                 const unsigned long long key = ((unsigned long long)f32_orderable(v[u]) << 32) | (unsigned long long)(uint32_t)g;
