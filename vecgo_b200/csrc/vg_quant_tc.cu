@@ -607,17 +607,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         const uint32_t keep_hi = A.keep_hi;
         float g1 = BIG, g2 = BIG;
         int cc = 0;
+        // row norms of a tile are fetched one tile ahead (global-load latency out of the per-tile critical path): the value
+        // for tile t + 1 is loaded at the top of tile t and stored after tile t's columns are reduced
+        auto xn_of = [&](int t_) {
+            const int64_t n0 = row_begin + (int64_t)t_ * TILE_ROWS;
+            const int64_t row = n0 + et;
+            return (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
+        };
+        if (ntiles > 0) xs[et] = xn_of(0);
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
             const int64_t n0 = row_begin + (int64_t)t * TILE_ROWS;
             float *xt = xs + as * TILE_ROWS;
-            {
-                const int64_t row = n0 + et;  // 256 epilogue threads stage the 256 row norms of the tile
-                // RaBitQ: xn = the stored norm ||y||; a padding row gets 1e19 so that s' = yn * (yn + f_q acc) ~ 1e38 stays finite
-                xt[et] = (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
-            }
             asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float xn_next = (t + 1 < ntiles) ? xn_of(t + 1) : 0.0f;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * BN);
@@ -669,6 +673,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                     cc = 0;
                 }
             }
+            if (t + 1 < ntiles) xs[((t + 1) & 1) * TILE_ROWS + et] = xn_next;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
