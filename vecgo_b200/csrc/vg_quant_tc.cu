@@ -203,6 +203,21 @@ struct Producer<Q_PQ> {
             g[c] = __ldg(reinterpret_cast<const uint2 *>(A.codebooks + (((int64_t)m * 256 + code) << A.dsub_shift) + o));
         }
     }
+    // same gather from a 16 KB codebook slice in shared memory (the subspaces of k-block kb start at byte 0 of the slice)
+    __device__ __forceinline__ void gather_smem(const KArgs &A, uint2 c8, int kb, uint32_t slice) {
+        const unsigned long long cw = ((unsigned long long)c8.y << 32) | c8.x;
+        const int m0 = (kb * 64) >> A.dsub_shift;
+        const int mb = m0 & ~7;
+        const int dsub = 1 << A.dsub_shift;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const int d0 = kb * 64 + 8 * c;
+            const int m = d0 >> A.dsub_shift, o = d0 & (dsub - 1);
+            const uint32_t code = (uint32_t)(cw >> (8 * (m - mb))) & 0xFFu;
+            const uint32_t addr = slice + ((((uint32_t)(m - m0) << 8) + code) << A.dsub_shift) + (uint32_t)o;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g[c].x), "=r"(g[c].y) : "r"(addr));
+        }
+    }
     __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -506,7 +521,7 @@ constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
 constexpr int TILE_ROWS = 2 * BN;       // 256 rows per pair tile
 constexpr size_t OFF_XN2 = (size_t)STAGES2 * STAGE2_BYTES;
 constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)2 * TILE_ROWS * 4;
-constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 4) * 8 + 16 + 1024;
+constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 8) * 8 + 16 + 1024;
 
 }  // namespace pair
 
@@ -526,22 +541,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
     if (row_end > A.rows) row_end = A.rows;
     const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
 
+    // PQ trades one pipeline stage for a two-slot ring of 16 KB codebook slices (the int8 centroids of the subspaces of one
+    // k-block, bulk-copied by the TMA thread): the decode warps gather from shared memory instead of from L2.
+    constexpr int NST = CODEC == Q_PQ ? STAGES2 - 1 : STAGES2;
+    constexpr uint32_t SLICE_BYTES = 16384;  // 64 dims x 256 centroids x 1 byte, whatever dsub is
+    constexpr uint32_t OFF_SLICE = (uint32_t)NST * STAGE2_BYTES;
+    constexpr uint32_t OFF_XN = OFF_SLICE + (CODEC == Q_PQ ? 2 * SLICE_BYTES : 0);
+    constexpr uint32_t OFF_BAR = OFF_XN + 2 * TILE_ROWS * 4;
     const uint32_t s_base = smem_u32(smem);
-    const uint32_t bar0 = s_base + (uint32_t)OFF_BAR2;
+    const uint32_t bar0 = s_base + OFF_BAR;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES2 + s); };
-    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * STAGES2 + s); };
-    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES2 + 2 + s); };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (NST + s); };
+    auto tfull_bar = [&](int s) { return bar0 + 8u * (2 * NST + s); };
+    auto tempty_bar = [&](int s) { return bar0 + 8u * (2 * NST + 2 + s); };
+    auto sfull_bar = [&](int s) { return bar0 + 8u * (2 * NST + 4 + s); };
+    auto sempty_bar = [&](int s) { return bar0 + 8u * (2 * NST + 6 + s); };
     constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages x 256 columns
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES2; s++) {
+        for (int s = 0; s < NST; s++) {
             mbar_init(full_bar(s), 1 + 4 + 4);  // leader's expect_tx arrive + one decode group (4 warps) of each CTA
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
             mbar_init(tempty_bar(s), 8 + 8);    // epilogue warps of both CTAs
+            mbar_init(sfull_bar(s), 1);         // codebook slice landed (PQ)
+            mbar_init(sempty_bar(s), 4);        // the four warps of decode group s are done gathering from it
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -561,9 +587,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         // ===================== TMA producer: this CTA's half of the query k-block =====================
         if (lane == 0) {
             for (int it = 0; it < total_it; it++) {
-                const int st = it % STAGES2;
-                const uint32_t ph = (it / STAGES2) & 1;
+                const int st = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 const int kb = it % A.kb;
+                if constexpr (CODEC == Q_PQ) {  // slice of iteration `it` into slot it % 2 (= the decode group that handles it)
+                    const int slot = it & 1;
+                    mbar_wait(sempty_bar(slot), ((uint32_t)(it >> 1) & 1) ^ 1);
+                    mbar_expect_tx(sfull_bar(slot), SLICE_BYTES);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                     s_base + OFF_SLICE + (uint32_t)slot * SLICE_BYTES),
+                                 "l"(A.codebooks + (int64_t)kb * SLICE_BYTES), "r"(SLICE_BYTES), "r"(sfull_bar(slot))
+                                 : "memory");
+                }
                 mbar_wait(empty_bar(st), ph ^ 1);
                 if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
                 tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
@@ -581,8 +616,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_ROWS);
                 for (int kb = 0; kb < A.kb; kb++, it++) {
-                    const int st = it % STAGES2;
-                    const uint32_t ph = (it / STAGES2) & 1;
+                    const int st = it % NST;
+                    const uint32_t ph = (it / NST) & 1;
                     mbar_wait_cluster(full_bar(st), ph);
                     tc_fence_after();
                     const uint32_t sa = s_base + st * STAGE2_BYTES;
@@ -601,7 +636,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         const int colhalf = (warp - 2) >> 2;
         const int et = (warp - 2) * 32 + lane;
         const int64_t q = (int64_t)q0 + quad * 32 + lane;
-        float *xs = reinterpret_cast<float *>(smem + OFF_XN2);
+        float *xs = reinterpret_cast<float *>(smem + OFF_XN);
         const float BIG = 3.0e38f;
         const float fq = q < A.nq ? __ldg(A.fq + q) : 0.0f;
         const uint32_t keep_hi = A.keep_hi;
@@ -706,27 +741,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 const int64_t row = half_begin + (int64_t)t * TILE_ROWS + r;
                 return row < A.rows ? row : A.rows - 1;
             };
-            Producer<Q_PQ> cur, nxt;
-            uint2 cnn = make_uint2(0u, 0u);
+            // codes of iterations it, it + 2, it + 4 in flight (8 bytes each); the centroid bytes come from the slice ring
+            Producer<Q_PQ> cur;
             Cursor c0, c2, c4;
             c0.init(grp, A.kb);
             c2 = c0;
             c2.advance2(A.kb);
             c4 = c2;
             c4.advance2(A.kb);
-            if (grp < total_it) nxt.gather(A, Producer<Q_PQ>::load_codes(A, row_of(c0.t), c0.kb), c0.kb);
-            if (grp + 2 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(c2.t), c2.kb);
+            uint2 k0 = make_uint2(0u, 0u), k2 = k0, k4 = k0;
+            if (grp < total_it) k0 = Producer<Q_PQ>::load_codes(A, row_of(c0.t), c0.kb);
+            if (grp + 2 < total_it) k2 = Producer<Q_PQ>::load_codes(A, row_of(c2.t), c2.kb);
+            const uint32_t slice = s_base + OFF_SLICE + (uint32_t)grp * SLICE_BYTES;
             for (int it = grp; it < total_it; it += 2) {
-                cur = nxt;
-                if (it + 2 < total_it) nxt.gather(A, cnn, c2.kb);
-                if (it + 4 < total_it) cnn = Producer<Q_PQ>::load_codes(A, row_of(c4.t), c4.kb);
-                const int st = it % STAGES2;
-                const uint32_t ph = (it / STAGES2) & 1;
+                if (it + 4 < total_it) k4 = Producer<Q_PQ>::load_codes(A, row_of(c4.t), c4.kb);
+                mbar_wait(sfull_bar(grp), (uint32_t)(it >> 1) & 1);
+                cur.gather_smem(A, k0, c0.kb, slice);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(sempty_bar(grp));  // the slot may take the slice of it + 2
+                const int st = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
                 cur.convert(A, c0.kb, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+                k0 = k2;
+                k2 = k4;
                 c0 = c2;
                 c2 = c4;
                 c4.advance2(A.kb);
@@ -750,8 +791,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             int kb_cur = cf.kb;  // k-block of iteration `it` (convert() does not need it, kept for symmetry)
             auto step = [&](const Producer<Q_RABITQ> &cur, Producer<Q_RABITQ> &far) {
                 fetch_next(far, it + 4);
-                const int st = it % STAGES2;
-                const uint32_t ph = (it / STAGES2) & 1;
+                const int st = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
                 cur.convert(A, kb_cur, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
@@ -785,8 +826,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             };
             auto step = [&](const ProducerBytes<CODEC> &cur, ProducerBytes<CODEC> &far) {
                 fetch_next(far, it + 4);
-                const int st = it % STAGES2;
-                const uint32_t ph = (it / STAGES2) & 1;
+                const int st = it % NST;
+                const uint32_t ph = (it / NST) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
                 cur.convert(s_base + st * STAGE2_BYTES + A2_BYTES, slab, lane);
                 fence_proxy_async_smem();
