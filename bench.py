@@ -225,8 +225,18 @@ def run_ours(a):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's version / debug lines must not share stdout with the JSON line
+        # NCCL's version / debug lines must not share stdout with the JSON line: fd 1 points at stderr while the
+        # communicator is created (NCCL prints "NCCL version ..." to stdout at NCCL_DEBUG=VERSION and above)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        torch.cuda.set_device(local)
+        dist.barrier()  # forces the communicator (and its banner) into existence now
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     torch.cuda.set_device(local)
     dev = torch.device(f"cuda:{local}")
     L.call("vg_init", local)
@@ -417,6 +427,15 @@ def run_ours(a):
     hq = queries.cpu().numpy()
     h2d, d2h = hq.nbytes, nq * k * 8 + nq * 4
     if world > 1:
+        # every rank gets the whole query batch from ITS pinned host copy and reads the merged result back into pinned
+        # host memory; the buffers are allocated once, the copies are inside the timed region
+        hq_pin = torch.from_numpy(hq).pin_memory()
+        dq = torch.empty((nq, dim), dtype=torch.float32, device=dev)
+        out_pin = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                   torch.empty((nq,), dtype=torch.int32).pin_memory())
+        dq.copy_(hq_pin, non_blocking=True)
+        sh.search_dev(dq, nq, k)  # untimed: first use of the buffers
+        torch.cuda.synchronize()
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -424,9 +443,12 @@ def run_ours(a):
         if world == 1:
             ix.search(hq, k)
         else:
-            dq = torch.from_numpy(hq).pin_memory().to(dev, non_blocking=True)
+            dq.copy_(hq_pin, non_blocking=True)
             r_, s_, c_ = sh.search_dev(dq, nq, k)
-            r_.cpu(), s_.cpu(), c_.cpu()
+            out_pin[0].copy_(r_, non_blocking=True)
+            out_pin[1].copy_(s_, non_blocking=True)
+            out_pin[2].copy_(c_, non_blocking=True)
+            torch.cuda.synchronize()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
