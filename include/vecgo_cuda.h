@@ -74,7 +74,11 @@ vg_status vg_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes);
 vg_status vg_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes);
 /* Number of kernels this library has launched since load (for gpu_launches). */
 uint64_t vg_launch_count(void);
-/* Run subsequent kernels on this CUDA stream (cudaStream_t as integer; 0 = library default). */
+/* Run subsequent kernels, copies and stream-ordered allocations on this CUDA stream (cudaStream_t as integer).
+ * 0 is the legacy default stream (what PyTorch's default stream reports), NOT "unset": a caller that prepares inputs
+ * on stream 0 and passes 0 gets correct ordering.  VG_STREAM_LIBRARY (~0) switches back to the library's own
+ * non-blocking stream, which is also what is used before the first call. */
+#define VG_STREAM_LIBRARY (~0ull)
 vg_status vg_set_stream(uint64_t cuda_stream);
 
 /* ------------------------------------------------ simd kernel-table mirrors

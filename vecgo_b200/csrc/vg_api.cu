@@ -277,8 +277,11 @@ vg_status vg_synchronize(void) {
 }
 vg_status vg_set_stream(uint64_t cuda_stream) {
     VG_TRY(ensure_init());
-    g_user_stream = reinterpret_cast<cudaStream_t>(cuda_stream);
-    g_user_stream_set = cuda_stream != 0;
+    // 0 is a real stream handle (the legacy default stream, what torch.cuda.current_stream().cuda_stream returns for
+    // PyTorch's default stream): the library must run ON it, otherwise its own non-blocking stream races with the
+    // caller's work on stream 0.  ~0 switches back to the library's own stream.
+    g_user_stream_set = cuda_stream != ~0ull;
+    g_user_stream = g_user_stream_set ? reinterpret_cast<cudaStream_t>(cuda_stream) : nullptr;
     return VG_OK;
 }
 vg_status vg_dev_alloc(void **d_ptr, size_t bytes) {
