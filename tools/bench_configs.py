@@ -3,6 +3,11 @@ configs), against the measured roofline.  One JSON line per config.  Not the dri
 is committed under profiles/ as the per-config evidence SURVEY.md §8(d) asks for.
 
     python tools/bench_configs.py [c1 c1big c2a c2b c3 c4 c5] [--small]
+
+Under torchrun (WORLD_SIZE > 1) only c3 and c4 run: every rank holds ONE shard of the 8-GPU layout (25M PQ rows /
+12.5M RaBitQ rows, i.e. weak scaling: W x 25M rows at W GPUs), scans it for the whole query batch, and the per-shard
+top-k lists go through the NCCL all-gather + device merge (C4: the two-exchange global-top-R rerank).
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 tools/bench_configs.py c3 c4
 """
 import ctypes as C
 import json
@@ -19,6 +24,9 @@ import vecgo_b200 as vg
 L = vg._lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SMALL = "--small" in sys.argv
+WORLD = int(os.environ.get("WORLD_SIZE", "1"))
+RANK = int(os.environ.get("RANK", "0"))
+LOCAL = int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def peaks():
@@ -33,17 +41,25 @@ HBM, TF, SRC = peaks()
 
 
 def timed(fn, warm=2, reps=3):
+    import torch.distributed as dist
+
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
+        if WORLD > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
         torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
+        t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if WORLD > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        ts.append(float(t.item()))
     return float(np.median(ts))
 
 
@@ -59,15 +75,17 @@ def out_bufs(nq, k, dev):
 
 
 def emit(name, workload, ms, nq, pairs, bytes_per_pair=None, flops=None, extra=None):
-    line = {"config": name, "workload": workload, "ms": ms, "qps": nq / ms * 1e3 if nq else None, "gpairs_per_s": pairs / ms / 1e6}
+    if RANK != 0:
+        return
+    line = {"config": name, "n_gpus": WORLD, "workload": workload, "ms": ms, "qps": nq / ms * 1e3 if nq else None, "gpairs_per_s": pairs / ms / 1e6}
     if bytes_per_pair is not None:
         ach = pairs * bytes_per_pair / ms / 1e6
-        line["roofline"] = {"bound": "hbm", "achieved_gbs": ach, "peak_gbs": HBM, "frac": ach / HBM, "peak_source": SRC}
+        line["roofline"] = {"bound": "hbm", "achieved_gbs": ach, "peak_gbs": HBM * WORLD, "frac": ach / (HBM * WORLD), "peak_source": SRC}
     if flops is not None:
         if "roofline" in line:
             line["hbm_equivalent"] = line.pop("roofline")  # per-query streaming bytes of the reference / time, vs the HBM peak
         ach = flops / ms / 1e9
-        line["roofline"] = {"bound": "tensor", "achieved_tflops": ach, "peak_tflops_bf16": TF, "frac": ach / TF, "peak_source": SRC,
+        line["roofline"] = {"bound": "tensor", "achieved_tflops": ach, "peak_tflops_bf16": TF * WORLD, "frac": ach / (TF * WORLD), "peak_source": SRC,
                             "note": "useful FLOPs 2*Q*N*d of the filter GEMM (Flat: TF32, nominal dense peak half of bf16; quantized scans: fp16)"}
     if extra:
         line.update(extra)
@@ -122,10 +140,10 @@ def sq(name, codec, n, dim, nq, k):
 
 
 def pq(name, n, dim, m, nq, k):
-    dev = torch.device("cuda:0")
-    g = torch.Generator(device=dev).manual_seed(42)
+    dev = torch.device(f"cuda:{LOCAL}")
+    g = torch.Generator(device=dev).manual_seed(42 + RANK)
     rng = np.random.default_rng(0)
-    ix = vg.index.DeviceIndex(codec=L.CODEC_PQ, metric=0, dim=dim, rows=n,
+    ix = vg.index.DeviceIndex(codec=L.CODEC_PQ, metric=0, dim=dim, rows=n, row_base=RANK * n,
                               pq=(rng.integers(-128, 128, m * 256 * (dim // m), dtype=np.int8), np.full(m, 0.01, np.float32),
                                   np.zeros(m, np.float32), m, 256))
     chunk = 1 << 22
@@ -133,21 +151,26 @@ def pq(name, n, dim, m, nq, k):
         mm = min(chunk, n - r0)
         codes = torch.randint(0, 256, (mm, m), dtype=torch.uint8, device=dev, generator=g)
         ix.upload_dev(mm, d_codes=codes.data_ptr(), row0=r0)
-    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
+    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=torch.Generator(device=dev).manual_seed(43))  # replicated
     r, s, c = out_bufs(nq, k, dev)
+    sh = vg.sharded.ShardedIndex(ix, descending=False)
     st0 = qtc_stats()
-    ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
+    if WORLD > 1:
+        ms = timed(lambda: sh.search_dev(q, nq, k), warm=1, reps=2)
+    else:
+        ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
     st1 = qtc_stats()
-    emit(name, f"PQ M={m} x 256 ADC scan, {n} rows ({dim}-d), {nq} queries, k={k} (per-GPU shard of the 8-GPU config)", ms, nq, n * nq,
-         bytes_per_pair=m, flops=2.0 * n * nq * dim,
+    emit(name, f"PQ M={m} x 256 ADC scan, {WORLD} x {n} rows ({dim}-d), {nq} queries, k={k} (one 25M-row shard of the 8-GPU config per GPU"
+         + (", NCCL all-gather + device merge of the per-shard top-k)" if WORLD > 1 else ")"), ms, nq, WORLD * n * nq,
+         bytes_per_pair=m, flops=2.0 * WORLD * n * nq * dim,
          extra={"tensor_core_filter": {"queries": st1[0] - st0[0], "exact_rerun_queries": st1[1] - st0[1]}})
     ix.close()
 
 
 def rabitq(name, n, dim, nq, r_top, k):
-    dev = torch.device("cuda:0")
-    g = torch.Generator(device=dev).manual_seed(42)
-    ix = vg.index.DeviceIndex(codec=L.CODEC_RABITQ, metric=0, dim=dim, rows=n)
+    dev = torch.device(f"cuda:{LOCAL}")
+    g = torch.Generator(device=dev).manual_seed(42 + RANK)
+    ix = vg.index.DeviceIndex(codec=L.CODEC_RABITQ, metric=0, dim=dim, rows=n, row_base=RANK * n)
     chunk = 1 << 18
     code_bytes = dim // 8 + 4
     codes = torch.empty((chunk, code_bytes), dtype=torch.uint8, device=dev)
@@ -159,15 +182,16 @@ def rabitq(name, n, dim, nq, r_top, k):
         ix.upload_dev(mm, d_codes=codes.data_ptr(), d_vectors=x.data_ptr(), row0=r0)
     torch.cuda.synchronize()
     gen_s = time.time() - t0
-    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
+    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=torch.Generator(device=dev).manual_seed(43))  # replicated
     sh = vg.sharded.ShardedIndex(ix, descending=False)
     rr, ss, cc = out_bufs(nq, r_top, dev)
     st0 = qtc_stats()
     ms_scan = timed(lambda: ix.search_dev(q.data_ptr(), nq, r_top, rr.data_ptr(), ss.data_ptr(), cc.data_ptr()), warm=1, reps=2)
     ms = timed(lambda: sh.search_rerank_dev(q, nq, r_top, k), warm=1, reps=2)
     st1 = qtc_stats()
-    emit(name, f"RaBitQ 1-bit scan + float32 rerank of top-{r_top}, {n} x {dim}, {nq} queries, final k={k} (per-GPU shard)", ms, nq, n * nq,
-         bytes_per_pair=code_bytes, flops=2.0 * n * nq * dim,
+    emit(name, f"RaBitQ 1-bit scan + float32 rerank of top-{r_top}, {WORLD} x {n} x {dim}, {nq} queries, final k={k} (one 12.5M-row shard of "
+         "the 8-GPU config per GPU" + (", two NCCL exchanges: global top-R, then exact scores)" if WORLD > 1 else ")"), ms, nq, WORLD * n * nq,
+         bytes_per_pair=code_bytes, flops=2.0 * WORLD * n * nq * dim,
          extra={"scan_only_ms": ms_scan, "rerank_and_merge_ms": ms - ms_scan, "generate_encode_upload_s": gen_s,
                 "tensor_core_filter": {"queries": st1[0] - st0[0], "exact_rerun_queries": st1[1] - st0[1]}})
     ix.close()
@@ -201,7 +225,22 @@ def pqtrain(name, n, dim, m, iters):
 
 def main():
     which = [a for a in sys.argv[1:] if not a.startswith("-")] or ["c1", "c1big", "c2a", "c2b", "c3", "c4", "c5"]
-    L.call("vg_init", 0)
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        which = [w for w in which if w in ("c3", "c4")]
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)  # NCCL banners go to stderr
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{LOCAL}"))
+        torch.cuda.set_device(LOCAL)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os.dup2(saved, 1)
+        os.close(saved)
+    torch.cuda.set_device(LOCAL)
+    L.call("vg_init", LOCAL)
     L.call("vg_set_stream", torch.cuda.current_stream().cuda_stream)
     for w in which:
         if w == "c1":
@@ -219,6 +258,10 @@ def main():
             rabitq("C4", 2_000_000 if SMALL else 12_500_000, 1536, 512 if SMALL else 1000, 1000, 100)
         elif w == "c5":
             pqtrain("C5", 100_000 if SMALL else 1_000_000, 768, 96, 25)
+    if WORLD > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
