@@ -304,3 +304,23 @@ def test_opq_index_through_the_filter(vg):
     assert qtc_stats(vg)[0] - before[0] == nq
     r2, s2, c2 = exact_scan(vg, make, q, k)
     assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)
+
+
+def test_tc_sparse_mask_returns_fewer_than_k(vg):
+    """A row bitmap that keeps 5 rows with k = 10: the filter cannot certify (fewer than k scored rows), the exact scan answers."""
+    n, dim, nq, k = 30000, 128, 20, 10
+    rng = np.random.default_rng(8)
+    v = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    sq = vg.quantization.ScalarQuantizer(dim)
+    sq.Train(v)
+    codes = sq.EncodeBatch(v)
+    keep = np.zeros(n, bool)
+    keep[[7, 4097, 12000, 12001, 29999]] = True
+    mask = np.packbits(keep, bitorder="little")
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(sq.mins, sq.invScales)) as ix:
+        ix.upload(codes=codes)
+        rows, scores, counts = ix.search(q, k, row_mask=mask)
+    want = oracle_flat(q, k, dim=dim, metric=0, quant=1, codes=codes, mins=sq.mins, inv=sq.invScales, mask=mask)
+    check(rows, scores, counts, want)
+    assert np.all(counts == 5)
