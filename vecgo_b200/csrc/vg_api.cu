@@ -54,7 +54,7 @@ vg_status ensure_init() {
 // Scratch buffers (per-call temporaries: query copies, partial top-k lists, result staging) come from the device's
 // stream-ordered memory pool — after warm-up an allocation is a pointer bump instead of a 100+ us cudaMalloc/cudaFree
 // pair, which matters for small batches.  Large, long-lived buffers (code / vector sections) use cudaMalloc.
-static const size_t kPoolMaxBytes = (size_t)4608 << 20;  // includes the <= 4 GiB group-minima buffers of the tensor-core filters
+static const size_t kPoolMaxBytes = (size_t)8704 << 20;  // includes the <= 8 GiB group-minima buffers of the tensor-core filters
 vg_status DevBuf::alloc(size_t n) {
     release();
     if (n == 0) n = 16;

@@ -1664,8 +1664,9 @@ vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, 
     const int kc = candidates_for(io.k);
     const int64_t G = qtc_group_rows(io.rows, kc);
     const int64_t groups = (io.rows + G - 1) / G;
-    // the [queries][groups] minima buffer is kept under 4 GiB: long batches go through in chunks of whole query tiles
-    int64_t chunk = std::max<int64_t>(BMQ, ((4ll << 30) / (groups * 8)) / BMQ * BMQ);
+    // the [queries][groups] minima buffer is kept under 8 GiB: longer batches go through in chunks of whole query tiles
+    // (the headline shape — 10k queries x 78k groups = 6.4 GB — is one launch: one tail instead of two)
+    int64_t chunk = std::max<int64_t>(BMQ, ((8ll << 30) / (groups * 8)) / BMQ * BMQ);
     DevBuf failb;
     VG_TRY(failb.alloc((size_t)io.nq * 4));
     for (int64_t q0 = 0; q0 < io.nq; q0 += chunk) {
