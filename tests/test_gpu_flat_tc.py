@@ -196,3 +196,29 @@ def test_kmeans_train_tc_matches_exact_path(vg):
         out.append(vg.kmeans.TrainKMeans(v, dim, k, 0, 5, init_rows=init, seed=3, return_assign=True))
     vg._lib.call("vg_flat_tc_enable", 1)
     assert np.array_equal(bits(out[0][0]), bits(out[1][0])) and np.array_equal(out[0][1], out[1][1]) and out[0][2] == out[1][2]
+
+
+@pytest.mark.parametrize("metric,k", [(0, 10), (2, 32)])
+def test_tc_long_segment_short_vectors_min_only_epilogue(vg, metric, k):
+    """>= 2^20 rows with d <= 256: the pair kernel keeps only group minima and the exact stage scores whole groups."""
+    n, dim, nq = 1_100_000, 64, 40
+    rng = np.random.default_rng(77)
+    x = (rng.random((n, dim), dtype=F) - (0.5 if metric else 0.0)).astype(F)
+    q = (rng.random((nq, dim), dtype=F) - (0.5 if metric else 0.0)).astype(F)
+    if metric == 2:
+        x, _ = vg.distance.NormalizeL2Batch(x)
+    x[n // 2] = x[n // 3]
+    vg._lib.call("vg_flat_tc_enable", 1)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=metric, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        before = tc_stats(vg)
+        rows, scores, counts = ix.search(q, k)
+        after = tc_stats(vg)
+        vg._lib.call("vg_flat_tc_enable", 0)
+        try:
+            r2, s2, c2 = ix.search(q, k)
+        finally:
+            vg._lib.call("vg_flat_tc_enable", 1)
+    assert after[0] - before[0] == nq
+    assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)
+    check(rows[:4], scores[:4], counts[:4], oracle_topk(q[:4], k, dim=dim, metric=metric, vectors=x))

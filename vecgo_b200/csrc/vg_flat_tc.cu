@@ -334,8 +334,11 @@ struct Args2 {
     uint32_t idx_mask, keep_hi;
 };
 
-template <bool IS_DOT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+// EPW = epilogue warps per CTA: 8 (thread = query x 128 columns of the tile) or 16 (query x 64 columns).  With few k-blocks
+// per tile (d <= 256) the epilogue sets the pace and runs at the latency of its dependent min chains; four warps per
+// scheduler instead of two hide that latency (groups are then at most 64 rows).
+template <bool IS_DOT, int EPW, bool MINONLY>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__((2 + EPW) * 32, 1)
 flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, Args2 A) {
     using namespace pairf;
     extern __shared__ unsigned char smem_raw[];
@@ -366,7 +369,7 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
-            mbar_init(tempty_bar(s), 8 + 8);
+            mbar_init(tempty_bar(s), EPW + EPW);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -425,9 +428,10 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             }
         }
     } else {
-        // ===================== epilogue: warps 2..9; thread = one query x one 128-column half of the tile =====================
+        // ===================== epilogue: warps 2 .. 2+EPW-1; thread = one query x CPT columns of the tile =====================
+        constexpr int CPT = TILE_ROWS / (EPW / 4);  // columns (rows of the tile) per thread: 128 or 64
         const int quad = warp & 3;
-        const int colhalf = (warp - 2) >> 2;
+        const int colhalf = (warp - 2) >> 2;        // which CPT-column part
         const int et = (warp - 2) * 32 + lane;
         const int64_t q = (int64_t)q0 + quad * 32 + lane;
         float *xs = reinterpret_cast<float *>(smem + OFF_XN2);
@@ -443,33 +447,33 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
             const int64_t row = n0 + et;
             return (row < row_end) ? (IS_DOT ? 0.0f : __ldg(A.xn + row)) : BIG;
         };
-        if (ntiles > 0) xs[et] = xn_of(0);
+        if (ntiles > 0 && et < TILE_ROWS) xs[et] = xn_of(0);
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
             const int64_t n0 = row_begin + (int64_t)t * TILE_ROWS;
             float *xt = xs + as * TILE_ROWS;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float xn_next = (t + 1 < ntiles) ? xn_of(t + 1) : 0.0f;
+            asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");
+            const float xn_next = (t + 1 < ntiles && et < TILE_ROWS) ? xn_of(t + 1) : 0.0f;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * BN);
-            const int64_t nh = n0 + colhalf * BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * CPT);
+            const int64_t nh = n0 + colhalf * CPT;
             // the TMEM load of chunk c + 1 is issued before chunk c is reduced (tcgen05.wait::ld at the top of the next
             // iteration): with few k-blocks per tile (d = 128) the epilogue, not the MMA, sets the pace
             uint32_t vn[32];
             tmem_ld32(taddr, vn);
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
+            for (int c = 0; c < CPT / 32; c++) {
                 uint32_t v[32];
                 uint32_t mw = 0xFFFFFFFFu;
                 if (A.mask) mw = (nh + c * 32 < A.rows) ? __ldg(A.mask + ((nh + c * 32) >> 5)) : 0u;
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; j++) v[j] = vn[j];
-                if (c + 1 < BN / 32) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vn);
+                if (c + 1 < CPT / 32) tmem_ld32(taddr + (uint32_t)((c + 1) * 32), vn);
                 float s[32];
-                const float4 *x4 = reinterpret_cast<const float4 *>(xt + colhalf * BN + c * 32);
+                const float4 *x4 = reinterpret_cast<const float4 *>(xt + colhalf * CPT + c * 32);
 #pragma unroll
                 for (int j4 = 0; j4 < 8; j4++) {
                     const float4 xv = x4[j4];
@@ -481,6 +485,18 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
                 }
+                if constexpr (MINONLY) {
+                    // Short contractions (d <= 256) over long segments: the epilogue is bound by the ALU pipe (LOP3 and FMNMX issue every other
+                    // cycle per scheduler), so only the group MINIMUM is kept — one FFMA + one FMNMX per element — and stored
+                    // as (m, m): the selection then treats every selected group as crowded and the exact stage scores all of
+                    // its (<= 64) rows.  Unscored rows are exactly the rows of unselected groups, s >= m >= tau.
+                    float a1[4] = {BIG, BIG, BIG, BIG};
+#pragma unroll
+                    for (int j = 0; j < 32; j++) a1[j & 3] = fminf(a1[j & 3], s[j]);
+                    const float c1 = fminf(fminf(a1[0], a1[1]), fminf(a1[2], a1[3]));
+                    g1 = fminf(g1, c1);
+                    g2 = g1;
+                } else {
                 float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
@@ -497,6 +513,7 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                 const float c2 = fminf(fmaxf(p1, r1), fminf(p2, r2));
                 g2 = fminf(fmaxf(g1, c1), fminf(g2, c2));
                 g1 = fminf(g1, c1);
+                }
                 if (++cc == A.cpg) {
                     const int64_t gid = (nh + c * 32) / (32 * (int64_t)A.cpg);
                     if (gid < A.groups) A.mins[q * A.groups + gid] = make_float2(g1, g2);
@@ -505,7 +522,7 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
                     cc = 0;
                 }
             }
-            if (t + 1 < ntiles) xs[((t + 1) & 1) * TILE_ROWS + et] = xn_next;
+            if (t + 1 < ntiles && et < TILE_ROWS) xs[((t + 1) & 1) * TILE_ROWS + et] = xn_next;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
@@ -926,7 +943,8 @@ bool uses_pair(const FilterArgs &f) {
 }
 int64_t filter_group_rows(const FilterArgs &f) {
     const int64_t G = group_rows(f.rows, f.kc);
-    return uses_pair(f) ? std::min<int64_t>(G, 128) : G;  // pair kernel: a group stays inside one thread's 128-column half
+    if (!uses_pair(f)) return G;
+    return std::min<int64_t>(G, f.dim <= 256 ? 64 : 128);  // pair kernel: a group stays inside one thread's 128 (64) columns
 }
 vg_status make_shadow16(const float *d_x, int64_t rows, int64_t dim, int dimp, int sx_exp, void *d_x16, cudaStream_t st) {
     const int64_t total = rows * dimp;
@@ -936,15 +954,17 @@ vg_status make_shadow16(const float *d_x, int64_t rows, int64_t dim, int dimp, i
     return VG_OK;
 }
 
-template <bool IS_DOT>
+template <bool IS_DOT, int EPW, bool MINONLY>
 static vg_status launch_pair(const CUtensorMap &mq, const CUtensorMap &mx, const Args2 &a, int64_t qtiles, int splits, cudaStream_t st) {
     const size_t sm = pairf::SMEM2_BYTES;
-    VG_CUDA(cudaFuncSetAttribute(flat2_kernel<IS_DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VG_CUDA(cudaFuncSetAttribute(flat2_kernel<IS_DOT, EPW, MINONLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)(2 * qtiles), (unsigned)splits);
-    flat2_kernel<IS_DOT><<<grid, NTHREADS, sm, st>>>(mq, mx, a);
+    flat2_kernel<IS_DOT, EPW, MINONLY><<<grid, (2 + EPW) * 32, sm, st>>>(mq, mx, a);
     VG_LAUNCHED();
     return VG_OK;
 }
+// sixteen epilogue warps when a tile has at most four k-blocks of MMA work (d <= 256)
+static bool pair_wide_epilogue(const FilterArgs &f) { return f.dim <= 256; }
 
 // The filter on the CTA-pair fp16 kernel (f.d_x16 set).
 static vg_status filter_pair(const FilterArgs &f, cudaStream_t st) {
@@ -992,8 +1012,16 @@ static vg_status filter_pair(const FilterArgs &f, cudaStream_t st) {
     a.groups = groups;
     a.idx_mask = (uint32_t)(G - 1);
     a.keep_hi = ~31u;
-    if (f.is_dot) VG_TRY((launch_pair<true>(mq, mx, a, qtiles, (int)splits, st)));
-    else VG_TRY((launch_pair<false>(mq, mx, a, qtiles, (int)splits, st)));
+    if (pair_wide_epilogue(f)) {
+        // minimum-only epilogue (every selected group scored whole, <= kc * 64 rows per query) when the GEMM dominates:
+        // on a 100k-row segment the larger exact stage costs more than the epilogue saves (measured 0.19 -> 0.28 ms)
+        const bool minonly = f.rows >= (1ll << 20);
+        if (f.is_dot) VG_TRY(minonly ? (launch_pair<true, 16, true>(mq, mx, a, qtiles, (int)splits, st)) : (launch_pair<true, 16, false>(mq, mx, a, qtiles, (int)splits, st)));
+        else VG_TRY(minonly ? (launch_pair<false, 16, true>(mq, mx, a, qtiles, (int)splits, st)) : (launch_pair<false, 16, false>(mq, mx, a, qtiles, (int)splits, st)));
+    } else {
+        if (f.is_dot) VG_TRY((launch_pair<true, 8, false>(mq, mx, a, qtiles, (int)splits, st)));
+        else VG_TRY((launch_pair<false, 8, false>(mq, mx, a, qtiles, (int)splits, st)));
+    }
     VG_TRY(select_groups(a.mins, groups, f.nq, f.kc, G, f.d_tau, f.d_gids, f.d_gcnt, st));
     return VG_OK;  // a16 / fq / mins are returned to the stream-ordered pool (freed in stream order); tensor maps were copied at launch
 }
