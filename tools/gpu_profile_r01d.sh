@@ -9,7 +9,7 @@ timeout -s KILL 900 python bench.py > gpurun_out/bench_n1_d.json 2> gpurun_out/b
 timeout -s KILL 400 python bench.py --impl reference --steps 1 --warmup 0 > gpurun_out/bench_ref_d.json 2> gpurun_out/bench_ref_d.err; echo "bench ref rc=$?"
 timeout -s KILL 600 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_bench_d.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/bench_under_ncu_d.log 2>&1; echo "launch list rc=$?"
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:qtc2_kernel -s 2 -c 1 \
+timeout -s KILL 600 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:qtc2_kernel -s 1 -c 1 \
     -o gpurun_out/qtc2_sq8_full_d -f python bench.py --steps 1 --warmup 1 --no-cpu-baseline > gpurun_out/qtc2_sq8_full_d.log 2>&1; echo "set full rc=$?"
 ncu -i gpurun_out/qtc2_sq8_full_d.ncu-rep --page raw --csv > gpurun_out/qtc2_sq8_full_d_raw.csv 2>/dev/null
 ncu -i gpurun_out/qtc2_sq8_full_d.ncu-rep --page details > gpurun_out/qtc2_sq8_full_d_details.txt 2>/dev/null

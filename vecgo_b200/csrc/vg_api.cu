@@ -172,6 +172,7 @@ struct Index {
     // decode-GEMM filter state of the quantized scans (vg_quant_tc.cu), rebuilt after code uploads
     qtc::Prepared qtc;
     bool qtc_dirty = true;
+    std::mutex prep_mu;   // lazy filter state (row norms, fp16 shadow, decode tables) is built once even if searches race
     size_t device_bytes() const {
         return codes.bytes + vectors.bytes + p0.bytes + p1.bytes + norms.bytes + ids.bytes + pq_cb.bytes + centroids.bytes;
     }
@@ -499,6 +500,7 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
 // Flat float32 search through the tcgen05 filter (vg_flat_tc.cu): candidates by TF32 GEMM, exact re-check in simd
 // pair order, certificate; queries whose certificate fails are re-run on the exact CUDA-core scan below.
 static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(ix->prep_mu);
     if (!ix->xn_dirty && ix->xn.p) return VG_OK;
     const int64_t rows = ix->d.rows;
     if (!ix->xn.p) VG_TRY(ix->xn.alloc_persistent((size_t)rows * 4));
@@ -585,6 +587,7 @@ static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArg
     if ((reinterpret_cast<uintptr_t>(a.mask) & 3) != 0) return VG_OK;  // the filter reads the row bitmap as 32-bit words
     if (a.q_stride != 0 && a.q_stride != d.dim) return VG_OK;
     cudaStream_t st = stream();
+    std::unique_lock<std::mutex> prep_lock(ix->prep_mu);
     if (ix->qtc_dirty || !ix->qtc.ready) {
         const bool pq = d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ;
         const size_t np = pq ? (size_t)d.pq_m : (size_t)d.dim;
@@ -597,6 +600,7 @@ static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArg
         VG_TRY(qtc::prepare(cp, d.rows, h0.data(), h1.data(), ix->qtc, st));
         ix->qtc_dirty = false;
     }
+    prep_lock.unlock();
     qtc::SearchIO io;
     io.d_queries = a.queries;
     io.q_stride = a.q_stride;
