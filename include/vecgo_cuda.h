@@ -214,6 +214,12 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
  * query against its r candidate rows (local row ids); rows >= RowCount give NaN. */
 vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores);
 vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, float *d_scores);
+/* Quantized gather scoring: the codec's own distance of every query to ITS r candidate rows (local row ids; rows >=
+ * RowCount give NaN), in the reference's arithmetic — what the DiskANN traversal evaluates per neighbour
+ * (internal/segment/diskann/segment.go:511-588: pq.AdcDistance, int4.L2Distance, rabitq.Distance), batched.  SQ8
+ * (L2), INT4, PQ / OPQ (K = 256) and RaBitQ; a float32 index scores exactly (= vg_index_rerank). */
+vg_status vg_index_score(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores);
+vg_status vg_index_score_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, float *d_scores);
 /* Approximate scan to top-r, exact rerank, final top-k (engine refine path,
  * internal/engine/search.go:188-192,913-973), all on device. */
 vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t nq, int64_t r, int64_t k,

@@ -112,6 +112,8 @@ _SIGS = {
     "vg_index_rerank": [u64, f32p, i64, u32p, i64, f32p],
     "vg_index_rerank_dev": [u64, vp, i64, vp, i64, vp],
     "vg_index_search_rerank": [u64, f32p, i64, i64, i64, u32p, f32p, i32p],
+    "vg_index_score": [u64, f32p, i64, u32p, i64, f32p],
+    "vg_index_score_dev": [u64, vp, i64, vp, i64, vp],
     "vg_flat_tc_enable": [i32],
     "vg_flat_tc_stats": [u64p, u64p],
     "vg_quant_tc_stats": [u64p, u64p],

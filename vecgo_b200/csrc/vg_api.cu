@@ -816,6 +816,63 @@ vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, co
     return staged_d2h(h_scores, scores.p, (size_t)nq * r * 4);
 }
 
+// Quantized gather scoring (DiskANN neighbour-list scoring, diskann/segment.go:511-588): the codec's own distance of every
+// query to its r candidate rows, in the reference's arithmetic.  A float32 index scores exactly (Segment.Rerank).
+vg_status vg_index_score_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, float *d_scores) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (nq <= 0 || r <= 0) return VG_OK;
+    const vg_index_desc &d = ix->d;
+    if (d.codec == VG_CODEC_F32) return vg_index_rerank_dev(idx, d_queries, nq, d_rows, r, d_scores);
+    if (d.codec == VG_CODEC_BQ) return fail(VG_ERR_UNSUPPORTED, "gather scoring covers SQ8, INT4, PQ, OPQ and RaBitQ");
+    if (!ix->has_codes) return fail(VG_ERR_STATE, "index rows were never uploaded");
+    cudaStream_t st = stream();
+    CodecParams cp = params_of(*ix);
+    DevBuf qwords, qnorms, rotated;
+    const float *queries = d_queries;
+    if (d.codec == VG_CODEC_RABITQ) {
+        VG_TRY(qwords.alloc((size_t)nq * ix->words32 * 4));
+        VG_CUDA(cudaMemsetAsync(qwords.p, 0, qwords.bytes, st));
+        VG_TRY(qnorms.alloc((size_t)nq * 4));
+        const int w_live = (int)(((d.dim + 63) / 64) * 2);
+        if (w_live == ix->words32) {
+            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, 0.0f, qwords.as<uint32_t>(), qnorms.as<float>(), st));
+        } else {
+            DevBuf tight;
+            VG_TRY(tight.alloc((size_t)nq * w_live * 4));
+            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, 0.0f, tight.as<uint32_t>(), qnorms.as<float>(), st));
+            VG_CUDA(cudaMemcpy2DAsync(qwords.p, (size_t)ix->words32 * 4, tight.p, (size_t)w_live * 4, (size_t)w_live * 4, (size_t)nq,
+                                      cudaMemcpyDeviceToDevice, st));
+            VG_CUDA(cudaStreamSynchronize(st));
+        }
+        cp.q_words = qwords.as<uint32_t>();
+        cp.q_norms = qnorms.as<float>();
+    }
+    if (d.codec == VG_CODEC_OPQ) {
+        VG_TRY(rotated.alloc((size_t)nq * d.dim * 4));
+        VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), rotated.as<float>(), st));
+        queries = rotated.as<float>();
+    }
+    VG_TRY(qtc::score_rows(cp, d.rows, queries, 0, nq, d_rows, r, d_scores, st));
+    VG_CUDA(cudaStreamSynchronize(st));  // the temporaries above are released on return
+    return VG_OK;
+}
+
+vg_status vg_index_score(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores) {
+    VG_TRY(ensure_init());
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (nq <= 0 || r <= 0) return VG_OK;
+    DevBuf q, rows, scores;
+    VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
+    VG_TRY(to_device(rows, h_rows, (size_t)nq * r));
+    VG_TRY(scores.alloc((size_t)nq * r * 4));
+    VG_TRY(vg_index_score_dev(idx, q.as<float>(), nq, rows.as<uint32_t>(), r, scores.as<float>()));
+    VG_CUDA(cudaStreamSynchronize(stream()));
+    return staged_d2h(h_scores, scores.p, (size_t)nq * r * 4);
+}
+
 // exact scores → keys → per-query top-k (one list per query of length r)
 __global__ void __launch_bounds__(256) rerank_keys_kernel(const uint32_t *rows, const float *scores, int64_t n, uint32_t row_base,
                                                           int descending, unsigned long long *keys) {

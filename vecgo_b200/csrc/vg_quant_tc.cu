@@ -1238,6 +1238,58 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     }
 }
 
+// ------------------------------------------------------------------ gather scoring
+// Quantized distance of every query to ITS r candidate rows, in the reference's arithmetic (the neighbour-list scoring of
+// the DiskANN traversal: internal/segment/diskann/segment.go:511-588 — pq.AdcDistance / int4.L2Distance /
+// rabitq.Distance per neighbour).  One CTA per query stages the query state once (query vector, decode parameters,
+// the PQ distance table built by the generic Go loop, RaBitQ sign words); a half-warp scores one row with exact_score.
+template <int CODEC>
+__global__ void __launch_bounds__(128) qtc_score_kernel(EArgs E, const uint32_t *rows, int r, float *out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
+    float *qs = reinterpret_cast<float *>(smem);
+    const size_t qbytes = ((size_t)E.dim * 4 + 15) & ~(size_t)15;
+    float *table = reinterpret_cast<float *>(smem + qbytes);
+    if constexpr (CODEC == Q_RABITQ) {
+        if (tid == 0) qs[0] = E.q_norms[q];
+        uint32_t *qw = reinterpret_cast<uint32_t *>(table);
+        for (int w = tid; w < E.words32; w += 128) qw[w] = E.q_words[q * E.words32 + w];
+    } else {
+        for (int64_t d = tid; d < E.dim; d += 128) qs[d] = E.queries[q * E.q_stride + d];
+        if constexpr (CODEC == Q_SQ8 || CODEC == Q_INT4)
+            for (int64_t d = tid; d < E.dim; d += 128) {
+                table[d] = E.p0[d];
+                table[E.dim + d] = E.p1[d];
+            }
+    }
+    __syncthreads();
+    if constexpr (CODEC == Q_PQ) {
+        const int ds = E.pq_dsub;
+        for (int idx = tid; idx < E.pq_m * 256; idx += 128) {
+            const int m = idx >> 8;
+            const int8_t *cb = E.codebooks + (int64_t)idx * ds;
+            const float scale = E.pq_scales[m], offset = E.pq_offsets[m];
+            const float *qv = qs + (int64_t)m * ds;
+            float sum = 0.0f;
+            for (int i = 0; i < ds; i++) {
+                const float v = __fadd_rn(__fmul_rn((float)cb[i], scale), offset);
+                const float d = __fsub_rn(qv[i], v);
+                sum = __fadd_rn(sum, __fmul_rn(d, d));
+            }
+            table[idx] = sum;
+        }
+        __syncthreads();
+    }
+    for (int j0 = 0; j0 < r; j0 += 8) {
+        const int j = j0 + hw;
+        const uint32_t row = j < r ? rows[q * r + j] : 0xFFFFFFFFu;
+        const bool valid = (int64_t)row < E.rows;
+        const float tot = exact_score<CODEC>(E, qs, table, valid ? (int64_t)row : 0, lane);
+        if (lane == 0 && j < r) out[q * r + j] = valid ? tot : __uint_as_float(0x7fc00000u);
+    }
+}
+
 // ------------------------------------------------------------------ ||decode(row)||^2 and ||decode(row) - mid||^2
 // One thread per row, eight interleaved float32 accumulators (the values only feed the filter and its bound).
 template <int CODEC>
@@ -1498,6 +1550,32 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     pp.mid_norm = (float)std::sqrt(mm) * 1.0001f;
     pp.ready = true;
     return VG_OK;
+}
+
+template <int CODEC>
+static vg_status launch_score(const EArgs &e, int64_t nq, const uint32_t *d_rows, int r, float *d_out, cudaStream_t st) {
+    const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) +
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : CODEC == Q_RABITQ ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
+    if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the gather-scoring kernel");
+    VG_CUDA(cudaFuncSetAttribute(qtc_score_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    qtc_score_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e, d_rows, r, d_out);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries, int64_t q_stride, int64_t nq, const uint32_t *d_rows,
+                     int64_t r, float *d_out, cudaStream_t st) {
+    if (nq <= 0 || r <= 0) return VG_OK;
+    const int qc = q_codec(cp);
+    if (qc < 0) return fail(VG_ERR_UNSUPPORTED, "codec has no gather-scoring kernel");
+    if (qc == Q_PQ && cp.pq_k != 256) return fail(VG_ERR_UNSUPPORTED, "PQ ADC requires K=256 (simd.PqAdcLookup hard-wires the table stride)");
+    if (qc == Q_SQ8 && (cp.variant & VG_VAR_GO_SCALAR)) return fail(VG_ERR_UNSUPPORTED, "SQ8 gather scoring is the L2 kernel (Sq8uL2BatchPerDimension)");
+    EArgs e = eargs_of(cp, rows);
+    e.queries = d_queries;
+    e.q_stride = q_stride ? q_stride : cp.dim;
+    if (qc == Q_SQ8) return launch_score<Q_SQ8>(e, nq, d_rows, (int)r, d_out, st);
+    if (qc == Q_INT4) return launch_score<Q_INT4>(e, nq, d_rows, (int)r, d_out, st);
+    if (qc == Q_RABITQ) return launch_score<Q_RABITQ>(e, nq, d_rows, (int)r, d_out, st);
+    return launch_score<Q_PQ>(e, nq, d_rows, (int)r, d_out, st);
 }
 
 static int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }

@@ -45,6 +45,11 @@ struct SearchIO {
 // caller re-runs those on the exact scan (scan_topk_subset).
 vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st);
 
+// Quantized distance of query q to its r candidate rows d_rows[q][0..r) (local row ids; rows >= `rows` give NaN), in the
+// reference's arithmetic.  RaBitQ needs cp.q_words / cp.q_norms (prep_sign_queries); OPQ queries must be rotated already.
+vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries, int64_t q_stride, int64_t nq, const uint32_t *d_rows,
+                     int64_t r, float *d_out, cudaStream_t st);
+
 void stats(uint64_t *queries, uint64_t *fallbacks);
 // Returns the accumulated CUDA-event time / launch count of the GEMM kernel since the last reset; enable = 1 / 0 turns
 // the event pair around every GEMM launch on / off and resets the counters, enable < 0 only reads.

@@ -110,6 +110,14 @@ class DeviceIndex:
         L.call("vg_index_rerank", self.handle, L.ptr(q, L.f32p), q.shape[0], L.ptr(r, L.u32p), r.shape[1], L.ptr(out, L.f32p))
         return out
 
+    def score(self, queries, rows):
+        """Quantized gather scoring: the codec's distance of query i to rows[i, :] (DiskANN neighbour-list scoring)."""
+        q = L.as_f32(queries).reshape(-1, self.dim)
+        rr = np.ascontiguousarray(rows, np.uint32).reshape(q.shape[0], -1)
+        out = np.full(rr.shape, np.nan, F)
+        L.call("vg_index_score", self.handle, L.ptr(q, L.f32p), q.shape[0], L.ptr(rr, L.u32p), rr.shape[1], L.ptr(out, L.f32p))
+        return out
+
     def search_rerank(self, queries, r: int, k: int):
         q = L.as_f32(queries).reshape(-1, self.dim)
         nq = q.shape[0]
