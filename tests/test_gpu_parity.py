@@ -611,3 +611,15 @@ def test_opq_train_matches_oracle(vg, n, dim, m, rounds):
     d_self = opq.ComputeAsymmetricDistance(v[0], codes[0])
     d_other = opq.ComputeAsymmetricDistance(v[0], codes[1])
     assert 0 < d_self < d_other
+
+
+def test_kmeanspp_parallel_prefix_equals_sequential_chain():
+    """PQ training with the exact parallel prefix (default) and with the one-lane sequential chain
+    (VECGO_KMEANSPP_SEQUENTIAL=1, its own process): bit-identical codebooks on data full of ties and zero distances."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "kmeanspp_ab.py"), "120000", "64", "8"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr

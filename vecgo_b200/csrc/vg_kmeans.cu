@@ -14,6 +14,7 @@
 #include "vg_flat_tc.cuh"
 #include "vg_kmeans.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 #include "vg_scan.cuh"
@@ -579,6 +580,211 @@ __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t 
         chosen[g] = pick;
     }
 }
+// ---------------------------------------------------------------- exact parallel form of the float32 prefix chain
+// s_{i+1} = fl(s_i + x_i), x_i >= 0, is sequential, but inside one binade of s it is INTEGER arithmetic: with
+// u = ulp(s) and s = S u (S in [2^23, 2^24)), fl(s + x) = (S + round(x / u)) u where round() is to nearest and an
+// exact half goes to the side that makes the result even.  So every element is a function of S of the form
+// S -> S + m (no tie) or S -> S + floor + [(S + floor) odd] (tie; the result is even, so every later tie of the block
+// is decided), a block of elements composes to  F(S) = S + K + t [(S + c) odd]  and these (K, c, t, parity) summaries
+// form a monoid: a block scan gives every thread the exact state at the start of its 32 elements.  The binade
+// changes ~25 times over a million elements; the chunk in which S would reach 2^24 is walked with real FADDs by its
+// thread and the scan restarts behind it with the new ulp.  The result — every 32-element checkpoint and the total —
+// is bit-identical to the sequential loop of pq.go:299-303,327-329 (tests/test_gpu_parity.py: PQ / OPQ training
+// against the sequential oracle; tools/prefix_proto.py is the Python model of the algorithm with its fuzz test).
+constexpr int PX_T = 256;           // threads per group
+constexpr int PX_CH = 32;           // elements per thread per round
+constexpr int PX_HUGE = 1 << 29;    // "certainly leaves the binade"
+struct PxSum {
+    int K;       // increment (saturating at PX_HUGE)
+    int f;       // bit 0: c, bit 1: t (tie seen), bit 2: parity of the output once a tie was seen
+};
+__device__ __forceinline__ PxSum px_compose(PxSum a, PxSum b) {  // b after a
+    PxSum r;
+    if (a.K >= PX_HUGE || b.K >= PX_HUGE) {
+        r.K = PX_HUGE;
+        r.f = 0;
+        return r;
+    }
+    const int ca = a.f & 1, ta = (a.f >> 1) & 1, pa = (a.f >> 2) & 1;
+    const int cb = b.f & 1, tb = (b.f >> 1) & 1, pb = (b.f >> 2) & 1;
+    if (ta) {
+        const int extra = tb & ((pa + cb) & 1);
+        r.K = a.K + b.K + extra;
+        const int pi = tb ? pb : ((pa + b.K) & 1);
+        r.f = ca | 2 | (pi << 2);
+    } else if (tb) {
+        r.K = a.K + b.K;
+        r.f = ((a.K + cb) & 1) | 2 | (pb << 2);
+    } else {
+        r.K = a.K + b.K;
+        r.f = 0;
+    }
+    if (r.K >= PX_HUGE) {
+        r.K = PX_HUGE;
+        r.f = 0;
+    }
+    return r;
+}
+__device__ __forceinline__ int px_apply(PxSum a, int S) { return S + a.K + (((a.f >> 1) & 1) & ((S + (a.f & 1)) & 1)); }
+// summary of up to PX_CH elements (shared-memory row) under ulp 2^Eu
+__device__ __forceinline__ PxSum px_summarize(const float *x, int cnt, int Eu) {
+    int K = 0, c = 0, t = 0, pi = 0;
+    for (int i = 0; i < cnt; i++) {
+        const uint32_t b = __float_as_uint(x[i]);
+        const int ex = (int)((b >> 23) & 0xFF);
+        const uint32_t fr = b & 0x7FFFFFu;
+        const uint32_t M = ex ? (fr | 0x800000u) : fr;
+        if (M == 0) continue;
+        const int E = ex ? ex - 150 : -149;
+        const int d = Eu - E;
+        if (d <= 0 || ex == 255) {
+            K = PX_HUGE;
+            break;
+        }
+        if (d >= 25) continue;
+        const int fl = (int)(M >> d);
+        const uint32_t rem = M & ((1u << d) - 1u), half = 1u << (d - 1);
+        if (rem != half) {
+            const int m = fl + (rem > half ? 1 : 0);
+            K += m;
+            if (t) pi = (pi + m) & 1;
+        } else if (!t) {
+            c = (K + fl) & 1;
+            K += fl;
+            t = 1;
+            pi = 0;
+        } else {
+            K += fl + ((pi + fl) & 1);
+            pi = 0;
+        }
+        if (K >= PX_HUGE) {
+            K = PX_HUGE;
+            break;
+        }
+    }
+    PxSum r;
+    r.K = K;
+    r.f = K >= PX_HUGE ? 0 : (c | (t << 1) | (pi << 2));
+    return r;
+}
+// One CTA per group: checkpoints ck[g][chunk] = running sum before element 32 * chunk, the total, then the k-means++
+// pick (pq.go:305-320) by binary search over the checkpoints (the chain is non-decreasing) + a 32-element walk.
+__global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *mind, int64_t n, int c, uint64_t seed, int *zero,
+                                                                int64_t *chosen, float *ckpt /*[G][chunks]*/) {
+    __shared__ float tile[PX_T * (PX_CH + 1)];
+    __shared__ PxSum wsum[PX_T / 32];
+    __shared__ float s_state;
+    __shared__ int s_cross;
+    const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float *m = mind + (int64_t)g * n;
+    const int64_t chunks = (n + PX_CH - 1) / PX_CH;
+    float *ck = ckpt + (int64_t)g * chunks;
+    if (tid == 0) s_state = 0.0f;
+    __syncthreads();
+    int64_t p = 0;
+    while (p < n) {
+        // coalesced load of the next PX_T * PX_CH elements, one padded shared-memory row per thread
+        for (int i = tid; i < PX_T * PX_CH; i += PX_T) {
+            const int64_t e = p + i;
+            tile[(i / PX_CH) * (PX_CH + 1) + (i % PX_CH)] = e < n ? m[e] : 0.0f;
+        }
+        if (tid == 0) s_cross = PX_T;
+        __syncthreads();
+        const float S = s_state;
+        const float *row = tile + tid * (PX_CH + 1);
+        const int64_t my0 = p + (int64_t)tid * PX_CH;
+        const int cnt = my0 >= n ? 0 : (int)((n - my0 < PX_CH) ? (n - my0) : PX_CH);
+        const uint32_t sb = __float_as_uint(S);
+        const int sex = (int)((sb >> 23) & 0xFF);
+        if (sex == 0 || sex == 255) {
+            // zero / denormal / non-finite state: skip whole chunks of zeros, then one thread walks its chunk
+            bool nz = false;
+            if (S == 0.0f)
+                for (int i = 0; i < cnt; i++) nz |= row[i] != 0.0f;
+            else nz = tid == 0;
+            if (nz) atomicMin(&s_cross, tid);
+            __syncthreads();
+            const int f = s_cross;
+            if (cnt > 0 && tid <= f) ck[my0 / PX_CH] = S;   // chunks before the first non-zero one start at S (= 0) too
+            if (tid == f) {
+                float acc = S;
+                for (int i = 0; i < cnt; i++) acc = __fadd_rn(acc, row[i]);
+                s_state = acc;
+            }
+            __syncthreads();
+            p += (int64_t)(f < PX_T ? f + 1 : PX_T) * PX_CH;
+            continue;
+        }
+        const int Eu = sex - 150;
+        const int S0 = (int)((sb & 0x7FFFFFu) | 0x800000u);
+        PxSum mine = px_summarize(row, cnt, Eu);
+        // inclusive scan of the summaries (composition is associative, not commutative: left operand = earlier elements)
+        PxSum inc = mine;
+        for (int o = 1; o < 32; o <<= 1) {
+            PxSum prev;
+            prev.K = __shfl_up_sync(0xffffffffu, inc.K, o);
+            prev.f = __shfl_up_sync(0xffffffffu, inc.f, o);
+            if (lane >= o) inc = px_compose(prev, inc);
+        }
+        if (lane == 31) wsum[warp] = inc;
+        __syncthreads();
+        PxSum before;  // composition of everything before this thread
+        before.K = 0;
+        before.f = 0;
+        for (int w = 0; w < warp; w++) before = px_compose(before, wsum[w]);
+        {
+            PxSum prev;
+            prev.K = __shfl_up_sync(0xffffffffu, inc.K, 1);
+            prev.f = __shfl_up_sync(0xffffffffu, inc.f, 1);
+            if (lane > 0) before = px_compose(before, prev);
+        }
+        const bool prefix_ok = before.K < PX_HUGE;
+        const int s_in = prefix_ok ? px_apply(before, S0) : (1 << 24);
+        const bool crosses = !prefix_ok || s_in >= (1 << 24) || mine.K >= PX_HUGE || s_in + mine.K + 1 >= (1 << 24);
+        if (crosses && cnt > 0) atomicMin(&s_cross, tid);
+        __syncthreads();
+        const int cross = s_cross;
+        if (cnt > 0 && tid <= cross) ck[my0 / PX_CH] = ldexpf((float)s_in, Eu);  // exact: s_in < 2^24
+        if (tid == cross) {
+            float acc = ldexpf((float)s_in, Eu);
+            for (int i = 0; i < cnt; i++) acc = __fadd_rn(acc, row[i]);
+            s_state = acc;
+        } else if (cross == PX_T && tid == PX_T - 1) {
+            s_state = ldexpf((float)px_apply(mine, s_in), Eu);  // state after the last element of the round
+        }
+        __syncthreads();
+        p += (int64_t)(cross < PX_T ? cross + 1 : PX_T) * PX_CH;
+    }
+    __syncthreads();
+    if (tid != 0) return;
+    const float sum = s_state;
+    if (sum == 0.0f) {
+        zero[g] = 1;
+        chosen[g] = rng_intn(seed, (uint64_t)g, (uint64_t)c, n);
+        return;
+    }
+    const float target = __fmul_rn(rng_f32(seed, (uint64_t)g, (uint64_t)c), sum);
+    // last chunk whose start is below the target (checkpoints are non-decreasing); chunk 0 when none is
+    int64_t lo = 0, hi = chunks - 1;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi + 1) >> 1;
+        if (ck[mid] < target) lo = mid;
+        else hi = mid - 1;
+    }
+    int64_t pick = 0;
+    bool found = false;
+    float cum = ck[lo];
+    for (int64_t i = lo * PX_CH; i < n && !found; i++) {
+        cum = __fadd_rn(cum, m[i]);
+        if (cum >= target) {
+            pick = i;
+            found = true;
+        }
+    }
+    zero[g] = 0;
+    chosen[g] = pick;
+}
+
 __global__ void pp_first_kernel(int64_t n, uint64_t seed, int G, int64_t *chosen, int *zero) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
@@ -668,6 +874,15 @@ static vg_status pq_assign_all(const float *d_vecs, int64_t n, int64_t dim, int 
 using namespace vg;
 
 namespace vg {
+// VECGO_KMEANSPP_SEQUENTIAL=1 keeps the one-lane sequential prefix chain (A/B check of the parallel exact form)
+static bool pp_sequential_pick() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECGO_KMEANSPP_SEQUENTIAL");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
 // ProductQuantizer.Train on device-resident vectors (pq.go:68-143,275-433); outputs stay on the device.
 vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed, DevBuf &cent,
                        DevBuf &cb, DevBuf &sc, DevBuf &of, cudaStream_t st) {
@@ -683,7 +898,7 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         VG_TRY(mind.alloc((size_t)G * n * 4));
         VG_TRY(zero.alloc((size_t)G * 4));
         VG_TRY(chosen.alloc((size_t)G * 8));
-        VG_TRY(ckpt.alloc((size_t)G * ((n + PP_TILE - 1) / PP_TILE) * 4));
+        VG_TRY(ckpt.alloc((size_t)G * ((n + PX_CH - 1) / PX_CH) * 4));
         pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
         VG_LAUNCHED();
         const size_t pp_sm = (size_t)G * (PP_ROWS + 1) * 4;
@@ -693,8 +908,11 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         if (pp_sm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(pp_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_sm));
         for (int c = 0; c < K; c++) {
             if (c > 0) {
-                pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
-                                                 ckpt.as<float>());
+                if (pp_sequential_pick())
+                    pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(), ckpt.as<float>());
+                else
+                    pp_pick_parallel_kernel<<<G, PX_T, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
+                                                                ckpt.as<float>());
                 VG_LAUNCHED();
             }
             gather_centroid_kernel<<<(G * ds + 255) / 256, 256, 0, st>>>(d_vecs, dim, ds, K, G, c, chosen.as<int64_t>(),
