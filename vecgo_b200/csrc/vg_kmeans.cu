@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t 
 // changes ~25 times over a million elements; the chunk in which S would reach 2^24 is walked with real FADDs by its
 // thread and the scan restarts behind it with the new ulp.  The result — every 32-element checkpoint and the total —
 // is bit-identical to the sequential loop of pq.go:299-303,327-329 (tests/test_gpu_parity.py: PQ / OPQ training
-// against the sequential oracle; tools/prefix_proto.py is the Python model of the algorithm with its fuzz test).
+// against the sequential chain; tools/prefix_proto.py is the Python model of the algorithm with its fuzz test).
 constexpr int PX_T = 256;           // threads per group
 constexpr int PX_CH = 32;           // elements per thread per round
 constexpr int PX_HUGE = 1 << 29;    // "certainly leaves the binade"
