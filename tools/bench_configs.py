@@ -139,6 +139,26 @@ def sq(name, codec, n, dim, nq, k):
     ix.close()
 
 
+def bq(name, n, dim, nq, k):
+    dev = torch.device("cuda:0")
+    g = torch.Generator(device=dev).manual_seed(42)
+    cb = (dim + 63) // 64 * 8
+    ix = vg.index.DeviceIndex(codec=L.CODEC_BQ, metric=0, dim=dim, rows=n, bq_threshold=0.0)
+    chunk = 1 << 20
+    for r0 in range(0, n, chunk):
+        m = min(chunk, n - r0)
+        codes = torch.randint(0, 256, (m, cb), dtype=torch.uint8, device=dev, generator=g)
+        ix.upload_dev(m, d_codes=codes.data_ptr(), row0=r0)
+    q = torch.randn((nq, dim), dtype=torch.float32, device=dev, generator=g)
+    r, s, c = out_bufs(nq, k, dev)
+    st0 = qtc_stats()
+    ms = timed(lambda: ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr()), warm=1, reps=2)
+    st1 = qtc_stats()
+    emit(name, f"BQ Hamming scan, {n} x {dim} bits, {nq} queries, k={k} (uniform random codes)", ms, nq, n * nq, bytes_per_pair=cb,
+         flops=2.0 * n * nq * dim, extra={"tensor_core_filter": {"queries": st1[0] - st0[0], "exact_rerun_queries": st1[1] - st0[1]}})
+    ix.close()
+
+
 def pq(name, n, dim, m, nq, k):
     dev = torch.device(f"cuda:{LOCAL}")
     g = torch.Generator(device=dev).manual_seed(42 + RANK)
@@ -256,6 +276,8 @@ def main():
             pq("C3", 4_000_000 if SMALL else 25_000_000, 768, 96, 592 if SMALL else 10_000, 100)
         elif w == "c4":
             rabitq("C4", 2_000_000 if SMALL else 12_500_000, 1536, 512 if SMALL else 1000, 1000, 100)
+        elif w == "bq":
+            bq("BQ", 2_000_000 if SMALL else 12_500_000, 1536, 512 if SMALL else 1000, 1000)
         elif w == "c5":
             pqtrain("C5", 100_000 if SMALL else 1_000_000, 768, 96, 25)
     if WORLD > 1:

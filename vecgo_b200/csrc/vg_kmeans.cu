@@ -213,14 +213,28 @@ __global__ void __launch_bounds__(256) pq_assign_small2_kernel(const float *vecs
 // changed[g] |= (new != old); old = new  (assignments start at zero, pq.go:349)
 __global__ void __launch_bounds__(256) diff_assign_kernel(const uint32_t *newa, int32_t *olda, int64_t n, int G, const int *active,
                                                           int *changed) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
-    if (i >= n || !active[g]) return;
-    const int32_t v = (int32_t)newa[(int64_t)g * n + i];
-    if (olda[(int64_t)g * n + i] != v) {
-        olda[(int64_t)g * n + i] = v;
-        changed[g] = 1;
+    if (!active[g]) return;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool diff = false;
+    if ((n & 3) == 0) {  // four samples per thread, 16-byte accesses (rows of n samples stay 16-byte aligned)
+        if (4 * t < n) {
+            const int4 v = *reinterpret_cast<const int4 *>(newa + (int64_t)g * n + 4 * t);
+            int4 *o = reinterpret_cast<int4 *>(olda + (int64_t)g * n + 4 * t);
+            const int4 w = *o;
+            diff = v.x != w.x || v.y != w.y || v.z != w.z || v.w != w.w;
+            if (diff) *o = v;
+        }
+    } else {
+        for (int64_t i = 4 * t; i < n && i < 4 * t + 4; i++) {
+            const int32_t v = (int32_t)newa[(int64_t)g * n + i];
+            if (olda[(int64_t)g * n + i] != v) {
+                olda[(int64_t)g * n + i] = v;
+                diff = true;
+            }
+        }
     }
+    if (__any_sync(0xffffffffu, diff) && (threadIdx.x & 31) == 0) changed[g] = 1;
 }
 // after the assignment pass: a group whose pass changed nothing stops (break before update)
 __global__ void settle_kernel(int *active, int *changed, int *iters, int G) {
@@ -250,17 +264,25 @@ __global__ void __launch_bounds__(256) part_count_kernel(const int32_t *assign, 
     for (int c = threadIdx.x; c < K; c += blockDim.x) counts[((int64_t)g * K + c) * B + b] = hist[c];
 }
 __global__ void __launch_bounds__(256) part_scan_kernel(int *counts, int K, int64_t B, int G, const int *active, int *totals) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per (group, cluster): exclusive scan of its B block counts, 32 at a time (coalesced)
+    const int64_t t = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     if (t >= (int64_t)G * K) return;
     if (!active[t / K]) return;
     int run = 0;
     int *p = counts + t * B;
-    for (int64_t b = 0; b < B; b++) {
-        const int v = p[b];
-        p[b] = run;
-        run += v;
+    for (int64_t b0 = 0; b0 < B; b0 += 32) {
+        const int64_t b = b0 + lane;
+        const int v = b < B ? p[b] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        if (b < B) p[b] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
     }
-    totals[t] = run;
+    if (lane == 0) totals[t] = run;
 }
 __global__ void part_base_kernel(const int *totals, int K, int G, const int *active, int64_t n, int64_t *base) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
@@ -271,8 +293,60 @@ __global__ void part_base_kernel(const int *totals, int K, int G, const int *act
         run += totals[(int64_t)g * K + c];
     }
 }
+// Stable scatter of one block of kSB samples: each of the 8 warps owns 128 consecutive samples; per-warp histograms
+// turn into per-(warp, cluster) start positions, and inside a warp the rank of a sample among the earlier samples of
+// the same cluster comes from __match_any_sync — O(samples) work, members of a cluster stay in sample order.
+constexpr int kScatterMaxK = 2048;  // 8 warps x K counters in shared memory
 __global__ void __launch_bounds__(256) part_scatter_kernel(const int32_t *assign, int64_t n, int K, int64_t B, const int *active,
                                                            const int *counts, const int64_t *base, uint32_t *members) {
+    extern __shared__ int sc_smem[];
+    int *a = sc_smem;         // [kSB]
+    int *hw = sc_smem + kSB;  // [8][K]
+    const int g = blockIdx.y;
+    if (!active[g]) return;
+    const int64_t b = blockIdx.x;
+    const int64_t i0 = b * kSB;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cnt = (int)((n - i0 < kSB) ? (n - i0) : kSB);
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) a[i] = assign[(int64_t)g * n + i0 + i];
+    for (int i = threadIdx.x; i < 8 * K; i += blockDim.x) hw[i] = 0;
+    __syncthreads();
+    constexpr int PER_WARP = kSB / 8;
+    for (int s_ = 0; s_ < PER_WARP; s_ += 32) {
+        const int i = warp * PER_WARP + s_ + lane;
+        if (i < cnt) atomicAdd(&hw[warp * K + a[i]], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        // position inside the group's member list (fits an int: n < 2^31)
+        int run = (int)(base[(int64_t)g * K + c] - (int64_t)g * n) + counts[((int64_t)g * K + c) * B + b];
+        for (int w = 0; w < 8; w++) {
+            const int t = hw[w * K + c];
+            hw[w * K + c] = run;
+            run += t;
+        }
+    }
+    __syncthreads();
+    uint32_t *mem = members + (int64_t)g * n;
+    for (int s_ = 0; s_ < PER_WARP; s_ += 32) {
+        const int i = warp * PER_WARP + s_ + lane;
+        const bool valid = i < cnt;
+        const unsigned vm = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const int key = a[i];
+            const unsigned same = __match_any_sync(vm, key);
+            const int rank = __popc(same & ((1u << lane) - 1u));
+            const int pos = hw[warp * K + key] + rank;
+            mem[pos] = (uint32_t)(i0 + i);
+            __syncwarp(vm);
+            if (rank == 0) hw[warp * K + key] += __popc(same);
+        }
+        __syncwarp();
+    }
+}
+// Any K: one thread per cluster walks the block (O(K x samples)).
+__global__ void __launch_bounds__(256) part_scatter_anyk_kernel(const int32_t *assign, int64_t n, int K, int64_t B, const int *active,
+                                                                const int *counts, const int64_t *base, uint32_t *members) {
     __shared__ int a[kSB];
     const int g = blockIdx.y;
     if (!active[g]) return;
@@ -356,7 +430,7 @@ struct Lloyd {
     // assign_new must hold this pass's assignments.  Returns (via host) whether any group is still active.
     vg_status step(const float *d_vecs, float *d_cent, int reciprocal, uint64_t seed, uint64_t tag_xor, int tag_is_group,
                    bool *any_active, cudaStream_t st) {
-        dim3 gd((unsigned)((n + 255) / 256), (unsigned)G);
+        dim3 gd((unsigned)(((n + 3) / 4 + 255) / 256), (unsigned)G);
         diff_assign_kernel<<<gd, 256, 0, st>>>(assign_new.as<uint32_t>(), assign_old.as<int32_t>(), n, G, active.as<int>(),
                                                changed.as<int>());
         VG_LAUNCHED();
@@ -372,13 +446,20 @@ struct Lloyd {
         dim3 gb((unsigned)B, (unsigned)G);
         part_count_kernel<<<gb, 256, (size_t)K * 4, st>>>(assign_old.as<int32_t>(), n, K, B, active.as<int>(), counts.as<int>());
         VG_LAUNCHED();
-        part_scan_kernel<<<(unsigned)(((int64_t)G * K + 255) / 256), 256, 0, st>>>(counts.as<int>(), K, B, G, active.as<int>(),
+        part_scan_kernel<<<(unsigned)(((int64_t)G * K * 32 + 255) / 256), 256, 0, st>>>(counts.as<int>(), K, B, G, active.as<int>(),
                                                                                   totals.as<int>());
         VG_LAUNCHED();
         part_base_kernel<<<(G + 63) / 64, 64, 0, st>>>(totals.as<int>(), K, G, active.as<int>(), n, base.as<int64_t>());
         VG_LAUNCHED();
-        part_scatter_kernel<<<gb, 256, 0, st>>>(assign_old.as<int32_t>(), n, K, B, active.as<int>(), counts.as<int>(),
-                                                base.as<int64_t>(), members.as<uint32_t>());
+        if (K <= kScatterMaxK) {
+            const size_t ssm = ((size_t)kSB + 8 * (size_t)K) * 4;
+            if (ssm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(part_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+            part_scatter_kernel<<<gb, 256, ssm, st>>>(assign_old.as<int32_t>(), n, K, B, active.as<int>(), counts.as<int>(),
+                                                      base.as<int64_t>(), members.as<uint32_t>());
+        } else {
+            part_scatter_anyk_kernel<<<gb, 256, 0, st>>>(assign_old.as<int32_t>(), n, K, B, active.as<int>(), counts.as<int>(),
+                                                         base.as<int64_t>(), members.as<uint32_t>());
+        }
         VG_LAUNCHED();
         const int64_t chains = (int64_t)G * K * ds;
         centroid_update_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(
@@ -591,9 +672,10 @@ __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t 
 // thread and the scan restarts behind it with the new ulp.  The result — every 32-element checkpoint and the total —
 // is bit-identical to the sequential loop of pq.go:299-303,327-329 (tests/test_gpu_parity.py: PQ / OPQ training
 // against the sequential chain; tools/prefix_proto.py is the Python model of the algorithm with its fuzz test).
-constexpr int PX_T = 256;           // threads per group
+constexpr int PX_T = 1024;          // threads per group (one CTA per group: the whole SM works on one chain)
 constexpr int PX_CH = 32;           // elements per thread per round
 constexpr int PX_HUGE = 1 << 29;    // "certainly leaves the binade"
+constexpr size_t PX_SMEM = (size_t)PX_T * (PX_CH + 1) * 4;
 struct PxSum {
     int K;       // increment (saturating at PX_HUGE)
     int f;       // bit 0: c, bit 1: t (tie seen), bit 2: parity of the output once a tie was seen
@@ -671,22 +753,39 @@ __device__ __forceinline__ PxSum px_summarize(const float *x, int cnt, int Eu) {
 // pick (pq.go:305-320) by binary search over the checkpoints (the chain is non-decreasing) + a 32-element walk.
 __global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *mind, int64_t n, int c, uint64_t seed, int *zero,
                                                                 int64_t *chosen, float *ckpt /*[G][chunks]*/) {
-    __shared__ float tile[PX_T * (PX_CH + 1)];
-    __shared__ PxSum wsum[PX_T / 32];
+    extern __shared__ float tile[];  // [PX_T][PX_CH + 1]
+    __shared__ PxSum wsum[PX_T / 32], wpre[PX_T / 32];
     __shared__ float s_state;
     __shared__ int s_cross;
+    __shared__ int s_cnt[PX_T / 32];
     const int g = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const float *m = mind + (int64_t)g * n;
     const int64_t chunks = (n + PX_CH - 1) / PX_CH;
     float *ck = ckpt + (int64_t)g * chunks;
+    const bool vec_ok = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(mind) & 15) == 0;
     if (tid == 0) s_state = 0.0f;
     __syncthreads();
     int64_t p = 0;
     while (p < n) {
         // coalesced load of the next PX_T * PX_CH elements, one padded shared-memory row per thread
-        for (int i = tid; i < PX_T * PX_CH; i += PX_T) {
-            const int64_t e = p + i;
-            tile[(i / PX_CH) * (PX_CH + 1) + (i % PX_CH)] = e < n ? m[e] : 0.0f;
+        if (vec_ok && p + (int64_t)PX_T * PX_CH <= n) {
+            float4 v[PX_CH / 4];
+#pragma unroll
+            for (int j = 0; j < PX_CH / 4; j++) v[j] = __ldg(reinterpret_cast<const float4 *>(m + p) + j * PX_T + tid);
+#pragma unroll
+            for (int j = 0; j < PX_CH / 4; j++) {
+                const int i = (j * PX_T + tid) * 4;  // element index inside the round: 4 consecutive elements of one row
+                float *dst = tile + (i / PX_CH) * (PX_CH + 1) + (i % PX_CH);
+                dst[0] = v[j].x;
+                dst[1] = v[j].y;
+                dst[2] = v[j].z;
+                dst[3] = v[j].w;
+            }
+        } else {
+            for (int i = tid; i < PX_T * PX_CH; i += PX_T) {
+                const int64_t e = p + i;
+                tile[(i / PX_CH) * (PX_CH + 1) + (i % PX_CH)] = e < n ? m[e] : 0.0f;
+            }
         }
         if (tid == 0) s_cross = PX_T;
         __syncthreads();
@@ -728,10 +827,25 @@ __global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *min
         }
         if (lane == 31) wsum[warp] = inc;
         __syncthreads();
-        PxSum before;  // composition of everything before this thread
-        before.K = 0;
-        before.f = 0;
-        for (int w = 0; w < warp; w++) before = px_compose(before, wsum[w]);
+        if (warp == 0) {  // exclusive scan of the warp summaries
+            PxSum wi = wsum[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                PxSum prev;
+                prev.K = __shfl_up_sync(0xffffffffu, wi.K, o);
+                prev.f = __shfl_up_sync(0xffffffffu, wi.f, o);
+                if (lane >= o) wi = px_compose(prev, wi);
+            }
+            PxSum ex;
+            ex.K = __shfl_up_sync(0xffffffffu, wi.K, 1);
+            ex.f = __shfl_up_sync(0xffffffffu, wi.f, 1);
+            if (lane == 0) {
+                ex.K = 0;
+                ex.f = 0;
+            }
+            wpre[lane] = ex;
+        }
+        __syncthreads();
+        PxSum before = wpre[warp];  // composition of everything before this thread
         {
             PxSum prev;
             prev.K = __shfl_up_sync(0xffffffffu, inc.K, 1);
@@ -756,21 +870,25 @@ __global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *min
         p += (int64_t)(cross < PX_T ? cross + 1 : PX_T) * PX_CH;
     }
     __syncthreads();
-    if (tid != 0) return;
     const float sum = s_state;
     if (sum == 0.0f) {
-        zero[g] = 1;
-        chosen[g] = rng_intn(seed, (uint64_t)g, (uint64_t)c, n);
+        if (tid == 0) {
+            zero[g] = 1;
+            chosen[g] = rng_intn(seed, (uint64_t)g, (uint64_t)c, n);
+        }
         return;
     }
     const float target = __fmul_rn(rng_f32(seed, (uint64_t)g, (uint64_t)c), sum);
-    // last chunk whose start is below the target (checkpoints are non-decreasing); chunk 0 when none is
-    int64_t lo = 0, hi = chunks - 1;
-    while (lo < hi) {
-        const int64_t mid = (lo + hi + 1) >> 1;
-        if (ck[mid] < target) lo = mid;
-        else hi = mid - 1;
-    }
+    // last chunk whose start is below the target (checkpoints are non-decreasing): count them, all threads; chunk 0 when none is
+    int below = 0;
+    for (int64_t j = tid; j < chunks; j += PX_T) below += ck[j] < target ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0) s_cnt[warp] = below;
+    __syncthreads();
+    if (tid != 0) return;
+    int64_t lo = 0;
+    for (int w = 0; w < PX_T / 32; w++) lo += s_cnt[w];
+    lo = lo > 0 ? lo - 1 : 0;
     int64_t pick = 0;
     bool found = false;
     float cum = ck[lo];
@@ -906,12 +1024,13 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         const int dsk = (dim % 4 == 0 && (ds == 4 || ds == 8 || ds == 16 || ds == 32)) ? ds : 0;
         auto pp_dist = dsk == 4 ? pp_dist_kernel<4> : dsk == 8 ? pp_dist_kernel<8> : dsk == 16 ? pp_dist_kernel<16> : dsk == 32 ? pp_dist_kernel<32> : pp_dist_kernel<0>;
         if (pp_sm > 48 * 1024) VG_CUDA(cudaFuncSetAttribute(pp_dist, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pp_sm));
+        VG_CUDA(cudaFuncSetAttribute(pp_pick_parallel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PX_SMEM));
         for (int c = 0; c < K; c++) {
             if (c > 0) {
                 if (pp_sequential_pick())
                     pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(), ckpt.as<float>());
                 else
-                    pp_pick_parallel_kernel<<<G, PX_T, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
+                    pp_pick_parallel_kernel<<<G, PX_T, PX_SMEM, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
                                                                 ckpt.as<float>());
                 VG_LAUNCHED();
             }
