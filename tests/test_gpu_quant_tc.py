@@ -275,6 +275,103 @@ def test_rabitq_tc_matches_oracle(vg, n, dim, nq, k):
     assert np.array_equal(r2, e2) and np.array_equal(bits(s2), bits(es2)) and np.array_equal(c2, ec2)
 
 
+@pytest.mark.parametrize("n,dim,nq,k", [
+    (20000, 1536, 33, 10),      # C4 dimension
+    (9000, 128, 300, 1),        # short codes: heavy ties at the k-th rank, many certificates fail -> exact re-run of those queries
+    (200000, 256, 32, 1000),    # deep result lists
+    (40000, 192, 20, 100),      # 6 sign words padded to 8 on the device
+    (30000, 64, 40, 10),        # one k-block, Hamming distances in 0..64: ties everywhere
+])
+def test_bq_tc_matches_oracle(vg, n, dim, nq, k):
+    """BinaryQuantizer Hamming scan (binary_quantizer.go / distance.Hamming): the +-1 GEMM gives D - 2 Hamming exactly, the
+    certificate is a strict integer comparison, ties at the k-th rank go to the exact scan; ids ordered (Hamming, row)."""
+    rng = np.random.default_rng(n + dim + 9)
+    v = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    v[n // 2] = v[n // 3]
+    q[1] = v[7]                  # Hamming distance 0
+    bq = vg.quantization.BinaryQuantizer(dim)
+    codes = bq.EncodeBatch(v)
+    mask_bits = rng.random(n) < 0.7
+    mask = np.packbits(mask_bits, bitorder="little")
+
+    def make():
+        ix = vg.index.DeviceIndex(codec=vg._lib.CODEC_BQ, metric=0, dim=dim, rows=n, bq_threshold=0.0)
+        ix.upload(codes=codes)
+        return ix
+
+    before = qtc_stats(vg)
+    with make() as ix:
+        rows, scores, counts = ix.search(q, k)
+        mrows, mscores, mcounts = ix.search(q, k, row_mask=mask)
+    after = qtc_stats(vg)
+    assert after[0] - before[0] >= 2 * nq, "the scan did not go through the tensor-core filter"
+    for i in range(min(nq, 6)):
+        qc = bq.Encode(q[i])
+        out = np.zeros(k, o.cand_dtype)
+        c = o.lib.vgo_bq_search(o.bp(qc), o.bp(codes), n, codes.shape[1], k, None, out.ctypes.data_as(C.POINTER(o.Cand)))
+        assert c == counts[i]
+        assert np.array_equal(rows[i, :c], out[:c]["row"]), i
+        assert np.array_equal(bits(scores[i, :c]), bits(out[:c]["score"])), i
+    assert rows[1, 0] == 7 and scores[1, 0] == 0.0
+    vg._lib.call("vg_flat_tc_enable", 0)
+    try:
+        with make() as ix:
+            e_rows, e_scores, e_counts = ix.search(q, k)
+            em_rows, em_scores, em_counts = ix.search(q, k, row_mask=mask)
+    finally:
+        vg._lib.call("vg_flat_tc_enable", 1)
+    assert np.array_equal(rows, e_rows) and np.array_equal(bits(scores), bits(e_scores)) and np.array_equal(counts, e_counts)
+    assert np.array_equal(mrows, em_rows) and np.array_equal(bits(mscores), bits(em_scores)) and np.array_equal(mcounts, em_counts)
+    live = mrows[mrows != 0xFFFFFFFF]
+    assert np.all(mask_bits[live])
+
+
+def test_sign_codecs_rerun_only_failed_queries(vg):
+    """A failed certificate of a RaBitQ / BQ query re-runs THAT query on the exact scan with its own sign words (gathered),
+    not the batch: duplicate rows beyond the candidate budget force failures for some queries only."""
+    rng = np.random.default_rng(77)
+    n, dim, nq, k = 60000, 128, 48, 10
+    v = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    # queries 0..7 have 400 rows at Hamming distance 0 148 rows apart, i.e. in 400 different groups (> 32 candidate groups): the
+    # k-th exact distance ties tau, the certificate must fail and the exact scan must pick the 10 smallest row ids
+    for j in range(8):
+        v[j * 97 + 148 * np.arange(400)] = q[j]
+    bq = vg.quantization.BinaryQuantizer(dim)
+    codes = bq.EncodeBatch(v)
+    before = qtc_stats(vg)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_BQ, metric=0, dim=dim, rows=n, bq_threshold=0.0) as ix:
+        ix.upload(codes=codes)
+        rows, scores, counts = ix.search(q, k)
+    after = qtc_stats(vg)
+    assert after[0] - before[0] == nq
+    assert 8 <= after[1] - before[1] < nq, "expected the planted queries (and only some queries) on the exact re-run"
+    for i in range(nq):
+        qc = bq.Encode(q[i])
+        out = np.zeros(k, o.cand_dtype)
+        c = o.lib.vgo_bq_search(o.bp(qc), o.bp(codes), n, codes.shape[1], k, None, out.ctypes.data_as(C.POINTER(o.Cand)))
+        assert c == counts[i]
+        assert np.array_equal(rows[i, :c], out[:c]["row"]), i
+        assert np.array_equal(bits(scores[i, :c]), bits(out[:c]["score"])), i
+    # RaBitQ: same planted duplicates (identical estimator values)
+    rq = vg.quantization.RaBitQuantizer(dim)
+    rcodes = rq.EncodeBatch(v)
+    before = qtc_stats(vg)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_RABITQ, metric=0, dim=dim, rows=n) as ix:
+        ix.upload(codes=rcodes, vectors=v)
+        rows, scores, counts = ix.search(q, k)
+    after = qtc_stats(vg)
+    assert after[0] - before[0] == nq
+    assert 8 <= after[1] - before[1] < nq
+    for i in range(nq):
+        out = np.zeros(k, o.cand_dtype)
+        c = o.lib.vgo_rabitq_search(o.fp(q[i]), o.bp(rcodes), n, dim, k, None, out.ctypes.data_as(C.POINTER(o.Cand)), None)
+        assert c == counts[i]
+        assert np.array_equal(rows[i, :c], out[:c]["row"]), i
+        assert np.array_equal(bits(scores[i, :c]), bits(out[:c]["score"])), i
+
+
 def test_single_cta_kernels_in_subprocess():
     """The pair switches are read once per process: the single-CTA kernels (qtc_kernel, flat_tc_kernel) get their own process."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))

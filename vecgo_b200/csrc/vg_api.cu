@@ -9,6 +9,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -110,6 +111,25 @@ static vg_status ensure_stage() {
     }
     return VG_OK;
 }
+// Pageable -> pinned staging copy: large chunks are split over a few host threads (one thread moves ~10 GB/s, the
+// PCIe link takes ~50 GB/s), so the staging copy of the next chunk keeps up with the DMA of the current one.
+static void stage_copy(void *dst, const void *src, size_t n) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const unsigned want = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), n / (4u << 20));
+    if (want <= 1) {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t slice = ((n + want - 1) / want + 4095) & ~(size_t)4095;
+    std::vector<std::thread> th;
+    th.reserve(want);
+    for (size_t off = slice; off < n; off += slice) {
+        const size_t len = std::min(slice, n - off);
+        th.emplace_back([=] { memcpy((char *)dst + off, (const char *)src + off, len); });
+    }
+    memcpy(dst, src, std::min(slice, n));
+    for (auto &t : th) t.join();
+}
 vg_status staged_h2d(void *d_dst, const void *h_src, size_t bytes) {
     if (bytes == 0) return VG_OK;
     std::lock_guard<std::mutex> lk(g_stage_mu);
@@ -120,7 +140,7 @@ vg_status staged_h2d(void *d_dst, const void *h_src, size_t bytes) {
     while (off < bytes) {
         const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
         VG_CUDA(cudaEventSynchronize(g_stage_ev[i]));
-        memcpy(g_stage[i], (const char *)h_src + off, n);
+        stage_copy(g_stage[i], (const char *)h_src + off, n);
         VG_CUDA(cudaMemcpyAsync((char *)d_dst + off, g_stage[i], n, cudaMemcpyHostToDevice, st));
         VG_CUDA(cudaEventRecord(g_stage_ev[i], st));
         off += n;
@@ -577,7 +597,7 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     return VG_OK;
 }
 
-// Quantized scans (SQ8 / INT4 / PQ / OPQ) through the tcgen05 decode-GEMM filter (vg_quant_tc.cu): candidates by fp16
+// Quantized scans (SQ8 / INT4 / PQ / OPQ / RaBitQ / BQ) through the tcgen05 decode-GEMM filter (vg_quant_tc.cu): candidates by fp16
 // GEMM over codes decoded inside the kernel, exact re-check in the reference's order, certificate; queries whose
 // certificate fails are re-run on the exact CUDA-core scan.  `d_queries` are already rotated for OPQ.
 static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArgs &a, bool *handled) {
@@ -592,7 +612,7 @@ static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArg
         const bool pq = d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ;
         const size_t np = pq ? (size_t)d.pq_m : (size_t)d.dim;
         std::vector<float> h0(np), h1(np);
-        if (d.codec != VG_CODEC_RABITQ) {  // RaBitQ has no decode parameters
+        if (d.codec != VG_CODEC_RABITQ && d.codec != VG_CODEC_BQ) {  // the sign codes have no decode parameters
             VG_CUDA(cudaMemcpyAsync(h0.data(), pq ? ix->pq_scales.p : ix->p0.p, np * 4, cudaMemcpyDeviceToHost, st));
             VG_CUDA(cudaMemcpyAsync(h1.data(), pq ? ix->pq_offsets.p : ix->p1.p, np * 4, cudaMemcpyDeviceToHost, st));
             VG_CUDA(cudaStreamSynchronize(st));
@@ -614,12 +634,7 @@ static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArg
     io.d_counts = a.out_counts;
     std::vector<int32_t> bad;
     VG_TRY(qtc::search(cp, ix->qtc, io, bad, st));
-    if (!bad.empty()) {
-        // RaBitQ: the exact scan reads per-query sign words prepared for the WHOLE batch, so a failed certificate sends
-        // the whole batch through it (the caller falls through); the other codecs re-run only the failed queries
-        if (d.codec == VG_CODEC_RABITQ) return VG_OK;
-        VG_TRY(scan_topk_subset(cp, a, bad, st));
-    }
+    if (!bad.empty()) VG_TRY(scan_topk_subset(cp, a, bad, st));  // exact CUDA-core scan of the queries whose certificate failed
     *handled = true;
     return VG_OK;
 }
@@ -683,7 +698,7 @@ static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, 
         a.queries = rotated.as<float>();
     }
     if (d.codec == VG_CODEC_SQ8 || d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ ||
-        d.codec == VG_CODEC_RABITQ) {
+        d.codec == VG_CODEC_RABITQ || d.codec == VG_CODEC_BQ) {
         bool handled = false;
         VG_TRY(quant_tc_search(ix, cp, a, &handled));
         if (handled) {

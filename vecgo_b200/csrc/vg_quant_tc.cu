@@ -76,7 +76,9 @@ constexpr int NTHREADS = (PROD_WARP0 + 8) * 32;
 constexpr size_t OFF_XN = (size_t)STAGES * STAGE_BYTES;
 constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
 constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024;  // + slack for the 1024-byte alignment
-constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2, Q_RABITQ = 3;
+constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2, Q_RABITQ = 3, Q_BQ = 4;
+// sign-bit codes (RaBitQ, BQ): the B tile is +-1, the GEMM is exact (acc = D - 2 Hamming)
+__host__ __device__ constexpr bool sign_codec(int c) { return c == Q_RABITQ || c == Q_BQ; }
 constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage
 
 // kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = F16 (0 at bits 7-9 / 10-12), both K-major,
@@ -103,6 +105,7 @@ struct KArgs {
     const uint32_t *mask;   // optional row bitmap as 32-bit words
     const float *fq;        // [nq] -2 / query scale
     int64_t nq, rows, rows_per_split;
+    float half_dim;           // BQ: D / 2 (Hamming = D / 2 - acc / 2)
     int kb;                 // k-blocks = dimp / 64
     int cpg;                // 32-row chunks per group
     float2 *mins;           // [nq_pad][groups]
@@ -647,7 +650,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         auto xn_of = [&](int t_) {
             const int64_t n0 = row_begin + (int64_t)t_ * TILE_ROWS;
             const int64_t row = n0 + et;
-            return (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
+            if constexpr (CODEC == Q_BQ) return (row < row_end) ? A.half_dim : BIG;  // s = D / 2 - acc / 2 = Hamming, exact
+            else return (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
         };
         if (ntiles > 0) xs[et] = xn_of(0);
         for (int t = 0; t < ntiles; t++) {
@@ -772,7 +776,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 c2 = c4;
                 c4.advance2(A.kb);
             }
-        } else if constexpr (CODEC == Q_RABITQ) {
+        } else if constexpr (sign_codec(CODEC)) {
             const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
             const int swz = r & 7;
             auto row_of = [&](int t) {
@@ -912,9 +916,14 @@ __global__ void __launch_bounds__(256) prep_queries_sign_kernel(const uint32_t *
         a16[q * dimp + p] = __float2half_rn(v);
     }
     if (lane == 0) {
-        const float qn = q_norms[q];
-        fq[q] = __fdiv_rn(__fmul_rn(-2.0f, qn), (float)dim);
-        cq[q] = __fmul_rn(qn, qn);
+        if (q_norms) {
+            const float qn = q_norms[q];
+            fq[q] = __fdiv_rn(__fmul_rn(-2.0f, qn), (float)dim);
+            cq[q] = __fmul_rn(qn, qn);
+        } else {  // BQ: s = D / 2 - acc / 2
+            fq[q] = -0.5f;
+            cq[q] = 0.0f;
+        }
     }
 }
 __global__ void __launch_bounds__(256) norm_sq_max_kernel(const float *norms, int64_t rows, unsigned int *max_bits) {
@@ -1081,7 +1090,7 @@ __device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, co
                 tot = __fmaf_rn(e, e, tot);
             }
         return tot;
-    } else if constexpr (CODEC == Q_RABITQ) {
+    } else if constexpr (sign_codec(CODEC)) {
         // rabitq.go:119-176: exact popcount (popcount_avx512.c:25-46), then the unfused Go estimator
         const uint32_t *code = reinterpret_cast<const uint32_t *>(E.codes + row * E.row_bytes);
         const uint32_t *qw = reinterpret_cast<const uint32_t *>(table);  // the query's sign words staged in shared memory
@@ -1091,6 +1100,7 @@ __device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, co
         h += __shfl_down_sync(0xffffffffu, h, 4, 16);
         h += __shfl_down_sync(0xffffffffu, h, 2, 16);
         h += __shfl_down_sync(0xffffffffu, h, 1, 16);
+        if constexpr (CODEC == Q_BQ) return (float)h;  // distance.Hamming as float32 (binary.go: score = float32(popcount))
         const float qn = qs[0], yn = __ldg(E.norms + row);
         const float t1 = __fsub_rn(qn, yn);
         float a = __fmul_rn(4.0f, qn);
@@ -1125,8 +1135,8 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     TopK tk = topk_carve(smem + qbytes, 1, E.C, E.k);
     int32_t *rowlist = reinterpret_cast<int32_t *>(smem + qbytes + topk_smem_bytes(1, E.C));
     float *table = reinterpret_cast<float *>(rowlist + LIST_CAP);
-    if constexpr (CODEC == Q_RABITQ) {
-        if (tid == 0) qs[0] = E.q_norms[q];
+    if constexpr (sign_codec(CODEC)) {
+        if (tid == 0) qs[0] = CODEC == Q_RABITQ ? E.q_norms[q] : 0.0f;
         uint32_t *qw = reinterpret_cast<uint32_t *>(table);
         for (int w = tid; w < E.words32; w += 128) qw[w] = E.q_words[q * E.words32 + w];
     } else {
@@ -1208,6 +1218,12 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
             if (!overflow && t < __int_as_float(0x7f800000)) {
                 if (m < E.k) {
                     fail = 1;
+                } else if (CODEC == Q_BQ) {
+                    // integer scores: tau carries the Hamming distance in its high bits (index bits below; exact for
+                    // D < 65536).  Every unscored row has Hamming >= that, so the k best are certain when the k-th
+                    // exact distance is strictly smaller (a tie could hide a smaller row id in an unscored group).
+                    const float th = __uint_as_float(__float_as_uint(t) & ~(uint32_t)(E.G - 1));
+                    if (!(E.out_scores[q * E.k + (E.k - 1)] < th)) fail = 1;
                 } else if (CODEC == Q_RABITQ) {
                     // the GEMM is exact (acc = D - 2 Hamming); only the epilogue's float32 arithmetic, the index bits and
                     // the reference estimator's own roundings separate s' + c_q from the reference score
@@ -1251,8 +1267,8 @@ __global__ void __launch_bounds__(128) qtc_score_kernel(EArgs E, const uint32_t 
     float *qs = reinterpret_cast<float *>(smem);
     const size_t qbytes = ((size_t)E.dim * 4 + 15) & ~(size_t)15;
     float *table = reinterpret_cast<float *>(smem + qbytes);
-    if constexpr (CODEC == Q_RABITQ) {
-        if (tid == 0) qs[0] = E.q_norms[q];
+    if constexpr (sign_codec(CODEC)) {
+        if (tid == 0) qs[0] = CODEC == Q_RABITQ ? E.q_norms[q] : 0.0f;
         uint32_t *qw = reinterpret_cast<uint32_t *>(table);
         for (int w = tid; w < E.words32; w += 128) qw[w] = E.q_words[q * E.words32 + w];
     } else {
@@ -1344,6 +1360,7 @@ static int q_codec(const CodecParams &cp) {
         case VG_CODEC_PQ:
         case VG_CODEC_OPQ: return Q_PQ;
         case VG_CODEC_RABITQ: return Q_RABITQ;
+        case VG_CODEC_BQ: return Q_BQ;
         default: return -1;
     }
 }
@@ -1401,7 +1418,7 @@ static bool use_pair() {
 bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int64_t k, int64_t num_partitions) {
     if (!enabled() || num_partitions > 1) return false;
     if (rows < 8192 || rows >= (1ll << 31) || nq < 16 || k < 1) return false;
-    if (k > (cp.codec == VG_CODEC_RABITQ ? 1024 : 128)) return false;
+    if (k > (cp.codec == VG_CODEC_RABITQ || cp.codec == VG_CODEC_BQ ? 1024 : 128)) return false;
     if (cp.dim % 64 != 0 || cp.dim < 64 || cp.dim > 2048) return false;
     if ((reinterpret_cast<uintptr_t>(cp.codes) & 15) != 0) return false;
     switch (cp.codec) {
@@ -1412,6 +1429,9 @@ bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int6
         case VG_CODEC_RABITQ:
             // the estimator is a distance whatever the segment metric; CTA-pair kernel only; candidate groups must exist
             return use_pair() && cp.norms != nullptr && cp.q_words != nullptr && cp.q_norms != nullptr && rows / 32 >= 2 * (k <= 16 ? 32 : 2 * k);
+        case VG_CODEC_BQ:
+            // Hamming distance whatever the segment metric; same kernel as RaBitQ without the row norms
+            return use_pair() && cp.q_words != nullptr && rows / 32 >= 2 * (k <= 16 ? 32 : 2 * k);
         case VG_CODEC_PQ:
         case VG_CODEC_OPQ: {
             if (metric != VG_METRIC_L2 || cp.pq_k != 256 || cp.pq_tables) return false;
@@ -1452,7 +1472,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     const int layout = layout_of(cp);
     // storage position (= position along K of the B tile the producer writes) -> dimension
     std::vector<int32_t> perm((size_t)dimp, -1);
-    if (qc == Q_RABITQ) {
+    if (sign_codec(qc)) {
         // Producer<Q_RABITQ>::convert: position 64 kb + 32 word + 8 c + 2 j + hi holds bit 64 kb + 32 word + 4 c + j + 16 hi
         for (int p = 0; p < dimp; p++) {
             const int base = p & ~31, in = p & 31, c = in >> 3, j = (in >> 1) & 3, hi = in & 1;
@@ -1463,7 +1483,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
         VG_TRY(pp.xmax.alloc(16));
         VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
         VG_CUDA(cudaMemsetAsync(pp.xmax.p, 0, 16, st));
-        if (rows > 0) {
+        if (rows > 0 && qc == Q_RABITQ) {
             norm_sq_max_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, st>>>(cp.norms, rows, pp.xmax.as<unsigned int>());
             VG_LAUNCHED();
         }
@@ -1555,7 +1575,7 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
 template <int CODEC>
 static vg_status launch_score(const EArgs &e, int64_t nq, const uint32_t *d_rows, int r, float *d_out, cudaStream_t st) {
     const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) +
-                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : CODEC == Q_RABITQ ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : sign_codec(CODEC) ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the gather-scoring kernel");
     VG_CUDA(cudaFuncSetAttribute(qtc_score_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     qtc_score_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e, d_rows, r, d_out);
@@ -1575,6 +1595,7 @@ vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries
     if (qc == Q_SQ8) return launch_score<Q_SQ8>(e, nq, d_rows, (int)r, d_out, st);
     if (qc == Q_INT4) return launch_score<Q_INT4>(e, nq, d_rows, (int)r, d_out, st);
     if (qc == Q_RABITQ) return launch_score<Q_RABITQ>(e, nq, d_rows, (int)r, d_out, st);
+    if (qc == Q_BQ) return launch_score<Q_BQ>(e, nq, d_rows, (int)r, d_out, st);
     return launch_score<Q_PQ>(e, nq, d_rows, (int)r, d_out, st);
 }
 
@@ -1606,7 +1627,7 @@ static int64_t qtc_group_rows(int64_t rows, int kc) {
 template <int CODEC>
 static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
     const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)LIST_CAP * 4 +
-                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : CODEC == Q_RABITQ ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : sign_codec(CODEC) ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
     VG_CUDA(cudaFuncSetAttribute(qtc_exact_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     qtc_exact_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e);
@@ -1632,8 +1653,9 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     VG_TRY(gids.alloc((size_t)nq * kc * 4));
     VG_TRY(gcnt.alloc((size_t)nq * 4));
     VG_TRY(tau.alloc((size_t)nq * 4));
-    if (qc == Q_RABITQ) {
-        prep_queries_sign_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32, cp.q_norms + io.q_index0, nq,
+    if (sign_codec(qc)) {
+        prep_queries_sign_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32,
+                                                                                   qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr, nq,
                                                                                    cp.words32, (int)cp.dim, pp.dimp, pp.perm.as<int32_t>(),
                                                                                    a16.as<__half>(), fq.as<float>(), cq.as<float>());
         VG_LAUNCHED();
@@ -1664,7 +1686,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     rps = (rps + unit - 1) / unit * unit;
     splits = (rows + rps - 1) / rps;
     KArgs a{};
-    a.xn = qc == Q_RABITQ ? cp.norms : pp.xn.as<float>();
+    a.xn = qc == Q_RABITQ ? cp.norms : pp.xn.as<float>();  // BQ: unused
+    a.half_dim = 0.5f * (float)cp.dim;
     a.mask = reinterpret_cast<const uint32_t *>(io.d_mask);
     a.fq = fq.as<float>();
     a.nq = nq;
@@ -1688,9 +1711,10 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_RABITQ) VG_TRY(launch_gemm_pair<Q_RABITQ>(mq, a, qtiles, (int)splits, st));
+        else if (qc == Q_BQ) VG_TRY(launch_gemm_pair<Q_BQ>(mq, a, qtiles, (int)splits, st));
         else VG_TRY(launch_gemm_pair<Q_PQ>(mq, a, qtiles, (int)splits, st));
     } else {
-        if (qc == Q_RABITQ) return fail(VG_ERR_UNSUPPORTED, "the RaBitQ filter needs the CTA-pair kernel");
+        if (sign_codec(qc)) return fail(VG_ERR_UNSUPPORTED, "the RaBitQ / BQ filter needs the CTA-pair kernel");
         if (qc == Q_SQ8) VG_TRY(launch_gemm<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm<Q_INT4>(mq, a, qtiles, (int)splits, st));
         else VG_TRY(launch_gemm<Q_PQ>(mq, a, qtiles, (int)splits, st));
@@ -1717,10 +1741,11 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     e.out_scores = io.d_scores;
     e.out_counts = io.d_counts;
     e.fail_flags = d_fail;
-    if (qc == Q_RABITQ) {
+    if (sign_codec(qc)) {
         e.q_words = cp.q_words + io.q_index0 * cp.words32;
-        e.q_norms = cp.q_norms + io.q_index0;
-        VG_TRY(launch_exact<Q_RABITQ>(e, nq, st));
+        e.q_norms = qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr;
+        if (qc == Q_RABITQ) VG_TRY(launch_exact<Q_RABITQ>(e, nq, st));
+        else VG_TRY(launch_exact<Q_BQ>(e, nq, st));
     } else if (qc == Q_SQ8) VG_TRY(launch_exact<Q_SQ8>(e, nq, st));
     else if (qc == Q_INT4) VG_TRY(launch_exact<Q_INT4>(e, nq, st));
     else VG_TRY(launch_exact<Q_PQ>(e, nq, st));

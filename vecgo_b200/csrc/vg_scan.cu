@@ -1251,6 +1251,22 @@ vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<
     gather_rows_kernel<<<(unsigned)((nb * dim + 255) / 256), 256, 0, st>>>(a.queries, a.q_stride ? a.q_stride : dim, bidx.as<int32_t>(), nb, dim,
                                                                           bq.as<float>());
     VG_LAUNCHED();
+    // sign codecs (BQ / RaBitQ) scan prepared per-query sign words (+ norms): gather those rows as well
+    CodecParams cps = cp;
+    DevBuf bqw, bqn;
+    if (cp.q_words) {
+        VG_TRY(bqw.alloc((size_t)nb * cp.words32 * 4));
+        gather_rows_kernel<<<(unsigned)((nb * cp.words32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float *>(cp.q_words), cp.words32,
+                                                                                    bidx.as<int32_t>(), nb, cp.words32, bqw.as<float>());
+        VG_LAUNCHED();
+        cps.q_words = bqw.as<uint32_t>();
+    }
+    if (cp.q_norms) {
+        VG_TRY(bqn.alloc((size_t)nb * 4));
+        gather_rows_kernel<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(cp.q_norms, 1, bidx.as<int32_t>(), nb, 1, bqn.as<float>());
+        VG_LAUNCHED();
+        cps.q_norms = bqn.as<float>();
+    }
     uint32_t *out_rows = a.out_rows;
     float *out_scores = a.out_scores;
     int32_t *out_counts = a.out_counts;
@@ -1260,7 +1276,7 @@ vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<
     a.out_rows = brow.as<uint32_t>();
     a.out_scores = bsc.as<float>();
     a.out_counts = bcnt.as<int32_t>();
-    VG_TRY(scan_topk(cp, a, st));
+    VG_TRY(scan_topk(cps, a, st));
     scatter_results_kernel<<<(unsigned)((nb * k + 255) / 256), 256, 0, st>>>(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(),
                                                                             bidx.as<int32_t>(), nb, k, out_rows, out_scores, out_counts);
     VG_LAUNCHED();
