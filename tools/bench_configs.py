@@ -270,6 +270,8 @@ def main():
             flat("C1-768d", 1_000_000, 768, 2048, 10)
         elif w == "c2a":
             sq("C2a", "sq8", 1_000_000 if SMALL else 10_000_000, 768, 2048 if SMALL else 10_000, 100)
+        elif w == "c2a8":  # the per-GPU work of the headline bench on eight GPUs: one 1.25M-row shard, the whole query batch
+            sq("C2a-shard-of-8", "sq8", 1_250_000, 768, 10_000, 100)
         elif w == "c2b":
             sq("C2b", "int4", 1_000_000 if SMALL else 10_000_000, 768, 2048 if SMALL else 10_000, 100)
         elif w == "c3":

@@ -567,6 +567,63 @@ __global__ void __launch_bounds__(256) prep_queries16_kernel(const float *querie
     if (lane == 0) fq[q] = -ldexpf(1.0f, (is_dot ? 0 : 1) - e - sx_exp);
 }
 
+// Compaction of a streaming selection WITHOUT a sort: any superset of the k smallest keys may stay, so it is enough to
+// find a pivot with at least k keys below it and drop the rest.  32 sampled keys are sorted across the warp with
+// shuffles, the smallest sample with >= k keys below it becomes the pivot (binary search, one counting pass each), and
+// the survivors are packed in place with ballots.  tau = pivot is a valid filter (the k-th smallest is below it).
+// ~10x fewer shared-memory operations than the bitonic sort of the whole buffer; the one exact sort happens at the end.
+__device__ __forceinline__ void select_compact_approx(const TopK &t, int slot, int lane) {
+    unsigned long long *a = t.keys + (size_t)slot * t.C;
+    int n = t.cnt[slot];
+    if (n > t.C) n = t.C;
+    __syncwarp();
+    if (n <= t.k) return;
+    unsigned long long s = a[(int)(((long long)lane * n) >> 5)];
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1)
+#pragma unroll
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xffffffffu, s, stride);
+            const bool take_min = ((lane & size) == 0) == ((lane & stride) == 0);
+            s = take_min ? (s < o ? s : o) : (s > o ? s : o);
+        }
+    int lo = 0, hi = 31, best = -1, kept = 0;
+    while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const unsigned long long pv = __shfl_sync(0xffffffffu, s, mid);
+        int c = 0;
+        for (int i = lane; i < n; i += 32) c += a[i] < pv ? 1 : 0;
+        c = __reduce_add_sync(0xffffffffu, c);
+        if (c >= t.k) {
+            best = mid;
+            kept = c;
+            hi = mid - 1;
+        } else {
+            lo = mid + 1;
+        }
+    }
+    if (best < 0 || kept > t.k + (t.C - t.k) / 2) {  // no usable pivot among the samples: exact compaction
+        topk_compact_warp(t, slot, lane, false);
+        return;
+    }
+    const unsigned long long pivot = __shfl_sync(0xffffffffu, s, best);
+    int base = 0;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const unsigned long long v = i < n ? a[i] : VG_KEY_EMPTY;
+        const bool keep = i < n && v < pivot;
+        const unsigned b = __ballot_sync(0xffffffffu, keep);  // every lane has read its key of this chunk before any lane writes
+        if (keep) a[base + __popc(b & ((1u << lane) - 1u))] = v;  // target index <= i: inside chunks already read
+        base += __popc(b);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        t.cnt[slot] = base;
+        t.tau[slot] = pivot;
+    }
+    __syncwarp();
+}
+
 // tau(q) = kc-th smallest group minimum (m1) of query q and the kc groups that reach it: one warp per query streams
 // mins[q][*] (coalesced) through the shared-memory bounded top-k (threshold filter + bitonic compaction).  Output per
 // selected group: the row its m1 names (gid * G + index bits) and a "crowded" flag (bit 31) when m2 <= tau as well.
@@ -604,7 +661,7 @@ __global__ void __launch_bounds__(256) tc_select_kernel(const float2 *mins, int6
                 }
             }
             __syncwarp();
-            if (tk.cnt[warp] > trigger) topk_compact_warp(tk, warp, lane, false);
+            if (tk.cnt[warp] > trigger) select_compact_approx(tk, warp, lane);
             __syncwarp();
         }
     }

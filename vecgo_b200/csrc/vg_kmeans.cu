@@ -548,16 +548,54 @@ __global__ void __launch_bounds__(256) pp_dist_kernel(const float *vecs, int64_t
     extern __shared__ float sd[];  // [G][PP_ROWS + 1]
     const int64_t i0 = (int64_t)blockIdx.x * PP_ROWS;
     const int pairs = PP_ROWS * G;
-    for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
-        const int r = p / G, g = p - r * G;
-        const int64_t i = i0 + r;
-        float d = 0.0f;
-        if (i < n) {
-            const float *a = vecs + i * stride + (int64_t)g * ds, *b = cent + ((int64_t)g * K + c) * ds;
-            if constexpr (DS > 0) d = sql2_tail_fixed<DS>(a, b);
-            else d = sql2_pair_thread(a, b, ds);
+    if constexpr (DS >= 8) {
+        // DS / 4 neighbouring lanes share one (sample, subspace) pair, one 16-byte load each: a warp reads 512 contiguous
+        // bytes of a sample row per instruction (a lane per pair read 32-byte-strided halves of every sector: ncu showed
+        // 16 of 32 bytes per sector used and the L1/L2 path 80 % busy).  The FMA chain keeps its order: lane j continues
+        // from the running sum of lane j - 1 (shuffle).
+        constexpr int L = DS / 4;
+        const int lane = threadIdx.x & 31, sub = lane & (L - 1);
+        const int items = pairs * L;
+        for (int p0 = 0; p0 < items; p0 += blockDim.x) {
+            const int it = p0 + threadIdx.x;
+            const int p = it / L;
+            const int r = p / G, g = p - r * G;
+            const int64_t i = i0 + r;
+            const bool live = it < items && i < n;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+            if (live) {
+                x = *reinterpret_cast<const float4 *>(vecs + i * stride + (int64_t)g * DS + sub * 4);
+                y = __ldg(reinterpret_cast<const float4 *>(cent + ((int64_t)g * K + c) * DS + sub * 4));
+            }
+            float tot = 0.0f;
+#pragma unroll
+            for (int s_ = 0; s_ < L; s_++) {
+                if (s_ > 0) tot = __shfl_sync(0xffffffffu, tot, (lane & ~(L - 1)) + s_ - 1);
+                if (sub == s_) {
+                    float d = __fsub_rn(x.x, y.x);
+                    tot = __fmaf_rn(d, d, tot);
+                    d = __fsub_rn(x.y, y.y);
+                    tot = __fmaf_rn(d, d, tot);
+                    d = __fsub_rn(x.z, y.z);
+                    tot = __fmaf_rn(d, d, tot);
+                    d = __fsub_rn(x.w, y.w);
+                    tot = __fmaf_rn(d, d, tot);
+                }
+            }
+            if (it < items && sub == L - 1) sd[g * (PP_ROWS + 1) + r] = live ? tot : 0.0f;
         }
-        sd[g * (PP_ROWS + 1) + r] = d;
+    } else {
+        for (int p = threadIdx.x; p < pairs; p += blockDim.x) {
+            const int r = p / G, g = p - r * G;
+            const int64_t i = i0 + r;
+            float d = 0.0f;
+            if (i < n) {
+                const float *a = vecs + i * stride + (int64_t)g * ds, *b = cent + ((int64_t)g * K + c) * ds;
+                if constexpr (DS > 0) d = sql2_tail_fixed<DS>(a, b);
+                else d = sql2_pair_thread(a, b, ds);
+            }
+            sd[g * (PP_ROWS + 1) + r] = d;
+        }
     }
     __syncthreads();
     for (int p = threadIdx.x; p < pairs; p += blockDim.x) {

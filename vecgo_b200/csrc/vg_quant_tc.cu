@@ -79,7 +79,7 @@ constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024
 constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2, Q_RABITQ = 3, Q_BQ = 4;
 // sign-bit codes (RaBitQ, BQ): the B tile is +-1, the GEMM is exact (acc = D - 2 Hamming)
 __host__ __device__ constexpr bool sign_codec(int c) { return c == Q_RABITQ || c == Q_BQ; }
-constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage
+constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage (work bound; beyond it the query goes to the exact scan)
 
 // kind::f16 instruction descriptor: D = f32 (bits 4-5 = 1), A = B = F16 (0 at bits 7-9 / 10-12), both K-major,
 // N >> 3 at bits 17-22, M >> 4 at bits 24-28.
@@ -1133,8 +1133,11 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     float *qs = reinterpret_cast<float *>(smem);
     const size_t qbytes = ((size_t)E.dim * 4 + 15) & ~(size_t)15;
     TopK tk = topk_carve(smem + qbytes, 1, E.C, E.k);
-    int32_t *rowlist = reinterpret_cast<int32_t *>(smem + qbytes + topk_smem_bytes(1, E.C));
-    float *table = reinterpret_cast<float *>(rowlist + LIST_CAP);
+    // candidate lists: rows named by a group's minimum, and crowded groups (all G rows are scored) — the r-th candidate
+    // row is found from these two short lists, so the CTA's shared memory does not depend on the row budget
+    uint32_t *singles = reinterpret_cast<uint32_t *>(smem + qbytes + topk_smem_bytes(1, E.C));
+    uint32_t *crowded = singles + E.kc;
+    float *table = reinterpret_cast<float *>(crowded + E.kc);
     if constexpr (sign_codec(CODEC)) {
         if (tid == 0) qs[0] = CODEC == Q_RABITQ ? E.q_norms[q] : 0.0f;
         uint32_t *qw = reinterpret_cast<uint32_t *>(table);
@@ -1168,36 +1171,41 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     }
     const int ng = E.gcnt[q];
     const int trigger = E.C - 16;
-    __shared__ int s_total;
-    if (tid == 0) {
-        int n = 0;
-        for (int gi = 0; gi < ng; gi++) n += (E.cand[q * E.kc + gi] & 0x80000000u) ? E.G : 1;
-        s_total = n;
+    __shared__ int s_total, s_ns;
+    if (tid < 32) {
+        int ns = 0, nc = 0;
+        for (int g0 = 0; g0 < ng; g0 += 32) {
+            const int gi = g0 + tid;
+            const uint32_t c = gi < ng ? E.cand[q * E.kc + gi] : 0u;
+            const bool is_c = gi < ng && (c & 0x80000000u) != 0, is_s = gi < ng && !is_c;
+            const unsigned bs = __ballot_sync(0xffffffffu, is_s), bc = __ballot_sync(0xffffffffu, is_c);
+            const unsigned lt = (1u << tid) - 1u;
+            if (is_s) singles[ns + __popc(bs & lt)] = c;
+            if (is_c) crowded[nc + __popc(bc & lt)] = c & 0x7FFFFFFFu;
+            ns += __popc(bs);
+            nc += __popc(bc);
+        }
+        if (tid == 0) {
+            s_ns = ns;
+            s_total = ns + nc * E.G;
+        }
     }
     __syncthreads();
     const bool overflow = s_total > LIST_CAP;
     if (!overflow) {
-        if (tid < 32) {
-            int off = 0;
-            for (int gi = 0; gi < ng; gi++) {
-                const uint32_t c = E.cand[q * E.kc + gi];
-                if (c & 0x80000000u) {
-                    const int64_t first = (int64_t)(c & 0x7FFFFFFFu) * E.G;
-                    for (int r = tid; r < E.G; r += 32) rowlist[off + r] = (first + r < E.rows) ? (int32_t)(first + r) : -1;
-                    off += E.G;
-                } else {
-                    if (tid == 0) rowlist[off] = ((int64_t)c < E.rows) ? (int32_t)c : -1;
-                    off += 1;
-                }
-            }
-        }
-        __syncthreads();
-        const int total = s_total;
+        const int total = s_total, ns = s_ns;
         for (int r0 = 0; r0 < total; r0 += 16) {
 #pragma unroll
             for (int u = 0; u < 2; u++) {
                 const int r = r0 + hw * 2 + u;
-                int64_t row = (r < total) ? (int64_t)rowlist[r] : -1;
+                int64_t row = -1;
+                if (r < ns) {
+                    row = (int64_t)singles[r];
+                } else if (r < total) {
+                    const int idx = r - ns;
+                    row = (int64_t)crowded[idx / E.G] * E.G + (idx % E.G);
+                }
+                if (row >= E.rows) row = -1;
                 if (row >= 0 && E.mask && !((E.mask[row >> 3] >> (row & 7)) & 1)) row = -1;
                 const bool valid = row >= 0;
                 const float tot = exact_score<CODEC>(E, qs, table, valid ? row : 0, lane);
@@ -1626,7 +1634,7 @@ static int64_t qtc_group_rows(int64_t rows, int kc) {
 }
 template <int CODEC>
 static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
-    const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)LIST_CAP * 4 +
+    const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)e.kc * 8 +
                       (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : sign_codec(CODEC) ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
     if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
     VG_CUDA(cudaFuncSetAttribute(qtc_exact_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
