@@ -250,6 +250,10 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
  * VECGO_QUANT_TC=0 (or vg_flat_tc_enable(0)) forces the CUDA-core scan.  Counters: queries that went through the
  * filter and how many of them needed the exact re-run. */
 vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks);
+/* PQ training (pq.go:347-386 assignClusters): (sample, subspace) pairs whose nearest centroid was found on the tensor
+ * cores (8-dim subspaces x 256 centroids, vg_pq_assign_tc.cu) and how many of them failed the gap certificate and were
+ * re-evaluated by the exact sequential-FMA loop, since the library was loaded.  VECGO_PQ_ASSIGN_TC=0 disables the path. */
+vg_status vg_pq_assign_tc_stats(uint64_t *pairs, uint64_t *fallback_pairs);
 /* Measurement aid: enable = 1 brackets every GEMM launch of the filter with a CUDA-event pair on its own stream and
  * resets the counters, 0 turns that off, < 0 only reads.  Returns the accumulated kernel time (ms) and launches. */
 vg_status vg_quant_tc_profile(int32_t enable, double *gemm_ms, uint64_t *gemm_launches);

@@ -7,6 +7,7 @@ kernels reproduce the reference's AVX-512 summation order, so distances are
 compared BIT-FOR-BIT and the 1e-4 bound is only the documented fallback.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -622,4 +623,16 @@ def test_kmeanspp_parallel_prefix_equals_sequential_chain():
 
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "kmeanspp_ab.py"), "120000", "64", "8"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("kind", ["gauss", "ties", "scaled"])
+def test_pq_training_tensor_core_assignment_equals_exact_assignment(kind):
+    """8-dim subspaces x 256 centroids: the tcgen05 assignment with its gap certificate + exact re-evaluation must give
+    the float32 centroids and int8 codebooks of the exact CUDA-core assignment, bit for bit (tools/pq_assign_ab.py)."""
+    import subprocess
+    import sys
+
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "pq_assign_ab.py")
+    r = subprocess.run([sys.executable, tool, "100000", "64", "8", "5", kind], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr

@@ -18,6 +18,7 @@
 #include "vg_scan.cuh"
 #include "vg_flat_tc.cuh"
 #include "vg_quant_tc.cuh"
+#include "vg_pq_assign_tc.cuh"
 
 namespace vg {
 
@@ -733,6 +734,11 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
 
 vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
     qtc::stats(queries, fallbacks);
+    return VG_OK;
+}
+
+vg_status vg_pq_assign_tc_stats(uint64_t *pairs, uint64_t *fallback_pairs) {
+    pqa::stats(pairs, fallback_pairs);
     return VG_OK;
 }
 

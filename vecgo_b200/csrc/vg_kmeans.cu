@@ -13,6 +13,7 @@
 // float32 running sums are sequential chains too and are kept sequential.
 #include "vg_flat_tc.cuh"
 #include "vg_kmeans.cuh"
+#include "vg_pq_assign_tc.cuh"
 
 #include <cstdlib>
 #include <vector>
@@ -1085,10 +1086,15 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
     // ---- runKMeansIterations
     Lloyd L;
     VG_TRY(L.init(G, K, ds, n, dim, st));
+    // 8-dim subspaces x 256 centroids: assignment on the tensor cores with an exactness certificate (vg_pq_assign_tc.cu)
+    pqa::Assigner tca;
+    if (iters > 0 && pqa::Assigner::supported(n, dim, G, K, ds)) VG_TRY(tca.prepare(d_vecs, n, dim, G, st));
     for (int64_t it = 0; it < iters; it++) {
-        VG_TRY(pq_assign_all(d_vecs, n, dim, G, K, ds, cent.as<float>(), L.assign_new.as<uint32_t>(), score, cnt, st));
+        if (tca.ready) VG_TRY(tca.assign(cent.as<float>(), L.assign_new.as<uint32_t>(), st));
+        else VG_TRY(pq_assign_all(d_vecs, n, dim, G, K, ds, cent.as<float>(), L.assign_new.as<uint32_t>(), score, cnt, st));
         bool any = false;
         VG_TRY(L.step(d_vecs, cent.as<float>(), 0, seed, 0xE0E0E0E0ull, 1, &any, st));
+        if (tca.ready) VG_TRY(tca.account(st));
         if (!any) break;
     }
     // ---- int8 codebooks
