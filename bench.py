@@ -503,7 +503,7 @@ def run_ours(a):
         line = {
             "metric": f"batched QPS, {a.workload.upper()} decode-and-scan top-{k}", "value": qps, "unit": "queries/s",
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": dtype,
+            "scaling": "strong", "vs_baseline": None, "dtype": dtype.split(" ")[0], "arithmetic": dtype,
             "data": f"synthetic: N(0,1) rows generated on device (torch.randn, seed {DATA_SEED}), quantizer trained on the first "
                     f"{train_rows} rows, queries N(0,1) seed {QUERY_SEED}; generation+encode took {t_gen:.0f}s",
             "config": workload_config(a),
