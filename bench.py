@@ -423,13 +423,17 @@ def run_ours(a):
             parity = {"error": repr(ex)}
 
     # ---- e2e: host buffers through the C ABI (vg_index_search), H2D/D2H inside the timed region
-    e2e_steps = max(1, min(a.steps, 2))
-    hq = queries.cpu().numpy()
+    e2e_steps = max(1, a.steps)   # same step count and warm-up as the device-timed loop: both run in the sustained (power-capped) regime
+    hq_t = queries.cpu().pin_memory()   # the step's inputs come from pinned host memory (the library DMAs page-locked buffers directly)
+    hq = hq_t.numpy()
+    e2e_out_t = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                 torch.empty((nq,), dtype=torch.int32).pin_memory())
+    e2e_out = (e2e_out_t[0].numpy().view(np.uint32), e2e_out_t[1].numpy(), e2e_out_t[2].numpy())
     h2d, d2h = hq.nbytes, nq * k * 8 + nq * 4
     if world > 1:
         # every rank gets the whole query batch from ITS pinned host copy and reads the merged result back into pinned
         # host memory; the buffers are allocated once, the copies are inside the timed region
-        hq_pin = torch.from_numpy(hq).pin_memory()
+        hq_pin = hq_t
         dq = torch.empty((nq, dim), dtype=torch.float32, device=dev)
         out_pin = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
                    torch.empty((nq,), dtype=torch.int32).pin_memory())
@@ -437,11 +441,19 @@ def run_ours(a):
         sh.search_dev(dq, nq, k)  # untimed: first use of the buffers
         torch.cuda.synchronize()
         dist.barrier()
+    for _ in range(max(1, a.warmup)):  # untimed: first use of the host buffers, clocks back under load after the CPU-side checks
+        if world == 1:
+            ix.search(hq, k, out=e2e_out)
+        else:
+            dq.copy_(hq_pin, non_blocking=True)
+            sh.search_dev(dq, nq, k)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         if world == 1:
-            ix.search(hq, k)
+            ix.search(hq, k, out=e2e_out)
         else:
             dq.copy_(hq_pin, non_blocking=True)
             r_, s_, c_ = sh.search_dev(dq, nq, k)

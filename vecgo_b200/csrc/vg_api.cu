@@ -131,8 +131,24 @@ static void stage_copy(void *dst, const void *src, size_t n) {
     memcpy(dst, src, std::min(slice, n));
     for (auto &t : th) t.join();
 }
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. the caller's own staging of mmap'd segments) is DMA'd
+// directly; pageable memory goes through the library's pinned ring.
+static bool host_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
 vg_status staged_h2d(void *d_dst, const void *h_src, size_t bytes) {
     if (bytes == 0) return VG_OK;
+    if (bytes >= (64u << 10) && host_pinned(h_src)) {
+        cudaStream_t st = stream();
+        VG_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        return VG_OK;
+    }
     std::lock_guard<std::mutex> lk(g_stage_mu);
     VG_TRY(ensure_stage());
     cudaStream_t st = stream();
@@ -153,6 +169,12 @@ vg_status staged_h2d(void *d_dst, const void *h_src, size_t bytes) {
 }
 vg_status staged_d2h(void *h_dst, const void *d_src, size_t bytes) {
     if (bytes == 0) return VG_OK;
+    if (bytes >= (64u << 10) && host_pinned(h_dst)) {
+        cudaStream_t st = stream();
+        VG_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        return VG_OK;
+    }
     std::lock_guard<std::mutex> lk(g_stage_mu);
     VG_TRY(ensure_stage());
     cudaStream_t st = stream();

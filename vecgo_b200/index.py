@@ -78,13 +78,22 @@ class DeviceIndex:
         return dict(rows=r.value, dim=d.value, code_bytes_per_row=cb.value, device_bytes=db.value)
 
     # ---------------------------------------------------------------- search
-    def search(self, queries, k: int, nprobes: int = 0, row_mask=None):
-        """Batched Segment.Search → (rows [nq,k] u32, scores [nq,k] f32, counts [nq] i32), best-first."""
+    def search(self, queries, k: int, nprobes: int = 0, row_mask=None, out=None):
+        """Batched Segment.Search → (rows [nq,k] u32, scores [nq,k] f32, counts [nq] i32), best-first.
+        `out` = (rows, scores, counts) C-contiguous arrays to fill instead of fresh ones — page-locked query / result
+        buffers (e.g. numpy views of pinned torch tensors) are DMA'd directly by the library, pageable ones are staged."""
         q = L.as_f32(queries).reshape(-1, self.dim)
         nq = q.shape[0]
-        rows = np.full((nq, k), EMPTY_ROW, np.uint32)
-        scores = np.full((nq, k), np.nan, F)
-        counts = np.zeros(nq, np.int32)
+        if out is not None:
+            rows, scores, counts = out
+            if (rows.shape != (nq, k) or scores.shape != (nq, k) or counts.shape != (nq,) or rows.dtype != np.uint32
+                    or scores.dtype != F or counts.dtype != np.int32
+                    or not (rows.flags.c_contiguous and scores.flags.c_contiguous and counts.flags.c_contiguous)):
+                raise ValueError("out must be C-contiguous (uint32 [nq,k], float32 [nq,k], int32 [nq]) arrays")
+        else:
+            rows = np.full((nq, k), EMPTY_ROW, np.uint32)
+            scores = np.full((nq, k), np.nan, F)
+            counts = np.zeros(nq, np.int32)
         m = None
         if row_mask is not None:
             m = L.as_u8(row_mask)
