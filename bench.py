@@ -521,7 +521,10 @@ def run_ours(a):
             "config": workload_config(a),
             "roofline": roofline,
             "cpu_baseline": cb,
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "note": "pinned host queries in, pinned host results out, every step; wall clock around the public call.  The "
+                            "device-timed loop above additionally records a CUDA-event pair and synchronises the library stream after "
+                            "every GEMM launch (roofline.kernel_ms), which costs it ~0.4 ms per step that this loop does not pay"},
             "gpu_launches": int(launches), "clocks": clocks, "recall_at_10": recall, "recall_queries": n_gt, "parity": parity,
             "search_ms": kernel_ms, "scanned_gbs_per_gpu": hbm_equiv,
             "tensor_core_filter": {"queries": int(qtc1[2] - qtc0[2]), "exact_rerun_queries": int(qtc1[3] - qtc0[3])},
