@@ -636,3 +636,27 @@ def test_pq_training_tensor_core_assignment_equals_exact_assignment(kind):
     tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "pq_assign_ab.py")
     r = subprocess.run([sys.executable, tool, "100000", "64", "8", "5", kind], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_search_with_page_locked_and_pageable_host_buffers(vg):
+    """vg_index_search DMA's page-locked query / result buffers directly and stages pageable ones: same answers."""
+    import torch
+
+    rng = np.random.default_rng(31)
+    n, dim, nq, k = 20000, 96, 700, 10   # 700 x 96 x 4 B > the 64 KB direct-DMA threshold
+    x = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_F32, metric=0, dim=dim, rows=n) as ix:
+        ix.upload(vectors=x)
+        rows, scores, counts = ix.search(q, k)
+        qp = torch.from_numpy(q).pin_memory()
+        out_t = (torch.empty((nq, k), dtype=torch.int32).pin_memory(), torch.empty((nq, k), dtype=torch.float32).pin_memory(),
+                 torch.empty((nq,), dtype=torch.int32).pin_memory())
+        out = (out_t[0].numpy().view(np.uint32), out_t[1].numpy(), out_t[2].numpy())
+        r2, s2, c2 = ix.search(qp.numpy(), k, out=out)
+        assert r2 is out[0] and s2 is out[1] and c2 is out[2]
+        with pytest.raises(ValueError):
+            ix.search(q, k, out=(out[0][:, :5], out[1], out[2]))
+    assert np.array_equal(rows, r2) and np.array_equal(bits(scores), bits(s2)) and np.array_equal(counts, c2)
+    want = _oracle_flat(q[:8], k, dim=dim, metric=0, vectors=x)
+    _check_topk(rows[:8], scores[:8], counts[:8], want, k)
