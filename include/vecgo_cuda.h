@@ -65,8 +65,22 @@ typedef uint64_t vg_index_t; /* device-resident scan index (one segment / one sh
 const char *vg_last_error(void);
 const char *vg_version(void);
 vg_status vg_device_count(int32_t *count);
-/* Binds the calling thread (and the library's streams) to `device`. */
+/* Devices, threads and streams.
+ * - A handle (vg_index_t) lives on ONE GPU: every call on it runs there, whichever thread makes it, so one process can
+ *   serve several GPUs (a Go host drives all GPUs of a box from one process).
+ * - vg_init(device) selects the GPU for calls WITHOUT a handle (training, encoders, simd mirrors, vg_index_create) made
+ *   by the calling thread; the first device initialised is the process default for threads that never call it.
+ *   vg_index_create_on / vg_flat_open_on take the device explicitly (no thread state: what a Go shim should use,
+ *   goroutines migrate between OS threads).
+ * - Every call runs on exactly one CUDA stream: the handle's (vg_index_set_stream), else the calling thread's
+ *   (vg_set_stream), else a stream leased from the device's pool for the duration of the call.  Concurrent callers
+ *   therefore run on different streams with their own scratch: search / rerank / score entry points are re-entrant on
+ *   a shared handle (flat segments are immutable, concurrent reads safe: flat/doc.go:52-55; Engine.BatchSearch runs
+ *   up to 100 goroutines, engine.go:365,1324).  create / upload / close are serialised per handle by the caller.
+ * - Host-pointer entry points return when their results are in the caller's buffers.  `_dev` entry points are
+ *   stream-ordered on a caller-provided stream (handle or thread stream) and complete on return otherwise. */
 vg_status vg_init(int32_t device);
+/* Waits for the library's streams on the calling thread's device (and the thread's own stream, if set). */
 vg_status vg_synchronize(void);
 vg_status vg_dev_alloc(void **d_ptr, size_t bytes);
 vg_status vg_dev_free(void *d_ptr);
@@ -74,10 +88,10 @@ vg_status vg_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes);
 vg_status vg_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes);
 /* Number of kernels this library has launched since load (for gpu_launches). */
 uint64_t vg_launch_count(void);
-/* Run subsequent kernels, copies and stream-ordered allocations on this CUDA stream (cudaStream_t as integer).
- * 0 is the legacy default stream (what PyTorch's default stream reports), NOT "unset": a caller that prepares inputs
- * on stream 0 and passes 0 gets correct ordering.  VG_STREAM_LIBRARY (~0) switches back to the library's own
- * non-blocking stream, which is also what is used before the first call. */
+/* Calls made by the CALLING THREAD run their kernels, copies and stream-ordered allocations on this CUDA stream
+ * (cudaStream_t as integer).  0 is the legacy default stream (what PyTorch's default stream reports), NOT "unset": a
+ * caller that prepares inputs on stream 0 and passes 0 gets correct ordering.  VG_STREAM_LIBRARY (~0) switches the
+ * thread back to library-owned streams, which is also the state of a thread that never called this. */
 #define VG_STREAM_LIBRARY (~0ull)
 vg_status vg_set_stream(uint64_t cuda_stream);
 
@@ -96,6 +110,8 @@ vg_status vg_simd_int4_l2_batch(const float *h_queries, int64_t nq, const uint8_
                                 const float *h_min, const float *h_diff, float *h_out);                          /* simd.Int4L2DistanceBatch */
 vg_status vg_simd_pq_adc_lookup(const float *h_tables, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t m, float *h_out); /* simd.PqAdcLookup; table [nq][m*256] */
 vg_status vg_simd_hamming(const uint8_t *h_queries, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t nbytes, int32_t *h_out); /* simd.Hamming */
+vg_status vg_simd_squared_l2_bounded(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, const float *h_bounds, float *h_out,
+                                     uint8_t *h_exceeded);                                                          /* simd.SquaredL2Bounded per pair */
 vg_status vg_simd_scale(float *h_a, int64_t n, float scalar);                                                    /* simd.ScaleInPlace */
 /* distance.NormalizeL2InPlace on each of n rows; h_ok[i]=0 for zero-norm rows (left untouched). */
 vg_status vg_normalize_l2(float *h_vecs, int64_t n, int64_t dim, uint8_t *h_ok);
@@ -190,7 +206,11 @@ typedef struct {
     const uint32_t *partition_offsets;               /* [P+1] */
 } vg_index_desc;
 
-vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out);
+vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out);      /* on the calling thread's device */
+vg_status vg_index_create_on(int32_t device, const vg_index_desc *desc, vg_index_t *out);
+/* Calls on this handle run on `cuda_stream` (VG_STREAM_LIBRARY: back to thread / leased streams); which GPU holds it. */
+vg_status vg_index_set_stream(vg_index_t idx, uint64_t cuda_stream);
+vg_status vg_index_device(vg_index_t idx, int32_t *device);
 /* Upload rows [row0,row0+n) of codes and/or float vectors from host memory
  * (e.g. the mmap'd segment) through the pinned staging ring.  Either may be
  * NULL.  Code row sizes: F32 none; SQ8 dim; INT4 (dim+1)/2; PQ m; BQ
@@ -207,9 +227,35 @@ vg_status vg_index_info(vg_index_t idx, int64_t *rows, int64_t *dim, int64_t *co
  * Outputs are [nq][k]; rows beyond out_counts[q] are 0xFFFFFFFF / NaN. */
 vg_status vg_index_search(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes,
                           const uint8_t *h_row_mask, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
-/* Same with device-resident queries and outputs (no host copies; stream-ordered). */
+/* Same with device-resident queries and outputs (no host copies of queries or results).  The tensor-core filters prove
+ * their result per query with a certificate; this call reads the nq certificate flags back (ONE stream synchronisation)
+ * and re-runs unproven queries before it returns, so the outputs are final on return.  The exact CUDA-core scan
+ * (small / partitioned shapes) has no flags and stays stream-ordered. */
 vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
                               const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
+/* The same search WITHOUT any host wait, for callers that keep the GPU queue full (needs a caller stream):
+ * vg_index_search_dev_async only launches; d_unproven[q] (device, [nq]) is 1 where the certificate of query q did not
+ * hold — that query's outputs are then candidates, not yet the reference's result.  vg_index_search_resolve, called
+ * with the same arguments whenever the caller synchronises anyway, reads the flags, gives those queries the filter's
+ * second chance and the exact scan, and overwrites their outputs; *n_resolved = how many needed it (0 on benign data). */
+vg_status vg_index_search_dev_async(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                                    const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts,
+                                    int32_t *d_unproven);
+vg_status vg_index_search_resolve(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                                  const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts,
+                                  const int32_t *d_unproven, int64_t *n_resolved);
+/* Counters of the last vg_index_search* / vg_index_search_resolve call made by the calling thread: what a Go caller adds
+ * to searcher.FilterGateStats / model.QueryStats (flat/segment.go:448-471,553-591).  distance_computations counts the
+ * (query, row) distance evaluations the reference's scan would report (rows visited per query, plus the rows of every
+ * exact re-run); the rest describes how the batch was answered. */
+typedef struct {
+    uint64_t queries;               /* queries in the call */
+    uint64_t distance_computations; /* FilterGateStats.DistanceComputations equivalent */
+    uint64_t filter_queries;        /* answered through a tensor-core filter + certificate */
+    uint64_t second_chance_queries; /* certificate failed once, filter re-run with twice the candidate groups */
+    uint64_t exact_rerun_queries;   /* no proof: re-run on the exact CUDA-core scan */
+} vg_search_stats;
+vg_status vg_last_search_stats(vg_search_stats *out);
 /* Batched Segment.Rerank (flat/segment.go:754-781): exact SquaredL2/Dot of each
  * query against its r candidate rows (local row ids); rows >= RowCount give NaN. */
 vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores);
@@ -217,9 +263,27 @@ vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq
 /* Quantized gather scoring: the codec's own distance of every query to ITS r candidate rows (local row ids; rows >=
  * RowCount give NaN), in the reference's arithmetic — what the DiskANN traversal evaluates per neighbour
  * (internal/segment/diskann/segment.go:511-588: pq.AdcDistance, int4.L2Distance, rabitq.Distance), batched.  SQ8
- * (L2), INT4, PQ / OPQ (K = 256) and RaBitQ; a float32 index scores exactly (= vg_index_rerank). */
+ * (L2), INT4, PQ / OPQ (K = 256), RaBitQ and BQ (Hamming distance as float32); a float32 index scores exactly
+ * (= vg_index_rerank). */
 vg_status vg_index_score(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores);
 vg_status vg_index_score_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, float *d_scores);
+/* INT4 gather scoring follows Int4Quantizer.L2Distance (int4.go:136-147): a trained / unmarshalled quantizer always has
+ * its lookup table, so the live path — and what DiskANN executes (diskann/segment.go:564,578) — is
+ * simd.Int4L2DistancePrecomputed over simd.BuildInt4LookupTable's values: VG_INT4_SCORE_LUT, the default.
+ * VG_INT4_SCORE_DIRECT selects simd.Int4L2Distance (FMA dequantisation, the nil-table fallback). */
+enum { VG_INT4_SCORE_LUT = 0, VG_INT4_SCORE_DIRECT = 1 };
+vg_status vg_index_set_int4_score_mode(vg_index_t idx, int32_t mode);
+/* simd.BuildInt4LookupTable (internal/simd/kernels.go:94-103): h_table [dim*16]. */
+vg_status vg_int4_build_lookup_table(const float *h_min, const float *h_diff, int64_t dim, float *h_table);
+/* distance.SquaredL2Bounded / simd.SquaredL2Bounded (distance/distance.go:24-31, internal/simd/kernels.go:163-217, AVX-512
+ * kernel internal/simd/src/bounded_l2_avx512.c:19-107) of every query against ITS r candidate rows of a float32 index:
+ * scores[q][j] is the distance, or the partial sum at the 64-dimension block where it first exceeded the bound, in
+ * which case exceeded[q][j] = 1.  Bounds: [nq] (one per query: the traversal's current worst result) or [nq][r] when
+ * per_pair_bounds.  Rows >= RowCount give NaN / 0. */
+vg_status vg_index_l2_bounded(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, const float *h_bounds,
+                              int32_t per_pair_bounds, float *h_scores, uint8_t *h_exceeded);
+vg_status vg_index_l2_bounded_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r,
+                                  const float *d_bounds, int32_t per_pair_bounds, float *d_scores, uint8_t *d_exceeded);
 /* Approximate scan to top-r, exact rerank, final top-k (engine refine path,
  * internal/engine/search.go:188-192,913-973), all on device. */
 vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t nq, int64_t r, int64_t k,
@@ -261,6 +325,7 @@ vg_status vg_quant_tc_profile(int32_t enable, double *gemm_ms, uint64_t *gemm_la
 /* flat.Open (internal/segment/flat/segment.go:105-342) on the raw file bytes:
  * header decode, optional CRC32C verify, section views, staging to HBM. */
 vg_status vg_flat_open(const uint8_t *h_file, size_t len, int32_t verify_checksum, vg_index_t *out);
+vg_status vg_flat_open_on(int32_t device, const uint8_t *h_file, size_t len, int32_t verify_checksum, vg_index_t *out);
 /* Header fields of an opened flat segment (format.go:28-51). */
 typedef struct {
     uint64_t segment_id;

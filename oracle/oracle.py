@@ -106,6 +106,8 @@ _sig(lib.vgo_int4_l2_batch_a512, None, f32p, u8p, i64, i64, f32p, f32p, f32p)
 _sig(lib.vgo_int4_build_lut, None, f32p, f32p, i64, f32p)
 _sig(lib.vgo_int4_l2_precomputed_generic, f32, f32p, u8p, i64, f32p)
 _sig(lib.vgo_int4_l2_precomputed_a512, f32, f32p, u8p, i64, f32p)
+_sig(lib.vgo_squared_l2_bounded_a512, f32, f32p, f32p, i64, f32, i32p)
+_sig(lib.vgo_squared_l2_bounded_generic, f32, f32p, f32p, i64, f32, i32p)
 _sig(lib.vgo_sql2_int8_dequant, f32, f32p, i8p, i64, f32, f32)
 _sig(lib.vgo_build_distance_table_int8, None, f32p, i8p, i64, f32, f32, i64, f32p)
 _sig(lib.vgo_find_nearest_centroid_int8, i64, f32p, i8p, i64, i64, f32, f32)
@@ -167,6 +169,7 @@ if ref is not None:
     _sig(ref.int4L2DistancePrecomputedAvx512, None, f32p, u8p, i64, f32p, f32p)
     _sig(ref.int4L2DistanceBatchAvx512, None, f32p, u8p, i64, i64, f32p, f32p, f32p)
     _sig(ref.hammingAvx512, C.c_longlong, u8p, u8p, i64)
+    _sig(ref.squaredL2BoundedAvx512, None, f32p, f32p, i64, f32, f32p, i32p)
     _sig(ref.squaredL2Int8DequantizedAvx512, None, f32p, i8p, i64, f32p, f32p, f32p)
 
 

@@ -394,6 +394,98 @@ VGO_API float vgo_int4_l2_precomputed_a512(const float *q, const uint8_t *code, 
 }
 
 /* ------------------------------------------------------------------------ */
+/* f4: simd.SquaredL2Bounded                                                 */
+/*     AVX-512: internal/simd/src/bounded_l2_avx512.c:19-107 (registered at  */
+/*     kernels_amd64.go:269); generic: internal/simd/kernels.go:178-217      */
+/* ------------------------------------------------------------------------ */
+static inline float hsum512_order(const float v[16]) { /* bounded_l2_avx512.c:6-17 */
+    float t[8], u[4];
+    for (int i = 0; i < 8; i++) t[i] = v[i] + v[i + 8];
+    for (int i = 0; i < 4; i++) u[i] = t[i] + t[i + 4];
+    float w0 = u[0] + u[1]; /* vhaddps */
+    float w1 = u[2] + u[3];
+    return w0 + w1;
+}
+VGO_API float vgo_squared_l2_bounded_a512(const float *a, const float *b, int64_t n, float bound, int32_t *exceeded) {
+    float s[4][16];
+    memset(s, 0, sizeof s);
+    float total = 0.0f;
+    int64_t i = 0;
+    while (i + 64 <= n) {
+        for (int j = 0; j < 4; j++)
+            for (int l = 0; l < 16; l++) {
+                float d = a[i + 16 * j + l] - b[i + 16 * j + l];
+                s[j][l] = fmaf(d, d, s[j][l]);
+            }
+        i += 64;
+        float c[16];
+        for (int l = 0; l < 16; l++) {
+            float x = s[0][l] + s[1][l];
+            float y = s[2][l] + s[3][l];
+            c[l] = x + y;
+        }
+        total = hsum512_order(c);
+        if (total > bound) {
+            *exceeded = 1;
+            return total;
+        }
+    }
+    {
+        float c[16];
+        for (int l = 0; l < 16; l++) {
+            float x = s[0][l] + s[1][l];
+            float y = s[2][l] + s[3][l];
+            c[l] = x + y;
+        }
+        total = hsum512_order(c);
+    }
+    for (; i + 8 <= n; i += 8) {
+        float sq[8], w[4];
+        for (int l = 0; l < 8; l++) {
+            float d = a[i + l] - b[i + l];
+            sq[l] = d * d;
+        }
+        for (int l = 0; l < 4; l++) w[l] = sq[l] + sq[l + 4];
+        float h0 = w[0] + w[1];
+        float h1 = w[2] + w[3];
+        float h = h0 + h1;
+        total = total + h;
+    }
+    for (; i < n; i++) { /* shipped asm fuses the scalar tail: bounded_l2_avx512.s:94-114 */
+        float d = a[i] - b[i];
+        total = fmaf(d, d, total);
+    }
+    *exceeded = (total > bound) ? 1 : 0;
+    return total;
+}
+VGO_API float vgo_squared_l2_bounded_generic(const float *a, const float *b, int64_t n, float bound, int32_t *exceeded) {
+    float distance = 0.0f;
+    int64_t i = 0;
+    for (; i + 64 <= n; i += 64) {
+        for (int64_t j = i; j < i + 64; j += 8) {
+            float acc = 0.0f;
+            for (int u = 0; u < 8; u++) {
+                float d = a[j + u] - b[j + u];
+                float p = d * d;
+                acc = (u == 0) ? p : acc + p; /* d0*d0 + d1*d1 + ... left to right */
+            }
+            distance = distance + acc;
+        }
+        if (distance > bound) {
+            *exceeded = 1;
+            return distance;
+        }
+    }
+    for (; i < n; i++) {
+        float d = a[i] - b[i];
+        float p = d * d;
+        distance = distance + p;
+    }
+    *exceeded = distance > bound ? 1 : 0;
+    return distance;
+}
+
+/* ------------------------------------------------------------------------ */
 /* a10: simd.PqAdcLookup, AVX-512 order — src/floats_avx512.c:135-167        */
 /* (table stride hard-wired to 256).                                         */
 /* ------------------------------------------------------------------------ */

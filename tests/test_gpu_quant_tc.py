@@ -451,12 +451,53 @@ def test_gather_scoring_matches_oracle(vg):
     c4 = iq.EncodeBatch(v)
     with vg.index.DeviceIndex(codec=vg._lib.CODEC_INT4, metric=0, dim=dim, rows=n, int4=(iq.min, iq.diff)) as ix:
         ix.upload(codes=c4)
+        got_lut = ix.score(q, cand)          # default: Int4Quantizer.L2Distance's live path (precomputed lookup table)
+        ix.set_int4_score_mode(direct=True)  # simd.Int4L2Distance (nil-table fallback, int4.go:146)
         got = ix.score(q, cand)
+    lut = np.zeros(dim * 16, F)
+    o.lib.vgo_int4_build_lut(o.fp(iq.min), o.fp(iq.diff), dim, o.fp(lut))
+    mine = np.zeros(dim * 16, F)
+    vg._lib.call("vg_int4_build_lookup_table", vg._lib.ptr(iq.min, vg._lib.f32p), vg._lib.ptr(iq.diff, vg._lib.f32p), dim,
+                 vg._lib.ptr(mine, vg._lib.f32p))
+    assert np.array_equal(bits(mine), bits(lut))  # simd.BuildInt4LookupTable, kernels.go:94-103
     for i in range(nq):
         for j in range(r):
             if cand[i, j] < n:
                 w = o.lib.vgo_int4_l2_a512(o.fp(q[i]), o.bp(c4[cand[i, j]]), dim, o.fp(iq.min), o.fp(iq.diff))
                 assert bits(got[i, j]) == bits(F(w)), (i, j)
+                w = o.lib.vgo_int4_l2_precomputed_a512(o.fp(q[i]), o.bp(c4[cand[i, j]]), dim, o.fp(lut))
+                assert bits(got_lut[i, j]) == bits(F(w)), (i, j)
+    # INT4 at an odd, non-multiple-of-16 dimension (row-major layout, scalar tail of the precomputed kernel)
+    d2 = 131
+    v2 = rng.standard_normal((500, d2)).astype(F)
+    iq2 = vg.quantization.Int4Quantizer(d2)
+    iq2.Train(v2)
+    c42 = iq2.EncodeBatch(v2)
+    q2 = rng.standard_normal((3, d2)).astype(F)
+    cand2 = rng.integers(0, 500, (3, 11)).astype(np.uint32)
+    lut2 = np.zeros(d2 * 16, F)
+    o.lib.vgo_int4_build_lut(o.fp(iq2.min), o.fp(iq2.diff), d2, o.fp(lut2))
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_INT4, metric=0, dim=d2, rows=500, int4=(iq2.min, iq2.diff)) as ix:
+        ix.upload(codes=c42)
+        got2 = ix.score(q2, cand2)
+    for i in range(3):
+        for j in range(11):
+            w = o.lib.vgo_int4_l2_precomputed_a512(o.fp(q2[i]), o.bp(c42[cand2[i, j]]), d2, o.fp(lut2))
+            assert bits(got2[i, j]) == bits(F(w)), (i, j)
+    # BQ (Hamming distance as float32: binary.go score = float32(popcount))
+    bq = vg.quantization.BinaryQuantizer(dim)
+    bq.Train(v)
+    bc = bq.EncodeBatch(v)
+    with vg.index.DeviceIndex(codec=vg._lib.CODEC_BQ, metric=0, dim=dim, rows=n, bq_threshold=float(bq.threshold)) as ix:
+        ix.upload(codes=bc)
+        gotb = ix.score(q, cand)
+    qb = bq.EncodeBatch(q)
+    for i in range(nq):
+        for j in range(r):
+            if cand[i, j] < n:
+                h = int(np.unpackbits(np.bitwise_xor(qb[i], bc[cand[i, j]])).sum())
+                assert gotb[i, j] == F(h), (i, j)
+    assert np.isnan(gotb[0, 3])
     # PQ (generic table build + pqAdcLookupAvx512 order), tiled layout
     m = 96
     cb, sc, of = random_pq(rng, dim, m)

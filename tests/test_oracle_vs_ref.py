@@ -136,3 +136,40 @@ def test_flat_search_oracle_vs_numpy_bruteforce():
         seg2 = o.FlatOracle(dim=d, metric=0, vectors=x, kernels=o.ref_kernels())
         out2, _ = seg2.search_batch(q, k, threads=4)
         assert np.array_equal(out2["row"], out["row"]) and np.array_equal(bits(out2["score"]), bits(out["score"]))
+
+
+@needs_ref
+def test_bounded_l2_bit_exact():
+    """simd.SquaredL2Bounded (bounded_l2_avx512.c:19-107): the early-exit partial totals, the flag and the tails."""
+    import ctypes as C
+
+    rng = np.random.default_rng(21)
+    for n in LENGTHS + [130, 136, 199, 640, 769]:
+        for _ in range(4):
+            a, b = rng.standard_normal(n).astype(F), rng.standard_normal(n).astype(F)
+            full = float(np.sum((a.astype(np.float64) - b) ** 2))
+            for bound in (np.inf, 0.0, full * 0.25, full * 0.5, full * 0.99, full * 1.01, -1.0, np.nan):
+                ex1, ex2 = C.c_int32(-1), C.c_int32(-1)
+                mine = o.lib.vgo_squared_l2_bounded_a512(o.fp(a), o.fp(b), n, F(bound), C.byref(ex1))
+                theirs = np.zeros(1, F)
+                o.ref.squaredL2BoundedAvx512(o.fp(a), o.fp(b), n, F(bound), o.fp(theirs), C.byref(ex2))
+                assert bits(mine) == bits(theirs[0]), (n, bound)
+                assert ex1.value == ex2.value, (n, bound)
+
+
+def test_bounded_l2_generic_semantics():
+    """distance_test / kernels.go:178-217: full distance when the bound is not exceeded, early exit otherwise; the SIMD
+    and generic paths agree within the reference's 1e-4 relative tolerance on the full distance."""
+    import ctypes as C
+
+    rng = np.random.default_rng(22)
+    for n in [1, 8, 63, 64, 65, 128, 200, 768]:
+        a, b = rng.standard_normal(n).astype(F), rng.standard_normal(n).astype(F)
+        ex = C.c_int32()
+        full = o.lib.vgo_squared_l2_bounded_generic(o.fp(a), o.fp(b), n, F(np.inf), C.byref(ex))
+        assert ex.value == 0
+        assert abs(full - o.lib.vgo_sql2_generic(o.fp(a), o.fp(b), n)) <= 1e-4 * max(1.0, full)
+        simd = o.lib.vgo_squared_l2_bounded_a512(o.fp(a), o.fp(b), n, F(np.inf), C.byref(ex))
+        assert abs(simd - full) <= 1e-4 * max(1.0, full)
+        part = o.lib.vgo_squared_l2_bounded_generic(o.fp(a), o.fp(b), n, F(full * 0.1), C.byref(ex))
+        assert ex.value == 1 and part <= full * (1 + 1e-6)

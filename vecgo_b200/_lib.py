@@ -51,6 +51,11 @@ class IndexDesc(C.Structure):
     ]
 
 
+class SearchStats(C.Structure):
+    _fields_ = [("queries", u64), ("distance_computations", u64), ("filter_queries", u64), ("second_chance_queries", u64),
+                ("exact_rerun_queries", u64)]
+
+
 class FlatHeader(C.Structure):
     _fields_ = [("segment_id", u64), ("row_count", C.c_uint32), ("dim", C.c_uint32), ("metric", C.c_uint32),
                 ("num_partitions", C.c_uint32), ("quantization_type", C.c_uint32), ("checksum", C.c_uint32)]
@@ -73,6 +78,7 @@ _SIGS = {
     "vg_simd_int4_l2_batch": [f32p, i64, u8p, i64, i64, f32p, f32p, f32p],
     "vg_simd_pq_adc_lookup": [f32p, i64, u8p, i64, i64, f32p],
     "vg_simd_hamming": [u8p, i64, u8p, i64, i64, i32p],
+    "vg_simd_squared_l2_bounded": [f32p, f32p, i64, i64, f32p, f32p, u8p],
     "vg_simd_scale": [f32p, i64, f32],
     "vg_normalize_l2": [f32p, i64, i64, u8p],
     "vg_sq8_train": [f32p, i64, i64, f32p, f32p, f32p, f32p],
@@ -104,6 +110,16 @@ _SIGS = {
     "vg_kmeans_assign": [f32p, i64, i64, f32p, i64, i32, i32p],
     "vg_kmeans_find_closest": [f32p, i64, i64, f32p, i64, i64, i32, i32p],
     "vg_index_create": [C.POINTER(IndexDesc), u64p],
+    "vg_index_create_on": [i32, C.POINTER(IndexDesc), u64p],
+    "vg_index_set_stream": [u64, u64],
+    "vg_index_device": [u64, i32p],
+    "vg_index_search_dev_async": [u64, vp, i64, i64, i64, vp, vp, vp, vp, vp],
+    "vg_index_search_resolve": [u64, vp, i64, i64, i64, vp, vp, vp, vp, vp, i64p],
+    "vg_last_search_stats": [C.POINTER(SearchStats)],
+    "vg_index_set_int4_score_mode": [u64, i32],
+    "vg_int4_build_lookup_table": [f32p, f32p, i64, f32p],
+    "vg_index_l2_bounded": [u64, f32p, i64, u32p, i64, f32p, i32, f32p, u8p],
+    "vg_index_l2_bounded_dev": [u64, vp, i64, vp, i64, vp, i32, vp, vp],
     "vg_index_upload": [u64, i64, i64, vp, f32p],
     "vg_index_upload_dev": [u64, i64, i64, vp, vp],
     "vg_index_close": [u64],
@@ -121,6 +137,7 @@ _SIGS = {
     "vg_quant_tc_profile": [i32, C.POINTER(C.c_double), u64p],
     "vg_flat_tc_candidates": [u64, f32p, i64, i64, u32p, i32p, f32p, i64p],
     "vg_flat_open": [u8p, sz, i32, u64p],
+    "vg_flat_open_on": [i32, u8p, sz, i32, u64p],
     "vg_flat_decode_header": [u8p, sz, C.POINTER(FlatHeader)],
     "vg_index_fetch_ids": [u64, u32p, i64, u64p],
     "vg_topk_merge_dev": [vp, vp, i64, i64, i64, i32, i64, vp, vp, vp],
@@ -145,6 +162,13 @@ def check(status: int) -> None:
 
 def call(name: str, *args) -> None:
     check(getattr(lib, name)(*args))
+
+
+def last_search_stats() -> dict:
+    """Counters of the calling thread's last search call (vg_last_search_stats)."""
+    st = SearchStats()
+    call("vg_last_search_stats", C.byref(st))
+    return {name: int(getattr(st, name)) for name, _ in SearchStats._fields_}
 
 
 def launch_count() -> int:

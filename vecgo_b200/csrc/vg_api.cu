@@ -23,14 +23,40 @@
 namespace vg {
 
 // ------------------------------------------------------------------ runtime
+// State is per DEVICE (streams, pinned staging ring) and per THREAD (the device selected with vg_init, the stream set
+// with vg_set_stream, the binding of the call in flight); nothing about a call lives in a process-wide variable, so a
+// host may drive several GPUs from one process and many threads may search one handle at once (Threading).
 static thread_local std::string t_error;
 std::atomic<uint64_t> g_launches{0};
-static cudaStream_t g_stream = nullptr;       // library stream (created by vg_init)
-static cudaStream_t g_user_stream = nullptr;  // vg_set_stream override
-static bool g_user_stream_set = false;
-static int g_device = -1;
-static int g_sms = 0;
-static std::mutex g_mu;
+static const int kMaxDevices = 64;
+static const size_t kStageBytes = 32u << 20;
+
+struct DeviceCtx {
+    int device = -1;
+    int sms = 0;
+    std::mutex mu;                           // stream leases
+    std::vector<cudaStream_t> free_streams;  // non-blocking streams owned by the library, handed out one per call
+    // Pinned staging ring: two 32 MiB page-locked buffers.  The CPU fills one while the copy engine drains the other
+    // (mmap'd segment pages are pageable, so this is where they become DMA-able).
+    std::mutex stage_mu;
+    void *stage[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+};
+static DeviceCtx *g_ctx[kMaxDevices] = {};
+static std::mutex g_mu;                      // contexts and the handle table
+static std::atomic<int> g_default_device{-1};
+
+struct ThreadState {
+    int device = -1;                 // vg_init on this thread (-1: process default)
+    bool user_stream_set = false;    // vg_set_stream on this thread
+    cudaStream_t user_stream = nullptr;
+    // the call in flight
+    int depth = 0;
+    DeviceCtx *ctx = nullptr;
+    cudaStream_t st = nullptr;
+    bool leased = false;
+};
+static thread_local ThreadState t_ts;
 
 void set_error(const std::string &msg) { t_error = msg; }
 vg_status fail(vg_status code, const std::string &msg) {
@@ -42,15 +68,104 @@ vg_status cuda_fail(cudaError_t e, const char *what) {
     cudaGetLastError();
     return VG_ERR_CUDA;
 }
-cudaStream_t stream() { return g_user_stream_set ? g_user_stream : g_stream; }
-int sm_count() { return g_sms > 0 ? g_sms : 148; }
+cudaStream_t stream() { return t_ts.st; }
+int sm_count() { return t_ts.ctx && t_ts.ctx->sms > 0 ? t_ts.ctx->sms : 148; }
 
-vg_status ensure_init() {
-    if (g_device >= 0) {
-        VG_CUDA(cudaSetDevice(g_device));
-        return VG_OK;
+static vg_status get_ctx(int device, DeviceCtx **out) {
+    if (device < 0 || device >= kMaxDevices) return fail(VG_ERR_INVALID, "device ordinal out of range");
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_ctx[device]) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0) {
+            if (e != cudaSuccess) cudaGetLastError();
+            return fail(VG_ERR_CUDA, "no CUDA device: libvecgo_cuda has no CPU path");
+        }
+        if (device >= n) return fail(VG_ERR_INVALID, "device ordinal out of range");
+        cudaDeviceProp prop;
+        VG_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) return fail(VG_ERR_CUDA, "libvecgo_cuda is built for sm_100a (Blackwell) only");
+        VG_CUDA(cudaSetDevice(device));
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;  // scratch stays cached in the pool (never trimmed at synchronisation points): its size is
+                                    // bounded by what the calls in flight need (<= ~8.5 GiB each for the largest group-minima buffer)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        DeviceCtx *c = new DeviceCtx();
+        c->device = device;
+        c->sms = prop.multiProcessorCount;
+        g_ctx[device] = c;
+        int none = -1;
+        g_default_device.compare_exchange_strong(none, device);
     }
-    return vg_init(0);
+    *out = g_ctx[device];
+    return VG_OK;
+}
+
+Call::Call(int device, bool handle_stream_set, cudaStream_t handle_stream) {
+    ThreadState &ts = t_ts;
+    if (ts.depth > 0) {  // nested entry point: keep the outer call's device and stream
+        if (device >= 0 && ts.ctx && ts.ctx->device != device) {
+            status = fail(VG_ERR_INVALID, "nested call on a different device");
+            return;
+        }
+        ts.depth++;
+        return;
+    }
+    if (device < 0) device = ts.device >= 0 ? ts.device : (g_default_device.load() >= 0 ? g_default_device.load() : 0);
+    DeviceCtx *ctx = nullptr;
+    status = get_ctx(device, &ctx);
+    if (status != VG_OK) return;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        status = cuda_fail(e, "cudaSetDevice");
+        return;
+    }
+    ts.ctx = ctx;
+    ts.leased = false;
+    if (handle_stream_set) {
+        ts.st = handle_stream;
+    } else if (ts.user_stream_set) {
+        ts.st = ts.user_stream;
+    } else {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        if (!ctx->free_streams.empty()) {
+            ts.st = ctx->free_streams.back();
+            ctx->free_streams.pop_back();
+        } else {
+            e = cudaStreamCreateWithFlags(&ts.st, cudaStreamNonBlocking);
+            if (e != cudaSuccess) {
+                status = cuda_fail(e, "cudaStreamCreateWithFlags");
+                ts.ctx = nullptr;
+                return;
+            }
+        }
+        ts.leased = true;
+    }
+    ts.depth = 1;
+    outer = true;
+}
+Call::~Call() {
+    ThreadState &ts = t_ts;
+    if (status != VG_OK && !outer) return;  // a failed nested constructor did not change the depth
+    if (ts.depth > 0) ts.depth--;
+    if (outer && ts.depth == 0) {
+        if (ts.leased && ts.ctx) {
+            // Work that is still queued on a leased stream (stream-ordered frees of scratch) stays ordered: the next
+            // lease of this stream simply queues behind it.
+            std::lock_guard<std::mutex> lk(ts.ctx->mu);
+            ts.ctx->free_streams.push_back(ts.st);
+        }
+        ts.ctx = nullptr;
+        ts.st = nullptr;
+        ts.leased = false;
+    }
+}
+bool Call::leased() const { return t_ts.leased; }
+vg_status Call::finish() {
+    if (t_ts.leased && t_ts.depth == 1) VG_CUDA(cudaStreamSynchronize(t_ts.st));
+    return VG_OK;
 }
 
 // Scratch buffers (per-call temporaries: query copies, partial top-k lists, result staging) come from the device's
@@ -96,19 +211,11 @@ void DevBuf::release() {
     bytes = 0;
 }
 
-// Pinned staging ring: two 32 MiB page-locked buffers.  The CPU fills one
-// while the copy engine drains the other (mmap'd segment pages are pageable,
-// so this is where they become DMA-able).
-static const size_t kStageBytes = 32u << 20;
-static void *g_stage[2] = {nullptr, nullptr};
-static cudaEvent_t g_stage_ev[2];
-static std::mutex g_stage_mu;
-
-static vg_status ensure_stage() {
-    if (g_stage[0]) return VG_OK;
+static vg_status ensure_stage(DeviceCtx *c) {
+    if (c->stage[0]) return VG_OK;
     for (int i = 0; i < 2; i++) {
-        VG_CUDA(cudaHostAlloc(&g_stage[i], kStageBytes, cudaHostAllocDefault));
-        VG_CUDA(cudaEventCreateWithFlags(&g_stage_ev[i], cudaEventDisableTiming));
+        VG_CUDA(cudaHostAlloc(&c->stage[i], kStageBytes, cudaHostAllocDefault));
+        VG_CUDA(cudaEventCreateWithFlags(&c->stage_ev[i], cudaEventDisableTiming));
     }
     return VG_OK;
 }
@@ -141,49 +248,52 @@ static bool host_pinned(const void *p) {
     }
     return at.type == cudaMemoryTypeHost;
 }
+// Small transfers from pageable memory (a query, a few result rows): cudaMemcpyAsync stages them through the driver's
+// own pinned buffer and returns once the source was read, so concurrent callers do not queue on the ring's mutex.
+static const size_t kSmallCopy = 64u << 10;
 vg_status staged_h2d(void *d_dst, const void *h_src, size_t bytes) {
     if (bytes == 0) return VG_OK;
-    if (bytes >= (64u << 10) && host_pinned(h_src)) {
-        cudaStream_t st = stream();
+    cudaStream_t st = stream();
+    if (bytes < kSmallCopy || host_pinned(h_src)) {
         VG_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st));
         VG_CUDA(cudaStreamSynchronize(st));
         return VG_OK;
     }
-    std::lock_guard<std::mutex> lk(g_stage_mu);
-    VG_TRY(ensure_stage());
-    cudaStream_t st = stream();
+    DeviceCtx *c = t_ts.ctx;
+    std::lock_guard<std::mutex> lk(c->stage_mu);
+    VG_TRY(ensure_stage(c));
     size_t off = 0;
     int i = 0;
     while (off < bytes) {
         const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
-        VG_CUDA(cudaEventSynchronize(g_stage_ev[i]));
-        stage_copy(g_stage[i], (const char *)h_src + off, n);
-        VG_CUDA(cudaMemcpyAsync((char *)d_dst + off, g_stage[i], n, cudaMemcpyHostToDevice, st));
-        VG_CUDA(cudaEventRecord(g_stage_ev[i], st));
+        VG_CUDA(cudaEventSynchronize(c->stage_ev[i]));
+        stage_copy(c->stage[i], (const char *)h_src + off, n);
+        VG_CUDA(cudaMemcpyAsync((char *)d_dst + off, c->stage[i], n, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaEventRecord(c->stage_ev[i], st));
         off += n;
         i ^= 1;
     }
-    VG_CUDA(cudaEventSynchronize(g_stage_ev[0]));
-    VG_CUDA(cudaEventSynchronize(g_stage_ev[1]));
+    VG_CUDA(cudaEventSynchronize(c->stage_ev[0]));
+    VG_CUDA(cudaEventSynchronize(c->stage_ev[1]));
     return VG_OK;
 }
 vg_status staged_d2h(void *h_dst, const void *d_src, size_t bytes) {
     if (bytes == 0) return VG_OK;
-    if (bytes >= (64u << 10) && host_pinned(h_dst)) {
-        cudaStream_t st = stream();
+    cudaStream_t st = stream();
+    if (bytes < kSmallCopy || host_pinned(h_dst)) {
         VG_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, st));
         VG_CUDA(cudaStreamSynchronize(st));
         return VG_OK;
     }
-    std::lock_guard<std::mutex> lk(g_stage_mu);
-    VG_TRY(ensure_stage());
-    cudaStream_t st = stream();
+    DeviceCtx *c = t_ts.ctx;
+    std::lock_guard<std::mutex> lk(c->stage_mu);
+    VG_TRY(ensure_stage(c));
     size_t off = 0;
     while (off < bytes) {
         const size_t n = bytes - off < kStageBytes ? bytes - off : kStageBytes;
-        VG_CUDA(cudaMemcpyAsync(g_stage[0], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaMemcpyAsync(c->stage[0], (const char *)d_src + off, n, cudaMemcpyDeviceToHost, st));
         VG_CUDA(cudaStreamSynchronize(st));
-        memcpy((char *)h_dst + off, g_stage[0], n);
+        memcpy((char *)h_dst + off, c->stage[0], n);
         off += n;
     }
     return VG_OK;
@@ -199,6 +309,9 @@ static vg_status to_device(DevBuf &buf, const T *h, size_t count) {
 // ------------------------------------------------------------------ index
 struct Index {
     vg_index_desc d{};
+    int device = 0;                  // the GPU that holds this index: every call on the handle runs there
+    bool stream_set = false;         // vg_index_set_stream: calls on this handle run on the caller's stream
+    cudaStream_t user_stream = nullptr;
     int variant = 0;
     int64_t code_row_bytes = 0;      // host/file layout
     int64_t dev_row_bytes = 0;       // device layout
@@ -206,6 +319,7 @@ struct Index {
     DevBuf pq_cb, pq_scales, pq_offsets, centroids, part_off, rotation;
     std::vector<uint32_t> h_part_off;
     int words32 = 0;
+    bool int4_direct = false;        // vg_index_score on INT4: simd.Int4L2Distance instead of the precomputed-LUT path
     bool has_vectors = false, has_codes = false, has_ids = false;
     // tensor-core Flat filter state (vg_flat_tc.cu): squared row norms + their maximum, rebuilt after uploads
     DevBuf xn, xmax;
@@ -222,6 +336,7 @@ struct Index {
 };
 static std::unordered_map<uint64_t, Index *> g_indexes;
 static uint64_t g_next_handle = 1;
+#define VG_ENTER_IX(ix) VG_ENTER((ix)->device, (ix)->stream_set, (ix)->user_stream)
 
 static Index *lookup(vg_index_t h) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -285,51 +400,52 @@ vg_status vg_device_count(int32_t *count) {
 }
 
 vg_status vg_init(int32_t device) {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n == 0) {
-        if (e != cudaSuccess) cudaGetLastError();
-        return fail(VG_ERR_CUDA, "no CUDA device: libvecgo_cuda has no CPU path");
-    }
-    if (device < 0 || device >= n) return fail(VG_ERR_INVALID, "device ordinal out of range");
+    // Selects `device` for the calling thread: calls without a handle (quantizer training, simd mirrors, vg_index_create)
+    // made by this thread run there.  The first device any thread initialises is also the process default, which
+    // threads that never call vg_init use.  Handles remember their device: calls on a handle run on its GPU whatever
+    // the calling thread selected, so one process can serve several GPUs.
+    DeviceCtx *ctx = nullptr;
+    VG_TRY(get_ctx(device, &ctx));
     VG_CUDA(cudaSetDevice(device));
-    std::lock_guard<std::mutex> lk(g_mu);
-    if (g_device != device) {
-        cudaDeviceProp prop;
-        VG_CUDA(cudaGetDeviceProperties(&prop, device));
-        if (prop.major < 10) return fail(VG_ERR_CUDA, "libvecgo_cuda is built for sm_100a (Blackwell) only");
-        g_sms = prop.multiProcessorCount;
-        if (g_stream) {
-            cudaStreamDestroy(g_stream);
-            g_stream = nullptr;
-        }
-        VG_CUDA(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-            uint64_t keep = ~0ull;  // scratch stays cached in the pool (never trimmed at synchronisation points): its size is
-                                    // bounded by what one call needs (<= ~5 GiB for the largest group-minima buffer)
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        g_device = device;
-    }
+    t_ts.device = device;
     return VG_OK;
 }
 vg_status vg_synchronize(void) {
-    VG_TRY(ensure_init());
+    // every stream the library owns on the calling thread's device, and the thread's own stream if it set one
+    VG_ENTER();
+    DeviceCtx *c = t_ts.ctx;
+    std::vector<cudaStream_t> all;
+    {
+        std::lock_guard<std::mutex> lk(c->mu);
+        all = c->free_streams;
+    }
+    for (cudaStream_t s_ : all) VG_CUDA(cudaStreamSynchronize(s_));
     VG_CUDA(cudaStreamSynchronize(stream()));
     return VG_OK;
 }
 vg_status vg_set_stream(uint64_t cuda_stream) {
-    VG_TRY(ensure_init());
     // 0 is a real stream handle (the legacy default stream, what torch.cuda.current_stream().cuda_stream returns for
-    // PyTorch's default stream): the library must run ON it, otherwise its own non-blocking stream races with the
-    // caller's work on stream 0.  ~0 switches back to the library's own stream.
-    g_user_stream_set = cuda_stream != ~0ull;
-    g_user_stream = g_user_stream_set ? reinterpret_cast<cudaStream_t>(cuda_stream) : nullptr;
+    // PyTorch's default stream): the library must run ON it, otherwise its own non-blocking streams race with the
+    // caller's work on stream 0.  ~0 switches back to library-owned streams.  The setting belongs to the calling THREAD.
+    t_ts.user_stream_set = cuda_stream != ~0ull;
+    t_ts.user_stream = t_ts.user_stream_set ? reinterpret_cast<cudaStream_t>(cuda_stream) : nullptr;
+    return VG_OK;
+}
+vg_status vg_index_set_stream(vg_index_t idx, uint64_t cuda_stream) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    ix->stream_set = cuda_stream != ~0ull;
+    ix->user_stream = ix->stream_set ? reinterpret_cast<cudaStream_t>(cuda_stream) : nullptr;
+    return VG_OK;
+}
+vg_status vg_index_device(vg_index_t idx, int32_t *device) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (device) *device = ix->device;
     return VG_OK;
 }
 vg_status vg_dev_alloc(void **d_ptr, size_t bytes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     VG_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
     return VG_OK;
 }
@@ -338,24 +454,28 @@ vg_status vg_dev_free(void *d_ptr) {
     return VG_OK;
 }
 vg_status vg_memcpy_h2d(void *d_dst, const void *h_src, size_t bytes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     return staged_h2d(d_dst, h_src, bytes);
 }
 vg_status vg_memcpy_d2h(void *h_dst, const void *d_src, size_t bytes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     VG_CUDA(cudaStreamSynchronize(stream()));
     return staged_d2h(h_dst, d_src, bytes);
 }
 
 // ----------------------------------------------------------- index lifecycle
-vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
-    VG_TRY(ensure_init());
+vg_status vg_index_create_on(int32_t device, const vg_index_desc *desc, vg_index_t *out) {
+    VG_ENTER(device);
     if (!desc || !out) return fail(VG_ERR_INVALID, "null argument");
     const vg_index_desc &d = *desc;
     if (d.dim <= 0 || d.rows < 0) return fail(VG_ERR_INVALID, "dim must be positive and rows non-negative");
     if (d.rows > 0xFFFFFFFEll) return fail(VG_ERR_INVALID, "rows exceed uint32 RowID space");
+    // global ids are uint32 (searcher.InternalCandidate.RowID) and 0xFFFFFFFF is the empty sentinel of the merges
+    if (d.row_base > 0xFFFFFFFEull || d.row_base + (uint64_t)d.rows > 0xFFFFFFFEull)
+        return fail(VG_ERR_INVALID, "row_base + rows exceeds the uint32 RowID space");
     std::unique_ptr<Index> ix(new Index());
     ix->d = d;
+    ix->device = t_ts.ctx->device;
     ix->code_row_bytes = host_code_bytes(d);
     ix->dev_row_bytes = ix->code_row_bytes;
     const int64_t rows = d.rows > 0 ? d.rows : 1;
@@ -430,6 +550,8 @@ vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) {
     return VG_OK;
 }
 
+vg_status vg_index_create(const vg_index_desc *desc, vg_index_t *out) { return vg_index_create_on(-1, desc, out); }
+
 vg_status vg_index_close(vg_index_t idx) {
     Index *ix = nullptr;
     {
@@ -439,7 +561,8 @@ vg_status vg_index_close(vg_index_t idx) {
         ix = it->second;
         g_indexes.erase(it);
     }
-    cudaStreamSynchronize(stream());
+    VG_ENTER(ix->device);
+    cudaDeviceSynchronize();  // searches still in flight on other streams of this device finish before the sections are freed
     delete ix;
     return VG_OK;
 }
@@ -488,9 +611,9 @@ static vg_status ensure_vectors(Index *ix) {
 }
 
 vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const void *d_codes, const float *d_vectors) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (row0 < 0 || n < 0 || row0 + n > ix->d.rows) return fail(VG_ERR_INVALID, "row range outside the index");
     if (n == 0) return VG_OK;
     if (d_codes) {
@@ -510,9 +633,9 @@ vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const voi
 }
 
 vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h_codes, const float *h_vectors) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (row0 < 0 || n < 0 || row0 + n > ix->d.rows) return fail(VG_ERR_INVALID, "row range outside the index");
     if (n == 0) return VG_OK;
     if (h_codes) {
@@ -540,14 +663,18 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
 }
 
 // --------------------------------------------------------------- search
-// Flat float32 search through the tcgen05 filter (vg_flat_tc.cu): candidates by TF32 GEMM, exact re-check in simd
-// pair order, certificate; queries whose certificate fails are re-run on the exact CUDA-core scan below.
+// Per-call statistics of the last search on the calling thread (the reference's searcher.FilterGateStats /
+// model.QueryStats counters a Go caller fills from them, flat/segment.go:448-471,553-591).
+static thread_local vg_search_stats t_stats;
+
+// Lazy per-index filter state.  Built once even if searches race (prep_mu) and COMPLETE on the device before the lock is
+// released: another thread's search runs on another stream and must not start before these kernels have finished.
 static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
     std::lock_guard<std::mutex> lk(ix->prep_mu);
     if (!ix->xn_dirty && ix->xn.p) return VG_OK;
     const int64_t rows = ix->d.rows;
     if (!ix->xn.p) VG_TRY(ix->xn.alloc_persistent((size_t)rows * 4));
-    if (!ix->xmax.p) VG_TRY(ix->xmax.alloc(16));
+    if (!ix->xmax.p) VG_TRY(ix->xmax.alloc_persistent(16));
     VG_CUDA(cudaMemsetAsync(ix->xmax.p, 0, 16, st));
     VG_TRY(tc::sqnorms(ix->vectors.as<float>(), rows, ix->d.dim, ix->d.dim, ix->xn.as<float>(), ix->xmax.as<unsigned int>(), st));
     if (rows >= 8192 && tc::pair_enabled()) {
@@ -566,20 +693,99 @@ static vg_status ensure_row_norms(Index *ix, cudaStream_t st) {
         VG_TRY(tc::make_shadow16(ix->vectors.as<float>(), rows, ix->d.dim, dimp, e, ix->x16.p, st));
         ix->x16_exp = e;
     }
+    VG_CUDA(cudaStreamSynchronize(st));
     ix->xn_dirty = false;
     return VG_OK;
 }
-static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, int64_t k, const uint8_t *d_mask, uint32_t *d_rows,
-                                float *d_scores, int32_t *d_counts, bool *handled) {
-    *handled = false;
+static vg_status ensure_qtc(Index *ix, const CodecParams &cp, cudaStream_t st) {
+    std::lock_guard<std::mutex> lk(ix->prep_mu);
+    if (!ix->qtc_dirty && ix->qtc.ready) return VG_OK;
     const vg_index_desc &d = ix->d;
-    if (!tc::enabled() || d.codec != VG_CODEC_F32 || d.num_partitions > 1 || !ix->has_vectors) return VG_OK;
-    if (!tc::supported(d.dim, d.rows, nq, k)) return VG_OK;
-    if ((reinterpret_cast<uintptr_t>(d_queries) & 15) != 0) return VG_OK;  // TMA needs 16-byte aligned bases
-    if ((reinterpret_cast<uintptr_t>(d_mask) & 3) != 0) return VG_OK;      // the filter reads the row bitmap as 32-bit words
-    cudaStream_t st = stream();
-    VG_TRY(ensure_row_norms(ix, st));
-    const int is_dot = d.metric != VG_METRIC_L2;
+    const bool pq = d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ;
+    const size_t np = pq ? (size_t)d.pq_m : (size_t)d.dim;
+    std::vector<float> h0(np), h1(np);
+    if (d.codec != VG_CODEC_RABITQ && d.codec != VG_CODEC_BQ) {  // the sign codes have no decode parameters
+        VG_CUDA(cudaMemcpyAsync(h0.data(), pq ? ix->pq_scales.p : ix->p0.p, np * 4, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaMemcpyAsync(h1.data(), pq ? ix->pq_offsets.p : ix->p1.p, np * 4, cudaMemcpyDeviceToHost, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+    }
+    VG_TRY(qtc::prepare(cp, d.rows, h0.data(), h1.data(), ix->qtc, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    ix->qtc_dirty = false;
+    return VG_OK;
+}
+
+// Everything one search call derives from its queries: codec view, scan arguments, prepared sign words (BQ / RaBitQ),
+// rotated queries (OPQ), probed partitions (IVF).  The buffers come from the stream-ordered pool: they are released in
+// stream order when the struct dies, after the kernels that read them.
+struct SearchTemps {
+    CodecParams cp;
+    ScanArgs a;
+    DevBuf qwords, qnorms, probe, rotated, tight;
+};
+// BQ / RaBitQ: sign words of the queries (+ norms in simd.Dot order) in rows of words32 (zero padded).
+static vg_status prep_sign(Index *ix, const float *d_queries, int64_t nq, DevBuf &qwords, DevBuf &qnorms, DevBuf &tight, cudaStream_t st) {
+    const vg_index_desc &d = ix->d;
+    VG_TRY(qwords.alloc((size_t)nq * ix->words32 * 4));
+    if (d.codec == VG_CODEC_RABITQ) VG_TRY(qnorms.alloc((size_t)nq * 4));
+    const float thr = d.codec == VG_CODEC_BQ ? d.bq_threshold : 0.0f;
+    // prep writes ceil(dim/64)*2 words per query
+    const int w_live = (int)(((d.dim + 63) / 64) * 2);
+    if (w_live == ix->words32) return prep_sign_queries(d_queries, nq, d.dim, thr, qwords.as<uint32_t>(), qnorms.as<float>(), st);
+    VG_CUDA(cudaMemsetAsync(qwords.p, 0, qwords.bytes, st));
+    VG_TRY(tight.alloc((size_t)nq * w_live * 4));
+    VG_TRY(prep_sign_queries(d_queries, nq, d.dim, thr, tight.as<uint32_t>(), qnorms.as<float>(), st));
+    VG_CUDA(cudaMemcpy2DAsync(qwords.p, (size_t)ix->words32 * 4, tight.p, (size_t)w_live * 4, (size_t)w_live * 4, (size_t)nq,
+                              cudaMemcpyDeviceToDevice, st));
+    return VG_OK;
+}
+static vg_status make_temps(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *d_mask, uint32_t *d_rows,
+                            float *d_scores, int32_t *d_counts, SearchTemps &t, cudaStream_t st) {
+    const vg_index_desc &d = ix->d;
+    t.cp = params_of(*ix);
+    ScanArgs &a = t.a;
+    a.queries = d_queries;
+    a.nq = nq;
+    a.rows = d.rows;
+    a.k = (int)k;
+    a.descending = d.metric != VG_METRIC_L2;
+    a.is_dot = d.metric != VG_METRIC_L2;
+    a.row_base = (uint32_t)d.row_base;
+    a.mask = d_mask;
+    a.out_rows = d_rows;
+    a.out_scores = d_scores;
+    a.out_counts = d_counts;
+    if (d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_BQ || d.codec == VG_CODEC_RABITQ) {
+        a.descending = 0;  // these scores are distances whatever the segment metric
+        a.is_dot = 0;
+    }
+    if (d.codec == VG_CODEC_BQ || d.codec == VG_CODEC_RABITQ) {
+        VG_TRY(prep_sign(ix, d_queries, nq, t.qwords, t.qnorms, t.tight, st));
+        t.cp.q_words = t.qwords.as<uint32_t>();
+        t.cp.q_norms = t.qnorms.as<float>();
+    }
+    if (d.codec == VG_CODEC_OPQ) {
+        VG_TRY(t.rotated.alloc((size_t)nq * d.dim * 4));
+        VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), t.rotated.as<float>(), st));  // opq.go:196-214
+        a.queries = t.rotated.as<float>();
+    }
+    if (d.num_partitions > 1) {
+        // kmeans.FindClosestCentroids per query (flat/segment.go:726-745)
+        int64_t np = nprobes <= 0 ? 1 : nprobes;
+        if (np > d.num_partitions) np = d.num_partitions;
+        VG_TRY(t.probe.alloc((size_t)nq * np * 4));
+        VG_TRY(dev_find_closest(a.queries, nq, d.dim, ix->centroids.as<float>(), d.num_partitions, np, d.metric, t.probe.as<int32_t>(), st));
+        a.probe = t.probe.as<int32_t>();
+        a.nprobe = (int)np;
+        a.part_off = ix->part_off.as<uint32_t>();
+        a.num_parts = (int)d.num_partitions;
+    }
+    return VG_OK;
+}
+
+static tc::SearchIO flat_io(Index *ix, const float *d_queries, int64_t nq, int64_t k, const uint8_t *d_mask, uint32_t *d_rows,
+                            float *d_scores, int32_t *d_counts) {
+    const vg_index_desc &d = ix->d;
     tc::SearchIO io;
     io.d_queries = d_queries;
     io.nq = nq;
@@ -592,166 +798,231 @@ static vg_status flat_tc_search(Index *ix, const float *d_queries, int64_t nq, i
     io.x16_exp = ix->x16_exp;
     io.d_mask = d_mask;
     io.k = (int)k;
-    io.is_dot = is_dot;
+    io.is_dot = d.metric != VG_METRIC_L2;
     io.row_base = (uint32_t)d.row_base;
     io.d_rows = d_rows;
     io.d_scores = d_scores;
     io.d_counts = d_counts;
-    std::vector<int32_t> bad;
-    VG_TRY(tc::search(io, tc::candidates_for(k, d.dim), bad, st));
-    if (!bad.empty()) {
-        // exact CUDA-core scan for the queries the certificate could not clear
-        CodecParams cp = params_of(*ix);
-        ScanArgs a;
-        a.queries = d_queries;
-        a.nq = nq;
-        a.rows = d.rows;
-        a.k = (int)k;
-        a.descending = is_dot;
-        a.is_dot = is_dot;
-        a.row_base = (uint32_t)d.row_base;
-        a.mask = d_mask;
-        a.out_rows = d_rows;
-        a.out_scores = d_scores;
-        a.out_counts = d_counts;
-        VG_TRY(scan_topk_subset(cp, a, bad, st));
-    }
-    *handled = true;
-    return VG_OK;
+    return io;
 }
-
-// Quantized scans (SQ8 / INT4 / PQ / OPQ / RaBitQ / BQ) through the tcgen05 decode-GEMM filter (vg_quant_tc.cu): candidates by fp16
-// GEMM over codes decoded inside the kernel, exact re-check in the reference's order, certificate; queries whose
-// certificate fails are re-run on the exact CUDA-core scan.  `d_queries` are already rotated for OPQ.
-static vg_status quant_tc_search(Index *ix, const CodecParams &cp, const ScanArgs &a, bool *handled) {
-    *handled = false;
-    const vg_index_desc &d = ix->d;
-    if (!ix->has_codes || !qtc::supported(cp, d.metric, d.rows, a.nq, a.k, d.num_partitions)) return VG_OK;
-    if ((reinterpret_cast<uintptr_t>(a.mask) & 3) != 0) return VG_OK;  // the filter reads the row bitmap as 32-bit words
-    if (a.q_stride != 0 && a.q_stride != d.dim) return VG_OK;
-    cudaStream_t st = stream();
-    std::unique_lock<std::mutex> prep_lock(ix->prep_mu);
-    if (ix->qtc_dirty || !ix->qtc.ready) {
-        const bool pq = d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ;
-        const size_t np = pq ? (size_t)d.pq_m : (size_t)d.dim;
-        std::vector<float> h0(np), h1(np);
-        if (d.codec != VG_CODEC_RABITQ && d.codec != VG_CODEC_BQ) {  // the sign codes have no decode parameters
-            VG_CUDA(cudaMemcpyAsync(h0.data(), pq ? ix->pq_scales.p : ix->p0.p, np * 4, cudaMemcpyDeviceToHost, st));
-            VG_CUDA(cudaMemcpyAsync(h1.data(), pq ? ix->pq_offsets.p : ix->p1.p, np * 4, cudaMemcpyDeviceToHost, st));
-            VG_CUDA(cudaStreamSynchronize(st));
-        }
-        VG_TRY(qtc::prepare(cp, d.rows, h0.data(), h1.data(), ix->qtc, st));
-        ix->qtc_dirty = false;
-    }
-    prep_lock.unlock();
+static qtc::SearchIO quant_io(Index *ix, const ScanArgs &a) {
     qtc::SearchIO io;
     io.d_queries = a.queries;
     io.q_stride = a.q_stride;
     io.nq = a.nq;
-    io.rows = d.rows;
+    io.rows = ix->d.rows;
     io.d_mask = a.mask;
     io.k = a.k;
     io.row_base = a.row_base;
     io.d_rows = a.out_rows;
     io.d_scores = a.out_scores;
     io.d_counts = a.out_counts;
-    std::vector<int32_t> bad;
-    VG_TRY(qtc::search(cp, ix->qtc, io, bad, st));
-    if (!bad.empty()) VG_TRY(scan_topk_subset(cp, a, bad, st));  // exact CUDA-core scan of the queries whose certificate failed
-    *handled = true;
-    return VG_OK;
+    return io;
 }
 
-static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
-                                 const uint8_t *d_mask, uint32_t *d_rows, float *d_scores, int32_t *d_counts) {
-    if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
-    if (nq == 0) return VG_OK;
+enum { SEARCH_EXACT = 0, SEARCH_FLAT_TC = 1, SEARCH_QUANT_TC = 2 };
+
+// Which path a (shape, pointer alignment) takes; same answer in enqueue and resolve.
+static int search_mode(Index *ix, const float *d_queries, int64_t nq, int64_t k, const uint8_t *d_mask, const CodecParams *cp_ready) {
+    const vg_index_desc &d = ix->d;
+    if (d.codec == VG_CODEC_F32) {
+        if (!tc::enabled() || d.num_partitions > 1 || !ix->has_vectors) return SEARCH_EXACT;
+        if (!tc::supported(d.dim, d.rows, nq, k)) return SEARCH_EXACT;
+        if ((reinterpret_cast<uintptr_t>(d_queries) & 15) != 0) return SEARCH_EXACT;  // TMA needs 16-byte aligned bases
+        if ((reinterpret_cast<uintptr_t>(d_mask) & 3) != 0) return SEARCH_EXACT;      // the filter reads the row bitmap as 32-bit words
+        return SEARCH_FLAT_TC;
+    }
+    if (!cp_ready || !ix->has_codes) return SEARCH_EXACT;
+    if (!qtc::supported(*cp_ready, d.metric, d.rows, nq, k, d.num_partitions)) return SEARCH_EXACT;
+    if ((reinterpret_cast<uintptr_t>(d_mask) & 3) != 0) return SEARCH_EXACT;
+    return SEARCH_QUANT_TC;
+}
+
+// Launches the whole search of one batch and returns without waiting for the device.  d_fail[q] = 1 marks a query whose
+// tensor-core filter result carries no proof yet (search_resolve re-runs those); the exact scan leaves all flags 0.
+static vg_status search_enqueue(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *d_mask,
+                                uint32_t *d_rows, float *d_scores, int32_t *d_counts, int32_t *d_fail, int *mode_out) {
     const vg_index_desc &d = ix->d;
     if (d.codec == VG_CODEC_F32 ? !ix->has_vectors : !ix->has_codes) {
         if (d.rows > 0) return fail(VG_ERR_STATE, "index rows were never uploaded");
     }
-    {
-        bool handled = false;
-        VG_TRY(flat_tc_search(ix, d_queries, nq, k, d_mask, d_rows, d_scores, d_counts, &handled));
-        if (handled) return VG_OK;
-    }
     cudaStream_t st = stream();
-    CodecParams cp = params_of(*ix);
-    ScanArgs a;
-    a.queries = d_queries;
-    a.nq = nq;
-    a.rows = d.rows;
-    a.k = (int)k;
-    a.descending = d.metric != VG_METRIC_L2;
-    a.is_dot = d.metric != VG_METRIC_L2;
-    a.row_base = (uint32_t)d.row_base;
-    a.mask = d_mask;
-    a.out_rows = d_rows;
-    a.out_scores = d_scores;
-    a.out_counts = d_counts;
-    DevBuf qwords, qnorms, probe, rotated;
-    if (d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_BQ || d.codec == VG_CODEC_RABITQ) {
-        a.descending = 0;  // these scores are distances whatever the segment metric
-        a.is_dot = 0;
+    t_stats.queries += (uint64_t)nq;
+    t_stats.distance_computations += (uint64_t)nq * (uint64_t)d.rows;
+    if (d.codec == VG_CODEC_F32) {
+        const int mode = search_mode(ix, d_queries, nq, k, d_mask, nullptr);
+        *mode_out = mode;
+        if (mode == SEARCH_FLAT_TC) {
+            VG_TRY(ensure_row_norms(ix, st));
+            t_stats.filter_queries += (uint64_t)nq;
+            return tc::enqueue(flat_io(ix, d_queries, nq, k, d_mask, d_rows, d_scores, d_counts), tc::candidates_for(k, d.dim), d_fail, st);
+        }
     }
-    if (d.codec == VG_CODEC_BQ || d.codec == VG_CODEC_RABITQ) {
-        VG_TRY(qwords.alloc((size_t)nq * ix->words32 * 4));
-        VG_CUDA(cudaMemsetAsync(qwords.p, 0, qwords.bytes, st));
-        if (d.codec == VG_CODEC_RABITQ) VG_TRY(qnorms.alloc((size_t)nq * 4));
-        // prep writes ceil(dim/64)*2 words per query into rows of words32 (zero padded)
-        const int w_live = (int)(((d.dim + 63) / 64) * 2);
-        if (w_live == ix->words32) {
-            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, d.codec == VG_CODEC_BQ ? d.bq_threshold : 0.0f, qwords.as<uint32_t>(),
-                                     qnorms.as<float>(), st));
-        } else {
-            DevBuf tight;
-            VG_TRY(tight.alloc((size_t)nq * w_live * 4));
-            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, d.codec == VG_CODEC_BQ ? d.bq_threshold : 0.0f, tight.as<uint32_t>(),
-                                     qnorms.as<float>(), st));
-            VG_CUDA(cudaMemcpy2DAsync(qwords.p, (size_t)ix->words32 * 4, tight.p, (size_t)w_live * 4, (size_t)w_live * 4, (size_t)nq,
-                                      cudaMemcpyDeviceToDevice, st));
+    SearchTemps t;
+    VG_TRY(make_temps(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, t, st));
+    const int mode = d.codec == VG_CODEC_F32 ? SEARCH_EXACT : search_mode(ix, d_queries, nq, k, d_mask, &t.cp);
+    *mode_out = mode;
+    if (mode == SEARCH_QUANT_TC) {
+        VG_TRY(ensure_qtc(ix, t.cp, st));
+        t_stats.filter_queries += (uint64_t)nq;
+        return qtc::enqueue(t.cp, ix->qtc, quant_io(ix, t.a), 1, d_fail, st);
+    }
+    if (d_fail) VG_CUDA(cudaMemsetAsync(d_fail, 0, (size_t)nq * 4, st));
+    return scan_topk(t.cp, t.a, st);
+}
+
+// Second half: `bad` = the queries whose flag was set (read back by the caller at a point where it synchronises anyway).
+// They get the filter's second chance (twice the candidate groups) and, failing that too, the exact CUDA-core scan.
+static vg_status search_resolve(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *d_mask,
+                                uint32_t *d_rows, float *d_scores, int32_t *d_counts, std::vector<int32_t> &bad, int mode) {
+    if (bad.empty() || mode == SEARCH_EXACT) return VG_OK;
+    const vg_index_desc &d = ix->d;
+    cudaStream_t st = stream();
+    SearchTemps t;
+    if (mode == SEARCH_FLAT_TC) {
+        t_stats.second_chance_queries += (uint64_t)bad.size();
+        VG_TRY(tc::retry(flat_io(ix, d_queries, nq, k, d_mask, d_rows, d_scores, d_counts), tc::candidates_for(k, d.dim), bad, st));
+        if (bad.empty()) return VG_OK;
+        VG_TRY(make_temps(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, t, st));
+    } else {
+        VG_TRY(make_temps(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, t, st));
+        if (qtc::second_chance_possible(t.cp, d.rows, k)) {
+            // gather the failed queries (and their prepared sign words / norms), filter them again with 2x the groups
+            const int64_t nb = (int64_t)bad.size();
+            t_stats.second_chance_queries += (uint64_t)nb;
+            DevBuf bidx, bq, bqw, bqn, brow, bsc, bcnt, bfail;
+            VG_TRY(bidx.alloc((size_t)nb * 4));
+            VG_TRY(bq.alloc((size_t)nb * d.dim * 4));
+            VG_TRY(brow.alloc((size_t)nb * k * 4));
+            VG_TRY(bsc.alloc((size_t)nb * k * 4));
+            VG_TRY(bcnt.alloc((size_t)nb * 4));
+            VG_TRY(bfail.alloc((size_t)nb * 4));
+            VG_CUDA(cudaMemcpyAsync(bidx.p, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
+            VG_TRY(dev_gather_rows(t.a.queries, d.dim, bidx.as<int32_t>(), nb, d.dim, bq.as<float>(), st));
+            CodecParams cps = t.cp;
+            if (t.cp.q_words) {
+                VG_TRY(bqw.alloc((size_t)nb * t.cp.words32 * 4));
+                VG_TRY(dev_gather_rows(reinterpret_cast<const float *>(t.cp.q_words), t.cp.words32, bidx.as<int32_t>(), nb, t.cp.words32,
+                                       bqw.as<float>(), st));
+                cps.q_words = bqw.as<uint32_t>();
+            }
+            if (t.cp.q_norms) {
+                VG_TRY(bqn.alloc((size_t)nb * 4));
+                VG_TRY(dev_gather_rows(t.cp.q_norms, 1, bidx.as<int32_t>(), nb, 1, bqn.as<float>(), st));
+                cps.q_norms = bqn.as<float>();
+            }
+            qtc::SearchIO io = quant_io(ix, t.a);
+            io.d_queries = bq.as<float>();
+            io.q_stride = 0;
+            io.nq = nb;
+            io.d_rows = brow.as<uint32_t>();
+            io.d_scores = bsc.as<float>();
+            io.d_counts = bcnt.as<int32_t>();
+            VG_TRY(qtc::enqueue(cps, ix->qtc, io, 2, bfail.as<int32_t>(), st));
+            VG_TRY(dev_scatter_results(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(), bidx.as<int32_t>(), nb, k, d_rows, d_scores,
+                                       d_counts, st));
+            std::vector<int32_t> h_fail((size_t)nb);
+            VG_CUDA(cudaMemcpyAsync(h_fail.data(), bfail.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
             VG_CUDA(cudaStreamSynchronize(st));
+            std::vector<int32_t> still;
+            for (int64_t j = 0; j < nb; j++)
+                if (h_fail[(size_t)j]) still.push_back(bad[(size_t)j]);
+            bad.swap(still);
         }
-        cp.q_words = qwords.as<uint32_t>();
-        cp.q_norms = qnorms.as<float>();
+        qtc::count_fallbacks((uint64_t)bad.size());
+        if (bad.empty()) return VG_OK;
     }
-    if (d.codec == VG_CODEC_OPQ) {
-        VG_TRY(rotated.alloc((size_t)nq * d.dim * 4));
-        VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), rotated.as<float>(), st));  // opq.go:196-214
-        a.queries = rotated.as<float>();
-    }
-    if (d.codec == VG_CODEC_SQ8 || d.codec == VG_CODEC_INT4 || d.codec == VG_CODEC_PQ || d.codec == VG_CODEC_OPQ ||
-        d.codec == VG_CODEC_RABITQ || d.codec == VG_CODEC_BQ) {
-        bool handled = false;
-        VG_TRY(quant_tc_search(ix, cp, a, &handled));
-        if (handled) {
-            VG_CUDA(cudaStreamSynchronize(st));  // `rotated` is freed on return
-            return VG_OK;
-        }
-    }
-    if (d.num_partitions > 1) {
-        // kmeans.FindClosestCentroids per query (flat/segment.go:726-745)
-        int64_t np = nprobes <= 0 ? 1 : nprobes;
-        if (np > d.num_partitions) np = d.num_partitions;
-        VG_TRY(probe.alloc((size_t)nq * np * 4));
-        VG_TRY(dev_find_closest(a.queries, nq, d.dim, ix->centroids.as<float>(), d.num_partitions, np, d.metric,
-                                probe.as<int32_t>(), st));
-        a.probe = probe.as<int32_t>();
-        a.nprobe = (int)np;
-        a.part_off = ix->part_off.as<uint32_t>();
-        a.num_parts = (int)d.num_partitions;
-    }
-    VG_TRY(scan_topk(cp, a, st));
-    VG_CUDA(cudaStreamSynchronize(st));  // temporaries above are freed on return
+    // exact CUDA-core scan for the queries no certificate could clear
+    t_stats.exact_rerun_queries += (uint64_t)bad.size();
+    t_stats.distance_computations += (uint64_t)bad.size() * (uint64_t)d.rows;
+    return scan_topk_subset(t.cp, t.a, bad, st);
+}
+
+static vg_status read_flags(const int32_t *d_fail, int64_t nq, std::vector<int32_t> &bad, cudaStream_t st) {
+    std::vector<int32_t> h((size_t)nq);
+    VG_CUDA(cudaMemcpyAsync(h.data(), d_fail, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    bad.clear();
+    for (int64_t q = 0; q < nq; q++)
+        if (h[(size_t)q]) bad.push_back((int32_t)q);
     return VG_OK;
+}
+
+// Host-synchronous search of device-resident queries: enqueue, read the flags, resolve.
+static vg_status search_dev_impl(Index *ix, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                                 const uint8_t *d_mask, uint32_t *d_rows, float *d_scores, int32_t *d_counts) {
+    if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
+    if (nq == 0) return VG_OK;
+    DevBuf failb;
+    VG_TRY(failb.alloc((size_t)nq * 4));
+    int mode = SEARCH_EXACT;
+    VG_TRY(search_enqueue(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, failb.as<int32_t>(), &mode));
+    if (mode == SEARCH_EXACT) return VG_OK;  // stream-ordered: nothing to resolve
+    std::vector<int32_t> bad;
+    VG_TRY(read_flags(failb.as<int32_t>(), nq, bad, stream()));
+    return search_resolve(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, bad, mode);
 }
 
 vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
                               const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
-    return search_dev_impl(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts);
+    VG_ENTER_IX(ix);
+    t_stats = vg_search_stats{};
+    VG_TRY(search_dev_impl(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts));
+    return _vg_call.finish();
+}
+
+vg_status vg_index_search_dev_async(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                                    const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts,
+                                    int32_t *d_unproven) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
+    if (_vg_call.leased()) return fail(VG_ERR_STATE, "asynchronous search needs a caller stream (vg_set_stream / vg_index_set_stream)");
+    if (nq < 0 || k <= 0 || !d_unproven) return fail(VG_ERR_INVALID, "nq must be >= 0, k > 0 and d_unproven non-null");
+    if (nq == 0) return VG_OK;
+    t_stats = vg_search_stats{};
+    int mode = SEARCH_EXACT;
+    return search_enqueue(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts, d_unproven, &mode);
+}
+
+vg_status vg_index_search_resolve(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
+                                  const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts,
+                                  const int32_t *d_unproven, int64_t *n_resolved) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
+    if (n_resolved) *n_resolved = 0;
+    if (nq <= 0) return VG_OK;
+    if (k <= 0 || !d_unproven) return fail(VG_ERR_INVALID, "k must be > 0 and d_unproven non-null");
+    t_stats = vg_search_stats{};
+    std::vector<int32_t> bad;
+    VG_TRY(read_flags(d_unproven, nq, bad, stream()));
+    if (n_resolved) *n_resolved = (int64_t)bad.size();
+    if (bad.empty()) return VG_OK;
+    // the mode is a function of the shape and the pointers: recompute what enqueue chose
+    int mode = SEARCH_EXACT;
+    if (ix->d.codec == VG_CODEC_F32) {
+        mode = search_mode(ix, d_queries, nq, k, d_row_mask, nullptr);
+    } else {
+        CodecParams cp = params_of(*ix);
+        static const uint32_t dummy_words = 0;
+        static const float dummy_norm = 0.0f;
+        if (ix->d.codec == VG_CODEC_BQ || ix->d.codec == VG_CODEC_RABITQ) {  // supported() only checks that the query state exists
+            cp.q_words = &dummy_words;
+            cp.q_norms = &dummy_norm;
+        }
+        mode = search_mode(ix, d_queries, nq, k, d_row_mask, &cp);
+    }
+    VG_TRY(search_resolve(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts, bad, mode));
+    return _vg_call.finish();
+}
+
+vg_status vg_last_search_stats(vg_search_stats *out) {
+    if (!out) return fail(VG_ERR_INVALID, "null argument");
+    *out = t_stats;
+    return VG_OK;
 }
 
 vg_status vg_quant_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
@@ -779,9 +1050,9 @@ vg_status vg_flat_tc_stats(uint64_t *queries, uint64_t *fallbacks) {
 }
 vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t nq, int64_t kc, uint32_t *h_groups, int32_t *h_counts,
                                 float *h_tau, int64_t *group_rows) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (ix->d.codec != VG_CODEC_F32 || !ix->has_vectors) return fail(VG_ERR_STATE, "not a float32 index");
     if (kc < 1 || kc > 64) return fail(VG_ERR_INVALID, "kc must be in 1..64");
     if (!tc::supported(ix->d.dim, ix->d.rows, nq, 1)) return fail(VG_ERR_UNSUPPORTED, "shape not supported by the tensor-core filter");
@@ -814,41 +1085,75 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
     return VG_OK;
 }
 
+// Device -> host without a host wait when the destination is page-locked (or small: the driver stages it itself);
+// everything else goes through the pinned ring, which synchronises.
+static vg_status d2h_enqueue(void *h_dst, const void *d_src, size_t bytes) {
+    if (bytes == 0) return VG_OK;
+    if (bytes < kSmallCopy || host_pinned(h_dst)) {
+        VG_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, stream()));
+        return VG_OK;
+    }
+    return staged_d2h(h_dst, d_src, bytes);
+}
+
 vg_status vg_index_search(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes,
                           const uint8_t *h_row_mask, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
     if (nq == 0) return VG_OK;
-    DevBuf q, mask, rows, scores, counts;
+    t_stats = vg_search_stats{};
+    cudaStream_t st = stream();
+    DevBuf q, mask, rows, scores, counts, failb;
     VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
     if (h_row_mask) VG_TRY(to_device(mask, h_row_mask, (size_t)((ix->d.rows + 7) / 8)));
     VG_TRY(rows.alloc((size_t)nq * k * 4));
     VG_TRY(scores.alloc((size_t)nq * k * 4));
     VG_TRY(counts.alloc((size_t)nq * 4));
-    VG_TRY(search_dev_impl(ix, q.as<float>(), nq, k, nprobes, h_row_mask ? mask.as<uint8_t>() : nullptr, rows.as<uint32_t>(),
-                           scores.as<float>(), counts.as<int32_t>()));
-    VG_TRY(staged_d2h(h_out_rows, rows.p, (size_t)nq * k * 4));
-    VG_TRY(staged_d2h(h_out_scores, scores.p, (size_t)nq * k * 4));
-    VG_TRY(staged_d2h(h_out_counts, counts.p, (size_t)nq * 4));
+    VG_TRY(failb.alloc((size_t)nq * 4));
+    const uint8_t *d_mask = h_row_mask ? mask.as<uint8_t>() : nullptr;
+    int mode = SEARCH_EXACT;
+    VG_TRY(search_enqueue(ix, q.as<float>(), nq, k, nprobes, d_mask, rows.as<uint32_t>(), scores.as<float>(), counts.as<int32_t>(),
+                          failb.as<int32_t>(), &mode));
+    // results and certificate flags come back behind ONE synchronisation; the (rare) unproven queries are then
+    // resolved and the results copied again
+    std::vector<int32_t> h_fail;
+    if (mode != SEARCH_EXACT) {
+        h_fail.resize((size_t)nq);
+        VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    }
+    for (int pass = 0; pass < 2; pass++) {
+        VG_TRY(d2h_enqueue(h_out_rows, rows.p, (size_t)nq * k * 4));
+        VG_TRY(d2h_enqueue(h_out_scores, scores.p, (size_t)nq * k * 4));
+        VG_TRY(d2h_enqueue(h_out_counts, counts.p, (size_t)nq * 4));
+        VG_CUDA(cudaStreamSynchronize(st));
+        if (pass == 1 || mode == SEARCH_EXACT) break;
+        std::vector<int32_t> bad;
+        for (int64_t i = 0; i < nq; i++)
+            if (h_fail[(size_t)i]) bad.push_back((int32_t)i);
+        if (bad.empty()) break;
+        VG_TRY(search_resolve(ix, q.as<float>(), nq, k, nprobes, d_mask, rows.as<uint32_t>(), scores.as<float>(), counts.as<int32_t>(), bad,
+                              mode));
+    }
     return VG_OK;
 }
 
 vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r,
                               float *d_scores) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
-    return rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2,
-                         d_scores, stream());
+    VG_TRY(rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2,
+                         d_scores, stream()));
+    return _vg_call.finish();  // stream-ordered on a caller stream; complete on return when the library chose the stream
 }
 
 vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (nq <= 0 || r <= 0) return VG_OK;
     DevBuf q, rows, scores;
     VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
@@ -862,33 +1167,19 @@ vg_status vg_index_rerank(vg_index_t idx, const float *h_queries, int64_t nq, co
 // Quantized gather scoring (DiskANN neighbour-list scoring, diskann/segment.go:511-588): the codec's own distance of every
 // query to its r candidate rows, in the reference's arithmetic.  A float32 index scores exactly (Segment.Rerank).
 vg_status vg_index_score_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, float *d_scores) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (nq <= 0 || r <= 0) return VG_OK;
     const vg_index_desc &d = ix->d;
     if (d.codec == VG_CODEC_F32) return vg_index_rerank_dev(idx, d_queries, nq, d_rows, r, d_scores);
-    if (d.codec == VG_CODEC_BQ) return fail(VG_ERR_UNSUPPORTED, "gather scoring covers SQ8, INT4, PQ, OPQ and RaBitQ");
     if (!ix->has_codes) return fail(VG_ERR_STATE, "index rows were never uploaded");
     cudaStream_t st = stream();
     CodecParams cp = params_of(*ix);
-    DevBuf qwords, qnorms, rotated;
+    DevBuf qwords, qnorms, rotated, tight;
     const float *queries = d_queries;
-    if (d.codec == VG_CODEC_RABITQ) {
-        VG_TRY(qwords.alloc((size_t)nq * ix->words32 * 4));
-        VG_CUDA(cudaMemsetAsync(qwords.p, 0, qwords.bytes, st));
-        VG_TRY(qnorms.alloc((size_t)nq * 4));
-        const int w_live = (int)(((d.dim + 63) / 64) * 2);
-        if (w_live == ix->words32) {
-            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, 0.0f, qwords.as<uint32_t>(), qnorms.as<float>(), st));
-        } else {
-            DevBuf tight;
-            VG_TRY(tight.alloc((size_t)nq * w_live * 4));
-            VG_TRY(prep_sign_queries(d_queries, nq, d.dim, 0.0f, tight.as<uint32_t>(), qnorms.as<float>(), st));
-            VG_CUDA(cudaMemcpy2DAsync(qwords.p, (size_t)ix->words32 * 4, tight.p, (size_t)w_live * 4, (size_t)w_live * 4, (size_t)nq,
-                                      cudaMemcpyDeviceToDevice, st));
-            VG_CUDA(cudaStreamSynchronize(st));
-        }
+    if (d.codec == VG_CODEC_RABITQ || d.codec == VG_CODEC_BQ) {
+        VG_TRY(prep_sign(ix, d_queries, nq, qwords, qnorms, tight, st));
         cp.q_words = qwords.as<uint32_t>();
         cp.q_norms = qnorms.as<float>();
     }
@@ -897,15 +1188,93 @@ vg_status vg_index_score_dev(vg_index_t idx, const float *d_queries, int64_t nq,
         VG_TRY(dev_opq_rotate(d_queries, nq, d.dim, (int)d.opq_block, ix->rotation.as<float>(), rotated.as<float>(), st));
         queries = rotated.as<float>();
     }
-    VG_TRY(qtc::score_rows(cp, d.rows, queries, 0, nq, d_rows, r, d_scores, st));
-    VG_CUDA(cudaStreamSynchronize(st));  // the temporaries above are released on return
+    VG_TRY(qtc::score_rows(cp, d.rows, queries, 0, nq, d_rows, r, d_scores, ix->int4_direct ? 0 : 1, st));
+    return _vg_call.finish();  // the temporaries above are released in stream order
+}
+
+__global__ void iota_kernel(uint32_t *p, int64_t n);
+// simd.SquaredL2Bounded per (query, candidate) pair against the index's float32 rows (the HNSW / DiskANN traversal's
+// early-exit distance, distance/distance.go:24-31).
+vg_status vg_index_l2_bounded_dev(vg_index_t idx, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r,
+                                  const float *d_bounds, int32_t per_pair_bounds, float *d_scores, uint8_t *d_exceeded) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
+    if (nq <= 0 || r <= 0) return VG_OK;
+    if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors");
+    VG_TRY(bounded_l2_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, d_bounds, per_pair_bounds, d_scores,
+                             d_exceeded, stream()));
+    return _vg_call.finish();
+}
+vg_status vg_index_l2_bounded(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, const float *h_bounds,
+                              int32_t per_pair_bounds, float *h_scores, uint8_t *h_exceeded) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
+    if (nq <= 0 || r <= 0) return VG_OK;
+    DevBuf q, rows, bounds, scores, ex;
+    VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
+    VG_TRY(to_device(rows, h_rows, (size_t)nq * r));
+    VG_TRY(to_device(bounds, h_bounds, (size_t)(per_pair_bounds ? nq * r : nq)));
+    VG_TRY(scores.alloc((size_t)nq * r * 4));
+    VG_TRY(ex.alloc((size_t)nq * r));
+    VG_TRY(vg_index_l2_bounded_dev(idx, q.as<float>(), nq, rows.as<uint32_t>(), r, bounds.as<float>(), per_pair_bounds, scores.as<float>(),
+                                   ex.as<uint8_t>()));
+    VG_TRY(staged_d2h(h_scores, scores.p, (size_t)nq * r * 4));
+    return staged_d2h(h_exceeded, ex.p, (size_t)nq * r);
+}
+// simd.SquaredL2Bounded mirror for explicit pairs (a[i], b[i]).
+vg_status vg_simd_squared_l2_bounded(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, const float *h_bounds, float *h_out,
+                                     uint8_t *h_exceeded) {
+    VG_ENTER();
+    if (n_pairs <= 0) return VG_OK;
+    if (dim <= 0) {
+        for (int64_t i = 0; i < n_pairs; i++) {
+            h_out[i] = 0.0f;
+            h_exceeded[i] = 0.0f > h_bounds[i] ? 1 : 0;
+        }
+        return VG_OK;
+    }
+    DevBuf a, b, rows, bounds, out, ex;
+    VG_TRY(to_device(a, h_a, (size_t)n_pairs * dim));
+    VG_TRY(to_device(b, h_b, (size_t)n_pairs * dim));
+    VG_TRY(to_device(bounds, h_bounds, (size_t)n_pairs));
+    VG_TRY(rows.alloc((size_t)n_pairs * 4));
+    VG_TRY(out.alloc((size_t)n_pairs * 4));
+    VG_TRY(ex.alloc((size_t)n_pairs));
+    iota_kernel<<<(unsigned)((n_pairs + 255) / 256), 256, 0, stream()>>>(rows.as<uint32_t>(), n_pairs);
+    VG_LAUNCHED();
+    VG_TRY(bounded_l2_gather(b.as<float>(), n_pairs, dim, a.as<float>(), n_pairs, rows.as<uint32_t>(), 1, bounds.as<float>(), 0, out.as<float>(),
+                             ex.as<uint8_t>(), stream()));
+    VG_TRY(staged_d2h(h_out, out.p, (size_t)n_pairs * 4));
+    return staged_d2h(h_exceeded, ex.p, (size_t)n_pairs);
+}
+// simd.BuildInt4LookupTable (kernels.go:94-103): table[d*16 + q] = (float32(q) / 15) * diff[d] + min[d], each operation
+// rounded to float32 on its own (Go never fuses) — parameter algebra, like vg_sq8_set_bounds.
+vg_status vg_int4_build_lookup_table(const float *h_min, const float *h_diff, int64_t dim, float *h_table) {
+    if (dim <= 0 || !h_min || !h_diff || !h_table) return fail(VG_ERR_INVALID, "dimension mismatch");
+    for (int64_t d = 0; d < dim; d++)
+        for (int q = 0; q < 16; q++) {
+            volatile float n = (float)q / 15.0f;
+            volatile float v = n * h_diff[d];
+            volatile float t = v + h_min[d];
+            h_table[d * 16 + q] = t;
+        }
+    return VG_OK;
+}
+
+vg_status vg_index_set_int4_score_mode(vg_index_t idx, int32_t mode) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (mode != VG_INT4_SCORE_LUT && mode != VG_INT4_SCORE_DIRECT) return fail(VG_ERR_INVALID, "unknown INT4 score mode");
+    ix->int4_direct = mode == VG_INT4_SCORE_DIRECT;
     return VG_OK;
 }
 
 vg_status vg_index_score(vg_index_t idx, const float *h_queries, int64_t nq, const uint32_t *h_rows, int64_t r, float *h_scores) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (nq <= 0 || r <= 0) return VG_OK;
     DevBuf q, rows, scores;
     VG_TRY(to_device(q, h_queries, (size_t)nq * ix->d.dim));
@@ -933,9 +1302,9 @@ __global__ void __launch_bounds__(256) local_rows_kernel(const uint32_t *rows, i
 
 vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t nq, int64_t r, int64_t k, uint32_t *h_out_rows,
                                  float *h_out_scores, int32_t *h_out_counts) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (nq <= 0) return VG_OK;
     if (r < k) r = k;
     if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
@@ -974,14 +1343,15 @@ vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t
 // --------------------------------------------------------------- top-k merge
 vg_status vg_topk_merge_dev(const uint32_t *d_rows, const float *d_scores, int64_t lists, int64_t nq, int64_t k_in,
                             int32_t descending, int64_t k_out, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(VG_ERR_INVALID, "bad merge shape");
-    return launch_merge_pairs(d_rows, d_scores, lists, nq, k_in, descending != 0, k_out, d_out_rows, d_out_scores, d_out_counts,
-                              stream());
+    VG_TRY(launch_merge_pairs(d_rows, d_scores, lists, nq, k_in, descending != 0, k_out, d_out_rows, d_out_scores, d_out_counts,
+                              stream()));
+    return _vg_call.finish();
 }
 vg_status vg_topk_merge(const uint32_t *h_rows, const float *h_scores, int64_t lists, int64_t nq, int64_t k_in,
                         int32_t descending, int64_t k_out, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(VG_ERR_INVALID, "bad merge shape");
     if (nq == 0) return VG_OK;
     DevBuf r, s, orow, osc, ocnt;
@@ -1009,7 +1379,7 @@ static vg_status dense_host(CodecParams cp, const float *h_q, int64_t nq, int64_
 
 static vg_status f32_dense(const float *h_q, int64_t nq, const float *h_t, int64_t n, int64_t dim, int is_dot, int variant,
                            float *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (dim < 0 || nq < 0 || n < 0) return fail(VG_ERR_INVALID, "negative size");
     if (nq == 0 || n == 0) return VG_OK;
     if (dim == 0) {
@@ -1038,7 +1408,7 @@ __global__ void iota_kernel(uint32_t *p, int64_t n) {
     if (i < n) p[i] = (uint32_t)i;
 }
 static vg_status pair_host(const float *h_a, const float *h_b, int64_t n_pairs, int64_t dim, int is_dot, float *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n_pairs <= 0) return VG_OK;
     if (dim <= 0) {
         memset(h_out, 0, (size_t)n_pairs * 4);
@@ -1065,7 +1435,7 @@ vg_status vg_simd_squared_l2(const float *h_a, const float *h_b, int64_t n_pairs
 
 vg_status vg_simd_sq8u_l2_batch(const float *h_q, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_mins,
                                 const float *h_inv, float *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (nq <= 0 || n <= 0) return VG_OK;
     if (dim <= 0) {
         memset(h_out, 0, (size_t)nq * n * 4);
@@ -1086,7 +1456,7 @@ vg_status vg_simd_sq8u_l2_batch(const float *h_q, int64_t nq, const uint8_t *h_c
 }
 vg_status vg_simd_int4_l2_batch(const float *h_q, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_min,
                                 const float *h_diff, float *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (nq <= 0 || n <= 0) return VG_OK;
     if (dim <= 0) {
         memset(h_out, 0, (size_t)nq * n * 4);
@@ -1107,7 +1477,7 @@ vg_status vg_simd_int4_l2_batch(const float *h_q, int64_t nq, const uint8_t *h_c
     return dense_host(cp, h_q, nq, dim, n, 0, h_out);
 }
 vg_status vg_simd_pq_adc_lookup(const float *h_tables, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t m, float *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (nq <= 0 || n <= 0) return VG_OK;
     if (m <= 0) {
         memset(h_out, 0, (size_t)nq * n * 4);
@@ -1127,7 +1497,7 @@ vg_status vg_simd_pq_adc_lookup(const float *h_tables, int64_t nq, const uint8_t
     return dense_host(cp, nullptr, nq, 0, n, 0, h_out);
 }
 vg_status vg_simd_hamming(const uint8_t *h_q, int64_t nq, const uint8_t *h_codes, int64_t n, int64_t nbytes, int32_t *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (nq <= 0 || n <= 0) return VG_OK;
     if (nbytes <= 0) {
         memset(h_out, 0, (size_t)nq * n * 4);
@@ -1142,7 +1512,7 @@ vg_status vg_simd_hamming(const uint8_t *h_q, int64_t nq, const uint8_t *h_codes
     return staged_d2h(h_out, out.p, (size_t)nq * n * 4);
 }
 vg_status vg_simd_scale(float *h_a, int64_t n, float scalar) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     DevBuf a;
     VG_TRY(to_device(a, h_a, (size_t)n));
@@ -1151,7 +1521,7 @@ vg_status vg_simd_scale(float *h_a, int64_t n, float scalar) {
     return staged_d2h(h_a, a.p, (size_t)n * 4);
 }
 vg_status vg_normalize_l2(float *h_vecs, int64_t n, int64_t dim, uint8_t *h_ok) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     if (dim <= 0) {
         if (h_ok) memset(h_ok, 0, (size_t)n);
@@ -1185,7 +1555,7 @@ vg_status vg_sq8_set_bounds(const float *h_mins, const float *h_maxs, int64_t di
     return VG_OK;
 }
 vg_status vg_sq8_train(const float *h_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs, float *h_scales, float *h_inv) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     if (dim <= 0) return fail(VG_ERR_INVALID, "vector dimension mismatch");
     DevBuf v, mm;
@@ -1208,7 +1578,7 @@ vg_status vg_sq8_train(const float *h_vecs, int64_t n, int64_t dim, float *h_min
 }
 vg_status vg_sq8_encode(const float *h_vecs, int64_t n, int64_t dim, const float *h_mins, const float *h_maxs, const float *h_scales,
                         uint8_t *h_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (!h_mins || !h_maxs || !h_scales) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
     if (n <= 0) return VG_OK;
     DevBuf v, mn, mx, sc, out;
@@ -1222,7 +1592,7 @@ vg_status vg_sq8_encode(const float *h_vecs, int64_t n, int64_t dim, const float
     return staged_d2h(h_codes, out.p, (size_t)n * dim);
 }
 vg_status vg_sq8_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_mins, const float *h_inv, float *h_vecs) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (!h_mins || !h_inv) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
     if (n <= 0) return VG_OK;
     DevBuf c, mn, iv, out;
@@ -1235,7 +1605,7 @@ vg_status vg_sq8_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const fl
     return staged_d2h(h_vecs, out.p, (size_t)n * dim * 4);
 }
 vg_status vg_int4_train(const float *h_vecs, int64_t n, int64_t dim, float *h_min, float *h_diff) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     DevBuf v, mm;
     VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
@@ -1251,7 +1621,7 @@ vg_status vg_int4_train(const float *h_vecs, int64_t n, int64_t dim, float *h_mi
     return VG_OK;
 }
 vg_status vg_int4_encode(const float *h_vecs, int64_t n, int64_t dim, const float *h_min, const float *h_diff, uint8_t *h_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     const int64_t cs = (dim + 1) / 2;
     DevBuf v, mn, df, out;
@@ -1264,7 +1634,7 @@ vg_status vg_int4_encode(const float *h_vecs, int64_t n, int64_t dim, const floa
     return staged_d2h(h_codes, out.p, (size_t)n * cs);
 }
 vg_status vg_int4_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const float *h_min, const float *h_diff, float *h_vecs) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     const int64_t cs = (dim + 1) / 2;
     DevBuf c, mn, df, out;
@@ -1277,7 +1647,7 @@ vg_status vg_int4_decode(const uint8_t *h_codes, int64_t n, int64_t dim, const f
     return staged_d2h(h_vecs, out.p, (size_t)n * dim * 4);
 }
 vg_status vg_bq_train(const float *h_vecs, int64_t n, int64_t dim, float *h_threshold) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     DevBuf v;
     VG_TRY(to_device(v, h_vecs, (size_t)n * dim));
@@ -1287,7 +1657,7 @@ vg_status vg_bq_train(const float *h_vecs, int64_t n, int64_t dim, float *h_thre
     return VG_OK;
 }
 static vg_status sign_encode_host(const float *h_vecs, int64_t n, int64_t dim, float thr, bool with_norm, uint8_t *h_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     const int64_t stride = ((dim + 63) / 64) * 8 + (with_norm ? 4 : 0);
     DevBuf v, out;
@@ -1317,7 +1687,7 @@ static vg_status pq_params(PqDev &p, int64_t dim, int64_t m, int64_t k, const in
 }
 vg_status vg_pq_encode(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc,
                        const float *h_of, uint8_t *h_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     PqDev p;
     VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
     if (n <= 0) return VG_OK;
@@ -1331,7 +1701,7 @@ vg_status vg_pq_encode(const float *h_vecs, int64_t n, int64_t dim, int64_t m, i
 }
 vg_status vg_pq_decode(const uint8_t *h_codes, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc,
                        const float *h_of, float *h_vecs) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     PqDev p;
     VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
     if (n <= 0) return VG_OK;
@@ -1345,7 +1715,7 @@ vg_status vg_pq_decode(const uint8_t *h_codes, int64_t n, int64_t dim, int64_t m
 }
 vg_status vg_pq_build_distance_table(const float *h_q, int64_t nq, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb,
                                      const float *h_sc, const float *h_of, float *h_tables) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     PqDev p;
     VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
     if (nq <= 0) return VG_OK;
@@ -1360,7 +1730,7 @@ vg_status vg_pq_build_distance_table(const float *h_q, int64_t nq, int64_t dim, 
 
 // device-resident variants
 vg_status vg_minmax_dev(const float *d_vecs, int64_t n, int64_t dim, float *h_mins, float *h_maxs) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0 || dim <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     DevBuf mm;
     VG_TRY(mm.alloc((size_t)dim * 8));
@@ -1370,7 +1740,7 @@ vg_status vg_minmax_dev(const float *d_vecs, int64_t n, int64_t dim, float *h_mi
 }
 vg_status vg_sq8_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const float *h_mins, const float *h_maxs,
                             const float *h_scales, uint8_t *d_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (!h_mins || !h_maxs || !h_scales) return fail(VG_ERR_STATE, "ScalarQuantizer not trained");
     if (n <= 0) return VG_OK;
     DevBuf mn, mx, sc;
@@ -1382,7 +1752,7 @@ vg_status vg_sq8_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const f
     return VG_OK;
 }
 vg_status vg_int4_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const float *h_min, const float *h_diff, uint8_t *d_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     DevBuf mn, df;
     VG_TRY(to_device(mn, h_min, (size_t)dim));
@@ -1392,7 +1762,7 @@ vg_status vg_int4_encode_dev(const float *d_vecs, int64_t n, int64_t dim, const 
     return VG_OK;
 }
 vg_status vg_rabitq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, uint8_t *d_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     VG_TRY(dev_sign_encode(d_vecs, n, dim, 0.0f, true, d_codes, stream()));
     VG_CUDA(cudaStreamSynchronize(stream()));
@@ -1400,7 +1770,7 @@ vg_status vg_rabitq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, uint
 }
 vg_status vg_pq_encode_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, const int8_t *h_cb, const float *h_sc,
                            const float *h_of, uint8_t *d_codes) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     PqDev p;
     VG_TRY(pq_params(p, dim, m, k, h_cb, h_sc, h_of));
     if (n <= 0) return VG_OK;
@@ -1504,14 +1874,37 @@ static vg_status device_crc32c(const uint8_t *d_data, size_t n, uint32_t *crc_ou
     return VG_OK;
 }
 
-vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg_index_t *out) {
-    VG_TRY(ensure_init());
+// A section [off, off + size) lies inside a file of `len` bytes — written so that neither side can wrap: a crafted
+// header with an offset near 2^64 must fail here, not read out of bounds (the Go reference slices with bounds checks).
+static bool section_ok(uint64_t len, uint64_t off, uint64_t size) { return off <= len && size <= len - off; }
+static bool mul_ok(uint64_t a, uint64_t b, uint64_t *out) {
+    if (a != 0 && b > UINT64_MAX / a) return false;
+    *out = a * b;
+    return true;
+}
+
+vg_status vg_flat_open_on(int32_t device, const uint8_t *f, size_t len, int32_t verify_checksum, vg_index_t *out) {
+    VG_ENTER(device);
     vg_flat_header h;
     VG_TRY(vg_flat_decode_header(f, len, &h));
+    // the checksum covers everything behind the header: verify it before any section is trusted
+    if (verify_checksum && h.checksum != 0 && len > kFlatHeaderSize) {
+        DevBuf body;
+        VG_TRY(to_device(body, f + kFlatHeaderSize, len - kFlatHeaderSize));
+        uint32_t crc = 0;
+        VG_TRY(device_crc32c(body.as<uint8_t>(), len - kFlatHeaderSize, &crc));
+        if (crc != h.checksum) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "checksum mismatch: expected %x, got %x", h.checksum, crc);
+            return fail(VG_ERR_FORMAT, msg);
+        }
+    }
     const uint64_t off_centroid = rd64(f + 40), off_part = rd64(f + 48), off_quant = rd64(f + 56), off_codes = rd64(f + 64),
                    off_vec = rd64(f + 72), off_pk = rd64(f + 80), off_meta = rd64(f + 88);
-    const uint64_t rows = h.row_count, dim = h.dim;
+    const uint64_t rows = h.row_count, dim = h.dim, L = (uint64_t)len;
     if (dim == 0) return fail(VG_ERR_FORMAT, "zero dimension");
+    uint64_t row_floats = 0, vec_bytes = 0;
+    if (!mul_ok(rows, dim, &row_floats) || !mul_ok(row_floats, 4, &vec_bytes)) return fail(VG_ERR_FORMAT, "rows x dim overflows");
     vg_index_desc d;
     memset(&d, 0, sizeof d);
     d.dim = (int64_t)dim;
@@ -1523,19 +1916,22 @@ vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg
     std::vector<float> pq_sc, pq_of;
     const uint8_t *codes = nullptr;
     if (h.num_partitions > 0) {
-        const uint64_t cb = (uint64_t)h.num_partitions * dim * 4;
-        if (len < off_centroid + cb) return fail(VG_ERR_FORMAT, "file too short for centroids");
-        if (len < off_part + ((uint64_t)h.num_partitions + 1) * 4) return fail(VG_ERR_FORMAT, "file too short for partition offsets");
+        uint64_t cb = 0;
+        if (!mul_ok((uint64_t)h.num_partitions, dim * 4, &cb) || !section_ok(L, off_centroid, cb))
+            return fail(VG_ERR_FORMAT, "file too short for centroids");
+        if (!section_ok(L, off_part, ((uint64_t)h.num_partitions + 1) * 4)) return fail(VG_ERR_FORMAT, "file too short for partition offsets");
         cent.resize((size_t)h.num_partitions * dim);
         memcpy(cent.data(), f + off_centroid, cb);
         poff.resize((size_t)h.num_partitions + 1);
         memcpy(poff.data(), f + off_part, poff.size() * 4);
+        for (size_t i = 0; i + 1 < poff.size(); i++)
+            if (poff[i] > poff[i + 1] || poff[i + 1] > rows) return fail(VG_ERR_FORMAT, "partition offsets are not a monotone cover of the rows");
         d.num_partitions = h.num_partitions;
         d.centroids = cent.data();
         d.partition_offsets = poff.data();
     }
     if (h.quantization_type == 1) {  // QuantizationSQ8 → SetBounds(mins, maxs)
-        if (len < off_quant + dim * 8) return fail(VG_ERR_FORMAT, "file too short for quantization metadata");
+        if (!section_ok(L, off_quant, dim * 8)) return fail(VG_ERR_FORMAT, "file too short for quantization metadata");
         mins.resize(dim);
         maxs.resize(dim);
         scales.resize(dim);
@@ -1543,22 +1939,24 @@ vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg
         memcpy(mins.data(), f + off_quant, dim * 4);
         memcpy(maxs.data(), f + off_quant + dim * 4, dim * 4);
         VG_TRY(vg_sq8_set_bounds(mins.data(), maxs.data(), (int64_t)dim, scales.data(), inv.data()));
-        if (len < off_codes + rows * dim) return fail(VG_ERR_FORMAT, "file too short for codes");
+        if (!section_ok(L, off_codes, row_floats)) return fail(VG_ERR_FORMAT, "file too short for codes");
         d.codec = VG_CODEC_SQ8;
         d.sq8_mins = mins.data();
         d.sq8_inv_scales = inv.data();
         codes = f + off_codes;
     } else if (h.quantization_type == 2) {  // QuantizationPQ
-        if (len < off_quant + 8) return fail(VG_ERR_FORMAT, "file too short for PQ metadata");
+        if (!section_ok(L, off_quant, 8)) return fail(VG_ERR_FORMAT, "file too short for PQ metadata");
         const uint64_t m = rd32(f + off_quant), k = rd32(f + off_quant + 4);
         if (m == 0 || dim % m != 0) return fail(VG_ERR_FORMAT, "dimension must be divisible by numSubvectors");
-        const uint64_t dsub = dim / m, cbsize = m * k * dsub, meta = 8 + m * 8 + cbsize;
-        if (len < off_quant + meta) return fail(VG_ERR_FORMAT, "file too short for PQ metadata");
+        if (k == 0 || k > 256) return fail(VG_ERR_FORMAT, "numCentroids must be in 1..256");
+        const uint64_t dsub = dim / m, cbsize = m * k * dsub, meta = 8 + m * 8 + cbsize;  // m <= dim < 2^32, k <= 256: no overflow
+        if (!section_ok(L, off_quant, meta)) return fail(VG_ERR_FORMAT, "file too short for PQ metadata");
         pq_sc.resize(m);
         pq_of.resize(m);
         memcpy(pq_sc.data(), f + off_quant + 8, m * 4);
         memcpy(pq_of.data(), f + off_quant + 8 + m * 4, m * 4);
-        if (len < off_codes + rows * m) return fail(VG_ERR_FORMAT, "file too short for codes");
+        uint64_t code_bytes = 0;
+        if (!mul_ok(rows, m, &code_bytes) || !section_ok(L, off_codes, code_bytes)) return fail(VG_ERR_FORMAT, "file too short for codes");
         d.codec = VG_CODEC_PQ;
         d.pq_m = (int64_t)m;
         d.pq_k = (int64_t)k;
@@ -1571,22 +1969,11 @@ vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg
     } else {
         return fail(VG_ERR_FORMAT, "unknown quantization type");
     }
-    if (len < off_vec + rows * dim * 4) return fail(VG_ERR_FORMAT, "file too short for vectors");
-    if (off_meta < off_pk || len < off_pk + (off_meta - off_pk)) return fail(VG_ERR_FORMAT, "file too short for IDs");
-    if (rows > 0 && off_meta - off_pk < rows * 8) return fail(VG_ERR_FORMAT, "id section too small");
-    if (verify_checksum && h.checksum != 0 && len > kFlatHeaderSize) {
-        DevBuf body;
-        VG_TRY(to_device(body, f + kFlatHeaderSize, len - kFlatHeaderSize));
-        uint32_t crc = 0;
-        VG_TRY(device_crc32c(body.as<uint8_t>(), len - kFlatHeaderSize, &crc));
-        if (crc != h.checksum) {
-            char msg[96];
-            snprintf(msg, sizeof msg, "checksum mismatch: expected %x, got %x", h.checksum, crc);
-            return fail(VG_ERR_FORMAT, msg);
-        }
-    }
+    if (!section_ok(L, off_vec, vec_bytes)) return fail(VG_ERR_FORMAT, "file too short for vectors");
+    if (off_meta < off_pk || !section_ok(L, off_pk, off_meta - off_pk)) return fail(VG_ERR_FORMAT, "file too short for IDs");
+    if (rows > 0 && (off_meta - off_pk) / 8 < rows) return fail(VG_ERR_FORMAT, "id section too small");
     vg_index_t idx = 0;
-    VG_TRY(vg_index_create(&d, &idx));
+    VG_TRY(vg_index_create_on(t_ts.ctx->device, &d, &idx));
     vg_status s = VG_OK;
     if (rows > 0) {
         // sections are only 4-byte aligned in the file (HeaderSize = 152); staging re-aligns them
@@ -1614,6 +2001,9 @@ vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg
     *out = idx;
     return VG_OK;
 }
+vg_status vg_flat_open(const uint8_t *f, size_t len, int32_t verify_checksum, vg_index_t *out) {
+    return vg_flat_open_on(-1, f, len, verify_checksum, out);
+}
 
 __global__ void gather_u64_kernel(const uint64_t *src, const uint32_t *rows, int64_t n, int64_t nrows, uint64_t *out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1621,9 +2011,9 @@ __global__ void gather_u64_kernel(const uint64_t *src, const uint32_t *rows, int
     out[i] = ((int64_t)rows[i] < nrows) ? src[rows[i]] : 0ull;
 }
 vg_status vg_index_fetch_ids(vg_index_t idx, const uint32_t *h_rows, int64_t n, uint64_t *h_ids) {
-    VG_TRY(ensure_init());
     Index *ix = lookup(idx);
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
     if (!ix->has_ids) return fail(VG_ERR_STATE, "index has no id column");
     if (n <= 0) return VG_OK;
     DevBuf r, o;

@@ -21,8 +21,32 @@ void set_error(const std::string &msg);
 vg_status fail(vg_status code, const std::string &msg);
 vg_status cuda_fail(cudaError_t e, const char *what);
 extern std::atomic<uint64_t> g_launches;
+// The stream of the API call running on this thread (see Call below).
 cudaStream_t stream();
-vg_status ensure_init();  // binds the thread to the library's device (vg_init(0) on first use)
+
+// One API call.  Constructed at the top of every extern "C" entry point: binds the calling thread to a device context
+// (the handle's device, else the device this thread selected with vg_init, else the process default) and to ONE stream
+// for the duration of the call: the handle's stream (vg_index_set_stream), else the calling thread's stream
+// (vg_set_stream), else a stream leased from the device context's pool — so concurrent callers (one goroutine per
+// query in the reference, engine.go:1320-1360) run on different streams and never share scratch.  Nested entry points
+// (vg_index_rerank -> vg_index_rerank_dev) reuse the outer call's binding.
+struct Call {
+    vg_status status = VG_OK;
+    bool outer = false;
+    explicit Call(int device = -1, bool handle_stream_set = false, cudaStream_t handle_stream = nullptr);
+    ~Call();
+    Call(const Call &) = delete;
+    Call &operator=(const Call &) = delete;
+    bool leased() const;      // the call runs on a library-owned stream (nobody else can order work after it)
+    // Results written by a call on a leased stream must be complete when the entry point returns; on a caller-provided
+    // stream the call stays stream-ordered.
+    vg_status finish();
+};
+#define VG_ENTER(...)                       \
+    ::vg::Call _vg_call{__VA_ARGS__};       \
+    do {                                    \
+        if (_vg_call.status != VG_OK) return _vg_call.status; \
+    } while (0)
 
 #define VG_CUDA(expr)                                              \
     do {                                                           \
@@ -92,7 +116,9 @@ __device__ __forceinline__ unsigned long long make_key(float score, uint32_t row
 }
 __device__ __forceinline__ float key_score(unsigned long long key, bool descending) {
     float s = f32_from_orderable((uint32_t)(key >> 32));
-    return descending ? -s : s;
+    // a zero score is stored as +0.0 (make_key canonicalises); negating it back must not turn it into -0.0: the
+    // reference's accumulators start at +0.0 and return +0.0 for orthogonal / zero vectors
+    return descending ? __fadd_rn(-s, 0.0f) : s;
 }
 __device__ __forceinline__ uint32_t key_row(unsigned long long key) { return (uint32_t)key; }
 #define VG_KEY_EMPTY 0xFFFFFFFFFFFFFFFFull

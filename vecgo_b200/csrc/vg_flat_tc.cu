@@ -1184,9 +1184,9 @@ void stats(uint64_t *queries, uint64_t *fallbacks) {
     if (fallbacks) *fallbacks = g_fallbacks.load();
 }
 
-// Filter + exact stage + certificate for one batch (norms of the queries included).
-static vg_status search_once(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
-    failed.clear();
+// Filter + exact stage + certificate for one batch (norms of the queries included): enqueue only.  d_fail[q] = 1
+// where the certificate did not hold.  Nothing here waits for the device.
+static vg_status enqueue_once(const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st) {
     FilterArgs f;
     f.d_queries = io.d_queries;
     f.q_stride = io.q_stride;
@@ -1201,40 +1201,52 @@ static vg_status search_once(const SearchIO &io, int kc, std::vector<int32_t> &f
     f.kc = kc;
     f.is_dot = io.is_dot;
     f.row_base = io.row_base;
-    DevBuf gids, gcnt, tau, qn, failb;
-    VG_TRY(gids.alloc((size_t)io.nq * kc * 4));
-    VG_TRY(gcnt.alloc((size_t)io.nq * 4));
-    VG_TRY(tau.alloc((size_t)io.nq * 4));
-    VG_TRY(qn.alloc((size_t)io.nq * 4));
-    VG_TRY(failb.alloc((size_t)io.nq * 4));
-    f.d_gids = gids.as<uint32_t>();
-    f.d_gcnt = gcnt.as<int32_t>();
-    f.d_tau = tau.as<float>();
-    VG_TRY(sqnorms(io.d_queries, io.nq, io.dim, io.q_stride ? io.q_stride : io.dim, qn.as<float>(), nullptr, st));
-    VG_TRY(filter(f, st));
-    VG_TRY(finalize(f, io.k, qn.as<float>(), io.d_xmax_bits, io.d_rows, io.d_scores, io.d_counts, failb.as<int32_t>(), st));
-    std::vector<int32_t> h_fail((size_t)io.nq);
-    VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)io.nq * 4, cudaMemcpyDeviceToHost, st));
-    VG_CUDA(cudaStreamSynchronize(st));
-    for (int64_t q = 0; q < io.nq; q++)
-        if (h_fail[(size_t)q]) failed.push_back((int32_t)q);
+    // the query tiles of one launch share a [queries][groups] minima buffer: keep it under 8 GiB by chunking the batch
+    // (whole query tiles), as the quantized filter does
+    const int64_t G = filter_group_rows(f);
+    const int64_t groups = (io.rows + G - 1) / G;
+    const int64_t chunk = std::max<int64_t>(BMQ, ((8ll << 30) / (groups * 8)) / BMQ * BMQ);
+    const int64_t q_stride = io.q_stride ? io.q_stride : io.dim;
+    for (int64_t q0 = 0; q0 < io.nq; q0 += chunk) {
+        const int64_t nq = std::min(chunk, io.nq - q0);
+        DevBuf gids, gcnt, tau, qn;
+        VG_TRY(gids.alloc((size_t)nq * kc * 4));
+        VG_TRY(gcnt.alloc((size_t)nq * 4));
+        VG_TRY(tau.alloc((size_t)nq * 4));
+        VG_TRY(qn.alloc((size_t)nq * 4));
+        f.d_queries = io.d_queries + q0 * q_stride;
+        f.nq = nq;
+        f.d_gids = gids.as<uint32_t>();
+        f.d_gcnt = gcnt.as<int32_t>();
+        f.d_tau = tau.as<float>();
+        VG_TRY(sqnorms(f.d_queries, nq, io.dim, q_stride, qn.as<float>(), nullptr, st));
+        VG_TRY(filter(f, st));
+        VG_TRY(finalize(f, io.k, qn.as<float>(), io.d_xmax_bits, io.d_rows + q0 * io.k, io.d_scores + q0 * io.k, io.d_counts + q0,
+                        d_fail + q0, st));
+    }
+    return VG_OK;  // the temporaries go back to the stream-ordered pool (freed in stream order)
+}
+
+vg_status enqueue(const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st) {
+    VG_TRY(enqueue_once(io, kc, d_fail, st));
+    g_queries.fetch_add((uint64_t)io.nq);
     return VG_OK;
 }
 
-// One batch end to end.  Queries whose certificate fails get a second chance with twice the number of groups (a
-// wider gap between the k-th best and tau) before they are reported in `failed` for the exact re-run.
-vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
-    VG_TRY(search_once(io, kc, failed, st));
+// Queries whose certificate failed get a second chance with twice the number of groups (a wider gap between the k-th
+// best and tau); the ones that fail again are returned in `failed` for the exact re-run.
+vg_status retry(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
     const int64_t groups = (io.rows + group_rows(io.rows, kc) - 1) / group_rows(io.rows, kc);
     const int kc2 = (int)std::min<int64_t>(64, std::min<int64_t>(2 * (int64_t)kc, groups / 2));
     if (!failed.empty() && kc2 > kc) {
         const int64_t nb = (int64_t)failed.size();
-        DevBuf bidx, bq, brow, bsc, bcnt;
+        DevBuf bidx, bq, brow, bsc, bcnt, bfail;
         VG_TRY(bidx.alloc((size_t)nb * 4));
         VG_TRY(bq.alloc((size_t)nb * io.dim * 4));
         VG_TRY(brow.alloc((size_t)nb * io.k * 4));
         VG_TRY(bsc.alloc((size_t)nb * io.k * 4));
         VG_TRY(bcnt.alloc((size_t)nb * 4));
+        VG_TRY(bfail.alloc((size_t)nb * 4));
         VG_CUDA(cudaMemcpyAsync(bidx.p, failed.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
         VG_TRY(dev_gather_rows(io.d_queries, io.q_stride ? io.q_stride : io.dim, bidx.as<int32_t>(), nb, io.dim, bq.as<float>(), st));
         SearchIO io2 = io;
@@ -1244,19 +1256,34 @@ vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaS
         io2.d_rows = brow.as<uint32_t>();
         io2.d_scores = bsc.as<float>();
         io2.d_counts = bcnt.as<int32_t>();
-        std::vector<int32_t> failed2;
-        VG_TRY(search_once(io2, kc2, failed2, st));
+        VG_TRY(enqueue_once(io2, kc2, bfail.as<int32_t>(), st));
         // results of the retried queries (also of those that failed again: the caller overwrites them)
         VG_TRY(dev_scatter_results(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(), bidx.as<int32_t>(), nb, io.k, io.d_rows,
                                    io.d_scores, io.d_counts, st));
+        std::vector<int32_t> h_fail((size_t)nb);
+        VG_CUDA(cudaMemcpyAsync(h_fail.data(), bfail.p, (size_t)nb * 4, cudaMemcpyDeviceToHost, st));
         VG_CUDA(cudaStreamSynchronize(st));
         std::vector<int32_t> still;
-        for (int32_t j : failed2) still.push_back(failed[(size_t)j]);
+        for (int64_t j = 0; j < nb; j++)
+            if (h_fail[(size_t)j]) still.push_back(failed[(size_t)j]);
         failed.swap(still);
     }
-    g_queries.fetch_add((uint64_t)io.nq);
     g_fallbacks.fetch_add((uint64_t)failed.size());
     return VG_OK;
+}
+
+// One batch end to end, host-synchronous: enqueue, read the certificate flags back, second chance.
+vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st) {
+    failed.clear();
+    DevBuf failb;
+    VG_TRY(failb.alloc((size_t)io.nq * 4));
+    VG_TRY(enqueue(io, kc, failb.as<int32_t>(), st));
+    std::vector<int32_t> h_fail((size_t)io.nq);
+    VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)io.nq * 4, cudaMemcpyDeviceToHost, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    for (int64_t q = 0; q < io.nq; q++)
+        if (h_fail[(size_t)q]) failed.push_back((int32_t)q);
+    return retry(io, kc, failed, st);
 }
 
 }  // namespace tc

@@ -69,6 +69,11 @@ struct SearchIO {
     int32_t *d_counts = nullptr;               // [nq]
 };
 vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st);
+// The same in two halves for callers that must not wait for the device: enqueue() launches the filter, the exact stage
+// and the certificate (d_fail[q] = 1 where it did not hold) and returns; retry() takes the failed queries (read back by
+// the caller whenever it synchronises anyway), gives them the second chance and leaves the still-unproven ones in `failed`.
+vg_status enqueue(const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st);
+vg_status retry(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st);
 
 // Process-wide switch (default on; environment VECGO_FLAT_TC=0 turns it off) and counters.
 bool enabled();

@@ -1111,7 +1111,7 @@ extern "C" {
 
 vg_status vg_kmeans_find_closest(const float *h_queries, int64_t nq, int64_t dim, const float *h_centroids, int64_t k,
                                  int64_t nprobe, int32_t metric, int32_t *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (nq <= 0) return VG_OK;
     if (k <= 0 || dim <= 0 || nprobe <= 0) return fail(VG_ERR_INVALID, "bad shape");
     if (nprobe > k) nprobe = k;
@@ -1132,7 +1132,7 @@ vg_status vg_kmeans_assign(const float *h_vecs, int64_t n, int64_t dim, const fl
 
 vg_status vg_kmeans_train(const float *h_vecs, int64_t n, int64_t dim, int64_t k, int32_t metric, int64_t max_iter,
                           const int64_t *h_init_rows, uint64_t seed, float *h_centroids, int32_t *h_assign, int64_t *iters_run) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (dim <= 0 || k <= 0) return fail(VG_ERR_INVALID, "bad shape");
     if (n < k) return fail(VG_ERR_INVALID, "not enough vectors to cluster (n < k)");  // Go returns (nil, nil)
     if (metric != VG_METRIC_L2 && metric != VG_METRIC_COSINE && metric != VG_METRIC_DOT)
@@ -1169,7 +1169,7 @@ vg_status vg_kmeans_train(const float *h_vecs, int64_t n, int64_t dim, int64_t k
 
 vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
                       int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
     if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");
@@ -1191,7 +1191,7 @@ vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, in
 // generated there): no host copy of the vectors inside the call.
 vg_status vg_pq_train_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
                           int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
     if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");

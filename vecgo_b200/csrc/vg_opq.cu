@@ -255,7 +255,7 @@ vg_status vg_opq_block_size(int64_t dim, int64_t m, int64_t *block_size) {
 }
 
 vg_status vg_opq_rotate(const float *h_vecs, int64_t n, int64_t dim, int64_t block, const float *h_rotations, int32_t inverse, float *h_out) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return VG_OK;
     if (block <= 0 || dim % block != 0) return fail(VG_ERR_INVALID, "OPQ needs block rotations with dim % block == 0");
     cudaStream_t st = stream();
@@ -276,7 +276,7 @@ vg_status vg_opq_rotate(const float *h_vecs, int64_t n, int64_t dim, int64_t blo
 }
 
 vg_status vg_opq_procrustes(const float *h_M, int64_t blocks, int64_t n, float *h_R, float *h_sigma) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (blocks <= 0 || n <= 0) return fail(VG_ERR_INVALID, "procrustes requires square matrix");
     cudaStream_t st = stream();
     DevBuf M, R, S;
@@ -293,7 +293,7 @@ vg_status vg_opq_procrustes(const float *h_M, int64_t blocks, int64_t n, float *
 
 vg_status vg_opq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t opq_iters, int64_t pq_iters,
                        uint64_t seed, float *h_rotations, int8_t *h_codebooks, float *h_scales, float *h_offsets) {
-    VG_TRY(ensure_init());
+    VG_ENTER();
     if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
     if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
     if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");

@@ -51,6 +51,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <mutex>
 #include <vector>
 
 #include "vg_flat_tc.cuh"
@@ -938,6 +939,7 @@ struct EArgs {
     const uint8_t *codes;
     int64_t row_bytes;
     int layout;               // SQ8: 0 row-major | VB of the lane-transposed layout; INT4: 0 | 1 permuted; PQ: 0 | 1 tiled
+    int int4_lut;             // INT4 gather scoring: 1 = simd.Int4L2DistancePrecomputed over BuildInt4LookupTable values
     const float *p0, *p1;     // SQ8 mins, invScales | INT4 min, diff (natural dimension order)
     const int8_t *codebooks;  // PQ
     const float *pq_scales, *pq_offsets;
@@ -1041,6 +1043,31 @@ __device__ __forceinline__ float exact_score(const EArgs &E, const float *qs, co
         // every 128-byte block, byte 4 e + b of them holds dims 64 e + 16 b + 2 p (+1).
         const uint8_t *code = E.codes + row * E.row_bytes;
         const float *mn = table, *df_ = table + dim;
+        if (E.int4_lut) {
+            // Int4Quantizer.L2Distance after Train / UnmarshalBinary (int4.go:62,141-144,216): simd.Int4L2DistancePrecomputed
+            // (int4_avx512.c:141-189: ONE 16-lane accumulator, e = q - lut[d*16 + nib], acc = fma(e, e, acc), lane tree,
+            // FMA tail) over the table BuildInt4LookupTable fills with unfused Go arithmetic (kernels.go:94-103:
+            // (float32(nib) / 15) * diff + min).  The table entry is recomputed here — same three roundings, same bits.
+            auto lutv = [&](int64_t d, float nib) { return __fadd_rn(__fmul_rn(__fdiv_rn(nib, 15.0f), df_[d]), mn[d]); };
+            auto nib_of = [&](int64_t d) {
+                const uint32_t b = __ldg(code + int4_off(d, E.layout));
+                return u8_to_f32((d & 1) ? (b & 0x0Fu) : (b >> 4));
+            };
+            float acc = 0.0f;
+            int64_t i = 0;
+            for (; i + 16 <= dim; i += 16) {
+                const int64_t d = i + lane;
+                const float e = __fsub_rn(qs[d], lutv(d, nib_of(d)));
+                acc = __fmaf_rn(e, e, acc);
+            }
+            float tot = reduce16(acc);
+            if (lane == 0)
+                for (int64_t d = i; d < dim; d++) {
+                    const float e = __fsub_rn(qs[d], lutv(d, nib_of(d)));
+                    tot = __fmaf_rn(e, e, tot);
+                }
+            return tot;
+        }
         const float k15 = __uint_as_float(0x3d888889u);
         auto val = [&](int64_t d, float nib) { return __fmaf_rn(__fmul_rn(nib, k15), df_[d], mn[d]); };
         float s1 = 0.0f, s2 = 0.0f;
@@ -1397,17 +1424,14 @@ void stats(uint64_t *queries, uint64_t *fallbacks) {
 }
 // Optional CUDA-event timing of the GEMM kernel on its own stream (bench.py's roofline line).
 static std::atomic<int> g_prof{0};
-static cudaEvent_t g_ev[2] = {nullptr, nullptr};
+static std::mutex g_prof_mu;
 static double g_gemm_ms = 0.0;
 static uint64_t g_gemm_launches = 0;
 void profile(int enable, double *gemm_ms, uint64_t *gemm_launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
     if (gemm_ms) *gemm_ms = g_gemm_ms;
     if (gemm_launches) *gemm_launches = g_gemm_launches;
     if (enable >= 0) {
-        if (enable && !g_ev[0]) {
-            cudaEventCreate(&g_ev[0]);
-            cudaEventCreate(&g_ev[1]);
-        }
         g_gemm_ms = 0.0;
         g_gemm_launches = 0;
         g_prof.store(enable ? 1 : 0);
@@ -1487,8 +1511,8 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
             const int d = base + 4 * c + j + 16 * hi;
             perm[(size_t)p] = d < dim ? d : -1;
         }
-        VG_TRY(pp.perm.alloc((size_t)dimp * 4));
-        VG_TRY(pp.xmax.alloc(16));
+        VG_TRY(pp.perm.alloc_persistent((size_t)dimp * 4));
+        VG_TRY(pp.xmax.alloc_persistent(16));
         VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
         VG_CUDA(cudaMemsetAsync(pp.xmax.p, 0, 16, st));
         if (rows > 0 && qc == Q_RABITQ) {
@@ -1556,11 +1580,11 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
         midp[(size_t)p] = mid[(size_t)d];
         mm += (double)mid[(size_t)d] * (double)mid[(size_t)d];
     }
-    VG_TRY(pp.perm.alloc((size_t)dimp * 4));
-    VG_TRY(pp.wq.alloc((size_t)dimp * 4));
-    VG_TRY(pp.midp.alloc((size_t)dimp * 4));
+    VG_TRY(pp.perm.alloc_persistent((size_t)dimp * 4));
+    VG_TRY(pp.wq.alloc_persistent((size_t)dimp * 4));
+    VG_TRY(pp.midp.alloc_persistent((size_t)dimp * 4));
     VG_TRY(pp.xn.alloc_persistent((size_t)std::max<int64_t>(rows, 1) * 4));
-    VG_TRY(pp.xmax.alloc(16));
+    VG_TRY(pp.xmax.alloc_persistent(16));
     VG_CUDA(cudaMemcpyAsync(pp.perm.p, perm.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
     VG_CUDA(cudaMemcpyAsync(pp.wq.p, wq.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
     VG_CUDA(cudaMemcpyAsync(pp.midp.p, midp.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
@@ -1591,7 +1615,7 @@ static vg_status launch_score(const EArgs &e, int64_t nq, const uint32_t *d_rows
     return VG_OK;
 }
 vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries, int64_t q_stride, int64_t nq, const uint32_t *d_rows,
-                     int64_t r, float *d_out, cudaStream_t st) {
+                     int64_t r, float *d_out, int int4_lut, cudaStream_t st) {
     if (nq <= 0 || r <= 0) return VG_OK;
     const int qc = q_codec(cp);
     if (qc < 0) return fail(VG_ERR_UNSUPPORTED, "codec has no gather-scoring kernel");
@@ -1600,6 +1624,7 @@ vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries
     EArgs e = eargs_of(cp, rows);
     e.queries = d_queries;
     e.q_stride = q_stride ? q_stride : cp.dim;
+    e.int4_lut = int4_lut;
     if (qc == Q_SQ8) return launch_score<Q_SQ8>(e, nq, d_rows, (int)r, d_out, st);
     if (qc == Q_INT4) return launch_score<Q_INT4>(e, nq, d_rows, (int)r, d_out, st);
     if (qc == Q_RABITQ) return launch_score<Q_RABITQ>(e, nq, d_rows, (int)r, d_out, st);
@@ -1713,8 +1738,13 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.dsub_shift = 0;
     while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
     a.tiled = (qc == Q_PQ && (cp.variant & VG_VAR_PERM)) ? 1 : 0;
-    const bool prof = g_prof.load() != 0 && g_ev[0];
-    if (prof) VG_CUDA(cudaEventRecord(g_ev[0], st));
+    const bool prof = g_prof.load() != 0;
+    cudaEvent_t g_ev[2] = {nullptr, nullptr};  // per call: the event pair lives on this call's device and stream
+    if (prof) {
+        VG_CUDA(cudaEventCreate(&g_ev[0]));
+        VG_CUDA(cudaEventCreate(&g_ev[1]));
+        VG_CUDA(cudaEventRecord(g_ev[0], st));
+    }
     if (pair_mode) {
         if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
@@ -1762,24 +1792,39 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_CUDA(cudaStreamSynchronize(st));
         float ms = 0.0f;
         if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess) {
+            std::lock_guard<std::mutex> lk(g_prof_mu);
             g_gemm_ms += ms;
             g_gemm_launches++;
         }
+        cudaEventDestroy(g_ev[0]);
+        cudaEventDestroy(g_ev[1]);
     }
     return VG_OK;
 }
 
-vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st) {
-    failed.clear();
+// Candidate groups per query of the first pass and of the second chance (twice as many: a wider gap between the k-th
+// best and tau); 0 when the segment is too short for a second pass to differ.
+static int kc_for(const CodecParams &cp, int64_t rows, int k, int kc_scale) {
+    const int kc = candidates_for(k);
+    if (kc_scale <= 1) return kc;
+    const int kc2 = kc * kc_scale;
+    if (kc2 > 4096 || rows / 32 < 2 * (int64_t)kc2) return 0;
+    (void)cp;
+    return kc2;
+}
+bool second_chance_possible(const CodecParams &cp, int64_t rows, int64_t k) { return kc_for(cp, rows, (int)k, 2) > 0; }
+
+// Enqueue only: filter, select, exact stage, certificate flags (d_fail[q] = 1 where the proof did not hold).  Nothing
+// here waits for the device unless the GEMM profile is on.
+vg_status enqueue(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc_scale, int32_t *d_fail, cudaStream_t st) {
     if (!pp.ready) return fail(VG_ERR_STATE, "decode-GEMM filter state was not prepared");
-    const int kc = candidates_for(io.k);
+    const int kc = kc_for(cp, io.rows, io.k, kc_scale);
+    if (kc <= 0) return fail(VG_ERR_UNSUPPORTED, "segment too short for a second filter pass");
     const int64_t G = qtc_group_rows(io.rows, kc);
     const int64_t groups = (io.rows + G - 1) / G;
     // the [queries][groups] minima buffer is kept under 8 GiB: longer batches go through in chunks of whole query tiles
     // (the headline shape — 10k queries x 78k groups = 6.4 GB — is one launch: one tail instead of two)
     int64_t chunk = std::max<int64_t>(BMQ, ((8ll << 30) / (groups * 8)) / BMQ * BMQ);
-    DevBuf failb;
-    VG_TRY(failb.alloc((size_t)io.nq * 4));
     for (int64_t q0 = 0; q0 < io.nq; q0 += chunk) {
         SearchIO part = io;
         part.nq = std::min(chunk, io.nq - q0);
@@ -1789,14 +1834,24 @@ vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, 
         part.d_rows = io.d_rows + q0 * io.k;
         part.d_scores = io.d_scores + q0 * io.k;
         part.d_counts = io.d_counts + q0;
-        VG_TRY(search_chunk(cp, pp, part, kc, failb.as<int32_t>() + q0, st));
+        VG_TRY(search_chunk(cp, pp, part, kc, d_fail + q0, st));
     }
+    if (kc_scale <= 1) g_queries.fetch_add((uint64_t)io.nq);
+    return VG_OK;
+}
+void count_fallbacks(uint64_t n) { g_fallbacks.fetch_add(n); }
+
+// Host-synchronous form: enqueue and read the certificate flags back.  `failed` lists the queries without a proof.
+vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st) {
+    failed.clear();
+    DevBuf failb;
+    VG_TRY(failb.alloc((size_t)io.nq * 4));
+    VG_TRY(enqueue(cp, pp, io, 1, failb.as<int32_t>(), st));
     std::vector<int32_t> h_fail((size_t)io.nq);
     VG_CUDA(cudaMemcpyAsync(h_fail.data(), failb.p, (size_t)io.nq * 4, cudaMemcpyDeviceToHost, st));
     VG_CUDA(cudaStreamSynchronize(st));
     for (int64_t q = 0; q < io.nq; q++)
         if (h_fail[(size_t)q]) failed.push_back((int32_t)q);
-    g_queries.fetch_add((uint64_t)io.nq);
     g_fallbacks.fetch_add((uint64_t)failed.size());
     return VG_OK;
 }

@@ -44,11 +44,19 @@ struct SearchIO {
 // Filter + exact stage + certificate for one batch.  `failed` lists the queries whose certificate did not hold: the
 // caller re-runs those on the exact scan (scan_topk_subset).
 vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st);
+// The same without waiting for the device: launches everything and leaves d_fail[q] = 1 where the certificate did not
+// hold.  kc_scale = 1 is the normal pass; kc_scale = 2 is the second chance for queries that failed it (twice the
+// candidate groups), available when second_chance_possible().  count_fallbacks() accounts queries that end on the exact scan.
+vg_status enqueue(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc_scale, int32_t *d_fail, cudaStream_t st);
+bool second_chance_possible(const CodecParams &cp, int64_t rows, int64_t k);
+void count_fallbacks(uint64_t n);
 
 // Quantized distance of query q to its r candidate rows d_rows[q][0..r) (local row ids; rows >= `rows` give NaN), in the
 // reference's arithmetic.  RaBitQ needs cp.q_words / cp.q_norms (prep_sign_queries); OPQ queries must be rotated already.
+// INT4: int4_lut = 1 scores like Int4Quantizer.L2Distance on a trained quantizer (simd.Int4L2DistancePrecomputed over the
+// BuildInt4LookupTable values, int4.go:141-144), 0 like simd.Int4L2Distance (FMA dequantisation).
 vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries, int64_t q_stride, int64_t nq, const uint32_t *d_rows,
-                     int64_t r, float *d_out, cudaStream_t st);
+                     int64_t r, float *d_out, int int4_lut, cudaStream_t st);
 
 void stats(uint64_t *queries, uint64_t *fallbacks);
 // Returns the accumulated CUDA-event time / launch count of the GEMM kernel since the last reset; enable = 1 / 0 turns

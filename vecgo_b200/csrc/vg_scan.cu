@@ -1346,6 +1346,89 @@ vg_status rerank_gather(const float *d_vectors, int64_t nrows, int64_t dim, cons
     return VG_OK;
 }
 
+// ------------------------------------------------------------ bounded L2 (gather)
+// simd.SquaredL2Bounded (kernels.go:163-176, AVX-512 path registered at kernels_amd64.go:269: bounded_l2_avx512.c:19-107)
+// for every (query, candidate row) pair: four 16-lane FMA accumulators over 64-dim blocks; after EVERY block the running
+// total (s1+s2)+(s3+s4), summed across the lanes in hsum512's order — i+8, i+4, then the two vhaddps: (u0+u1)+(u2+u3) —
+// is compared with the bound and the pair exits with (that partial total, exceeded = 1) when it is larger.  The rest goes
+// in 8-wide steps (unfused diff*diff, lanes i+4, (w0+w1)+(w2+w3), added to the total) and a fused scalar tail
+// (bounded_l2_avx512.s:94-114).  NaN totals never exit early (ucomiss / jbe) and end with exceeded = 0 (seta).
+__device__ __forceinline__ float hsum512_order(float v) {
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 8, 16));
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 4, 16));
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 1, 16));   // (u0+u1) in lane 0, (u2+u3) in lane 2
+    v = __fadd_rn(v, __shfl_down_sync(0xffffffffu, v, 2, 16));
+    return v;
+}
+__global__ void __launch_bounds__(256) bounded_l2_kernel(const float *vectors, int64_t nrows, int64_t dim, const float *queries, int64_t nq,
+                                                         const uint32_t *rows, int64_t r, const float *bounds, int64_t bound_stride, float *out,
+                                                         uint8_t *exceeded) {
+    const int64_t pair = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const int64_t total = nq * r;
+    const bool live = pair < total;
+    const int64_t p = live ? pair : total - 1;
+    const int64_t q = p / r;
+    const uint32_t row = rows[p];
+    const bool valid = (int64_t)row < nrows;
+    const float *x = vectors + (valid ? (int64_t)row : 0) * dim;
+    const float *qv = queries + q * dim;
+    const float bound = bounds[bound_stride ? p : q];
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    float tot = 0.0f;
+    int64_t i = 0;
+    bool done = false;
+    for (; i + 64 <= dim; i += 64) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t d = i + j * 16 + lane;
+            const float df = __fsub_rn(qv[d], __ldg(x + d));
+            a[j] = __fmaf_rn(df, df, a[j]);
+        }
+        tot = hsum512_order(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+        tot = __shfl_sync(0xffffffffu, tot, 0, 16);
+        if (tot > bound) {  // uniform across the half-warp
+            done = true;
+            break;
+        }
+    }
+    uint8_t ex = 1;
+    if (!done) {
+        for (; i + 8 <= dim; i += 8) {
+            float sq = 0.0f;
+            if (lane < 8) {
+                const float df = __fsub_rn(qv[i + lane], __ldg(x + i + lane));
+                sq = __fmul_rn(df, df);
+            }
+            sq = __fadd_rn(sq, __shfl_down_sync(0xffffffffu, sq, 4, 16));  // w[i] = sq[i] + sq[i+4]
+            sq = __fadd_rn(sq, __shfl_down_sync(0xffffffffu, sq, 1, 16));  // w0+w1 (lane 0), w2+w3 (lane 2)
+            sq = __fadd_rn(sq, __shfl_down_sync(0xffffffffu, sq, 2, 16));
+            sq = __shfl_sync(0xffffffffu, sq, 0, 16);
+            tot = __fadd_rn(tot, sq);
+        }
+        for (; i < dim; i++) {
+            const float df = __fsub_rn(qv[i], __ldg(x + i));
+            tot = __fmaf_rn(df, df, tot);
+        }
+        ex = tot > bound ? 1 : 0;
+    }
+    if (lane == 0 && live) {
+        out[p] = valid ? tot : __uint_as_float(0x7fc00000u);
+        exceeded[p] = valid ? ex : 0;
+    }
+}
+vg_status bounded_l2_gather(const float *d_vectors, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq, const uint32_t *d_rows,
+                            int64_t r, const float *d_bounds, int per_pair_bounds, float *d_out, uint8_t *d_exceeded, cudaStream_t st) {
+    const int64_t total = nq * r;
+    if (total <= 0) return VG_OK;
+    if (!d_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors");
+    const int64_t threads = total * 16;
+    bounded_l2_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(d_vectors, nrows, dim, d_queries, nq, d_rows, r, d_bounds,
+                                                                        per_pair_bounds ? 1 : 0, d_out, d_exceeded);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
 // ------------------------------------------------------------ hamming matrix
 __global__ void __launch_bounds__(256) hamming_kernel(const uint8_t *q, int64_t nq, const uint8_t *codes, int64_t n,
                                                       int64_t nbytes, int32_t *out) {

@@ -77,6 +77,10 @@ vg_status scan_dense(const CodecParams &cp, const float *d_queries, int64_t nq, 
 // Exact per-candidate scores: out[q][j] = dist(query q, vectors[rows[q][j]]) in simd pair order.
 vg_status rerank_gather(const float *d_vectors, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq,
                         const uint32_t *d_rows, int64_t r, int is_dot, float *d_out, cudaStream_t st);
+// simd.SquaredL2Bounded per (query, candidate row): out = the distance, or the partial sum at the 64-dim block where it
+// first exceeded the bound (exceeded = 1).  Bounds: one per query, or one per pair when per_pair_bounds.
+vg_status bounded_l2_gather(const float *d_vectors, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq, const uint32_t *d_rows,
+                            int64_t r, const float *d_bounds, int per_pair_bounds, float *d_out, uint8_t *d_exceeded, cudaStream_t st);
 // Hamming matrix out[nq][n] between byte strings.
 vg_status hamming_dense(const uint8_t *d_q, int64_t nq, const uint8_t *d_codes, int64_t n, int64_t nbytes, int32_t *d_out,
                         cudaStream_t st);

@@ -15,7 +15,7 @@ EMPTY_ROW = 0xFFFFFFFF
 class DeviceIndex:
     def __init__(self, *, codec: int, metric: int, dim: int, rows: int, segment_id: int = 0, row_base: int = 0,
                  sq8=None, int4=None, pq=None, opq=None, bq_threshold: float = 0.0, centroids=None,
-                 partition_offsets=None, _handle=None):
+                 partition_offsets=None, device=None, _handle=None):
         self.codec, self.metric, self.dim, self.rows = codec, metric, dim, rows
         self.segment_id, self.row_base = segment_id, row_base
         self.handle = None
@@ -50,7 +50,10 @@ class DeviceIndex:
             keep += [cen, po]
             d.num_partitions, d.centroids, d.partition_offsets = cen.shape[0], L.ptr(cen, L.f32p), L.ptr(po, L.u32p)
         h = C.c_uint64()
-        L.call("vg_index_create", C.byref(d), C.byref(h))
+        if device is None:
+            L.call("vg_index_create", C.byref(d), C.byref(h))      # the calling thread's device (vg_init)
+        else:
+            L.call("vg_index_create_on", int(device), C.byref(d), C.byref(h))
         self.handle = h.value
 
     # ------------------------------------------------------------------ data
@@ -106,6 +109,45 @@ class DeviceIndex:
     def search_dev(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int, nprobes: int = 0,
                    d_mask: int = 0):
         L.call("vg_index_search_dev", self.handle, d_queries, nq, k, nprobes, d_mask or None, d_rows, d_scores, d_counts)
+
+    def search_dev_async(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int, d_unproven: int,
+                         nprobes: int = 0, d_mask: int = 0):
+        """Launch-only search (no host wait): d_unproven [nq] int32 receives 1 where a query's certificate did not hold."""
+        L.call("vg_index_search_dev_async", self.handle, d_queries, nq, k, nprobes, d_mask or None, d_rows, d_scores, d_counts,
+               d_unproven)
+
+    def search_resolve(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int, d_unproven: int,
+                       nprobes: int = 0, d_mask: int = 0) -> int:
+        """Second half of search_dev_async: re-runs the flagged queries; returns how many needed it."""
+        n = C.c_int64()
+        L.call("vg_index_search_resolve", self.handle, d_queries, nq, k, nprobes, d_mask or None, d_rows, d_scores, d_counts,
+               d_unproven, C.byref(n))
+        return int(n.value)
+
+    def set_stream(self, cuda_stream: int):
+        """Calls on this handle run on `cuda_stream` (a cudaStream_t as integer; ~0 = library / thread streams)."""
+        L.call("vg_index_set_stream", self.handle, cuda_stream & 0xFFFFFFFFFFFFFFFF)
+
+    def device(self) -> int:
+        d = C.c_int32()
+        L.call("vg_index_device", self.handle, C.byref(d))
+        return int(d.value)
+
+    def l2_bounded(self, queries, rows, bounds):
+        """simd.SquaredL2Bounded of query i against rows[i, :]; bounds [nq] or [nq, r] → (scores, exceeded)."""
+        q = L.as_f32(queries).reshape(-1, self.dim)
+        rr = np.ascontiguousarray(rows, np.uint32).reshape(q.shape[0], -1)
+        b = L.as_f32(bounds)
+        per_pair = int(b.size == rr.size and b.size != q.shape[0])
+        out = np.full(rr.shape, np.nan, F)
+        ex = np.zeros(rr.shape, np.uint8)
+        L.call("vg_index_l2_bounded", self.handle, L.ptr(q, L.f32p), q.shape[0], L.ptr(rr, L.u32p), rr.shape[1], L.ptr(b, L.f32p),
+               per_pair, L.ptr(out, L.f32p), L.ptr(ex, L.u8p))
+        return out, ex.astype(bool)
+
+    def set_int4_score_mode(self, direct: bool):
+        """score() on INT4: False (default) = Int4Quantizer.L2Distance's precomputed-LUT path, True = simd.Int4L2Distance."""
+        L.call("vg_index_set_int4_score_mode", self.handle, 1 if direct else 0)
 
     def rerank_dev(self, d_queries: int, nq: int, d_rows: int, r: int, d_scores: int):
         """Device-resident Segment.Rerank: d_rows [nq, r] LOCAL row ids (0xFFFFFFFF / out of range -> NaN score)."""

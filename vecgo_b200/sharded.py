@@ -72,6 +72,18 @@ class ShardedIndex:
         self.group = group
         self._merge_fn = merge                    # test hook; default = vg_topk_merge_dev
 
+    @staticmethod
+    def _bind_stream(t):
+        """The library must run on the stream torch (and NCCL) order their work on: rows / scores written by library
+        kernels are read by torch ops and collectives, and their outputs are read by library kernels again.  Binding the
+        calling thread's library stream to torch's current stream makes every step of a search one in-order queue."""
+        if t.is_cuda:
+            import torch
+
+            from . import _lib as L
+
+            L.call("vg_set_stream", torch.cuda.current_stream(t.device).cuda_stream)
+
     def _merge(self, all_rows, all_scores, k_in: int, k_out: int, descending: bool):
         import torch
 
@@ -96,6 +108,7 @@ class ShardedIndex:
         (score, row) pairs and merge to the final top-k."""
         import torch
 
+        self._bind_stream(d_queries)
         dev = d_queries.device
         rows = torch.empty((nq, r), dtype=torch.int32, device=dev)
         scores = torch.empty((nq, r), dtype=torch.float32, device=dev)
@@ -118,6 +131,7 @@ class ShardedIndex:
 
         from . import _lib as L
 
+        self._bind_stream(d_queries)
         dev = d_queries.device
         rows = torch.empty((nq, k), dtype=torch.int32, device=dev)
         scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
