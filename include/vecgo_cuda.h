@@ -147,6 +147,14 @@ vg_status vg_pq_train(const float *h_vecs, int64_t n, int64_t dim, int64_t m, in
 vg_status vg_pq_train_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
                       int8_t *h_codebooks, float *h_scales, float *h_offsets, float *h_centroids_f32 /* optional [m][k][dim/m] */);
 
+/* The same for subspaces [subspace_lo, subspace_hi) only; outputs hold that many subspaces.  ProductQuantizer.Train runs
+ * one goroutine per subspace (pq.go:79-140): they are independent, so GPU r of W trains subspaces [r*m/W, (r+1)*m/W) of
+ * the same training set and the W slices are concatenated — bit-identical to the single-GPU training (every float32
+ * sum still runs in sample order; the seeded k-means++ / re-seeding draws are indexed by the subspace's number). */
+vg_status vg_pq_train_range_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
+                                int64_t subspace_lo, int64_t subspace_hi, int8_t *h_codebooks, float *h_scales, float *h_offsets,
+                                float *h_centroids_f32 /* optional */);
+
 /* OptimizedProductQuantizer (opq.go:28-282, svd.go:13-216).  Rotations are [dim/block][block][block] float32,
  * block = vg_opq_block_size(dim, m) (NewOptimizedProductQuantizer's rule, opq.go:41-58).
  * vg_opq_train: `opq_iters` rounds of rotate -> ProductQuantizer.Train (`pq_iters` Lloyd iterations, seed + round)

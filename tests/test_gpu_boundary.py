@@ -305,3 +305,35 @@ def test_flat_open_rejects_wrapping_offsets(vg):
         struct.pack_into("<II", bad, 16, 0xFFFFFFFF, 0xFFFFFFFF)
         with pytest.raises(vg.VecgoError):
             vg.flat.Segment.Open(bytes(bad), verify_checksum=False)
+
+
+# ------------------------------------------------------------------ PQ training split by subspace
+@pytest.mark.parametrize("n,dim,m,parts", [(6000, 768, 96, 8), (5000, 64, 8, 3), (3000, 48, 6, 2)])
+def test_pq_train_subspace_ranges_equal_whole(vg, n, dim, m, parts):
+    """pq.go:79-140 trains every subspace in its own goroutine: subspaces [lo, hi) trained on their own (what one GPU of W
+    does, vg_pq_train_range_dev) must give the same codebooks, scales, offsets and float32 centroids, bit for bit, as the
+    slice of the whole training — including the seeded k-means++ draws and empty-cluster re-seeding (RNG stream = the
+    subspace's number).  96 x 8-dim subspaces go through the tensor-core assignment on a column slice."""
+    import torch
+
+    L = vg._lib
+    rng = np.random.default_rng(5)
+    v = rng.standard_normal((n, dim)).astype(F)
+    v[: n // 10] = v[0]  # duplicates: empty clusters appear and get re-seeded
+    ds = dim // m
+    dx = torch.from_numpy(v).cuda()
+    cb, sc, of = np.zeros(m * 256 * ds, np.int8), np.zeros(m, F), np.zeros(m, F)
+    cent = np.zeros((m, 256, ds), F)
+    L.call("vg_pq_train_dev", dx.data_ptr(), n, dim, m, 256, 4, 9, L.ptr(cb, L.i8p), L.ptr(sc, L.f32p), L.ptr(of, L.f32p), L.ptr(cent, L.f32p))
+    from vecgo_b200.sharded import shard_range
+
+    for r in range(parts):
+        lo, hi = shard_range(m, r, parts)
+        g = hi - lo
+        cb2, sc2, of2 = np.zeros(g * 256 * ds, np.int8), np.zeros(g, F), np.zeros(g, F)
+        cent2 = np.zeros((g, 256, ds), F)
+        L.call("vg_pq_train_range_dev", dx.data_ptr(), n, dim, m, 256, 4, 9, lo, hi, L.ptr(cb2, L.i8p), L.ptr(sc2, L.f32p), L.ptr(of2, L.f32p),
+               L.ptr(cent2, L.f32p))
+        assert np.array_equal(cb2, cb[lo * 256 * ds:hi * 256 * ds]), (r, "codebooks")
+        assert np.array_equal(bits(sc2), bits(sc[lo:hi])) and np.array_equal(bits(of2), bits(of[lo:hi])), (r, "scales/offsets")
+        assert np.array_equal(bits(cent2), bits(cent[lo:hi])), (r, "centroids")

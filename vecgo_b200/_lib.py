@@ -96,6 +96,7 @@ _SIGS = {
     "vg_pq_build_distance_table": [f32p, i64, i64, i64, i64, i8p, f32p, f32p, f32p],
     "vg_pq_train": [f32p, i64, i64, i64, i64, i64, u64, i8p, f32p, f32p, f32p],
     "vg_pq_train_dev": [vp, i64, i64, i64, i64, i64, u64, i8p, f32p, f32p, f32p],
+    "vg_pq_train_range_dev": [vp, i64, i64, i64, i64, i64, u64, i64, i64, i8p, f32p, f32p, f32p],
     "vg_pq_assign_tc_stats": [u64p, u64p],
     "vg_opq_block_size": [i64, i64, i64p],
     "vg_opq_train": [f32p, i64, i64, i64, i64, i64, i64, u64, f32p, i8p, f32p, f32p],

@@ -607,12 +607,14 @@ __device__ __forceinline__ void select_compact_approx(const TopK &t, int slot, i
         return;
     }
     const unsigned long long pivot = __shfl_sync(0xffffffffu, s, best);
+    __syncwarp();  // the counting passes above read the whole buffer: ordered before the in-place packing below
     int base = 0;
     for (int i0 = 0; i0 < n; i0 += 32) {
         const int i = i0 + lane;
         const unsigned long long v = i < n ? a[i] : VG_KEY_EMPTY;
         const bool keep = i < n && v < pivot;
-        const unsigned b = __ballot_sync(0xffffffffu, keep);  // every lane has read its key of this chunk before any lane writes
+        const unsigned b = __ballot_sync(0xffffffffu, keep);
+        __syncwarp();  // every lane has read its key of this chunk before any lane writes (memory ordering, not only convergence)
         if (keep) a[base + __popc(b & ((1u << lane) - 1u))] = v;  // target index <= i: inside chunks already read
         base += __popc(b);
     }

@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(256) part_scatter_anyk_kernel(const int32_t *a
 __global__ void __launch_bounds__(256) centroid_update_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int G,
                                                               const int *active, const int *totals, const int64_t *base,
                                                               const uint32_t *members, int reciprocal, uint64_t seed,
-                                                              uint64_t tag_xor, int tag_is_group, const int *iters,
+                                                              uint64_t tag_xor, int tag_is_group, int g_base, const int *iters,
                                                               float *cent /*[G][K][ds]*/) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)G * K * ds) return;
@@ -394,7 +394,7 @@ __global__ void __launch_bounds__(256) centroid_update_kernel(const float *vecs,
         else cent[t] = __fdiv_rn(sum, (float)cntc);
     } else {
         // empty cluster: re-seed from a random sample (explicit RNG; iteration = completed updates)
-        const uint64_t tag = (tag_is_group ? (uint64_t)g : 0ull) ^ tag_xor;
+        const uint64_t tag = (tag_is_group ? (uint64_t)(g_base + g) : 0ull) ^ tag_xor;
         const int64_t idx = rng_intn(seed, tag, (uint64_t)((int64_t)(iters[g] - 1) * K + c), n);
         cent[t] = col[idx * stride];
     }
@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(256) centroid_update_kernel(const float *vecs,
 
 struct Lloyd {
     int G, K, ds;
+    int g_base = 0;   // index of the first subspace trained here inside the whole quantizer (selects the RNG streams)
     int64_t n, stride, B;
     DevBuf assign_new, assign_old, counts, totals, base, members, active, changed, iters, score, cnt;
     vg_status init(int G_, int K_, int ds_, int64_t n_, int64_t stride_, cudaStream_t st) {
@@ -465,7 +466,7 @@ struct Lloyd {
         const int64_t chains = (int64_t)G * K * ds;
         centroid_update_kernel<<<(unsigned)((chains + 255) / 256), 256, 0, st>>>(
             d_vecs, n, stride, ds, K, G, active.as<int>(), totals.as<int>(), base.as<int64_t>(), members.as<uint32_t>(), reciprocal,
-            seed, tag_xor, tag_is_group, iters.as<int>(), d_cent);
+            seed, tag_xor, tag_is_group, g_base, iters.as<int>(), d_cent);
         VG_LAUNCHED();
         return VG_OK;
     }
@@ -628,7 +629,7 @@ __device__ __forceinline__ void pp_load_tile(const float *m, int64_t n, int64_t 
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t n, int c, uint64_t seed, int *zero,
+__global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t n, int c, uint64_t seed, int g_base, int *zero,
                                                      int64_t *chosen, float *ckpt /*[G][tiles]*/) {
     __shared__ __align__(16) float buf[2][PP_TILE];
     const int g = blockIdx.x, lane = threadIdx.x;
@@ -669,11 +670,11 @@ __global__ void __launch_bounds__(32) pp_pick_kernel(const float *mind, int64_t 
     if (sum == 0.0f) {
         if (lane == 0) {
             zero[g] = 1;
-            chosen[g] = rng_intn(seed, (uint64_t)g, (uint64_t)c, n);
+            chosen[g] = rng_intn(seed, (uint64_t)(g_base + g), (uint64_t)c, n);
         }
         return;
     }
-    const float target = __fmul_rn(rng_f32(seed, (uint64_t)g, (uint64_t)c), sum);
+    const float target = __fmul_rn(rng_f32(seed, (uint64_t)(g_base + g), (uint64_t)c), sum);
     __syncwarp();
     long long bt = 0;
     for (int64_t t = lane; t < tiles; t += 32)
@@ -790,7 +791,7 @@ __device__ __forceinline__ PxSum px_summarize(const float *x, int cnt, int Eu) {
 }
 // One CTA per group: checkpoints ck[g][chunk] = running sum before element 32 * chunk, the total, then the k-means++
 // pick (pq.go:305-320) by binary search over the checkpoints (the chain is non-decreasing) + a 32-element walk.
-__global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *mind, int64_t n, int c, uint64_t seed, int *zero,
+__global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *mind, int64_t n, int c, uint64_t seed, int g_base, int *zero,
                                                                 int64_t *chosen, float *ckpt /*[G][chunks]*/) {
     extern __shared__ float tile[];  // [PX_T][PX_CH + 1]
     __shared__ PxSum wsum[PX_T / 32], wpre[PX_T / 32];
@@ -913,11 +914,11 @@ __global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *min
     if (sum == 0.0f) {
         if (tid == 0) {
             zero[g] = 1;
-            chosen[g] = rng_intn(seed, (uint64_t)g, (uint64_t)c, n);
+            chosen[g] = rng_intn(seed, (uint64_t)(g_base + g), (uint64_t)c, n);
         }
         return;
     }
-    const float target = __fmul_rn(rng_f32(seed, (uint64_t)g, (uint64_t)c), sum);
+    const float target = __fmul_rn(rng_f32(seed, (uint64_t)(g_base + g), (uint64_t)c), sum);
     // last chunk whose start is below the target (checkpoints are non-decreasing): count them, all threads; chunk 0 when none is
     int below = 0;
     for (int64_t j = tid; j < chunks; j += PX_T) below += ck[j] < target ? 1 : 0;
@@ -942,10 +943,10 @@ __global__ void __launch_bounds__(PX_T) pp_pick_parallel_kernel(const float *min
     chosen[g] = pick;
 }
 
-__global__ void pp_first_kernel(int64_t n, uint64_t seed, int G, int64_t *chosen, int *zero) {
+__global__ void pp_first_kernel(int64_t n, uint64_t seed, int G, int g_base, int64_t *chosen, int *zero) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= G) return;
-    chosen[g] = rng_intn(seed, (uint64_t)g, 0, n);
+    chosen[g] = rng_intn(seed, (uint64_t)(g_base + g), 0, n);
     zero[g] = 0;
 }
 __global__ void __launch_bounds__(256) pp_small_init_kernel(const float *vecs, int64_t n, int64_t stride, int ds, int K, int G,
@@ -1043,7 +1044,14 @@ static bool pp_sequential_pick() {
 // ProductQuantizer.Train on device-resident vectors (pq.go:68-143,275-433); outputs stay on the device.
 vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed, DevBuf &cent,
                        DevBuf &cb, DevBuf &sc, DevBuf &of, cudaStream_t st) {
-    const int G = (int)m, K = (int)k, ds = (int)(dim / m);
+    return dev_pq_train_range(d_vecs, n, dim, m, k, iters, seed, 0, m, cent, cb, sc, of, st);
+}
+// Subspaces [g0, g1) of the quantizer only (pq.go:79-140 trains every subspace in its own goroutine: they are independent,
+// so a subset trained elsewhere — another GPU — gives the same centroids bit for bit).  Outputs hold g1 - g0 subspaces.
+vg_status dev_pq_train_range(const float *d_vecs_all, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed, int64_t g0,
+                             int64_t g1, DevBuf &cent, DevBuf &cb, DevBuf &sc, DevBuf &of, cudaStream_t st) {
+    const int G = (int)(g1 - g0), K = (int)k, ds = (int)(dim / m), g_base = (int)g0;
+    const float *d_vecs = d_vecs_all + g0 * ds;   // column slice: same row stride `dim`
     DevBuf mind, zero, chosen, score, cnt, ckpt;
     VG_TRY(cent.alloc((size_t)G * K * ds * 4));
     // ---- initializeCentroids
@@ -1056,7 +1064,7 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         VG_TRY(zero.alloc((size_t)G * 4));
         VG_TRY(chosen.alloc((size_t)G * 8));
         VG_TRY(ckpt.alloc((size_t)G * ((n + PX_CH - 1) / PX_CH) * 4));
-        pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, chosen.as<int64_t>(), zero.as<int>());
+        pp_first_kernel<<<(G + 63) / 64, 64, 0, st>>>(n, seed, G, g_base, chosen.as<int64_t>(), zero.as<int>());
         VG_LAUNCHED();
         const size_t pp_sm = (size_t)G * (PP_ROWS + 1) * 4;
         // subspace lengths with a compile-time kernel (16-byte loads, unrolled chain); the row stride must keep them aligned
@@ -1067,9 +1075,9 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
         for (int c = 0; c < K; c++) {
             if (c > 0) {
                 if (pp_sequential_pick())
-                    pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(), ckpt.as<float>());
+                    pp_pick_kernel<<<G, 32, 0, st>>>(mind.as<float>(), n, c, seed, g_base, zero.as<int>(), chosen.as<int64_t>(), ckpt.as<float>());
                 else
-                    pp_pick_parallel_kernel<<<G, PX_T, PX_SMEM, st>>>(mind.as<float>(), n, c, seed, zero.as<int>(), chosen.as<int64_t>(),
+                    pp_pick_parallel_kernel<<<G, PX_T, PX_SMEM, st>>>(mind.as<float>(), n, c, seed, g_base, zero.as<int>(), chosen.as<int64_t>(),
                                                                 ckpt.as<float>());
                 VG_LAUNCHED();
             }
@@ -1086,6 +1094,7 @@ vg_status dev_pq_train(const float *d_vecs, int64_t n, int64_t dim, int64_t m, i
     // ---- runKMeansIterations
     Lloyd L;
     VG_TRY(L.init(G, K, ds, n, dim, st));
+    L.g_base = g_base;
     // 8-dim subspaces x 256 centroids: assignment on the tensor cores with an exactness certificate (vg_pq_assign_tc.cu)
     pqa::Assigner tca;
     if (iters > 0 && pqa::Assigner::supported(n, dim, G, K, ds)) VG_TRY(tca.prepare(d_vecs, n, dim, G, st));
@@ -1199,6 +1208,27 @@ vg_status vg_pq_train_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m
     const int G = (int)m, K = (int)k, ds = (int)(dim / m);
     DevBuf cent, cb, sc, of;
     VG_TRY(dev_pq_train(d_vecs, n, dim, m, k, iters, seed, cent, cb, sc, of, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    VG_TRY(staged_d2h(h_codebooks, cb.p, (size_t)G * K * ds));
+    VG_TRY(staged_d2h(h_scales, sc.p, (size_t)G * 4));
+    VG_TRY(staged_d2h(h_offsets, of.p, (size_t)G * 4));
+    if (h_centroids_f32) VG_TRY(staged_d2h(h_centroids_f32, cent.p, (size_t)G * K * ds * 4));
+    return VG_OK;
+}
+
+vg_status vg_pq_train_range_dev(const float *d_vecs, int64_t n, int64_t dim, int64_t m, int64_t k, int64_t iters, uint64_t seed,
+                                int64_t subspace_lo, int64_t subspace_hi, int8_t *h_codebooks, float *h_scales, float *h_offsets,
+                                float *h_centroids_f32) {
+    VG_ENTER();
+    if (n <= 0) return fail(VG_ERR_INVALID, "no vectors provided for training");
+    if (m <= 0 || dim <= 0 || dim % m != 0) return fail(VG_ERR_INVALID, "dimension must be divisible by numSubvectors");
+    if (k <= 0 || k > 256) return fail(VG_ERR_INVALID, "numCentroids must be <= 256 for uint8 encoding");
+    if (subspace_lo < 0 || subspace_hi > m || subspace_lo > subspace_hi) return fail(VG_ERR_INVALID, "subspace range outside the quantizer");
+    if (subspace_lo == subspace_hi) return VG_OK;
+    cudaStream_t st = stream();
+    const int G = (int)(subspace_hi - subspace_lo), K = (int)k, ds = (int)(dim / m);
+    DevBuf cent, cb, sc, of;
+    VG_TRY(dev_pq_train_range(d_vecs, n, dim, m, k, iters, seed, subspace_lo, subspace_hi, cent, cb, sc, of, st));
     VG_CUDA(cudaStreamSynchronize(st));
     VG_TRY(staged_d2h(h_codebooks, cb.p, (size_t)G * K * ds));
     VG_TRY(staged_d2h(h_scales, sc.p, (size_t)G * 4));

@@ -366,7 +366,7 @@ static bool enabled() {
 }
 
 bool Assigner::supported(int64_t n, int64_t dim, int G, int K, int ds) {
-    return enabled() && ds == 8 && K == TN && (G & 1) == 0 && dim == (int64_t)G * 8 && n >= 4096 && n * (int64_t)G < (1ll << 32) &&
+    return enabled() && ds == 8 && K == TN && (G & 1) == 0 && dim >= (int64_t)G * 8 && dim % 4 == 0 && n >= 4096 && n * (int64_t)G < (1ll << 32) &&
            n * (int64_t)G * 64 <= (32ll << 30);  // the fp16 shadow is twice the training set
 }
 
@@ -378,10 +378,11 @@ vg_status Assigner::prepare(const float *d_vecs, int64_t n_, int64_t dim_, int G
     vecs = d_vecs;
     if ((reinterpret_cast<uintptr_t>(d_vecs) & 15) != 0) return VG_OK;
     DevBuf mm, am;
-    VG_TRY(mm.alloc((size_t)dim * 8));
+    const int64_t cols = (int64_t)G * 8;  // the G subspaces trained here: a column slice when the subspaces are split across GPUs
+    VG_TRY(mm.alloc((size_t)cols * 8));
     VG_TRY(am.alloc(8));
-    VG_TRY(dev_minmax(d_vecs, n, dim, mm.as<float>(), mm.as<float>() + dim, st));
-    absmax_kernel<<<1, 256, 0, st>>>(mm.as<float>(), mm.as<float>() + dim, dim, am.as<float>());
+    VG_TRY(dev_minmax_strided(d_vecs, n, cols, dim, mm.as<float>(), mm.as<float>() + cols, st));
+    absmax_kernel<<<1, 256, 0, st>>>(mm.as<float>(), mm.as<float>() + cols, cols, am.as<float>());
     VG_LAUNCHED();
     float h[2] = {0.f, 0.f};
     VG_CUDA(cudaMemcpyAsync(h, am.p, 8, cudaMemcpyDeviceToHost, st));

@@ -10,7 +10,7 @@ namespace vg {
 // ScalarQuantizer.Train (quantizer.go:130-180) / Int4Quantizer.Train
 // (int4.go:29-65).  min/max are order independent, so a column-parallel
 // two-stage reduction is exact.
-__global__ void __launch_bounds__(256) minmax_partial_kernel(const float *v, int64_t n, int64_t dim, int64_t rows_per_block,
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const float *v, int64_t n, int64_t dim, int64_t stride, int64_t rows_per_block,
                                                              float *pmin, float *pmax) {
     const int64_t d = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= dim) return;
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(256) minmax_partial_kernel(const float *v, int
     if (r1 > n) r1 = n;
     float mn = 3.402823466e+38f, mx = -3.402823466e+38f;
     for (int64_t r = r0; r < r1; r++) {
-        const float x = v[r * dim + d];
+        const float x = v[r * stride + d];
         if (x < mn) mn = x;
         if (x > mx) mx = x;
     }
@@ -40,6 +40,10 @@ __global__ void __launch_bounds__(256) minmax_final_kernel(const float *pmin, co
     maxs[d] = mx;
 }
 vg_status dev_minmax(const float *d_vecs, int64_t n, int64_t dim, float *d_mins, float *d_maxs, cudaStream_t st) {
+    return dev_minmax_strided(d_vecs, n, dim, dim, d_mins, d_maxs, st);
+}
+// min / max of the first `dim` columns of rows that are `stride` floats apart (a column slice of a wider matrix)
+vg_status dev_minmax_strided(const float *d_vecs, int64_t n, int64_t dim, int64_t stride, float *d_mins, float *d_maxs, cudaStream_t st) {
     int64_t parts = (n + 1023) / 1024;
     if (parts > 512) parts = 512;
     if (parts < 1) parts = 1;
@@ -49,7 +53,7 @@ vg_status dev_minmax(const float *d_vecs, int64_t n, int64_t dim, float *d_mins,
     VG_TRY(scratch.alloc((size_t)parts * dim * 8));
     float *pmin = scratch.as<float>(), *pmax = pmin + parts * dim;
     dim3 grid((unsigned)((dim + 255) / 256), (unsigned)parts);
-    minmax_partial_kernel<<<grid, 256, 0, st>>>(d_vecs, n, dim, rpb, pmin, pmax);
+    minmax_partial_kernel<<<grid, 256, 0, st>>>(d_vecs, n, dim, stride, rpb, pmin, pmax);
     VG_LAUNCHED();
     minmax_final_kernel<<<(unsigned)((dim + 255) / 256), 256, 0, st>>>(pmin, pmax, parts, dim, d_mins, d_maxs);
     VG_LAUNCHED();

@@ -4,6 +4,7 @@
 
 namespace vg {
 vg_status dev_minmax(const float *d_vecs, int64_t n, int64_t dim, float *d_mins, float *d_maxs, cudaStream_t st);
+vg_status dev_minmax_strided(const float *d_vecs, int64_t n, int64_t dim, int64_t stride, float *d_mins, float *d_maxs, cudaStream_t st);
 vg_status dev_sq8_encode(const float *d_vecs, int64_t n, int64_t dim, const float *d_mins, const float *d_maxs,
                          const float *d_scales, uint8_t *d_codes, cudaStream_t st);
 vg_status dev_sq8_decode(const uint8_t *d_codes, int64_t n, int64_t dim, const float *d_mins, const float *d_inv, float *d_vecs,

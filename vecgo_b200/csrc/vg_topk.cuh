@@ -24,7 +24,10 @@ struct TopK {
     unsigned long long *keys;  // [nq_slots][C]
     unsigned long long *tau;   // [nq_slots]
     int *cnt;                  // [nq_slots]
-    int *flag;                 // [1] set when some buffer passed the trigger
+    int *flag;                 // set when some buffer passed the trigger.  TWO flags in turn (flag / flag_next swap at every
+    int *flag_next;            // topk_block_maintain): a thread that has already read "no compaction" and runs ahead into
+                               // the next tile's offers must not raise the flag a slower thread is still about to read —
+                               // that thread would enter the compaction (and its barriers) alone (racecheck found this)
     int C;                     // capacity per query, power of two
     int k;
 };
@@ -47,6 +50,7 @@ __device__ __forceinline__ TopK topk_carve(unsigned char *smem, int slots, int C
     t.tau = t.keys + (size_t)slots * C;
     t.cnt = reinterpret_cast<int *>(t.tau + slots);
     t.flag = t.cnt + slots;
+    t.flag_next = t.flag + 1;
     t.C = C;
     t.k = k;
     return t;
@@ -57,7 +61,10 @@ __device__ __forceinline__ void topk_init(const TopK &t, int slots, int tid, int
         t.tau[i] = VG_KEY_EMPTY;
         t.cnt[i] = 0;
     }
-    if (tid == 0) *t.flag = 0;
+    if (tid == 0) {
+        t.flag[0] = 0;
+        t.flag[1] = 0;
+    }
 }
 
 // Offer one candidate.  `trigger`: request a compaction once count exceeds it.
@@ -107,14 +114,16 @@ __device__ __forceinline__ void topk_compact_warp(const TopK &t, int slot, int l
 }
 
 // Block-wide: after a __syncthreads(), compact every slot if any producer asked.
-// Must be called by all threads of the block.
-__device__ __forceinline__ void topk_block_maintain(const TopK &t, int slots, int tid, int nthreads) {
-    if (*t.flag) {
+// Must be called by all threads of the block, the same number of times (the two flags alternate per call).
+__device__ __forceinline__ void topk_block_maintain(TopK &t, int slots, int tid, int nthreads) {
+    int *cur = t.flag;
+    t.flag = t.flag_next;   // offers of the next tile raise the OTHER flag
+    t.flag_next = cur;
+    if (*cur) {
         int warp = tid >> 5, lane = tid & 31, nw = nthreads >> 5;
         for (int s = warp; s < slots; s += nw) topk_compact_warp(t, s, lane, false);
         __syncthreads();
-        if (tid == 0) *t.flag = 0;
-        __syncthreads();
+        if (tid == 0) *cur = 0;   // not raised again before the barrier that ends the tile after next
     }
 }
 

@@ -40,6 +40,60 @@ def exchange_topk(rows, scores, group=None):
     return all_rows.view(world, nq, k), all_scores.view(world, nq, k)
 
 
+def pq_train_sharded(d_vecs, n: int, dim: int, m: int, k: int, iters: int, seed: int, codebooks, scales, offsets, centroids=None,
+                     group=None):
+    """ProductQuantizer.Train across GPUs (pq.go:68-143): the reference trains every subspace in its own goroutine
+    (pq.go:79-140) — they are independent — so rank r trains subspaces shard_range(m, r, W) of the SAME training set
+    (d_vecs: CUDA float32 [n, dim], replicated) and the slices are all-gathered: codebooks, scales and offsets are
+    bit-identical to the single-GPU training.  Outputs are the caller's numpy arrays (codebooks int8 [m*k*ds], scales /
+    offsets float32 [m], optional centroids float32 [m, k, ds]), filled on every rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from . import _lib as L
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    ds = dim // m
+    lo, hi = shard_range(m, rank, world)
+    g = hi - lo
+    cb = np.zeros(max(g, 1) * k * ds, np.int8)
+    sc, of = np.zeros(max(g, 1), np.float32), np.zeros(max(g, 1), np.float32)
+    cent = np.zeros((max(g, 1), k, ds), np.float32)
+    if d_vecs.is_cuda:
+        L.call("vg_set_stream", torch.cuda.current_stream(d_vecs.device).cuda_stream)
+    L.call("vg_pq_train_range_dev", d_vecs.data_ptr(), n, dim, m, k, iters, seed, lo, hi, L.ptr(cb, L.i8p), L.ptr(sc, L.f32p),
+           L.ptr(of, L.f32p), L.ptr(cent, L.f32p))
+    if world == 1:
+        parts = [(lo, hi, cb, sc, of, cent)]
+    elif m % world == 0:
+        # equal slices: ONE all-gather of the packed bytes (codebook | scales | offsets | float32 centroids)
+        blob = np.concatenate([cb.view(np.uint8), sc.view(np.uint8), of.view(np.uint8), cent.reshape(-1).view(np.uint8)])
+        mine = torch.from_numpy(blob).to(d_vecs.device)
+        allb = torch.empty((world, blob.size), dtype=torch.uint8, device=d_vecs.device)
+        dist.all_gather_into_tensor(allb.view(-1), mine, group=group)
+        hb = allb.cpu().numpy()
+        parts = []
+        n_cb = g * k * ds
+        for r in range(world):
+            b = hb[r]
+            parts.append((r * g, (r + 1) * g, b[:n_cb].view(np.int8), b[n_cb:n_cb + 4 * g].view(np.float32),
+                          b[n_cb + 4 * g:n_cb + 8 * g].view(np.float32), b[n_cb + 8 * g:].view(np.float32).reshape(g, k, ds)))
+    else:
+        objs = [None] * world
+        dist.all_gather_object(objs, (lo, hi, cb, sc, of, cent), group=group)
+        parts = objs
+    for lo_, hi_, cb_, sc_, of_, cent_ in parts:
+        if hi_ <= lo_:
+            continue
+        codebooks[lo_ * k * ds:hi_ * k * ds] = cb_[:(hi_ - lo_) * k * ds]
+        scales[lo_:hi_] = sc_[:hi_ - lo_]
+        offsets[lo_:hi_] = of_[:hi_ - lo_]
+        if centroids is not None:
+            centroids[lo_:hi_] = cent_[:hi_ - lo_]
+
+
 EMPTY_ROW = 0xFFFFFFFF
 
 
