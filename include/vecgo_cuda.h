@@ -350,6 +350,13 @@ vg_status vg_index_fetch_ids(vg_index_t idx, const uint32_t *h_rows, int64_t n, 
  * with row 0xFFFFFFFF are empty. */
 vg_status vg_topk_merge_dev(const uint32_t *d_rows, const float *d_scores, int64_t lists, int64_t nq, int64_t k_in,
                             int32_t descending, int64_t k_out, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
+/* Packed exchange format of the sharded search: one sortable 8-byte key per candidate ((score under the heap order) << 32
+ * | row; empty = all ones).  vg_topk_pack_dev turns a shard's [nq][k] (rows, scores) into keys; the all-gather then
+ * moves ONE buffer per rank, and vg_topk_merge_keys_dev merges the gathered [lists][nq][k_in] keys without a
+ * conversion pass. */
+vg_status vg_topk_pack_dev(const uint32_t *d_rows, const float *d_scores, int64_t n, int32_t descending, uint64_t *d_keys);
+vg_status vg_topk_merge_keys_dev(const uint64_t *d_keys, int64_t lists, int64_t nq, int64_t k_in, int32_t descending, int64_t k_out,
+                                 uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
 vg_status vg_topk_merge(const uint32_t *h_rows, const float *h_scores, int64_t lists, int64_t nq, int64_t k_in,
                         int32_t descending, int64_t k_out, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
 

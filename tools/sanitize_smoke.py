@@ -59,7 +59,7 @@ if "quant" in which:
 if "misc" in which:
     rows = rng.integers(0, 1000, (3, 4, 8)).astype(np.uint32)
     vg.index.topk_merge(rows, rng.random((3, 4, 8), dtype=F), False, 8)
-    vg.simd.SquaredL2Batch(rng.random(33, dtype=F), rng.random((7, 33), dtype=F))
+    vg.simd.SquaredL2Batch(rng.random(33, dtype=F), rng.random((7, 33), dtype=F), 33)
     print("misc ok", flush=True)
 if "train" in which:
     v = rng.standard_normal((4096, 64)).astype(F)

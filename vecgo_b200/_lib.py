@@ -142,6 +142,8 @@ _SIGS = {
     "vg_flat_decode_header": [u8p, sz, C.POINTER(FlatHeader)],
     "vg_index_fetch_ids": [u64, u32p, i64, u64p],
     "vg_topk_merge_dev": [vp, vp, i64, i64, i64, i32, i64, vp, vp, vp],
+    "vg_topk_pack_dev": [vp, vp, i64, i32, vp],
+    "vg_topk_merge_keys_dev": [vp, i64, i64, i64, i32, i64, vp, vp, vp],
     "vg_topk_merge": [u32p, f32p, i64, i64, i64, i32, i64, u32p, f32p, i32p],
 }
 for _name, _args in _SIGS.items():

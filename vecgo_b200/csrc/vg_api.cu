@@ -1349,6 +1349,22 @@ vg_status vg_topk_merge_dev(const uint32_t *d_rows, const float *d_scores, int64
                               stream()));
     return _vg_call.finish();
 }
+// Packed exchange format of the sharded search (one 8-byte key per candidate): pack this shard's result, all-gather the
+// keys (ONE collective instead of one for rows and one for scores), merge the gathered [lists][nq][k_in] keys directly.
+vg_status vg_topk_pack_dev(const uint32_t *d_rows, const float *d_scores, int64_t n, int32_t descending, uint64_t *d_keys) {
+    VG_ENTER();
+    if (n < 0 || !d_keys) return fail(VG_ERR_INVALID, "bad pack shape");
+    VG_TRY(launch_pack_keys(d_rows, d_scores, n, descending != 0, reinterpret_cast<unsigned long long *>(d_keys), stream()));
+    return _vg_call.finish();
+}
+vg_status vg_topk_merge_keys_dev(const uint64_t *d_keys, int64_t lists, int64_t nq, int64_t k_in, int32_t descending, int64_t k_out,
+                                 uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts) {
+    VG_ENTER();
+    if (lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(VG_ERR_INVALID, "bad merge shape");
+    VG_TRY(launch_merge_keys(reinterpret_cast<const unsigned long long *>(d_keys), lists, nq, k_in, nq * k_in, k_in, descending != 0, k_out,
+                             d_out_rows, d_out_scores, d_out_counts, stream()));
+    return _vg_call.finish();
+}
 vg_status vg_topk_merge(const uint32_t *h_rows, const float *h_scores, int64_t lists, int64_t nq, int64_t k_in,
                         int32_t descending, int64_t k_out, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
     VG_ENTER();

@@ -997,8 +997,14 @@ vg_status tensor_map_2d(void *map, bool f16, const void *base, int64_t rows, int
 int64_t group_rows(int64_t rows, int kc) {
     // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
     // while the exact scan of kc*G rows per query stays ~1% of the GEMM's work
+    static int per_kc = -1;   // groups per candidate; VECGO_TC_GROUPS_PER_KC overrides (tuning / measurement)
+    if (per_kc < 0) {
+        const char *e = getenv("VECGO_TC_GROUPS_PER_KC");
+        const int v = e ? atoi(e) : 0;
+        per_kc = v >= 4 && v <= 4096 ? v : 128;
+    }
     int64_t G = 32;
-    while (G < 1024 && rows / (G * 2) >= 128ll * kc) G *= 2;  // <= 10 mantissa bits carry the row index
+    while (G < 1024 && rows / (G * 2) >= (int64_t)per_kc * kc) G *= 2;  // <= 10 mantissa bits carry the row index
     return G;
 }
 
@@ -1229,7 +1235,14 @@ static vg_status enqueue_once(const SearchIO &io, int kc, int32_t *d_fail, cudaS
     return VG_OK;  // the temporaries go back to the stream-ordered pool (freed in stream order)
 }
 
+void count_queries(uint64_t n) { g_queries.fetch_add(n); }
+
 vg_status enqueue(const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st) {
+    if (io.d_x16 && (io.q_stride == 0 || io.q_stride == io.dim) && fs::single_supported(io.dim, io.rows, io.nq, io.k)) {
+        VG_TRY(fs::single_enqueue(io, d_fail, st));
+        g_queries.fetch_add((uint64_t)io.nq);
+        return VG_OK;
+    }
     VG_TRY(enqueue_once(io, kc, d_fail, st));
     g_queries.fetch_add((uint64_t)io.nq);
     return VG_OK;

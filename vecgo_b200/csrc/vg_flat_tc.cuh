@@ -75,6 +75,15 @@ vg_status search(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaS
 vg_status enqueue(const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st);
 vg_status retry(const SearchIO &io, int kc, std::vector<int32_t> &failed, cudaStream_t st);
 
+// Single-launch search for short vectors (vg_flat_single.cu): phase 0 query preparation, sampled thresholds, threshold
+// filter, exact stage and certificate in ONE cooperative kernel with grid-wide barriers — no intermediate plane, no
+// host round trip.  dim <= 256, k <= 16, batches whose query tiles fit half the SM pairs.  VECGO_FLAT_SINGLE=0 disables.
+namespace fs {
+bool single_supported(int64_t dim, int64_t rows, int64_t nq, int64_t k);
+vg_status single_enqueue(const SearchIO &io, int32_t *d_fail, cudaStream_t st);
+}  // namespace fs
+void count_queries(uint64_t n);
+
 // Process-wide switch (default on; environment VECGO_FLAT_TC=0 turns it off) and counters.
 bool enabled();
 void set_enabled(bool on);

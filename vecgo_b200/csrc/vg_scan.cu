@@ -1105,9 +1105,18 @@ vg_status launch_merge_pairs(const uint32_t *d_rows_in, const float *d_scores_in
     pairs_to_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_rows_in, d_scores_in, n, descending ? 1 : 0,
                                                                       keys.as<unsigned long long>());
     VG_LAUNCHED();
-    VG_TRY(launch_merge_keys(keys.as<unsigned long long>(), lists, nq, k_in, nq * k_in, k_in, descending, k_out, d_rows, d_scores,
-                             d_counts, st));
-    VG_CUDA(cudaStreamSynchronize(st));  // keys is freed on return
+    // `keys` goes back to the stream-ordered pool when this returns: freed in stream order, no host wait
+    return launch_merge_keys(keys.as<unsigned long long>(), lists, nq, k_in, nq * k_in, k_in, descending, k_out, d_rows, d_scores,
+                             d_counts, st);
+}
+
+// Exchange format of the sharded search: one 8-byte sortable key per candidate (what the all-gather moves and the merge
+// reads directly): packing is one pass over the shard's [nq][k] result, merging needs no conversion pass.
+vg_status launch_pack_keys(const uint32_t *d_rows_in, const float *d_scores_in, int64_t n, bool descending, unsigned long long *d_keys,
+                           cudaStream_t st) {
+    if (n <= 0) return VG_OK;
+    pairs_to_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_rows_in, d_scores_in, n, descending ? 1 : 0, d_keys);
+    VG_LAUNCHED();
     return VG_OK;
 }
 

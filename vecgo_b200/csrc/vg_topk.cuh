@@ -162,4 +162,8 @@ vg_status launch_merge_pairs(const uint32_t *d_rows_in, const float *d_scores_in
                              bool descending, int64_t k_out, uint32_t *d_rows, float *d_scores, int32_t *d_counts,
                              cudaStream_t st);
 
+// (rows, scores) of a result -> sortable keys (row 0xFFFFFFFF -> empty key).
+vg_status launch_pack_keys(const uint32_t *d_rows_in, const float *d_scores_in, int64_t n, bool descending, unsigned long long *d_keys,
+                           cudaStream_t st);
+
 }  // namespace vg

@@ -154,6 +154,36 @@ class ShardedIndex:
                int(descending), k_out, orow.data_ptr(), osc.data_ptr(), ocnt.data_ptr())
         return orow, osc, ocnt
 
+    def _exchange_merge(self, rows, scores, counts, k_in: int, k_out: int, descending: bool):
+        """Per-shard best-first lists -> the global best k_out on every rank.  On the GPU the exchange is ONE all-gather
+        of 8-byte sortable keys (vg_topk_pack_dev) that vg_topk_merge_keys_dev merges directly; the two-tensor form
+        (exchange_topk + a merge callback) serves the CPU / gloo tests of the host logic."""
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        if world == 1 and k_in == k_out and self._merge_fn is None:
+            return rows, scores, counts
+        if self._merge_fn is not None or not rows.is_cuda:
+            all_rows, all_scores = exchange_topk(rows, scores, self.group)
+            return self._merge(all_rows, all_scores, k_in, k_out, descending)
+        nq, dev = rows.shape[0], rows.device
+        keys = torch.empty((nq, k_in), dtype=torch.int64, device=dev)
+        L.call("vg_topk_pack_dev", rows.data_ptr(), scores.data_ptr(), nq * k_in, int(descending), keys.data_ptr())
+        if world > 1:
+            allk = torch.empty((world * nq, k_in), dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(allk, keys, group=self.group)
+        else:
+            allk = keys
+        orow = torch.empty((nq, k_out), dtype=torch.int32, device=dev)
+        osc = torch.empty((nq, k_out), dtype=torch.float32, device=dev)
+        ocnt = torch.empty((nq,), dtype=torch.int32, device=dev)
+        L.call("vg_topk_merge_keys_dev", allk.data_ptr(), world, nq, k_in, int(descending), k_out, orow.data_ptr(), osc.data_ptr(),
+               ocnt.data_ptr())
+        return orow, osc, ocnt
+
     def search_rerank_dev(self, d_queries, nq: int, r: int, k: int):
         """Quantized scan + exact rerank across shards with the reference's semantics (engine/search.go:188-192,
         913-973): the GLOBAL approximate top-r is reranked, not each shard's own top-r, so the ids are identical
@@ -168,22 +198,17 @@ class ShardedIndex:
         scores = torch.empty((nq, r), dtype=torch.float32, device=dev)
         counts = torch.empty((nq,), dtype=torch.int32, device=dev)
         self.index.search_dev(d_queries.data_ptr(), nq, r, rows.data_ptr(), scores.data_ptr(), counts.data_ptr())
-        all_rows, all_scores = exchange_topk(rows, scores, self.group)
-        if all_rows.shape[0] > 1:
-            rows, scores, counts = self._merge(all_rows, all_scores, r, r, self.approx_descending)
+        rows, scores, counts = self._exchange_merge(rows, scores, counts, r, r, self.approx_descending)
         local, owned = owned_local_rows(rows, self.index.row_base, self.index.rows)
         exact = torch.empty((nq, r), dtype=torch.float32, device=dev)
         self.index.rerank_dev(d_queries.data_ptr(), nq, local.contiguous().data_ptr(), r, exact.data_ptr())
         mine = torch.where(owned, rows, torch.full_like(rows, -1))  # -1 = 0xFFFFFFFF: not scored here
-        all_rows, all_exact = exchange_topk(mine, exact, self.group)
-        return self._merge(all_rows, all_exact, r, k, self.descending)
+        return self._exchange_merge(mine, exact, counts, r, k, self.descending)
 
     def search_dev(self, d_queries, nq: int, k: int):
         """d_queries: CUDA float32 tensor [nq, dim] (replicated on every rank).
         Returns (rows int32-viewed-uint32 [nq,k], scores [nq,k], counts [nq]) — identical on all ranks."""
         import torch
-
-        from . import _lib as L
 
         self._bind_stream(d_queries)
         dev = d_queries.device
@@ -191,13 +216,4 @@ class ShardedIndex:
         scores = torch.empty((nq, k), dtype=torch.float32, device=dev)
         counts = torch.empty((nq,), dtype=torch.int32, device=dev)
         self.index.search_dev(d_queries.data_ptr(), nq, k, rows.data_ptr(), scores.data_ptr(), counts.data_ptr())
-        all_rows, all_scores = exchange_topk(rows, scores, self.group)
-        world = all_rows.shape[0]
-        if world == 1:
-            return rows, scores, counts
-        orow = torch.empty_like(rows)
-        osc = torch.empty_like(scores)
-        ocnt = torch.empty_like(counts)
-        L.call("vg_topk_merge_dev", all_rows.data_ptr(), all_scores.data_ptr(), world, nq, k, int(self.descending), k,
-               orow.data_ptr(), osc.data_ptr(), ocnt.data_ptr())
-        return orow, osc, ocnt
+        return self._exchange_merge(rows, scores, counts, k, k, self.descending)
