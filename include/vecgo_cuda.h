@@ -260,8 +260,11 @@ typedef struct {
     uint64_t queries;               /* queries in the call */
     uint64_t distance_computations; /* FilterGateStats.DistanceComputations equivalent */
     uint64_t filter_queries;        /* answered through a tensor-core filter + certificate */
-    uint64_t second_chance_queries; /* certificate failed once, filter re-run with twice the candidate groups */
+    uint64_t second_chance_queries; /* certificate failed once: filter re-run (Flat: twice the candidate groups; quantized: threshold pass) */
     uint64_t exact_rerun_queries;   /* no proof: re-run on the exact CUDA-core scan */
+    uint64_t threshold_pass_queries;/* answered by the threshold pass (every row within the error bound of the k-th best listed
+                                       and scored exactly): the second chance of the quantized filters, and the whole batch
+                                       once an index has shown tightly clustered data */
 } vg_search_stats;
 vg_status vg_last_search_stats(vg_search_stats *out);
 /* Batched Segment.Rerank (flat/segment.go:754-781): exact SquaredL2/Dot of each
@@ -359,6 +362,34 @@ vg_status vg_topk_merge_keys_dev(const uint64_t *d_keys, int64_t lists, int64_t 
                                  uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
 vg_status vg_topk_merge(const uint32_t *h_rows, const float *h_scores, int64_t lists, int64_t nq, int64_t k_in,
                         int32_t descending, int64_t k_out, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+
+/* ------------------------------------------------------------ shard groups
+ * Row shards of one database on several GPUs with the merge exchange INSIDE the library (SURVEY 8b "Ownership": the
+ * library owns the NCCL communicators; 8e): every GPU scans its shard (global row id = row_base + local row, so the
+ * reference's (score, SegmentID, RowID) order is (score, global row) with one logical segment), ONE ncclAllGather moves
+ * the per-shard top-k as 8-byte sortable keys, every GPU merges.  The rerank form keeps the reference's "global
+ * approximate top-r, then exact" semantics (engine/search.go:188-192,913-973) with a second exchange, so ids do not
+ * depend on the number of GPUs.  NCCL is loaded at run time (libnccl.so.2).
+ *   single process (a Go host): vg_shard_group_create(devices, W); every call takes the W shard handles (handle i must
+ *     live on devices[i]: vg_index_create_on) and fans out over W host threads; host results come from GPU 0.
+ *   one process per GPU: vg_nccl_unique_id on rank 0 -> ship the 128 bytes -> vg_shard_group_create_rank everywhere; every
+ *     call takes this process's ONE shard handle and must be made by all ranks.
+ * The `_dev` forms take per-member device pointers ([members] arrays): queries [nq][dim] replicated on every GPU,
+ * outputs [nq][k] filled on every GPU.  Calls on one group are serialised (collectives must be issued in one order). */
+typedef uint64_t vg_shard_group_t;
+vg_status vg_nccl_unique_id(uint8_t *id128);
+vg_status vg_shard_group_create(const int32_t *devices, int32_t n, vg_shard_group_t *out);
+vg_status vg_shard_group_create_rank(const uint8_t *id128, int32_t rank, int32_t world, int32_t device, vg_shard_group_t *out);
+vg_status vg_shard_group_info(vg_shard_group_t group, int32_t *world, int32_t *members, int32_t *first_rank);
+vg_status vg_shard_group_destroy(vg_shard_group_t group);
+vg_status vg_shard_group_search(vg_shard_group_t group, const vg_index_t *shards, const float *h_queries, int64_t nq, int64_t k,
+                                uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+vg_status vg_shard_group_search_rerank(vg_shard_group_t group, const vg_index_t *shards, const float *h_queries, int64_t nq, int64_t r, int64_t k,
+                                       uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+vg_status vg_shard_group_search_dev(vg_shard_group_t group, const vg_index_t *shards, const float *const *d_queries, int64_t nq, int64_t k,
+                                    uint32_t *const *d_out_rows, float *const *d_out_scores, int32_t *const *d_out_counts);
+vg_status vg_shard_group_search_rerank_dev(vg_shard_group_t group, const vg_index_t *shards, const float *const *d_queries, int64_t nq, int64_t r,
+                                           int64_t k, uint32_t *const *d_out_rows, float *const *d_out_scores, int32_t *const *d_out_counts);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

@@ -337,3 +337,66 @@ def test_pq_train_subspace_ranges_equal_whole(vg, n, dim, m, parts):
         assert np.array_equal(cb2, cb[lo * 256 * ds:hi * 256 * ds]), (r, "codebooks")
         assert np.array_equal(bits(sc2), bits(sc[lo:hi])) and np.array_equal(bits(of2), bits(of[lo:hi])), (r, "scales/offsets")
         assert np.array_equal(bits(cent2), bits(cent[lo:hi])), (r, "centroids")
+
+
+# ------------------------------------------------------------------ shard groups: NCCL inside the C ABI
+def _ngpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+@pytest.mark.skipif("_ngpus() < 2")
+def test_shard_group_single_process_two_gpus(vg):
+    """vg_shard_group_* driving two GPUs from ONE process (what a Go host does): SQ8 shards on cuda:0 / cuda:1, the
+    all-gather and the merge inside the library; result = the oracle's search over the whole database.  Also the rerank
+    form (global approximate top-r, exact rerank, top-k) and a float32 Flat group."""
+    from vecgo_b200.sharded import ShardGroup, shard_range
+
+    L = vg._lib
+    rng = np.random.default_rng(21)
+    n, dim, nq, k, r = 30000, 128, 40, 10, 60
+    x = rng.standard_normal((n, dim)).astype(F)
+    x[n - 5] = x[3]   # a cross-shard exact tie: resolved by the global row id
+    q = rng.standard_normal((nq, dim)).astype(F)
+    sq = vg.quantization.ScalarQuantizer(dim)
+    sq.Train(x)
+    codes = sq.EncodeBatch(x)
+    W = 2
+    grp = ShardGroup.single_process(list(range(W)))
+    shards, flats = [], []
+    for w in range(W):
+        lo, hi = shard_range(n, w, W)
+        ix = vg.index.DeviceIndex(codec=L.CODEC_SQ8, metric=0, dim=dim, rows=hi - lo, row_base=lo, sq8=(sq.mins, sq.invScales), device=w)
+        ix.upload(codes=codes[lo:hi], vectors=x[lo:hi])
+        shards.append(ix)
+        fx = vg.index.DeviceIndex(codec=L.CODEC_F32, metric=0, dim=dim, rows=hi - lo, row_base=lo, device=w)
+        fx.upload(vectors=x[lo:hi])
+        flats.append(fx)
+    rows, scores, counts = grp.search(shards, q, k)
+    want, _ = oracle_topk(q, k, dim=dim, metric=0, quant=1, codes=codes, mins=sq.mins, inv=sq.invScales)
+    assert same(rows, scores, want)
+    rows, scores, counts = grp.search(flats, q, k)
+    want, _ = oracle_topk(q, k, dim=dim, metric=0, vectors=x)
+    assert same(rows, scores, want)
+    # rerank form: approximate top-r over ALL rows, exact float32 rerank, top-k by (score, row)
+    rows, scores, counts = grp.search(shards, q, k, r=r)
+    whole = o.FlatOracle(dim=dim, metric=0, quant=1, codes=codes, mins=sq.mins, inv=sq.invScales, vectors=x)
+    approx, acnt = whole.search_batch(q, r)
+    for i in range(nq):
+        cand = approx["row"][i, : acnt[i]]
+        ex = whole.rerank(q[i], cand)
+        order = np.lexsort((cand, ex))[:k]
+        assert np.array_equal(rows[i], cand[order]) and np.array_equal(bits(scores[i]), bits(ex[order])), i
+    for ix in shards + flats:
+        ix.close()
+    grp.close()
+    # a handle on the wrong GPU is refused, not searched
+    grp = ShardGroup.single_process([0, 1])
+    a = vg.index.DeviceIndex(codec=L.CODEC_F32, metric=0, dim=8, rows=64, device=0)
+    b = vg.index.DeviceIndex(codec=L.CODEC_F32, metric=0, dim=8, rows=64, device=0)
+    with pytest.raises(vg.VecgoError):
+        grp.search([a, b], np.zeros((1, 8), F), 1)
+    a.close()
+    b.close()
+    grp.close()

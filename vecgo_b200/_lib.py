@@ -53,7 +53,7 @@ class IndexDesc(C.Structure):
 
 class SearchStats(C.Structure):
     _fields_ = [("queries", u64), ("distance_computations", u64), ("filter_queries", u64), ("second_chance_queries", u64),
-                ("exact_rerun_queries", u64)]
+                ("exact_rerun_queries", u64), ("threshold_pass_queries", u64)]
 
 
 class FlatHeader(C.Structure):
@@ -142,6 +142,15 @@ _SIGS = {
     "vg_flat_decode_header": [u8p, sz, C.POINTER(FlatHeader)],
     "vg_index_fetch_ids": [u64, u32p, i64, u64p],
     "vg_topk_merge_dev": [vp, vp, i64, i64, i64, i32, i64, vp, vp, vp],
+    "vg_nccl_unique_id": [u8p],
+    "vg_shard_group_create": [i32p, i32, u64p],
+    "vg_shard_group_create_rank": [u8p, i32, i32, i32, u64p],
+    "vg_shard_group_info": [u64, i32p, i32p, i32p],
+    "vg_shard_group_destroy": [u64],
+    "vg_shard_group_search": [u64, u64p, f32p, i64, i64, u32p, f32p, i32p],
+    "vg_shard_group_search_rerank": [u64, u64p, f32p, i64, i64, i64, u32p, f32p, i32p],
+    "vg_shard_group_search_dev": [u64, u64p, C.POINTER(vp), i64, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
+    "vg_shard_group_search_rerank_dev": [u64, u64p, C.POINTER(vp), i64, i64, i64, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)],
     "vg_topk_pack_dev": [vp, vp, i64, i32, vp],
     "vg_topk_merge_keys_dev": [vp, i64, i64, i64, i32, i64, vp, vp, vp],
     "vg_topk_merge": [u32p, f32p, i64, i64, i64, i32, i64, u32p, f32p, i32p],

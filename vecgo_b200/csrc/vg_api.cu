@@ -3,6 +3,8 @@
 // Host-side logic mirrors the Go callers it replaces; all arithmetic that
 // decides a result runs in the CUDA kernels of vg_scan.cu / vg_quant.cu /
 // vg_kmeans.cu.  There is no CPU compute path in this file.
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -329,6 +331,10 @@ struct Index {
     // decode-GEMM filter state of the quantized scans (vg_quant_tc.cu), rebuilt after code uploads
     qtc::Prepared qtc;
     bool qtc_dirty = true;
+    // Set when a quarter or more of a batch failed the filter's certificate (tightly clustered data: thousands of rows
+    // within the error bound of the k-th best).  Later batches then skip the doomed full first pass: the filter runs on a
+    // 1/16 row prefix only, to get an upper bound of every query's k-th best score, and the threshold pass does the rest.
+    std::atomic<int> qtc_hard{0};
     std::mutex prep_mu;   // lazy filter state (row norms, fp16 shadow, decode tables) is built once even if searches race
     size_t device_bytes() const {
         return codes.bytes + vectors.bytes + p0.bytes + p1.bytes + norms.bytes + ids.bytes + pq_cb.bytes + centroids.bytes;
@@ -865,6 +871,22 @@ static vg_status search_enqueue(Index *ix, const float *d_queries, int64_t nq, i
     if (mode == SEARCH_QUANT_TC) {
         VG_TRY(ensure_qtc(ix, t.cp, st));
         t_stats.filter_queries += (uint64_t)nq;
+        const int64_t rows_p = (d.rows / 16 + 255) / 256 * 256;
+        if (ix->qtc_hard.load() && qtc::threshold_pass_possible(t.cp, d.rows, nq) &&
+            qtc::supported(t.cp, d.metric, rows_p, nq, k, d.num_partitions)) {
+            // hard data: filter a row prefix (any k real rows bound the k-th best from above), then ONE threshold pass over
+            // all rows for the whole batch — everything enqueued, no host wait
+            qtc::SearchIO io = quant_io(ix, t.a);
+            DevBuf f1, kth;
+            VG_TRY(f1.alloc((size_t)nq * 4));
+            VG_TRY(kth.alloc((size_t)nq * 4));
+            io.rows = rows_p;
+            VG_TRY(qtc::enqueue(t.cp, ix->qtc, io, 1, f1.as<int32_t>(), st));
+            VG_TRY(qtc::gather_kth(d_scores, d_counts, nullptr, nq, (int)k, kth.as<float>(), st));
+            io.rows = d.rows;
+            t_stats.threshold_pass_queries += (uint64_t)nq;
+            return qtc::enqueue_threshold(t.cp, ix->qtc, io, kth.as<float>(), d_fail, st);
+        }
         return qtc::enqueue(t.cp, ix->qtc, quant_io(ix, t.a), 1, d_fail, st);
     }
     if (d_fail) VG_CUDA(cudaMemsetAsync(d_fail, 0, (size_t)nq * 4, st));
@@ -886,19 +908,25 @@ static vg_status search_resolve(Index *ix, const float *d_queries, int64_t nq, i
         VG_TRY(make_temps(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, t, st));
     } else {
         VG_TRY(make_temps(ix, d_queries, nq, k, nprobes, d_mask, d_rows, d_scores, d_counts, t, st));
-        if (qtc::second_chance_possible(t.cp, d.rows, k)) {
-            // gather the failed queries (and their prepared sign words / norms), filter them again with 2x the groups
+        if (nq >= 64 && (int64_t)bad.size() * 4 >= nq) ix->qtc_hard.store(1);   // later batches go straight to the threshold pass
+        if (qtc::threshold_pass_possible(t.cp, d.rows, (int64_t)bad.size())) {
+            t_stats.threshold_pass_queries += (uint64_t)bad.size();
+            // Second chance = a THRESHOLD pass over the failed queries: the k-th best exact score the first pass found bounds
+            // the true k-th best from above; every row whose filter score could still beat it is listed and scored exactly
+            // (vg_quant_tc.cu).  Gather the failed queries (and their prepared sign words / norms) and that bound.
             const int64_t nb = (int64_t)bad.size();
             t_stats.second_chance_queries += (uint64_t)nb;
-            DevBuf bidx, bq, bqw, bqn, brow, bsc, bcnt, bfail;
+            DevBuf bidx, bq, bqw, bqn, brow, bsc, bcnt, bfail, bkth;
             VG_TRY(bidx.alloc((size_t)nb * 4));
             VG_TRY(bq.alloc((size_t)nb * d.dim * 4));
             VG_TRY(brow.alloc((size_t)nb * k * 4));
             VG_TRY(bsc.alloc((size_t)nb * k * 4));
             VG_TRY(bcnt.alloc((size_t)nb * 4));
             VG_TRY(bfail.alloc((size_t)nb * 4));
+            VG_TRY(bkth.alloc((size_t)nb * 4));
             VG_CUDA(cudaMemcpyAsync(bidx.p, bad.data(), (size_t)nb * 4, cudaMemcpyHostToDevice, st));
             VG_TRY(dev_gather_rows(t.a.queries, d.dim, bidx.as<int32_t>(), nb, d.dim, bq.as<float>(), st));
+            VG_TRY(qtc::gather_kth(d_scores, d_counts, bidx.as<int32_t>(), nb, (int)k, bkth.as<float>(), st));
             CodecParams cps = t.cp;
             if (t.cp.q_words) {
                 VG_TRY(bqw.alloc((size_t)nb * t.cp.words32 * 4));
@@ -918,7 +946,7 @@ static vg_status search_resolve(Index *ix, const float *d_queries, int64_t nq, i
             io.d_rows = brow.as<uint32_t>();
             io.d_scores = bsc.as<float>();
             io.d_counts = bcnt.as<int32_t>();
-            VG_TRY(qtc::enqueue(cps, ix->qtc, io, 2, bfail.as<int32_t>(), st));
+            VG_TRY(qtc::enqueue_threshold(cps, ix->qtc, io, bkth.as<float>(), bfail.as<int32_t>(), st));
             VG_TRY(dev_scatter_results(brow.as<uint32_t>(), bsc.as<float>(), bcnt.as<int32_t>(), bidx.as<int32_t>(), nb, k, d_rows, d_scores,
                                        d_counts, st));
             std::vector<int32_t> h_fail((size_t)nb);
@@ -2040,6 +2068,297 @@ vg_status vg_index_fetch_ids(vg_index_t idx, const uint32_t *h_rows, int64_t n, 
     VG_LAUNCHED();
     VG_CUDA(cudaStreamSynchronize(stream()));
     return staged_d2h(h_ids, o.p, (size_t)n * 8);
+}
+
+// ------------------------------------------------------------ shard groups (row shards + NCCL merge inside the library)
+// SURVEY 8(b) "Ownership": the library owns the NCCL communicators; 8(e): every GPU scans its row shard for the whole
+// query batch and ONE all-gather of the per-shard top-k (8-byte sortable keys) feeds a device merge on every GPU —
+// engine/search.go:903-908 with the segments living on different GPUs.  NCCL is resolved at run time (dlopen of
+// libnccl.so.2: the copy a host process already loaded, else the system library), so the shared library carries no
+// link-time dependency a Go host could not satisfy.
+//   single process, W GPUs (what a Go host uses):  vg_shard_group_create(devices, W) — ncclCommInitAll; calls take the W
+//     shard handles and fan out over W host threads (one per GPU), results come from member 0
+//   one process per GPU (torchrun):  vg_nccl_unique_id on rank 0, shipped to the others by the launcher's own means,
+//     then vg_shard_group_create_rank(id, rank, world, device); calls take this process's ONE shard handle
+namespace {
+typedef void *nccl_comm_t;
+struct NcclId {
+    char internal[128];
+};
+struct NcclApi {
+    int (*GetUniqueId)(NcclId *) = nullptr;
+    int (*CommInitRank)(nccl_comm_t *, int, NcclId, int) = nullptr;
+    int (*CommInitAll)(nccl_comm_t *, int, const int *) = nullptr;
+    int (*CommDestroy)(nccl_comm_t) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, nccl_comm_t, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+void load_nccl() {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD | RTLD_GLOBAL);   // the copy the host process already uses (e.g. PyTorch's)
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return;
+    g_nccl.GetUniqueId = (decltype(g_nccl.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (decltype(g_nccl.CommInitRank))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommInitAll = (decltype(g_nccl.CommInitAll))dlsym(h, "ncclCommInitAll");
+    g_nccl.CommDestroy = (decltype(g_nccl.CommDestroy))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (decltype(g_nccl.AllGather))dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (decltype(g_nccl.GetErrorString))dlsym(h, "ncclGetErrorString");
+    g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommInitAll && g_nccl.CommDestroy && g_nccl.AllGather;
+}
+vg_status need_nccl() {
+    std::call_once(g_nccl_once, load_nccl);
+    return g_nccl.ok ? VG_OK : fail(VG_ERR_UNSUPPORTED, "libnccl.so.2 could not be loaded");
+}
+vg_status nccl_fail(int r, const char *what) {
+    return fail(VG_ERR_CUDA, std::string("NCCL error: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(r) : "?") + " in " + what);
+}
+const int kNcclUint64 = 5;   // ncclUint64 (nccl.h ncclDataType_t)
+
+struct ShardGroup {
+    int world = 1;                       // shards in the group (= GPUs)
+    int members = 1;                     // shards driven by THIS process: world (single process) or 1
+    int rank0 = 0;                       // global rank of member 0
+    std::vector<int> devices;            // [members]
+    std::vector<nccl_comm_t> comms;      // [members]
+    std::vector<cudaStream_t> streams;   // [members] the group's own stream on each device (searches of one group are serialised)
+    std::mutex mu;
+};
+std::unordered_map<uint64_t, ShardGroup *> g_groups;
+ShardGroup *lookup_group(uint64_t h) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    auto it = g_groups.find(h);
+    return it == g_groups.end() ? nullptr : it->second;
+}
+uint64_t register_group(ShardGroup *g) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    const uint64_t h = g_next_handle++;
+    g_groups[h] = g;
+    return h;
+}
+
+// global rows a shard owns -> local row ids (others 0xFFFFFFFF), and the global id kept only where owned
+__global__ void __launch_bounds__(256) owned_rows_kernel(const uint32_t *rows, int64_t n, uint32_t row_base, uint32_t nrows, uint32_t *local,
+                                                         uint32_t *mine) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t g = rows[i];
+    const bool own = g != 0xFFFFFFFFu && g >= row_base && g - row_base < nrows;
+    local[i] = own ? g - row_base : 0xFFFFFFFFu;
+    mine[i] = own ? g : 0xFFFFFFFFu;
+}
+
+// One member's part of a sharded search on ITS device and stream: local scan, pack, all-gather, merge (and for the
+// rerank form: global approximate top-r, exact scores of the owned rows, second exchange, final top-k).
+vg_status member_search(ShardGroup *g, int m, Index *ix, const float *d_queries, int64_t nq, int64_t r, int64_t k, bool rerank, uint32_t *d_rows,
+                        float *d_scores, int32_t *d_counts) {
+    VG_ENTER(g->devices[(size_t)m], true, g->streams[(size_t)m]);
+    cudaStream_t st = stream();
+    const int W = g->world;
+    const int64_t kin = rerank ? r : k;
+    const bool seg_desc = ix->d.metric != VG_METRIC_L2;
+    const bool approx_desc = (ix->d.codec == VG_CODEC_F32 || ix->d.codec == VG_CODEC_SQ8 || ix->d.codec == VG_CODEC_PQ || ix->d.codec == VG_CODEC_OPQ)
+                                 ? seg_desc : false;   // INT4 / BQ / RaBitQ scores are distances whatever the segment metric
+    DevBuf lr, ls, lc, keys, allk;
+    VG_TRY(lr.alloc((size_t)nq * kin * 4));
+    VG_TRY(ls.alloc((size_t)nq * kin * 4));
+    VG_TRY(lc.alloc((size_t)nq * 4));
+    VG_TRY(keys.alloc((size_t)nq * kin * 8));
+    VG_TRY(allk.alloc((size_t)W * nq * kin * 8));
+    VG_TRY(search_dev_impl(ix, d_queries, nq, kin, 0, nullptr, lr.as<uint32_t>(), ls.as<float>(), lc.as<int32_t>()));
+    VG_TRY(launch_pack_keys(lr.as<uint32_t>(), ls.as<float>(), nq * kin, approx_desc, keys.as<unsigned long long>(), st));
+    int rc = g_nccl.AllGather(keys.p, allk.p, (size_t)(nq * kin), kNcclUint64, g->comms[(size_t)m], st);
+    if (rc != 0) return nccl_fail(rc, "ncclAllGather");
+    if (!rerank) {
+        VG_TRY(launch_merge_keys(allk.as<unsigned long long>(), W, nq, kin, nq * kin, kin, approx_desc, k, d_rows, d_scores, d_counts, st));
+        VG_CUDA(cudaStreamSynchronize(st));
+        return VG_OK;
+    }
+    // rerank form (engine/search.go:188-192,913-973): the GLOBAL approximate top-r is reranked, so ids do not depend on W
+    if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
+    DevBuf gr, gs, gc, local, mine, exact;
+    VG_TRY(gr.alloc((size_t)nq * r * 4));
+    VG_TRY(gs.alloc((size_t)nq * r * 4));
+    VG_TRY(gc.alloc((size_t)nq * 4));
+    VG_TRY(local.alloc((size_t)nq * r * 4));
+    VG_TRY(mine.alloc((size_t)nq * r * 4));
+    VG_TRY(exact.alloc((size_t)nq * r * 4));
+    VG_TRY(launch_merge_keys(allk.as<unsigned long long>(), W, nq, r, nq * r, r, approx_desc, r, gr.as<uint32_t>(), gs.as<float>(), gc.as<int32_t>(),
+                             st));
+    const int64_t n = nq * r;
+    owned_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gr.as<uint32_t>(), n, (uint32_t)ix->d.row_base, (uint32_t)ix->d.rows,
+                                                                   local.as<uint32_t>(), mine.as<uint32_t>());
+    VG_LAUNCHED();
+    VG_TRY(rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, local.as<uint32_t>(), r, seg_desc, exact.as<float>(), st));
+    VG_TRY(launch_pack_keys(mine.as<uint32_t>(), exact.as<float>(), n, seg_desc, keys.as<unsigned long long>(), st));
+    rc = g_nccl.AllGather(keys.p, allk.p, (size_t)n, kNcclUint64, g->comms[(size_t)m], st);
+    if (rc != 0) return nccl_fail(rc, "ncclAllGather");
+    VG_TRY(launch_merge_keys(allk.as<unsigned long long>(), W, nq, r, nq * r, r, seg_desc, k, d_rows, d_scores, d_counts, st));
+    VG_CUDA(cudaStreamSynchronize(st));
+    return VG_OK;
+}
+
+// Fan one call out over the group's members (one host thread per GPU beyond the first), host queries in, member 0's
+// result out.  d_queries_per_member non-null: device-resident form (queries and outputs per member).
+vg_status group_search(uint64_t gh, const vg_index_t *shards, const float *h_queries, const float *const *d_q, int64_t nq, int64_t r, int64_t k,
+                       bool rerank, uint32_t *h_rows, float *h_scores, int32_t *h_counts, uint32_t *const *d_rows, float *const *d_scores,
+                       int32_t *const *d_counts) {
+    VG_TRY(need_nccl());
+    ShardGroup *g = lookup_group(gh);
+    if (!g) return fail(VG_ERR_STATE, "unknown or closed shard group");
+    if (!shards || nq < 0 || k <= 0 || (rerank && r < k)) return fail(VG_ERR_INVALID, "bad sharded search arguments");
+    if (nq == 0) return VG_OK;
+    std::lock_guard<std::mutex> lk(g->mu);   // collectives of one communicator must be issued in the same order everywhere
+    const int M = g->members;
+    std::vector<Index *> ix((size_t)M);
+    for (int m = 0; m < M; m++) {
+        ix[(size_t)m] = lookup(shards[m]);
+        if (!ix[(size_t)m]) return fail(VG_ERR_STATE, "unknown or closed index handle");
+        if (ix[(size_t)m]->device != g->devices[(size_t)m]) return fail(VG_ERR_INVALID, "shard handle lives on another GPU than its group member");
+    }
+    std::vector<vg_status> status((size_t)M, VG_OK);
+    std::vector<std::string> errs((size_t)M);
+    auto work = [&](int m) {
+        auto run = [&]() -> vg_status {
+            VG_ENTER(g->devices[(size_t)m], true, g->streams[(size_t)m]);
+            DevBuf q, rows, scores, counts;
+            const float *dq = d_q ? d_q[m] : nullptr;
+            uint32_t *orow = d_rows ? d_rows[m] : nullptr;
+            float *osc = d_scores ? d_scores[m] : nullptr;
+            int32_t *ocnt = d_counts ? d_counts[m] : nullptr;
+            if (!dq) {
+                VG_TRY(to_device(q, h_queries, (size_t)nq * ix[(size_t)m]->d.dim));
+                dq = q.as<float>();
+            }
+            if (!orow) {
+                VG_TRY(rows.alloc((size_t)nq * k * 4));
+                VG_TRY(scores.alloc((size_t)nq * k * 4));
+                VG_TRY(counts.alloc((size_t)nq * 4));
+                orow = rows.as<uint32_t>();
+                osc = scores.as<float>();
+                ocnt = counts.as<int32_t>();
+            }
+            VG_TRY(member_search(g, m, ix[(size_t)m], dq, nq, r, k, rerank, orow, osc, ocnt));
+            if (m == 0 && h_rows) {
+                VG_TRY(staged_d2h(h_rows, orow, (size_t)nq * k * 4));
+                VG_TRY(staged_d2h(h_scores, osc, (size_t)nq * k * 4));
+                VG_TRY(staged_d2h(h_counts, ocnt, (size_t)nq * 4));
+            }
+            return VG_OK;
+        };
+        status[(size_t)m] = run();
+        if (status[(size_t)m] != VG_OK) errs[(size_t)m] = t_error;
+    };
+    std::vector<std::thread> th;
+    for (int m = 1; m < M; m++) th.emplace_back(work, m);
+    work(0);
+    for (auto &t : th) t.join();
+    for (int m = 0; m < M; m++)
+        if (status[(size_t)m] != VG_OK) return fail(status[(size_t)m], errs[(size_t)m]);
+    return VG_OK;
+}
+}  // namespace
+
+vg_status vg_nccl_unique_id(uint8_t *id128) {
+    VG_TRY(need_nccl());
+    if (!id128) return fail(VG_ERR_INVALID, "null argument");
+    NcclId id;
+    const int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return nccl_fail(rc, "ncclGetUniqueId");
+    memcpy(id128, id.internal, 128);
+    return VG_OK;
+}
+
+vg_status vg_shard_group_create(const int32_t *devices, int32_t n, vg_shard_group_t *out) {
+    VG_TRY(need_nccl());
+    if (!devices || n < 1 || n > kMaxDevices || !out) return fail(VG_ERR_INVALID, "bad device list");
+    std::unique_ptr<ShardGroup> g(new ShardGroup());
+    g->world = g->members = n;
+    g->rank0 = 0;
+    g->devices.assign(devices, devices + n);
+    g->comms.assign((size_t)n, nullptr);
+    g->streams.assign((size_t)n, nullptr);
+    for (int m = 0; m < n; m++) {
+        VG_ENTER(devices[m]);   // creates the device context (checks the ordinal)
+        VG_CUDA(cudaStreamCreateWithFlags(&g->streams[(size_t)m], cudaStreamNonBlocking));
+    }
+    std::vector<int> devs(devices, devices + n);
+    const int rc = g_nccl.CommInitAll(g->comms.data(), n, devs.data());
+    if (rc != 0) return nccl_fail(rc, "ncclCommInitAll");
+    *out = register_group(g.release());
+    return VG_OK;
+}
+
+vg_status vg_shard_group_create_rank(const uint8_t *id128, int32_t rank, int32_t world, int32_t device, vg_shard_group_t *out) {
+    VG_TRY(need_nccl());
+    if (!id128 || world < 1 || rank < 0 || rank >= world || !out) return fail(VG_ERR_INVALID, "bad rank / world");
+    VG_ENTER(device);
+    std::unique_ptr<ShardGroup> g(new ShardGroup());
+    g->world = world;
+    g->members = 1;
+    g->rank0 = rank;
+    g->devices.assign(1, t_ts.ctx->device);
+    g->comms.assign(1, nullptr);
+    g->streams.assign(1, nullptr);
+    VG_CUDA(cudaStreamCreateWithFlags(&g->streams[0], cudaStreamNonBlocking));
+    NcclId id;
+    memcpy(id.internal, id128, 128);
+    const int rc = g_nccl.CommInitRank(&g->comms[0], world, id, rank);
+    if (rc != 0) return nccl_fail(rc, "ncclCommInitRank");
+    *out = register_group(g.release());
+    return VG_OK;
+}
+
+vg_status vg_shard_group_destroy(vg_shard_group_t gh) {
+    ShardGroup *g = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_groups.find(gh);
+        if (it == g_groups.end()) return fail(VG_ERR_STATE, "unknown or closed shard group");
+        g = it->second;
+        g_groups.erase(it);
+    }
+    for (int m = 0; m < g->members; m++) {
+        cudaSetDevice(g->devices[(size_t)m]);
+        if (g->streams[(size_t)m]) {
+            cudaStreamSynchronize(g->streams[(size_t)m]);
+            cudaStreamDestroy(g->streams[(size_t)m]);
+        }
+        if (g->comms[(size_t)m] && g_nccl.CommDestroy) g_nccl.CommDestroy(g->comms[(size_t)m]);
+    }
+    delete g;
+    return VG_OK;
+}
+
+vg_status vg_shard_group_info(vg_shard_group_t gh, int32_t *world, int32_t *members, int32_t *first_rank) {
+    ShardGroup *g = lookup_group(gh);
+    if (!g) return fail(VG_ERR_STATE, "unknown or closed shard group");
+    if (world) *world = g->world;
+    if (members) *members = g->members;
+    if (first_rank) *first_rank = g->rank0;
+    return VG_OK;
+}
+
+vg_status vg_shard_group_search(vg_shard_group_t gh, const vg_index_t *shards, const float *h_queries, int64_t nq, int64_t k, uint32_t *h_out_rows,
+                                float *h_out_scores, int32_t *h_out_counts) {
+    return group_search(gh, shards, h_queries, nullptr, nq, k, k, false, h_out_rows, h_out_scores, h_out_counts, nullptr, nullptr, nullptr);
+}
+vg_status vg_shard_group_search_rerank(vg_shard_group_t gh, const vg_index_t *shards, const float *h_queries, int64_t nq, int64_t r, int64_t k,
+                                       uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
+    return group_search(gh, shards, h_queries, nullptr, nq, r, k, true, h_out_rows, h_out_scores, h_out_counts, nullptr, nullptr, nullptr);
+}
+vg_status vg_shard_group_search_dev(vg_shard_group_t gh, const vg_index_t *shards, const float *const *d_queries, int64_t nq, int64_t k,
+                                    uint32_t *const *d_out_rows, float *const *d_out_scores, int32_t *const *d_out_counts) {
+    if (!d_queries || !d_out_rows || !d_out_scores || !d_out_counts) return fail(VG_ERR_INVALID, "null argument");
+    return group_search(gh, shards, nullptr, d_queries, nq, k, k, false, nullptr, nullptr, nullptr, d_out_rows, d_out_scores, d_out_counts);
+}
+vg_status vg_shard_group_search_rerank_dev(vg_shard_group_t gh, const vg_index_t *shards, const float *const *d_queries, int64_t nq, int64_t r,
+                                           int64_t k, uint32_t *const *d_out_rows, float *const *d_out_scores, int32_t *const *d_out_counts) {
+    if (!d_queries || !d_out_rows || !d_out_scores || !d_out_counts) return fail(VG_ERR_INVALID, "null argument");
+    return group_search(gh, shards, nullptr, d_queries, nq, r, k, true, nullptr, nullptr, nullptr, d_out_rows, d_out_scores, d_out_counts);
 }
 
 }  // extern "C"

@@ -1003,8 +1003,11 @@ int64_t group_rows(int64_t rows, int kc) {
         const int v = e ? atoi(e) : 0;
         per_kc = v >= 4 && v <= 4096 ? v : 128;
     }
+    // short segments (a shard of a multi-GPU database): half as many groups — the selection reads half the plane and the
+    // exact stage barely grows (measured on a 1.25M-row SQ8 shard, 10k queries: 16.4 -> 15.6 ms)
+    const int64_t want = (getenv("VECGO_TC_GROUPS_PER_KC") || rows > (4ll << 20)) ? per_kc : 64;
     int64_t G = 32;
-    while (G < 1024 && rows / (G * 2) >= (int64_t)per_kc * kc) G *= 2;  // <= 10 mantissa bits carry the row index
+    while (G < 1024 && rows / (G * 2) >= want * kc) G *= 2;  // <= 10 mantissa bits carry the row index
     return G;
 }
 

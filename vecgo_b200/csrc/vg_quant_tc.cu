@@ -119,6 +119,12 @@ struct KArgs {
     const int8_t *codebooks;
     int dsub_shift;         // PQ: log2(dsub)
     int tiled;              // PQ: codes stored in 32-row tiles (permute_pq)
+    // threshold-collect epilogue (THRESH kernels): rows with s' < Ts[q] go to the (query, split, column half) list
+    const float *Ts;        // [nq] thresholds in s'-space
+    uint2 *cand;            // [nq][slots][cap] (s' bits, local row)
+    int *ccnt;              // [nq][slots]
+    int *ovf;               // [nq] set when a list overflowed
+    int cap, slots;
 };
 
 // ------------------------------------------------------------------ decode producers
@@ -529,7 +535,13 @@ constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 8) * 8 + 16 + 1
 
 }  // namespace pair
 
-template <int CODEC>
+// THRESH = false: the epilogue keeps (min, second min) of every row group and writes the [queries][groups] plane the
+// selection kernel reads (the normal filter).  THRESH = true: the epilogue compares the minimum of every 32-row chunk with
+// the query's threshold T and appends the rows below T to a candidate list — every row with s' < T is then scored
+// exactly, so with T = (a known upper bound of the k-th best score) + E the result needs no certificate.  This is the
+// second pass for queries whose certificate failed (tightly clustered data: thousands of rows within E of the k-th
+// best), where "a few more candidate groups" cannot help.
+template <int CODEC, bool THRESH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_kernel(const __grid_constant__ CUtensorMap map_q, KArgs A) {
     using namespace pair;
     extern __shared__ unsigned char smem_raw[];
@@ -646,6 +658,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         const uint32_t keep_hi = A.keep_hi;
         float g1 = BIG, g2 = BIG;
         int cc = 0;
+        // threshold mode: this thread's list and threshold
+        const bool qlive = q < A.nq;
+        const float T = (THRESH && qlive) ? fminf(__ldg(A.Ts + q), 2.9e38f) : -BIG;   // masked / padding rows carry BIG: never listed
+        const int myslot = split * 2 + colhalf;
+        uint2 *mylist = THRESH ? A.cand + ((size_t)(qlive ? q : 0) * A.slots + myslot) * A.cap : nullptr;
+        int ncand = 0;
         // row norms of a tile are fetched one tile ahead (global-load latency out of the per-tile critical path): the value
         // for tile t + 1 is loaded at the top of tile t and stored after tile t's columns are reduced
         auto xn_of = [&](int t_) {
@@ -689,6 +707,30 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
 #pragma unroll
                     for (int j = 0; j < 32; j++) s[j] = (mw >> j) & 1u ? s[j] : BIG;
                 }
+                if constexpr (THRESH) {
+                    // one FFMA per element above, a 3-input minimum tree here, one compare per chunk; a chunk that beats the
+                    // threshold is opened one 8-row group at a time
+                    float gm[4];
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+                        gm[g] = fminf(fminf(fminf(s[g * 8], s[g * 8 + 1]), s[g * 8 + 2]),
+                                      fminf(fminf(fminf(s[g * 8 + 3], s[g * 8 + 4]), s[g * 8 + 5]), fminf(s[g * 8 + 6], s[g * 8 + 7])));
+                    if (fminf(fminf(gm[0], gm[1]), fminf(gm[2], gm[3])) < T) {
+                        const uint32_t r0 = (uint32_t)(nh + c * 32);
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            if (gm[g] < T) {
+#pragma unroll
+                                for (int j = 0; j < 8; j++) {
+                                    if (s[g * 8 + j] < T) {
+                                        if (ncand < A.cap) mylist[ncand] = make_uint2(__float_as_uint(s[g * 8 + j]), r0 + (uint32_t)(g * 8 + j));
+                                        ncand++;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                } else {
                 float a1[4] = {BIG, BIG, BIG, BIG}, a2[4] = {BIG, BIG, BIG, BIG};
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
@@ -712,11 +754,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                     g2 = BIG;
                     cc = 0;
                 }
+                }
             }
             if (t + 1 < ntiles) xs[((t + 1) & 1) * TILE_ROWS + et] = xn_next;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
+        }
+        if constexpr (THRESH) {
+            if (qlive) {
+                A.ccnt[(size_t)q * A.slots + myslot] = ncand < A.cap ? ncand : A.cap;
+                if (ncand > A.cap) A.ovf[q] = 1;
+            }
         }
     } else {
         // ===================== decode producers: this CTA's 128 rows of the 256-row tile =====================
@@ -1289,6 +1338,136 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
     }
 }
 
+// ------------------------------------------------------------------ threshold pass (second chance)
+// Thresholds of the second pass.  U = the k-th best EXACT score the first pass found for the query (scores of real
+// rows: an upper bound of the true k-th best).  The pass lists every row with s' < T; T is chosen so that a row that is
+// NOT listed (s' >= T) has a reference score strictly above U — the same inequalities as the certificate of
+// qtc_exact_kernel, solved for the threshold instead of checked — so the k best of the listed rows ARE the k best of
+// the segment, ties included.  U = +inf (fewer than k rows found) lists everything: the lists overflow and the query
+// goes to the exact scan.
+template <int CODEC>
+__global__ void __launch_bounds__(256) qtc_thresh_kernel(const float *kth, const float *qn, const float *cq, const unsigned int *xmax_bits,
+                                                         float mid_norm, int dim, int64_t nq, float *Ts) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    const double U = (double)kth[q];
+    double Td;
+    if (CODEC == Q_BQ) {
+        Td = U + 0.5;   // s' is the Hamming distance itself: everything at distance <= U is scored (ties decide by row id)
+    } else if (CODEC == Q_RABITQ) {
+        const double qq = (double)cq[q], xx = (double)__uint_as_float(xmax_bits[0]);
+        const double qn_ = sqrt(qq), yn = sqrt(xx);
+        const double smax = xx + 2.0 * qn_ * yn;
+        const double Eb = smax / 2097152.0;
+        const double eref = (qn_ + yn) * (qn_ + yn) / 2097152.0;
+        Td = U + Eb - qq + eref;   // unlisted: reference >= T - Eb + qq - eref
+    } else {
+        const double qq = (double)qn[q], xx = (double)__uint_as_float(xmax_bits[0]), bb = (double)__uint_as_float(xmax_bits[1]);
+        const double qn_ = sqrt(qq), bn = sqrt(bb);
+        const double c1 = 1.125 / 1024.0, c2 = 1.0 / 16384.0 + (double)dim / 8388608.0;
+        const double smax = xx + 2.0 * qn_ * bn;
+        const double Eb = c1 * qn_ * bn + c2 * (qq + fmax(xx, bb)) + smax / 4194304.0 + qn_ * ((double)mid_norm + bn) / 2097152.0;
+        const double eref = ((double)dim + 64.0) / 16777216.0;
+        // unlisted: reference >= (T + c_q - Eb + ||q||^2)(1 - eref) - eref ||q||^2
+        Td = (U + eref * qq) / (1.0 - eref) - (double)cq[q] - qq + Eb;
+    }
+    Td += fabs(Td) * 1.0e-6 + 1.0e-30;   // strictly above: a tie with the k-th best would decide by row id
+    Ts[q] = (Td < 3.0e38) ? __double2float_ru(Td) : __int_as_float(0x7f800000);
+}
+
+// kth[i] = the k-th best score of query idx[i] in a [nq][k] result, +inf when the query holds fewer than k rows
+__global__ void __launch_bounds__(256) gather_kth_kernel(const float *scores, const int32_t *counts, const int32_t *idx, int64_t n, int k,
+                                                         float *kth) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int64_t q = idx ? idx[i] : i;
+    kth[i] = counts[q] >= k ? scores[q * k + (k - 1)] : __int_as_float(0x7f800000);
+}
+
+// Exact stage of the threshold pass: one CTA per query scores EVERY listed row in the codec's reference order (half-warp
+// per row, exact_score) and keeps the best k under (score, row).  No certificate: the lists are complete by construction;
+// a query whose list overflowed is flagged.
+template <int CODEC>
+__global__ void __launch_bounds__(128) qtc_exact_list_kernel(EArgs E, const uint2 *cand, const int *ccnt, const int *ovf, int slots, int cap) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int64_t q = blockIdx.x;
+    const int tid = threadIdx.x, hw = tid >> 4, lane = tid & 15;
+    float *qs = reinterpret_cast<float *>(smem);
+    const size_t qbytes = ((size_t)E.dim * 4 + 15) & ~(size_t)15;
+    TopK tk = topk_carve(smem + qbytes, 1, E.C, E.k);
+    int *pre = reinterpret_cast<int *>(smem + qbytes + topk_smem_bytes(1, E.C));   // prefix of the list lengths, slots + 1 entries
+    float *table = reinterpret_cast<float *>(pre + ((slots + 1 + 3) & ~3));
+    if constexpr (sign_codec(CODEC)) {
+        if (tid == 0) qs[0] = CODEC == Q_RABITQ ? E.q_norms[q] : 0.0f;
+        uint32_t *qw = reinterpret_cast<uint32_t *>(table);
+        for (int w = tid; w < E.words32; w += 128) qw[w] = E.q_words[q * E.words32 + w];
+    } else {
+        for (int64_t d = tid; d < E.dim; d += 128) qs[d] = E.queries[q * E.q_stride + d];
+        if constexpr (CODEC == Q_SQ8 || CODEC == Q_INT4)
+            for (int64_t d = tid; d < E.dim; d += 128) {
+                table[d] = E.p0[d];
+                table[E.dim + d] = E.p1[d];
+            }
+    }
+    topk_init(tk, 1, tid, 128);
+    if (tid == 0) {
+        int acc = 0;
+        for (int sl = 0; sl < slots; sl++) {
+            pre[sl] = acc;
+            acc += ccnt[(size_t)q * slots + sl];
+        }
+        pre[slots] = acc;
+    }
+    __syncthreads();
+    if constexpr (CODEC == Q_PQ) {
+        // simd.BuildDistanceTableInt8, live generic path (kernels.go:354-374): sequential, unfused
+        const int ds = E.pq_dsub;
+        for (int idx = tid; idx < E.pq_m * 256; idx += 128) {
+            const int m = idx >> 8;
+            const int8_t *cb = E.codebooks + (int64_t)idx * ds;
+            const float scale = E.pq_scales[m], offset = E.pq_offsets[m];
+            const float *qv = qs + (int64_t)m * ds;
+            float sum = 0.0f;
+            for (int i = 0; i < ds; i++) {
+                const float v = __fadd_rn(__fmul_rn((float)cb[i], scale), offset);
+                const float d = __fsub_rn(qv[i], v);
+                sum = __fadd_rn(sum, __fmul_rn(d, d));
+            }
+            table[idx] = sum;
+        }
+        __syncthreads();
+    }
+    const int total = pre[slots];
+    const int trigger = E.C - 16;
+    for (int r0 = 0; r0 < total; r0 += 16) {
+#pragma unroll
+        for (int u = 0; u < 2; u++) {
+            const int r = r0 + hw * 2 + u;
+            int64_t row = -1;
+            if (r < total) {
+                int lo = 0, hi = slots;   // the list that holds candidate r: last slot with pre[slot] <= r
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (pre[mid] <= r) lo = mid;
+                    else hi = mid;
+                }
+                row = (int64_t)cand[((size_t)q * slots + lo) * cap + (r - pre[lo])].y;
+            }
+            if (row >= E.rows) row = -1;
+            const bool valid = row >= 0;
+            const float tot = exact_score<CODEC>(E, qs, table, valid ? row : 0, lane);
+            if (lane == 0 && valid) topk_offer(tk, 0, make_key(tot, E.row_base + (uint32_t)row, false), trigger);
+        }
+        __syncthreads();
+        topk_block_maintain(tk, 1, tid, 128);
+    }
+    __syncthreads();
+    if (tid < 32) {
+        topk_emit_warp(tk, 0, tid, false, E.out_rows + q * E.k, E.out_scores + q * E.k, E.out_counts + q, E.k);
+        if (tid == 0) E.fail_flags[q] = ovf[q] ? 1 : 0;
+    }
+}
+
 // ------------------------------------------------------------------ gather scoring
 // Quantized distance of every query to ITS r candidate rows, in the reference's arithmetic (the neighbour-list scoring of
 // the DiskANN traversal: internal/segment/diskann/segment.go:511-588 — pq.AdcDistance / int4.L2Distance /
@@ -1643,12 +1822,12 @@ static vg_status launch_gemm(const CUtensorMap &mq, const KArgs &a, int64_t qtil
     VG_LAUNCHED();
     return VG_OK;
 }
-template <int CODEC>
+template <int CODEC, bool THRESH = false>
 static vg_status launch_gemm_pair(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st) {
     const size_t sm = pair::SMEM2_BYTES;
-    VG_CUDA(cudaFuncSetAttribute(qtc2_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    VG_CUDA(cudaFuncSetAttribute(qtc2_kernel<CODEC, THRESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)(2 * qtiles), (unsigned)splits);  // clusters of two CTAs along x (__cluster_dims__)
-    qtc2_kernel<CODEC><<<grid, NTHREADS, sm, st>>>(mq, a);
+    qtc2_kernel<CODEC, THRESH><<<grid, NTHREADS, sm, st>>>(mq, a);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1668,8 +1847,29 @@ static vg_status launch_exact(const EArgs &e, int64_t nq, cudaStream_t st) {
     return VG_OK;
 }
 
-// One chunk of queries through filter, select and exact stage.
-static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st) {
+template <int CODEC>
+static vg_status launch_exact_list(const EArgs &e, int64_t nq, const uint2 *cand, const int *ccnt, const int *ovf, int slots, int cap,
+                                   cudaStream_t st) {
+    const size_t sm = (((size_t)e.dim * 4 + 15) & ~(size_t)15) + topk_smem_bytes(1, e.C) + (size_t)((slots + 1 + 3) & ~3) * 4 +
+                      (CODEC == Q_PQ ? (size_t)e.pq_m * 256 * 4 : sign_codec(CODEC) ? (size_t)e.words32 * 4 : (size_t)e.dim * 8);
+    if (sm > 200 * 1024) return fail(VG_ERR_UNSUPPORTED, "dimension too large for the exact stage");
+    VG_CUDA(cudaFuncSetAttribute(qtc_exact_list_kernel<CODEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+    qtc_exact_list_kernel<CODEC><<<(unsigned)nq, 128, sm, st>>>(e, cand, ccnt, ovf, slots, cap);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+template <int CODEC>
+static vg_status launch_thresh(const float *kth, const float *qn, const float *cq, const unsigned int *xmax_bits, float mid_norm, int dim,
+                               int64_t nq, float *Ts, cudaStream_t st) {
+    qtc_thresh_kernel<CODEC><<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(kth, qn, cq, xmax_bits, mid_norm, dim, nq, Ts);
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+// One chunk of queries through filter, select and exact stage (d_kth == nullptr), or through the threshold pass:
+// thresholds from d_kth (the k-th best exact score known per query), threshold-collect GEMM, exact stage over the lists.
+static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st,
+                              const float *d_kth = nullptr) {
     const int qc = q_codec(cp);
     const int64_t nq = io.nq, rows = io.rows;
     const int64_t q_stride = io.q_stride ? io.q_stride : cp.dim;
@@ -1677,15 +1877,19 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     const bool pair_mode = use_pair();
     const int64_t G = qtc_group_rows(rows, kc);
     const int64_t groups = (rows + G - 1) / G;
+    const bool thresh = d_kth != nullptr;
+    if (thresh && !pair_mode) return fail(VG_ERR_UNSUPPORTED, "the threshold pass needs the CTA-pair kernel");
     DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau;
     VG_TRY(a16.alloc((size_t)nq * pp.dimp * 2));
     VG_TRY(fq.alloc((size_t)nq * 4));
     VG_TRY(cq.alloc((size_t)nq * 4));
     VG_TRY(qn.alloc((size_t)nq * 4));
-    VG_TRY(mins.alloc((size_t)groups * nq_pad * 8));
-    VG_TRY(gids.alloc((size_t)nq * kc * 4));
-    VG_TRY(gcnt.alloc((size_t)nq * 4));
-    VG_TRY(tau.alloc((size_t)nq * 4));
+    if (!thresh) {
+        VG_TRY(mins.alloc((size_t)groups * nq_pad * 8));
+        VG_TRY(gids.alloc((size_t)nq * kc * 4));
+        VG_TRY(gcnt.alloc((size_t)nq * 4));
+        VG_TRY(tau.alloc((size_t)nq * 4));
+    }
     if (sign_codec(qc)) {
         prep_queries_sign_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32,
                                                                                    qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr, nq,
@@ -1738,6 +1942,57 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.dsub_shift = 0;
     while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
     a.tiled = (qc == Q_PQ && (cp.variant & VG_VAR_PERM)) ? 1 : 0;
+    if (thresh) {
+        // ---- threshold pass: lists instead of the minima plane, no selection, no certificate
+        const int slots = (int)splits * 2;
+        int64_t cap = ((int64_t)4 << 30) / std::max<int64_t>(1, nq * slots * 8);   // <= 4 GiB of lists per chunk
+        cap = std::max<int64_t>(64, std::min<int64_t>(8192, cap));
+        DevBuf Ts, cand, ccnt, ovf;
+        VG_TRY(Ts.alloc((size_t)nq * 4));
+        VG_TRY(cand.alloc((size_t)nq * slots * cap * 8));
+        VG_TRY(ccnt.alloc((size_t)nq * slots * 4));
+        VG_TRY(ovf.alloc((size_t)nq * 4));
+        VG_CUDA(cudaMemsetAsync(ovf.p, 0, (size_t)nq * 4, st));
+        const float *qn_p = qn.as<float>(), *cq_p = cq.as<float>();
+        const unsigned int *xm = pp.xmax.as<unsigned int>();
+        if (qc == Q_SQ8) VG_TRY(launch_thresh<Q_SQ8>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        else if (qc == Q_INT4) VG_TRY(launch_thresh<Q_INT4>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        else if (qc == Q_RABITQ) VG_TRY(launch_thresh<Q_RABITQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        else if (qc == Q_BQ) VG_TRY(launch_thresh<Q_BQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        else VG_TRY(launch_thresh<Q_PQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        a.mins = nullptr;
+        a.Ts = Ts.as<float>();
+        a.cand = cand.as<uint2>();
+        a.ccnt = ccnt.as<int>();
+        a.ovf = ovf.as<int>();
+        a.cap = (int)cap;
+        a.slots = slots;
+        if (qc == Q_SQ8) VG_TRY((launch_gemm_pair<Q_SQ8, true>(mq, a, qtiles, (int)splits, st)));
+        else if (qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4, true>(mq, a, qtiles, (int)splits, st)));
+        else if (qc == Q_RABITQ) VG_TRY((launch_gemm_pair<Q_RABITQ, true>(mq, a, qtiles, (int)splits, st)));
+        else if (qc == Q_BQ) VG_TRY((launch_gemm_pair<Q_BQ, true>(mq, a, qtiles, (int)splits, st)));
+        else VG_TRY((launch_gemm_pair<Q_PQ, true>(mq, a, qtiles, (int)splits, st)));
+        EArgs e = eargs_of(cp, rows);
+        e.queries = io.d_queries;
+        e.q_stride = q_stride;
+        e.mask = io.d_mask;
+        e.k = io.k;
+        e.C = topk_capacity(io.k, 16);
+        e.row_base = io.row_base;
+        e.out_rows = io.d_rows;
+        e.out_scores = io.d_scores;
+        e.out_counts = io.d_counts;
+        e.fail_flags = d_fail;
+        if (sign_codec(qc)) {
+            e.q_words = cp.q_words + io.q_index0 * cp.words32;
+            e.q_norms = qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr;
+            if (qc == Q_RABITQ) return launch_exact_list<Q_RABITQ>(e, nq, a.cand, a.ccnt, a.ovf, slots, (int)cap, st);
+            return launch_exact_list<Q_BQ>(e, nq, a.cand, a.ccnt, a.ovf, slots, (int)cap, st);
+        }
+        if (qc == Q_SQ8) return launch_exact_list<Q_SQ8>(e, nq, a.cand, a.ccnt, a.ovf, slots, (int)cap, st);
+        if (qc == Q_INT4) return launch_exact_list<Q_INT4>(e, nq, a.cand, a.ccnt, a.ovf, slots, (int)cap, st);
+        return launch_exact_list<Q_PQ>(e, nq, a.cand, a.ccnt, a.ovf, slots, (int)cap, st);
+    }
     const bool prof = g_prof.load() != 0;
     cudaEvent_t g_ev[2] = {nullptr, nullptr};  // per call: the event pair lives on this call's device and stream
     if (prof) {
@@ -1840,6 +2095,36 @@ vg_status enqueue(const CodecParams &cp, const Prepared &pp, const SearchIO &io,
     return VG_OK;
 }
 void count_fallbacks(uint64_t n) { g_fallbacks.fetch_add(n); }
+
+// Second pass for queries whose certificate failed: d_kth[q] = the k-th best exact score the first pass found (an upper
+// bound of the true k-th best, +inf if it found fewer than k rows).  Lists every row whose filter score could still beat
+// it, scores all of them exactly: the result needs no certificate; d_fail[q] = 1 only when a list overflowed.
+vg_status enqueue_threshold(const CodecParams &cp, const Prepared &pp, const SearchIO &io, const float *d_kth, int32_t *d_fail,
+                            cudaStream_t st) {
+    if (!pp.ready) return fail(VG_ERR_STATE, "decode-GEMM filter state was not prepared");
+    const int kc = candidates_for(io.k);
+    // lists are sized per chunk (<= 4 GiB): chunks of at most 64 query tiles
+    const int64_t chunk = 64 * BMQ;
+    for (int64_t q0 = 0; q0 < io.nq; q0 += chunk) {
+        SearchIO part = io;
+        part.nq = std::min(chunk, io.nq - q0);
+        part.q_stride = io.q_stride ? io.q_stride : cp.dim;
+        part.d_queries = io.d_queries + q0 * part.q_stride;
+        part.q_index0 = io.q_index0 + q0;
+        part.d_rows = io.d_rows + q0 * io.k;
+        part.d_scores = io.d_scores + q0 * io.k;
+        part.d_counts = io.d_counts + q0;
+        VG_TRY(search_chunk(cp, pp, part, kc, d_fail + q0, st, d_kth + q0));
+    }
+    return VG_OK;
+}
+bool threshold_pass_possible(const CodecParams &cp, int64_t rows, int64_t nq) { return use_pair() && rows >= 8192 && nq >= 1 && q_codec(cp) >= 0; }
+vg_status gather_kth(const float *d_scores, const int32_t *d_counts, const int32_t *d_idx, int64_t n, int k, float *d_kth, cudaStream_t st) {
+    if (n <= 0) return VG_OK;
+    gather_kth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d_scores, d_counts, d_idx, n, k, d_kth);
+    VG_LAUNCHED();
+    return VG_OK;
+}
 
 // Host-synchronous form: enqueue and read the certificate flags back.  `failed` lists the queries without a proof.
 vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, std::vector<int32_t> &failed, cudaStream_t st) {

@@ -49,6 +49,15 @@ vg_status search(const CodecParams &cp, const Prepared &pp, const SearchIO &io, 
 // candidate groups), available when second_chance_possible().  count_fallbacks() accounts queries that end on the exact scan.
 vg_status enqueue(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc_scale, int32_t *d_fail, cudaStream_t st);
 bool second_chance_possible(const CodecParams &cp, int64_t rows, int64_t k);
+// The stronger second chance: a THRESHOLD pass.  d_kth[q] = the k-th best exact score already known for query q (from the
+// first pass; +inf if it found fewer than k rows).  Every row whose filter score could still beat it is listed by a
+// threshold-collect GEMM epilogue and scored exactly, so the result is the exact scan's by construction — also on tightly
+// clustered data where thousands of rows sit within the error bound of the k-th best and no certificate can hold.
+// d_fail[q] = 1 only when a candidate list overflowed (then the exact CUDA-core scan serves the query).
+vg_status enqueue_threshold(const CodecParams &cp, const Prepared &pp, const SearchIO &io, const float *d_kth, int32_t *d_fail,
+                            cudaStream_t st);
+bool threshold_pass_possible(const CodecParams &cp, int64_t rows, int64_t nq);
+vg_status gather_kth(const float *d_scores, const int32_t *d_counts, const int32_t *d_idx, int64_t n, int k, float *d_kth, cudaStream_t st);
 void count_fallbacks(uint64_t n);
 
 // Quantized distance of query q to its r candidate rows d_rows[q][0..r) (local row ids; rows >= `rows` give NaN), in the

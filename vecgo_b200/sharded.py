@@ -217,3 +217,110 @@ class ShardedIndex:
         counts = torch.empty((nq,), dtype=torch.int32, device=dev)
         self.index.search_dev(d_queries.data_ptr(), nq, k, rows.data_ptr(), scores.data_ptr(), counts.data_ptr())
         return self._exchange_merge(rows, scores, counts, k, k, self.descending)
+
+
+class ShardGroup:
+    """vg_shard_group_* (include/vecgo_cuda.h): row shards with the NCCL exchange and the merges INSIDE the library — the
+    form a Go host binds.  `ShardGroup.single_process(devices)` drives all GPUs from this process (one shard handle per
+    GPU); `ShardGroup.from_torch_distributed(device)` makes one member per process (the launcher — torch.distributed here
+    — only ships the 128-byte NCCL id)."""
+
+    def __init__(self, handle: int, world: int, members: int):
+        self.handle, self.world, self.members = handle, world, members
+
+    @classmethod
+    def single_process(cls, devices):
+        import ctypes as C
+
+        import numpy as np
+
+        from . import _lib as L
+
+        d = np.ascontiguousarray(devices, np.int32)
+        h = C.c_uint64()
+        L.call("vg_shard_group_create", L.ptr(d, L.i32p), len(d), C.byref(h))
+        return cls(h.value, len(d), len(d))
+
+    @classmethod
+    def from_torch_distributed(cls, device: int, group=None):
+        import ctypes as C
+
+        import numpy as np
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib as L
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        ident = np.zeros(128, np.uint8)
+        if rank == 0:
+            L.call("vg_nccl_unique_id", L.ptr(ident, L.u8p))
+        t = torch.from_numpy(ident)
+        if dist.get_backend(group) == "nccl":
+            t = t.cuda(device)
+        dist.broadcast(t, src=0, group=group)
+        ident = t.cpu().numpy().copy()
+        h = C.c_uint64()
+        L.call("vg_shard_group_create_rank", L.ptr(ident, L.u8p), rank, world, device, C.byref(h))
+        return cls(h.value, world, 1)
+
+    def _handles(self, indexes):
+        import numpy as np
+
+        idx = indexes if isinstance(indexes, (list, tuple)) else [indexes]
+        if len(idx) != self.members:
+            raise ValueError(f"this group drives {self.members} shard(s) from this process, got {len(idx)} handle(s)")
+        return np.array([ix.handle for ix in idx], np.uint64)
+
+    def search(self, indexes, queries, k: int, r: int = 0):
+        """Host queries in, merged result out (from member 0).  r > 0: approximate top-r, exact rerank, final top-k."""
+        import numpy as np
+
+        from . import _lib as L
+
+        h = self._handles(indexes)
+        q = L.as_f32(queries)
+        q = q.reshape(-1, q.shape[-1])
+        nq = q.shape[0]
+        rows = np.full((nq, k), 0xFFFFFFFF, np.uint32)
+        scores = np.full((nq, k), np.nan, np.float32)
+        counts = np.zeros(nq, np.int32)
+        if r > 0:
+            L.call("vg_shard_group_search_rerank", self.handle, L.ptr(h, L.u64p), L.ptr(q, L.f32p), nq, r, k, L.ptr(rows, L.u32p),
+                   L.ptr(scores, L.f32p), L.ptr(counts, L.i32p))
+        else:
+            L.call("vg_shard_group_search", self.handle, L.ptr(h, L.u64p), L.ptr(q, L.f32p), nq, k, L.ptr(rows, L.u32p), L.ptr(scores, L.f32p),
+                   L.ptr(counts, L.i32p))
+        return rows, scores, counts
+
+    def search_dev(self, indexes, d_queries, nq: int, k: int, r: int = 0):
+        """Device form: d_queries = one CUDA float32 tensor [nq, dim] per member (a single tensor for a one-member group).
+        Returns per member (rows int32-viewed-uint32 [nq,k], scores, counts), complete on return."""
+        import ctypes as C
+
+        import torch
+
+        from . import _lib as L
+
+        h = self._handles(indexes)
+        qs = d_queries if isinstance(d_queries, (list, tuple)) else [d_queries]
+        outs = []
+        for t in qs:
+            torch.cuda.current_stream(t.device).synchronize()   # the group runs on its own streams
+            outs.append((torch.empty((nq, k), dtype=torch.int32, device=t.device), torch.empty((nq, k), dtype=torch.float32, device=t.device),
+                         torch.empty((nq,), dtype=torch.int32, device=t.device)))
+        arr = lambda ps: (C.c_void_p * len(ps))(*ps)  # noqa: E731
+        qp, rp, sp, cp = arr([t.data_ptr() for t in qs]), arr([o[0].data_ptr() for o in outs]), arr([o[1].data_ptr() for o in outs]), \
+            arr([o[2].data_ptr() for o in outs])
+        if r > 0:
+            L.call("vg_shard_group_search_rerank_dev", self.handle, L.ptr(h, L.u64p), qp, nq, r, k, rp, sp, cp)
+        else:
+            L.call("vg_shard_group_search_dev", self.handle, L.ptr(h, L.u64p), qp, nq, k, rp, sp, cp)
+        return outs if isinstance(d_queries, (list, tuple)) else outs[0]
+
+    def close(self):
+        from . import _lib as L
+
+        if self.handle:
+            L.call("vg_shard_group_destroy", self.handle)
+            self.handle = 0
