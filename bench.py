@@ -615,6 +615,33 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
             parity["merged"] = {"sample": f"{nmt} queries: {world} shards + NCCL all-gather + device merge vs ONE index holding all {rows} rows on rank 0",
                                 "ids_and_score_bits_identical": merged_parity}
 
+    # ---- the same sharded search with the exchange INSIDE the C ABI (vg_shard_group_*: what a Go host binds); torch.distributed
+    # only ships the 128-byte NCCL id.  Timed un-overlapped (the call returns when the merged result is complete).
+    abi_group = None
+    if world > 1:
+        try:
+            from vecgo_b200.sharded import ShardGroup
+
+            grp = ShardGroup.from_torch_distributed(env.local)
+            gr, gs_, gc = grp.search_dev(ix, queries, nq, k)
+            mr, ms_, mc = sh.search_dev(queries, nq, k)
+            i_ok, s_ok = same_results(torch, gr, gs_, mr, ms_)
+            ok = env.all_true(i_ok and s_ok)
+            for _ in range(2):
+                grp.search_dev(ix, queries, nq, k)
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                grp.search_dev(ix, queries, nq, k)
+            env.barrier()
+            dt = env.max_over_ranks((time.perf_counter() - t0) / 5)
+            grp.close()
+            abi_group = {"value": nq / dt, "unit": "queries/s", "ms_per_step": dt * 1e3, "identical_to_torch_distributed_path": ok,
+                         "note": "vg_shard_group_search_dev: per-shard scan, ONE ncclAllGather of 8-byte keys and the merge inside libvecgo_cuda "
+                                 "(NCCL via dlopen); wall clock around the call, no overlap between batches"}
+        except Exception as ex:  # noqa: BLE001
+            abi_group = {"error": repr(ex)}
+
     # ---- e2e: host buffers through the C ABI (vg_index_search), H2D/D2H inside the timed region
     e2e = None
     if headline:
@@ -712,6 +739,7 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
                                                 "(+ the host read of the certificate flags); exchange = pack to 8-byte keys + ONE NCCL all-gather + "
                                                 "device merge, timed alone in a separate loop"}
             res["merged_parity"] = merged_parity
+            res["c_abi_shard_group"] = abi_group
     ix.close()
     del db
     torch.cuda.empty_cache()
@@ -1221,7 +1249,7 @@ def run_ours(a):
             "recall_queries": head["recall_queries"], "parity": head["parity"], "search_ms": head["search_ms"],
             "scanned_gbs_per_gpu": head["scanned_gbs_per_gpu"], "tensor_core_filter": head["tensor_core_filter"],
         }
-        for key in ("step_breakdown_ms", "merged_parity"):
+        for key in ("step_breakdown_ms", "merged_parity", "c_abi_shard_group"):
             if key in head:
                 line[key] = head[key]
         line["configs"] = configs
