@@ -482,6 +482,126 @@ def scan_parity(env, db, queries_t, rows, k):
     return out, (r1, s1)
 
 
+def run_replicas(env, a, workload, whole, queries, rows, nq, k, steps, warmup, sh):
+    """SURVEY 8(e), "a database that fits one GPU (C1, C2)": every GPU holds the WHOLE database and answers 1/W of the query
+    batch; one all-gather (8-byte keys) gives every rank the whole batch's result.  Same total work as the row-sharded
+    mode, but the per-query stages (selection, exact stage) shrink with the number of GPUs instead of staying fixed."""
+    torch, dist, vg, L = env.torch, env.dist, env.vg, env.L
+    from vecgo_b200.sharded import shard_range
+
+    world, rank, dev = env.world, env.rank, env.dev
+    dim = a.dim
+    nql = (nq + world - 1) // world           # queries per rank (the last rank's slice is padded with repeats of its first query)
+    qlo = min(rank * nql, nq - 1)
+    idx = torch.clamp(torch.arange(qlo, qlo + nql, device=dev), max=nq - 1)
+    myq = queries[idx].contiguous()
+    main_stream = torch.cuda.current_stream()
+    comm_stream = torch.cuda.Stream()
+    bufs = [env.out_bufs(nql, k) for _ in range(2)]
+    keyb = [torch.empty((nql, k), dtype=torch.int64, device=dev) for _ in range(2)]
+    allk = [torch.empty((world * nql, k), dtype=torch.int64, device=dev) for _ in range(2)]
+    outs = [env.out_bufs(world * nql, k) for _ in range(2)]
+    pending = [None, None]
+
+    def one_step(i):
+        b = i & 1
+        r_, s_, c_ = bufs[b]
+        if pending[b] is not None:
+            main_stream.wait_event(pending[b])
+        whole.ix.search_dev(myq.data_ptr(), nql, k, r_.data_ptr(), s_.data_ptr(), c_.data_ptr())
+        ready = torch.cuda.Event()
+        ready.record(main_stream)
+        with torch.cuda.stream(comm_stream):
+            comm_stream.wait_event(ready)
+            L.call("vg_set_stream", comm_stream.cuda_stream)
+            try:
+                L.call("vg_topk_pack_dev", r_.data_ptr(), s_.data_ptr(), nql * k, 0, keyb[b].data_ptr())
+                dist.all_gather_into_tensor(allk[b], keyb[b])
+                orow, osc, ocnt = outs[b]
+                # one list per query: the "merge" only unpacks the gathered keys into (rows, scores, counts)
+                L.call("vg_topk_merge_keys_dev", allk[b].data_ptr(), 1, world * nql, k, 0, k, orow.data_ptr(), osc.data_ptr(), ocnt.data_ptr())
+            finally:
+                L.call("vg_set_stream", main_stream.cuda_stream)
+            done = torch.cuda.Event()
+            done.record(comm_stream)
+        pending[b] = done
+        return outs[b]
+
+    for i in range(warmup):
+        one_step(i)
+    main_stream.wait_stream(comm_stream)
+    env.barrier()
+    sampler = ClockSampler(env.local)
+    if rank == 0:
+        sampler.start()
+    qtc0 = env.qtc_counters(1)
+    launches0 = vg.launch_count()
+    scan_ms = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    res = None
+    for i in range(steps):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record()
+        res = one_step(i)
+        eb.record()
+        scan_ms.append((ea, eb))
+    main_stream.wait_stream(comm_stream)
+    e1.record()
+    env.barrier()
+    launches = vg.launch_count() - launches0
+    qtc1 = env.qtc_counters(0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = env.max_over_ranks(e0.elapsed_time(e1)) / steps
+    search_ms = env.max_over_ranks(float(np.mean([x.elapsed_time(y) for x, y in scan_ms])))
+    gl = int(qtc1[1])
+    gemm_ms = env.max_over_ranks(qtc1[0] / gl if gl else 0.0)
+    # parity: the gathered result of the whole batch equals the row-sharded, NCCL-merged result
+    mr, ms_, mc = sh.search_dev(queries, nq, k)
+    i_ok, s_ok = same_results(torch, res[0][:nq], res[1][:nq], mr, ms_)
+    same = env.all_true(i_ok and s_ok)
+    # e2e: every rank's query slice from ITS pinned host buffer, the whole batch's result back into pinned host memory
+    hq = myq.cpu().pin_memory()
+    dq = torch.empty_like(myq)
+    hout = (torch.empty((world * nql, k), dtype=torch.int32).pin_memory(), torch.empty((world * nql, k), dtype=torch.float32).pin_memory())
+
+    def e2e_step():
+        dq.copy_(hq, non_blocking=True)
+        r_, s_, c_ = bufs[0]
+        whole.ix.search_dev(dq.data_ptr(), nql, k, r_.data_ptr(), s_.data_ptr(), c_.data_ptr())
+        L.call("vg_topk_pack_dev", r_.data_ptr(), s_.data_ptr(), nql * k, 0, keyb[0].data_ptr())
+        dist.all_gather_into_tensor(allk[0], keyb[0])
+        orow, osc, ocnt = outs[0]
+        L.call("vg_topk_merge_keys_dev", allk[0].data_ptr(), 1, world * nql, k, 0, k, orow.data_ptr(), osc.data_ptr(), ocnt.data_ptr())
+        hout[0].copy_(orow, non_blocking=True)
+        hout[1].copy_(osc, non_blocking=True)
+        torch.cuda.synchronize()
+
+    for _ in range(max(1, warmup)):
+        e2e_step()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        e2e_step()
+    env.barrier()
+    e2e_s = env.max_over_ranks((time.perf_counter() - t0) / steps)
+    flops = 2.0 * nql * rows * dim * steps / max(gl, 1)
+    ach = flops / (gemm_ms / 1e3) / 1e12 if gl else 0.0
+    return {"value": nq / (ms_per_step / 1e3), "unit": "queries/s", "ms_per_step": ms_per_step, "queries_per_gpu": nql,
+            "step_breakdown_ms": {"step": ms_per_step, "per_rank_search": search_ms, "gemm_kernel": gemm_ms, "search_minus_gemm": search_ms - gemm_ms,
+                                  "note": "per-rank search of nq / W queries over ALL rows; the pack + all-gather + unpack of step i runs on a second "
+                                          "stream under the scan of step i + 1"},
+            "identical_to_row_sharded_result": same, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": ach, "peak": env.tf_sustained, "unit": "TFLOP/s", "frac": ach / env.tf_sustained,
+                         "frac_of_burst_peak": ach / env.tf_burst, "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gl,
+                         "share_of_step": gemm_ms * gl / steps / ms_per_step if gl else None, "algorithmic_flops_per_launch": flops,
+                         "kernel": f"qtc2_kernel<{workload.upper()}> (CTA pair, tcgen05.mma cta_group::2 kind::f16, M=256 x N=256, fp32 accumulate in TMEM)",
+                         "peak_source": env.peak_src, "traffic": None},
+            "e2e": {"value": nq / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": int(nql * dim * 4) * world, "d2h_bytes_per_step": int(world * nql * k * 8),
+                    "steps": steps, "note": "every rank copies ITS query slice from pinned host memory and reads the whole batch's result back into "
+                                            "pinned host memory, every step; bytes are the sum over ranks of the inputs and one copy of the result"}}
+
+
 def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
     torch, dist, vg, L = env.torch, env.dist, env.vg, env.L
     from vecgo_b200.sharded import ShardedIndex, exchange_topk, shard_range
@@ -597,23 +717,24 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
     # ---- parity
     parity, (mt_rows, mt_scores) = scan_parity(env, db, queries, nloc, k)
     merged_parity = None
+    replicas = None
     if world > 1:
-        # the NCCL-merged result of 512 queries against ONE index holding all rows on rank 0
+        # the NCCL-merged result of 512 queries against ONE index holding all rows (every rank holds one: it is also the
+        # replica of the query-sharded mode below)
         nmt = min(512, nq)
         mr, ms_, mc = sh.search_dev(queries[:nmt].contiguous(), nmt, k)
-        ok = True
+        whole = ScanDB(env, workload, rows, dim, 0, rows)
+        wr, ws, wc = env.out_bufs(nmt, k)
+        whole.ix.search_dev(queries.data_ptr(), nmt, k, wr.data_ptr(), ws.data_ptr(), wc.data_ptr())
+        i_ok, s_ok = same_results(torch, mr, ms_, wr, ws)
+        merged_parity = env.all_true(i_ok and s_ok)
         if rank == 0:
-            whole = ScanDB(env, workload, rows, dim, 0, rows)
-            wr, ws, wc = env.out_bufs(nmt, k)
-            whole.ix.search_dev(queries.data_ptr(), nmt, k, wr.data_ptr(), ws.data_ptr(), wc.data_ptr())
-            i_ok, s_ok = same_results(torch, mr, ms_, wr, ws)
-            ok = i_ok and s_ok
-            whole.ix.close()
-            del whole
-        merged_parity = env.all_true(ok)
-        if rank == 0:
-            parity["merged"] = {"sample": f"{nmt} queries: {world} shards + NCCL all-gather + device merge vs ONE index holding all {rows} rows on rank 0",
+            parity["merged"] = {"sample": f"{nmt} queries: {world} shards + NCCL all-gather + device merge vs ONE index holding all {rows} rows (on every rank)",
                                 "ids_and_score_bits_identical": merged_parity}
+        if headline:
+            replicas = run_replicas(env, a, workload, whole, queries, rows, nq, k, steps, warmup, sh)
+        whole.ix.close()
+        del whole
 
     # ---- the same sharded search with the exchange INSIDE the C ABI (vg_shard_group_*: what a Go host binds); torch.distributed
     # only ships the 128-byte NCCL id.  Timed un-overlapped (the call returns when the merged result is complete).
@@ -740,6 +861,7 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
                                                 "device merge, timed alone in a separate loop"}
             res["merged_parity"] = merged_parity
             res["c_abi_shard_group"] = abi_group
+            res["replicas"] = replicas
     ix.close()
     del db
     torch.cuda.empty_cache()
@@ -1239,17 +1361,34 @@ def run_ours(a):
             res["wall_s"] = time.time() - t0
             configs[{"c1": "C1", "c2b": "C2b", "c3": "C3", "c4": "C4", "c5": "C5"}[name]] = res
     if env.rank == 0:
+        cfg = workload_config(a)
+        rep = head.get("replicas") if env.world > 1 else None
+        if rep and not rep.get("error") and os.environ.get("BENCH_ROW_SHARDED_VALUE") != "1":
+            # N > 1: the headline database (7.68 GB of codes) fits one GPU, so the multi-GPU mode SURVEY 8(e) names for it is
+            # replicas + a query-sharded batch; the row-sharded run (what configs[2] / [3] need, C3 / C4 below) is kept beside it
+            row_sharded = {key: head[key] for key in ("value", "ms_per_step", "roofline", "e2e", "gpu_launches", "clocks", "step_breakdown_ms",
+                                                     "merged_parity", "c_abi_shard_group") if key in head}
+            row_sharded["sharding"] = cfg["sharding"]
+            cfg["sharding"] = (f"replicas: every GPU holds all {a.rows} rows and answers {rep['queries_per_gpu']} of the {a.queries} queries; ONE NCCL "
+                               "all-gather of 8-byte keys gives every rank the whole result (SURVEY 8e: a database that fits one GPU); the "
+                               "row-sharded run of the same batch is under `row_sharded`")
+            head = dict(head)
+            for key in ("value", "ms_per_step", "roofline", "e2e", "gpu_launches", "clocks"):
+                head[key] = rep[key]
+            head["step_breakdown_ms"] = rep["step_breakdown_ms"]
+            head["row_sharded"] = row_sharded
+            head["replicas_identical_to_row_sharded"] = rep["identical_to_row_sharded_result"]
         line = {
             "metric": head["metric"], "value": head["value"], "unit": "queries/s",
             "n_gpus": env.world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": head["dtype"], "arithmetic": head["arithmetic"],
-            "data": head["data"], "config": workload_config(a),
+            "data": head["data"], "config": cfg,
             "roofline": head["roofline"], "cpu_baseline": head["cpu_baseline"], "e2e": head["e2e"],
             "gpu_launches": head["gpu_launches"], "clocks": head["clocks"], "recall_at_10": head["recall_at_10"],
             "recall_queries": head["recall_queries"], "parity": head["parity"], "search_ms": head["search_ms"],
             "scanned_gbs_per_gpu": head["scanned_gbs_per_gpu"], "tensor_core_filter": head["tensor_core_filter"],
         }
-        for key in ("step_breakdown_ms", "merged_parity", "c_abi_shard_group"):
+        for key in ("step_breakdown_ms", "merged_parity", "c_abi_shard_group", "row_sharded", "replicas_identical_to_row_sharded"):
             if key in head:
                 line[key] = head[key]
         line["configs"] = configs
