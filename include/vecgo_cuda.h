@@ -226,6 +226,12 @@ vg_status vg_index_device(vg_index_t idx, int32_t *device);
 vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h_codes, const float *h_vectors);
 /* Fill rows from device memory instead (d_codes / d_vectors already resident). */
 vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const void *d_codes, const float *d_vectors);
+/* Rerank source in HOST memory: float32 rows [rows][dim] (e.g. the mmap'd vector section of the segment) that do not fit
+ * next to the codes in HBM (100M x 1536-d = 614 GB).  The library page-locks and maps the region (or uses it as is when
+ * the caller already page-locked it); vg_index_rerank* / vg_index_search_rerank / the shard-group rerank then gather the
+ * candidate rows over the host link — same arithmetic and bits as the device-resident Segment.Rerank
+ * (flat/segment.go:754-781).  Quantized indexes only; the region must stay valid and unchanged until vg_index_close. */
+vg_status vg_index_set_host_vectors(vg_index_t idx, const float *h_vectors, int64_t rows);
 vg_status vg_index_close(vg_index_t idx);
 vg_status vg_index_info(vg_index_t idx, int64_t *rows, int64_t *dim, int64_t *code_bytes_per_row, int64_t *device_bytes);
 
@@ -317,7 +323,7 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
                                 float *h_tau, int64_t *group_rows);
 
 /* Tensor-core filter of the quantized scans (csrc/vg_quant_tc.cu).  vg_index_search / vg_index_search_dev on an
- * SQ8 / INT4 / PQ / OPQ index (L2, no IVF partitions, dim % 64 == 0, k <= 128, batches of >= 16 queries over >= 8192
+ * SQ8 / INT4 / PQ / OPQ index (L2, no IVF partitions, dim % 64 == 0, k <= 1024, batches of >= 16 queries over >= 8192
  * rows) run simd.Sq8uL2BatchPerDimension / simd.Int4L2DistanceBatch / simd.PqAdcLookup
  * (internal/segment/flat/segment.go:543-552,603-611) as a tcgen05 fp16 GEMM over codes that are decoded inside the
  * kernel; the candidates are re-scored in the reference's exact float32 order and a certificate proves the result

@@ -400,3 +400,40 @@ def test_shard_group_single_process_two_gpus(vg):
     a.close()
     b.close()
     grp.close()
+
+
+def test_rerank_from_host_resident_vectors(vg):
+    """vg_index_set_host_vectors: the float32 rows stay in host memory (pageable numpy array, page-locked by the library;
+    and a region the caller page-locked itself); rerank / search_rerank give the same bits as the device-resident path."""
+    import torch
+
+    L = vg._lib
+    rng = np.random.default_rng(31)
+    n, dim, nq, r, k = 20000, 96, 24, 50, 10
+    x = rng.standard_normal((n, dim)).astype(F)
+    q = rng.standard_normal((nq, dim)).astype(F)
+    sq = vg.quantization.ScalarQuantizer(dim)
+    sq.Train(x)
+    codes = sq.EncodeBatch(x)
+    with vg.index.DeviceIndex(codec=L.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(sq.mins, sq.invScales)) as dev_ix:
+        dev_ix.upload(codes=codes, vectors=x)
+        rows, _, _ = dev_ix.search(q, r)
+        want_scores = dev_ix.rerank(q, rows)
+        want = dev_ix.search_rerank(q, r, k)
+    pinned = torch.from_numpy(x.copy()).pin_memory()
+    for host in (x.copy(), pinned.numpy()):
+        with vg.index.DeviceIndex(codec=L.CODEC_SQ8, metric=0, dim=dim, rows=n, sq8=(sq.mins, sq.invScales)) as ix:
+            ix.upload(codes=codes)
+            with pytest.raises(vg.VecgoError):
+                ix.rerank(q, rows)          # no float32 rows yet
+            ix.set_host_vectors(host)
+            got_scores = ix.rerank(q, rows)
+            got = ix.search_rerank(q, r, k)
+        assert np.array_equal(bits(got_scores), bits(want_scores))
+        assert np.array_equal(got[0], want[0]) and np.array_equal(bits(got[1]), bits(want[1])) and np.array_equal(got[2], want[2])
+    for i in range(nq):   # and against the oracle's Segment.Rerank
+        ex = np.array([o.lib.vgo_sql2_a512(o.fp(q[i]), o.fp(x[rw]), dim) for rw in rows[i]], F)
+        assert np.array_equal(bits(want_scores[i]), bits(ex))
+    with vg.index.DeviceIndex(codec=L.CODEC_F32, metric=0, dim=dim, rows=n) as fx:
+        with pytest.raises(vg.VecgoError):
+            fx.set_host_vectors(x)          # a float32 index scans its rows: device-resident only

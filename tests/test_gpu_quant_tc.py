@@ -74,6 +74,7 @@ def random_pq(rng, dim, m, k=256):
     (9000, 64, 300, 1),       # VB=4 layout, one k-block, two query tiles, ragged row tile
     (70000, 256, 64, 32),     # many row splits
     (150000, 128, 32, 100),   # k = 100 -> 200 candidate groups
+    (300000, 128, 20, 1000),  # k = 1000 (the engine's refine depth): 2000 candidate groups
 ])
 def test_sq8_tc_matches_oracle(vg, n, dim, nq, k):
     rng = np.random.default_rng(n + dim)
@@ -103,7 +104,8 @@ def test_sq8_tc_matches_oracle(vg, n, dim, nq, k):
         assert after[1] - before[1] <= nq // 4, "too many certificate failures on benign data"
 
 
-@pytest.mark.parametrize("n,dim,nq,k", [(30000, 768, 33, 10), (9000, 256, 20, 5), (12000, 64, 17, 10), (100000, 192, 32, 50)])
+@pytest.mark.parametrize("n,dim,nq,k", [(30000, 768, 33, 10), (9000, 256, 20, 5), (12000, 64, 17, 10), (100000, 192, 32, 50),
+                                        (280000, 256, 18, 1000)])
 def test_int4_tc_matches_exact_scan(vg, n, dim, nq, k):
     rng = np.random.default_rng(n + dim + 1)
     v = rng.standard_normal((n, dim)).astype(F)
@@ -139,6 +141,7 @@ def test_int4_tc_matches_exact_scan(vg, n, dim, nq, k):
     (40000, 128, 8, 20, 10),     # dsub = 16
     (60000, 256, 32, 32, 100),   # k = 100
     (10000, 128, 16, 16, 10),     # m = 16, dsub = 8
+    (300000, 768, 96, 17, 1000), # k = 1000 at the C3 code shape
 ])
 def test_pq_tc_matches_oracle(vg, n, dim, m, nq, k):
     rng = np.random.default_rng(n + m)

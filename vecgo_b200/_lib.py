@@ -123,6 +123,7 @@ _SIGS = {
     "vg_index_l2_bounded_dev": [u64, vp, i64, vp, i64, vp, i32, vp, vp],
     "vg_index_upload": [u64, i64, i64, vp, f32p],
     "vg_index_upload_dev": [u64, i64, i64, vp, vp],
+    "vg_index_set_host_vectors": [u64, vp, i64],
     "vg_index_close": [u64],
     "vg_index_info": [u64, i64p, i64p, i64p, i64p],
     "vg_index_search": [u64, f32p, i64, i64, i64, u8p, u32p, f32p, i32p],

@@ -321,6 +321,9 @@ struct Index {
     DevBuf pq_cb, pq_scales, pq_offsets, centroids, part_off, rotation;
     std::vector<uint32_t> h_part_off;
     int words32 = 0;
+    const float *host_vectors = nullptr;   // vg_index_set_host_vectors: float32 rows stay in (page-locked) host memory, rerank reads them over PCIe
+    const float *host_vectors_base = nullptr;   // the caller's host address of that region
+    bool host_registered = false;          // the library page-locked the region itself (undone at close)
     bool int4_direct = false;        // vg_index_score on INT4: simd.Int4L2Distance instead of the precomputed-LUT path
     bool has_vectors = false, has_codes = false, has_ids = false;
     // tensor-core Flat filter state (vg_flat_tc.cu): squared row norms + their maximum, rebuilt after uploads
@@ -349,6 +352,9 @@ static Index *lookup(vg_index_t h) {
     auto it = g_indexes.find(h);
     return it == g_indexes.end() ? nullptr : it->second;
 }
+
+// float32 rows a rerank gathers from: the device copy, or the device alias of a page-locked host region
+static const float *rerank_source(const Index *ix) { return ix->host_vectors ? ix->host_vectors : ix->vectors.as<float>(); }
 
 static int64_t host_code_bytes(const vg_index_desc &d) {
     switch (d.codec) {
@@ -569,6 +575,7 @@ vg_status vg_index_close(vg_index_t idx) {
     }
     VG_ENTER(ix->device);
     cudaDeviceSynchronize();  // searches still in flight on other streams of this device finish before the sections are freed
+    if (ix->host_registered) cudaHostUnregister(const_cast<float *>(ix->host_vectors_base));
     delete ix;
     return VG_OK;
 }
@@ -1173,7 +1180,7 @@ vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
     VG_ENTER_IX(ix);
     if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
-    VG_TRY(rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2,
+    VG_TRY(rerank_gather(rerank_source(ix), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2,
                          d_scores, stream()));
     return _vg_call.finish();  // stream-ordered on a caller stream; complete on return when the library chose the stream
 }
@@ -1230,7 +1237,7 @@ vg_status vg_index_l2_bounded_dev(vg_index_t idx, const float *d_queries, int64_
     VG_ENTER_IX(ix);
     if (nq <= 0 || r <= 0) return VG_OK;
     if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors");
-    VG_TRY(bounded_l2_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, d_bounds, per_pair_bounds, d_scores,
+    VG_TRY(bounded_l2_gather(rerank_source(ix), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, d_bounds, per_pair_bounds, d_scores,
                              d_exceeded, stream()));
     return _vg_call.finish();
 }
@@ -1288,6 +1295,44 @@ vg_status vg_int4_build_lookup_table(const float *h_min, const float *h_diff, in
             volatile float t = v + h_min[d];
             h_table[d * 16 + q] = t;
         }
+    return VG_OK;
+}
+
+// Float32 rows that stay in HOST memory (the mmap'd vector section of a segment whose rows do not fit next to the codes:
+// 100M x 1536 float32 = 614 GB against 180 GB of HBM, SURVEY hard part 6).  The region is page-locked (unless the caller
+// already did) and mapped into the device's address space; Segment.Rerank (flat/segment.go:754-781) then gathers the R
+// candidate rows of every query over the host link instead of from HBM — R * dim * 4 bytes per query, same arithmetic,
+// same bits.  The caller keeps the region valid and unchanged until vg_index_close (an mmap lives until Segment.Close).
+vg_status vg_index_set_host_vectors(vg_index_t idx, const float *h_vectors, int64_t rows) {
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
+    if (!h_vectors || rows != ix->d.rows) return fail(VG_ERR_INVALID, "host vector region must cover every row of the index");
+    if (ix->d.codec == VG_CODEC_F32) return fail(VG_ERR_UNSUPPORTED, "a float32 index scans its rows: they must be device-resident");
+    if (ix->has_vectors) return fail(VG_ERR_STATE, "the index already holds float32 rows");
+    const size_t bytes = (size_t)rows * (size_t)ix->d.dim * 4;
+    cudaPointerAttributes at;
+    const bool pinned = cudaPointerGetAttributes(&at, h_vectors) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (!pinned) {
+        cudaGetLastError();
+        cudaError_t e = cudaHostRegister(const_cast<float *>(h_vectors), bytes, cudaHostRegisterMapped | cudaHostRegisterReadOnly);
+        if (e == cudaErrorNotSupported || e == cudaErrorInvalidValue) {
+            cudaGetLastError();
+            e = cudaHostRegister(const_cast<float *>(h_vectors), bytes, cudaHostRegisterMapped);
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostRegister");
+        ix->host_registered = true;
+    }
+    void *dptr = nullptr;
+    cudaError_t e = cudaHostGetDevicePointer(&dptr, const_cast<float *>(h_vectors), 0);
+    if (e != cudaSuccess) {
+        if (ix->host_registered) cudaHostUnregister(const_cast<float *>(h_vectors));
+        ix->host_registered = false;
+        return cuda_fail(e, "cudaHostGetDevicePointer");
+    }
+    ix->host_vectors = reinterpret_cast<const float *>(dptr);
+    ix->host_vectors_base = h_vectors;
+    ix->has_vectors = true;
     return VG_OK;
 }
 
@@ -1354,7 +1399,7 @@ vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t
                                                                    local.as<uint32_t>());
     VG_LAUNCHED();
     const int desc = ix->d.metric != VG_METRIC_L2;
-    VG_TRY(rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, q.as<float>(), nq, local.as<uint32_t>(), r, desc,
+    VG_TRY(rerank_gather(rerank_source(ix), ix->d.rows, ix->d.dim, q.as<float>(), nq, local.as<uint32_t>(), r, desc,
                          exact.as<float>(), st));
     rerank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows.as<uint32_t>(), exact.as<float>(), n,
                                                                     (uint32_t)ix->d.row_base, desc, keys.as<unsigned long long>());
@@ -2192,7 +2237,7 @@ vg_status member_search(ShardGroup *g, int m, Index *ix, const float *d_queries,
     owned_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gr.as<uint32_t>(), n, (uint32_t)ix->d.row_base, (uint32_t)ix->d.rows,
                                                                    local.as<uint32_t>(), mine.as<uint32_t>());
     VG_LAUNCHED();
-    VG_TRY(rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, local.as<uint32_t>(), r, seg_desc, exact.as<float>(), st));
+    VG_TRY(rerank_gather(rerank_source(ix), ix->d.rows, ix->d.dim, d_queries, nq, local.as<uint32_t>(), r, seg_desc, exact.as<float>(), st));
     VG_TRY(launch_pack_keys(mine.as<uint32_t>(), exact.as<float>(), n, seg_desc, keys.as<unsigned long long>(), st));
     rc = g_nccl.AllGather(keys.p, allk.p, (size_t)n, kNcclUint64, g->comms[(size_t)m], st);
     if (rc != 0) return nccl_fail(rc, "ncclAllGather");

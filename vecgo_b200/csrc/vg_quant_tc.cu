@@ -1629,7 +1629,8 @@ static bool use_pair() {
 bool supported(const CodecParams &cp, int metric, int64_t rows, int64_t nq, int64_t k, int64_t num_partitions) {
     if (!enabled() || num_partitions > 1) return false;
     if (rows < 8192 || rows >= (1ll << 31) || nq < 16 || k < 1) return false;
-    if (k > (cp.codec == VG_CODEC_RABITQ || cp.codec == VG_CODEC_BQ ? 1024 : 128)) return false;
+    if (k > 1024) return false;                                             // the engine's refine depth (k * RefineFactor) fits
+    if (rows / 32 < 2 * (int64_t)(k <= 16 ? 32 : 2 * k)) return false;      // candidate groups must exist (2k groups of >= 32 rows, twice over)
     if (cp.dim % 64 != 0 || cp.dim < 64 || cp.dim > 2048) return false;
     if ((reinterpret_cast<uintptr_t>(cp.codes) & 15) != 0) return false;
     switch (cp.codec) {

@@ -75,6 +75,15 @@ class DeviceIndex:
         """Fill rows from device pointers (e.g. torch tensors' data_ptr())."""
         L.call("vg_index_upload_dev", self.handle, row0, n, d_codes or None, d_vectors or None)
 
+    def set_host_vectors(self, vectors):
+        """Rerank source in host memory: a C-contiguous float32 array [rows, dim] (numpy, or a numpy view of a pinned torch
+        tensor) that must stay alive and unchanged until close(); Rerank gathers candidate rows from it over the host link."""
+        v = np.ascontiguousarray(vectors, dtype=F)
+        if v.shape != (self.rows, self.dim):
+            raise ValueError("host vectors must be [rows, dim]")
+        self._host_vectors = v   # keep the region alive
+        L.call("vg_index_set_host_vectors", self.handle, v.ctypes.data, self.rows)
+
     def info(self):
         r, d, cb, db = (C.c_int64() for _ in range(4))
         L.call("vg_index_info", self.handle, C.byref(r), C.byref(d), C.byref(cb), C.byref(db))
