@@ -355,6 +355,11 @@ static Index *lookup(vg_index_t h) {
 
 // float32 rows a rerank gathers from: the device copy, or the device alias of a page-locked host region
 static const float *rerank_source(const Index *ix) { return ix->host_vectors ? ix->host_vectors : ix->vectors.as<float>(); }
+static vg_status rerank_rows(const Index *ix, const float *d_queries, int64_t nq, const uint32_t *d_rows, int64_t r, int is_dot,
+                             float *d_out, cudaStream_t st) {
+    if (ix->host_vectors) return rerank_gather_host(ix->host_vectors, ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, is_dot, d_out, st);
+    return rerank_gather(ix->vectors.as<float>(), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, is_dot, d_out, st);
+}
 
 static int64_t host_code_bytes(const vg_index_desc &d) {
     switch (d.codec) {
@@ -1180,8 +1185,7 @@ vg_status vg_index_rerank_dev(vg_index_t idx, const float *d_queries, int64_t nq
     if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
     VG_ENTER_IX(ix);
     if (!ix->has_vectors) return fail(VG_ERR_STATE, "index holds no float32 vectors to rerank against");
-    VG_TRY(rerank_gather(rerank_source(ix), ix->d.rows, ix->d.dim, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2,
-                         d_scores, stream()));
+    VG_TRY(rerank_rows(ix, d_queries, nq, d_rows, r, ix->d.metric != VG_METRIC_L2, d_scores, stream()));
     return _vg_call.finish();  // stream-ordered on a caller stream; complete on return when the library chose the stream
 }
 
@@ -1399,8 +1403,7 @@ vg_status vg_index_search_rerank(vg_index_t idx, const float *h_queries, int64_t
                                                                    local.as<uint32_t>());
     VG_LAUNCHED();
     const int desc = ix->d.metric != VG_METRIC_L2;
-    VG_TRY(rerank_gather(rerank_source(ix), ix->d.rows, ix->d.dim, q.as<float>(), nq, local.as<uint32_t>(), r, desc,
-                         exact.as<float>(), st));
+    VG_TRY(rerank_rows(ix, q.as<float>(), nq, local.as<uint32_t>(), r, desc, exact.as<float>(), st));
     rerank_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rows.as<uint32_t>(), exact.as<float>(), n,
                                                                     (uint32_t)ix->d.row_base, desc, keys.as<unsigned long long>());
     VG_LAUNCHED();
@@ -2237,7 +2240,7 @@ vg_status member_search(ShardGroup *g, int m, Index *ix, const float *d_queries,
     owned_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gr.as<uint32_t>(), n, (uint32_t)ix->d.row_base, (uint32_t)ix->d.rows,
                                                                    local.as<uint32_t>(), mine.as<uint32_t>());
     VG_LAUNCHED();
-    VG_TRY(rerank_gather(rerank_source(ix), ix->d.rows, ix->d.dim, d_queries, nq, local.as<uint32_t>(), r, seg_desc, exact.as<float>(), st));
+    VG_TRY(rerank_rows(ix, d_queries, nq, local.as<uint32_t>(), r, seg_desc, exact.as<float>(), st));
     VG_TRY(launch_pack_keys(mine.as<uint32_t>(), exact.as<float>(), n, seg_desc, keys.as<unsigned long long>(), st));
     rc = g_nccl.AllGather(keys.p, allk.p, (size_t)n, kNcclUint64, g->comms[(size_t)m], st);
     if (rc != 0) return nccl_fail(rc, "ncclAllGather");

@@ -1355,6 +1355,87 @@ vg_status rerank_gather(const float *d_vectors, int64_t nrows, int64_t dim, cons
     return VG_OK;
 }
 
+// Rerank against float32 rows in mapped HOST memory (vg_index_set_host_vectors).  Scalar 64-byte half-warp reads over the
+// host link reach about a third of what it can carry, so the candidate rows are first pulled into an HBM staging buffer by
+// a copy-only kernel (one warp per pair, 16-byte loads, every load of a row in flight before the first store), chunk by
+// chunk, and the rerank kernel then reads that buffer: same arithmetic, same order, same bits.
+__global__ void __launch_bounds__(256) host_rows_gather_kernel(const float *vectors, int64_t nrows, int64_t dim, const uint32_t *rows,
+                                                               int64_t pair0, int64_t npairs, float *stage) {
+    const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= npairs) return;
+    const uint32_t row = rows[pair0 + w];
+    if ((int64_t)row >= nrows) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(vectors + (int64_t)row * dim);
+    uint4 *dst = reinterpret_cast<uint4 *>(stage + w * dim);
+    const int n16 = (int)(dim >> 2);
+    for (int i = lane; i < n16; i += 32 * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (i + u * 32 < n16) v[u] = __ldcs(src + i + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+            if (i + u * 32 < n16) dst[i + u * 32] = v[u];
+    }
+}
+// rerank_kernel over a staged chunk: pair p = pair0 + local reads row `local` of the staging buffer
+__global__ void __launch_bounds__(256) rerank_staged_kernel(const float *stage, int64_t nrows, int64_t dim, const float *queries,
+                                                            const uint32_t *rows, int64_t r, int64_t pair0, int64_t npairs, int is_dot, float *out) {
+    const int64_t local = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int lane = threadIdx.x & 15;
+    const bool live = local < npairs;
+    const int64_t l = live ? local : npairs - 1;
+    const int64_t p = pair0 + l;
+    const int64_t q = p / r;
+    const bool valid = (int64_t)rows[p] < nrows;
+    const float *x = stage + (valid ? l : 0) * dim;
+    const float *qv = queries + q * dim;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    const int64_t epochs = dim >> 6;
+    for (int64_t e = 0; e < epochs; e++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int64_t d = e * 64 + j * 16 + lane;
+            if (is_dot) {
+                a[j] = __fmaf_rn(qv[d], x[d], a[j]);
+            } else {
+                const float df = __fsub_rn(qv[d], x[d]);
+                a[j] = __fmaf_rn(df, df, a[j]);
+            }
+        }
+    float tot = reduce16(__fadd_rn(__fadd_rn(a[0], a[1]), __fadd_rn(a[2], a[3])));
+    if (lane == 0 && live) {
+        for (int64_t d = epochs * 64; d < dim; d++) {
+            if (is_dot) {
+                tot = __fmaf_rn(qv[d], x[d], tot);
+            } else {
+                const float df = __fsub_rn(qv[d], x[d]);
+                tot = __fmaf_rn(df, df, tot);
+            }
+        }
+        out[p] = valid ? tot : __uint_as_float(0x7fc00000u);
+    }
+}
+vg_status rerank_gather_host(const float *d_host_alias, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq,
+                             const uint32_t *d_rows, int64_t r, int is_dot, float *d_out, cudaStream_t st) {
+    const int64_t total = nq * r;
+    if (total <= 0) return VG_OK;
+    if (dim % 4 != 0)   // rows are not 16-byte aligned: read them in place
+        return rerank_gather(d_host_alias, nrows, dim, d_queries, nq, d_rows, r, is_dot, d_out, st);
+    const int64_t chunk = std::max<int64_t>(1024, std::min<int64_t>(total, ((int64_t)768 << 20) / (dim * 4)));
+    DevBuf stage;
+    VG_TRY(stage.alloc((size_t)chunk * dim * 4));
+    for (int64_t p0 = 0; p0 < total; p0 += chunk) {
+        const int64_t np = std::min(chunk, total - p0);
+        host_rows_gather_kernel<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(d_host_alias, nrows, dim, d_rows, p0, np, stage.as<float>());
+        VG_LAUNCHED();
+        rerank_staged_kernel<<<(unsigned)((np * 16 + 255) / 256), 256, 0, st>>>(stage.as<float>(), nrows, dim, d_queries, d_rows, r, p0, np, is_dot, d_out);
+        VG_LAUNCHED();
+    }
+    return VG_OK;
+}
+
 // ------------------------------------------------------------ bounded L2 (gather)
 // simd.SquaredL2Bounded (kernels.go:163-176, AVX-512 path registered at kernels_amd64.go:269: bounded_l2_avx512.c:19-107)
 // for every (query, candidate row) pair: four 16-lane FMA accumulators over 64-dim blocks; after EVERY block the running

@@ -77,6 +77,9 @@ vg_status scan_dense(const CodecParams &cp, const float *d_queries, int64_t nq, 
 // Exact per-candidate scores: out[q][j] = dist(query q, vectors[rows[q][j]]) in simd pair order.
 vg_status rerank_gather(const float *d_vectors, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq,
                         const uint32_t *d_rows, int64_t r, int is_dot, float *d_out, cudaStream_t st);
+// the same against rows in mapped host memory: staged through HBM chunk by chunk (see vg_scan.cu)
+vg_status rerank_gather_host(const float *d_host_alias, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq,
+                             const uint32_t *d_rows, int64_t r, int is_dot, float *d_out, cudaStream_t st);
 // simd.SquaredL2Bounded per (query, candidate row): out = the distance, or the partial sum at the 64-dim block where it
 // first exceeded the bound (exceeded = 1).  Bounds: one per query, or one per pair when per_pair_bounds.
 vg_status bounded_l2_gather(const float *d_vectors, int64_t nrows, int64_t dim, const float *d_queries, int64_t nq, const uint32_t *d_rows,
