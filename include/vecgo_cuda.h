@@ -258,6 +258,21 @@ vg_status vg_index_search_dev_async(vg_index_t idx, const float *d_queries, int6
 vg_status vg_index_search_resolve(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,
                                   const uint8_t *d_row_mask, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts,
                                   const int32_t *d_unproven, int64_t *n_resolved);
+/* Segment.Search with block-stat skipping (flat/segment.go:524-541,613-630): h_block_keep is a bitmap over the
+ * BlockSize = 1024-row blocks of the segment, bit b set = scan block b, clear = the caller's filter.MatchesBlock /
+ * matchesFilterSet verdict on block b's statistics was "cannot match" and the block is jumped over.  Only blocks wholly
+ * inside the segment are skipped (the ragged last block is always scanned, as `i + BlockSize <= end`); the bitmap holds
+ * ceil(floor(rows / 1024) / 8) bytes and always lives in HOST memory (it is the product of host metadata logic, and
+ * distance_computations is counted from it).  The row bitmap (host / device as in vg_index_search / _dev) may be NULL.
+ * On the device the verdicts are folded into the row bitmap; the tensor-core filters never fetch a 256-row tile
+ * without an allowed row, so skipped blocks cost no HBM traffic.  NULL h_block_keep = vg_index_search[_dev]. */
+vg_status vg_index_search_blocks(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *h_row_mask,
+                                 const uint8_t *h_block_keep, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
+vg_status vg_index_search_blocks_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *d_row_mask,
+                                     const uint8_t *h_block_keep, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
+/* Tile skipping of the quantized tensor-core filters when a row bitmap is given (default on; VECGO_TILE_SKIP=0): off
+ * only for A/B measurements — results are identical either way. */
+vg_status vg_tile_skip_enable(int32_t on);
 /* Counters of the last vg_index_search* / vg_index_search_resolve call made by the calling thread: what a Go caller adds
  * to searcher.FilterGateStats / model.QueryStats (flat/segment.go:448-471,553-591).  distance_computations counts the
  * (query, row) distance evaluations the reference's scan would report (rows visited per query, plus the rows of every

@@ -684,6 +684,7 @@ vg_status vg_index_upload(vg_index_t idx, int64_t row0, int64_t n, const void *h
 // Per-call statistics of the last search on the calling thread (the reference's searcher.FilterGateStats /
 // model.QueryStats counters a Go caller fills from them, flat/segment.go:448-471,553-591).
 static thread_local vg_search_stats t_stats;
+static thread_local uint64_t t_rows_skipped = 0;   // rows of the blocks the current vg_index_search_blocks* call jumps over
 
 // Lazy per-index filter state.  Built once even if searches race (prep_mu) and COMPLETE on the device before the lock is
 // released: another thread's search runs on another stream and must not start before these kernels have finished.
@@ -866,7 +867,7 @@ static vg_status search_enqueue(Index *ix, const float *d_queries, int64_t nq, i
     }
     cudaStream_t st = stream();
     t_stats.queries += (uint64_t)nq;
-    t_stats.distance_computations += (uint64_t)nq * (uint64_t)d.rows;
+    t_stats.distance_computations += (uint64_t)nq * ((uint64_t)d.rows - t_rows_skipped);
     if (d.codec == VG_CODEC_F32) {
         const int mode = search_mode(ix, d_queries, nq, k, d_mask, nullptr);
         *mode_out = mode;
@@ -974,7 +975,7 @@ static vg_status search_resolve(Index *ix, const float *d_queries, int64_t nq, i
     }
     // exact CUDA-core scan for the queries no certificate could clear
     t_stats.exact_rerun_queries += (uint64_t)bad.size();
-    t_stats.distance_computations += (uint64_t)bad.size() * (uint64_t)d.rows;
+    t_stats.distance_computations += (uint64_t)bad.size() * ((uint64_t)d.rows - t_rows_skipped);
     return scan_topk_subset(t.cp, t.a, bad, st);
 }
 
@@ -1011,6 +1012,95 @@ vg_status vg_index_search_dev(vg_index_t idx, const float *d_queries, int64_t nq
     t_stats = vg_search_stats{};
     VG_TRY(search_dev_impl(ix, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts));
     return _vg_call.finish();
+}
+
+// ---------------------------------------------------------------- block-stat skipping
+// flat.Segment.Search jumps over a whole BlockSize = 1024-row block when the block's field statistics cannot match the
+// filter (flat/segment.go:524-541,613-630; filter.MatchesBlock / matchesFilterSet are host-side metadata logic).  The
+// caller hands the verdicts over as a bitmap (bit b set = scan block b); only blocks that lie wholly inside the segment
+// are ever skipped (i + BlockSize <= end).  On the device the verdicts are folded into the row bitmap; the tensor-core
+// filters then drop every 256-row tile without an allowed row before it is fetched (vg_quant_tc.cu: tile skipping).
+constexpr int64_t kBlockRows = 1024;
+__global__ void __launch_bounds__(256) apply_block_mask_kernel(const uint8_t *row_mask, const uint8_t *block_keep, int64_t rows, int64_t words,
+                                                               uint32_t *eff) {
+    const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= words) return;
+    const int64_t blk = (w * 32) / kBlockRows;
+    const bool full = (blk + 1) * kBlockRows <= rows;
+    const bool keep = !full || ((block_keep[blk >> 3] >> (blk & 7)) & 1);
+    uint32_t v = 0;
+    if (keep) {
+        if (!row_mask) v = 0xFFFFFFFFu;
+        else {
+            const int64_t nbytes = (rows + 7) / 8;
+            for (int b = 0; b < 4; b++)
+                if (w * 4 + b < nbytes) v |= (uint32_t)row_mask[w * 4 + b] << (8 * b);
+        }
+    }
+    eff[w] = v;
+}
+static vg_status effective_mask(Index *ix, const uint8_t *d_row_mask, const uint8_t *h_block_keep, DevBuf &eff, uint64_t *rows_skipped) {
+    const int64_t rows = ix->d.rows;
+    const int64_t full_blocks = rows / kBlockRows, words = (rows + 31) / 32;
+    uint64_t skipped = 0;
+    for (int64_t b = 0; b < full_blocks; b++)
+        if (!((h_block_keep[b >> 3] >> (b & 7)) & 1)) skipped++;
+    *rows_skipped = skipped * (uint64_t)kBlockRows;
+    DevBuf keep;
+    const size_t kb = (size_t)((rows / kBlockRows + 1 + 7) / 8);
+    std::vector<uint8_t> h_keep(kb, 0xFF);   // bits past the caller's bitmap (the ragged last block) read as "scan"
+    memcpy(h_keep.data(), h_block_keep, (size_t)((full_blocks + 7) / 8));
+    VG_TRY(to_device(keep, h_keep.data(), kb));
+    VG_TRY(eff.alloc((size_t)words * 4 + 16));
+    apply_block_mask_kernel<<<(unsigned)((words + 255) / 256), 256, 0, stream()>>>(d_row_mask, keep.as<uint8_t>(), rows, words, eff.as<uint32_t>());
+    VG_LAUNCHED();
+    return VG_OK;
+}
+
+vg_status vg_index_search_blocks_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *d_row_mask,
+                                     const uint8_t *h_block_keep, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts) {
+    if (!h_block_keep) return vg_index_search_dev(idx, d_queries, nq, k, nprobes, d_row_mask, d_out_rows, d_out_scores, d_out_counts);
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    VG_ENTER_IX(ix);
+    t_stats = vg_search_stats{};
+    DevBuf eff;
+    uint64_t skipped = 0;
+    VG_TRY(effective_mask(ix, d_row_mask, h_block_keep, eff, &skipped));
+    t_rows_skipped = skipped;
+    const vg_status rc = search_dev_impl(ix, d_queries, nq, k, nprobes, eff.as<uint8_t>(), d_out_rows, d_out_scores, d_out_counts);
+    t_rows_skipped = 0;
+    if (rc != VG_OK) return rc;
+    return _vg_call.finish();   // the folded bitmap goes back to the stream-ordered pool behind the kernels that read it
+}
+
+vg_status vg_index_search_blocks(vg_index_t idx, const float *h_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *h_row_mask,
+                                 const uint8_t *h_block_keep, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts) {
+    if (!h_block_keep) return vg_index_search(idx, h_queries, nq, k, nprobes, h_row_mask, h_out_rows, h_out_scores, h_out_counts);
+    Index *ix = lookup(idx);
+    if (!ix) return fail(VG_ERR_STATE, "unknown or closed index handle");
+    if (nq < 0 || k <= 0) return fail(VG_ERR_INVALID, "nq must be >= 0 and k > 0");
+    if (nq == 0) return VG_OK;
+    // fold the verdicts into the row bitmap on the host (rows / 8 bytes) and take the ordinary path
+    const int64_t rows = ix->d.rows, nbytes = (rows + 7) / 8, full_blocks = rows / kBlockRows;
+    std::vector<uint8_t> m((size_t)nbytes + 4, 0);
+    if (h_row_mask) memcpy(m.data(), h_row_mask, (size_t)nbytes);
+    else memset(m.data(), 0xFF, (size_t)nbytes);
+    uint64_t skipped = 0;
+    for (int64_t b = 0; b < full_blocks; b++)
+        if (!((h_block_keep[b >> 3] >> (b & 7)) & 1)) {
+            memset(m.data() + b * (kBlockRows / 8), 0, (size_t)(kBlockRows / 8));
+            skipped++;
+        }
+    t_rows_skipped = skipped * (uint64_t)kBlockRows;
+    const vg_status rc = vg_index_search(idx, h_queries, nq, k, nprobes, m.data(), h_out_rows, h_out_scores, h_out_counts);
+    t_rows_skipped = 0;
+    return rc;
+}
+
+vg_status vg_tile_skip_enable(int32_t on) {
+    qtc::set_tile_skip(on != 0);
+    return VG_OK;
 }
 
 vg_status vg_index_search_dev_async(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes,

@@ -104,6 +104,10 @@ __device__ __forceinline__ uint32_t bytes23_h2(uint32_t w) { return __byte_perm(
 struct KArgs {
     const float *xn;        // [rows] ||x^||^2
     const uint32_t *mask;   // optional row bitmap as 32-bit words
+    // tile skipping (pair kernel, with a row bitmap): the 256-row tiles that hold at least one allowed row, in ascending
+    // order, and their number; the splits share the list evenly.  nullptr = every tile of the split's row range.
+    const int32_t *tile_list;
+    const int32_t *tile_count;
     const float *fq;        // [nq] -2 / query scale
     int64_t nq, rows, rows_per_split;
     float half_dim;           // BQ: D / 2 (Hamming = D / 2 - acc / 2)
@@ -555,7 +559,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
     const int64_t row_begin = (int64_t)split * A.rows_per_split;
     int64_t row_end = row_begin + A.rows_per_split;
     if (row_end > A.rows) row_end = A.rows;
-    const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
+    int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
+    const int32_t *tiles = nullptr;  // this split's slice of the active-tile list (tile skipping)
+    if (A.tile_list) {
+        const int n_act = __ldg(A.tile_count);
+        const int per = (n_act + (int)gridDim.y - 1) / (int)gridDim.y;
+        const int first = split * per;
+        ntiles = n_act - first < per ? n_act - first : per;
+        if (ntiles < 0) ntiles = 0;
+        tiles = A.tile_list + first;
+        row_end = A.rows;
+    }
+    // first row of the split's t-th tile
+    auto tile_row0 = [&](int t) -> int64_t {
+        return tiles ? (int64_t)__ldg(tiles + t) * TILE_ROWS : row_begin + (int64_t)t * TILE_ROWS;
+    };
 
     // PQ trades one pipeline stage for a two-slot ring of 16 KB codebook slices (the int8 centroids of the subspaces of one
     // k-block, bulk-copied by the TMA thread): the decode warps gather from shared memory instead of from L2.
@@ -667,7 +685,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         // row norms of a tile are fetched one tile ahead (global-load latency out of the per-tile critical path): the value
         // for tile t + 1 is loaded at the top of tile t and stored after tile t's columns are reduced
         auto xn_of = [&](int t_) {
-            const int64_t n0 = row_begin + (int64_t)t_ * TILE_ROWS;
+            const int64_t n0 = tile_row0(t_);
             const int64_t row = n0 + et;
             if constexpr (CODEC == Q_BQ) return (row < row_end) ? A.half_dim : BIG;  // s = D / 2 - acc / 2 = Hamming, exact
             else return (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
@@ -676,7 +694,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
-            const int64_t n0 = row_begin + (int64_t)t * TILE_ROWS;
+            const int64_t n0 = tile_row0(t);
             float *xt = xs + as * TILE_ROWS;
             asm volatile("bar.sync 1, 256;" ::: "memory");
             const float xn_next = (t + 1 < ntiles) ? xn_of(t + 1) : 0.0f;
@@ -787,12 +805,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 return moved;
             }
         };
-        const int64_t half_begin = row_begin + (int64_t)rank * BN;
+        const int64_t half_off = (int64_t)rank * BN;   // this CTA's half of every tile
         if constexpr (CODEC == Q_PQ) {
             const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
             const int swz = r & 7;
             auto row_of = [&](int t) {
-                const int64_t row = half_begin + (int64_t)t * TILE_ROWS + r;
+                const int64_t row = tile_row0(t) + half_off + r;
                 return row < A.rows ? row : A.rows - 1;
             };
             // codes of iterations it, it + 2, it + 4 in flight (8 bytes each); the centroid bytes come from the slice ring
@@ -830,7 +848,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
             const int swz = r & 7;
             auto row_of = [&](int t) {
-                const int64_t row = half_begin + (int64_t)t * TILE_ROWS + r;
+                const int64_t row = tile_row0(t) + half_off + r;
                 return row < A.rows ? row : A.rows - 1;
             };
             // three buffers in rotation (see the byte producers below): loads of it + 2 and it + 4 in flight
@@ -872,11 +890,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             typename ProducerBytes<CODEC>::Rows rows;
             Cursor cf;  // cursor of the iteration whose loads are issued next
             cf.init(grp, A.kb);
-            rows.set(A, half_begin + (int64_t)cf.t * TILE_ROWS + slab, lane);
+            rows.set(A, tile_row0(cf.t < ntiles ? cf.t : 0) + half_off + slab, lane);
             int it = grp;
             auto fetch_next = [&](ProducerBytes<CODEC> &buf, int it_f) {
                 if (it_f < total_it) buf.fetch(rows, cf.kb);
-                if (cf.advance2(A.kb)) rows.set(A, half_begin + (int64_t)cf.t * TILE_ROWS + slab, lane);
+                if (cf.advance2(A.kb)) rows.set(A, tile_row0(cf.t < ntiles ? cf.t : 0) + half_off + slab, lane);
             };
             auto step = [&](const ProducerBytes<CODEC> &cur, ProducerBytes<CODEC> &far) {
                 fetch_next(far, it + 4);
@@ -1601,6 +1619,18 @@ void stats(uint64_t *queries, uint64_t *fallbacks) {
     if (queries) *queries = g_queries.load();
     if (fallbacks) *fallbacks = g_fallbacks.load();
 }
+// Tile skipping (on unless VECGO_TILE_SKIP=0; vg_tile_skip_enable for A/B measurements)
+static std::atomic<int> g_tile_skip{-1};
+static bool tile_skip_on() {
+    int v = g_tile_skip.load();
+    if (v < 0) {
+        const char *e = getenv("VECGO_TILE_SKIP");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_tile_skip.store(v);
+    }
+    return v != 0;
+}
+void set_tile_skip(bool on) { g_tile_skip.store(on ? 1 : 0); }
 // Optional CUDA-event timing of the GEMM kernel on its own stream (bench.py's roofline line).
 static std::atomic<int> g_prof{0};
 static std::mutex g_prof_mu;
@@ -1867,6 +1897,71 @@ static vg_status launch_thresh(const float *kth, const float *qn, const float *c
     return VG_OK;
 }
 
+// Tile skipping.  A 256-row tile that lies wholly inside the segment and whose 256 bitmap bits are all clear cannot
+// contribute a row: the pair kernel then never fetches, decodes or multiplies it.  This is where the reference's
+// block-stat skipping lands on the device (flat/segment.go:524-541,613-630: a BlockSize = 1024-row block whose stats
+// cannot match the filter is jumped over — the host clears those blocks' bits, vg_index_search_blocks*), and the same
+// test also drops tiles emptied by tombstones or a selective metadata filter.
+//   list[0 .. *count)  active tiles, ascending (one block, ordered compaction: the work split is reproducible)
+//   skip[0 .. *nskip)  the others (their row groups get the "nothing here" entry the select kernel expects)
+__global__ void __launch_bounds__(1024) build_tile_list_kernel(const uint32_t *mask, int64_t rows, int ntiles, int32_t *list, int32_t *count,
+                                                               int32_t *skip, int32_t *nskip) {
+    __shared__ int wsum[32];
+    __shared__ int base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int t0 = 0; t0 < ntiles; t0 += 1024) {
+        const int t = t0 + tid;
+        bool act = false;
+        if (t < ntiles) {
+            const int64_t n0 = (int64_t)t * pair::TILE_ROWS;
+            if (n0 + pair::TILE_ROWS > rows) act = true;   // the ragged last tile is always scanned (as i + BlockSize <= end)
+            else {
+                uint32_t any = 0;
+#pragma unroll
+                for (int w = 0; w < pair::TILE_ROWS / 32; w++) any |= __ldg(mask + (n0 >> 5) + w);
+                act = any != 0;
+            }
+        }
+        const uint32_t b = __ballot_sync(0xffffffffu, act);
+        if (lane == 0) wsum[warp] = __popc(b);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 32; w++) {
+            const int c = wsum[w];
+            if (w < warp) before += c;
+            total += c;
+        }
+        const int base = base_s;
+        if (t < ntiles) {
+            const int rank_act = before + __popc(b & ((1u << lane) - 1u));
+            if (act) list[base + rank_act] = t;
+            else skip[(t0 - base) + (tid - rank_act)] = t;   // skipped tiles before t0 = t0 - base
+        }
+        __syncthreads();
+        if (tid == 0) base_s = base + total;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        *count = base_s;
+        *nskip = ntiles - base_s;
+    }
+}
+// the minima-plane entries of the skipped tiles' row groups: (BIG, BIG) — what the epilogue writes for a group whose
+// rows are all masked (the exact stage drops any row it decodes from such an entry: its bitmap bit is clear)
+__global__ void __launch_bounds__(256) fill_skipped_groups_kernel(const int32_t *skip, const int32_t *nskip, int gpt, int64_t groups, int64_t nq,
+                                                                  float2 *mins) {
+    const int n = __ldg(nskip);
+    const float BIG = 3.0e38f;
+    for (int i = blockIdx.x; i < n; i += gridDim.x) {
+        const int64_t g0 = (int64_t)__ldg(skip + i) * gpt;
+        for (int64_t q = threadIdx.x; q < nq; q += blockDim.x)
+            for (int j = 0; j < gpt; j++)
+                if (g0 + j < groups) mins[q * groups + g0 + j] = make_float2(BIG, BIG);
+    }
+}
+
 // One chunk of queries through filter, select and exact stage (d_kth == nullptr), or through the threshold pass:
 // thresholds from d_kth (the k-th best exact score known per query), threshold-collect GEMM, exact stage over the lists.
 static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st,
@@ -1943,6 +2038,22 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.dsub_shift = 0;
     while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
     a.tiled = (qc == Q_PQ && (cp.variant & VG_VAR_PERM)) ? 1 : 0;
+    DevBuf tl;  // active-tile list, skipped-tile list, the two counts
+    if (io.d_mask && pair_mode && tile_skip_on()) {
+        const int64_t nt = (rows + pair::TILE_ROWS - 1) / pair::TILE_ROWS;
+        const size_t list_ints = (size_t)nt + 1024;   // slack: a split's empty slice may start a few entries past the end
+        VG_TRY(tl.alloc((2 * list_ints + 2) * 4));
+        VG_CUDA(cudaMemsetAsync(tl.p, 0, (2 * list_ints + 2) * 4, st));
+        int32_t *list = tl.as<int32_t>(), *skip = list + list_ints, *cnt = skip + list_ints;
+        build_tile_list_kernel<<<1, 1024, 0, st>>>(a.mask, rows, (int)nt, list, cnt, skip, cnt + 1);
+        VG_LAUNCHED();
+        if (!thresh) {
+            fill_skipped_groups_kernel<<<(unsigned)(sm_count() * 4), 256, 0, st>>>(skip, cnt + 1, (int)(pair::TILE_ROWS / G), groups, nq, a.mins);
+            VG_LAUNCHED();
+        }
+        a.tile_list = list;
+        a.tile_count = cnt;
+    }
     if (thresh) {
         // ---- threshold pass: lists instead of the minima plane, no selection, no certificate
         const int slots = (int)splits * 2;

@@ -90,8 +90,10 @@ class DeviceIndex:
         return dict(rows=r.value, dim=d.value, code_bytes_per_row=cb.value, device_bytes=db.value)
 
     # ---------------------------------------------------------------- search
-    def search(self, queries, k: int, nprobes: int = 0, row_mask=None, out=None):
+    def search(self, queries, k: int, nprobes: int = 0, row_mask=None, out=None, block_keep=None):
         """Batched Segment.Search → (rows [nq,k] u32, scores [nq,k] f32, counts [nq] i32), best-first.
+        `block_keep`: block-stat skipping verdicts (flat/segment.go:524-541): one bool per full 1024-row block (or the packed
+        bitmap), False = the block's statistics cannot match the filter and the block is jumped over.
         `out` = (rows, scores, counts) C-contiguous arrays to fill instead of fresh ones — page-locked query / result
         buffers (e.g. numpy views of pinned torch tensors) are DMA'd directly by the library, pageable ones are staged."""
         q = L.as_f32(queries).reshape(-1, self.dim)
@@ -111,9 +113,36 @@ class DeviceIndex:
             m = L.as_u8(row_mask)
             if m.size < (self.rows + 7) // 8:
                 raise ValueError("row mask shorter than ceil(rows/8) bytes")
+        if block_keep is not None:
+            bk = self._block_keep(block_keep)
+            L.call("vg_index_search_blocks", self.handle, L.ptr(q, L.f32p), nq, k, nprobes, L.ptr(m, L.u8p), L.ptr(bk, L.u8p),
+                   L.ptr(rows, L.u32p), L.ptr(scores, L.f32p), L.ptr(counts, L.i32p))
+            return rows, scores, counts
         L.call("vg_index_search", self.handle, L.ptr(q, L.f32p), nq, k, nprobes, L.ptr(m, L.u8p), L.ptr(rows, L.u32p),
                L.ptr(scores, L.f32p), L.ptr(counts, L.i32p))
         return rows, scores, counts
+
+    BLOCK_ROWS = 1024   # flat.BlockSize (internal/segment/flat/format.go:14)
+
+    def _block_keep(self, block_keep):
+        """Block verdict bitmap (bit b set = scan block b): packed uint8, or a bool array with one entry per full block."""
+        b = np.asarray(block_keep)
+        full = self.rows // self.BLOCK_ROWS
+        if b.dtype == np.bool_:
+            if b.size < full:
+                raise ValueError("block verdicts shorter than floor(rows / 1024)")
+            b = np.packbits(b[:full], bitorder="little")
+        b = np.ascontiguousarray(b, np.uint8)
+        if b.size < (full + 7) // 8:
+            raise ValueError("block bitmap shorter than ceil(floor(rows / 1024) / 8) bytes")
+        return b if b.size else np.zeros(1, np.uint8)
+
+    def search_blocks_dev(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int, block_keep,
+                          nprobes: int = 0, d_mask: int = 0):
+        """search_dev with block-stat skipping: block_keep (host) as in search(); d_mask an optional device row bitmap."""
+        bk = self._block_keep(block_keep)
+        L.call("vg_index_search_blocks_dev", self.handle, d_queries, nq, k, nprobes, d_mask or None, L.ptr(bk, L.u8p), d_rows, d_scores,
+               d_counts)
 
     def search_dev(self, d_queries: int, nq: int, k: int, d_rows: int, d_scores: int, d_counts: int, nprobes: int = 0,
                    d_mask: int = 0):
