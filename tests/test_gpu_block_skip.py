@@ -53,7 +53,11 @@ def verdicts(rng, n, kind):
 def make(vg, codec, rng, n, dim):
     L = vg._lib
     x = rng.standard_normal((n, dim)).astype(F)
-    if codec == "sq8":
+    if codec == "f32":
+        codes = None
+        mk = lambda: vg.index.DeviceIndex(codec=L.CODEC_F32, metric=0, dim=dim, rows=n)
+        okw = dict(dim=dim, metric=0, vectors=x)
+    elif codec == "sq8":
         sq = vg.quantization.ScalarQuantizer(dim)
         sq.Train(x)
         codes = sq.EncodeBatch(x)
@@ -72,13 +76,14 @@ def make(vg, codec, rng, n, dim):
     return x, codes, mk, okw
 
 
-@pytest.mark.parametrize("codec,n,dim", [("sq8", 70_000 + 333, 128), ("int4", 40_000 + 77, 128), ("rabitq", 50_000 + 1, 256)])
+@pytest.mark.parametrize("codec,n,dim", [("sq8", 70_000 + 333, 128), ("int4", 40_000 + 77, 128), ("rabitq", 50_000 + 1, 256),
+                                         ("f32", 60_000 + 99, 128)])
 @pytest.mark.parametrize("kind", ["random", "clustered", "none", "all"])
 def test_block_skipping_matches_masked_scan(vg, codec, n, dim, kind):
     L = vg._lib
     rng = np.random.default_rng(len(codec) * 100 + len(kind))
     x, codes, mk, okw = make(vg, codec, rng, n, dim)
-    nq, k = 40, 10
+    nq, k = 40, (20 if codec == "f32" else 10)    # k > 16: the Flat CTA-pair filter (the single-launch kernel serves k <= 16)
     q = rng.standard_normal((nq, dim)).astype(F)
     keep = verdicts(rng, n, kind)
     tomb = rng.random(n) < 0.9                     # tombstones on top of the block verdicts
@@ -87,7 +92,10 @@ def test_block_skipping_matches_masked_scan(vg, codec, n, dim, kind):
         eq_mask = np.packbits(eq, bitorder="little")
         rmask = None if row_bits is None else np.packbits(row_bits, bitorder="little")
         with mk() as ix:
-            ix.upload(codes=codes)
+            if codec == "f32":
+                ix.upload(vectors=x)
+            else:
+                ix.upload(codes=codes)
             got = ix.search(q, k, row_mask=rmask, block_keep=keep)
             st = L.last_search_stats()
             L.call("vg_tile_skip_enable", 0)

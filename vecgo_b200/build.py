@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libvecgo_cuda.so")
 OBJ = os.path.join(HERE, "_obj")
-SOURCES = ["vg_api.cu", "vg_scan.cu", "vg_quant.cu", "vg_kmeans.cu", "vg_flat_tc.cu", "vg_flat_single.cu", "vg_quant_tc.cu", "vg_pq_assign_tc.cu", "vg_opq.cu"]
+SOURCES = ["vg_api.cu", "vg_scan.cu", "vg_quant.cu", "vg_kmeans.cu", "vg_tiles.cu", "vg_flat_tc.cu", "vg_flat_single.cu", "vg_quant_tc.cu", "vg_pq_assign_tc.cu", "vg_opq.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-fmad=false",

@@ -20,6 +20,7 @@
 #include "vg_scan.cuh"
 #include "vg_flat_tc.cuh"
 #include "vg_quant_tc.cuh"
+#include "vg_tiles.cuh"
 #include "vg_pq_assign_tc.cuh"
 
 namespace vg {
@@ -1099,7 +1100,7 @@ vg_status vg_index_search_blocks(vg_index_t idx, const float *h_queries, int64_t
 }
 
 vg_status vg_tile_skip_enable(int32_t on) {
-    qtc::set_tile_skip(on != 0);
+    tiles::set_enabled(on != 0);
     return VG_OK;
 }
 

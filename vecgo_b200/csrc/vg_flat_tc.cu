@@ -54,6 +54,7 @@
 #include <vector>
 
 #include "vg_flat_tc.cuh"
+#include "vg_tiles.cuh"
 #include "vg_scan.cuh"
 #include "vg_tc_ptx.cuh"
 #include "vg_topk.cuh"
@@ -325,6 +326,8 @@ constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 4) * 8 + 16 + 1
 struct Args2 {
     const float *xn;        // [rows] ||x||^2 (L2) or nullptr (dot)
     const uint32_t *mask;
+    const int32_t *tile_list;   // tile skipping (vg_tiles.cuh): active 256-row tiles and their number, or nullptr
+    const int32_t *tile_count;
     const float *fq;        // [nq] -2 (L2) or -1 (dot) / (query scale x database scale)
     int64_t nq, rows, rows_per_split;
     int kb;                 // k-blocks = dimp / 64
@@ -352,7 +355,20 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
     const int64_t row_begin = (int64_t)split * A.rows_per_split;
     int64_t row_end = row_begin + A.rows_per_split;
     if (row_end > A.rows) row_end = A.rows;
-    const int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
+    int ntiles = row_end > row_begin ? (int)((row_end - row_begin + TILE_ROWS - 1) / TILE_ROWS) : 0;
+    const int32_t *tiles = nullptr;  // this split's slice of the active-tile list
+    if (A.tile_list) {
+        const int n_act = __ldg(A.tile_count);
+        const int per = (n_act + (int)gridDim.y - 1) / (int)gridDim.y;
+        const int first = split * per;
+        ntiles = n_act - first < per ? n_act - first : per;
+        if (ntiles < 0) ntiles = 0;
+        tiles = A.tile_list + first;
+        row_end = A.rows;
+    }
+    auto tile_row0 = [&](int t) -> int64_t {
+        return tiles ? (int64_t)__ldg(tiles + t) * TILE_ROWS : row_begin + (int64_t)t * TILE_ROWS;
+    };
 
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar0 = s_base + (uint32_t)OFF_BAR2;
@@ -389,7 +405,7 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         if (lane == 0) {
             uint32_t it = 0;
             for (int t = 0; t < ntiles; t++) {
-                const int n0 = (int)(row_begin + (int64_t)t * TILE_ROWS) + (int)rank * BN;
+                const int n0 = (int)tile_row0(t) + (int)rank * BN;
                 for (int kb = 0; kb < A.kb; kb++, it++) {
                     const int st = it % STAGES2;
                     const uint32_t ph = (it / STAGES2) & 1;
@@ -443,7 +459,7 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         // row norms of a tile are fetched one tile ahead (global-load latency out of the per-tile critical path): the value
         // for tile t + 1 is loaded at the top of tile t and stored after tile t's columns are reduced
         auto xn_of = [&](int t_) {
-            const int64_t n0 = row_begin + (int64_t)t_ * TILE_ROWS;
+            const int64_t n0 = tile_row0(t_);
             const int64_t row = n0 + et;
             return (row < row_end) ? (IS_DOT ? 0.0f : __ldg(A.xn + row)) : BIG;
         };
@@ -451,7 +467,7 @@ flat2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ 
         for (int t = 0; t < ntiles; t++) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
-            const int64_t n0 = row_begin + (int64_t)t * TILE_ROWS;
+            const int64_t n0 = tile_row0(t);
             float *xt = xs + as * TILE_ROWS;
             asm volatile("bar.sync 1, %0;" ::"n"(EPW * 32) : "memory");
             const float xn_next = (t + 1 < ntiles && et < TILE_ROWS) ? xn_of(t + 1) : 0.0f;
@@ -1094,6 +1110,15 @@ static vg_status filter_pair(const FilterArgs &f, cudaStream_t st) {
     a.groups = groups;
     a.idx_mask = (uint32_t)(G - 1);
     a.keep_hi = ~31u;
+    a.tile_list = nullptr;
+    a.tile_count = nullptr;
+    tiles::Lists tl;
+    if (f.d_mask && tiles::enabled()) {
+        VG_TRY(tiles::build(a.mask, f.rows, tl, st));
+        VG_TRY(tiles::fill_skipped_groups(tl, (int)(pairf::TILE_ROWS / G), groups, f.nq, a.mins, st));
+        a.tile_list = tl.list;
+        a.tile_count = tl.count;
+    }
     if (pair_wide_epilogue(f)) {
         // minimum-only epilogue (every selected group scored whole, <= kc * 64 rows per query) when the GEMM dominates:
         // on a 100k-row segment the larger exact stage costs more than the epilogue saves (measured 0.19 -> 0.28 ms)

@@ -56,6 +56,7 @@
 
 #include "vg_flat_tc.cuh"
 #include "vg_quant_tc.cuh"
+#include "vg_tiles.cuh"
 #include "vg_tc_ptx.cuh"
 #include "vg_topk.cuh"
 
@@ -1619,18 +1620,6 @@ void stats(uint64_t *queries, uint64_t *fallbacks) {
     if (queries) *queries = g_queries.load();
     if (fallbacks) *fallbacks = g_fallbacks.load();
 }
-// Tile skipping (on unless VECGO_TILE_SKIP=0; vg_tile_skip_enable for A/B measurements)
-static std::atomic<int> g_tile_skip{-1};
-static bool tile_skip_on() {
-    int v = g_tile_skip.load();
-    if (v < 0) {
-        const char *e = getenv("VECGO_TILE_SKIP");
-        v = (e && e[0] == '0') ? 0 : 1;
-        g_tile_skip.store(v);
-    }
-    return v != 0;
-}
-void set_tile_skip(bool on) { g_tile_skip.store(on ? 1 : 0); }
 // Optional CUDA-event timing of the GEMM kernel on its own stream (bench.py's roofline line).
 static std::atomic<int> g_prof{0};
 static std::mutex g_prof_mu;
@@ -1897,71 +1886,6 @@ static vg_status launch_thresh(const float *kth, const float *qn, const float *c
     return VG_OK;
 }
 
-// Tile skipping.  A 256-row tile that lies wholly inside the segment and whose 256 bitmap bits are all clear cannot
-// contribute a row: the pair kernel then never fetches, decodes or multiplies it.  This is where the reference's
-// block-stat skipping lands on the device (flat/segment.go:524-541,613-630: a BlockSize = 1024-row block whose stats
-// cannot match the filter is jumped over — the host clears those blocks' bits, vg_index_search_blocks*), and the same
-// test also drops tiles emptied by tombstones or a selective metadata filter.
-//   list[0 .. *count)  active tiles, ascending (one block, ordered compaction: the work split is reproducible)
-//   skip[0 .. *nskip)  the others (their row groups get the "nothing here" entry the select kernel expects)
-__global__ void __launch_bounds__(1024) build_tile_list_kernel(const uint32_t *mask, int64_t rows, int ntiles, int32_t *list, int32_t *count,
-                                                               int32_t *skip, int32_t *nskip) {
-    __shared__ int wsum[32];
-    __shared__ int base_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid == 0) base_s = 0;
-    __syncthreads();
-    for (int t0 = 0; t0 < ntiles; t0 += 1024) {
-        const int t = t0 + tid;
-        bool act = false;
-        if (t < ntiles) {
-            const int64_t n0 = (int64_t)t * pair::TILE_ROWS;
-            if (n0 + pair::TILE_ROWS > rows) act = true;   // the ragged last tile is always scanned (as i + BlockSize <= end)
-            else {
-                uint32_t any = 0;
-#pragma unroll
-                for (int w = 0; w < pair::TILE_ROWS / 32; w++) any |= __ldg(mask + (n0 >> 5) + w);
-                act = any != 0;
-            }
-        }
-        const uint32_t b = __ballot_sync(0xffffffffu, act);
-        if (lane == 0) wsum[warp] = __popc(b);
-        __syncthreads();
-        int before = 0, total = 0;
-        for (int w = 0; w < 32; w++) {
-            const int c = wsum[w];
-            if (w < warp) before += c;
-            total += c;
-        }
-        const int base = base_s;
-        if (t < ntiles) {
-            const int rank_act = before + __popc(b & ((1u << lane) - 1u));
-            if (act) list[base + rank_act] = t;
-            else skip[(t0 - base) + (tid - rank_act)] = t;   // skipped tiles before t0 = t0 - base
-        }
-        __syncthreads();
-        if (tid == 0) base_s = base + total;
-        __syncthreads();
-    }
-    if (tid == 0) {
-        *count = base_s;
-        *nskip = ntiles - base_s;
-    }
-}
-// the minima-plane entries of the skipped tiles' row groups: (BIG, BIG) — what the epilogue writes for a group whose
-// rows are all masked (the exact stage drops any row it decodes from such an entry: its bitmap bit is clear)
-__global__ void __launch_bounds__(256) fill_skipped_groups_kernel(const int32_t *skip, const int32_t *nskip, int gpt, int64_t groups, int64_t nq,
-                                                                  float2 *mins) {
-    const int n = __ldg(nskip);
-    const float BIG = 3.0e38f;
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const int64_t g0 = (int64_t)__ldg(skip + i) * gpt;
-        for (int64_t q = threadIdx.x; q < nq; q += blockDim.x)
-            for (int j = 0; j < gpt; j++)
-                if (g0 + j < groups) mins[q * groups + g0 + j] = make_float2(BIG, BIG);
-    }
-}
-
 // One chunk of queries through filter, select and exact stage (d_kth == nullptr), or through the threshold pass:
 // thresholds from d_kth (the k-th best exact score known per query), threshold-collect GEMM, exact stage over the lists.
 static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const SearchIO &io, int kc, int32_t *d_fail, cudaStream_t st,
@@ -2038,21 +1962,12 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.dsub_shift = 0;
     while ((1 << a.dsub_shift) < cp.pq_dsub) a.dsub_shift++;
     a.tiled = (qc == Q_PQ && (cp.variant & VG_VAR_PERM)) ? 1 : 0;
-    DevBuf tl;  // active-tile list, skipped-tile list, the two counts
-    if (io.d_mask && pair_mode && tile_skip_on()) {
-        const int64_t nt = (rows + pair::TILE_ROWS - 1) / pair::TILE_ROWS;
-        const size_t list_ints = (size_t)nt + 1024;   // slack: a split's empty slice may start a few entries past the end
-        VG_TRY(tl.alloc((2 * list_ints + 2) * 4));
-        VG_CUDA(cudaMemsetAsync(tl.p, 0, (2 * list_ints + 2) * 4, st));
-        int32_t *list = tl.as<int32_t>(), *skip = list + list_ints, *cnt = skip + list_ints;
-        build_tile_list_kernel<<<1, 1024, 0, st>>>(a.mask, rows, (int)nt, list, cnt, skip, cnt + 1);
-        VG_LAUNCHED();
-        if (!thresh) {
-            fill_skipped_groups_kernel<<<(unsigned)(sm_count() * 4), 256, 0, st>>>(skip, cnt + 1, (int)(pair::TILE_ROWS / G), groups, nq, a.mins);
-            VG_LAUNCHED();
-        }
-        a.tile_list = list;
-        a.tile_count = cnt;
+    tiles::Lists tl;  // active / skipped 256-row tiles (tile skipping: vg_tiles.cuh)
+    if (io.d_mask && pair_mode && tiles::enabled()) {
+        VG_TRY(tiles::build(a.mask, rows, tl, st));
+        if (!thresh) VG_TRY(tiles::fill_skipped_groups(tl, (int)(pair::TILE_ROWS / G), groups, nq, a.mins, st));
+        a.tile_list = tl.list;
+        a.tile_count = tl.count;
     }
     if (thresh) {
         // ---- threshold pass: lists instead of the minima plane, no selection, no certificate

@@ -71,7 +71,6 @@ void stats(uint64_t *queries, uint64_t *fallbacks);
 // Returns the accumulated CUDA-event time / launch count of the GEMM kernel since the last reset; enable = 1 / 0 turns
 // the event pair around every GEMM launch on / off and resets the counters, enable < 0 only reads.
 void profile(int enable, double *gemm_ms, uint64_t *gemm_launches);
-void set_tile_skip(bool on);   // 256-row tiles without an allowed row are not fetched (pair kernel, with a row bitmap)
 
 }  // namespace qtc
 }  // namespace vg
