@@ -273,6 +273,12 @@ vg_status vg_index_search_blocks_dev(vg_index_t idx, const float *d_queries, int
 /* Tile skipping of the quantized tensor-core filters when a row bitmap is given (default on; VECGO_TILE_SKIP=0): off
  * only for A/B measurements — results are identical either way. */
 vg_status vg_tile_skip_enable(int32_t on);
+/* IVF-partitioned segments (num_partitions > 1, flat/segment.go:726-745): a query scans only the rows of its nprobes
+ * closest partitions.  The (query, partition) pairs of a batch are sorted by partition and scanned as independent
+ * virtual queries over that partition's row range, then merged per query: work and HBM traffic are nprobes /
+ * num_partitions of the full scan.  Off (VECGO_IVF_GROUPED=0) = the full scan with a per-row partition test — same
+ * results, for A/B measurements only. */
+vg_status vg_ivf_grouped_enable(int32_t on);
 /* Counters of the last vg_index_search* / vg_index_search_resolve call made by the calling thread: what a Go caller adds
  * to searcher.FilterGateStats / model.QueryStats (flat/segment.go:448-471,553-591).  distance_computations counts the
  * (query, row) distance evaluations the reference's scan would report (rows visited per query, plus the rows of every

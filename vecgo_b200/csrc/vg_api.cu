@@ -842,6 +842,19 @@ static qtc::SearchIO quant_io(Index *ix, const ScanArgs &a) {
 
 enum { SEARCH_EXACT = 0, SEARCH_FLAT_TC = 1, SEARCH_QUANT_TC = 2 };
 
+// IVF-partitioned segments scan only the probed partitions (scan_topk_partitioned); VECGO_IVF_GROUPED=0 selects the
+// full scan with a per-row partition test (same results; kept for A/B measurements).
+static std::atomic<int> g_ivf_grouped{-1};
+static bool partition_grouping() {
+    int v = g_ivf_grouped.load();
+    if (v < 0) {
+        const char *e = getenv("VECGO_IVF_GROUPED");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_ivf_grouped.store(v);
+    }
+    return v != 0;
+}
+
 // Which path a (shape, pointer alignment) takes; same answer in enqueue and resolve.
 static int search_mode(Index *ix, const float *d_queries, int64_t nq, int64_t k, const uint8_t *d_mask, const CodecParams *cp_ready) {
     const vg_index_desc &d = ix->d;
@@ -904,6 +917,7 @@ static vg_status search_enqueue(Index *ix, const float *d_queries, int64_t nq, i
         return qtc::enqueue(t.cp, ix->qtc, quant_io(ix, t.a), 1, d_fail, st);
     }
     if (d_fail) VG_CUDA(cudaMemsetAsync(d_fail, 0, (size_t)nq * 4, st));
+    if (t.a.probe && partition_grouping()) return scan_topk_partitioned(t.cp, t.a, st);
     return scan_topk(t.cp, t.a, st);
 }
 
@@ -1097,6 +1111,11 @@ vg_status vg_index_search_blocks(vg_index_t idx, const float *h_queries, int64_t
     const vg_status rc = vg_index_search(idx, h_queries, nq, k, nprobes, m.data(), h_out_rows, h_out_scores, h_out_counts);
     t_rows_skipped = 0;
     return rc;
+}
+
+vg_status vg_ivf_grouped_enable(int32_t on) {
+    g_ivf_grouped.store(on != 0 ? 1 : 0);
+    return VG_OK;
 }
 
 vg_status vg_tile_skip_enable(int32_t on) {

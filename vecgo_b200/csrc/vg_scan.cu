@@ -988,9 +988,26 @@ __global__ void __launch_bounds__(Codec::THREADS, Codec::MINB) scan_topk_kernel(
     Codec::stage(P, A.queries, A.q_stride ? A.q_stride : P.dim, q0, nqv, smem, tid);
     topk_init(sink.tk, Codec::QT, tid, Codec::THREADS);
     __syncthreads();
-    const int64_t row_begin = (int64_t)split * A.rows_per_split;
+    int64_t row_begin = (int64_t)split * A.rows_per_split;
     int64_t row_end = row_begin + A.rows_per_split;
     if (row_end > A.rows) row_end = A.rows;
+    if (A.by_partition) {
+        // the block's rows: from the first to the last partition of its (sorted) virtual queries — one partition, or two
+        // neighbouring ones where the block straddles a boundary of the sorted list; the sink keeps each slot to its own
+        int64_t lo = A.rows, hi = 0;
+        for (int s = 0; s < nqv; s++) {
+            const int p = A.probe[q0 + s];
+            if (p < 0) continue;
+            const int64_t b = A.part_off[p], e = A.part_off[p + 1];
+            if (e > b) {
+                lo = b < lo ? b : lo;
+                hi = e > hi ? e : hi;
+            }
+        }
+        row_begin = lo / Codec::RB * Codec::RB;
+        row_end = hi < A.rows ? hi : A.rows;
+        if (row_end < row_begin) row_end = row_begin;
+    }
     if constexpr (is_pipelined<Codec>::value) {
         typename Codec::State stt;
         Codec::prefetch(P, stt, row_begin, row_end, tid);
@@ -1010,7 +1027,9 @@ __global__ void __launch_bounds__(Codec::THREADS, Codec::MINB) scan_topk_kernel(
     const int warp = tid >> 5, lane = tid & 31;
     for (int s = warp; s < nqv; s += Codec::THREADS / 32) {
         const int64_t q = q0 + s;
-        if (A.splits == 1)
+        if (A.by_partition)
+            topk_emit_keys_warp(sink.tk, s, lane, A.partial + (int64_t)A.emit_index[q] * A.k, A.k);
+        else if (A.splits == 1)
             topk_emit_warp(sink.tk, s, lane, A.descending != 0, A.out_rows + q * A.k, A.out_scores + q * A.k, A.out_counts + q,
                            A.k);
         else
@@ -1129,6 +1148,14 @@ static vg_status run_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st) {
     const size_t sm = qb + topk_smem_bytes(Codec::QT, a.C);
     if (sm > 227 * 1024) return fail(VG_ERR_UNSUPPORTED, "query tile + top-k state exceed 227 KB of shared memory (dim or k too large)");
     const int64_t qtiles = (a.nq + Codec::QT - 1) / Codec::QT;
+    if (a.by_partition) {  // one block per four virtual queries, no row splits; the caller owns `partial` and merges
+        a.splits = 1;
+        a.rows_per_split = a.rows;
+        VG_CUDA(cudaFuncSetAttribute(scan_topk_kernel<Codec>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        scan_topk_kernel<Codec><<<dim3((unsigned)qtiles, 1), Codec::THREADS, sm, st>>>(cp, a, qb);
+        VG_LAUNCHED();
+        return VG_OK;
+    }
     // Row splits only when the query tiles alone cannot fill the machine.
     const int64_t target = (int64_t)sm_count() * Codec::MINB;
     int64_t splits = 1;
@@ -1246,6 +1273,105 @@ vg_status dev_scatter_results(const uint32_t *d_rows, const float *d_scores, con
     VG_LAUNCHED();
     return VG_OK;
 }
+// ------------------------------------------------------------ partition-grouped scan
+__global__ void __launch_bounds__(256) vq_count_kernel(const int32_t *probe, int64_t nv, int P, int *hist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const int p = probe[i];
+    atomicAdd(&hist[(p >= 0 && p < P) ? p : P], 1);
+}
+// exclusive scan of hist[0 .. n) into cursor (one block)
+__global__ void __launch_bounds__(1024) vq_scan_kernel(const int *hist, int n, int *cursor) {
+    __shared__ int wsum[32];
+    __shared__ int carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        const int v = i < n ? hist[i] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) wsum[warp] = x;
+        __syncthreads();
+        int before = 0;
+        for (int w = 0; w < warp; w++) before += wsum[w];
+        const int carry = carry_s;
+        if (i < n) cursor[i] = carry + before + x - v;
+        __syncthreads();
+        if (tid == 1023) carry_s = carry + before + x;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(256) vq_scatter_kernel(const int32_t *probe, int64_t nv, int P, int np, int *cursor, int32_t *order,
+                                                         int32_t *probe_v, int32_t *qidx) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const int p = probe[i];
+    const bool ok = p >= 0 && p < P;
+    const int pos = atomicAdd(&cursor[ok ? p : P], 1);
+    order[pos] = (int32_t)i;
+    probe_v[pos] = ok ? p : -1;
+    qidx[pos] = (int32_t)(i / np);
+}
+vg_status scan_topk_partitioned(const CodecParams &cp, ScanArgs a, cudaStream_t st) {
+    if (a.nq <= 0) return VG_OK;
+    if (a.k <= 0) return fail(VG_ERR_INVALID, "k must be positive");
+    if (!a.probe || a.nprobe < 1 || !a.part_off || a.num_parts < 1) return fail(VG_ERR_INVALID, "partitioned scan without probes");
+    if (a.rows <= 0) return scan_topk(cp, a, st);
+    const int np = a.nprobe, P = a.num_parts;
+    const int64_t nv = a.nq * np, dim = cp.dim, k = a.k;
+    if (nv >= (1ll << 31)) return fail(VG_ERR_UNSUPPORTED, "too many (query, partition) pairs in one batch");
+    DevBuf hist, cursor, order, probe_v, qidx, vq, partial, vqw, vqn;
+    VG_TRY(hist.alloc((size_t)(P + 1) * 4));
+    VG_TRY(cursor.alloc((size_t)(P + 1) * 4));
+    VG_TRY(order.alloc((size_t)nv * 4));
+    VG_TRY(probe_v.alloc((size_t)nv * 4));
+    VG_TRY(qidx.alloc((size_t)nv * 4));
+    VG_TRY(vq.alloc((size_t)nv * dim * 4));
+    VG_TRY(partial.alloc((size_t)nv * k * 8));
+    VG_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)(P + 1) * 4, st));
+    vq_count_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(a.probe, nv, P, hist.as<int>());
+    VG_LAUNCHED();
+    vq_scan_kernel<<<1, 1024, 0, st>>>(hist.as<int>(), P + 1, cursor.as<int>());
+    VG_LAUNCHED();
+    vq_scatter_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(a.probe, nv, P, np, cursor.as<int>(), order.as<int32_t>(), probe_v.as<int32_t>(),
+                                                                   qidx.as<int32_t>());
+    VG_LAUNCHED();
+    gather_rows_kernel<<<(unsigned)((nv * dim + 255) / 256), 256, 0, st>>>(a.queries, a.q_stride ? a.q_stride : dim, qidx.as<int32_t>(), nv, dim,
+                                                                          vq.as<float>());
+    VG_LAUNCHED();
+    CodecParams cps = cp;
+    if (cp.q_words) {  // sign codecs scan prepared per-query sign words (+ norms)
+        VG_TRY(vqw.alloc((size_t)nv * cp.words32 * 4));
+        gather_rows_kernel<<<(unsigned)((nv * cp.words32 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float *>(cp.q_words), cp.words32,
+                                                                                    qidx.as<int32_t>(), nv, cp.words32, vqw.as<float>());
+        VG_LAUNCHED();
+        cps.q_words = vqw.as<uint32_t>();
+    }
+    if (cp.q_norms) {
+        VG_TRY(vqn.alloc((size_t)nv * 4));
+        gather_rows_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(cp.q_norms, 1, qidx.as<int32_t>(), nv, 1, vqn.as<float>());
+        VG_LAUNCHED();
+        cps.q_norms = vqn.as<float>();
+    }
+    ScanArgs av = a;
+    av.queries = vq.as<float>();
+    av.q_stride = 0;
+    av.nq = nv;
+    av.probe = probe_v.as<int32_t>();
+    av.nprobe = 1;
+    av.by_partition = 1;
+    av.emit_index = order.as<int32_t>();
+    av.partial = partial.as<unsigned long long>();
+    VG_TRY(scan_topk(cps, av, st));
+    // the nprobe sorted lists of query q sit at partial[(q * nprobe + j) * k]
+    return launch_merge_keys(av.partial, np, a.nq, k, k, (int64_t)np * k, a.descending != 0, (int)k, a.out_rows, a.out_scores, a.out_counts, st);
+}
+
 vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<int32_t> &which, cudaStream_t st) {
     const int64_t nb = (int64_t)which.size();
     if (nb == 0) return VG_OK;

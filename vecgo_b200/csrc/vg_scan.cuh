@@ -54,6 +54,11 @@ struct ScanArgs {
     int nprobe = 0;
     const uint32_t *part_off = nullptr;
     int num_parts = 0;
+    // Partition-grouped form (scan_topk_partitioned): the batch is nq x nprobe VIRTUAL queries sorted by probed partition,
+    // nprobe = 1, probe[v] = that partition; a block scans only the row ranges of its slots' partitions and writes
+    // the sorted keys of virtual query v to partial + emit_index[v] * k.
+    int by_partition = 0;
+    const int32_t *emit_index = nullptr;
     // outputs (splits == 1)
     uint32_t *out_rows = nullptr;
     float *out_scores = nullptr;
@@ -64,6 +69,12 @@ struct ScanArgs {
 
 // Full top-k scan of one index (chooses tile kernel, row splits and merge).
 vg_status scan_topk(const CodecParams &cp, ScanArgs a, cudaStream_t st);
+// IVF-partitioned segment (flat/segment.go:726-745): every query scans only the rows of its `nprobe` probed partitions.
+// The (query, partition) pairs are sorted by partition so that the four virtual queries of a block share a row range
+// and concurrent blocks of a partition hit the same rows in L2; each pair keeps its own top-k, merged per query at the
+// end.  Work and traffic are proportional to nprobe / num_partitions of the full scan; results are the full masked
+// scan's, bit for bit.
+vg_status scan_topk_partitioned(const CodecParams &cp, ScanArgs a, cudaStream_t st);
 // Exact re-run of a subset of the batch (`which`: query indices into a.queries / a.out_*): gathers those queries,
 // scans them with scan_topk and scatters the results back into a.out_rows / a.out_scores / a.out_counts.
 vg_status scan_topk_subset(const CodecParams &cp, ScanArgs a, const std::vector<int32_t> &which, cudaStream_t st);
