@@ -26,7 +26,23 @@ if "flat" in which:
         L.call("vg_flat_tc_enable", 1)
         ix.rerank(q, r1)
         ix.l2_bounded(q, r1, np.full(nq, 10.0, F))
+        # block-stat skipping: the CTA-pair filter (k > 16) over a tile list
+        keep = np.array([True, False, False, True, True, False, True, False])
+        r3, s3, _ = ix.search(q, 20, block_keep=keep)
+        L.call("vg_flat_tc_enable", 0)
+        r4, s4, _ = ix.search(q, 20, block_keep=keep)
+        L.call("vg_flat_tc_enable", 1)
+        assert np.array_equal(r3, r4) and np.array_equal(s3.view(np.uint32), s4.view(np.uint32))
     assert np.array_equal(r1, r2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32))
+    # IVF-partitioned segment: partition-grouped scan
+    data = vg.flat.write_segment(segment_id=1, vectors=x, metric=0, k_partitions=4, seed=1, kmeans_iters=2)
+    seg = vg.flat.Segment.Open(data)
+    g1 = seg.Search(q, k, nprobes=2)
+    L.call("vg_ivf_grouped_enable", 0)
+    g2 = seg.Search(q, k, nprobes=2)
+    L.call("vg_ivf_grouped_enable", 1)
+    seg.Close()
+    assert np.array_equal(g1[0], g2[0]) and np.array_equal(g1[1].view(np.uint32), g2[1].view(np.uint32))
     print("flat ok", flush=True)
 if "quant" in which:
     n, dim, nq, k = 8192, 128, 16, 10
@@ -54,6 +70,15 @@ if "quant" in which:
             r2, s2, _ = ix.search(q, k)
             L.call("vg_flat_tc_enable", 1)
             ix.score(q, r1)
+            keep = np.array([True, False, True, True, False, False, True, False])
+            r3, s3, _ = ix.search(q, k, block_keep=keep)     # tile list + skipped-group fill
+            L.call("vg_flat_tc_enable", 0)
+            r4, s4, _ = ix.search(q, k, block_keep=keep)
+            L.call("vg_flat_tc_enable", 1)
+            assert np.array_equal(r3, r4) and np.array_equal(s3.view(np.uint32), s4.view(np.uint32)), c["codec"]
+            if c["codec"] == L.CODEC_SQ8:
+                ix.set_host_vectors(v)                      # rerank from mapped host memory (staged gather)
+                ix.rerank(q, r1)
         assert np.array_equal(r1, r2) and np.array_equal(s1.view(np.uint32), s2.view(np.uint32)), c["codec"]
     print("quant ok", flush=True)
 if "misc" in which:
