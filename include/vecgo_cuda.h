@@ -270,6 +270,11 @@ vg_status vg_index_search_blocks(vg_index_t idx, const float *h_queries, int64_t
                                  const uint8_t *h_block_keep, uint32_t *h_out_rows, float *h_out_scores, int32_t *h_out_counts);
 vg_status vg_index_search_blocks_dev(vg_index_t idx, const float *d_queries, int64_t nq, int64_t k, int64_t nprobes, const uint8_t *d_row_mask,
                                      const uint8_t *h_block_keep, uint32_t *d_out_rows, float *d_out_scores, int32_t *d_out_counts);
+/* SQ8 filter through tcgen05 kind::i8 (raw code bytes as the unsigned B operand by TMA, query tile quantised to signed
+ * 8-bit per query, int32 accumulators; dim % 128 == 0, row-major or lane-transposed codes).  Default on (VECGO_QTC_I8=0);
+ * off = the fp16 decode-GEMM.  Results are identical either way (same exact stage, certificate with the measured
+ * quantisation error of each query). */
+vg_status vg_quant_tc_i8_enable(int32_t on);
 /* Tile skipping of the quantized tensor-core filters when a row bitmap is given (default on; VECGO_TILE_SKIP=0): off
  * only for A/B measurements — results are identical either way. */
 vg_status vg_tile_skip_enable(int32_t on);

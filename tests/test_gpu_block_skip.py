@@ -130,7 +130,7 @@ def test_block_skipping_matches_masked_scan(vg, codec, n, dim, kind):
 
 
 def test_block_skipping_device_entry_and_threshold_pass(vg):
-    """vg_index_search_blocks_dev with a device row bitmap, on data whose certificates fail (4000 identical rows): the
+    """vg_index_search_blocks_dev with a device row bitmap, on data whose certificates fail (15000 identical rows): the
     threshold pass walks the same tile list."""
     import torch
 
@@ -141,7 +141,7 @@ def test_block_skipping_device_entry_and_threshold_pass(vg):
     sq = vg.quantization.ScalarQuantizer(dim)
     sq.Train(x)
     codes = sq.EncodeBatch(x)
-    codes[5000:9000] = codes[5000]
+    codes[5000:20000] = codes[5000]    # ~470 groups of 32 tied rows: more than any candidate budget (64 groups with kind::i8)
     q = (x[5000] + 0.01 * rng.standard_normal((nq, dim))).astype(F)
     keep = np.ones(n // BLOCK, bool)
     keep[5:7] = False              # rows 5120 .. 7167 of the tied range are jumped over

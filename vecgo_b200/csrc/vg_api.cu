@@ -1118,6 +1118,11 @@ vg_status vg_ivf_grouped_enable(int32_t on) {
     return VG_OK;
 }
 
+vg_status vg_quant_tc_i8_enable(int32_t on) {
+    qtc::set_i8(on != 0);
+    return VG_OK;
+}
+
 vg_status vg_tile_skip_enable(int32_t on) {
     tiles::set_enabled(on != 0);
     return VG_OK;

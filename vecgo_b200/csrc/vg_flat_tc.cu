@@ -1010,6 +1010,20 @@ vg_status tensor_map_2d(void *map, bool f16, const void *base, int64_t rows, int
     return VG_OK;
 }
 
+// the same for byte matrices (kind::i8 operands): box_cols bytes x box_rows rows, 128-byte swizzle
+vg_status tensor_map_2d_u8(void *map, const void *base, int64_t rows, int64_t cols, int64_t stride_bytes, int box_cols, int box_rows) {
+    VG_TRY(get_encode());
+    const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)stride_bytes};
+    const cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = g_encode(reinterpret_cast<CUtensorMap *>(map), CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(VG_ERR_CUDA, "cuTensorMapEncodeTiled (uint8) failed (code " + std::to_string((int)r) + ")");
+    return VG_OK;
+}
+
 int64_t group_rows(int64_t rows, int kc) {
     // minimum groups of G rows: about 128*kc groups make tau tight (two of the best kc rows rarely share a group)
     // while the exact scan of kc*G rows per query stays ~1% of the GEMM's work

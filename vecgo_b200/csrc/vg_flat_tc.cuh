@@ -45,6 +45,7 @@ vg_status select_groups(const float2 *d_mins, int64_t groups, int64_t nq, int kc
                         int32_t *d_gcnt, cudaStream_t st);
 // CUtensorMap (`map` points at one) over a row-major [rows][cols] matrix of float32 or float16, 128-byte swizzled boxes.
 vg_status tensor_map_2d(void *map, bool f16, const void *base, int64_t rows, int64_t cols, int64_t stride_elems, int box_cols, int box_rows);
+vg_status tensor_map_2d_u8(void *map, const void *base, int64_t rows, int64_t cols, int64_t stride_bytes, int box_cols, int box_rows);
 // TF32 GEMM with group-minimum epilogue → tau and the kc best groups per query.
 vg_status filter(const FilterArgs &f, cudaStream_t st);
 // Exact scores of the candidate rows in simd pair order, top-k by (score,row), certificate → d_fail[q] (1 = re-run exactly).

@@ -79,6 +79,9 @@ constexpr size_t OFF_XN = (size_t)STAGES * STAGE_BYTES;
 constexpr size_t OFF_BAR = OFF_XN + (size_t)2 * BN * 4;
 constexpr size_t SMEM_BYTES = OFF_BAR + (size_t)(2 * STAGES + 4) * 8 + 16 + 1024;  // + slack for the 1024-byte alignment
 constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2, Q_RABITQ = 3, Q_BQ = 4;
+// GEMM-only variant of SQ8 (qtc2_kernel): kind::i8 — the raw code bytes ARE the B operand (unsigned 8-bit, loaded by TMA,
+// no decode warps), the query tile is quantised to signed 8-bit per query; everything after the GEMM is Q_SQ8's.
+constexpr int Q_SQ8I = 5;
 // sign-bit codes (RaBitQ, BQ): the B tile is +-1, the GEMM is exact (acc = D - 2 Hamming)
 __host__ __device__ constexpr bool sign_codec(int c) { return c == Q_RABITQ || c == Q_BQ; }
 constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage (work bound; beyond it the query goes to the exact scan)
@@ -535,7 +538,7 @@ constexpr int B2_BYTES = BN * BK * 2;   // 16 KB: this CTA's 128 rows x 64 halve
 constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
 constexpr int TILE_ROWS = 2 * BN;       // 256 rows per pair tile
 constexpr size_t OFF_XN2 = (size_t)STAGES2 * STAGE2_BYTES;
-constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)2 * TILE_ROWS * 4;
+constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)4 * TILE_ROWS * 4;   // row-norm staging: two buffers per epilogue group
 constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 8) * 8 + 16 + 1024;
 
 }  // namespace pair
@@ -547,7 +550,8 @@ constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 8) * 8 + 16 + 1
 // second pass for queries whose certificate failed (tightly clustered data: thousands of rows within E of the k-th
 // best), where "a few more candidate groups" cannot help.
 template <int CODEC, bool THRESH>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_kernel(const __grid_constant__ CUtensorMap map_q, KArgs A) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_x, KArgs A) {
     using namespace pair;
     extern __shared__ unsigned char smem_raw[];
     __shared__ uint32_t tmem_base_slot;
@@ -582,7 +586,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
     constexpr uint32_t SLICE_BYTES = 16384;  // 64 dims x 256 centroids x 1 byte, whatever dsub is
     constexpr uint32_t OFF_SLICE = (uint32_t)NST * STAGE2_BYTES;
     constexpr uint32_t OFF_XN = OFF_SLICE + (CODEC == Q_PQ ? 2 * SLICE_BYTES : 0);
-    constexpr uint32_t OFF_BAR = OFF_XN + 2 * TILE_ROWS * 4;
+    constexpr uint32_t OFF_BAR = OFF_XN + 4 * TILE_ROWS * 4;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar0 = s_base + OFF_BAR;
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
@@ -595,7 +599,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NST; s++) {
-            mbar_init(full_bar(s), 1 + 4 + 4);  // leader's expect_tx arrive + one decode group (4 warps) of each CTA
+            // leader's expect_tx arrive + one decode group (4 warps) of each CTA; kind::i8: both operands arrive by TMA
+            mbar_init(full_bar(s), CODEC == Q_SQ8I ? 1 : 1 + 4 + 4);
             mbar_init(empty_bar(s), 1);
         }
         for (int s = 0; s < 2; s++) {
@@ -635,14 +640,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                                  : "memory");
                 }
                 mbar_wait(empty_bar(st), ph ^ 1);
-                if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
-                tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
+                if constexpr (CODEC == Q_SQ8I) {
+                    // 128 query bytes and 128 code bytes per row and k-block, straight from global memory
+                    if (leader) mbar_expect_tx(full_bar(st), 2 * STAGE2_BYTES);
+                    const int n0 = (int)(tile_row0(it / A.kb) + (int64_t)rank * BN);
+                    tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * 128, q0, full_bar(st));
+                    tma_load_2d_pair(s_base + st * STAGE2_BYTES + A2_BYTES, &map_x, kb * 128, n0, full_bar(st));
+                } else {
+                    if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
+                    tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16_pair();
+            constexpr uint32_t idesc = CODEC == Q_SQ8I ? make_idesc_i8_pair() : make_idesc_f16_pair();
             int it = 0;
             for (int t = 0; t < ntiles; t++) {
                 const int as = t & 1;
@@ -658,18 +671,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                     const uint32_t sa = s_base + st * STAGE2_BYTES;
                     const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A2_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++)
-                        umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; k++) {  // 32 bytes of K per instruction: 16 halves or 32 bytes
+                        if constexpr (CODEC == Q_SQ8I) umma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit_pair(empty_bar(st));
                 }
                 umma_commit_pair(tfull_bar(as));
             }
         }
-    } else if (warp < PROD_WARP0) {
+    } else if (warp < PROD_WARP0 || CODEC == Q_SQ8I) {
         // ===================== epilogue: warps 2..9; thread = one query x one 128-column half of the tile =====================
-        const int quad = warp & 3;
-        const int colhalf = (warp - 2) >> 2;
-        const int et = (warp - 2) * 32 + lane;
+        // kind::i8 has no decode warps and an MMA twice as fast: warps 10..17 are a SECOND epilogue group; group g takes the
+        // tiles t = g, g + 2, ... (= accumulator stage g), so each group has two tile times per tile.
+        constexpr int EG = CODEC == Q_SQ8I ? 2 : 1;
+        const int eg = EG == 2 ? (warp - 2) >> 3 : 0;
+        const int wl = (warp - 2) & 7;          // warp inside its group
+        const int quad = warp & 3;              // TMEM lane quarter this warp may read
+        const int colhalf = wl >> 2;
+        const int et = wl * 32 + lane;
         const int64_t q = (int64_t)q0 + quad * 32 + lane;
         float *xs = reinterpret_cast<float *>(smem + OFF_XN);
         const float BIG = 3.0e38f;
@@ -680,7 +700,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
         // threshold mode: this thread's list and threshold
         const bool qlive = q < A.nq;
         const float T = (THRESH && qlive) ? fminf(__ldg(A.Ts + q), 2.9e38f) : -BIG;   // masked / padding rows carry BIG: never listed
-        const int myslot = split * 2 + colhalf;
+        const int myslot = (split * EG + eg) * 2 + colhalf;
         uint2 *mylist = THRESH ? A.cand + ((size_t)(qlive ? q : 0) * A.slots + myslot) * A.cap : nullptr;
         int ncand = 0;
         // row norms of a tile are fetched one tile ahead (global-load latency out of the per-tile critical path): the value
@@ -691,14 +711,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             if constexpr (CODEC == Q_BQ) return (row < row_end) ? A.half_dim : BIG;  // s = D / 2 - acc / 2 = Hamming, exact
             else return (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
         };
-        if (ntiles > 0) xs[et] = xn_of(0);
-        for (int t = 0; t < ntiles; t++) {
+        // staging buffer of tile t: two per epilogue group (a group's next tile is written while slower warps of the group may
+        // still read the current one)
+        auto xbuf = [&](int t_) { return EG == 2 ? eg * 2 + ((t_ >> 1) & 1) : (t_ & 1); };
+        if (eg < ntiles) xs[xbuf(eg) * TILE_ROWS + et] = xn_of(eg);
+        for (int t = eg; t < ntiles; t += EG) {
             const int as = t & 1;
             const uint32_t aph = (t >> 1) & 1;
             const int64_t n0 = tile_row0(t);
-            float *xt = xs + as * TILE_ROWS;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            const float xn_next = (t + 1 < ntiles) ? xn_of(t + 1) : 0.0f;
+            float *xt = xs + xbuf(t) * TILE_ROWS;
+            if (EG == 2 && eg == 1) asm volatile("bar.sync 2, 256;" ::: "memory");
+            else asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float xn_next = (t + EG < ntiles) ? xn_of(t + EG) : 0.0f;
             mbar_wait(tfull_bar(as), aph);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(as * TILE_ROWS + colhalf * BN);
@@ -718,7 +742,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                     const float xx[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const float t = __fmaf_rn(fq, __uint_as_float(v[j4 * 4 + i]), xx[i]);
+                        // kind::i8 accumulates in int32 (|acc| <= 768 * 127 * 255 < 2^25: the conversion is exact or within 2^-24)
+                        const float accf = CODEC == Q_SQ8I ? __int2float_rn((int)v[j4 * 4 + i]) : __uint_as_float(v[j4 * 4 + i]);
+                        const float t = __fmaf_rn(fq, accf, xx[i]);
                         s[j4 * 4 + i] = CODEC == Q_RABITQ ? __fmul_rn(t, xx[i]) : t;  // RaBitQ: yn^2 - (2 qn / D) yn acc
                     }
                 }
@@ -775,7 +801,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
                 }
                 }
             }
-            if (t + 1 < ntiles) xs[((t + 1) & 1) * TILE_ROWS + et] = xn_next;
+            if (t + EG < ntiles) xs[xbuf(t + EG) * TILE_ROWS + et] = xn_next;
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(tempty_bar(as), 0);
@@ -807,7 +833,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) qtc2_ke
             }
         };
         const int64_t half_off = (int64_t)rank * BN;   // this CTA's half of every tile
-        if constexpr (CODEC == Q_PQ) {
+        if constexpr (CODEC == Q_SQ8I) {
+            (void)grp;   // kind::i8: the code bytes are the operand, TMA delivers them — these warps have nothing to decode
+            (void)half_off;
+        } else if constexpr (CODEC == Q_PQ) {
             const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
             const int swz = r & 7;
             auto row_of = [&](int t) {
@@ -969,6 +998,69 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *queries,
     }
 }
 
+// kind::i8 form of the query tile (SQ8).  a_p = q[perm[p]] * w[p] as above, quantised per query to signed 8-bit:
+// Delta = max|a_p| / 127, ah_p = rint(a_p / Delta), e_p = a_p - Delta ah_p.  With the RAW code bytes c_p = b_p + 128 as the
+// B operand the GEMM gives acc = sum ah_p c_p exactly, and
+//     sum a_p b_p = Delta acc - 128 Delta sum ah_p + sum e_p b_p
+// so the epilogue's s' = ||x^||^2 - 2 Delta acc differs from the fp16 filter's target by the per-query constant
+// 256 Delta sum ah_p (folded into c_q) and by 2 sum e_p b_p, which Cauchy-Schwarz bounds by
+// 2 ||e / w|| ||x^ - mid|| = ea[q] * max ||x^ - mid||: the term that replaces c1 ||q|| max||x^ - mid|| in the certificate.
+__global__ void __launch_bounds__(256) prep_queries_i8_kernel(const float *queries, int64_t nq, int64_t q_stride, int dimp, const int32_t *perm,
+                                                              const float *wq, const float *midp, int8_t *a8, float *fq, float *cq, float *ea) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const float *qv = queries + q * q_stride;
+    float mx = 0.0f;
+    double cm = 0.0;
+    for (int p = lane; p < dimp; p += 32) {
+        const int d = perm[p];
+        if (d >= 0) {
+            mx = fmaxf(mx, fabsf(__fmul_rn(qv[d], wq[p])));
+            cm += (double)qv[d] * (double)midp[p];
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        cm += __shfl_xor_sync(0xffffffffu, cm, o);
+    }
+    const bool ok = mx > 0.0f && mx < __int_as_float(0x7f800000);
+    const float delta = ok ? __fdiv_rn(mx, 127.0f) : 0.0f;
+    const float inv = ok ? __fdiv_rn(127.0f, mx) : 0.0f;
+    double err2 = 0.0;
+    int suma = 0;
+    bool bad = false;
+    for (int p = lane; p < dimp; p += 32) {
+        const int d = perm[p];
+        int ah = 0;
+        if (d >= 0) {
+            const float a = __fmul_rn(qv[d], wq[p]);
+            if (!(fabsf(a) <= mx)) bad = true;   // NaN
+            ah = __float2int_rn(__fmul_rn(a, inv));
+            ah = ah > 127 ? 127 : (ah < -127 ? -127 : ah);
+            const double e = (double)a - (double)delta * (double)ah;
+            if (wq[p] != 0.0f) {
+                const double ew = e / (double)wq[p];
+                err2 += ew * ew;
+            }
+            suma += ah;
+        }
+        a8[q * dimp + p] = (int8_t)ah;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        err2 += __shfl_xor_sync(0xffffffffu, err2, o);
+        suma += __shfl_xor_sync(0xffffffffu, suma, o);
+        bad = __shfl_xor_sync(0xffffffffu, bad ? 1 : 0, o) || bad;
+    }
+    if (lane == 0) {
+        fq[q] = __fmul_rn(-2.0f, delta);
+        // s'_true = s'_filter + 256 Delta sum ah - 2 sum e b;  reference ~ s'_true + c_q + ||q||^2 with c_q = -2 q.mid
+        cq[q] = (float)(-2.0 * cm + 256.0 * (double)delta * (double)suma);
+        const bool finite_q = (mx == 0.0f) || ok;
+        ea[q] = (bad || !finite_q) ? __int_as_float(0x7f800000) : (float)(2.0 * sqrt(err2) * 1.000001 + 1.0e-30);
+    }
+}
+
 // RaBitQ: the query side of the estimator (rabitq.go:119-176) is sign(q) and ||q||, both already prepared for the exact
 // scan (prep_sign_queries): a_p = +-1 in storage order, f_q = -2 ||q|| / D, c_q = ||q||^2, so that
 // dist = (qn - yn)^2 + (4 qn yn / D) h = c_q + yn^2 + f_q yn acc   with acc = sum s_q s_x = D - 2 h  (exact in fp16 x fp16 -> fp32).
@@ -1023,6 +1115,7 @@ struct EArgs {
     const int32_t *gcnt;
     int kc, G;
     const float *tau, *qn, *cq;
+    const float *ea;                // kind::i8 filter: per-query operand-quantisation term (replaces c1 ||q||), else nullptr
     const unsigned int *xmax_bits;  // [0] max ||x^||^2, [1] max ||x^ - mid||^2 (float bits)
     float mid_norm;                 // ||mid||
     const uint8_t *mask;
@@ -1342,7 +1435,8 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
                     const double qn_ = sqrt(qq), bn = sqrt(bb);
                     const double c1 = 1.125 / 1024.0, c2 = 1.0 / 16384.0 + (double)E.dim / 8388608.0;
                     const double smax = xx + 2.0 * qn_ * bn;  // |s'| of any row
-                    const double Eb = c1 * qn_ * bn + c2 * (qq + fmax(xx, bb)) + smax * (1.0 / 4194304.0 + (double)E.G / 8388608.0) +
+                    const double ca = E.ea ? (double)E.ea[q] : c1 * qn_;   // operand rounding: int8 (measured per query) or fp16 (2^-11 relative)
+                    const double Eb = ca * bn + c2 * (qq + fmax(xx, bb)) + smax * (1.0 / 4194304.0 + (double)E.G / 8388608.0) +
                                       qn_ * ((double)E.mid_norm + bn) / 2097152.0;
                     const double eref = ((double)E.dim + 64.0) / 16777216.0;  // the reference's own float32 summation
                     const double ex = (double)E.out_scores[q * E.k + (E.k - 1)];
@@ -1366,7 +1460,7 @@ __global__ void __launch_bounds__(128) qtc_exact_kernel(EArgs E) {
 // goes to the exact scan.
 template <int CODEC>
 __global__ void __launch_bounds__(256) qtc_thresh_kernel(const float *kth, const float *qn, const float *cq, const unsigned int *xmax_bits,
-                                                         float mid_norm, int dim, int64_t nq, float *Ts) {
+                                                         float mid_norm, int dim, int64_t nq, float *Ts, const float *ea) {
     const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     const double U = (double)kth[q];
@@ -1385,7 +1479,8 @@ __global__ void __launch_bounds__(256) qtc_thresh_kernel(const float *kth, const
         const double qn_ = sqrt(qq), bn = sqrt(bb);
         const double c1 = 1.125 / 1024.0, c2 = 1.0 / 16384.0 + (double)dim / 8388608.0;
         const double smax = xx + 2.0 * qn_ * bn;
-        const double Eb = c1 * qn_ * bn + c2 * (qq + fmax(xx, bb)) + smax / 4194304.0 + qn_ * ((double)mid_norm + bn) / 2097152.0;
+        const double ca = ea ? (double)ea[q] : c1 * qn_;
+        const double Eb = ca * bn + c2 * (qq + fmax(xx, bb)) + smax / 4194304.0 + qn_ * ((double)mid_norm + bn) / 2097152.0;
         const double eref = ((double)dim + 64.0) / 16777216.0;
         // unlisted: reference >= (T + c_q - Eb + ||q||^2)(1 - eref) - eref ||q||^2
         Td = (U + eref * qq) / (1.0 - eref) - (double)cq[q] - qq + Eb;
@@ -1833,6 +1928,28 @@ vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries
 
 static int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }
 
+// SQ8 through kind::i8 (twice the kind::f16 rate, no decode): on unless VECGO_QTC_I8=0 / set_i8(false).  The 8-bit query
+// tile makes the certificate margin ~13x the fp16 one, so the filter keeps 2.5x the candidate groups (5k instead of 2k);
+// shapes whose candidate count would not fit stay on the fp16 kernel.
+static std::atomic<int> g_i8{-1};
+static bool i8_on() {
+    int v = g_i8.load();
+    if (v < 0) {
+        const char *e = getenv("VECGO_QTC_I8");
+        v = (e && e[0] == '0') ? 0 : 1;
+        g_i8.store(v);
+    }
+    return v != 0;
+}
+void set_i8(bool on) { g_i8.store(on ? 1 : 0); }
+static int candidates_i8(int64_t k) { return k <= 16 ? 64 : (int)(5 * k); }
+static bool use_i8(const CodecParams &cp, int64_t rows, int64_t k) {
+    if (!i8_on() || !use_pair() || q_codec(cp) != Q_SQ8) return false;
+    if (cp.dim % 128 != 0 || cp.row_bytes != cp.dim) return false;        // 128-byte k-blocks, TMA row stride % 16
+    const int kc = candidates_i8(k);
+    return kc <= 2048 && rows / 32 >= 4 * (int64_t)kc;
+}
+
 template <int CODEC>
 static vg_status launch_gemm(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st) {
     const size_t sm = SMEM_BYTES;
@@ -1843,11 +1960,11 @@ static vg_status launch_gemm(const CUtensorMap &mq, const KArgs &a, int64_t qtil
     return VG_OK;
 }
 template <int CODEC, bool THRESH = false>
-static vg_status launch_gemm_pair(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st) {
+static vg_status launch_gemm_pair(const CUtensorMap &mq, const KArgs &a, int64_t qtiles, int splits, cudaStream_t st, const CUtensorMap *mx = nullptr) {
     const size_t sm = pair::SMEM2_BYTES;
     VG_CUDA(cudaFuncSetAttribute(qtc2_kernel<CODEC, THRESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     dim3 grid((unsigned)(2 * qtiles), (unsigned)splits);  // clusters of two CTAs along x (__cluster_dims__)
-    qtc2_kernel<CODEC, THRESH><<<grid, NTHREADS, sm, st>>>(mq, a);
+    qtc2_kernel<CODEC, THRESH><<<grid, NTHREADS, sm, st>>>(mq, mx ? *mx : mq, a);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1880,8 +1997,8 @@ static vg_status launch_exact_list(const EArgs &e, int64_t nq, const uint2 *cand
 }
 template <int CODEC>
 static vg_status launch_thresh(const float *kth, const float *qn, const float *cq, const unsigned int *xmax_bits, float mid_norm, int dim,
-                               int64_t nq, float *Ts, cudaStream_t st) {
-    qtc_thresh_kernel<CODEC><<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(kth, qn, cq, xmax_bits, mid_norm, dim, nq, Ts);
+                               int64_t nq, float *Ts, cudaStream_t st, const float *ea = nullptr) {
+    qtc_thresh_kernel<CODEC><<<(unsigned)((nq + 255) / 256), 256, 0, st>>>(kth, qn, cq, xmax_bits, mid_norm, dim, nq, Ts, ea);
     VG_LAUNCHED();
     return VG_OK;
 }
@@ -1899,8 +2016,11 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     const int64_t groups = (rows + G - 1) / G;
     const bool thresh = d_kth != nullptr;
     if (thresh && !pair_mode) return fail(VG_ERR_UNSUPPORTED, "the threshold pass needs the CTA-pair kernel");
-    DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau;
-    VG_TRY(a16.alloc((size_t)nq * pp.dimp * 2));
+    const bool i8 = pair_mode && use_i8(cp, rows, io.k);
+    DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau, eab;
+    VG_TRY(a16.alloc((size_t)nq * pp.dimp * (i8 ? 1 : 2)));
+    if (i8) VG_TRY(eab.alloc((size_t)nq * 4));
+    const float *ea_p = i8 ? eab.as<float>() : nullptr;
     VG_TRY(fq.alloc((size_t)nq * 4));
     VG_TRY(cq.alloc((size_t)nq * 4));
     VG_TRY(qn.alloc((size_t)nq * 4));
@@ -1918,11 +2038,20 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_LAUNCHED();
     } else {
     VG_TRY(tc::sqnorms(io.d_queries, nq, cp.dim, q_stride, qn.as<float>(), nullptr, st));
-    prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.wq.as<float>(),
-                                                                          pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
+    if (i8)
+        prep_queries_i8_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(),
+                                                                                 pp.wq.as<float>(), pp.midp.as<float>(), a16.as<int8_t>(), fq.as<float>(),
+                                                                                 cq.as<float>(), eab.as<float>());
+    else
+        prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.wq.as<float>(),
+                                                                              pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
     VG_LAUNCHED();
     }
-    CUtensorMap mq;
+    CUtensorMap mq, mx;
+    if (i8) {
+        VG_TRY(tc::tensor_map_2d_u8(&mq, a16.p, nq, pp.dimp, pp.dimp, 128, BM));
+        VG_TRY(tc::tensor_map_2d_u8(&mx, cp.codes, rows, cp.dim, cp.row_bytes, 128, BN));
+    } else
     VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, pair_mode ? BM : BMQ));
     // row splits: one CTA (pair) per SM (pair), whole waves
     const int64_t unit = pair_mode ? pair::TILE_ROWS : std::max<int64_t>(BN, G);
@@ -1950,7 +2079,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.nq = nq;
     a.rows = rows;
     a.rows_per_split = rps;
-    a.kb = pp.dimp / BK;
+    a.kb = i8 ? pp.dimp / 128 : pp.dimp / BK;
     a.cpg = (int)(G / 32);
     a.mins = mins.as<float2>();
     a.groups = groups;
@@ -1971,7 +2100,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     }
     if (thresh) {
         // ---- threshold pass: lists instead of the minima plane, no selection, no certificate
-        const int slots = (int)splits * 2;
+        const int slots = (int)splits * (i8 ? 4 : 2);   // (split, epilogue group, column half)
         int64_t cap = ((int64_t)4 << 30) / std::max<int64_t>(1, nq * slots * 8);   // <= 4 GiB of lists per chunk
         cap = std::max<int64_t>(64, std::min<int64_t>(8192, cap));
         DevBuf Ts, cand, ccnt, ovf;
@@ -1982,7 +2111,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_CUDA(cudaMemsetAsync(ovf.p, 0, (size_t)nq * 4, st));
         const float *qn_p = qn.as<float>(), *cq_p = cq.as<float>();
         const unsigned int *xm = pp.xmax.as<unsigned int>();
-        if (qc == Q_SQ8) VG_TRY(launch_thresh<Q_SQ8>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        if (qc == Q_SQ8) VG_TRY(launch_thresh<Q_SQ8>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st, ea_p));
         else if (qc == Q_INT4) VG_TRY(launch_thresh<Q_INT4>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
         else if (qc == Q_RABITQ) VG_TRY(launch_thresh<Q_RABITQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
         else if (qc == Q_BQ) VG_TRY(launch_thresh<Q_BQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
@@ -1994,7 +2123,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         a.ovf = ovf.as<int>();
         a.cap = (int)cap;
         a.slots = slots;
-        if (qc == Q_SQ8) VG_TRY((launch_gemm_pair<Q_SQ8, true>(mq, a, qtiles, (int)splits, st)));
+        if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I, true>(mq, a, qtiles, (int)splits, st, &mx)));
+        else if (qc == Q_SQ8) VG_TRY((launch_gemm_pair<Q_SQ8, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_RABITQ) VG_TRY((launch_gemm_pair<Q_RABITQ, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_BQ) VG_TRY((launch_gemm_pair<Q_BQ, true>(mq, a, qtiles, (int)splits, st)));
@@ -2028,7 +2158,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_CUDA(cudaEventRecord(g_ev[0], st));
     }
     if (pair_mode) {
-        if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
+        if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I>(mq, a, qtiles, (int)splits, st, &mx)));
+        else if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_RABITQ) VG_TRY(launch_gemm_pair<Q_RABITQ>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_BQ) VG_TRY(launch_gemm_pair<Q_BQ>(mq, a, qtiles, (int)splits, st));
@@ -2051,6 +2182,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     e.tau = tau.as<float>();
     e.qn = qn.as<float>();
     e.cq = cq.as<float>();
+    e.ea = ea_p;
     e.mid_norm = pp.mid_norm;
     e.xmax_bits = pp.xmax.as<unsigned int>();
     e.mask = io.d_mask;
@@ -2087,11 +2219,10 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
 // Candidate groups per query of the first pass and of the second chance (twice as many: a wider gap between the k-th
 // best and tau); 0 when the segment is too short for a second pass to differ.
 static int kc_for(const CodecParams &cp, int64_t rows, int k, int kc_scale) {
-    const int kc = candidates_for(k);
+    const int kc = use_i8(cp, rows, k) ? candidates_i8(k) : candidates_for(k);
     if (kc_scale <= 1) return kc;
     const int kc2 = kc * kc_scale;
     if (kc2 > 4096 || rows / 32 < 2 * (int64_t)kc2) return 0;
-    (void)cp;
     return kc2;
 }
 bool second_chance_possible(const CodecParams &cp, int64_t rows, int64_t k) { return kc_for(cp, rows, (int)k, 2) > 0; }
@@ -2129,7 +2260,7 @@ void count_fallbacks(uint64_t n) { g_fallbacks.fetch_add(n); }
 vg_status enqueue_threshold(const CodecParams &cp, const Prepared &pp, const SearchIO &io, const float *d_kth, int32_t *d_fail,
                             cudaStream_t st) {
     if (!pp.ready) return fail(VG_ERR_STATE, "decode-GEMM filter state was not prepared");
-    const int kc = candidates_for(io.k);
+    const int kc = kc_for(cp, io.rows, io.k, 1);
     // lists are sized per chunk (<= 4 GiB): chunks of at most 64 query tiles
     const int64_t chunk = 64 * BMQ;
     for (int64_t q0 = 0; q0 < io.nq; q0 += chunk) {

@@ -142,6 +142,22 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
                  "h"((unsigned short)3)
                  : "memory");
 }
+// kind::i8: 8-bit integer operands (K = 32 per instruction), int32 accumulators in TMEM — twice the kind::f16 rate on sm_100a
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// M = 256, N = 256, A = signed 8-bit, B = UNSIGNED 8-bit, int32 accumulate, K-major A and B
+// (instruction descriptor: c_format [4,6) = 2 (S32), a_format [7,10) = 1 (signed), b_format [10,13) = 0 (unsigned))
+__host__ __device__ constexpr uint32_t make_idesc_i8_pair() {
+    return (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
 // M = 256, N = 256, fp16 operands, fp32 accumulate, K-major A and B
 __host__ __device__ constexpr uint32_t make_idesc_f16_pair() { return (1u << 4) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
 }  // namespace pair
