@@ -539,7 +539,7 @@ constexpr int STAGE2_BYTES = A2_BYTES + B2_BYTES;
 constexpr int TILE_ROWS = 2 * BN;       // 256 rows per pair tile
 constexpr size_t OFF_XN2 = (size_t)STAGES2 * STAGE2_BYTES;
 constexpr size_t OFF_BAR2 = OFF_XN2 + (size_t)4 * TILE_ROWS * 4;   // row-norm staging: two buffers per epilogue group
-constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)(2 * STAGES2 + 8) * 8 + 16 + 1024;
+constexpr size_t SMEM2_BYTES = OFF_BAR2 + (size_t)40 * 8 + 16 + 1024;   // 40 mbarrier slots (kind::i8 uses 20..36)
 
 }  // namespace pair
 
@@ -596,12 +596,27 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     auto sfull_bar = [&](int s) { return bar0 + 8u * (2 * NST + 4 + s); };
     auto sempty_bar = [&](int s) { return bar0 + 8u * (2 * NST + 6 + s); };
     constexpr uint32_t TMEM_COLS = 512;  // 2 accumulator stages x 256 columns
+    // kind::i8 (SQ8I): the CTA's 128 queries x dim bytes stay RESIDENT in shared memory (kb x 16 KB at offset 0, loaded once)
+    // and only the code tiles stream: nstb stages of 16 KB behind them, inside the 192 KB the other codecs use for their
+    // six 32 KB stages.  Reloading the query k-blocks with every row tile doubled the L2 -> SM traffic (ncu: 10.8 TB/s,
+    // tensor pipe 69 % active).
+    const int nstb = 12 - A.kb < 8 ? 12 - A.kb : 8;
+    auto bfull_bar = [&](int s) { return bar0 + 8u * (20 + s); };
+    auto bempty_bar = [&](int s) { return bar0 + 8u * (28 + s); };
+    const uint32_t afull_bar = bar0 + 8u * 36;
+    const uint32_t b_base = s_base + (uint32_t)A.kb * A2_BYTES;
 
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NST; s++) {
-            // leader's expect_tx arrive + one decode group (4 warps) of each CTA; kind::i8: both operands arrive by TMA
-            mbar_init(full_bar(s), CODEC == Q_SQ8I ? 1 : 1 + 4 + 4);
+            mbar_init(full_bar(s), 1 + 4 + 4);  // leader's expect_tx arrive + one decode group (4 warps) of each CTA
             mbar_init(empty_bar(s), 1);
+        }
+        if constexpr (CODEC == Q_SQ8I) {
+            for (int s = 0; s < 8; s++) {
+                mbar_init(bfull_bar(s), 1);     // the leader's expect_tx arrive; both CTAs' TMA bytes land here
+                mbar_init(bempty_bar(s), 1);
+            }
+            mbar_init(afull_bar, 1);
         }
         for (int s = 0; s < 2; s++) {
             mbar_init(tfull_bar(s), 1);
@@ -623,7 +638,24 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     const uint32_t tmem_base = tmem_base_slot;
     const int total_it = ntiles * A.kb;
 
-    if (warp == 0) {
+    if (warp == 0 && CODEC == Q_SQ8I) {
+        // ===================== TMA producer (kind::i8): the query tile once, then this CTA's half of every code tile =========
+        if (lane == 0) {
+            if (total_it > 0) {
+                if (leader) mbar_expect_tx(afull_bar, 2u * A2_BYTES * (uint32_t)A.kb);
+                for (int kb = 0; kb < A.kb; kb++) tma_load_2d_pair(s_base + kb * A2_BYTES, &map_q, kb * 128, q0, afull_bar);
+            }
+            for (int it = 0; it < total_it; it++) {
+                const int st = it % nstb;
+                const uint32_t ph = (it / nstb) & 1;
+                const int t = it / A.kb, kb = it - t * A.kb;
+                mbar_wait(bempty_bar(st), ph ^ 1);
+                if (leader) mbar_expect_tx(bfull_bar(st), 2 * B2_BYTES);
+                const int n0 = (int)(tile_row0(t) + (int64_t)rank * BN);
+                tma_load_2d_pair(b_base + st * B2_BYTES, &map_x, kb * 128, n0, bfull_bar(st));
+            }
+        }
+    } else if (warp == 0) {
         // ===================== TMA producer: this CTA's half of the query k-block =====================
         if (lane == 0) {
             for (int it = 0; it < total_it; it++) {
@@ -640,16 +672,8 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                                  : "memory");
                 }
                 mbar_wait(empty_bar(st), ph ^ 1);
-                if constexpr (CODEC == Q_SQ8I) {
-                    // 128 query bytes and 128 code bytes per row and k-block, straight from global memory
-                    if (leader) mbar_expect_tx(full_bar(st), 2 * STAGE2_BYTES);
-                    const int n0 = (int)(tile_row0(it / A.kb) + (int64_t)rank * BN);
-                    tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * 128, q0, full_bar(st));
-                    tma_load_2d_pair(s_base + st * STAGE2_BYTES + A2_BYTES, &map_x, kb * 128, n0, full_bar(st));
-                } else {
-                    if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
-                    tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
-                }
+                if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
+                tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
             }
         }
     } else if (warp == 1) {
@@ -657,6 +681,31 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if (leader && lane == 0) {
             constexpr uint32_t idesc = CODEC == Q_SQ8I ? make_idesc_i8_pair() : make_idesc_f16_pair();
             int it = 0;
+            if constexpr (CODEC == Q_SQ8I) {
+                if (ntiles > 0) {
+                    mbar_wait_cluster(afull_bar, 0);
+                    tc_fence_after();
+                }
+                for (int t = 0; t < ntiles; t++) {
+                    const int as = t & 1;
+                    const uint32_t aph = (t >> 1) & 1;
+                    mbar_wait_cluster(tempty_bar(as), aph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_ROWS);
+                    for (int kb = 0; kb < A.kb; kb++, it++) {
+                        const int st = it % nstb;
+                        const uint32_t ph = (it / nstb) & 1;
+                        mbar_wait_cluster(bfull_bar(st), ph);
+                        tc_fence_after();
+                        const uint64_t adesc = make_sdesc(s_base + kb * A2_BYTES), bdesc = make_sdesc(b_base + st * B2_BYTES);
+#pragma unroll
+                        for (int k = 0; k < 4; k++)  // 32 bytes of K per instruction
+                            umma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        umma_commit_pair(bempty_bar(st));
+                    }
+                    umma_commit_pair(tfull_bar(as));
+                }
+            } else
             for (int t = 0; t < ntiles; t++) {
                 const int as = t & 1;
                 const uint32_t aph = (t >> 1) & 1;
@@ -671,10 +720,8 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     const uint32_t sa = s_base + st * STAGE2_BYTES;
                     const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A2_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++) {  // 32 bytes of K per instruction: 16 halves or 32 bytes
-                        if constexpr (CODEC == Q_SQ8I) umma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
-                    }
+                    for (int k = 0; k < BK / 16; k++)
+                        umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
                     umma_commit_pair(empty_bar(st));
                 }
                 umma_commit_pair(tfull_bar(as));
@@ -1945,7 +1992,7 @@ void set_i8(bool on) { g_i8.store(on ? 1 : 0); }
 static int candidates_i8(int64_t k) { return k <= 16 ? 64 : (int)(5 * k); }
 static bool use_i8(const CodecParams &cp, int64_t rows, int64_t k) {
     if (!i8_on() || !use_pair() || q_codec(cp) != Q_SQ8) return false;
-    if (cp.dim % 128 != 0 || cp.row_bytes != cp.dim) return false;        // 128-byte k-blocks, TMA row stride % 16
+    if (cp.dim % 128 != 0 || cp.dim > 1024 || cp.row_bytes != cp.dim) return false;   // 128-byte k-blocks, resident query tile <= 128 KB, TMA row stride % 16
     const int kc = candidates_i8(k);
     return kc <= 2048 && rows / 32 >= 4 * (int64_t)kc;
 }
