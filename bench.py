@@ -819,19 +819,35 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
             # processes every pair of the batch (a 10k-query batch is one launch; longer batches are chunked).
             flops = 2.0 * nq * nloc * dim * steps / gemm_launches
             ach = flops / (gemm_ms / 1e3) / 1e12
-            roofline = {"bound": "tensor", "achieved": ach, "peak": env.tf_sustained, "unit": "TFLOP/s", "frac": ach / env.tf_sustained, "traffic": traffic,
+            st_i8 = C.c_int32(0)
+            L.call("vg_quant_tc_i8_state", C.byref(st_i8))
+            i8 = bool(st_i8.value) and workload == "sq8" and dim % 128 == 0 and dim <= 1024 and (k <= 16 or 6 * k <= 2048)
+            # kind::i8 issues at twice the kind::f16 rate (4.5 vs 2.25 P dense nominal); MEASURED_PEAKS.json holds no 8-bit figure,
+            # so the denominator is twice the MEASURED sustained bf16 rate — stated in peak_source
+            peak = env.tf_sustained * (2.0 if i8 else 1.0)
+            roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak,
+                        "traffic": None if i8 else traffic,
                         "kernel": (f"qtc_kernel<{workload.upper()}> (tcgen05.mma cta_group::1 kind::f16, M=128 x N=128)"
                                    if os.environ.get("VECGO_QTC_PAIR", "1")[:1] == "0" else
+                                   "qtc2_kernel<SQ8I> (CTA pair, tcgen05.mma cta_group::2 kind::i8, M=256 x N=256: s8 query tile resident in shared "
+                                   "memory x u8 code tiles by TMA, int32 accumulate in TMEM, two epilogue groups)" if i8 else
                                    f"qtc2_kernel<{workload.upper()}> (CTA pair, tcgen05.mma cta_group::2 kind::f16, M=256 x N=256, fp32 accumulate in TMEM)"),
                         "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gemm_launches, "share_of_step": gemm_ms * gemm_launches / steps / ms_per_step,
-                        "algorithmic_flops_per_launch": flops, "peak_source": env.peak_src, "frac_of_burst_peak": ach / env.tf_burst,
+                        "algorithmic_flops_per_launch": flops,
+                        "peak_source": (env.peak_src + "; kind::i8: 2 x bf16_tflops_sustained (no measured 8-bit peak; the 8-bit MMA issues at twice "
+                                        "the 16-bit rate)") if i8 else env.peak_src,
+                        "frac_of_bf16_sustained_peak": ach / env.tf_sustained, "frac_of_burst_peak": ach / (env.tf_burst * (2.0 if i8 else 1.0)),
                         "hbm_equivalent": {"achieved_gbs": hbm_equiv, "peak_gbs": env.hbm_peak, "frac": hbm_equiv / env.hbm_peak,
                                            "note": "queries x rows x code bytes per row / whole-search time: the per-query streaming bytes of "
                                                    "the reference (SURVEY 8d). Above 1 because one decoded code tile serves 256 queries."},
                         "note": "achieved = 2 x queries x rows x dim / GEMM kernel time (CUDA events on the launching stream around every "
-                                "launch). Codes are decoded to exact fp16 integers inside the kernel; the binding limit is the tensor pipe, "
-                                "not HBM (DRAM traffic per launch in `traffic`)."}
-            dtype = ("f16 tensor-core filter over exact integer codes with f32 accumulate, then f32 exact re-check in the reference's "
+                                "launch). " + ("The raw code bytes are the unsigned 8-bit B operand; the query tile is quantised to signed 8-bit per "
+                                               "query and its measured quantisation error enters the certificate." if i8 else
+                                               "Codes are decoded to exact fp16 integers inside the kernel; the binding limit is the tensor pipe, "
+                                               "not HBM (DRAM traffic per launch in `traffic`).")}
+            dtype = ("i8 tensor-core filter (u8 codes x s8 queries, int32 accumulate), then f32 exact re-check in the reference's AVX-512 order "
+                     "(results bit-identical to the f32 scan)") if i8 else (
+                     "f16 tensor-core filter over exact integer codes with f32 accumulate, then f32 exact re-check in the reference's "
                      "AVX-512 order (results bit-identical to the f32 scan)")
         else:
             kernel_name = "scan_topk_kernel<CodecSQ8Perm<16>>" if workload == "sq8" else "scan_topk_kernel<CodecINT4Perm>"

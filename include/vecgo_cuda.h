@@ -275,6 +275,7 @@ vg_status vg_index_search_blocks_dev(vg_index_t idx, const float *d_queries, int
  * off = the fp16 decode-GEMM.  Results are identical either way (same exact stage, certificate with the measured
  * quantisation error of each query). */
 vg_status vg_quant_tc_i8_enable(int32_t on);
+vg_status vg_quant_tc_i8_state(int32_t *on);   /* 1 when SQ8 batches of eligible shapes (dim % 128 == 0, <= 1024; 6k <= 2048) take the kind::i8 filter */
 /* Tile skipping of the quantized tensor-core filters when a row bitmap is given (default on; VECGO_TILE_SKIP=0): off
  * only for A/B measurements — results are identical either way. */
 vg_status vg_tile_skip_enable(int32_t on);

@@ -139,6 +139,7 @@ _SIGS = {
     "vg_index_search_blocks_dev": [u64, vp, i64, i64, i64, vp, u8p, vp, vp, vp],
     "vg_tile_skip_enable": [i32],
     "vg_quant_tc_i8_enable": [i32],
+    "vg_quant_tc_i8_state": [i32p],
     "vg_ivf_grouped_enable": [i32],
     "vg_quant_tc_stats": [u64p, u64p],
     "vg_quant_tc_profile": [i32, C.POINTER(C.c_double), u64p],

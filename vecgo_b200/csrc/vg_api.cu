@@ -1122,6 +1122,11 @@ vg_status vg_quant_tc_i8_enable(int32_t on) {
     qtc::set_i8(on != 0);
     return VG_OK;
 }
+vg_status vg_quant_tc_i8_state(int32_t *on) {
+    if (!on) return fail(VG_ERR_INVALID, "null argument");
+    *on = qtc::i8_state() ? 1 : 0;
+    return VG_OK;
+}
 
 vg_status vg_tile_skip_enable(int32_t on) {
     tiles::set_enabled(on != 0);

@@ -1976,7 +1976,8 @@ vg_status score_rows(const CodecParams &cp, int64_t rows, const float *d_queries
 static int candidates_for(int64_t k) { return k <= 16 ? 32 : (int)(2 * k); }
 
 // SQ8 through kind::i8 (twice the kind::f16 rate, no decode): on unless VECGO_QTC_I8=0 / set_i8(false).  The 8-bit query
-// tile makes the certificate margin ~13x the fp16 one, so the filter keeps 2.5x the candidate groups (5k instead of 2k);
+// tile makes the certificate margin ~13x the fp16 one, so the filter keeps 3x the candidate groups (6k instead of 2k:
+// measured on the headline shape, 5k left 2 of 10 000 queries to the second chance, 4k 49, 3k 2330);
 // shapes whose candidate count would not fit stay on the fp16 kernel.
 static std::atomic<int> g_i8{-1};
 static bool i8_on() {
@@ -1989,7 +1990,16 @@ static bool i8_on() {
     return v != 0;
 }
 void set_i8(bool on) { g_i8.store(on ? 1 : 0); }
-static int candidates_i8(int64_t k) { return k <= 16 ? 64 : (int)(5 * k); }
+bool i8_state() { return i8_on() && use_pair(); }
+static int candidates_i8(int64_t k) {
+    static int tenths = -1;   // candidate groups per k, in tenths (VECGO_QTC_I8_KC, tuning / measurement)
+    if (tenths < 0) {
+        const char *e = getenv("VECGO_QTC_I8_KC");
+        const int v = e ? atoi(e) : 0;
+        tenths = v >= 20 && v <= 200 ? v : 60;
+    }
+    return k <= 16 ? 64 : (int)(k * tenths / 10);
+}
 static bool use_i8(const CodecParams &cp, int64_t rows, int64_t k) {
     if (!i8_on() || !use_pair() || q_codec(cp) != Q_SQ8) return false;
     if (cp.dim % 128 != 0 || cp.dim > 1024 || cp.row_bytes != cp.dim) return false;   // 128-byte k-blocks, resident query tile <= 128 KB, TMA row stride % 16

@@ -71,6 +71,7 @@ void stats(uint64_t *queries, uint64_t *fallbacks);
 // Returns the accumulated CUDA-event time / launch count of the GEMM kernel since the last reset; enable = 1 / 0 turns
 // the event pair around every GEMM launch on / off and resets the counters, enable < 0 only reads.
 void profile(int enable, double *gemm_ms, uint64_t *gemm_launches);
+bool i8_state();
 void set_i8(bool on);   // SQ8 filter through tcgen05 kind::i8 (default on; VECGO_QTC_I8=0)
 
 }  // namespace qtc
