@@ -55,6 +55,8 @@
 #include <vector>
 
 #include "vg_flat_tc.cuh"
+#include <type_traits>
+
 #include "vg_quant_tc.cuh"
 #include "vg_tiles.cuh"
 #include "vg_tc_ptx.cuh"
@@ -82,6 +84,11 @@ constexpr int Q_SQ8 = 0, Q_INT4 = 1, Q_PQ = 2, Q_RABITQ = 3, Q_BQ = 4;
 // GEMM-only variant of SQ8 (qtc2_kernel): kind::i8 — the raw code bytes ARE the B operand (unsigned 8-bit, loaded by TMA,
 // no decode warps), the query tile is quantised to signed 8-bit per query; everything after the GEMM is Q_SQ8's.
 constexpr int Q_SQ8I = 5;
+// kind::i8 variants that still decode in the kernel (streamed query k-blocks, decode warps write BYTES): RaBitQ / BQ sign
+// bits as exact +-1 signed bytes (128 dims per 128-byte k-block instead of 64)
+constexpr int Q_RABITQI = 6, Q_BQI = 7;
+__host__ __device__ constexpr bool i8_codec(int c) { return c == Q_SQ8I || c == Q_RABITQI || c == Q_BQI; }
+__host__ __device__ constexpr int base_codec(int c) { return c == Q_SQ8I ? Q_SQ8 : c == Q_RABITQI ? Q_RABITQ : c == Q_BQI ? Q_BQ : c; }
 // sign-bit codes (RaBitQ, BQ): the B tile is +-1, the GEMM is exact (acc = D - 2 Hamming)
 __host__ __device__ constexpr bool sign_codec(int c) { return c == Q_RABITQ || c == Q_BQ; }
 constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage (work bound; beyond it the query goes to the exact scan)
@@ -264,6 +271,27 @@ struct Producer<Q_RABITQ> {
             uint32_t h[4];
 #pragma unroll
             for (int j = 0; j < 4; j++) h[j] = ((v << (15 - (p0 + j))) & 0x80008000u) | 0x3C003C00u;
+            sts128(dst_row + (uint32_t)((c ^ swz) << 4), h[0], h[1], h[2], h[3]);
+        }
+    }
+};
+
+// The same for kind::i8: 16 stored bytes (128 dims) per k-block -> +1 / -1 as SIGNED bytes in natural dimension order.
+// Four bits n -> four bytes: (n * 0x00204081) & 0x01010101 puts bit i into byte i (the four shifted copies of a 4-bit n
+// do not overlap, so nothing carries), t -> ~(t * 0xFE) maps 1 -> 0x01 and 0 -> 0xFF per byte.
+struct ProducerSignI8 {
+    uint4 w;
+    __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
+        w = __ldg(reinterpret_cast<const uint4 *>(A.codes + row * A.row_bytes + (int64_t)kb * 16));
+    }
+    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
+        const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            const uint32_t v = wv[c >> 1] >> ((c & 1) * 16);
+            uint32_t h[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) h[j] = ~(((((v >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFEu);
             sts128(dst_row + (uint32_t)((c ^ swz) << 4), h[0], h[1], h[2], h[3]);
         }
     }
@@ -606,6 +634,7 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     const uint32_t afull_bar = bar0 + 8u * 36;
     const uint32_t b_base = s_base + (uint32_t)A.kb * A2_BYTES;
 
+    constexpr int BASE = base_codec(CODEC);
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < NST; s++) {
             mbar_init(full_bar(s), 1 + 4 + 4);  // leader's expect_tx arrive + one decode group (4 warps) of each CTA
@@ -673,13 +702,14 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 }
                 mbar_wait(empty_bar(st), ph ^ 1);
                 if (leader) mbar_expect_tx(full_bar(st), 2 * A2_BYTES);  // both CTAs' loads are counted on the leader's barrier
-                tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * BK, q0, full_bar(st));
+                tma_load_2d_pair(s_base + st * STAGE2_BYTES, &map_q, kb * (i8_codec(CODEC) ? 128 : BK), q0, full_bar(st));
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            constexpr uint32_t idesc = CODEC == Q_SQ8I ? make_idesc_i8_pair() : make_idesc_f16_pair();
+            // kind::i8: signed A (query side); B = unsigned code bytes (SQ8I) or signed +-1 bytes (sign codecs: b_format bit 10)
+            constexpr uint32_t idesc = CODEC == Q_SQ8I ? make_idesc_i8_pair() : i8_codec(CODEC) ? (make_idesc_i8_pair() | (1u << 10)) : make_idesc_f16_pair();
             int it = 0;
             if constexpr (CODEC == Q_SQ8I) {
                 if (ntiles > 0) {
@@ -720,8 +750,10 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                     const uint32_t sa = s_base + st * STAGE2_BYTES;
                     const uint64_t adesc = make_sdesc(sa), bdesc = make_sdesc(sa + A2_BYTES);
 #pragma unroll
-                    for (int k = 0; k < BK / 16; k++)
-                        umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    for (int k = 0; k < BK / 16; k++) {  // 32 bytes of K per instruction: 16 halves or 32 bytes
+                        if constexpr (i8_codec(CODEC)) umma_i8_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_f16_pair(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
                     umma_commit_pair(empty_bar(st));
                 }
                 umma_commit_pair(tfull_bar(as));
@@ -755,8 +787,8 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         auto xn_of = [&](int t_) {
             const int64_t n0 = tile_row0(t_);
             const int64_t row = n0 + et;
-            if constexpr (CODEC == Q_BQ) return (row < row_end) ? A.half_dim : BIG;  // s = D / 2 - acc / 2 = Hamming, exact
-            else return (row < row_end) ? __ldg(A.xn + row) : (CODEC == Q_RABITQ ? 1.0e19f : BIG);
+            if constexpr (BASE == Q_BQ) return (row < row_end) ? A.half_dim : BIG;  // s = D / 2 - acc / 2 = Hamming, exact
+            else return (row < row_end) ? __ldg(A.xn + row) : (BASE == Q_RABITQ ? 1.0e19f : BIG);
         };
         // staging buffer of tile t: two per epilogue group (a group's next tile is written while slower warps of the group may
         // still read the current one)
@@ -790,9 +822,9 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         // kind::i8 accumulates in int32 (|acc| <= 768 * 127 * 255 < 2^25: the conversion is exact or within 2^-24)
-                        const float accf = CODEC == Q_SQ8I ? __int2float_rn((int)v[j4 * 4 + i]) : __uint_as_float(v[j4 * 4 + i]);
+                        const float accf = i8_codec(CODEC) ? __int2float_rn((int)v[j4 * 4 + i]) : __uint_as_float(v[j4 * 4 + i]);
                         const float t = __fmaf_rn(fq, accf, xx[i]);
-                        s[j4 * 4 + i] = CODEC == Q_RABITQ ? __fmul_rn(t, xx[i]) : t;  // RaBitQ: yn^2 - (2 qn / D) yn acc
+                        s[j4 * 4 + i] = BASE == Q_RABITQ ? __fmul_rn(t, xx[i]) : t;  // RaBitQ: yn^2 - (2 qn / D) yn acc
                     }
                 }
                 if (mw != 0xFFFFFFFFu) {
@@ -921,7 +953,8 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 c2 = c4;
                 c4.advance2(A.kb);
             }
-        } else if constexpr (sign_codec(CODEC)) {
+        } else if constexpr (sign_codec(BASE)) {
+            using SignProducer = std::conditional_t<i8_codec(CODEC), ProducerSignI8, Producer<Q_RABITQ>>;
             const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
             const int swz = r & 7;
             auto row_of = [&](int t) {
@@ -929,16 +962,16 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 return row < A.rows ? row : A.rows - 1;
             };
             // three buffers in rotation (see the byte producers below): loads of it + 2 and it + 4 in flight
-            Producer<Q_RABITQ> b0, b1, b2;
+            SignProducer b0, b1, b2;
             Cursor cf;
             cf.init(grp, A.kb);
             int it = grp;
-            auto fetch_next = [&](Producer<Q_RABITQ> &buf, int it_f) {
+            auto fetch_next = [&](SignProducer &buf, int it_f) {
                 if (it_f < total_it) buf.fetch(A, row_of(cf.t), cf.kb);
                 cf.advance2(A.kb);
             };
             int kb_cur = cf.kb;  // k-block of iteration `it` (convert() does not need it, kept for symmetry)
-            auto step = [&](const Producer<Q_RABITQ> &cur, Producer<Q_RABITQ> &far) {
+            auto step = [&](const SignProducer &cur, SignProducer &far) {
                 fetch_next(far, it + 4);
                 const int st = it % NST;
                 const uint32_t ph = (it / NST) & 1;
@@ -1123,6 +1156,25 @@ __global__ void __launch_bounds__(256) prep_queries_sign_kernel(const uint32_t *
         if (d >= 0) v = ((qw[d >> 5] >> (d & 31)) & 1u) ? 1.0f : -1.0f;
         a16[q * dimp + p] = __float2half_rn(v);
     }
+    if (lane == 0) {
+        if (q_norms) {
+            const float qn = q_norms[q];
+            fq[q] = __fdiv_rn(__fmul_rn(-2.0f, qn), (float)dim);
+            cq[q] = __fmul_rn(qn, qn);
+        } else {  // BQ: s = D / 2 - acc / 2
+            fq[q] = -0.5f;
+            cq[q] = 0.0f;
+        }
+    }
+}
+// kind::i8 form: sign(q) as +-1 signed bytes in natural dimension order (dim % 128 == 0: no padding), same f_q / c_q
+__global__ void __launch_bounds__(256) prep_queries_sign_i8_kernel(const uint32_t *q_words, const float *q_norms, int64_t nq, int words32, int dim,
+                                                                   int8_t *a8, float *fq, float *cq) {
+    const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const uint32_t *qw = q_words + q * words32;
+    for (int d = lane; d < dim; d += 32) a8[q * dim + d] = ((qw[d >> 5] >> (d & 31)) & 1u) ? (int8_t)1 : (int8_t)-1;
     if (lane == 0) {
         if (q_norms) {
             const float qn = q_norms[q];
@@ -2074,8 +2126,9 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     const bool thresh = d_kth != nullptr;
     if (thresh && !pair_mode) return fail(VG_ERR_UNSUPPORTED, "the threshold pass needs the CTA-pair kernel");
     const bool i8 = pair_mode && use_i8(cp, rows, io.k);
+    const bool i8s = pair_mode && sign_codec(qc) && i8_on() && cp.dim % 128 == 0 && cp.row_bytes % 16 == 0;   // sign bits as +-1 bytes
     DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau, eab;
-    VG_TRY(a16.alloc((size_t)nq * pp.dimp * (i8 ? 1 : 2)));
+    VG_TRY(a16.alloc((size_t)nq * pp.dimp * ((i8 || i8s) ? 1 : 2)));
     if (i8) VG_TRY(eab.alloc((size_t)nq * 4));
     const float *ea_p = i8 ? eab.as<float>() : nullptr;
     VG_TRY(fq.alloc((size_t)nq * 4));
@@ -2087,7 +2140,12 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_TRY(gcnt.alloc((size_t)nq * 4));
         VG_TRY(tau.alloc((size_t)nq * 4));
     }
-    if (sign_codec(qc)) {
+    if (i8s) {
+        prep_queries_sign_i8_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32,
+                                                                                      qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr, nq, cp.words32,
+                                                                                      (int)cp.dim, a16.as<int8_t>(), fq.as<float>(), cq.as<float>());
+        VG_LAUNCHED();
+    } else if (sign_codec(qc)) {
         prep_queries_sign_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32,
                                                                                    qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr, nq,
                                                                                    cp.words32, (int)cp.dim, pp.dimp, pp.perm.as<int32_t>(),
@@ -2108,6 +2166,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     if (i8) {
         VG_TRY(tc::tensor_map_2d_u8(&mq, a16.p, nq, pp.dimp, pp.dimp, 128, BM));
         VG_TRY(tc::tensor_map_2d_u8(&mx, cp.codes, rows, cp.dim, cp.row_bytes, 128, BN));
+    } else if (i8s) {
+        VG_TRY(tc::tensor_map_2d_u8(&mq, a16.p, nq, cp.dim, cp.dim, 128, BM));
     } else
     VG_TRY(tc::tensor_map_2d(&mq, true, a16.p, nq, pp.dimp, pp.dimp, BK, pair_mode ? BM : BMQ));
     // row splits: one CTA (pair) per SM (pair), whole waves
@@ -2136,7 +2196,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.nq = nq;
     a.rows = rows;
     a.rows_per_split = rps;
-    a.kb = i8 ? pp.dimp / 128 : pp.dimp / BK;
+    a.kb = i8 ? pp.dimp / 128 : i8s ? (int)(cp.dim / 128) : pp.dimp / BK;
     a.cpg = (int)(G / 32);
     a.mins = mins.as<float2>();
     a.groups = groups;
@@ -2183,6 +2243,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I, true>(mq, a, qtiles, (int)splits, st, &mx)));
         else if (qc == Q_SQ8) VG_TRY((launch_gemm_pair<Q_SQ8, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4, true>(mq, a, qtiles, (int)splits, st)));
+        else if (qc == Q_RABITQ && i8s) VG_TRY((launch_gemm_pair<Q_RABITQI, true>(mq, a, qtiles, (int)splits, st)));
+        else if (qc == Q_BQ && i8s) VG_TRY((launch_gemm_pair<Q_BQI, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_RABITQ) VG_TRY((launch_gemm_pair<Q_RABITQ, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_BQ) VG_TRY((launch_gemm_pair<Q_BQ, true>(mq, a, qtiles, (int)splits, st)));
         else VG_TRY((launch_gemm_pair<Q_PQ, true>(mq, a, qtiles, (int)splits, st)));
@@ -2218,6 +2280,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I>(mq, a, qtiles, (int)splits, st, &mx)));
         else if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
+        else if (qc == Q_RABITQ && i8s) VG_TRY(launch_gemm_pair<Q_RABITQI>(mq, a, qtiles, (int)splits, st));
+        else if (qc == Q_BQ && i8s) VG_TRY(launch_gemm_pair<Q_BQI>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_RABITQ) VG_TRY(launch_gemm_pair<Q_RABITQ>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_BQ) VG_TRY(launch_gemm_pair<Q_BQ>(mq, a, qtiles, (int)splits, st));
         else VG_TRY(launch_gemm_pair<Q_PQ>(mq, a, qtiles, (int)splits, st));
