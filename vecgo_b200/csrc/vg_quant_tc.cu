@@ -87,8 +87,12 @@ constexpr int Q_SQ8I = 5;
 // kind::i8 variants that still decode in the kernel (streamed query k-blocks, decode warps write BYTES): RaBitQ / BQ sign
 // bits as exact +-1 signed bytes (128 dims per 128-byte k-block instead of 64)
 constexpr int Q_RABITQI = 6, Q_BQI = 7;
-__host__ __device__ constexpr bool i8_codec(int c) { return c == Q_SQ8I || c == Q_RABITQI || c == Q_BQI; }
-__host__ __device__ constexpr int base_codec(int c) { return c == Q_SQ8I ? Q_SQ8 : c == Q_RABITQI ? Q_RABITQ : c == Q_BQI ? Q_BQ : c; }
+// INT4 nibbles as unsigned bytes 0..15 (64 stored bytes = 128 dims per k-block), queries quantised as for Q_SQ8I
+constexpr int Q_INT4I = 8;
+__host__ __device__ constexpr bool i8_codec(int c) { return c == Q_SQ8I || c == Q_RABITQI || c == Q_BQI || c == Q_INT4I; }
+__host__ __device__ constexpr int base_codec(int c) {
+    return c == Q_SQ8I ? Q_SQ8 : c == Q_RABITQI ? Q_RABITQ : c == Q_BQI ? Q_BQ : c == Q_INT4I ? Q_INT4 : c;
+}
 // sign-bit codes (RaBitQ, BQ): the B tile is +-1, the GEMM is exact (acc = D - 2 Hamming)
 __host__ __device__ constexpr bool sign_codec(int c) { return c == Q_RABITQ || c == Q_BQ; }
 constexpr int LIST_CAP = 8192;            // candidate rows per query in the exact stage (work bound; beyond it the query goes to the exact scan)
@@ -154,7 +158,7 @@ struct ProducerBytes;
 // j < LPR, the 16-byte piece (lane % LPR) of slab row  j * (32/LPR) + lane / LPR.
 template <int CODEC>
 struct ProducerBytes {
-    static constexpr int BPR = CODEC == Q_SQ8 ? 64 : 32;
+    static constexpr int BPR = (CODEC == Q_SQ8 || CODEC == Q_INT4I) ? 64 : 32;
     static constexpr int LPR = BPR / 16;
     static constexpr int RPI = 32 / LPR;  // rows per load instruction
     uint4 w[LPR];
@@ -183,7 +187,14 @@ struct ProducerBytes {
             const uint32_t dst = b_tile + (uint32_t)r * 128u;
             const int swz = r & 7;
             const uint32_t ww[4] = {w[j].x, w[j].y, w[j].z, w[j].w};
-            if constexpr (CODEC == Q_SQ8) {
+            if constexpr (CODEC == Q_INT4I) {
+                // kind::i8: 16 stored bytes = 32 nibbles -> 32 unsigned bytes = chunks 2*piece, 2*piece + 1; word h of the piece
+                // gives the two words (low nibbles of its four bytes, high nibbles of its four bytes)
+#pragma unroll
+                for (int h = 0; h < 2; h++)
+                    sts128(dst + (uint32_t)(((2 * piece + h) ^ swz) << 4), ww[2 * h] & 0x0F0F0F0Fu, (ww[2 * h] >> 4) & 0x0F0F0F0Fu,
+                           ww[2 * h + 1] & 0x0F0F0F0Fu, (ww[2 * h + 1] >> 4) & 0x0F0F0F0Fu);
+            } else if constexpr (CODEC == Q_SQ8) {
                 // 16 bytes = chunks 2*piece, 2*piece + 1; code - 128
 #pragma unroll
                 for (int h = 0; h < 2; h++)
@@ -708,8 +719,10 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            // kind::i8: signed A (query side); B = unsigned code bytes (SQ8I) or signed +-1 bytes (sign codecs: b_format bit 10)
-            constexpr uint32_t idesc = CODEC == Q_SQ8I ? make_idesc_i8_pair() : i8_codec(CODEC) ? (make_idesc_i8_pair() | (1u << 10)) : make_idesc_f16_pair();
+            // kind::i8: signed A (query side); B = unsigned code bytes / nibbles (SQ8I, INT4I) or signed +-1 bytes (sign codecs: b_format bit 10)
+            constexpr uint32_t idesc = (CODEC == Q_SQ8I || CODEC == Q_INT4I) ? make_idesc_i8_pair()
+                                       : i8_codec(CODEC)                    ? (make_idesc_i8_pair() | (1u << 10))
+                                                                            : make_idesc_f16_pair();
             int it = 0;
             if constexpr (CODEC == Q_SQ8I) {
                 if (ntiles > 0) {
@@ -1083,10 +1096,11 @@ __global__ void __launch_bounds__(256) prep_queries_kernel(const float *queries,
 // B operand the GEMM gives acc = sum ah_p c_p exactly, and
 //     sum a_p b_p = Delta acc - 128 Delta sum ah_p + sum e_p b_p
 // so the epilogue's s' = ||x^||^2 - 2 Delta acc differs from the fp16 filter's target by the per-query constant
-// 256 Delta sum ah_p (folded into c_q) and by 2 sum e_p b_p, which Cauchy-Schwarz bounds by
+// 256 Delta sum ah_p (2 x offset x Delta sum ah_p in general; folded into c_q) and by 2 sum e_p b_p, which Cauchy-Schwarz bounds by
 // 2 ||e / w|| ||x^ - mid|| = ea[q] * max ||x^ - mid||: the term that replaces c1 ||q|| max||x^ - mid|| in the certificate.
 __global__ void __launch_bounds__(256) prep_queries_i8_kernel(const float *queries, int64_t nq, int64_t q_stride, int dimp, const int32_t *perm,
-                                                              const float *wq, const float *midp, int8_t *a8, float *fq, float *cq, float *ea) {
+                                                              const float *wq, const float *midp, int8_t *a8, float *fq, float *cq, float *ea,
+                                                              float code_offset /* c = b + offset: 128 (SQ8 bytes), 8 (INT4 nibbles) */) {
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
@@ -1135,7 +1149,7 @@ __global__ void __launch_bounds__(256) prep_queries_i8_kernel(const float *queri
     if (lane == 0) {
         fq[q] = __fmul_rn(-2.0f, delta);
         // s'_true = s'_filter + 256 Delta sum ah - 2 sum e b;  reference ~ s'_true + c_q + ||q||^2 with c_q = -2 q.mid
-        cq[q] = (float)(-2.0 * cm + 256.0 * (double)delta * (double)suma);
+        cq[q] = (float)(-2.0 * cm + 2.0 * (double)code_offset * (double)delta * (double)suma);
         const bool finite_q = (mx == 0.0f) || ok;
         ea[q] = (bad || !finite_q) ? __int_as_float(0x7f800000) : (float)(2.0 * sqrt(err2) * 1.000001 + 1.0e-30);
     }
@@ -1948,6 +1962,26 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     } else {
         for (int d = 0; d < dim; d++) perm[(size_t)d] = d;
     }
+    // kind::i8 decode of INT4 (ProducerBytes<Q_INT4I>): position 128 kb + 32 piece + 16 (h >> 1) + 8 (h & 1) + 4 hi + i of the
+    // K axis holds the (hi ? high : low) nibble of device byte 64 kb + 16 piece + 4 h + i
+    std::vector<int32_t> perm8;
+    if (qc == Q_INT4 && dim % 128 == 0) {
+        std::vector<int> nat((size_t)(dim / 2));
+        for (int o = 0; o < dim / 2; o++) {
+            int B = o;
+            if (layout) {
+                const int w = o & 127;
+                B = (o >> 7) * 128 + 16 * (w & 7) + 4 * (w >> 5) + ((w >> 3) & 3);
+            }
+            nat[(size_t)B] = o;
+        }
+        perm8.assign((size_t)dim, -1);
+        for (int p = 0; p < dim; p++) {
+            const int kb = p >> 7, r = p & 127, pc = r >> 5, h = 2 * ((r >> 4) & 1) + ((r >> 3) & 1), hi = (r >> 2) & 1, i = r & 3;
+            const int o = nat[(size_t)(64 * kb + 16 * pc + 4 * h + i)];
+            perm8[(size_t)p] = 2 * o + (hi ? 0 : 1);  // high nibble = even dimension
+        }
+    }
     // x^_d = mid_d + w_d * b_d with the integer b_d the producer emits
     std::vector<float> w((size_t)dim), mid((size_t)dim);
     const float k15 = 1.0f / 15.0f;  // 0x3d888889, the constant of int4_avx512.c
@@ -1982,6 +2016,21 @@ vg_status prepare(const CodecParams &cp, int64_t rows, const float *h_p0, const 
     VG_CUDA(cudaMemcpyAsync(pp.wq.p, wq.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
     VG_CUDA(cudaMemcpyAsync(pp.midp.p, midp.data(), (size_t)dimp * 4, cudaMemcpyHostToDevice, st));
     VG_CUDA(cudaMemsetAsync(pp.xmax.p, 0, 16, st));
+    std::vector<float> wq8, midp8;
+    if (!perm8.empty()) {
+        wq8.resize((size_t)dim);
+        midp8.resize((size_t)dim);
+        for (int p = 0; p < dim; p++) {
+            wq8[(size_t)p] = w[(size_t)perm8[(size_t)p]];
+            midp8[(size_t)p] = mid[(size_t)perm8[(size_t)p]];
+        }
+        VG_TRY(pp.perm8.alloc_persistent((size_t)dim * 4));
+        VG_TRY(pp.wq8.alloc_persistent((size_t)dim * 4));
+        VG_TRY(pp.midp8.alloc_persistent((size_t)dim * 4));
+        VG_CUDA(cudaMemcpyAsync(pp.perm8.p, perm8.data(), (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaMemcpyAsync(pp.wq8.p, wq8.data(), (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+        VG_CUDA(cudaMemcpyAsync(pp.midp8.p, midp8.data(), (size_t)dim * 4, cudaMemcpyHostToDevice, st));
+    }
     EArgs e = eargs_of(cp, rows);
     const unsigned blocks = (unsigned)((rows + 127) / 128);
     if (rows > 0) {
@@ -2053,8 +2102,11 @@ static int candidates_i8(int64_t k) {
     return k <= 16 ? 64 : (int)(k * tenths / 10);
 }
 static bool use_i8(const CodecParams &cp, int64_t rows, int64_t k) {
-    if (!i8_on() || !use_pair() || q_codec(cp) != Q_SQ8) return false;
-    if (cp.dim % 128 != 0 || cp.dim > 1024 || cp.row_bytes != cp.dim) return false;   // 128-byte k-blocks, resident query tile <= 128 KB, TMA row stride % 16
+    const int qc = q_codec(cp);
+    if (!i8_on() || !use_pair() || (qc != Q_SQ8 && qc != Q_INT4)) return false;
+    if (cp.dim % 128 != 0) return false;                                              // 128-byte k-blocks
+    if (qc == Q_SQ8 && (cp.dim > 1024 || cp.row_bytes != cp.dim)) return false;      // resident query tile <= 128 KB, TMA row stride % 16
+    if (qc == Q_INT4 && cp.row_bytes != cp.dim / 2) return false;
     const int kc = candidates_i8(k);
     return kc <= 2048 && rows / 32 >= 4 * (int64_t)kc;
 }
@@ -2153,19 +2205,26 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_LAUNCHED();
     } else {
     VG_TRY(tc::sqnorms(io.d_queries, nq, cp.dim, q_stride, qn.as<float>(), nullptr, st));
-    if (i8)
+    if (i8 && qc == Q_INT4) {
+        if (!pp.perm8.p) return fail(VG_ERR_STATE, "kind::i8 decode tables of the INT4 index were not prepared");
+        prep_queries_i8_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm8.as<int32_t>(),
+                                                                                 pp.wq8.as<float>(), pp.midp8.as<float>(), a16.as<int8_t>(), fq.as<float>(),
+                                                                                 cq.as<float>(), eab.as<float>(), 8.0f);
+    } else if (i8)
         prep_queries_i8_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(),
                                                                                  pp.wq.as<float>(), pp.midp.as<float>(), a16.as<int8_t>(), fq.as<float>(),
-                                                                                 cq.as<float>(), eab.as<float>());
+                                                                                 cq.as<float>(), eab.as<float>(), 128.0f);
     else
         prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.wq.as<float>(),
                                                                               pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
     VG_LAUNCHED();
     }
     CUtensorMap mq, mx;
-    if (i8) {
+    if (i8 && qc == Q_SQ8) {
         VG_TRY(tc::tensor_map_2d_u8(&mq, a16.p, nq, pp.dimp, pp.dimp, 128, BM));
         VG_TRY(tc::tensor_map_2d_u8(&mx, cp.codes, rows, cp.dim, cp.row_bytes, 128, BN));
+    } else if (i8) {
+        VG_TRY(tc::tensor_map_2d_u8(&mq, a16.p, nq, pp.dimp, pp.dimp, 128, BM));
     } else if (i8s) {
         VG_TRY(tc::tensor_map_2d_u8(&mq, a16.p, nq, cp.dim, cp.dim, 128, BM));
     } else
@@ -2217,7 +2276,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     }
     if (thresh) {
         // ---- threshold pass: lists instead of the minima plane, no selection, no certificate
-        const int slots = (int)splits * (i8 ? 4 : 2);   // (split, epilogue group, column half)
+        const int slots = (int)splits * ((i8 && qc == Q_SQ8) ? 4 : 2);   // (split, epilogue group [SQ8I], column half)
         int64_t cap = ((int64_t)4 << 30) / std::max<int64_t>(1, nq * slots * 8);   // <= 4 GiB of lists per chunk
         cap = std::max<int64_t>(64, std::min<int64_t>(8192, cap));
         DevBuf Ts, cand, ccnt, ovf;
@@ -2229,7 +2288,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         const float *qn_p = qn.as<float>(), *cq_p = cq.as<float>();
         const unsigned int *xm = pp.xmax.as<unsigned int>();
         if (qc == Q_SQ8) VG_TRY(launch_thresh<Q_SQ8>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st, ea_p));
-        else if (qc == Q_INT4) VG_TRY(launch_thresh<Q_INT4>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        else if (qc == Q_INT4) VG_TRY(launch_thresh<Q_INT4>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st, ea_p));
         else if (qc == Q_RABITQ) VG_TRY(launch_thresh<Q_RABITQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
         else if (qc == Q_BQ) VG_TRY(launch_thresh<Q_BQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
         else VG_TRY(launch_thresh<Q_PQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
@@ -2240,7 +2299,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         a.ovf = ovf.as<int>();
         a.cap = (int)cap;
         a.slots = slots;
-        if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I, true>(mq, a, qtiles, (int)splits, st, &mx)));
+        if (i8 && qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4I, true>(mq, a, qtiles, (int)splits, st)));
+        else if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I, true>(mq, a, qtiles, (int)splits, st, &mx)));
         else if (qc == Q_SQ8) VG_TRY((launch_gemm_pair<Q_SQ8, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_RABITQ && i8s) VG_TRY((launch_gemm_pair<Q_RABITQI, true>(mq, a, qtiles, (int)splits, st)));
@@ -2277,7 +2337,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         VG_CUDA(cudaEventRecord(g_ev[0], st));
     }
     if (pair_mode) {
-        if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I>(mq, a, qtiles, (int)splits, st, &mx)));
+        if (i8 && qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4I>(mq, a, qtiles, (int)splits, st)));
+        else if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I>(mq, a, qtiles, (int)splits, st, &mx)));
         else if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_RABITQ && i8s) VG_TRY(launch_gemm_pair<Q_RABITQI>(mq, a, qtiles, (int)splits, st));

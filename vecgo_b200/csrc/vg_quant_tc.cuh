@@ -15,6 +15,7 @@ struct Prepared {
     DevBuf perm;      // int32 [dimp]: dimension held at position p along K of the B tile (-1 = padding)
     DevBuf wq;        // float [dimp]: decode weight w of that dimension (x^_d = mid_d + w_d b_d, b_d the integer the producer emits)
     DevBuf midp;      // float [dimp]: mid of that dimension
+    DevBuf perm8, wq8, midp8;   // the same three in the K order of the kind::i8 decode (INT4, dim % 128 == 0); empty otherwise
     DevBuf xn;        // float [rows]: ||decode(row)||^2
     DevBuf xmax;      // uint  [4]: max ||decode(row)||^2, max ||decode(row) - mid||^2 (float bits)
     int dimp = 0;     // dim rounded up to a multiple of 64
