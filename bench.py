@@ -821,7 +821,7 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
             ach = flops / (gemm_ms / 1e3) / 1e12
             st_i8 = C.c_int32(0)
             L.call("vg_quant_tc_i8_state", C.byref(st_i8))
-            i8 = bool(st_i8.value) and workload == "sq8" and dim % 128 == 0 and dim <= 1024 and (k <= 16 or 6 * k <= 2048)
+            i8 = bool(st_i8.value) and dim % 128 == 0 and (workload == "int4" or dim <= 1024) and (k <= 16 or 6 * k <= 2048)
             # kind::i8 issues at twice the kind::f16 rate (4.5 vs 2.25 P dense nominal); MEASURED_PEAKS.json holds no 8-bit figure,
             # so the denominator is twice the MEASURED sustained bf16 rate — stated in peak_source
             peak = env.tf_sustained * (2.0 if i8 else 1.0)
@@ -830,7 +830,9 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
                         "kernel": (f"qtc_kernel<{workload.upper()}> (tcgen05.mma cta_group::1 kind::f16, M=128 x N=128)"
                                    if os.environ.get("VECGO_QTC_PAIR", "1")[:1] == "0" else
                                    "qtc2_kernel<SQ8I> (CTA pair, tcgen05.mma cta_group::2 kind::i8, M=256 x N=256: s8 query tile resident in shared "
-                                   "memory x u8 code tiles by TMA, int32 accumulate in TMEM, two epilogue groups)" if i8 else
+                                   "memory x u8 code tiles by TMA, int32 accumulate in TMEM, two epilogue groups)" if i8 and workload == "sq8" else
+                                   "qtc2_kernel<INT4I> (CTA pair, tcgen05.mma cta_group::2 kind::i8, M=256 x N=256: s8 query k-blocks by TMA x nibbles "
+                                   "expanded to u8 by the decode warps, int32 accumulate in TMEM)" if i8 else
                                    f"qtc2_kernel<{workload.upper()}> (CTA pair, tcgen05.mma cta_group::2 kind::f16, M=256 x N=256, fp32 accumulate in TMEM)"),
                         "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gemm_launches, "share_of_step": gemm_ms * gemm_launches / steps / ms_per_step,
                         "algorithmic_flops_per_launch": flops,
@@ -842,7 +844,9 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
                                                    "the reference (SURVEY 8d). Above 1 because one decoded code tile serves 256 queries."},
                         "note": "achieved = 2 x queries x rows x dim / GEMM kernel time (CUDA events on the launching stream around every "
                                 "launch). " + ("The raw code bytes are the unsigned 8-bit B operand; the query tile is quantised to signed 8-bit per "
-                                               "query and its measured quantisation error enters the certificate." if i8 else
+                                               "query and its measured quantisation error enters the certificate." if i8 and workload == "sq8" else
+                                               "The 4-bit codes are expanded to unsigned bytes inside the kernel; the query tile is quantised to signed 8-bit "
+                                               "per query and its measured quantisation error enters the certificate." if i8 else
                                                "Codes are decoded to exact fp16 integers inside the kernel; the binding limit is the tensor pipe, "
                                                "not HBM (DRAM traffic per launch in `traffic`).")}
             dtype = ("i8 tensor-core filter (u8 codes x s8 queries, int32 accumulate), then f32 exact re-check in the reference's AVX-512 order "
@@ -1202,6 +1206,9 @@ def run_c4(env, a):
                                            "one GPU; the same exchange is checked at 12.5M rows per GPU"}
         flops = 2.0 * nq * n * dim * steps / max(gl, 1)
         ach = flops / (gemm_ms / 1e3) / 1e12 if gl else 0.0
+        st_i8 = C.c_int32(0)
+        L.call("vg_quant_tc_i8_state", C.byref(st_i8))
+        c4_i8 = bool(st_i8.value) and dim % 128 == 0
         hbm_equiv = float(nq) * n * world * code_bytes / (ms / 1e3) / 1e9
         cbase = None
         if world == 1 and not a.no_cpu_baseline:
@@ -1227,8 +1234,11 @@ def run_c4(env, a):
                "metric": "batched QPS, RaBitQ scan + rerank", "value": nq / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "steps": steps, "scaling": "weak",
                "scan_only_ms": ms_scan, "rerank_exchange_merge_ms": ms - ms_scan, "rows_total": n * world, "dtype": "f16",
                "generate_encode_upload_s": gen_s,
-               "roofline": {"bound": "tensor", "achieved": ach, "peak": env.tf_burst, "unit": "TFLOP/s", "frac": ach / env.tf_burst,
-                            "kernel": "qtc2_kernel<RABITQ> (sign bits as exact +-1 fp16 operands)", "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gl,
+               "roofline": {"bound": "tensor", "achieved": ach, "peak": env.tf_burst * (2.0 if c4_i8 else 1.0), "unit": "TOP/s" if c4_i8 else "TFLOP/s",
+                            "frac": ach / (env.tf_burst * (2.0 if c4_i8 else 1.0)), "frac_of_bf16_burst_peak": ach / env.tf_burst,
+                            "kernel": ("qtc2_kernel<RABITQI> (kind::i8: sign bits as exact +-1 signed bytes, 128 dims per k-block; peak = 2 x the measured "
+                                       "bf16 burst rate, MEASURED_PEAKS.json holds no 8-bit figure)" if c4_i8 else
+                                       "qtc2_kernel<RABITQ> (sign bits as exact +-1 fp16 operands)"), "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gl,
                             "share_of_step": gemm_ms * gl / steps / ms if gl else None, "traffic": None, "peak_source": env.peak_src,
                             "hbm_equivalent": {"achieved_gbs": hbm_equiv, "peak_gbs": env.hbm_peak * world, "frac": hbm_equiv / (env.hbm_peak * world),
                                                "note": "queries x rows x 196 code bytes / step time (SURVEY 8d byte view) against the summed HBM peaks"}},
