@@ -1080,13 +1080,20 @@ def run_c3(env, a):
             t2 = time.perf_counter() - t0
             cbase = {"value": nq2 / t2 * sub / (n * world), "unit": "queries/s", "cores": th, "kind": "reference" if o.ref is not None else "port",
                      "sample": f"{nq2} queries x {sub} rows (the host-held prefix) in {t2:.1f}s on {th} threads; linear extrapolation x{sub}/{n * world} rows"}
+        st_i8 = C.c_int32(0)
+        L.call("vg_quant_tc_i8_state", C.byref(st_i8))
+        c3_i8 = bool(st_i8.value) and dim % 128 == 0 and dim // m == 8 and os.environ.get("VECGO_QTC_PQ_I8", "1")[:1] != "0" and 6 * k <= 2048
         res = {"workload": f"PQ M={m} x 256 ADC scan, {world} x {n} rows of {dim}-d codes (uniform random bytes, random int8 codebooks), {nq} queries, k={k}"
                            + (f"; {world} GPUs: NCCL all-gather of the per-shard top-k + device merge" if world > 1 else "")
                            + (" = BASELINE configs[2]" if world == 8 and not a.small else "") + (" [--small]" if a.small else ""),
                "metric": "batched QPS, PQ ADC scan top-100", "value": nq / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms, "steps": steps, "scaling": "weak",
-               "dtype": "f16", "rows_total": n * world,
-               "roofline": {"bound": "tensor", "achieved": ach, "peak": env.tf_sustained, "unit": "TFLOP/s", "frac": ach / env.tf_sustained,
-                            "frac_of_burst_peak": ach / env.tf_burst, "kernel": "qtc2_kernel<PQ>", "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gl,
+               "dtype": "i8" if c3_i8 else "f16", "rows_total": n * world,
+               "roofline": {"bound": "tensor", "achieved": ach, "peak": env.tf_sustained * (2.0 if c3_i8 else 1.0), "unit": "TOP/s" if c3_i8 else "TFLOP/s",
+                            "frac": ach / (env.tf_sustained * (2.0 if c3_i8 else 1.0)), "frac_of_bf16_sustained_peak": ach / env.tf_sustained,
+                            "frac_of_burst_peak": ach / (env.tf_burst * (2.0 if c3_i8 else 1.0)),
+                            "kernel": ("qtc2_kernel<PQI> (kind::i8: int8 centroids gathered from a 32 KB shared-memory slice as signed bytes, 128 dims per "
+                                       "k-block; peak = 2 x the measured sustained bf16 rate)" if c3_i8 else "qtc2_kernel<PQ>"),
+                            "kernel_ms": gemm_ms, "kernel_launches_in_timed_region": gl,
                             "share_of_step": gemm_ms * gl / steps / ms if gl else None, "traffic": None, "peak_source": env.peak_src,
                             "hbm_equivalent": {"achieved_gbs": hbm_equiv, "peak_gbs": env.hbm_peak * world, "frac": hbm_equiv / (env.hbm_peak * world),
                                                "note": "queries x rows x 96 code bytes / step time (SURVEY 8d byte view) against the summed HBM peaks"}},

@@ -89,9 +89,11 @@ constexpr int Q_SQ8I = 5;
 constexpr int Q_RABITQI = 6, Q_BQI = 7;
 // INT4 nibbles as unsigned bytes 0..15 (64 stored bytes = 128 dims per k-block), queries quantised as for Q_SQ8I
 constexpr int Q_INT4I = 8;
-__host__ __device__ constexpr bool i8_codec(int c) { return c == Q_SQ8I || c == Q_RABITQI || c == Q_BQI || c == Q_INT4I; }
+// PQ (dsub = 8): the int8 codebook entries ARE signed bytes — 16 gathers of 8 bytes per row and k-block (128 dims), stored as they are
+constexpr int Q_PQI = 9;
+__host__ __device__ constexpr bool i8_codec(int c) { return c == Q_SQ8I || c == Q_RABITQI || c == Q_BQI || c == Q_INT4I || c == Q_PQI; }
 __host__ __device__ constexpr int base_codec(int c) {
-    return c == Q_SQ8I ? Q_SQ8 : c == Q_RABITQI ? Q_RABITQ : c == Q_BQI ? Q_BQ : c == Q_INT4I ? Q_INT4 : c;
+    return c == Q_SQ8I ? Q_SQ8 : c == Q_RABITQI ? Q_RABITQ : c == Q_BQI ? Q_BQ : c == Q_INT4I ? Q_INT4 : c == Q_PQI ? Q_PQ : c;
 }
 // sign-bit codes (RaBitQ, BQ): the B tile is +-1, the GEMM is exact (acc = D - 2 Hamming)
 __host__ __device__ constexpr bool sign_codec(int c) { return c == Q_RABITQ || c == Q_BQ; }
@@ -306,6 +308,37 @@ struct ProducerSignI8 {
             sts128(dst_row + (uint32_t)((c ^ swz) << 4), h[0], h[1], h[2], h[3]);
         }
     }
+};
+
+// PQ for kind::i8 (dsub = 8): the 16 codes of a k-block (subspaces 16 kb .. 16 kb + 15 = 128 dims) in one 16-byte load, 16
+// gathers of one centroid (8 signed bytes) from the 32 KB codebook slice in shared memory, stored unchanged: chunk c of
+// the B row = centroids of subspaces 2c, 2c + 1 — natural dimension order.
+struct ProducerPQI8 {
+    using Codes = uint4;
+    uint2 g[16];
+    __device__ __forceinline__ static Codes zero() { return make_uint4(0u, 0u, 0u, 0u); }
+    __device__ __forceinline__ static Codes load_codes(const KArgs &A, int64_t row, int kb) {
+        const uint8_t *p = A.tiled ? A.codes + (row >> 5) * (32 * A.row_bytes) + (int64_t)kb * 512 + (row & 31) * 16
+                                   : A.codes + row * A.row_bytes + (int64_t)kb * 16;
+        return __ldg(reinterpret_cast<const uint4 *>(p));
+    }
+    __device__ __forceinline__ void gather_smem(const KArgs &, Codes c16, int, uint32_t slice) {
+        const uint32_t cw[4] = {c16.x, c16.y, c16.z, c16.w};
+#pragma unroll
+        for (int c = 0; c < 16; c++) {
+            const uint32_t code = (cw[c >> 2] >> (8 * (c & 3))) & 0xFFu;
+            const uint32_t addr = slice + ((((uint32_t)c << 8) + code) << 3);
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(g[c].x), "=r"(g[c].y) : "r"(addr));
+        }
+    }
+    __device__ __forceinline__ void convert(const KArgs &, int, uint32_t dst_row, int swz) const {
+#pragma unroll
+        for (int c = 0; c < 8; c++) sts128(dst_row + (uint32_t)((c ^ swz) << 4), g[2 * c].x, g[2 * c].y, g[2 * c + 1].x, g[2 * c + 1].y);
+    }
+};
+struct ProducerPQF16 : Producer<Q_PQ> {
+    using Codes = uint2;
+    __device__ __forceinline__ static Codes zero() { return make_uint2(0u, 0u); }
 };
 
 // ------------------------------------------------------------------ GEMM + group minima
@@ -621,10 +654,12 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 
     // PQ trades one pipeline stage for a two-slot ring of 16 KB codebook slices (the int8 centroids of the subspaces of one
     // k-block, bulk-copied by the TMA thread): the decode warps gather from shared memory instead of from L2.
-    constexpr int NST = CODEC == Q_PQ ? STAGES2 - 1 : STAGES2;
-    constexpr uint32_t SLICE_BYTES = 16384;  // 64 dims x 256 centroids x 1 byte, whatever dsub is
+    // (kind::i8 PQ: k-blocks of 128 dims = 32 KB slices, four stages)
+    constexpr bool IS_PQ = CODEC == Q_PQ || CODEC == Q_PQI;
+    constexpr int NST = CODEC == Q_PQ ? STAGES2 - 1 : CODEC == Q_PQI ? STAGES2 - 2 : STAGES2;
+    constexpr uint32_t SLICE_BYTES = CODEC == Q_PQI ? 32768 : 16384;  // 64 (128) dims x 256 centroids x 1 byte, whatever dsub is
     constexpr uint32_t OFF_SLICE = (uint32_t)NST * STAGE2_BYTES;
-    constexpr uint32_t OFF_XN = OFF_SLICE + (CODEC == Q_PQ ? 2 * SLICE_BYTES : 0);
+    constexpr uint32_t OFF_XN = OFF_SLICE + (IS_PQ ? 2 * SLICE_BYTES : 0);
     constexpr uint32_t OFF_BAR = OFF_XN + 4 * TILE_ROWS * 4;
     const uint32_t s_base = smem_u32(smem);
     const uint32_t bar0 = s_base + OFF_BAR;
@@ -702,7 +737,7 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 const int st = it % NST;
                 const uint32_t ph = (it / NST) & 1;
                 const int kb = it % A.kb;
-                if constexpr (CODEC == Q_PQ) {  // slice of iteration `it` into slot it % 2 (= the decode group that handles it)
+                if constexpr (IS_PQ) {  // slice of iteration `it` into slot it % 2 (= the decode group that handles it)
                     const int slot = it & 1;
                     mbar_wait(sempty_bar(slot), ((uint32_t)(it >> 1) & 1) ^ 1);
                     mbar_expect_tx(sfull_bar(slot), SLICE_BYTES);
@@ -720,7 +755,7 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
             // kind::i8: signed A (query side); B = unsigned code bytes / nibbles (SQ8I, INT4I) or signed +-1 bytes (sign codecs: b_format bit 10)
-            constexpr uint32_t idesc = (CODEC == Q_SQ8I || CODEC == Q_INT4I) ? make_idesc_i8_pair()
+            constexpr uint32_t idesc = (CODEC == Q_SQ8I || CODEC == Q_INT4I) ? make_idesc_i8_pair()   // others: signed B (sign bytes, int8 centroids)
                                        : i8_codec(CODEC)                    ? (make_idesc_i8_pair() | (1u << 10))
                                                                             : make_idesc_f16_pair();
             int it = 0;
@@ -928,7 +963,9 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         if constexpr (CODEC == Q_SQ8I) {
             (void)grp;   // kind::i8: the code bytes are the operand, TMA delivers them — these warps have nothing to decode
             (void)half_off;
-        } else if constexpr (CODEC == Q_PQ) {
+        } else if constexpr (IS_PQ) {
+            using PQProducer = std::conditional_t<CODEC == Q_PQI, ProducerPQI8, ProducerPQF16>;
+            using PQCodes = typename PQProducer::Codes;
             const int r = ((warp - PROD_WARP0) & 3) * 32 + lane;
             const int swz = r & 7;
             auto row_of = [&](int t) {
@@ -936,19 +973,19 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 return row < A.rows ? row : A.rows - 1;
             };
             // codes of iterations it, it + 2, it + 4 in flight (8 bytes each); the centroid bytes come from the slice ring
-            Producer<Q_PQ> cur;
+            PQProducer cur;
             Cursor c0, c2, c4;
             c0.init(grp, A.kb);
             c2 = c0;
             c2.advance2(A.kb);
             c4 = c2;
             c4.advance2(A.kb);
-            uint2 k0 = make_uint2(0u, 0u), k2 = k0, k4 = k0;
-            if (grp < total_it) k0 = Producer<Q_PQ>::load_codes(A, row_of(c0.t), c0.kb);
-            if (grp + 2 < total_it) k2 = Producer<Q_PQ>::load_codes(A, row_of(c2.t), c2.kb);
+            PQCodes k0 = PQProducer::zero(), k2 = k0, k4 = k0;
+            if (grp < total_it) k0 = PQProducer::load_codes(A, row_of(c0.t), c0.kb);
+            if (grp + 2 < total_it) k2 = PQProducer::load_codes(A, row_of(c2.t), c2.kb);
             const uint32_t slice = s_base + OFF_SLICE + (uint32_t)grp * SLICE_BYTES;
             for (int it = grp; it < total_it; it += 2) {
-                if (it + 4 < total_it) k4 = Producer<Q_PQ>::load_codes(A, row_of(c4.t), c4.kb);
+                if (it + 4 < total_it) k4 = PQProducer::load_codes(A, row_of(c4.t), c4.kb);
                 mbar_wait(sfull_bar(grp), (uint32_t)(it >> 1) & 1);
                 cur.gather_smem(A, k0, c0.kb, slice);
                 __syncwarp();
@@ -2092,6 +2129,14 @@ static bool i8_on() {
 }
 void set_i8(bool on) { g_i8.store(on ? 1 : 0); }
 bool i8_state() { return i8_on() && use_pair(); }
+static bool pq_i8_off() {   // VECGO_QTC_PQ_I8=0 keeps PQ on the fp16 kernel (A/B measurements)
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("VECGO_QTC_PQ_I8");
+        v = (e && e[0] == '0') ? 1 : 0;
+    }
+    return v != 0;
+}
 static int candidates_i8(int64_t k) {
     static int tenths = -1;   // candidate groups per k, in tenths (VECGO_QTC_I8_KC, tuning / measurement)
     if (tenths < 0) {
@@ -2103,8 +2148,9 @@ static int candidates_i8(int64_t k) {
 }
 static bool use_i8(const CodecParams &cp, int64_t rows, int64_t k) {
     const int qc = q_codec(cp);
-    if (!i8_on() || !use_pair() || (qc != Q_SQ8 && qc != Q_INT4)) return false;
+    if (!i8_on() || !use_pair() || (qc != Q_SQ8 && qc != Q_INT4 && qc != Q_PQ)) return false;
     if (cp.dim % 128 != 0) return false;                                              // 128-byte k-blocks
+    if (qc == Q_PQ && (cp.pq_dsub != 8 || cp.pq_k != 256 || pq_i8_off())) return false;   // 16 whole subspaces per k-block
     if (qc == Q_SQ8 && (cp.dim > 1024 || cp.row_bytes != cp.dim)) return false;      // resident query tile <= 128 KB, TMA row stride % 16
     if (qc == Q_INT4 && cp.row_bytes != cp.dim / 2) return false;
     const int kc = candidates_i8(k);
@@ -2213,7 +2259,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     } else if (i8)
         prep_queries_i8_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(),
                                                                                  pp.wq.as<float>(), pp.midp.as<float>(), a16.as<int8_t>(), fq.as<float>(),
-                                                                                 cq.as<float>(), eab.as<float>(), 128.0f);
+                                                                                 cq.as<float>(), eab.as<float>(), qc == Q_PQ ? 0.0f : 128.0f);
     else
         prep_queries_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(io.d_queries, nq, q_stride, pp.dimp, pp.perm.as<int32_t>(), pp.wq.as<float>(),
                                                                               pp.midp.as<float>(), a16.as<__half>(), fq.as<float>(), cq.as<float>());
@@ -2291,7 +2337,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         else if (qc == Q_INT4) VG_TRY(launch_thresh<Q_INT4>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st, ea_p));
         else if (qc == Q_RABITQ) VG_TRY(launch_thresh<Q_RABITQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
         else if (qc == Q_BQ) VG_TRY(launch_thresh<Q_BQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
-        else VG_TRY(launch_thresh<Q_PQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st));
+        else VG_TRY(launch_thresh<Q_PQ>(d_kth, qn_p, cq_p, xm, pp.mid_norm, (int)cp.dim, nq, Ts.as<float>(), st, ea_p));
         a.mins = nullptr;
         a.Ts = Ts.as<float>();
         a.cand = cand.as<uint2>();
@@ -2300,6 +2346,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
         a.cap = (int)cap;
         a.slots = slots;
         if (i8 && qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4I, true>(mq, a, qtiles, (int)splits, st)));
+        else if (i8 && qc == Q_PQ) VG_TRY((launch_gemm_pair<Q_PQI, true>(mq, a, qtiles, (int)splits, st)));
         else if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I, true>(mq, a, qtiles, (int)splits, st, &mx)));
         else if (qc == Q_SQ8) VG_TRY((launch_gemm_pair<Q_SQ8, true>(mq, a, qtiles, (int)splits, st)));
         else if (qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4, true>(mq, a, qtiles, (int)splits, st)));
@@ -2338,6 +2385,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     }
     if (pair_mode) {
         if (i8 && qc == Q_INT4) VG_TRY((launch_gemm_pair<Q_INT4I>(mq, a, qtiles, (int)splits, st)));
+        else if (i8 && qc == Q_PQ) VG_TRY((launch_gemm_pair<Q_PQI>(mq, a, qtiles, (int)splits, st)));
         else if (i8) VG_TRY((launch_gemm_pair<Q_SQ8I>(mq, a, qtiles, (int)splits, st, &mx)));
         else if (qc == Q_SQ8) VG_TRY(launch_gemm_pair<Q_SQ8>(mq, a, qtiles, (int)splits, st));
         else if (qc == Q_INT4) VG_TRY(launch_gemm_pair<Q_INT4>(mq, a, qtiles, (int)splits, st));
