@@ -809,11 +809,13 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
     if rank == 0:
         alg_bytes = float(nq) * nloc * code_bytes  # one (query,row) pair = the row's code bytes
         hbm_equiv = alg_bytes / (kernel_ms / 1e3) / 1e9
-        traffic = None
+        traffic = traffic_i8 = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get(f"qtc:{workload}:{nloc}x{dim}:q{nq}:k{k}")
+                tj = json.load(f)
+                traffic = tj.get(f"qtc:{workload}:{nloc}x{dim}:q{nq}:k{k}")
+                traffic_i8 = tj.get(f"qtc_i8:{workload}:{nloc}x{dim}:q{nq}:k{k}")
         if gemm_launches > 0:
             # dominant kernel: the decode-GEMM filter.  Algorithmic FLOPs per (query,row) pair = 2*dim; one launch
             # processes every pair of the batch (a 10k-query batch is one launch; longer batches are chunked).
@@ -826,7 +828,7 @@ def run_c2(env, a, workload, rows, nq, k, steps, warmup, headline):
             # so the denominator is twice the MEASURED sustained bf16 rate — stated in peak_source
             peak = env.tf_sustained * (2.0 if i8 else 1.0)
             roofline = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s" if i8 else "TFLOP/s", "frac": ach / peak,
-                        "traffic": None if i8 else traffic,
+                        "traffic": traffic_i8 if i8 else traffic,
                         "kernel": (f"qtc_kernel<{workload.upper()}> (tcgen05.mma cta_group::1 kind::f16, M=128 x N=128)"
                                    if os.environ.get("VECGO_QTC_PAIR", "1")[:1] == "0" else
                                    "qtc2_kernel<SQ8I> (CTA pair, tcgen05.mma cta_group::2 kind::i8, M=256 x N=256: s8 query tile resident in shared "
