@@ -115,3 +115,39 @@ def test_full_size_filter_equals_exact_scan_and_shards_merge(vg, codec, n, dim, 
     all_scores = np.stack([p[1] for p in parts])
     m_rows, m_scores, m_counts = vg.index.topk_merge(all_rows, all_scores, False, k)
     assert np.array_equal(m_rows, rows[:8]) and np.array_equal(bits(m_scores), bits(scores[:8]))
+
+
+@pytest.mark.parametrize("codec,n,dim", [("pq", 25_000_000, 768), ("sq8", 10_000_000, 768), ("rabitq", 12_500_000, 1536)])
+def test_full_size_repeatable_under_load(vg, codec, n, dim):
+    """The same 512-query batch, searched again and again between full 10 000-query batches, must return the same bits
+    every time (and the exact scan's).  Regression test of a timing-dependent hazard the 8-GPU merged-parity check of
+    bench.py found: the kind::i8 PQ producers released a codebook-slice slot right behind their ld.shared gathers, and the
+    next slice (an async-proxy bulk copy) could land while gathers were still in flight — about one batch in fourteen
+    came back with one wrong neighbour, only on a GPU kept busy by large batches."""
+    L = vg._lib
+    dev = torch.device("cuda:0")
+    k = 100
+    ix = build(vg, codec, n, dim)
+    g = torch.Generator(device=dev).manual_seed(5)
+    q = torch.randn((10_000, dim), device=dev, generator=g)
+
+    def run(nq):
+        r = torch.empty((nq, k), dtype=torch.int32, device=dev)
+        s = torch.empty((nq, k), dtype=torch.float32, device=dev)
+        c = torch.empty((nq,), dtype=torch.int32, device=dev)
+        ix.search_dev(q.data_ptr(), nq, k, r.data_ptr(), s.data_ptr(), c.data_ptr())
+        torch.cuda.synchronize()
+        return r, s
+
+    L.call("vg_flat_tc_enable", 0)
+    try:
+        er, es = run(64)
+    finally:
+        L.call("vg_flat_tc_enable", 1)
+    first = run(512)
+    assert torch.equal(first[0][:64], er) and torch.equal(first[1][:64].view(torch.int32), es.view(torch.int32))
+    for _ in range(8):
+        run(10_000)
+        again = run(512)
+        assert torch.equal(again[0], first[0]) and torch.equal(again[1].view(torch.int32), first[1].view(torch.int32))
+    ix.close()

@@ -988,15 +988,19 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
                 if (it + 4 < total_it) k4 = PQProducer::load_codes(A, row_of(c4.t), c4.kb);
                 mbar_wait(sfull_bar(grp), (uint32_t)(it >> 1) & 1);
                 cur.gather_smem(A, k0, c0.kb, slice);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(sempty_bar(grp));  // the slot may take the slice of it + 2
                 const int st = it % NST;
                 const uint32_t ph = (it / NST) & 1;
                 mbar_wait(empty_bar(st), ph ^ 1);
                 cur.convert(A, c0.kb, s_base + st * STAGE2_BYTES + A2_BYTES + r * 128, swz);
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(full_bar(st), 0);
+                // The slot is released only AFTER convert() has consumed the gathered registers: released right behind the
+                // ld.shared instructions, the next slice (an async-proxy bulk copy) could land while gathers were still in
+                // flight — 1 batch in ~14 came back with a wrong neighbour (found by the 8-GPU merged-parity check).
+                if (lane == 0) {
+                    mbar_arrive(sempty_bar(grp));  // the slot may take the slice of it + 2
+                    mbar_arrive_cluster(full_bar(st), 0);
+                }
                 k0 = k2;
                 k2 = k4;
                 c0 = c2;
@@ -1870,8 +1874,25 @@ static std::atomic<int> g_prof{0};
 static std::mutex g_prof_mu;
 static double g_gemm_ms = 0.0;
 static uint64_t g_gemm_launches = 0;
+// event pairs recorded around GEMM launches and not read yet: the search call does NOT wait for them (a synchronisation per
+// launch cost the 8-GPU step 4 %); profile() settles them when the counters are read
+static std::vector<std::pair<cudaEvent_t, cudaEvent_t>> g_prof_pending;
+static void settle_profile_events() {   // g_prof_mu held
+    for (auto &pr : g_prof_pending) {
+        float ms = 0.0f;
+        if (cudaEventSynchronize(pr.second) == cudaSuccess && cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) {
+            g_gemm_ms += ms;
+            g_gemm_launches++;
+        }
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof_pending.clear();
+    cudaGetLastError();
+}
 void profile(int enable, double *gemm_ms, uint64_t *gemm_launches) {
     std::lock_guard<std::mutex> lk(g_prof_mu);
+    settle_profile_events();
     if (gemm_ms) *gemm_ms = g_gemm_ms;
     if (gemm_launches) *gemm_launches = g_gemm_launches;
     if (enable >= 0) {
@@ -2433,15 +2454,9 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     else VG_TRY(launch_exact<Q_PQ>(e, nq, st));
     // the temporaries above go back to the stream-ordered pool (freed in stream order): no synchronisation needed for them
     if (prof) {
-        VG_CUDA(cudaStreamSynchronize(st));
-        float ms = 0.0f;
-        if (cudaEventElapsedTime(&ms, g_ev[0], g_ev[1]) == cudaSuccess) {
-            std::lock_guard<std::mutex> lk(g_prof_mu);
-            g_gemm_ms += ms;
-            g_gemm_launches++;
-        }
-        cudaEventDestroy(g_ev[0]);
-        cudaEventDestroy(g_ev[1]);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof_pending.emplace_back(g_ev[0], g_ev[1]);
+        if (g_prof_pending.size() > 4096) settle_profile_events();   // bounded: a forgotten profile switch must not leak events
     }
     return VG_OK;
 }
