@@ -352,8 +352,8 @@ vg_status vg_flat_tc_candidates(vg_index_t idx, const float *h_queries, int64_t 
 /* Tensor-core filter of the quantized scans (csrc/vg_quant_tc.cu).  vg_index_search / vg_index_search_dev on an
  * SQ8 / INT4 / PQ / OPQ index (L2, no IVF partitions, dim % 64 == 0, k <= 1024, batches of >= 16 queries over >= 8192
  * rows) run simd.Sq8uL2BatchPerDimension / simd.Int4L2DistanceBatch / simd.PqAdcLookup
- * (internal/segment/flat/segment.go:543-552,603-611) as a tcgen05 fp16 GEMM over codes that are decoded inside the
- * kernel; the candidates are re-scored in the reference's exact float32 order and a certificate proves the result
+ * (internal/segment/flat/segment.go:543-552,603-611) as a tcgen05 GEMM over codes that are decoded inside the
+ * kernel — kind::i8 (8-bit integer operands, see vg_quant_tc_i8_enable) where the shape allows, fp16 otherwise; the candidates are re-scored in the reference's exact float32 order and a certificate proves the result
  * equals the exact scan's (queries without a proof are re-run on the exact CUDA-core scan).  Environment
  * VECGO_QUANT_TC=0 (or vg_flat_tc_enable(0)) forces the CUDA-core scan.  Counters: queries that went through the
  * filter and how many of them needed the exact re-run. */
