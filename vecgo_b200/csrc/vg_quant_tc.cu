@@ -126,6 +126,7 @@ struct KArgs {
     const int32_t *tile_list;
     const int32_t *tile_count;
     const float *fq;        // [nq] -2 / query scale
+    const int32_t *asum;    // kind::i8 sign codecs: [nq] sum of the query's +-1 bytes (B holds the bits 0 / 1), else nullptr
     int64_t nq, rows, rows_per_split;
     float half_dim;           // BQ: D / 2 (Hamming = D / 2 - acc / 2)
     int kb;                 // k-blocks = dimp / 64
@@ -289,9 +290,11 @@ struct Producer<Q_RABITQ> {
     }
 };
 
-// The same for kind::i8: 16 stored bytes (128 dims) per k-block -> +1 / -1 as SIGNED bytes in natural dimension order.
-// Four bits n -> four bytes: (n * 0x00204081) & 0x01010101 puts bit i into byte i (the four shifted copies of a 4-bit n
-// do not overlap, so nothing carries), t -> ~(t * 0xFE) maps 1 -> 0x01 and 0 -> 0xFF per byte.
+// The same for kind::i8: 16 stored bytes (128 dims) per k-block -> the bits themselves as UNSIGNED bytes 0 / 1 in natural
+// dimension order.  Four bits n -> four bytes: (n * 0x00204081) & 0x01010101 puts bit i into byte i (the four shifted copies
+// of a 4-bit n do not overlap, so nothing carries).  With a = +-1 on the query side, sum a s_x = 2 sum a bit - sum a: the
+// epilogue forms 2 acc - asum with one IMAD (FMA pipe) — cheaper than mapping the bytes to +-1 here (two more ALU operations
+// per four bits; the decode warps were two thirds of a 70 % busy ALU pipe).
 struct ProducerSignI8 {
     uint4 w;
     __device__ __forceinline__ void fetch(const KArgs &A, int64_t row, int kb) {
@@ -304,7 +307,7 @@ struct ProducerSignI8 {
             const uint32_t v = wv[c >> 1] >> ((c & 1) * 16);
             uint32_t h[4];
 #pragma unroll
-            for (int j = 0; j < 4; j++) h[j] = ~(((((v >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u) * 0xFEu);
+            for (int j = 0; j < 4; j++) h[j] = (((v >> (4 * j)) & 0xFu) * 0x00204081u) & 0x01010101u;
             sts128(dst_row + (uint32_t)((c ^ swz) << 4), h[0], h[1], h[2], h[3]);
         }
     }
@@ -758,10 +761,10 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA only) =====================
         if (leader && lane == 0) {
-            // kind::i8: signed A (query side); B = unsigned code bytes / nibbles (SQ8I, INT4I) or signed +-1 bytes (sign codecs: b_format bit 10)
-            constexpr uint32_t idesc = (CODEC == Q_SQ8I || CODEC == Q_INT4I) ? make_idesc_i8_pair()   // others: signed B (sign bytes, int8 centroids)
-                                       : i8_codec(CODEC)                    ? (make_idesc_i8_pair() | (1u << 10))
-                                                                            : make_idesc_f16_pair();
+            // kind::i8: signed A (query side); B = unsigned code bytes / nibbles / sign bits, or the signed int8 centroids (PQI: b_format bit 10)
+            constexpr uint32_t idesc = CODEC == Q_PQI    ? (make_idesc_i8_pair() | (1u << 10))   // signed B: the int8 centroids
+                                       : i8_codec(CODEC) ? make_idesc_i8_pair()                 // unsigned B: code bytes, nibbles, sign bits
+                                                         : make_idesc_f16_pair();
             int it = 0;
             if (res_a) {
                 if (ntiles > 0) {
@@ -825,6 +828,7 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
         float *xs = reinterpret_cast<float *>(smem + OFF_XN);
         const float BIG = 3.0e38f;
         const float fq = q < A.nq ? __ldg(A.fq + q) : 0.0f;
+        const int nasum = ((CODEC == Q_RABITQI || CODEC == Q_BQI) && q < A.nq) ? -__ldg(A.asum + q) : 0;
         const uint32_t keep_hi = A.keep_hi;
         float g1 = BIG, g2 = BIG;
         int cc = 0;
@@ -874,7 +878,12 @@ qtc2_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ C
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         // kind::i8 accumulates in int32 (|acc| <= 768 * 127 * 255 < 2^25: the conversion is exact or within 2^-24)
-                        const float accf = i8_codec(CODEC) ? __int2float_rn((int)v[j4 * 4 + i]) : __uint_as_float(v[j4 * 4 + i]);
+                        float accf;
+                        if constexpr (CODEC == Q_RABITQI || CODEC == Q_BQI) {   // sum a s_x = 2 sum a bit - sum a
+                            int t;
+                            asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(t) : "r"((int)v[j4 * 4 + i]), "r"(nasum));
+                            accf = __int2float_rn(t);
+                        } else accf = i8_codec(CODEC) ? __int2float_rn((int)v[j4 * 4 + i]) : __uint_as_float(v[j4 * 4 + i]);
                         const float t = __fmaf_rn(fq, accf, xx[i]);
                         s[j4 * 4 + i] = BASE == Q_RABITQ ? __fmul_rn(t, xx[i]) : t;  // RaBitQ: yn^2 - (2 qn / D) yn acc
                     }
@@ -1238,13 +1247,20 @@ __global__ void __launch_bounds__(256) prep_queries_sign_kernel(const uint32_t *
 }
 // kind::i8 form: sign(q) as +-1 signed bytes in natural dimension order (dim % 128 == 0: no padding), same f_q / c_q
 __global__ void __launch_bounds__(256) prep_queries_sign_i8_kernel(const uint32_t *q_words, const float *q_norms, int64_t nq, int words32, int dim,
-                                                                   int8_t *a8, float *fq, float *cq) {
+                                                                   int8_t *a8, float *fq, float *cq, int32_t *asum) {
     const int64_t q = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
     const uint32_t *qw = q_words + q * words32;
-    for (int d = lane; d < dim; d += 32) a8[q * dim + d] = ((qw[d >> 5] >> (d & 31)) & 1u) ? (int8_t)1 : (int8_t)-1;
+    int sa = 0;
+    for (int d = lane; d < dim; d += 32) {
+        const int v = ((qw[d >> 5] >> (d & 31)) & 1u) ? 1 : -1;
+        a8[q * dim + d] = (int8_t)v;
+        sa += v;
+    }
+    for (int o = 16; o > 0; o >>= 1) sa += __shfl_xor_sync(0xffffffffu, sa, o);
     if (lane == 0) {
+        asum[q] = sa;
         if (q_norms) {
             const float qn = q_norms[q];
             fq[q] = __fdiv_rn(__fmul_rn(-2.0f, qn), (float)dim);
@@ -2262,7 +2278,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     const bool i8s = pair_mode && sign_codec(qc) && i8_on() && cp.dim % 128 == 0 && cp.row_bytes % 16 == 0;   // sign bits as +-1 bytes
     DevBuf a16, fq, cq, qn, mins, gids, gcnt, tau, eab;
     VG_TRY(a16.alloc((size_t)nq * pp.dimp * ((i8 || i8s) ? 1 : 2)));
-    if (i8) VG_TRY(eab.alloc((size_t)nq * 4));
+    if (i8 || i8s) VG_TRY(eab.alloc((size_t)nq * 4));   // i8: certificate term (float); i8s: sum of the query's +-1 bytes (int32)
     const float *ea_p = i8 ? eab.as<float>() : nullptr;
     VG_TRY(fq.alloc((size_t)nq * 4));
     VG_TRY(cq.alloc((size_t)nq * 4));
@@ -2276,7 +2292,8 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     if (i8s) {
         prep_queries_sign_i8_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32,
                                                                                       qc == Q_RABITQ ? cp.q_norms + io.q_index0 : nullptr, nq, cp.words32,
-                                                                                      (int)cp.dim, a16.as<int8_t>(), fq.as<float>(), cq.as<float>());
+                                                                                      (int)cp.dim, a16.as<int8_t>(), fq.as<float>(), cq.as<float>(),
+                                                                                      eab.as<int32_t>());
         VG_LAUNCHED();
     } else if (sign_codec(qc)) {
         prep_queries_sign_kernel<<<(unsigned)((nq * 32 + 255) / 256), 256, 0, st>>>(cp.q_words + io.q_index0 * cp.words32,
@@ -2333,6 +2350,7 @@ static vg_status search_chunk(const CodecParams &cp, const Prepared &pp, const S
     a.half_dim = 0.5f * (float)cp.dim;
     a.mask = reinterpret_cast<const uint32_t *>(io.d_mask);
     a.fq = fq.as<float>();
+    a.asum = i8s ? eab.as<int32_t>() : nullptr;
     a.nq = nq;
     a.rows = rows;
     a.rows_per_split = rps;
