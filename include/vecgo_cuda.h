@@ -230,7 +230,8 @@ vg_status vg_index_upload_dev(vg_index_t idx, int64_t row0, int64_t n, const voi
  * next to the codes in HBM (100M x 1536-d = 614 GB).  The library page-locks and maps the region (or uses it as is when
  * the caller already page-locked it); vg_index_rerank* / vg_index_search_rerank / the shard-group rerank then gather the
  * candidate rows over the host link — same arithmetic and bits as the device-resident Segment.Rerank
- * (flat/segment.go:754-781).  Quantized indexes only; the region must stay valid and unchanged until vg_index_close. */
+ * (flat/segment.go:754-781).  Quantized indexes only; the region must stay valid and unchanged until vg_index_close.
+ * Part of building the handle (like vg_index_upload): call it before the handle is shared with searching threads. */
 vg_status vg_index_set_host_vectors(vg_index_t idx, const float *h_vectors, int64_t rows);
 vg_status vg_index_close(vg_index_t idx);
 vg_status vg_index_info(vg_index_t idx, int64_t *rows, int64_t *dim, int64_t *code_bytes_per_row, int64_t *device_bytes);
